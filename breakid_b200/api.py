@@ -1,0 +1,356 @@
+"""ctypes binding of include/breakid_b200.h (the C ABI of the CUDA library) and of the host BAM
+decoder.  Python here is test / bench plumbing: the product is ``libbreakid_b200.so`` (CUDA) and
+the C++ host driver ``BreakID`` (breakid_b200/host).  There is no CPU fallback: if the CUDA library
+is missing or no device is usable, loading / ``Context()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_CUDA = os.path.join(_HERE, "csrc", "libbreakid_b200.so")
+LIB_HOST = os.path.join(_HERE, "host", "libbreakid_host.so")
+
+
+class Header(C.Structure):
+    _fields_ = [("n_targets", C.c_int32), ("target_len", C.POINTER(C.c_uint32)),
+                ("target_name", C.POINTER(C.c_char_p))]
+
+
+class Params(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("qual", "times", "fast", "min_reads", "bp_pos_error",
+                                         "mismatch_num", "sd_mult", "reserved")]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n", C.c_int64), ("flag", C.c_void_p), ("mapq", C.c_void_p),
+                ("tid", C.c_void_p), ("pos", C.c_void_p), ("mtid", C.c_void_p), ("mpos", C.c_void_p),
+                ("isize", C.c_void_p), ("endpos", C.c_void_p), ("name_hash", C.c_void_p),
+                ("n_sa", C.c_int64), ("sa_rec", C.c_void_p), ("cig_off", C.c_void_p), ("cig_ops", C.c_void_p),
+                ("sa_off", C.c_void_p), ("sa_txt", C.c_void_p), ("oc_off", C.c_void_p), ("oc_txt", C.c_void_p)]
+
+
+PAIR_DTYPE = np.dtype([
+    ("name_lo", "<u8"), ("name_hi", "<u8"), ("p1_tid", "<i4"), ("p2_tid", "<i4"),
+    ("p1_pos", "<u4"), ("p2_pos", "<u4"), ("p1_chr_pos", "<u4"), ("p2_chr_pos", "<u4"),
+    ("p1_flag", "<u2"), ("p2_flag", "<u2"), ("p1_mapq", "u1"), ("p2_mapq", "u1"),
+    ("p1_strand", "u1"), ("p2_strand", "u1"), ("bucket", "<i4"), ("cluster", "<i4"),
+    ("orig", "<u4"), ("_pad", "<u4")])
+assert PAIR_DTYPE.itemsize == 64
+
+CLUSTER_DTYPE = np.dtype([
+    ("bucket", "<i4"), ("id", "<i4"), ("p1_tid", "<i4"), ("p2_tid", "<i4"),
+    ("p1_mean_pos", "<u8"), ("p2_mean_pos", "<u8"),
+    ("p1_min_pos", "<u4"), ("p1_max_pos", "<u4"), ("p2_min_pos", "<u4"), ("p2_max_pos", "<u4"),
+    ("p1_exact_pos", "<u4"), ("p2_exact_pos", "<i4"),
+    ("n_split_read", "<i8"), ("n_discordant_pair", "<i8"),
+    ("p1_bp_depth", "<f8"), ("p2_bp_depth", "<f8"), ("p1_alle_freq", "<f4"), ("p2_alle_freq", "<f4"),
+    ("fusion_type", "<i4"), ("is_rpt", "<i4"), ("p1_rpt", "S44"), ("p2_rpt", "S44")])
+assert CLUSTER_DTYPE.itemsize == 192
+
+EVIDENCE_DTYPE = np.dtype([
+    ("name_lo", "<u8"), ("name_hi", "<u8"), ("primary_chr", "<i4"), ("secondary_chr", "<i4"),
+    ("primary_start", "<u4"), ("secondary_start", "<u4"), ("primary_end", "<u4"), ("secondary_end", "<u4"),
+    ("primary_bp", "<u4"), ("secondary_bp", "<u4"), ("primary_cigar_h", "<u8"), ("secondary_cigar_h", "<u8"),
+    ("flag", "<u2"), ("secondary", "u1"), ("_pad", "u1", 5)])
+assert EVIDENCE_DTYPE.itemsize == 72
+
+TIMING_FIELDS_F = ("h2d", "insert_stats", "classify", "join", "bucket_sort", "mask", "cluster", "summarize",
+                   "evidence", "refine", "total")
+TIMING_FIELDS_I = ("n_records", "n_candidates", "n_pairs", "n_masked", "n_clustered", "n_clusters", "n_sa",
+                   "n_evidence", "n_called", "kernel_launches")
+
+
+class Timings(C.Structure):
+    _fields_ = [(k, C.c_float) for k in TIMING_FIELDS_F] + [("_pad", C.c_float)] + \
+               [(k, C.c_int64) for k in TIMING_FIELDS_I]
+
+
+FUSION_TYPES = ["Unknown", "Translocation", "Inversion", "Duplication", "Deletion"]
+
+_COLS = (("flag", np.uint16), ("mapq", np.uint8), ("tid", np.int32), ("pos", np.int32), ("mtid", np.int32),
+         ("mpos", np.int32), ("isize", np.int32), ("endpos", np.int32))
+_SIDE = (("sa_rec", np.uint32), ("cig_off", np.uint32), ("cig_ops", np.uint32), ("sa_off", np.uint32),
+         ("sa_txt", np.uint8), ("oc_off", np.uint32), ("oc_txt", np.uint8))
+
+
+class HostBatch:
+    """numpy-backed record batch + header; owns the arrays a ``Batch`` struct points to."""
+
+    def __init__(self, cols: Dict[str, np.ndarray], name_hash: np.ndarray, side: Dict[str, np.ndarray],
+                 target_len: Sequence[int], target_names: Sequence[str]):
+        self.cols = {k: np.ascontiguousarray(cols[k], dtype=dt) for k, dt in _COLS}
+        self.name_hash = np.ascontiguousarray(name_hash, dtype=np.uint64).reshape(-1)
+        self.n = int(self.cols["flag"].shape[0])
+        assert self.name_hash.shape[0] == 2 * self.n
+        n_sa = int(side["sa_rec"].shape[0]) if "sa_rec" in side else 0
+        side = dict(side)
+        if "oc_off" not in side:
+            side["oc_off"] = np.zeros(n_sa + 1, np.uint32)
+            side["oc_txt"] = np.zeros(0, np.uint8)
+        self.side = {k: np.ascontiguousarray(side[k], dtype=dt) for k, dt in _SIDE}
+        self.n_sa = n_sa
+        self.target_len = np.ascontiguousarray(target_len, dtype=np.uint32)
+        self.target_names = [str(x) for x in target_names]
+
+    # -- views -----------------------------------------------------------------------------
+    def struct(self) -> Batch:
+        b = Batch()
+        b.n = self.n
+        for k, _ in _COLS:
+            setattr(b, k, self.cols[k].ctypes.data)
+        b.name_hash = self.name_hash.ctypes.data
+        b.n_sa = self.n_sa
+        for k, _ in _SIDE:
+            setattr(b, k, self.side[k].ctypes.data)
+        return b
+
+    def header(self) -> Header:
+        h = Header()
+        h.n_targets = len(self.target_names)
+        h.target_len = self.target_len.ctypes.data_as(C.POINTER(C.c_uint32))
+        self._name_arr = (C.c_char_p * len(self.target_names))(*[s.encode() for s in self.target_names])
+        h.target_name = C.cast(self._name_arr, C.POINTER(C.c_char_p))
+        return h
+
+    def nbytes(self) -> int:
+        return sum(a.nbytes for a in self.cols.values()) + self.name_hash.nbytes + sum(a.nbytes for a in self.side.values())
+
+    # -- constructors ----------------------------------------------------------------------
+    @staticmethod
+    def from_synth(d) -> "HostBatch":
+        from . import synth
+        cols = {k: d.cols[k].cpu().numpy() for k, _ in _COLS if k != "flag"}
+        cols["flag"] = d.cols["flag"].cpu().numpy().view(np.uint16)
+        nh = synth.name_hash_ids(d.cols["name_id"]).cpu().numpy().view(np.uint64).reshape(-1)
+        side = {"sa_rec": d.sa_rec.cpu().numpy(), "cig_off": d.cig_off.cpu().numpy(),
+                "cig_ops": d.cig_ops.cpu().numpy(), "sa_off": d.sa_off.cpu().numpy(),
+                "sa_txt": d.sa_txt.cpu().numpy()}
+        names = [synth.chrom_name(t) for t in range(len(d.cfg.chrom_lens))]
+        return HostBatch(cols, nh, side, d.cfg.chrom_lens, names)
+
+    @staticmethod
+    def from_bam(path: str, threads: int = 8) -> "HostBatch":
+        lib = host_lib()
+        err = C.create_string_buffer(256)
+        h = lib.bkid_host_read_bam(path.encode(), threads, err, 256)
+        if not h:
+            raise IOError("bkid_host_read_bam: " + err.value.decode())
+        try:
+            b = C.cast(lib.bkid_host_bam_batch(h), C.POINTER(Batch)).contents
+            hd = C.cast(lib.bkid_host_bam_header(h), C.POINTER(Header)).contents
+            n, n_sa = int(b.n), int(b.n_sa)
+
+            def arr(ptr, count, dt):
+                if count == 0:
+                    return np.zeros(0, dt)
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (count * np.dtype(dt).itemsize,)).view(dt).copy()
+
+            cols = {k: arr(getattr(b, k), n, dt) for k, dt in _COLS}
+            nh = arr(b.name_hash, 2 * n, np.uint64)
+            cig_off = arr(b.cig_off, n_sa + 1, np.uint32)
+            sa_off = arr(b.sa_off, n_sa + 1, np.uint32)
+            oc_off = arr(b.oc_off, n_sa + 1, np.uint32)
+            side = {"sa_rec": arr(b.sa_rec, n_sa, np.uint32), "cig_off": cig_off,
+                    "cig_ops": arr(b.cig_ops, int(cig_off[-1]), np.uint32), "sa_off": sa_off,
+                    "sa_txt": arr(b.sa_txt, int(sa_off[-1]), np.uint8), "oc_off": oc_off,
+                    "oc_txt": arr(b.oc_txt, int(oc_off[-1]), np.uint8)}
+            tl = [int(hd.target_len[i]) for i in range(hd.n_targets)]
+            names = [hd.target_name[i].decode() for i in range(hd.n_targets)]
+        finally:
+            lib.bkid_host_bam_free(h)
+        return HostBatch(cols, nh, side, tl, names)
+
+
+_host = None
+_cuda = None
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        if not os.path.exists(LIB_HOST):
+            raise RuntimeError("host library missing: %s (run __graft_entry__.build())" % LIB_HOST)
+        L = C.CDLL(LIB_HOST)
+        L.bkid_host_read_bam.restype = C.c_void_p
+        L.bkid_host_read_bam.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.bkid_host_bam_header.restype = C.c_void_p
+        L.bkid_host_bam_header.argtypes = [C.c_void_p]
+        L.bkid_host_bam_batch.restype = C.c_void_p
+        L.bkid_host_bam_batch.argtypes = [C.c_void_p]
+        L.bkid_host_bam_free.argtypes = [C.c_void_p]
+        _host = L
+    return _host
+
+
+EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_create", "bkid_destroy",
+           "bkid_reserve", "bkid_push_batch", "bkid_push_batch_device", "bkid_reset", "bkid_insert_stats",
+           "bkid_scan", "bkid_cluster", "bkid_set_nib", "bkid_refine", "bkid_run", "bkid_fetch_clusters",
+           "bkid_fetch_pairs", "bkid_fetch_class", "bkid_get_timings", "bkid_op_sort_perm",
+           "bkid_op_remove_isolated", "bkid_op_cluster"]
+
+
+def cuda_lib():
+    """Load libbreakid_b200.so.  Raises (never falls back) when it has not been built."""
+    global _cuda
+    if _cuda is None:
+        if not os.path.exists(LIB_CUDA):
+            raise RuntimeError("CUDA library missing: %s (run __graft_entry__.build()); there is no CPU fallback" % LIB_CUDA)
+        L = C.CDLL(LIB_CUDA)
+        vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
+        dp = C.POINTER(C.c_double)
+        L.bkid_abi_version.restype = C.c_int
+        L.bkid_last_error.restype = C.c_char_p
+        L.bkid_last_error.argtypes = [vp]
+        L.bkid_default_params.argtypes = [C.POINTER(Params)]
+        L.bkid_create.restype = vp
+        L.bkid_create.argtypes = [C.c_int, C.POINTER(Header), C.POINTER(Params)]
+        L.bkid_destroy.argtypes = [vp]
+        L.bkid_reserve.argtypes = [vp] + [C.c_int64] * 5
+        L.bkid_push_batch.argtypes = [vp, C.POINTER(Batch)]
+        L.bkid_push_batch_device.argtypes = [vp, C.POINTER(Batch)]
+        L.bkid_reset.argtypes = [vp]
+        L.bkid_insert_stats.argtypes = [vp, dp, dp]
+        L.bkid_scan.argtypes = [vp, C.c_double, i64p]
+        L.bkid_cluster.argtypes = [vp, C.c_double, C.c_int, i64p]
+        L.bkid_set_nib.argtypes = [vp, C.c_int32, vp, C.c_uint64]
+        L.bkid_refine.argtypes = [vp, C.c_double, i64p]
+        L.bkid_run.argtypes = [vp, dp, dp, dp, i64p]
+        L.bkid_fetch_clusters.argtypes = [vp, vp, C.c_int64, i64p]
+        L.bkid_fetch_pairs.argtypes = [vp, C.c_int, vp, C.c_int64, i64p]
+        L.bkid_fetch_class.argtypes = [vp, vp, C.c_int64]
+        L.bkid_get_timings.argtypes = [vp, C.POINTER(Timings)]
+        L.bkid_op_sort_perm.argtypes = [vp, C.c_int64, vp, vp]
+        L.bkid_op_remove_isolated.argtypes = [vp, C.c_int64, vp, vp, C.c_double, vp, i64p]
+        L.bkid_op_cluster.argtypes = [vp, C.c_int, C.c_int64, vp, vp, C.c_double, vp, vp, i64p, C.POINTER(C.c_int32)]
+        _cuda = L
+    return _cuda
+
+
+class BkidError(RuntimeError):
+    pass
+
+
+class Context:
+    """One device context (``bkid_ctx``)."""
+
+    def __init__(self, target_len: Sequence[int], target_names: Sequence[str], device: int = 0, **params):
+        self.lib = cuda_lib()
+        self._tl = np.ascontiguousarray(target_len, dtype=np.uint32)
+        self._names = (C.c_char_p * len(target_names))(*[s.encode() for s in target_names])
+        h = Header(len(target_names), self._tl.ctypes.data_as(C.POINTER(C.c_uint32)), C.cast(self._names, C.POINTER(C.c_char_p)))
+        p = Params()
+        self.lib.bkid_default_params(C.byref(p))
+        for k, v in params.items():
+            setattr(p, k, int(v))
+        self.params = p
+        self.ctx = self.lib.bkid_create(device, C.byref(h), C.byref(p))
+        if not self.ctx:
+            raise BkidError("bkid_create failed: " + (self.lib.bkid_last_error(None) or b"?").decode())
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise BkidError("bkid error %d: %s" % (rc, (self.lib.bkid_last_error(self.ctx) or b"").decode()))
+
+    def close(self):
+        if self.ctx:
+            self.lib.bkid_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reserve(self, n, n_sa=0, n_cig=0, sa_bytes=0, oc_bytes=0):
+        self._chk(self.lib.bkid_reserve(self.ctx, n, n_sa, n_cig, sa_bytes, oc_bytes))
+
+    def push(self, hb: HostBatch):
+        b = hb.struct()
+        self._chk(self.lib.bkid_push_batch(self.ctx, C.byref(b)))
+
+    def push_device(self, b: Batch):
+        self._chk(self.lib.bkid_push_batch_device(self.ctx, C.byref(b)))
+
+    def reset(self):
+        self._chk(self.lib.bkid_reset(self.ctx))
+
+    def insert_stats(self):
+        m, s = C.c_double(), C.c_double()
+        self._chk(self.lib.bkid_insert_stats(self.ctx, C.byref(m), C.byref(s)))
+        return m.value, s.value
+
+    def scan(self, w: float) -> int:
+        n = C.c_int64()
+        self._chk(self.lib.bkid_scan(self.ctx, w, C.byref(n)))
+        return n.value
+
+    def cluster(self, dist: float, mode: int = 0) -> int:
+        n = C.c_int64()
+        self._chk(self.lib.bkid_cluster(self.ctx, dist, mode, C.byref(n)))
+        return n.value
+
+    def set_nib(self, tid: int, packed: np.ndarray, n_bases: int):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        self._chk(self.lib.bkid_set_nib(self.ctx, tid, packed.ctypes.data, n_bases))
+
+    def refine(self, dist: float) -> int:
+        n = C.c_int64()
+        self._chk(self.lib.bkid_refine(self.ctx, dist, C.byref(n)))
+        return n.value
+
+    def run(self):
+        m, s, d, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        self._chk(self.lib.bkid_run(self.ctx, C.byref(m), C.byref(s), C.byref(d), C.byref(n)))
+        return m.value, s.value, d.value, n.value
+
+    def fetch_clusters(self) -> np.ndarray:
+        n = C.c_int64()
+        self._chk(self.lib.bkid_fetch_clusters(self.ctx, None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), CLUSTER_DTYPE)
+        self._chk(self.lib.bkid_fetch_clusters(self.ctx, out.ctypes.data, out.shape[0], C.byref(n)))
+        return out[:n.value]
+
+    def fetch_pairs(self, stage: int) -> np.ndarray:
+        n = C.c_int64()
+        self._chk(self.lib.bkid_fetch_pairs(self.ctx, stage, None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), PAIR_DTYPE)
+        self._chk(self.lib.bkid_fetch_pairs(self.ctx, stage, out.ctypes.data, out.shape[0], C.byref(n)))
+        return out[:n.value]
+
+    def fetch_class(self, n: int) -> np.ndarray:
+        out = np.zeros(n, np.uint8)
+        self._chk(self.lib.bkid_fetch_class(self.ctx, out.ctypes.data, n))
+        return out
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._chk(self.lib.bkid_get_timings(self.ctx, C.byref(t)))
+        return {k: getattr(t, k) for k in TIMING_FIELDS_F + TIMING_FIELDS_I}
+
+    # stand-alone operators
+    def op_sort_perm(self, key: np.ndarray) -> np.ndarray:
+        key = np.ascontiguousarray(key, np.uint32)
+        perm = np.zeros(key.shape[0], np.uint32)
+        self._chk(self.lib.bkid_op_sort_perm(self.ctx, key.shape[0], key.ctypes.data, perm.ctypes.data))
+        return perm
+
+    def op_remove_isolated(self, p1, p2, w):
+        p1 = np.ascontiguousarray(p1, np.uint32); p2 = np.ascontiguousarray(p2, np.uint32)
+        out = np.zeros(p1.shape[0] + 2, np.uint32)
+        n = C.c_int64()
+        self._chk(self.lib.bkid_op_remove_isolated(self.ctx, p1.shape[0], p1.ctypes.data, p2.ctypes.data, w, out.ctypes.data, C.byref(n)))
+        return out[:n.value]
+
+    def op_cluster(self, mode, p1, p2, thr):
+        p1 = np.ascontiguousarray(p1, np.uint32); p2 = np.ascontiguousarray(p2, np.uint32)
+        oi = np.zeros(p1.shape[0] + 2, np.uint32); oc = np.zeros(p1.shape[0] + 2, np.int32)
+        n = C.c_int64(); r = C.c_int32()
+        self._chk(self.lib.bkid_op_cluster(self.ctx, mode, p1.shape[0], p1.ctypes.data, p2.ctypes.data, thr,
+                                           oi.ctypes.data, oc.ctypes.data, C.byref(n), C.byref(r)))
+        return oi[:n.value], oc[:n.value], r.value

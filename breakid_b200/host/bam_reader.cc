@@ -1,0 +1,265 @@
+// bam_reader.cc -- host-side BAM decode into the struct-of-arrays batch of include/breakid_b200.h.
+//
+// Role in the reference: htslib's bgzf inflate + bam_read1 (thirdparty/.../htslib-1.3.1/sam.c:407-441)
+// driven by the samread / sam_read1 loops of src/BreakID.cc:1414,1929.  BASELINE.json keeps decode on
+// the host; this is a from-scratch multi-threaded BGZF/BAM reader (zlib only) that extracts exactly
+// the columns the hot path consumes: the bam1_core_t fields, bam_endpos (sam.c:344-350), a 128-bit
+// read-name hash, and for SA-tagged records the raw cigar ops and SA / OC tag text.
+//
+// BGZF blocks are located by walking the BSIZE fields, inflated in parallel, and record boundaries
+// are then walked once; column extraction is parallel over records.
+#include "bam_reader.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Block { size_t coff; uint32_t csize, usize; size_t uoff; };
+
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+bool inflate_block(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usize)
+{
+  // BGZF: 12-byte gzip header + XLEN extra, deflate payload, CRC32, ISIZE
+  uint16_t xlen = rd16(src + 10);
+  const uint8_t *payload = src + 12 + xlen;
+  uint32_t plen = csize - 12 - xlen - 8;
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, -15) != Z_OK) return false;
+  zs.next_in = const_cast<uint8_t *>(payload); zs.avail_in = plen;
+  zs.next_out = dst; zs.avail_out = usize;
+  int r = inflate(&zs, Z_FINISH);
+  inflateEnd(&zs);
+  return r == Z_STREAM_END && zs.total_out == usize;
+}
+
+template <class F>
+void parallel_for(int threads, size_t n, F f)
+{
+  if (threads <= 1 || n < 2) { f(0, n); return; }
+  std::vector<std::thread> th;
+  size_t chunk = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    size_t b = t * chunk, e = b + chunk < n ? b + chunk : n;
+    if (b >= e) break;
+    th.emplace_back([=] { f(b, e); });
+  }
+  for (auto &x : th) x.join();
+}
+
+}  // namespace
+
+struct bkid_host_bam {
+  std::vector<uint32_t> target_len;
+  std::vector<std::string> names;
+  std::vector<const char *> name_ptrs;
+  bkid_header hdr;
+  std::vector<uint16_t> flag;
+  std::vector<uint8_t> mapq;
+  std::vector<int32_t> tid, pos, mtid, mpos, isize, endpos;
+  std::vector<uint64_t> name_hash;
+  std::vector<uint32_t> sa_rec, cig_off, cig_ops, sa_off, oc_off;
+  std::vector<uint8_t> sa_txt, oc_txt;
+  int32_t first_l_qseq = 0;
+  bkid_batch batch;
+  double t_inflate = 0, t_parse = 0;
+};
+
+static void set_err(char *err, int errlen, const std::string &s)
+{
+  if (err && errlen > 0) { snprintf(err, errlen, "%s", s.c_str()); }
+}
+
+extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char *err, int errlen)
+{
+  if (threads < 1) threads = 1;
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_err(err, errlen, std::string("cannot open ") + path); return nullptr; }
+  struct stat st;
+  fstat(fd, &st);
+  size_t fsz = (size_t)st.st_size;
+  const uint8_t *file = (const uint8_t *)mmap(nullptr, fsz, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (file == MAP_FAILED) { set_err(err, errlen, "mmap failed"); return nullptr; }
+
+  // 1. locate BGZF blocks
+  std::vector<Block> blocks;
+  size_t off = 0, utotal = 0;
+  while (off + 18 <= fsz) {
+    const uint8_t *p = file + off;
+    if (p[0] != 0x1f || p[1] != 0x8b) { munmap((void *)file, fsz); set_err(err, errlen, "not a BGZF file"); return nullptr; }
+    uint16_t xlen = rd16(p + 10);
+    uint32_t bsize = 0;
+    for (uint32_t x = 0; x + 4 <= xlen;) {        // find the BC subfield
+      const uint8_t *q = p + 12 + x;
+      uint16_t slen = rd16(q + 2);
+      if (q[0] == 'B' && q[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(q + 4) + 1;
+      x += 4 + slen;
+    }
+    if (!bsize || off + bsize > fsz) { munmap((void *)file, fsz); set_err(err, errlen, "corrupt BGZF block"); return nullptr; }
+    uint32_t usize = rd32(p + bsize - 4);
+    blocks.push_back(Block{off, bsize, usize, utotal});
+    utotal += usize;
+    off += bsize;
+  }
+  // 2. inflate in parallel
+  std::vector<uint8_t> u(utotal + 8);
+  std::atomic<bool> ok{true};
+  std::atomic<size_t> next{0};
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t)
+      th.emplace_back([&] {
+        for (;;) {
+          size_t i = next.fetch_add(16);
+          if (i >= blocks.size()) break;
+          size_t e = i + 16 < blocks.size() ? i + 16 : blocks.size();
+          for (; i < e; ++i) {
+            const Block &b = blocks[i];
+            if (b.usize && !inflate_block(file + b.coff, b.csize, u.data() + b.uoff, b.usize)) ok = false;
+          }
+        }
+      });
+    for (auto &x : th) x.join();
+  }
+  munmap((void *)file, fsz);
+  if (!ok) { set_err(err, errlen, "inflate failed"); return nullptr; }
+
+  // 3. header
+  bkid_host_bam *h = new bkid_host_bam();
+  const uint8_t *p = u.data();
+  if (utotal < 12 || memcmp(p, "BAM\1", 4) != 0) { delete h; set_err(err, errlen, "not a BAM file"); return nullptr; }
+  size_t o = 4;
+  uint32_t l_text = rd32(p + o); o += 4 + l_text;
+  uint32_t n_ref = rd32(p + o); o += 4;
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    uint32_t l_name = rd32(p + o); o += 4;
+    h->names.emplace_back((const char *)(p + o)); o += l_name;
+    h->target_len.push_back(rd32(p + o)); o += 4;
+  }
+  // 4. record boundaries
+  std::vector<size_t> rec;
+  while (o + 4 <= utotal) {
+    uint32_t bs = rd32(p + o);
+    if (o + 4 + bs > utotal) { delete h; set_err(err, errlen, "truncated BAM record"); return nullptr; }
+    rec.push_back(o);
+    o += 4 + bs;
+  }
+  size_t n = rec.size();
+  h->flag.resize(n); h->mapq.resize(n);
+  h->tid.resize(n); h->pos.resize(n); h->mtid.resize(n); h->mpos.resize(n); h->isize.resize(n); h->endpos.resize(n);
+  h->name_hash.resize(2 * n);
+  // 5. columns (parallel) + per-thread SA side tables (merged in order afterwards)
+  struct Side { std::vector<uint32_t> rec, ncig, cig, salen, oclen; std::vector<uint8_t> sa, oc; };
+  int T = threads;
+  std::vector<Side> sides(T);
+  size_t chunk = (n + T - 1) / (T ? T : 1);
+  parallel_for(T, (size_t)T, [&](size_t tb, size_t te) {
+    for (size_t t = tb; t < te; ++t) {
+      Side &S = sides[t];
+      size_t b = t * chunk, e = b + chunk < n ? b + chunk : n;
+      for (size_t i = b; i < e; ++i) {
+        const uint8_t *r = p + rec[i];
+        uint32_t bs = rd32(r);
+        int32_t tid = (int32_t)rd32(r + 4), pos = (int32_t)rd32(r + 8);
+        uint8_t l_name = r[12], mq = r[13];
+        uint16_t n_cig = rd16(r + 16), fl = rd16(r + 18);
+        int32_t l_seq = (int32_t)rd32(r + 20);
+        h->tid[i] = tid; h->pos[i] = pos; h->mapq[i] = mq; h->flag[i] = fl;
+        h->mtid[i] = (int32_t)rd32(r + 24); h->mpos[i] = (int32_t)rd32(r + 28); h->isize[i] = (int32_t)rd32(r + 32);
+        const char *qn = (const char *)(r + 36);
+        bkid_name_hash(qn, &h->name_hash[2 * i], &h->name_hash[2 * i + 1]);
+        const uint8_t *cg = r + 36 + l_name;
+        int32_t rlen = 0;
+        for (uint32_t k = 0; k < n_cig; ++k) {
+          uint32_t c = rd32(cg + 4 * k), op = c & 0xf;
+          if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += (int32_t)(c >> 4);
+        }
+        h->endpos[i] = (!(fl & 0x4) && n_cig > 0) ? pos + rlen : pos + 1;   // bam_endpos, sam.c:344-350
+        // aux scan for SA:Z / OC:Z (first occurrence, like bam_aux_get)
+        const uint8_t *a = cg + 4 * (size_t)n_cig + (size_t)((l_seq + 1) / 2) + (size_t)l_seq;
+        const uint8_t *end = r + 4 + bs;
+        const uint8_t *sa = nullptr, *oc = nullptr;
+        while (a + 3 <= end) {
+          uint8_t t0 = a[0], t1 = a[1], ty = a[2];
+          const uint8_t *v = a + 3;
+          size_t len;
+          switch (ty) {
+            case 'A': case 'c': case 'C': len = 1; break;
+            case 's': case 'S': len = 2; break;
+            case 'i': case 'I': case 'f': len = 4; break;
+            case 'd': len = 8; break;
+            case 'Z': case 'H': len = strnlen((const char *)v, end - v) + 1; break;
+            case 'B': {
+              uint8_t st = v[0]; uint32_t cnt = rd32(v + 1);
+              size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+              len = 5 + es * cnt; break;
+            }
+            default: len = (size_t)(end - v); break;
+          }
+          if (ty == 'Z') {
+            if (t0 == 'S' && t1 == 'A' && !sa) sa = v;
+            if (t0 == 'O' && t1 == 'C' && !oc) oc = v;
+          }
+          a = v + len;
+        }
+        if (sa && sa[0]) {                       // saTag() != "" (src/BreakID.cc:896-898)
+          S.rec.push_back((uint32_t)i);
+          S.ncig.push_back(n_cig);
+          for (uint32_t k = 0; k < n_cig; ++k) S.cig.push_back(rd32(cg + 4 * k));
+          size_t sl = strlen((const char *)sa);
+          S.salen.push_back((uint32_t)sl);
+          S.sa.insert(S.sa.end(), sa, sa + sl);
+          size_t ol = oc ? strlen((const char *)oc) : 0;
+          S.oclen.push_back((uint32_t)ol);
+          if (ol) S.oc.insert(S.oc.end(), oc, oc + ol);
+        }
+        if (i == 0) h->first_l_qseq = l_seq;
+      }
+    }
+  });
+  h->cig_off.push_back(0); h->sa_off.push_back(0); h->oc_off.push_back(0);
+  for (Side &S : sides) {
+    size_t ci = 0;
+    for (size_t k = 0; k < S.rec.size(); ++k) {
+      h->sa_rec.push_back(S.rec[k]);
+      for (uint32_t c = 0; c < S.ncig[k]; ++c) h->cig_ops.push_back(S.cig[ci++]);
+      h->cig_off.push_back((uint32_t)h->cig_ops.size());
+      h->sa_off.push_back(h->sa_off.back() + S.salen[k]);
+      h->oc_off.push_back(h->oc_off.back() + S.oclen[k]);
+    }
+    h->sa_txt.insert(h->sa_txt.end(), S.sa.begin(), S.sa.end());
+    h->oc_txt.insert(h->oc_txt.end(), S.oc.begin(), S.oc.end());
+  }
+  for (auto &s : h->names) h->name_ptrs.push_back(s.c_str());
+  h->hdr.n_targets = (int32_t)h->names.size();
+  h->hdr.target_len = h->target_len.data();
+  h->hdr.target_name = h->name_ptrs.data();
+  bkid_batch &B = h->batch;
+  B.n = (int64_t)n;
+  B.flag = h->flag.data(); B.mapq = h->mapq.data();
+  B.tid = h->tid.data(); B.pos = h->pos.data(); B.mtid = h->mtid.data(); B.mpos = h->mpos.data();
+  B.isize = h->isize.data(); B.endpos = h->endpos.data(); B.name_hash = h->name_hash.data();
+  B.n_sa = (int64_t)h->sa_rec.size();
+  B.sa_rec = h->sa_rec.data(); B.cig_off = h->cig_off.data(); B.cig_ops = h->cig_ops.data();
+  B.sa_off = h->sa_off.data(); B.sa_txt = h->sa_txt.data();
+  B.oc_off = h->oc_off.data(); B.oc_txt = h->oc_txt.data();
+  return h;
+}
+
+extern "C" const bkid_header *bkid_host_bam_header(const bkid_host_bam *h) { return &h->hdr; }
+extern "C" const bkid_batch *bkid_host_bam_batch(const bkid_host_bam *h) { return &h->batch; }
+extern "C" void bkid_host_bam_free(bkid_host_bam *h) { delete h; }

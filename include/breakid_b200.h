@@ -1,0 +1,188 @@
+/* breakid_b200.h -- C ABI of the B200 implementation of BreakID's data-parallel core.
+ *
+ * The reference (SinOncology/BreakID) has no library target, plugin or FFI ("We don't make a
+ * library at the moment", reference src/CMakeLists.txt:5): its hot path is a set of C++ free
+ * functions called from main() (reference src/BreakID.cc:93-170).  This header is the boundary a
+ * maintainer binds instead: each entry point names the reference function(s) it replaces.
+ * Plain pointers and sizes only; no C++ or torch types.  One context per GPU; a context is not
+ * thread-safe, different contexts are independent.  Every function returns 0 on success and a
+ * negative bkid_status on failure (bkid_last_error() gives the message); nothing throws.
+ * There is NO CPU fallback: without a usable CUDA device bkid_create() fails.
+ *
+ * Stage order (mirrors reference main(), src/BreakID.cc:98-170):
+ *   bkid_create -> [bkid_reserve] -> bkid_push_batch* -> bkid_insert_stats -> bkid_scan
+ *   -> bkid_cluster -> [bkid_set_nib*] -> bkid_refine -> bkid_fetch_clusters -> bkid_destroy
+ * or the single call bkid_run() which does insert_stats..refine with dist from the reference's
+ * own formula (src/BreakID.cc:103).
+ */
+#ifndef BREAKID_B200_H
+#define BREAKID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BKID_ABI_VERSION 1
+
+typedef enum {
+  BKID_OK = 0,
+  BKID_ERR_CUDA = -1,       /* CUDA runtime / no device */
+  BKID_ERR_ARG = -2,        /* bad argument or call order */
+  BKID_ERR_NOMEM = -3,      /* device memory exhausted (e.g. AHC component too large) */
+  BKID_ERR_CIGAR = -4,      /* the reference's fatal "error cigar" path, src/BreakID.cc:954-968 */
+  BKID_ERR_HASH = -5,       /* 64-bit name-hash run with differing 128-bit hashes could not be resolved */
+  BKID_ERR_IO = -6
+} bkid_status;
+
+typedef struct bkid_ctx bkid_ctx;
+
+/* BAM header facts the path needs (reference: bam_header_t target_len / target_name as used by
+ * src/util_bam.cc:57-68 combine_genome_chr_pos and src/BreakID.cc:1500-1512 bucket naming). */
+typedef struct {
+  int32_t n_targets;
+  const uint32_t *target_len;       /* [n_targets] */
+  const char *const *target_name;   /* [n_targets] NUL-terminated */
+} bkid_header;
+
+/* Reference command-line parameters (src/BreakID.cc:27-39) plus the constants it hard-codes. */
+typedef struct {
+  int32_t qual;            /* -q   [20]  src/BreakID.cc:29,1419 */
+  int32_t times;           /* -t   [2]   src/BreakID.cc:30,103 */
+  int32_t fast;            /* -fast [0]  src/BreakID.cc:35,129 */
+  int32_t min_reads;       /* 2          src/BreakID.cc:34 */
+  int32_t bp_pos_error;    /* 2          src/BreakID.cc:444-445 */
+  int32_t mismatch_num;    /* 10         src/BreakID.cc:891 */
+  int32_t sd_mult;         /* 3          the literal in src/BreakID.cc:103 (north_star's -s) */
+  int32_t reserved;
+} bkid_params;
+
+/* One struct-of-arrays batch of decoded alignment records, in BAM file order.  All pointers are
+ * borrowed for the duration of the call.  Per-record columns are exactly the bam1_core_t fields
+ * the reference reads (htslib sam.h:148-157) + bam_endpos (htslib sam.c:344-350) + a 128-bit hash
+ * of the read name (bkid_name_hash) which replaces std::string equality in the mate join
+ * (src/BreakID.cc:1424) and the split-read name match (src/BreakID.cc:605).
+ * Records carrying an SA:Z tag additionally appear in the side table with their raw BAM cigar ops
+ * and the raw SA / OC tag text; all CIGAR / SA arithmetic happens on the device. */
+typedef struct {
+  int64_t n;
+  const uint16_t *flag;
+  const uint8_t *mapq;
+  const int32_t *tid, *pos, *mtid, *mpos, *isize, *endpos;
+  const uint64_t *name_hash;        /* [2n]: lo, hi */
+  int64_t n_sa;
+  const uint32_t *sa_rec;           /* [n_sa] ascending batch-local record index */
+  const uint32_t *cig_off;          /* [n_sa+1] into cig_ops */
+  const uint32_t *cig_ops;          /* BAM encoding len<<4|op */
+  const uint32_t *sa_off;           /* [n_sa+1] into sa_txt */
+  const uint8_t *sa_txt;            /* SA:Z value bytes, no terminator */
+  const uint32_t *oc_off;           /* [n_sa+1] into oc_txt (all equal when no OC tags) */
+  const uint8_t *oc_txt;
+} bkid_batch;
+
+/* A discordant pair (reference struct discordant_pair, src/BreakID.h:39-58) as kept on the device. */
+typedef struct {
+  uint64_t name_lo, name_hi;
+  int32_t p1_tid, p2_tid;
+  uint32_t p1_pos, p2_pos;          /* 1-based */
+  uint32_t p1_chr_pos, p2_chr_pos;  /* genome-wide, uint32 wrap */
+  uint16_t p1_flag, p2_flag;
+  uint8_t p1_mapq, p2_mapq;
+  uint8_t p1_strand, p2_strand;     /* '+' '-' */
+  int32_t bucket;                   /* dense rank of "chrA_chrB" in std::map<string> order */
+  int32_t cluster;
+  uint32_t orig;                    /* index in scan output order */
+  uint32_t _pad;
+} bkid_pair;
+
+/* One called cluster (reference struct cluster_info, src/BreakID.h:60-113), numeric part.  The
+ * host driver adds gene annotation (src/BreakID.cc:492-567) and writes the call file. */
+typedef struct {
+  int32_t bucket;
+  int32_t id;
+  int32_t p1_tid, p2_tid;
+  uint64_t p1_mean_pos, p2_mean_pos;
+  uint32_t p1_min_pos, p1_max_pos, p2_min_pos, p2_max_pos;
+  uint32_t p1_exact_pos;
+  int32_t p2_exact_pos;
+  int64_t n_split_read, n_discordant_pair;
+  double p1_bp_depth, p2_bp_depth;
+  float p1_alle_freq, p2_alle_freq;
+  int32_t fusion_type;              /* 0 Unknown 1 Translocation 2 Inversion 3 Duplication 4 Deletion */
+  int32_t is_rpt;
+  char p1_rpt[44], p2_rpt[44];      /* 41-mer neighbour sequences, NUL padded */
+} bkid_cluster_rec;
+
+/* per-stage device timings of the last run, milliseconds (CUDA events) */
+typedef struct {
+  float h2d, insert_stats, classify, join, bucket_sort, mask, cluster, summarize, evidence, refine, total;
+  int64_t n_records, n_candidates, n_pairs, n_masked, n_clustered, n_clusters, n_sa, n_evidence, n_called;
+  int64_t kernel_launches;
+} bkid_timings;
+
+/* 128-bit read-name hash (FNV-1a 64 + an independent multiply-xorshift 64). */
+static inline void bkid_name_hash(const char *s, uint64_t *lo, uint64_t *hi)
+{
+  uint64_t a = 0xcbf29ce484222325ULL, b = 0x9E3779B97F4A7C15ULL;
+  for (; *s; ++s) {
+    uint64_t c = (unsigned char)*s;
+    a = (a ^ c) * 0x100000001b3ULL;
+    b = (b ^ c) * 0xff51afd7ed558ccdULL;
+    b ^= b >> 32;
+  }
+  *lo = a; *hi = b;
+}
+
+int bkid_abi_version(void);
+const char *bkid_last_error(const bkid_ctx *ctx);       /* ctx may be NULL: last create error */
+void bkid_default_params(bkid_params *p);
+
+/* replaces: process start-up in reference main() (src/BreakID.cc:93-112) */
+bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *params);
+void bkid_destroy(bkid_ctx *ctx);
+
+/* optional capacity hint so pushes never reallocate */
+int bkid_reserve(bkid_ctx *ctx, int64_t n_records, int64_t n_sa, int64_t n_cig_ops, int64_t sa_bytes, int64_t oc_bytes);
+/* replaces: the samread / sam_read1 loops (src/BreakID.cc:1414,1929) as the producer of records.
+ * Host pointers; the host->device copy happens inside (pinned staging, async). */
+int bkid_push_batch(bkid_ctx *ctx, const bkid_batch *batch);
+/* same, but every pointer in `batch` is a DEVICE pointer (already-resident input) */
+int bkid_push_batch_device(bkid_ctx *ctx, const bkid_batch *batch);
+/* forget all records (keeps allocations) */
+int bkid_reset(bkid_ctx *ctx);
+
+/* replaces get_mean_insert_size (src/BreakID.cc:1909-1954) */
+int bkid_insert_stats(bkid_ctx *ctx, double *mean, double *sd);
+/* replaces scan_discordant_pairs (src/BreakID.cc:1362-1515): classify, mate join, p1/p2 order, bucket */
+int bkid_scan(bkid_ctx *ctx, double w, int64_t *n_pairs);
+/* replaces, per bucket, remove_isolated_pairs + find_cluster_pairs_enspan_{ahc,fast} + the summary
+ * half of findClusterBreakPointInfoSaTag (src/BreakID.cc:119-144,201-352); mode 0 = AHC, 1 = -fast */
+int bkid_cluster(bkid_ctx *ctx, double dist, int mode, int64_t *n_clusters);
+/* replaces nib::open/getBase (src/nibtools.cc:7-64): packed 4-bit payload (file bytes after the 8-byte header) */
+int bkid_set_nib(bkid_ctx *ctx, int32_t tid, const uint8_t *packed, uint64_t n_bases);
+/* replaces findEncompassingReadsAndBreakPointInfo (src/BreakID.cc:390-490: find_sa_reads, find_bp_pair,
+ * cal_single_base_depth, AF, fusion type) and the 41-mer / homopolymer part of annotate (:554-561) */
+int bkid_refine(bkid_ctx *ctx, double dist, int64_t *n_called);
+/* everything from insert stats to refine; dist = times*sqrt(times)*(mean+sd_mult*sd) (src/BreakID.cc:103) */
+int bkid_run(bkid_ctx *ctx, double *mean, double *sd, double *dist, int64_t *n_called);
+
+/* results, in the order reference main() appends them (bucket order, then cluster id; src/BreakID.cc:154-161) */
+int bkid_fetch_clusters(bkid_ctx *ctx, bkid_cluster_rec *out, int64_t cap, int64_t *n);
+/* stage outputs for parity tests: stage 0 = after scan, 1 = after isolated-pair removal, 2 = after clustering */
+int bkid_fetch_pairs(bkid_ctx *ctx, int stage, bkid_pair *out, int64_t cap, int64_t *n);
+int bkid_fetch_class(bkid_ctx *ctx, uint8_t *out, int64_t cap);   /* per-record class mask of the classify kernel */
+int bkid_get_timings(bkid_ctx *ctx, bkid_timings *t);
+
+/* Stand-alone operator entry points (device work on caller host arrays) used by the parity tests:
+ * util_cluster / std::sort replay / isolated-pair mask on one bucket. */
+int bkid_op_sort_perm(bkid_ctx *ctx, int64_t n, const uint32_t *key, uint32_t *perm);
+int bkid_op_remove_isolated(bkid_ctx *ctx, int64_t n, const uint32_t *p1, const uint32_t *p2, double w,
+                            uint32_t *out_idx, int64_t *n_out);
+int bkid_op_cluster(bkid_ctx *ctx, int mode, int64_t n, const uint32_t *p1, const uint32_t *p2, double thr,
+                    uint32_t *out_idx, int32_t *out_cluster, int64_t *n_out, int32_t *n_roots);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BREAKID_B200_H */

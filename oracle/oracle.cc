@@ -678,4 +678,428 @@ long orc_model_cluster_ahc(long n, const uint32_t *p1, const uint32_t *p2, doubl
   return tree_to_clusters(n, nn, r.data(), a.data(), b.data(), out_idx, out_cluster, roots);
 }
 
+
+/* ==========================================================================================
+ * Refinement: a7 cluster summary, a8 split-read evidence, a9 vote, a10 depth/AF/type, a11 nib.
+ * ========================================================================================== */
+}  /* extern "C" (reopened below) */
+
+namespace {
+
+/* CigarRoller semantics (src/CigarRoller.cc:26-136,187-205; src/Cigar.cc:80-144; src/Cigar.h:215-228).
+ * op codes: 1 match 3 insert 4 del 5 skip 6 softClip 7 hardClip 8 pad (enum src/Cigar.h:66-77). */
+struct Roller {
+  std::vector<std::pair<int, uint32_t>> ops;
+  void add(int op, int count) {                                /* operator+= :26-46 */
+    if ((uint32_t)count == 0) return;
+    if (ops.empty() || ops.back().first != op) ops.push_back({op, (uint32_t)count});
+    else ops.back().second += (uint32_t)count;
+  }
+  void add_char(int ch, int count) {                           /* Add(char,int) :67-117 */
+    switch (ch) {
+      case 0: case 'M': add(1, count); break;
+      case 1: case 'I': add(3, count); break;
+      case 2: case 'D': add(4, count); break;
+      case 3: case 'N': add(5, count); break;
+      case 4: case 'S': add(6, count); break;
+      case 5: case 'H': add(7, count); break;
+      case 6: case 'P': add(8, count); break;
+      case 7: case '=': add(1, count); break;
+      case 8: case 'X': add(1, count); break;
+      default: break;                                          /* reference prints an error and continues */
+    }
+  }
+  void set_text(const std::string &t) {                        /* Add(const char*) :120-136: the count is NOT reset */
+    ops.clear();
+    int cnt = 0;
+    const char *c = t.c_str();
+    while (*c) {
+      if (isdigit((unsigned char)*c)) { char *e; cnt = (int)strtol(c, &e, 10); c = e; }
+      else { add_char((unsigned char)*c, cnt); ++c; }
+    }
+  }
+  void set_bam(const uint32_t *b, int n) { ops.clear(); for (int i = 0; i < n; ++i) add_char(b[i] & 0xF, (int)(b[i] >> 4)); }
+  std::string str() const {                                    /* Cigar::getCigarString :22-38 */
+    static const char ch[] = "?MMIDNSHP";
+    std::string s;
+    for (auto &o : ops) s += std::to_string(o.second) + ch[o.first];
+    return s;
+  }
+  int matches() const { int n = 0; for (auto &o : ops) if (o.first == 1) n += o.second; return n; }
+  int begin_clips() const { int n = 0; for (auto &o : ops) { if (o.first == 6 || o.first == 7) n += o.second; else break; } return n; }
+  int end_clips() const { int n = 0; for (size_t i = ops.size(); i-- > 0;) { if (ops[i].first == 6 || ops[i].first == 7) n += ops[i].second; else break; } return n; }
+  int ref_count() const { int n = 0; for (auto &o : ops) if (o.first == 1 || o.first == 2 || o.first == 4 || o.first == 5) n += o.second; return n; }
+  uint32_t aln_end(uint32_t start) const { return start + ref_count() - 1; }   /* :316-321 */
+};
+
+/* full match of ([0-9]+[MS]){2} (src/CigarRoller.cc:326) */
+bool regex_2ms(const std::string &s)
+{
+  size_t i = 0;
+  for (int g = 0; g < 2; ++g) {
+    size_t d = i;
+    while (i < s.size() && s[i] >= '0' && s[i] <= '9') ++i;
+    if (i == d || i >= s.size() || (s[i] != 'M' && s[i] != 'S')) return false;
+    ++i;
+  }
+  return i == s.size();
+}
+
+/* src/CigarRoller.cc:323-346 */
+bool complementary(const Roller &c1, const std::string &c2, int err)
+{
+  Roller r2; r2.set_text(c2);
+  if (!(regex_2ms(c1.str()) && regex_2ms(c2))) return false;
+  int c1_m = c1.matches(), c2_m = r2.matches();
+  int c1_s = c1.begin_clips() + c1.end_clips(), c2_s = r2.end_clips() + r2.begin_clips();
+  return (c1_m <= c2_s + err && c1_m >= c2_s - err) && (c1_m + c1_s == c2_m + c2_s);
+}
+
+std::vector<std::string> split_nonempty(const std::string &s, char delim)   /* src/util_bed.cc:194-222 */
+{
+  std::vector<std::string> r; std::string cur;
+  for (char c : s) { if (c == delim) { if (!cur.empty()) r.push_back(cur); cur.clear(); } else cur += c; }
+  if (!cur.empty()) r.push_back(cur);
+  return r;
+}
+
+std::string chrom_id_name(int t)                                            /* src/util_bam.cc:128-142 */
+{
+  if (t == 23) return "chrY";
+  if (t == 22) return "chrX";
+  if (t >= 0 && t < 22) return "chr" + std::to_string(t + 1);
+  return "";
+}
+
+struct Ev {
+  uint64_t lo, hi; std::string pchr, schr, pcig, scig;
+  uint32_t pstart, sstart, pend, send, pbp, sbp; bool secondary; uint16_t flag;
+};
+
+struct Recs {
+  long n; const uint16_t *flag; const uint8_t *mapq; const int32_t *tid, *pos, *endpos; const uint64_t *nh;
+  long n_sa; const uint32_t *sa_rec, *cig_off, *cig_ops, *sa_off; const uint8_t *sa_txt; const uint32_t *oc_off; const uint8_t *oc_txt;
+  std::vector<long> sa_slot_of;   /* filled lazily: record -> sa slot or -1 */
+};
+
+int g_cigar_error = 0;
+
+/* src/BreakID.cc:868-1037.  Region semantics of the index iterator (htslib hts.c:1776-1777,1963-1965):
+ * same tid, pos0 < end, bam_endpos > max(beg,0). */
+void find_sa_reads(const Recs &R, int tid, uint32_t region_start, uint32_t region_end,
+                   std::map<std::pair<uint64_t, uint64_t>, std::vector<Ev>> &out, std::vector<Ev> *flat, int mismatch)
+{
+  out.clear();
+  int beg = (int)region_start, end = (int)region_end;
+  if (beg < 0) beg = 0;
+  int total_cov = 0, total_ev = 0;
+  if (end < beg) return;     /* NULL iterator: the reference then reads the rest of the file; out of domain here */
+  /* records are coordinate sorted: binary search the first record of tid, then walk */
+  long lo = 0, hi = R.n;
+  while (lo < hi) { long m = (lo + hi) / 2; if ((uint32_t)R.tid[m] < (uint32_t)tid) lo = m + 1; else hi = m; }
+  for (long i = lo; i < R.n && R.tid[i] == tid && R.pos[i] < end; ++i) {
+    if (!(R.endpos[i] > beg)) continue;
+    ++total_cov;                                                          /* :894 every record counts */
+    long k = R.sa_slot_of[i];
+    if (k < 0) continue;
+    std::string sa((const char *)R.sa_txt + R.sa_off[k], R.sa_off[k + 1] - R.sa_off[k]);
+    if (!(!sa.empty() && !(R.flag[i] & F_DUP) && (R.flag[i] & F_PAIRED))) continue;   /* :898 */
+    std::string oc((const char *)R.oc_txt + R.oc_off[k], R.oc_off[k + 1] - R.oc_off[k]);
+    std::vector<std::string> f = split_nonempty(sa, ',');
+    if (f.size() < 4) continue;                                           /* reference: UB; out of domain */
+    Roller sa_c, c1, rec_c;
+    sa_c.set_text(f[3]);
+    rec_c.set_bam(R.cig_ops + R.cig_off[k], (int)(R.cig_off[k + 1] - R.cig_off[k]));
+    if (!oc.empty()) c1.set_text(oc); else c1 = rec_c;                    /* :906-913 */
+    if (!complementary(c1, f[3], mismatch)) continue;                     /* :915 */
+    ++total_ev;
+    Ev e; e.lo = R.nh[2 * i]; e.hi = R.nh[2 * i + 1]; e.flag = R.flag[i];
+    e.secondary = (R.flag[i] & F_SECONDARY) != 0;
+    uint32_t sa_start = (uint32_t)atoi(f[1].c_str());                     /* stoi :929 */
+    uint32_t sa_end = sa_c.aln_end(sa_start);
+    uint32_t a_start = (uint32_t)((long)R.pos[i] + 1);                    /* getAlignmentStart */
+    int alen = rec_c.ref_count();
+    uint32_t a_end = (uint32_t)((long)(alen == 0 ? R.pos[i] : R.pos[i] + alen - 1) + 1);   /* getAlignmentEnd */
+    std::string rec_str = rec_c.str();
+    std::string own_chr = chrom_id_name(R.tid[i]);
+    uint32_t own_end = !oc.empty() ? c1.aln_end(a_start) : a_end;
+    std::string own_cig = !oc.empty() ? oc : rec_str;
+    uint32_t own_bp, sa_bp;
+    if (c1.begin_clips() != 0) own_bp = a_start; else if (c1.end_clips() != 0) own_bp = a_end; else { g_cigar_error = 1; continue; }
+    if (sa_c.begin_clips() != 0) sa_bp = sa_start; else if (sa_c.end_clips() != 0) sa_bp = sa_end; else { g_cigar_error = 1; continue; }
+    if (!e.secondary) {                                                   /* :933-973 */
+      e.pchr = own_chr; e.pstart = a_start; e.pend = own_end; e.pcig = own_cig; e.pbp = own_bp;
+      e.schr = f[0]; e.sstart = sa_start; e.send = sa_end; e.scig = f[3]; e.sbp = sa_bp;
+    } else {                                                              /* :974-1016 */
+      e.pchr = f[0]; e.pstart = sa_start; e.pend = sa_end; e.pcig = f[3]; e.pbp = sa_bp;
+      e.schr = own_chr; e.sstart = a_start; e.send = own_end; e.scig = own_cig; e.sbp = own_bp;
+    }
+    out[{e.lo, e.hi}].push_back(e);
+    if (flat) flat->push_back(e);
+  }
+  if (total_cov < 5 || total_ev < 2) { out.clear(); if (flat) flat->clear(); }   /* :1032-1035 */
+}
+
+/* src/BreakID.cc:577-857 (the "update version" vote, :797-855) */
+int find_bp_pair(const std::map<std::pair<uint64_t, uint64_t>, std::vector<Ev>> &m1,
+                 const std::map<std::pair<uint64_t, uint64_t>, std::vector<Ev>> &m2,
+                 const std::string &p1_chr, int bp_err, int32_t *p1_bp, int32_t *p2_bp)
+{
+  std::vector<std::pair<int32_t, int32_t>> upd;
+  for (auto &kv : m1) {
+    auto it = m2.find(kv.first);
+    if (it == m2.end()) continue;
+    for (const Ev &a : kv.second) for (const Ev &b : it->second) {
+      bool c = a.secondary != b.secondary && a.pchr == b.pchr && a.schr == b.schr && a.pstart == b.pstart &&
+               a.sstart == b.sstart && a.pend == b.pend && a.send == b.send && a.pcig == b.pcig && a.scig == b.scig &&
+               a.pbp == b.pbp && a.sbp == b.sbp;                           /* new_condition :627-637 */
+      if (!c) continue;
+      if (a.pchr == p1_chr) upd.push_back({(int32_t)a.pbp, (int32_t)a.sbp});  /* :647,671-672 */
+      else upd.push_back({(int32_t)a.sbp, (int32_t)a.pbp});                   /* :717-718 */
+    }
+  }
+  std::map<std::string, int> cnt;
+  for (auto &u : upd) cnt[std::to_string(u.first) + "," + std::to_string(u.second)] = 0;
+  for (auto &kv : cnt) {
+    size_t c = kv.first.find(',');
+    uint32_t k1 = (uint32_t)strtoull(kv.first.substr(0, c).c_str(), nullptr, 10);
+    uint32_t k2 = (uint32_t)strtoull(kv.first.substr(c + 1).c_str(), nullptr, 10);
+    for (auto &u : upd)                                                     /* mixed int32/uint32 compares :820-821 */
+      if (((uint32_t)u.first <= k1 + bp_err && (uint32_t)u.first >= k1 - bp_err) &&
+          ((uint32_t)u.second <= k2 + bp_err && (uint32_t)u.second >= k2 - bp_err)) kv.second++;
+  }
+  int best = 0; *p1_bp = -1; *p2_bp = -1;
+  for (auto &kv : cnt)
+    if (best < kv.second) {                                                 /* first strict max in string order :841-855 */
+      best = kv.second;
+      size_t c = kv.first.find(',');
+      *p1_bp = (int32_t)(uint32_t)strtoull(kv.first.substr(0, c).c_str(), nullptr, 10);
+      *p2_bp = (int32_t)(uint32_t)strtoull(kv.first.substr(c + 1).c_str(), nullptr, 10);
+    }
+  return best;
+}
+
+/* src/util_bed.cc:154-192: records overlapping 0-based [pos-1,pos) with qual>0, !DUP, PAIRED */
+double single_base_depth(const Recs &R, int tid, uint64_t pos)
+{
+  int beg = (int)(pos - 1), end = (int)pos;
+  if (beg < 0) beg = 0;
+  if (end < beg) return 0;
+  long lo = 0, hi = R.n;
+  while (lo < hi) { long m = (lo + hi) / 2; if ((uint32_t)R.tid[m] < (uint32_t)tid) lo = m + 1; else hi = m; }
+  int depth = 0;
+  for (long i = lo; i < R.n && R.tid[i] == tid && R.pos[i] < end; ++i)
+    if (R.endpos[i] > beg && R.mapq[i] > 0 && !(R.flag[i] & F_DUP) && (R.flag[i] & F_PAIRED)) ++depth;
+  return depth;
+}
+
+/* src/nibtools.cc:38-64 + src/nibtools.h:23-59 */
+char nib_base(const uint8_t *packed, uint64_t nbases, long pos, char prev)
+{
+  if (pos < 0 || (uint64_t)pos >= nbases) return prev;           /* reference leaves `base` untouched (status 4) */
+  int b = packed[pos / 2];
+  int v = (pos % 2 == 0) ? (b >> 4) : (b & 0xf);
+  switch (v) { case 0: case 8: return 'T'; case 1: case 9: return 'C'; case 2: case 10: return 'A'; case 3: case 11: return 'G'; default: return 'N'; }
+}
+
+int longest_run(const char *s)                                    /* src/util_bed.cc:224-261 */
+{
+  int best = 0;
+  for (int i = 0; s[i];) { int j = i; while (s[j] == s[i]) ++j; if (j - i > best) best = j - i; i = j; }
+  return best;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_is_complementary(const char *c1, const char *c2, int err)
+{
+  Roller r; r.set_text(c1);
+  return complementary(r, c2, err) ? 1 : 0;
+}
+
+static void fill_recs(Recs &R, long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos,
+                      const int32_t *endpos, const uint64_t *nh, long n_sa, const uint32_t *sa_rec, const uint32_t *cig_off,
+                      const uint32_t *cig_ops, const uint32_t *sa_off, const uint8_t *sa_txt, const uint32_t *oc_off, const uint8_t *oc_txt)
+{
+  R.n = n; R.flag = flag; R.mapq = mapq; R.tid = tid; R.pos = pos; R.endpos = endpos; R.nh = nh;
+  R.n_sa = n_sa; R.sa_rec = sa_rec; R.cig_off = cig_off; R.cig_ops = cig_ops; R.sa_off = sa_off; R.sa_txt = sa_txt;
+  R.oc_off = oc_off; R.oc_txt = oc_txt;
+  R.sa_slot_of.assign(n, -1);
+  for (long k = 0; k < n_sa; ++k) R.sa_slot_of[sa_rec[k]] = k;
+}
+
+static void ev_to_pod(const Ev &s, orc_evidence &e, std::vector<std::string> &others)
+{
+  auto cid = [&](const std::string &x) -> int {
+    if (x.empty()) return -1;
+    for (int t = 0; t < 24; ++t) if (chrom_id_name(t) == x) return t;
+    for (size_t k = 0; k < others.size(); ++k) if (others[k] == x) return -2 - (int)k;
+    others.push_back(x); return -2 - (int)(others.size() - 1);
+  };
+  memset(&e, 0, sizeof e);
+  e.name_lo = s.lo; e.name_hi = s.hi;
+  e.primary_chr = cid(s.pchr); e.secondary_chr = cid(s.schr);
+  e.primary_start = s.pstart; e.secondary_start = s.sstart; e.primary_end = s.pend; e.secondary_end = s.send;
+  e.primary_bp = s.pbp; e.secondary_bp = s.sbp;
+  e.primary_cigar_h = orc_str_hash(s.pcig.c_str()); e.secondary_cigar_h = orc_str_hash(s.scig.c_str());
+  e.flag = s.flag; e.secondary = s.secondary;
+}
+
+/* evidence rows of one region in std::map<name> ... the reference iterates names in string order which
+ * the hashes cannot reproduce, so rows are returned in RECORD order (tests sort both sides). */
+long orc_find_sa_reads(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos,
+                       const int32_t *endpos, const uint64_t *nh, long n_sa, const uint32_t *sa_rec, const uint32_t *cig_off,
+                       const uint32_t *cig_ops, const uint32_t *sa_off, const uint8_t *sa_txt, const uint32_t *oc_off,
+                       const uint8_t *oc_txt, int q_tid, uint32_t start, uint32_t end, orc_evidence **out)
+{
+  Recs R; fill_recs(R, n, flag, mapq, tid, pos, endpos, nh, n_sa, sa_rec, cig_off, cig_ops, sa_off, sa_txt, oc_off, oc_txt);
+  std::map<std::pair<uint64_t, uint64_t>, std::vector<Ev>> m; std::vector<Ev> flat;
+  find_sa_reads(R, q_tid, start, end, m, &flat, 10);
+  orc_evidence *o = (orc_evidence *)calloc(flat.size() ? flat.size() : 1, sizeof(orc_evidence));
+  std::vector<std::string> others;
+  for (size_t k = 0; k < flat.size(); ++k) ev_to_pod(flat[k], o[k], others);
+  *out = o;
+  return (long)flat.size();
+}
+
+int orc_find_bp(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos,
+                const int32_t *endpos, const uint64_t *nh, long n_sa, const uint32_t *sa_rec, const uint32_t *cig_off,
+                const uint32_t *cig_ops, const uint32_t *sa_off, const uint8_t *sa_txt, const uint32_t *oc_off,
+                const uint8_t *oc_txt, int tid1, const char *chr1, uint32_t s1, uint32_t e1, int tid2, uint32_t s2, uint32_t e2,
+                int32_t *p1_bp, int32_t *p2_bp)
+{
+  Recs R; fill_recs(R, n, flag, mapq, tid, pos, endpos, nh, n_sa, sa_rec, cig_off, cig_ops, sa_off, sa_txt, oc_off, oc_txt);
+  std::map<std::pair<uint64_t, uint64_t>, std::vector<Ev>> m1, m2;
+  *p1_bp = -1; *p2_bp = -1;
+  find_sa_reads(R, tid1, s1, e1, m1, nullptr, 10);
+  if (!m1.empty()) find_sa_reads(R, tid2, s2, e2, m2, nullptr, 10);
+  if (m1.empty() || m2.empty()) return 0;
+  return find_bp_pair(m1, m2, chr1, 2, p1_bp, p2_bp);
+}
+
+double orc_single_base_depth(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos,
+                             const int32_t *endpos, int q_tid, uint64_t q_pos)
+{
+  Recs R; R.n = n; R.flag = flag; R.mapq = mapq; R.tid = tid; R.pos = pos; R.endpos = endpos;
+  return single_base_depth(R, q_tid, q_pos);
+}
+
+/* src/BreakID.cc:554-561: 41-mer = 1-based [bp-20, bp+20] */
+void orc_neighbor_41(const uint8_t *packed, uint64_t nbases, int32_t bp, char *out42)
+{
+  memset(out42, 0, 42);
+  char prev = 'N';
+  int k = 0;
+  for (int32_t i = bp - 20; i < bp; ++i) { prev = nib_base(packed, nbases, (long)i - 1, prev); out42[k++] = prev; }
+  for (int32_t i = bp - 1; i < bp - 1 + 21; ++i) { prev = nib_base(packed, nbases, (long)i, prev); out42[k++] = prev; }
+}
+int orc_longest_repeat(const char *s) { return longest_run(s); }
+
+/* ------------------------------------------------------------------------------------------
+ * Whole hot path on one record batch -- what reference main() computes between
+ * src/BreakID.cc:98 and :167, minus gene annotation and file writing.  Output: the valid clusters in
+ * the order main() appends them (bucket order, then cluster id).
+ * mode 0 = AHC (default), 1 = -fast.  nib_packed[t] may be NULL (41-mers left empty).
+ * Returns the number of clusters, or -1 when the reference's fatal "error cigar" path was hit. */
+long orc_run(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos,
+             const int32_t *mtid, const int32_t *mpos, const int32_t *isize, const int32_t *endpos, const uint64_t *nh,
+             long n_sa, const uint32_t *sa_rec, const uint32_t *cig_off, const uint32_t *cig_ops, const uint32_t *sa_off,
+             const uint8_t *sa_txt, const uint32_t *oc_off, const uint8_t *oc_txt,
+             int n_targets, const uint32_t *target_len, const char *const *names,
+             const uint8_t *const *nib_packed, const uint64_t *nib_len,
+             int qual, int times, int mode, double *mean_out, double *sd_out, double *dist_out, orc_cluster **out)
+{
+  g_cigar_error = 0;
+  double mean, sd;
+  orc_insert_stats(n, flag, isize, &mean, &sd, nullptr, nullptr, nullptr);
+  double dist = orc_dist(mean, sd, times);
+  if (mean_out) *mean_out = mean;
+  if (sd_out) *sd_out = sd;
+  if (dist_out) *dist_out = dist;
+  orc_pair *pairs = nullptr;
+  long np = orc_scan(n, flag, mapq, tid, pos, mtid, mpos, nh, n_targets, target_len, names, qual, dist, &pairs);
+  Recs R; fill_recs(R, n, flag, mapq, tid, pos, endpos, nh, n_sa, sa_rec, cig_off, cig_ops, sa_off, sa_txt, oc_off, oc_txt);
+  std::vector<orc_cluster> result;
+  long s = 0;
+  while (s < np) {
+    long e = s;
+    while (e < np && pairs[e].bucket == pairs[s].bucket) ++e;
+    long nb = e - s;
+    std::vector<uint32_t> p1(nb), p2(nb), idx(nb + 2);
+    for (long i = 0; i < nb; ++i) { p1[i] = pairs[s + i].p1_chr_pos; p2[i] = pairs[s + i].p2_chr_pos; }
+    long nm = orc_remove_isolated(nb, p1.data(), p2.data(), dist, idx.data());          /* :123 */
+    if (nm >= 2) {                                                                       /* :125 */
+      std::vector<uint32_t> q1(nm), q2(nm), cidx(nm + 2); std::vector<int32_t> cl(nm + 2);
+      for (long i = 0; i < nm; ++i) { q1[i] = p1[idx[i]]; q2[i] = p2[idx[i]]; }
+      int roots = 0;
+      long nc = mode ? orc_cluster_fast(nm, q1.data(), q2.data(), dist, cidx.data(), cl.data(), &roots)
+                     : orc_cluster_ahc(nm, q1.data(), q2.data(), dist, cidx.data(), cl.data(), &roots);
+      /* a7: per-cluster summary (src/BreakID.cc:222-352); order inside a cluster does not matter */
+      std::map<long, std::vector<long>> members;
+      for (long i = 0; i < nc; ++i) members[cl[i]].push_back(s + idx[cidx[i]]);
+      for (auto &kv : members) {
+        orc_cluster c; memset(&c, 0, sizeof c);
+        const orc_pair &f = pairs[kv.second[0]];
+        c.bucket = f.bucket; c.id = (int32_t)kv.first; c.p1_tid = f.p1_tid; c.p2_tid = f.p2_tid;
+        uint64_t s1 = 0, s2 = 0; uint32_t mn1 = UINT32_MAX, mx1 = 0, mn2 = UINT32_MAX, mx2 = 0;
+        bool t_diff = false, t_rev = false, t_same = false, t_def = false;
+        for (long m : kv.second) {
+          const orc_pair &p = pairs[m];
+          s1 += p.p1_pos; s2 += p.p2_pos;
+          mn1 = std::min(mn1, p.p1_pos); mx1 = std::max(mx1, p.p1_pos); mn2 = std::min(mn2, p.p2_pos); mx2 = std::max(mx2, p.p2_pos);
+          if (p.p1_tid != p.p2_tid) t_diff = true;                                       /* :231-253 */
+          else {
+            if (p.p1_strand == '-' && p.p2_strand == '+') t_rev = true;
+            if (p.p1_strand == p.p2_strand) t_same = true;
+            if (p.p1_strand == '+' && p.p2_strand == '-') t_def = true;
+          }
+        }
+        c.n_discordant_pair = (int64_t)kv.second.size();
+        c.p1_mean_pos = (uint32_t)((double)s1 / (double)c.n_discordant_pair);            /* :342-343 */
+        c.p2_mean_pos = (uint32_t)((double)s2 / (double)c.n_discordant_pair);
+        c.p1_min_pos = mn1; c.p1_max_pos = mx1; c.p2_min_pos = mn2; c.p2_max_pos = mx2;
+        int64_t md = (int64_t)(c.p1_mean_pos - c.p2_mean_pos);                            /* :345 */
+        if (c.p1_tid == c.p2_tid && md <= 2 * dist && md >= -2 * dist) continue;          /* :348 */
+        /* a8-a10 (src/BreakID.cc:421-485) */
+        int w = (int)dist;                                                                /* const int w, :390 */
+        uint32_t r1s = (uint32_t)(c.p1_mean_pos - w), r1e = (uint32_t)(c.p1_mean_pos + w);
+        uint32_t r2s = (uint32_t)(c.p2_mean_pos - w), r2e = (uint32_t)(c.p2_mean_pos + w);
+        std::map<std::pair<uint64_t, uint64_t>, std::vector<Ev>> m1, m2;
+        find_sa_reads(R, c.p1_tid, r1s, r1e, m1, nullptr, 10);
+        if (!m1.empty()) find_sa_reads(R, c.p2_tid, r2s, r2e, m2, nullptr, 10);
+        if (m1.empty() || m2.empty()) continue;
+        int32_t b1, b2;
+        std::string p1name = c.p1_tid >= 0 ? names[c.p1_tid] : "*";
+        int votes = find_bp_pair(m1, m2, p1name, 2, &b1, &b2);
+        if (votes < 2) continue;                                                          /* :446 */
+        c.p1_exact_pos = (uint32_t)b1; c.p2_exact_pos = b2; c.n_split_read = votes;
+        c.p1_bp_depth = single_base_depth(R, c.p1_tid, (uint64_t)c.p1_exact_pos);
+        c.p2_bp_depth = single_base_depth(R, c.p2_tid, (uint64_t)(int64_t)c.p2_exact_pos);
+        c.p1_alle_freq = (float)c.n_split_read / (float)c.p1_bp_depth;                    /* :475-478 */
+        c.p2_alle_freq = (float)c.n_split_read / (float)c.p2_bp_depth;
+        c.fusion_type = 0;                                                                /* :1888-1907 */
+        if (t_diff) c.fusion_type = 1;
+        if (t_same) c.fusion_type = 2;
+        if (t_rev) c.fusion_type = 3;
+        if (t_def) c.fusion_type = 4;
+        if (nib_packed) {
+          if (c.p1_tid >= 0 && nib_packed[c.p1_tid]) orc_neighbor_41(nib_packed[c.p1_tid], nib_len[c.p1_tid], (int32_t)c.p1_exact_pos, c.p1_rpt);
+          if (c.p2_tid >= 0 && nib_packed[c.p2_tid]) orc_neighbor_41(nib_packed[c.p2_tid], nib_len[c.p2_tid], c.p2_exact_pos, c.p2_rpt);
+          c.is_rpt = (longest_run(c.p1_rpt) > 10 || longest_run(c.p2_rpt) > 10) ? 1 : 0;
+        }
+        result.push_back(c);
+      }
+    }
+    s = e;
+  }
+  free(pairs);
+  orc_cluster *o = (orc_cluster *)calloc(result.size() ? result.size() : 1, sizeof(orc_cluster));
+  for (size_t i = 0; i < result.size(); ++i) o[i] = result[i];
+  *out = o;
+  if (g_cigar_error) return -1;
+  return (long)result.size();
+}
+
 }  /* extern "C" */
