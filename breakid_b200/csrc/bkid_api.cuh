@@ -1,0 +1,1084 @@
+// bkid_api.cuh -- context, host orchestration and the exported C ABI.  Included by bkid_core.cu.
+#pragma once
+
+#define GRID1(n, t) (unsigned)div_up((long long)(n), (t))
+
+struct Scratch {          // reusable device scratch for sorts / scans over `cap` elements
+  DBuf keys, keys_alt, vals, vals_alt, hist, scan_tmp, a32, b32, c32, d32, e32;
+  int ensure(long long n, cudaStream_t st)
+  {
+    size_t m = (size_t)std::max<long long>(n, 1);
+    BK_TRY(keys.ensure(m * 8, 0, st)); BK_TRY(keys_alt.ensure(m * 8, 0, st));
+    BK_TRY(vals.ensure(m * 4, 0, st)); BK_TRY(vals_alt.ensure(m * 4, 0, st));
+    BK_TRY(hist.ensure(bk::radix_hist_elems(n) * 4, 0, st));
+    BK_TRY(scan_tmp.ensure((bk::scan_tmp_elems(std::max<long long>((long long)bk::radix_hist_elems(n), n)) + 8) * 8, 0, st));
+    BK_TRY(a32.ensure(m * 4 + 16, 0, st)); BK_TRY(b32.ensure(m * 4 + 16, 0, st)); BK_TRY(c32.ensure(m * 4 + 16, 0, st));
+    BK_TRY(d32.ensure(m * 4 + 16, 0, st)); BK_TRY(e32.ensure(m * 4 + 16, 0, st));
+    return 0;
+  }
+  bk::RadixTmp rt() { return bk::RadixTmp{keys_alt.as<uint64_t>(), vals_alt.as<uint32_t>(), hist.as<uint32_t>(), scan_tmp.as<unsigned long long>()}; }
+  void release() { for (DBuf *b : {&keys, &keys_alt, &vals, &vals_alt, &hist, &scan_tmp, &a32, &b32, &c32, &d32, &e32}) b->release(); }
+};
+
+struct bkid_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  bkid_params prm;
+  int nt = 0;
+  std::vector<uint32_t> target_len;
+  std::vector<std::string> names;
+  std::string err;
+  // header tables
+  DBuf d_cum, d_bucket_rank, d_canon;
+  // resident record columns (file order)
+  long long n = 0, cap_n = 0;
+  bool borrowed = false;
+  DBuf flag, mapq, tid, pos, mtid, mpos, isize, endpos, nh, cls;
+  const uint16_t *p_flag = nullptr; const uint8_t *p_mapq = nullptr;
+  const int32_t *p_tid = nullptr, *p_pos = nullptr, *p_mtid = nullptr, *p_mpos = nullptr, *p_isize = nullptr, *p_endpos = nullptr;
+  const uint64_t *p_nh = nullptr;
+  // SA side table
+  long long n_sa = 0, n_cig = 0, sa_bytes = 0, oc_bytes = 0;
+  DBuf sa_rec, cig_off, cig_ops, sa_off, sa_txt, oc_off, oc_txt;
+  const uint32_t *p_sa_rec = nullptr, *p_cig_off = nullptr, *p_cig_ops = nullptr, *p_sa_off = nullptr, *p_oc_off = nullptr;
+  const uint8_t *p_sa_txt = nullptr, *p_oc_txt = nullptr;
+  // nib
+  std::vector<DBuf> nib;
+  std::vector<uint64_t> nib_len;
+  DBuf d_nib_ptr, d_nib_len;
+  // state
+  bool classified = false, have_stats = false, scanned = false, clustered = false, refined = false;
+  double mean = 0, sd = 0;
+  long long sum_abs = 0, cnt_insert = 0, sd_total = 0;
+  DBuf tile_cand, counters, cand_idx;
+  long long n_cand = 0;
+  // pairs (stage 0)
+  DBuf pairs0, pairs_tmp, bucket_off0;
+  long long np0 = 0; int nb = 0;
+  DBuf X, Y, bucket_of_pair;
+  // stage 1 (after isolated-pair removal): pair ids in order + bucket offsets
+  DBuf cur1, curb1, seg1;
+  long long n1 = 0;
+  // stage 2 (after clustering): members grouped by (bucket, cluster)
+  DBuf mem_pair, mem_bucket, mem_cluster;
+  long long n2 = 0;
+  std::vector<int32_t> roots_per_bucket;
+  // clusters
+  DBuf clusters, clusters_out;
+  long long n_clusters = 0, n_called = 0;
+  Scratch sc;
+  DBuf tmpA, tmpB, tmpC, tmpD, tmpE, tmpF, tmpG;
+  bkid_timings tm;
+  cudaEvent_t ev[16];
+  long long launches0 = 0;
+};
+
+static int fail(bkid_ctx *c, int code, const std::string &msg)
+{
+  if (c) c->err = msg;
+  else g_create_err = msg;
+  return code;
+}
+#define CU(c, x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { bk_set_cuda_error(e__, __FILE__, __LINE__); return fail((c), e__ == cudaErrorMemoryAllocation ? BKID_ERR_NOMEM : BKID_ERR_CUDA, g_last_cuda_err); } } while (0)
+#define TRY(c, x) do { int rc__ = (x); if (rc__ != 0) { if ((c)->err.empty()) (c)->err = g_last_cuda_err; return rc__; } } while (0)
+
+static int sync_check(bkid_ctx *c)
+{
+  CU(c, cudaStreamSynchronize(c->st));
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// std::sort replay over segments (buckets).  key/val are permuted in place.
+// ---------------------------------------------------------------------------------------------
+static int exact_sort_segments(bkid_ctx *c, uint32_t *key, uint32_t *val, const uint32_t *seg_off, int nseg, long long n)
+{
+  if (n < 2 || nseg <= 0) return 0;
+  cudaStream_t st = c->st;
+  size_t seg_bytes = ((size_t)n / 2 + 16) * sizeof(Seg);
+  TRY(c, c->tmpA.ensure(seg_bytes, 0, st));
+  TRY(c, c->tmpB.ensure(seg_bytes, 0, st));
+  TRY(c, c->tmpC.ensure(seg_bytes, 0, st));
+  TRY(c, c->tmpD.ensure((size_t)n * 4 + 16, 0, st));
+  TRY(c, c->tmpE.ensure((size_t)n * 4 + 16, 0, st));
+  TRY(c, c->counters.ensure(256, 0, st));
+  unsigned *cnt = c->counters.as<unsigned>() + 16;     // [0]=act A, [1]=act B, [2]=terminal
+  CU(c, cudaMemsetAsync(cnt, 0, 16, st));
+  Seg *act[2] = {c->tmpA.as<Seg>(), c->tmpB.as<Seg>()};
+  Seg *term = c->tmpC.as<Seg>();
+  BK_LAUNCH(is_init_roots, GRID1(nseg, 256), 256, 0, st, seg_off, nseg, act[0], cnt + 0, term, cnt + 2);
+  int lg = 0;
+  for (long long t = n; t > 1; t >>= 1) ++lg;
+  int max_levels = 2 * lg + 2;
+  int cur = 0;
+  for (int level = 0; level < max_levels; ++level) {
+    if (level > 0 && (level % 8) == 0) {               // early exit once no segment is active
+      unsigned h = 0;
+      CU(c, cudaMemcpyAsync(&h, cnt + cur, 4, cudaMemcpyDeviceToHost, st));
+      CU(c, cudaStreamSynchronize(st));
+      if (h == 0) break;
+    }
+    CU(c, cudaMemsetAsync(cnt + (cur ^ 1), 0, 4, st));
+    BK_LAUNCH(is_level, 592, IS_THREADS, 0, st, key, val, act[cur], cnt + cur, act[cur ^ 1], cnt + (cur ^ 1), term, cnt + 2,
+              c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>());
+    cur ^= 1;
+  }
+  BK_LAUNCH(is_terminal, 592, 128, 0, st, key, val, term, cnt + 2);
+  return 0;
+}
+
+// sort the current order of every bucket by coord[cur[p]] with std::sort semantics
+static int sort_current_by(bkid_ctx *c, uint32_t *cur, long long n, const uint32_t *coord, const uint32_t *seg_off, int nseg)
+{
+  if (n < 2) return 0;
+  TRY(c, c->tmpF.ensure((size_t)n * 4 + 16, 0, c->st));
+  uint32_t *key = c->tmpF.as<uint32_t>();
+  BK_LAUNCH(gather_u32, GRID1(n, 256), 256, 0, c->st, coord, cur, n, key);
+  return exact_sort_segments(c, key, cur, seg_off, nseg, n);
+}
+
+// one isolated-pair mask pass: (cur, curb, seg) -> (cur_out, curb_out, seg_out); returns new count
+static int mask_pass(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, const uint32_t *seg, long long n, int nseg, const uint32_t *X, const uint32_t *Y,
+                     long long distance, uint32_t *cur_out, uint32_t *curb_out, uint32_t *seg_out, long long *n_out)
+{
+  cudaStream_t st = c->st;
+  if (n == 0) { CU(c, cudaMemsetAsync(seg_out, 0, (size_t)(nseg + 1) * 4, st)); *n_out = 0; return 0; }
+  TRY(c, c->sc.ensure(n, st));
+  uint32_t *cnt = c->sc.a32.as<uint32_t>(), *off = c->sc.b32.as<uint32_t>();
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  BK_LAUNCH(k4_mask_count, GRID1(n, 256), 256, 0, st, cur, curb, seg, n, X, Y, distance, cnt);
+  bk::exclusive_scan<uint32_t, uint32_t>(cnt, off, n, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+  unsigned long long h = 0;
+  CU(c, cudaMemcpyAsync(&h, tot, 8, cudaMemcpyDeviceToHost, st));
+  CU(c, cudaStreamSynchronize(st));
+  BK_LAUNCH(k4_mask_write, GRID1(n, 256), 256, 0, st, cur, curb, n, cnt, off, cur_out, curb_out);
+  BK_LAUNCH(k4_new_offsets, GRID1(nseg + 1, 256), 256, 0, st, seg, nseg, off, n, h, seg_out);
+  *n_out = (long long)h;
+  return 0;
+}
+
+// generic keep-compaction of (cur, curb) with new segment offsets
+static int compact_pass(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, const uint32_t *seg, long long n, int nseg, const uint32_t *keep,
+                        uint32_t *cur_out, uint32_t *curb_out, uint32_t *seg_out, uint32_t *off_keep /* n scratch */, long long *n_out)
+{
+  cudaStream_t st = c->st;
+  if (n == 0) { CU(c, cudaMemsetAsync(seg_out, 0, (size_t)(nseg + 1) * 4, st)); *n_out = 0; return 0; }
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  bk::exclusive_scan<uint32_t, uint32_t>(keep, off_keep, n, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+  unsigned long long h = 0;
+  CU(c, cudaMemcpyAsync(&h, tot, 8, cudaMemcpyDeviceToHost, st));
+  CU(c, cudaStreamSynchronize(st));
+  BK_LAUNCH(compact_write, GRID1(n, 256), 256, 0, st, cur, curb, keep, off_keep, n, cur_out, curb_out);
+  BK_LAUNCH(k4_new_offsets, GRID1(nseg + 1, 256), 256, 0, st, seg, nseg, off_keep, n, h, seg_out);
+  *n_out = (long long)h;
+  return 0;
+}
+
+// remove_isolated_pairs (src/BreakID.cc:1271-1285) for all buckets; result in c->cur1/curb1/seg1/n1
+static int remove_isolated_all(bkid_ctx *c, const uint32_t *cur0, const uint32_t *curb0, const uint32_t *seg0, long long n0, int nseg,
+                               const uint32_t *X, const uint32_t *Y, double w)
+{
+  cudaStream_t st = c->st;
+  long long distance = (long long)w;                     // double -> long at the call (src/BreakID.cc:1275)
+  size_t m = (size_t)std::max<long long>(n0, 1) * 4 + 64, sb = (size_t)(nseg + 2) * 4;
+  TRY(c, c->cur1.ensure(m, 0, st)); TRY(c, c->curb1.ensure(m, 0, st)); TRY(c, c->seg1.ensure(sb, 0, st));
+  DBuf &ca = c->sc.c32, &cb = c->sc.d32;
+  TRY(c, c->sc.ensure(n0 + 8, st));
+  TRY(c, c->tmpG.ensure(3 * sb + m * 2, 0, st));
+  uint32_t *segA = c->tmpG.as<uint32_t>(), *segB = segA + (nseg + 2);
+  uint32_t *curA = ca.as<uint32_t>(), *curbA = cb.as<uint32_t>();
+  uint32_t *work_cur = c->tmpG.as<uint32_t>() + 3 * (nseg + 2);
+  uint32_t *work_curb = work_cur + std::max<long long>(n0, 1) + 8;
+  if (n0 > 0) {
+    CU(c, cudaMemcpyAsync(work_cur, cur0, (size_t)n0 * 4, cudaMemcpyDeviceToDevice, st));
+    CU(c, cudaMemcpyAsync(work_curb, curb0, (size_t)n0 * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  TRY(c, sort_current_by(c, work_cur, n0, X, seg0, nseg));                                  // :1274
+  long long na = 0, nb2 = 0;
+  TRY(c, mask_pass(c, work_cur, work_curb, seg0, n0, nseg, X, Y, distance, curA, curbA, segA, &na));   // :1275
+  TRY(c, sort_current_by(c, curA, na, Y, segA, nseg));                                       // :1278
+  TRY(c, mask_pass(c, curA, curbA, segA, na, nseg, X, Y, distance, c->cur1.as<uint32_t>(), c->curb1.as<uint32_t>(), segB, &nb2));   // :1279
+  TRY(c, sort_current_by(c, c->cur1.as<uint32_t>(), nb2, X, segB, nseg));                    // :1282
+  CU(c, cudaMemcpyAsync(c->seg1.p, segB, (size_t)(nseg + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  c->n1 = nb2;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// clustering of the stage-1 order; fills mem_pair / mem_bucket / mem_cluster grouped by (bucket, cluster)
+// ---------------------------------------------------------------------------------------------
+static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, const uint32_t *seg, long long n, int nseg, const uint32_t *X, const uint32_t *Y, double thr_d)
+{
+  cudaStream_t st = c->st;
+  c->n2 = 0;
+  c->roots_per_bucket.assign(nseg, 0);
+  if (n == 0) return 0;
+  long long thr = (long long)thr_d;                      // long distance_threshold (src/util_cluster.cc:7)
+  TRY(c, c->sc.ensure(n + 8, st));
+  // coordinates in leaf order
+  DBuf &LX = c->tmpA, &LY = c->tmpB;
+  TRY(c, LX.ensure((size_t)n * 4 + 16, 0, st)); TRY(c, LY.ensure((size_t)n * 4 + 16, 0, st));
+  BK_LAUNCH(gather_u32, GRID1(n, 256), 256, 0, st, X, cur, n, LX.as<uint32_t>());
+  BK_LAUNCH(gather_u32, GRID1(n, 256), 256, 0, st, Y, cur, n, LY.as<uint32_t>());
+  uint64_t *key = c->sc.keys.as<uint64_t>();
+  uint32_t *val = c->sc.vals.as<uint32_t>();
+  uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>();
+  unsigned long long *stmp = c->sc.scan_tmp.as<unsigned long long>();
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  int bbits = 1; while ((1ll << bbits) < nseg + 1) ++bbits;
+  // pieces: sort by (bucket, x), cut at x gaps
+  BK_LAUNCH(ahc_key_bx, GRID1(n, 256), 256, 0, st, curb, LX.as<uint32_t>(), n, key, val);
+  bk::radix_sort_pairs(key, val, n, 0, 32 + bbits, c->sc.rt(), st);
+  BK_LAUNCH(ahc_gap_heads, GRID1(n, 256), 256, 0, st, key, n, thr, head);
+  bk::exclusive_scan<uint32_t, uint32_t>(head, hex, n, stmp, tot, st);
+  unsigned long long npiece = 0;
+  CU(c, cudaMemcpyAsync(&npiece, tot, 8, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+  int pbits = 1; while ((1ull << pbits) < npiece + 1) ++pbits;
+  // components: sort by (piece, y), cut at y gaps
+  BK_LAUNCH(ahc_key_group, GRID1(n, 256), 256, 0, st, head, hex, val, LY.as<uint32_t>(), n, key);
+  bk::radix_sort_pairs(key, val, n, 0, 32 + pbits, c->sc.rt(), st);
+  BK_LAUNCH(ahc_gap_heads, GRID1(n, 256), 256, 0, st, key, n, thr, head);
+  bk::exclusive_scan<uint32_t, uint32_t>(head, hex, n, stmp, tot, st);
+  unsigned long long ncomp64 = 0;
+  CU(c, cudaMemcpyAsync(&ncomp64, tot, 8, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+  uint32_t ncomp = (uint32_t)ncomp64;
+  int cbits = 1; while ((1ull << cbits) < ncomp64 + 1) ++cbits;
+  // leaves of a component in ascending leaf index: sort by (comp, p)
+  BK_LAUNCH(ahc_key_group, GRID1(n, 256), 256, 0, st, head, hex, val, (const uint32_t *)nullptr, n, key);
+  bk::radix_sort_pairs(key, val, n, 0, 32 + cbits, c->sc.rt(), st);
+  BK_LAUNCH(ahc_comp_heads, GRID1(n, 256), 256, 0, st, key, n, head);
+  // component tables
+  DBuf &T = c->tmpC;
+  size_t nc1 = (size_t)ncomp + 2;
+  size_t bytes = nc1 * (4 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 8 + 8 + 4 + 8 + 4 + 4) + (size_t)n * (4 + 4 + 4) + (size_t)(nseg + 2) * (4 + 4 + 4 + 4) + 4096;
+  TRY(c, T.ensure(bytes, 0, st));
+  CU(c, cudaMemsetAsync(T.p, 0, bytes, st));
+  char *bp = (char *)T.p;
+  auto take = [&](size_t b) { char *r = bp; bp += (b + 15) & ~(size_t)15; return r; };
+  uint32_t *comp_off = (uint32_t *)take(nc1 * 4), *comp_bucket = (uint32_t *)take(nc1 * 4);
+  int32_t *hi_oc = (int32_t *)take(nc1 * 4);
+  unsigned long long *pts_sz = (unsigned long long *)take(nc1 * 8), *row_sz = (unsigned long long *)take(nc1 * 8);
+  unsigned long long *pts_off = (unsigned long long *)take(nc1 * 8), *row_off = (unsigned long long *)take(nc1 * 8);
+  uint32_t *comp_nnodes = (uint32_t *)take(nc1 * 4);
+  unsigned long long *comp_pts_used = (unsigned long long *)take(nc1 * 8), *comp_row_used = (unsigned long long *)take(nc1 * 8);
+  int32_t *comp_head_j = (int32_t *)take(nc1 * 4);
+  double *comp_head_d = (double *)take(nc1 * 8);
+  int32_t *comp_flag = (int32_t *)take(nc1 * 4);
+  uint32_t *comp_cursor = (uint32_t *)take(nc1 * 4);
+  uint32_t *comp_of_point = (uint32_t *)take((size_t)n * 4);
+  uint32_t *comp_leaf = (uint32_t *)take((size_t)n * 4);
+  int32_t *lo_oc = (int32_t *)take((size_t)n * 4);
+  uint32_t *bucket_comp_off = (uint32_t *)take((size_t)(nseg + 2) * 4);
+  int32_t *bucket_flag = (int32_t *)take((size_t)(nseg + 2) * 4);
+  unsigned *merges_pb = (unsigned *)take((size_t)(nseg + 2) * 4);
+  uint32_t *bucket_first_root = (uint32_t *)take((size_t)(nseg + 2) * 4);
+  BK_LAUNCH(ahc_comp_fill, GRID1(n, 256), 256, 0, st, key, head, val, n, curb, comp_off, comp_bucket, comp_of_point);
+  CU(c, cudaMemcpyAsync(comp_leaf, val, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  { uint32_t nn = (uint32_t)n; CU(c, cudaMemcpyAsync(comp_off + ncomp, &nn, 4, cudaMemcpyHostToDevice, st)); CU(c, cudaStreamSynchronize(st)); }
+  BK_LAUNCH(ahc_comp_static, GRID1(ncomp, 128), 128, 0, st, comp_off, comp_leaf, comp_bucket, comp_of_point, seg, ncomp, lo_oc, hi_oc, pts_sz, row_sz);
+  unsigned long long *tot2 = tot + 1;
+  bk::exclusive_scan<unsigned long long, unsigned long long>(pts_sz, pts_off, ncomp, stmp, tot, st);
+  bk::exclusive_scan<unsigned long long, unsigned long long>(row_sz, row_off, ncomp, stmp, tot2, st);
+  unsigned long long pool[2] = {0, 0};
+  CU(c, cudaMemcpyAsync(pool, tot, 16, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+  if ((pool[0] * 4 + pool[1] * 12) > (100ull << 30)) return fail(c, BKID_ERR_NOMEM, "AHC component too large for the row pools");
+  BK_LAUNCH(ahc_bucket_comp_off, GRID1(nseg + 1, 128), 128, 0, st, comp_bucket, ncomp, (uint32_t)nseg, bucket_comp_off);
+  // node arrays + pools + events
+  DBuf &NB = c->tmpD;
+  size_t nn2 = (size_t)2 * n + 2;
+  size_t nbytes = nn2 * (1 + 4 + 8 + 8 + 4 + 4 + 8 + 4 + 4 + 4) + (size_t)n * (8 + 4) + pool[0] * 4 + pool[1] * 12 + 8192;
+  TRY(c, NB.ensure(nbytes, 0, st));
+  bp = (char *)NB.p;
+  AhcView v;
+  memset(&v, 0, sizeof v);
+  v.seg_off = seg; v.X = LX.as<uint32_t>(); v.Y = LY.as<uint32_t>();
+  v.comp_off = comp_off; v.comp_leaf = comp_leaf; v.comp_bucket = comp_bucket; v.lo_oc = lo_oc; v.hi_oc = hi_oc;
+  v.pts_off = pts_off; v.row_off = row_off;
+  v.node_best_d = (double *)take(nn2 * 8);
+  v.node_pts = (unsigned long long *)take(nn2 * 8); v.node_row = (unsigned long long *)take(nn2 * 8);
+  v.row_d = (double *)take(pool[1] * 8 + 8);
+  v.ev_d = (double *)take((size_t)n * 8 + 8);
+  v.node_npts = (uint32_t *)take(nn2 * 4); v.node_rowlen = (uint32_t *)take(nn2 * 4);
+  v.node_best_t = (int32_t *)take(nn2 * 4); v.node_grank = (int32_t *)take(nn2 * 4);
+  v.node_ma = (int32_t *)take(nn2 * 4); v.node_mb = (int32_t *)take(nn2 * 4);
+  v.pts_pool = (uint32_t *)take(pool[0] * 4 + 8); v.row_t = (int32_t *)take(pool[1] * 4 + 8);
+  v.ev_first = (int32_t *)take((size_t)n * 4 + 8);
+  v.node_root = (uint8_t *)take(nn2);
+  v.comp_nnodes = comp_nnodes; v.comp_pts_used = comp_pts_used; v.comp_row_used = comp_row_used;
+  v.comp_head_j = comp_head_j; v.comp_head_d = comp_head_d; v.comp_flag = comp_flag; v.comp_cursor = comp_cursor;
+  v.thr = (double)thr;
+  BK_LAUNCH(ahc_components, GRID1(ncomp, 4), 128, 0, st, v, ncomp);
+  BK_LAUNCH(ahc_bucket_flags, GRID1(ncomp, 128), 128, 0, st, comp_flag, comp_bucket, ncomp, bucket_flag);
+  BK_LAUNCH(ahc_replay, GRID1(nseg, 4), 128, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag);
+  BK_LAUNCH(ahc_bucket_exact, (unsigned)nseg, 32, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag);
+  // final roots -> clusters
+  unsigned *cnt = c->counters.as<unsigned>() + 48;
+  CU(c, cudaMemsetAsync(cnt, 0, 4, st));
+  uint64_t *rkey = c->sc.keys.as<uint64_t>();
+  uint32_t *rnode = c->sc.vals.as<uint32_t>();
+  BK_LAUNCH(ahc_final_roots, GRID1(ncomp, 128), 128, 0, st, v, ncomp, rkey, rnode, cnt, merges_pb);
+  unsigned nroot = 0;
+  CU(c, cudaMemcpyAsync(&nroot, cnt, 4, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+  std::vector<unsigned> merges(nseg);
+  std::vector<uint32_t> segh(nseg + 1);
+  CU(c, cudaMemcpyAsync(merges.data(), merges_pb, (size_t)nseg * 4, cudaMemcpyDeviceToHost, st));
+  CU(c, cudaMemcpyAsync(segh.data(), seg, (size_t)(nseg + 1) * 4, cudaMemcpyDeviceToHost, st));
+  CU(c, cudaStreamSynchronize(st));
+  for (int b = 0; b < nseg; ++b) c->roots_per_bucket[b] = (int32_t)(segh[b + 1] - segh[b]) - (int32_t)merges[b];   // print_root_nodes
+  if (nroot == 0) return sync_check(c);
+  bk::radix_sort_pairs(rkey, rnode, nroot, 0, 32 + bbits, c->sc.rt(), st);
+  uint32_t *rsize = c->sc.a32.as<uint32_t>(), *roff = c->sc.b32.as<uint32_t>(), *rhead = c->sc.e32.as<uint32_t>();
+  BK_LAUNCH(ahc_root_sizes, GRID1(nroot, 128), 128, 0, st, v, rkey, rnode, nroot, rsize, rhead);
+  BK_LAUNCH(ahc_root_firsts, GRID1(nroot, 128), 128, 0, st, rhead, nroot, rkey, bucket_first_root);
+  bk::exclusive_scan<uint32_t, uint32_t>(rsize, roff, nroot, stmp, tot, st);
+  unsigned long long nm = 0;
+  CU(c, cudaMemcpyAsync(&nm, tot, 8, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+  size_t mb = (size_t)std::max<unsigned long long>(nm, 1) * 4 + 16;
+  TRY(c, c->mem_pair.ensure(mb, 0, st)); TRY(c, c->mem_bucket.ensure(mb, 0, st)); TRY(c, c->mem_cluster.ensure(mb, 0, st));
+  TRY(c, c->tmpE.ensure(mb, 0, st));
+  BK_LAUNCH(ahc_emit, GRID1(nroot, 4), 128, 0, st, v, rkey, rnode, roff, bucket_first_root, nroot, c->tmpE.as<uint32_t>(), c->mem_cluster.as<int32_t>(), c->mem_bucket.as<uint32_t>());
+  // members are positions in the stage-1 order; translate to pair ids
+  BK_LAUNCH(gather_u32, GRID1(nm, 256), 256, 0, st, cur, c->tmpE.as<uint32_t>(), (long long)nm, c->mem_pair.as<uint32_t>());
+  c->n2 = (long long)nm;
+  return sync_check(c);
+}
+
+__global__ void fast_member_keys(const uint32_t *__restrict__ curb, const int32_t *__restrict__ cl, long long n, uint64_t *__restrict__ key, uint32_t *__restrict__ val)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) { key[p] = ((uint64_t)curb[p] << 32) | (uint32_t)cl[p]; val[p] = (uint32_t)p; }
+}
+__global__ void fast_member_write(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, const uint32_t *__restrict__ cur, long long n,
+                                  uint32_t *__restrict__ mem_pair, uint32_t *__restrict__ mem_bucket, int32_t *__restrict__ mem_cluster)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) { mem_pair[p] = cur[val[p]]; mem_bucket[p] = (uint32_t)(key[p] >> 32); mem_cluster[p] = (int32_t)(key[p] & 0xffffffffu); }
+}
+
+static int cluster_fast(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, const uint32_t *seg, long long n, int nseg, const uint32_t *X, const uint32_t *Y, double w,
+                        long long np0)
+{
+  cudaStream_t st = c->st;
+  c->n2 = 0;
+  c->roots_per_bucket.assign(nseg, 0);
+  if (n == 0) return 0;
+  int min_reads = c->prm.min_reads;
+  TRY(c, c->sc.ensure(std::max(n, np0) + 8, st));
+  size_t m = (size_t)n * 4 + 64, sb = (size_t)(nseg + 2) * 4;
+  // tmpA..tmpF belong to the sort replay; the sweep state lives in tmpG
+  TRY(c, c->tmpG.ensure(4 * m + 4 * sb + (size_t)np0 * 8 + 64, 0, st));
+  uint32_t *curA = c->tmpG.as<uint32_t>(), *curbA = curA + n + 8, *curB = curbA + n + 8, *curbB = curB + n + 8;
+  uint32_t *segA = curbB + n + 8, *segB = segA + nseg + 2;
+  uint32_t *k1 = segB + nseg + 2, *k2 = k1 + np0;
+  uint32_t *keep = c->sc.a32.as<uint32_t>(), *off = c->sc.b32.as<uint32_t>();
+  long long na = 0, nb2 = 0, nc = 0;
+  BK_LAUNCH(fast_sweep, GRID1(nseg, 64), 64, 0, st, cur, seg, (uint32_t)nseg, X, w, min_reads, k1, keep);                       // :1056-1087
+  TRY(c, compact_pass(c, cur, curb, seg, n, nseg, keep, curA, curbA, segA, off, &na));
+  TRY(c, sort_current_by(c, curA, na, Y, segA, nseg));                                                                         // :1091
+  if (na > 0) BK_LAUNCH(fast_sweep, GRID1(nseg, 64), 64, 0, st, curA, segA, (uint32_t)nseg, Y, w, min_reads, k2, keep);         // :1093-1123
+  TRY(c, compact_pass(c, curA, curbA, segA, na, nseg, keep, curB, curbB, segB, off, &nb2));
+  TRY(c, sort_current_by(c, curB, nb2, X, segB, nseg));                                                                        // :1127
+  if (nb2 == 0) return sync_check(c);
+  int32_t *cl = (int32_t *)c->sc.c32.as<uint32_t>();
+  int32_t *ncl = (int32_t *)c->sc.d32.as<uint32_t>();
+  BK_LAUNCH(fast_number, GRID1(nseg, 64), 64, 0, st, curB, segB, (uint32_t)nseg, k1, k2, min_reads, cl, keep, ncl);             // :1129-1157
+  CU(c, cudaMemcpyAsync(c->roots_per_bucket.data(), ncl, (size_t)nseg * 4, cudaMemcpyDeviceToHost, st));
+  // drop ids seen fewer than min_reads times, group the rest by (bucket, cluster)
+  uint32_t *curC = curA, *curbC = curbA;     // reuse
+  // compact the cluster ids alongside: write cl through the same offsets
+  bk::exclusive_scan<uint32_t, uint32_t>(keep, off, nb2, c->sc.scan_tmp.as<unsigned long long>(), (unsigned long long *)(c->counters.as<unsigned>() + 32), st);
+  unsigned long long h = 0;
+  CU(c, cudaMemcpyAsync(&h, c->counters.as<unsigned>() + 32, 8, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+  nc = (long long)h;
+  if (nc == 0) return 0;
+  BK_LAUNCH(compact_write, GRID1(nb2, 256), 256, 0, st, curB, curbB, keep, off, nb2, curC, curbC);
+  uint32_t *clC = c->sc.e32.as<uint32_t>();
+  BK_LAUNCH(compact_write, GRID1(nb2, 256), 256, 0, st, (const uint32_t *)cl, curbB, keep, off, nb2, clC, c->sc.vals_alt.as<uint32_t>() /* unused copy */);
+  uint64_t *key = c->sc.keys.as<uint64_t>();
+  uint32_t *val = c->sc.vals.as<uint32_t>();
+  BK_LAUNCH(fast_member_keys, GRID1(nc, 256), 256, 0, st, curbC, (const int32_t *)clC, nc, key, val);
+  int bbits = 1; while ((1ll << bbits) < nseg + 1) ++bbits;
+  bk::radix_sort_pairs(key, val, nc, 0, 32 + bbits, c->sc.rt(), st);
+  size_t mb = (size_t)nc * 4 + 16;
+  TRY(c, c->mem_pair.ensure(mb, 0, st)); TRY(c, c->mem_bucket.ensure(mb, 0, st)); TRY(c, c->mem_cluster.ensure(mb, 0, st));
+  BK_LAUNCH(fast_member_write, GRID1(nc, 256), 256, 0, st, key, val, curC, nc, c->mem_pair.as<uint32_t>(), c->mem_bucket.as<uint32_t>(), c->mem_cluster.as<int32_t>());
+  c->n2 = nc;
+  return sync_check(c);
+}
+
+// =============================================================================================
+// exported C ABI
+// =============================================================================================
+extern "C" {
+
+int bkid_abi_version(void) { return BKID_ABI_VERSION; }
+
+const char *bkid_last_error(const bkid_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+void bkid_default_params(bkid_params *p)
+{
+  p->qual = 20; p->times = 2; p->fast = 0; p->min_reads = 2; p->bp_pos_error = 2; p->mismatch_num = 10; p->sd_mult = 3; p->reserved = 0;
+}
+
+bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *params)
+{
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { g_create_err = std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e); return nullptr; }
+  if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return nullptr; }
+  if (!hdr || hdr->n_targets < 0) { g_create_err = "bad header"; return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_create_err = "cudaSetDevice failed"; return nullptr; }
+  bkid_ctx *c = new bkid_ctx();
+  c->device = device;
+  if (params) c->prm = *params; else bkid_default_params(&c->prm);
+  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { g_create_err = "cudaStreamCreate failed"; delete c; return nullptr; }
+  for (auto &ev : c->ev) cudaEventCreate(&ev);
+  c->nt = hdr->n_targets;
+  for (int i = 0; i < c->nt; ++i) { c->target_len.push_back(hdr->target_len[i]); c->names.emplace_back(hdr->target_name[i]); }
+  int nt = c->nt, m = nt + 1;
+  std::vector<uint32_t> cum(nt + 1, 0);
+  for (int i = 0; i < nt; ++i) cum[i + 1] = cum[i] + c->target_len[i];                 // uint32 wrap, src/util_bam.cc:61-64
+  // rank of every "A_B" bucket name in std::map<string> order (src/BreakID.cc:1500-1512); index 0 = "*"
+  std::vector<std::pair<std::string, int>> bn;
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b < m; ++b) bn.push_back({(a ? c->names[a - 1] : std::string("*")) + "_" + (b ? c->names[b - 1] : std::string("*")), a * m + b});
+  std::sort(bn.begin(), bn.end());
+  std::vector<int32_t> rank((size_t)m * m);
+  for (size_t r = 0; r < bn.size(); ++r) rank[bn[r].second] = (int32_t)r;
+  std::vector<uint64_t> canon(nt ? nt : 1);
+  for (int i = 0; i < nt; ++i) canon[i] = chr_code((const uint8_t *)c->names[i].data(), (uint32_t)c->names[i].size());
+  bool ok = c->d_cum.ensure((size_t)(nt + 1) * 4, 0, c->st) == 0 && c->d_bucket_rank.ensure(rank.size() * 4, 0, c->st) == 0 &&
+            c->d_canon.ensure(canon.size() * 8, 0, c->st) == 0 && c->counters.ensure(1024, 0, c->st) == 0 &&
+            c->d_nib_ptr.ensure((size_t)(nt + 1) * 8, 0, c->st) == 0 && c->d_nib_len.ensure((size_t)(nt + 1) * 8, 0, c->st) == 0;
+  if (!ok) { g_create_err = "device allocation failed: " + g_last_cuda_err; delete c; return nullptr; }
+  cudaMemcpy(c->d_cum.p, cum.data(), (size_t)(nt + 1) * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_bucket_rank.p, rank.data(), rank.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_canon.p, canon.data(), canon.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemset(c->d_nib_ptr.p, 0, (size_t)(nt + 1) * 8);
+  cudaMemset(c->d_nib_len.p, 0, (size_t)(nt + 1) * 8);
+  c->nib.resize(nt); c->nib_len.assign(nt, 0);
+  cudaFuncSetAttribute(sd_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_BLOCK * 9);
+  memset(&c->tm, 0, sizeof c->tm);
+  if (cudaGetLastError() != cudaSuccess) { g_create_err = "CUDA error during create"; delete c; return nullptr; }
+  return c;
+}
+
+void bkid_destroy(bkid_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->mtid, &c->mpos, &c->isize, &c->endpos, &c->nh, &c->cls,
+                  &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
+                  &c->cand_idx, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
+                  &c->mem_bucket, &c->mem_cluster, &c->clusters, &c->clusters_out, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG})
+    b->release();
+  for (auto &b : c->nib) b.release();
+  c->sc.release();
+  for (auto &ev : c->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->st);
+  delete c;
+}
+
+static void invalidate(bkid_ctx *c) { c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; }
+
+static int reserve_impl(bkid_ctx *c, long long n, long long n_sa, long long n_cig, long long sa_b, long long oc_b)
+{
+  cudaStream_t st = c->st;
+  if (c->borrowed) return fail(c, BKID_ERR_ARG, "context holds borrowed device columns; bkid_reset first");
+  size_t k = (size_t)c->n;
+  TRY(c, c->flag.ensure((size_t)n * 2 + 64, k * 2, st)); TRY(c, c->mapq.ensure((size_t)n + 64, k, st));
+  TRY(c, c->tid.ensure((size_t)n * 4 + 64, k * 4, st)); TRY(c, c->pos.ensure((size_t)n * 4 + 64, k * 4, st));
+  TRY(c, c->mtid.ensure((size_t)n * 4 + 64, k * 4, st)); TRY(c, c->mpos.ensure((size_t)n * 4 + 64, k * 4, st));
+  TRY(c, c->isize.ensure((size_t)n * 4 + 64, k * 4, st)); TRY(c, c->endpos.ensure((size_t)n * 4 + 64, k * 4, st));
+  TRY(c, c->nh.ensure((size_t)n * 16 + 64, k * 16, st));
+  size_t s = (size_t)c->n_sa;
+  TRY(c, c->sa_rec.ensure((size_t)n_sa * 4 + 64, s * 4, st));
+  TRY(c, c->cig_off.ensure((size_t)(n_sa + 1) * 4 + 64, (s + 1) * 4, st));
+  TRY(c, c->sa_off.ensure((size_t)(n_sa + 1) * 4 + 64, (s + 1) * 4, st));
+  TRY(c, c->oc_off.ensure((size_t)(n_sa + 1) * 4 + 64, (s + 1) * 4, st));
+  TRY(c, c->cig_ops.ensure((size_t)n_cig * 4 + 64, (size_t)c->n_cig * 4, st));
+  TRY(c, c->sa_txt.ensure((size_t)sa_b + 64, (size_t)c->sa_bytes, st));
+  TRY(c, c->oc_txt.ensure((size_t)oc_b + 64, (size_t)c->oc_bytes, st));
+  return 0;
+}
+
+int bkid_reserve(bkid_ctx *c, int64_t n, int64_t n_sa, int64_t n_cig, int64_t sa_b, int64_t oc_b)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  return reserve_impl(c, std::max<long long>(n, c->n), std::max<long long>(n_sa, c->n_sa), std::max<long long>(n_cig, c->n_cig),
+                      std::max<long long>(sa_b, c->sa_bytes), std::max<long long>(oc_b, c->oc_bytes));
+}
+
+__global__ void add_offset_u32(uint32_t *p, long long n, uint32_t d)
+{
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += d;
+}
+
+static void set_ptrs(bkid_ctx *c)
+{
+  c->p_flag = c->flag.as<uint16_t>(); c->p_mapq = c->mapq.as<uint8_t>(); c->p_tid = c->tid.as<int32_t>(); c->p_pos = c->pos.as<int32_t>();
+  c->p_mtid = c->mtid.as<int32_t>(); c->p_mpos = c->mpos.as<int32_t>(); c->p_isize = c->isize.as<int32_t>(); c->p_endpos = c->endpos.as<int32_t>();
+  c->p_nh = c->nh.as<uint64_t>();
+  c->p_sa_rec = c->sa_rec.as<uint32_t>(); c->p_cig_off = c->cig_off.as<uint32_t>(); c->p_cig_ops = c->cig_ops.as<uint32_t>();
+  c->p_sa_off = c->sa_off.as<uint32_t>(); c->p_sa_txt = c->sa_txt.as<uint8_t>(); c->p_oc_off = c->oc_off.as<uint32_t>(); c->p_oc_txt = c->oc_txt.as<uint8_t>();
+}
+
+static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
+{
+  if (!c || !b || b->n < 0 || b->n_sa < 0) return c ? fail(c, BKID_ERR_ARG, "bad batch") : BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->st;
+  if ((unsigned long long)(c->n + b->n) >= 0xffffffffull) return fail(c, BKID_ERR_ARG, "more than 2^32-1 records per context");
+  invalidate(c);
+  cudaEventRecord(c->ev[0], st);
+  long long n0 = c->n, s0 = c->n_sa;
+  // side-table sizes need the last offsets of the incoming batch
+  uint32_t ncig = 0, nsa_b = 0, noc_b = 0;
+  if (b->n_sa > 0) {
+    if (kind == cudaMemcpyHostToDevice) { ncig = b->cig_off[b->n_sa]; nsa_b = b->sa_off[b->n_sa]; noc_b = b->oc_off[b->n_sa]; }
+    else {
+      CU(c, cudaMemcpy(&ncig, b->cig_off + b->n_sa, 4, cudaMemcpyDeviceToHost));
+      CU(c, cudaMemcpy(&nsa_b, b->sa_off + b->n_sa, 4, cudaMemcpyDeviceToHost));
+      CU(c, cudaMemcpy(&noc_b, b->oc_off + b->n_sa, 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  TRY(c, reserve_impl(c, n0 + b->n, s0 + b->n_sa, c->n_cig + ncig, c->sa_bytes + nsa_b, c->oc_bytes + noc_b));
+  size_t n = (size_t)b->n;
+  if (n) {
+    CU(c, cudaMemcpyAsync(c->flag.as<uint16_t>() + n0, b->flag, n * 2, kind, st));
+    CU(c, cudaMemcpyAsync(c->mapq.as<uint8_t>() + n0, b->mapq, n, kind, st));
+    CU(c, cudaMemcpyAsync(c->tid.as<int32_t>() + n0, b->tid, n * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->pos.as<int32_t>() + n0, b->pos, n * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->mtid.as<int32_t>() + n0, b->mtid, n * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->mpos.as<int32_t>() + n0, b->mpos, n * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->isize.as<int32_t>() + n0, b->isize, n * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->endpos.as<int32_t>() + n0, b->endpos, n * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->nh.as<uint64_t>() + 2 * n0, b->name_hash, n * 16, kind, st));
+  }
+  size_t ns = (size_t)b->n_sa;
+  if (ns) {
+    CU(c, cudaMemcpyAsync(c->sa_rec.as<uint32_t>() + s0, b->sa_rec, ns * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->cig_off.as<uint32_t>() + s0, b->cig_off, (ns + 1) * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->sa_off.as<uint32_t>() + s0, b->sa_off, (ns + 1) * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->oc_off.as<uint32_t>() + s0, b->oc_off, (ns + 1) * 4, kind, st));
+    if (ncig) CU(c, cudaMemcpyAsync(c->cig_ops.as<uint32_t>() + c->n_cig, b->cig_ops, (size_t)ncig * 4, kind, st));
+    if (nsa_b) CU(c, cudaMemcpyAsync(c->sa_txt.as<uint8_t>() + c->sa_bytes, b->sa_txt, nsa_b, kind, st));
+    if (noc_b) CU(c, cudaMemcpyAsync(c->oc_txt.as<uint8_t>() + c->oc_bytes, b->oc_txt, noc_b, kind, st));
+    if (n0) BK_LAUNCH(add_offset_u32, GRID1(ns, 256), 256, 0, st, c->sa_rec.as<uint32_t>() + s0, (long long)ns, (uint32_t)n0);
+    if (c->n_cig) BK_LAUNCH(add_offset_u32, GRID1(ns + 1, 256), 256, 0, st, c->cig_off.as<uint32_t>() + s0, (long long)ns + 1, (uint32_t)c->n_cig);
+    if (c->sa_bytes) BK_LAUNCH(add_offset_u32, GRID1(ns + 1, 256), 256, 0, st, c->sa_off.as<uint32_t>() + s0, (long long)ns + 1, (uint32_t)c->sa_bytes);
+    if (c->oc_bytes) BK_LAUNCH(add_offset_u32, GRID1(ns + 1, 256), 256, 0, st, c->oc_off.as<uint32_t>() + s0, (long long)ns + 1, (uint32_t)c->oc_bytes);
+  } else if (s0 == 0) {
+    CU(c, cudaMemsetAsync(c->cig_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->sa_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->oc_off.p, 0, 4, st));
+  }
+  c->n += b->n; c->n_sa += b->n_sa; c->n_cig += ncig; c->sa_bytes += nsa_b; c->oc_bytes += noc_b;
+  set_ptrs(c);
+  cudaEventRecord(c->ev[1], st);
+  TRY(c, sync_check(c));
+  float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->tm.h2d += ms;
+  return 0;
+}
+
+int bkid_push_batch(bkid_ctx *c, const bkid_batch *b) { return push_impl(c, b, cudaMemcpyHostToDevice); }
+
+int bkid_push_batch_device(bkid_ctx *c, const bkid_batch *b)
+{
+  if (!c || !b) return BKID_ERR_ARG;
+  if (c->n == 0 && !c->borrowed && c->flag.p == nullptr) {
+    // adopt the caller's device columns without copying (already-resident input)
+    cudaSetDevice(c->device);
+    if ((unsigned long long)b->n >= 0xffffffffull) return fail(c, BKID_ERR_ARG, "more than 2^32-1 records per context");
+    invalidate(c);
+    c->borrowed = true;
+    c->n = b->n; c->n_sa = b->n_sa;
+    c->p_flag = b->flag; c->p_mapq = b->mapq; c->p_tid = b->tid; c->p_pos = b->pos; c->p_mtid = b->mtid; c->p_mpos = b->mpos;
+    c->p_isize = b->isize; c->p_endpos = b->endpos; c->p_nh = b->name_hash;
+    c->p_sa_rec = b->sa_rec; c->p_cig_off = b->cig_off; c->p_cig_ops = b->cig_ops; c->p_sa_off = b->sa_off; c->p_sa_txt = b->sa_txt;
+    c->p_oc_off = b->oc_off; c->p_oc_txt = b->oc_txt;
+    return 0;
+  }
+  return push_impl(c, b, cudaMemcpyDeviceToDevice);
+}
+
+int bkid_reset(bkid_ctx *c)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  c->n = c->n_sa = c->n_cig = c->sa_bytes = c->oc_bytes = 0;
+  c->borrowed = false;
+  set_ptrs(c);
+  invalidate(c);
+  memset(&c->tm, 0, sizeof c->tm);
+  return 0;
+}
+
+static int classify_impl(bkid_ctx *c)
+{
+  if (c->classified) return 0;
+  cudaStream_t st = c->st;
+  long long n = c->n;
+  int ntiles = div_up(std::max<long long>(n, 1), K1_TILE);
+  TRY(c, c->cls.ensure((size_t)n + 64, 0, st));
+  TRY(c, c->tile_cand.ensure((size_t)(ntiles + 1) * 4 * 2 + 64, 0, st));
+  unsigned long long *g = (unsigned long long *)c->counters.as<unsigned>();     // [0] sum |isize|, [1] count
+  CU(c, cudaMemsetAsync(g, 0, 64, st));
+  cudaEventRecord(c->ev[2], st);
+  if (n > 0)
+    BK_LAUNCH(k1_classify, (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, n, c->prm.qual, c->cls.as<uint8_t>(), c->tile_cand.as<uint32_t>(), g, g + 1);
+  cudaEventRecord(c->ev[3], st);
+  unsigned long long h[2] = {0, 0};
+  CU(c, cudaMemcpyAsync(h, g, 16, cudaMemcpyDeviceToHost, st));
+  TRY(c, sync_check(c));
+  float ms = 0; cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+  c->tm.classify = ms;
+  c->sum_abs = (long long)h[0]; c->cnt_insert = (long long)h[1];
+  c->classified = true;
+  c->tm.n_records = n;
+  return 0;
+}
+
+int bkid_insert_stats(bkid_ctx *c, double *mean, double *sd)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  c->err.clear();
+  TRY(c, classify_impl(c));
+  if (!c->have_stats) {
+    cudaStream_t st = c->st;
+    long long n = c->n;
+    c->mean = (double)c->sum_abs / (double)c->cnt_insert;                     // src/BreakID.cc:1941
+    int nb = div_up(std::max<long long>(n, 1), SD_BLOCK);
+    TRY(c, c->tmpA.ensure((size_t)nb * (8 + SD_K * 4 + 4 + 8) + 256, 0, st));
+    char *bp = (char *)c->tmpA.p;
+    long long *blkF = (long long *)bp; bp += (size_t)nb * 8;
+    double *blkA = (double *)bp; bp += (size_t)nb * 8;
+    uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
+    uint32_t *blkN = (uint32_t *)bp;
+    long long *out = (long long *)(c->counters.as<unsigned>() + 8);
+    cudaEventRecord(c->ev[4], st);
+    long long h[2] = {0, 0};
+    if (n > 0 && c->cnt_insert > 0) {
+      BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, blkF, blkCum, blkN, blkA);
+      BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, out);
+      CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
+      TRY(c, sync_check(c));
+      if (h[1]) {                                                              // total left the closed-form regime: literal replay
+        BK_LAUNCH(sd_sequential, 1, 1, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, out);
+        CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
+        TRY(c, sync_check(c));
+      }
+    }
+    cudaEventRecord(c->ev[5], st);
+    TRY(c, sync_check(c));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+    c->tm.insert_stats = ms;
+    c->sd_total = h[0];
+    c->sd = sqrt((double)c->sd_total / (double)c->cnt_insert);                // :1946
+    c->have_stats = true;
+  }
+  if (mean) *mean = c->mean;
+  if (sd) *sd = c->sd;
+  return 0;
+}
+
+int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  c->err.clear();
+  TRY(c, classify_impl(c));
+  cudaStream_t st = c->st;
+  long long n = c->n;
+  int ntiles = div_up(std::max<long long>(n, 1), K1_TILE);
+  uint32_t *tile_cand = c->tile_cand.as<uint32_t>(), *tile_off = tile_cand + ntiles + 1;
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  cudaEventRecord(c->ev[6], st);
+  TRY(c, c->sc.ensure(ntiles + 8, st));
+  unsigned long long nc = 0;
+  if (n > 0) {
+    bk::exclusive_scan<uint32_t, uint32_t>(tile_cand, tile_off, ntiles, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    CU(c, cudaMemcpyAsync(&nc, tot, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+  }
+  c->n_cand = (long long)nc;
+  c->np0 = 0; c->nb = 0;
+  if (nc > 0) {
+    TRY(c, c->cand_idx.ensure((size_t)nc * 4 + 64, 0, st));
+    BK_LAUNCH(k1_compact, (unsigned)ntiles, K1_THREADS, 0, st, c->cls.as<uint8_t>(), n, tile_off, c->cand_idx.as<uint32_t>());
+    TRY(c, c->sc.ensure((long long)nc + 8, st));
+    uint64_t *key = c->sc.keys.as<uint64_t>();
+    uint32_t *val = c->sc.vals.as<uint32_t>();
+    BK_LAUNCH(k2_gather_keys, GRID1(nc, 256), 256, 0, st, c->cand_idx.as<uint32_t>(), (long long)nc, c->p_nh, key, val);
+    bk::radix_sort_pairs(key, val, (long long)nc, 0, 64, c->sc.rt(), st);
+    uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
+    int *errf = (int *)(c->counters.as<unsigned>() + 40);
+    CU(c, cudaMemsetAsync(errf, 0, 4, st));
+    BK_LAUNCH(k2_run_heads, GRID1(nc, 256), 256, 0, st, key, val, (long long)nc, c->p_nh, head, errf);
+    bk::exclusive_scan<uint32_t, uint32_t>(head, hex, (long long)nc, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    BK_LAUNCH(k2_run_starts, GRID1(nc, 256), 256, 0, st, head, hex, (long long)nc, rstart);
+    // emit (unordered), then order by (bucket rank, index of the second-seen mate)
+    size_t maxp = (size_t)nc / 2 + 1;
+    TRY(c, c->pairs_tmp.ensure(maxp * sizeof(bkid_pair), 0, st));
+    TRY(c, c->pairs0.ensure(maxp * sizeof(bkid_pair), 0, st));
+    TRY(c, c->tmpA.ensure(maxp * 8 + 64, 0, st)); TRY(c, c->tmpB.ensure(maxp * 4 + 64, 0, st));
+    unsigned long long *pcount = tot + 1;
+    CU(c, cudaMemsetAsync(pcount, 0, 8, st));
+    unsigned long long *pkey = c->tmpA.as<unsigned long long>();
+    uint32_t *pslot = c->tmpB.as<uint32_t>();
+    BK_LAUNCH(k2_emit_pairs, GRID1(nc, 256), 256, 0, st, val, head, hex, rstart, (long long)nc, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_mtid, c->p_mpos,
+              c->p_nh, c->d_cum.as<uint32_t>(), c->nt, c->d_bucket_rank.as<int32_t>(), w, c->pairs_tmp.as<bkid_pair>(), pkey, pslot, pcount);
+    unsigned long long np = 0; int herr = 0;
+    CU(c, cudaMemcpyAsync(&np, pcount, 8, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(&herr, errf, 4, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    if (herr) return fail(c, BKID_ERR_HASH, "two different read names share a 64-bit hash prefix");
+    cudaEventRecord(c->ev[7], st);
+    c->np0 = (long long)np;
+    if (np > 0) {
+      // keys were written into tmpA (uint64) -- sort with slot payload; reuse the scratch alt buffers
+      TRY(c, c->sc.ensure((long long)std::max<unsigned long long>(np, nc) + 8, st));
+      int rbits = 1; while ((1ll << rbits) < (long long)(c->nt + 1) * (c->nt + 1) + 1) ++rbits;
+      bk::radix_sort_pairs((uint64_t *)pkey, pslot, (long long)np, 0, 32 + rbits, c->sc.rt(), st);
+      uint32_t *bh = c->sc.a32.as<uint32_t>(), *bhx = c->sc.b32.as<uint32_t>();
+      BK_LAUNCH(k2_gather_pairs, GRID1(np, 256), 256, 0, st, c->pairs_tmp.as<bkid_pair>(), pslot, pkey, (long long)np, c->pairs0.as<bkid_pair>(), bh);
+      bk::exclusive_scan<uint32_t, uint32_t>(bh, bhx, (long long)np, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+      unsigned long long nbk = 0;
+      CU(c, cudaMemcpyAsync(&nbk, tot, 8, cudaMemcpyDeviceToHost, st));
+      TRY(c, sync_check(c));
+      c->nb = (int)nbk;
+      TRY(c, c->bucket_off0.ensure((size_t)(nbk + 2) * 4, 0, st));
+      BK_LAUNCH(k2_bucket_ids, GRID1(np, 256), 256, 0, st, c->pairs0.as<bkid_pair>(), bh, bhx, (long long)np, c->bucket_off0.as<uint32_t>());
+      uint32_t npu = (uint32_t)np;
+      CU(c, cudaMemcpyAsync(c->bucket_off0.as<uint32_t>() + nbk, &npu, 4, cudaMemcpyHostToDevice, st));
+      TRY(c, c->X.ensure((size_t)np * 4 + 64, 0, st)); TRY(c, c->Y.ensure((size_t)np * 4 + 64, 0, st)); TRY(c, c->bucket_of_pair.ensure((size_t)np * 4 + 64, 0, st));
+      BK_LAUNCH(pair_xy, GRID1(np, 256), 256, 0, st, c->pairs0.as<bkid_pair>(), (long long)np, c->X.as<uint32_t>(), c->Y.as<uint32_t>(), c->bucket_of_pair.as<uint32_t>());
+    }
+  } else cudaEventRecord(c->ev[7], st);
+  cudaEventRecord(c->ev[8], st);
+  TRY(c, sync_check(c));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]); c->tm.join = ms;
+  cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); c->tm.bucket_sort = ms;
+  c->tm.n_candidates = c->n_cand; c->tm.n_pairs = c->np0;
+  c->scanned = true; c->clustered = c->refined = false;
+  if (n_pairs) *n_pairs = c->np0;
+  return 0;
+}
+
+int bkid_cluster(bkid_ctx *c, double dist, int mode, int64_t *n_clusters)
+{
+  if (!c) return BKID_ERR_ARG;
+  if (!c->scanned) return fail(c, BKID_ERR_ARG, "bkid_cluster before bkid_scan");
+  cudaSetDevice(c->device);
+  c->err.clear();
+  cudaStream_t st = c->st;
+  c->n1 = c->n2 = 0; c->n_clusters = 0;
+  cudaEventRecord(c->ev[9], st);
+  if (c->np0 > 0) {
+    long long np = c->np0;
+    TRY(c, c->sc.ensure(np + 8, st));
+    // initial order = scan emission order (already grouped by bucket)
+    TRY(c, c->tmpB.ensure((size_t)np * 4 + 64, 0, st));
+    uint32_t *cur0 = c->tmpB.as<uint32_t>();
+    BK_LAUNCH(iota_u32, GRID1(np, 256), 256, 0, st, cur0, np);
+    // tmpB is used by nothing inside remove_isolated_all except via explicit arguments
+    TRY(c, remove_isolated_all(c, cur0, c->bucket_of_pair.as<uint32_t>(), c->bucket_off0.as<uint32_t>(), np, c->nb, c->X.as<uint32_t>(), c->Y.as<uint32_t>(), dist));
+  }
+  cudaEventRecord(c->ev[10], st);
+  if (c->n1 > 0) {
+    if (mode) TRY(c, cluster_fast(c, c->cur1.as<uint32_t>(), c->curb1.as<uint32_t>(), c->seg1.as<uint32_t>(), c->n1, c->nb, c->X.as<uint32_t>(), c->Y.as<uint32_t>(), dist, c->np0));
+    else TRY(c, cluster_ahc(c, c->cur1.as<uint32_t>(), c->curb1.as<uint32_t>(), c->seg1.as<uint32_t>(), c->n1, c->nb, c->X.as<uint32_t>(), c->Y.as<uint32_t>(), dist));
+  }
+  cudaEventRecord(c->ev[11], st);
+  // K6 summary
+  if (c->n2 > 0) {
+    long long nm = c->n2;
+    TRY(c, c->sc.ensure(nm + 8, st));
+    uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *start = c->sc.c32.as<uint32_t>(), *keep = c->sc.d32.as<uint32_t>(), *koff = c->sc.e32.as<uint32_t>();
+    unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+    BK_LAUNCH(k6_cluster_heads, GRID1(nm, 256), 256, 0, st, c->mem_bucket.as<uint32_t>(), c->mem_cluster.as<int32_t>(), nm, head);
+    bk::exclusive_scan<uint32_t, uint32_t>(head, hex, nm, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    unsigned long long ncl = 0;
+    CU(c, cudaMemcpyAsync(&ncl, tot, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    BK_LAUNCH(k6_cluster_starts, GRID1(nm, 256), 256, 0, st, head, hex, nm, start);
+    TRY(c, c->clusters.ensure((size_t)(ncl + 1) * sizeof(bkid_cluster_rec), 0, st));
+    TRY(c, c->clusters_out.ensure((size_t)(ncl + 1) * sizeof(bkid_cluster_rec), 0, st));
+    BK_LAUNCH(k6_summarize, GRID1(ncl, 128), 128, 0, st, c->pairs0.as<bkid_pair>(), c->mem_pair.as<uint32_t>(), c->mem_cluster.as<int32_t>(), start, (uint32_t)ncl, nm, dist,
+              c->clusters_out.as<bkid_cluster_rec>(), keep);
+    bk::exclusive_scan<uint32_t, uint32_t>(keep, koff, (long long)ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    unsigned long long nk = 0;
+    CU(c, cudaMemcpyAsync(&nk, tot, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    BK_LAUNCH(compact_clusters, GRID1(ncl, 128), 128, 0, st, c->clusters_out.as<bkid_cluster_rec>(), keep, koff, (uint32_t)ncl, c->clusters.as<bkid_cluster_rec>());
+    c->n_clusters = (long long)nk;
+    c->tm.n_clustered = nm;
+  }
+  cudaEventRecord(c->ev[12], st);
+  TRY(c, sync_check(c));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]); c->tm.mask = ms;
+  cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]); c->tm.cluster = ms;
+  cudaEventElapsedTime(&ms, c->ev[11], c->ev[12]); c->tm.summarize = ms;
+  c->tm.n_masked = c->n1; c->tm.n_clusters = c->n_clusters;
+  c->clustered = true; c->refined = false;
+  if (n_clusters) *n_clusters = c->n_clusters;
+  return 0;
+}
+
+int bkid_set_nib(bkid_ctx *c, int32_t tid, const uint8_t *packed, uint64_t n_bases)
+{
+  if (!c || tid < 0 || tid >= c->nt) return c ? fail(c, BKID_ERR_ARG, "bad tid") : BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  size_t bytes = (size_t)((n_bases + 1) / 2);
+  TRY(c, c->nib[tid].ensure(bytes + 64, 0, c->st));
+  CU(c, cudaMemcpyAsync(c->nib[tid].p, packed, bytes, cudaMemcpyHostToDevice, c->st));
+  c->nib_len[tid] = n_bases;
+  void *p = c->nib[tid].p;
+  CU(c, cudaMemcpyAsync((char *)c->d_nib_ptr.p + (size_t)tid * 8, &p, 8, cudaMemcpyHostToDevice, c->st));
+  CU(c, cudaMemcpyAsync((char *)c->d_nib_len.p + (size_t)tid * 8, &n_bases, 8, cudaMemcpyHostToDevice, c->st));
+  return sync_check(c);
+}
+
+int bkid_refine(bkid_ctx *c, double dist, int64_t *n_called)
+{
+  if (!c) return BKID_ERR_ARG;
+  if (!c->clustered) return fail(c, BKID_ERR_ARG, "bkid_refine before bkid_cluster");
+  cudaSetDevice(c->device);
+  c->err.clear();
+  cudaStream_t st = c->st;
+  c->n_called = 0;
+  cudaEventRecord(c->ev[13], st);
+  uint32_t ncl = (uint32_t)c->n_clusters;
+  if (ncl > 0) {
+    // K7a evidence rows for every SA record
+    TRY(c, c->tmpA.ensure((size_t)(c->n_sa + 1) * sizeof(EvRow), 0, st));
+    EvRow *rows = c->tmpA.as<EvRow>();
+    if (c->n_sa > 0)
+      BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->p_flag, c->p_tid, c->p_pos, c->p_cig_off, c->p_cig_ops, c->p_sa_off, c->p_sa_txt,
+                c->p_oc_off, c->p_oc_txt, c->prm.mismatch_num, rows);
+    int *mx = (int *)(c->counters.as<unsigned>() + 44);
+    CU(c, cudaMemsetAsync(mx, 0, 4, st));
+    if (c->n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, st, c->p_pos, c->p_endpos, c->n, mx);
+    int maxspan = 0;
+    CU(c, cudaMemcpyAsync(&maxspan, mx, 4, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    cudaEventRecord(c->ev[14], st);
+    RefineView v;
+    v.n = c->n; v.flag = c->p_flag; v.cls = c->cls.as<uint8_t>(); v.tid = c->p_tid; v.pos = c->p_pos; v.endpos = c->p_endpos; v.nh = c->p_nh;
+    v.n_sa = c->n_sa; v.sa_rec = c->p_sa_rec; v.rows = rows; v.maxspan = maxspan + 1;
+    v.canon = c->d_canon.as<uint64_t>(); v.nt = c->nt;
+    v.nib = (const uint8_t *const *)c->d_nib_ptr.p; v.nib_len = c->d_nib_len.as<uint64_t>();
+    TRY(c, c->sc.ensure((long long)ncl + 8, st));
+    TRY(c, c->tmpB.ensure((size_t)(ncl + 1) * sizeof(ClusterWork), 0, st));
+    ClusterWork *work = c->tmpB.as<ClusterWork>();
+    uint32_t *evcap = c->sc.a32.as<uint32_t>(), *evoff = c->sc.b32.as<uint32_t>(), *entcnt = c->sc.c32.as<uint32_t>(), *entoff = c->sc.d32.as<uint32_t>(), *valid = c->sc.e32.as<uint32_t>();
+    unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+    int w = (int)dist;                                                       // const int w (src/BreakID.cc:390)
+    BK_LAUNCH(k7_regions, GRID1(ncl, 128), 128, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, w, work, evcap);
+    bk::exclusive_scan<uint32_t, uint32_t>(evcap, evoff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    unsigned long long nev = 0;
+    CU(c, cudaMemcpyAsync(&nev, tot, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    TRY(c, c->tmpC.ensure((size_t)(nev + 1) * 4, 0, st));
+    int *fatal = (int *)(c->counters.as<unsigned>() + 46);
+    CU(c, cudaMemsetAsync(fatal, 0, 4, st));
+    BK_LAUNCH((k7_collect<false>), ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, evoff, c->tmpC.as<uint32_t>(), (const uint32_t *)nullptr, (int2 *)nullptr);
+    BK_LAUNCH(k7_entry_counts, GRID1(ncl, 128), 128, 0, st, work, ncl, entcnt, fatal);
+    bk::exclusive_scan<uint32_t, uint32_t>(entcnt, entoff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    unsigned long long nent = 0; int hf = 0;
+    CU(c, cudaMemcpyAsync(&nent, tot, 8, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(&hf, fatal, 4, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    if (hf) return fail(c, BKID_ERR_CIGAR, "error cigar: a complementary split alignment has no clip (reference exits at src/BreakID.cc:954-968)");
+    TRY(c, c->tmpD.ensure((size_t)(nent + 1) * sizeof(int2), 0, st));
+    BK_LAUNCH((k7_collect<true>), ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, evoff, c->tmpC.as<uint32_t>(), entoff, c->tmpD.as<int2>());
+    BK_LAUNCH(k8_vote, ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, entoff, c->tmpD.as<int2>(), c->prm.bp_pos_error, valid);
+    uint32_t *voff = evoff;
+    bk::exclusive_scan<uint32_t, uint32_t>(valid, voff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    unsigned long long nv = 0;
+    CU(c, cudaMemcpyAsync(&nv, tot, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    BK_LAUNCH(compact_clusters, GRID1(ncl, 128), 128, 0, st, c->clusters.as<bkid_cluster_rec>(), valid, voff, ncl, c->clusters_out.as<bkid_cluster_rec>());
+    c->n_called = (long long)nv;
+    c->tm.n_evidence = (long long)nent;
+  } else cudaEventRecord(c->ev[14], st);
+  cudaEventRecord(c->ev[15], st);
+  TRY(c, sync_check(c));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[13], c->ev[14]); c->tm.evidence = ms;
+  cudaEventElapsedTime(&ms, c->ev[14], c->ev[15]); c->tm.refine = ms;
+  c->tm.n_sa = c->n_sa; c->tm.n_called = c->n_called;
+  c->refined = true;
+  if (n_called) *n_called = c->n_called;
+  return 0;
+}
+
+int bkid_run(bkid_ctx *c, double *mean, double *sd, double *dist, int64_t *n_called)
+{
+  if (!c) return BKID_ERR_ARG;
+  long long l0 = g_bk_launches;
+  double m, s;
+  int rc;
+  if ((rc = bkid_insert_stats(c, &m, &s)) != 0) return rc;
+  int times = c->prm.times;
+  double d = times * sqrt((double)times) * (m + c->prm.sd_mult * s);          // src/BreakID.cc:103
+  int64_t np, ncl, ncall;
+  if ((rc = bkid_scan(c, d, &np)) != 0) return rc;
+  if ((rc = bkid_cluster(c, d, c->prm.fast, &ncl)) != 0) return rc;
+  if ((rc = bkid_refine(c, d, &ncall)) != 0) return rc;
+  if (mean) *mean = m;
+  if (sd) *sd = s;
+  if (dist) *dist = d;
+  if (n_called) *n_called = ncall;
+  c->tm.kernel_launches = g_bk_launches - l0;
+  c->tm.total = c->tm.classify + c->tm.insert_stats + c->tm.join + c->tm.bucket_sort + c->tm.mask + c->tm.cluster + c->tm.summarize + c->tm.evidence + c->tm.refine;
+  return 0;
+}
+
+int bkid_fetch_clusters(bkid_ctx *c, bkid_cluster_rec *out, int64_t cap, int64_t *n)
+{
+  if (!c || !c->refined) return c ? fail(c, BKID_ERR_ARG, "bkid_fetch_clusters before bkid_refine") : BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (n) *n = c->n_called;
+  if (out && cap > 0 && c->n_called > 0) {
+    long long k = std::min<long long>(cap, c->n_called);
+    CU(c, cudaMemcpy(out, c->clusters_out.p, (size_t)k * sizeof(bkid_cluster_rec), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+__global__ void pairs_by_index(const bkid_pair *__restrict__ src, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ bucket, const int32_t *__restrict__ cluster,
+                               long long n, bkid_pair *__restrict__ dst)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  bkid_pair P = src[idx[p]];
+  if (bucket) P.bucket = (int32_t)bucket[p];
+  if (cluster) P.cluster = cluster[p];
+  dst[p] = P;
+}
+
+int bkid_fetch_pairs(bkid_ctx *c, int stage, bkid_pair *out, int64_t cap, int64_t *n)
+{
+  if (!c || !c->scanned) return c ? fail(c, BKID_ERR_ARG, "bkid_fetch_pairs before bkid_scan") : BKID_ERR_ARG;
+  if (stage > 0 && !c->clustered) return fail(c, BKID_ERR_ARG, "stage not computed yet");
+  cudaSetDevice(c->device);
+  long long cnt = stage == 0 ? c->np0 : stage == 1 ? c->n1 : c->n2;
+  if (n) *n = cnt;
+  if (!out || cap <= 0 || cnt == 0) return 0;
+  long long k = std::min<long long>(cap, cnt);
+  if (stage == 0) { CU(c, cudaMemcpy(out, c->pairs0.p, (size_t)k * sizeof(bkid_pair), cudaMemcpyDeviceToHost)); return 0; }
+  TRY(c, c->pairs_tmp.ensure((size_t)cnt * sizeof(bkid_pair), 0, c->st));
+  if (stage == 1)
+    BK_LAUNCH(pairs_by_index, GRID1(cnt, 256), 256, 0, c->st, c->pairs0.as<bkid_pair>(), c->cur1.as<uint32_t>(), c->curb1.as<uint32_t>(), (const int32_t *)nullptr, cnt, c->pairs_tmp.as<bkid_pair>());
+  else
+    BK_LAUNCH(pairs_by_index, GRID1(cnt, 256), 256, 0, c->st, c->pairs0.as<bkid_pair>(), c->mem_pair.as<uint32_t>(), c->mem_bucket.as<uint32_t>(), c->mem_cluster.as<int32_t>(), cnt,
+              c->pairs_tmp.as<bkid_pair>());
+  TRY(c, sync_check(c));
+  CU(c, cudaMemcpy(out, c->pairs_tmp.p, (size_t)k * sizeof(bkid_pair), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bkid_fetch_class(bkid_ctx *c, uint8_t *out, int64_t cap)
+{
+  if (!c || !c->classified) return c ? fail(c, BKID_ERR_ARG, "not classified yet") : BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  long long k = std::min<long long>(cap, c->n);
+  if (k > 0) CU(c, cudaMemcpy(out, c->cls.p, (size_t)k, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bkid_get_timings(bkid_ctx *c, bkid_timings *t)
+{
+  if (!c || !t) return BKID_ERR_ARG;
+  *t = c->tm;
+  return 0;
+}
+
+// ---- stand-alone operators ------------------------------------------------------------------
+int bkid_op_sort_perm(bkid_ctx *c, int64_t n, const uint32_t *key, uint32_t *perm)
+{
+  if (!c || n < 0) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  c->err.clear();
+  if (n == 0) return 0;
+  cudaStream_t st = c->st;
+  DBuf k, v, so;
+  int rc = 0;
+  if ((rc = k.ensure((size_t)n * 4 + 16, 0, st)) || (rc = v.ensure((size_t)n * 4 + 16, 0, st)) || (rc = so.ensure(16, 0, st))) return fail(c, rc, g_last_cuda_err);
+  uint32_t seg[2] = {0, (uint32_t)n};
+  cudaMemcpyAsync(k.p, key, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(so.p, seg, 8, cudaMemcpyHostToDevice, st);
+  BK_LAUNCH(iota_u32, GRID1(n, 256), 256, 0, st, v.as<uint32_t>(), (long long)n);
+  rc = exact_sort_segments(c, k.as<uint32_t>(), v.as<uint32_t>(), so.as<uint32_t>(), 1, n);
+  if (!rc) rc = sync_check(c);
+  if (!rc) cudaMemcpy(perm, v.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  k.release(); v.release(); so.release();
+  return rc;
+}
+
+static int op_setup(bkid_ctx *c, int64_t n, const uint32_t *p1, const uint32_t *p2, DBuf &x, DBuf &y, DBuf &cur, DBuf &curb, DBuf &seg)
+{
+  cudaStream_t st = c->st;
+  size_t m = (size_t)std::max<int64_t>(n, 1) * 4 + 16;
+  TRY(c, x.ensure(m, 0, st)); TRY(c, y.ensure(m, 0, st)); TRY(c, cur.ensure(m, 0, st)); TRY(c, curb.ensure(m, 0, st)); TRY(c, seg.ensure(16, 0, st));
+  TRY(c, c->counters.ensure(1024, 0, st));
+  uint32_t so[2] = {0, (uint32_t)n};
+  if (n > 0) {
+    CU(c, cudaMemcpyAsync(x.p, p1, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(y.p, p2, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    BK_LAUNCH(iota_u32, GRID1(n, 256), 256, 0, st, cur.as<uint32_t>(), (long long)n);
+    CU(c, cudaMemsetAsync(curb.p, 0, (size_t)n * 4, st));
+  }
+  CU(c, cudaMemcpyAsync(seg.p, so, 8, cudaMemcpyHostToDevice, st));
+  return sync_check(c);
+}
+
+int bkid_op_remove_isolated(bkid_ctx *c, int64_t n, const uint32_t *p1, const uint32_t *p2, double w, uint32_t *out_idx, int64_t *n_out)
+{
+  if (!c || n < 0) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  c->err.clear();
+  DBuf x, y, cur, curb, seg;
+  int rc = op_setup(c, n, p1, p2, x, y, cur, curb, seg);
+  if (!rc) rc = remove_isolated_all(c, cur.as<uint32_t>(), curb.as<uint32_t>(), seg.as<uint32_t>(), n, 1, x.as<uint32_t>(), y.as<uint32_t>(), w);
+  if (!rc) rc = sync_check(c);
+  if (!rc) {
+    *n_out = c->n1;
+    if (c->n1 > 0) cudaMemcpy(out_idx, c->cur1.p, (size_t)c->n1 * 4, cudaMemcpyDeviceToHost);
+  }
+  for (DBuf *b : {&x, &y, &cur, &curb, &seg}) b->release();
+  return rc;
+}
+
+int bkid_op_cluster(bkid_ctx *c, int mode, int64_t n, const uint32_t *p1, const uint32_t *p2, double thr, uint32_t *out_idx, int32_t *out_cluster, int64_t *n_out,
+                    int32_t *n_roots)
+{
+  if (!c || n < 0) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  c->err.clear();
+  DBuf x, y, cur, curb, seg;
+  int rc = op_setup(c, n, p1, p2, x, y, cur, curb, seg);
+  if (!rc) rc = mode ? cluster_fast(c, cur.as<uint32_t>(), curb.as<uint32_t>(), seg.as<uint32_t>(), n, 1, x.as<uint32_t>(), y.as<uint32_t>(), thr, n)
+                     : cluster_ahc(c, cur.as<uint32_t>(), curb.as<uint32_t>(), seg.as<uint32_t>(), n, 1, x.as<uint32_t>(), y.as<uint32_t>(), thr);
+  if (!rc) rc = sync_check(c);
+  if (!rc) {
+    *n_out = c->n2;
+    if (n_roots) *n_roots = c->roots_per_bucket.empty() ? 0 : c->roots_per_bucket[0];
+    if (c->n2 > 0) {
+      cudaMemcpy(out_idx, c->mem_pair.p, (size_t)c->n2 * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(out_cluster, c->mem_cluster.p, (size_t)c->n2 * 4, cudaMemcpyDeviceToHost);
+    }
+  }
+  for (DBuf *b : {&x, &y, &cur, &curb, &seg}) b->release();
+  return rc;
+}
+
+}  // extern "C"

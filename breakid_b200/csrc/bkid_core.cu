@@ -1,0 +1,741 @@
+// bkid_core.cu -- CUDA (sm_100a) implementation of BreakID's data-parallel core behind the C ABI of
+// include/breakid_b200.h.  Written from scratch for B200: every stage is HBM-bound integer / FP64
+// scalar work (no dense contraction anywhere on this path, so no tensor cores), laid out as
+// struct-of-arrays columns resident in HBM, 128-bit vector loads on the streaming kernels, grids
+// sized from the tile count, and no host round trips inside a stage except the small counters a
+// stage boundary needs.
+//
+// Reference files cited below are relative to the reference tree (SinOncology/BreakID).
+//
+//   K1  classify + insert statistics        src/BreakID.cc:1419-1420, 1909-1954, util_bed.cc:183
+//   K1s exact replay of the truncating sd accumulator (src/BreakID.cc:1913,1944)
+//   K2  mate join (radix sort on name hash + pairwise protocol)      src/BreakID.cc:1424-1494
+//   K3  bucket ordering + std::sort replay (parallel introsort)      src/BreakID.cc:1274-1282,1500-1512
+//   K4  isolated-pair mask                                           src/BreakID.cc:1813-1877
+//   K5a AHC by components (closed-form tie rule)                     src/util_cluster.cc:7-396
+//   K5b -fast anchored-window sweep                                  src/BreakID.cc:1046-1160
+//   K6  cluster summary + 2w filter                                  src/BreakID.cc:297-352
+//   K7  split-read evidence (CIGAR / SA arithmetic)                  src/BreakID.cc:868-1037
+//   K8  breakpoint vote                                              src/BreakID.cc:577-857
+//   K9  depth / AF / type                                            src/util_bed.cc:154-192
+//   K10 nib 41-mer + homopolymer                                     src/util_bam.cc:78-122
+#include "../../include/breakid_b200.h"
+#include "prims.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+thread_local long long g_bk_launches = 0;
+static thread_local std::string g_last_cuda_err;
+static std::string g_create_err;
+
+void bk_set_cuda_error(cudaError_t e, const char *file, int line)
+{
+  char buf[256];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
+  g_last_cuda_err = buf;
+}
+
+using bk::div_up;
+
+enum { F_PAIRED = 0x1, F_PROPER = 0x2, F_UNMAP = 0x4, F_REVERSE = 0x10, F_SECONDARY = 0x100, F_QCFAIL = 0x200, F_DUP = 0x400 };
+enum { CL_INSERT = 1, CL_CAND = 2, CL_DEPTH = 4, CL_SPLITOK = 8 };
+
+// ---------------------------------------------------------------------------------------------
+// growable device buffer
+// ---------------------------------------------------------------------------------------------
+struct DBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  template <typename T> T *as() const { return (T *)p; }
+  // grow to at least `bytes`; keep the first `keep` bytes
+  int ensure(size_t bytes, size_t keep, cudaStream_t st)
+  {
+    if (bytes <= cap) return 0;
+    size_t ncap = std::max(bytes, cap + cap / 2);
+    ncap = (ncap + 255) & ~(size_t)255;
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, ncap);
+    if (e != cudaSuccess) { bk_set_cuda_error(e, __FILE__, __LINE__); return e == cudaErrorMemoryAllocation ? BKID_ERR_NOMEM : BKID_ERR_CUDA; }
+    if (p && keep) cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st);
+    if (p) { cudaStreamSynchronize(st); cudaFree(p); }
+    p = q; cap = ncap;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+#define BK_TRY(x) do { int rc__ = (x); if (rc__ != 0) return rc__; } while (0)
+
+// =============================================================================================
+// K1: classify + insert statistics.  One block per tile of 4096 records; each thread handles 4
+// groups of 4 consecutive records with 64/32/128-bit loads of flag/mapq/isize and one 32-bit store of
+// the class mask.  Algorithmic traffic: 2 + 1 + 4 B read, 1 B written per record.
+// =============================================================================================
+constexpr int K1_THREADS = 256;
+constexpr int K1_TILE = 4096;
+
+__device__ __forceinline__ unsigned classify_one(unsigned flag, unsigned mapq, int qual)
+{
+  unsigned c = 0;
+  if ((flag & F_PAIRED) && (flag & F_PROPER) && !(flag & (F_UNMAP | F_SECONDARY | F_QCFAIL | F_DUP))) c |= CL_INSERT;      // :1932
+  if ((int)mapq >= qual && !(flag & F_DUP) && !(flag & F_SECONDARY) && (flag & F_PAIRED) && !(flag & F_PROPER)) c |= CL_CAND; // :1419-1420
+  if (mapq > 0 && !(flag & F_DUP) && (flag & F_PAIRED)) c |= CL_DEPTH;                                                       // util_bed.cc:183
+  if (!(flag & F_DUP) && (flag & F_PAIRED)) c |= CL_SPLITOK;                                                                // :898
+  return c;
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ isize, long long n, int qual,
+            uint8_t *__restrict__ cls, uint32_t *__restrict__ tile_cand, unsigned long long *__restrict__ g_sum_abs,
+            unsigned long long *__restrict__ g_cnt_insert)
+{
+  __shared__ unsigned long long sh64[33];
+  __shared__ unsigned sh32[33];
+  long long tile0 = (long long)blockIdx.x * K1_TILE;
+  unsigned long long sum_abs = 0;
+  unsigned n_ins = 0, n_cand = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    long long i = tile0 + g * (K1_THREADS * 4) + threadIdx.x * 4;
+    if (i + 3 < n) {
+      uint2 f2 = *reinterpret_cast<const uint2 *>(flag + i);
+      uchar4 m4 = *reinterpret_cast<const uchar4 *>(mapq + i);
+      int4 s4 = *reinterpret_cast<const int4 *>(isize + i);
+      unsigned f[4] = {f2.x & 0xffffu, f2.x >> 16, f2.y & 0xffffu, f2.y >> 16};
+      unsigned m[4] = {m4.x, m4.y, m4.z, m4.w};
+      int s[4] = {s4.x, s4.y, s4.z, s4.w};
+      unsigned c[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        c[k] = classify_one(f[k], m[k], qual);
+        if (c[k] & CL_INSERT) { sum_abs += (unsigned long long)(s[k] < 0 ? -(long long)s[k] : (long long)s[k]); ++n_ins; }
+        n_cand += (c[k] >> 1) & 1u;
+      }
+      *reinterpret_cast<uchar4 *>(cls + i) = make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], (unsigned char)c[3]);
+    } else {
+      for (int k = 0; k < 4; ++k)
+        if (i + k < n) {
+          unsigned c = classify_one(flag[i + k], mapq[i + k], qual);
+          int s = isize[i + k];
+          if (c & CL_INSERT) { sum_abs += (unsigned long long)(s < 0 ? -(long long)s : (long long)s); ++n_ins; }
+          n_cand += (c >> 1) & 1u;
+          cls[i + k] = (uint8_t)c;
+        }
+    }
+  }
+  unsigned long long tot64;
+  bk::block_excl_scan<unsigned long long>(sum_abs, sh64, tot64);
+  unsigned tot_ins, tot_cand;
+  bk::block_excl_scan<unsigned>(n_ins, sh32, tot_ins);
+  bk::block_excl_scan<unsigned>(n_cand, sh32, tot_cand);
+  if (threadIdx.x == 0) {
+    tile_cand[blockIdx.x] = tot_cand;
+    if (tot_ins) { atomicAdd(g_sum_abs, tot64); atomicAdd(g_cnt_insert, (unsigned long long)tot_ins); }
+  }
+}
+
+// ordered compaction of candidate record indices: each thread owns 16 consecutive class bytes
+__global__ void __launch_bounds__(K1_THREADS)
+k1_compact(const uint8_t *__restrict__ cls, long long n, const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ cand_idx)
+{
+  __shared__ unsigned sh32[33];
+  long long i0 = (long long)blockIdx.x * K1_TILE + threadIdx.x * 16;
+  unsigned char c[16];
+  if (i0 + 15 < n) {
+    uint4 v = *reinterpret_cast<const uint4 *>(cls + i0);
+    memcpy(c, &v, 16);
+  } else {
+    for (int k = 0; k < 16; ++k) c[k] = (i0 + k < n) ? cls[i0 + k] : 0;
+  }
+  unsigned cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) cnt += (c[k] >> 1) & 1u;
+  unsigned tot;
+  unsigned off = bk::block_excl_scan<unsigned>(cnt, sh32, tot) + tile_off[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (c[k] & CL_CAND) cand_idx[off++] = (uint32_t)(i0 + k);
+}
+
+// =============================================================================================
+// K1s: exact replay of `long sd_total += d*d` (src/BreakID.cc:1913,1944).
+// The reference converts the long accumulator to double, adds d*d, and truncates back on every
+// element: t' = floor(RN(t + a)).  For t + a < 2^52 this is t + floor(a) + c with
+// c = [frac(a) >= 1 - 2^(k-53)], k = floor(log2(t + a)): the correction depends on the running
+// total only through its binade.  So one pass computes, per block of SD_BLOCK records, F = sum of
+// floor(a) and the cumulative histogram cum[k] = #{ i : kmin_i <= k } (kmin_i = 53+ceil(log2(1-frac)));
+// a single-CTA resolver then walks the blocks with exact integer arithmetic, 1024 blocks per step,
+// and only blocks that really straddle a power of two are re-read element by element.
+// Totals >= 2^52 leave the closed form: the host then runs the literal sequential kernel.
+// =============================================================================================
+constexpr int SD_BLOCK = 8192;
+constexpr int SD_THREADS = 256;
+constexpr int SD_K = 52;
+
+__device__ __forceinline__ int binade_of(double s)   // floor(log2(s)) for s >= 1, -1 below
+{
+  if (!(s >= 1.0)) return -1;
+  return (int)((__double_as_longlong(s) >> 52) & 0x7ff) - 1023;
+}
+
+// a = (x-mean)^2 exactly as the reference computes it; returns floor(a) and kmin (255 = never)
+__device__ __forceinline__ void sd_elem(int isz, double mean, double &a, long long &fa, unsigned &kmin)
+{
+  double x = (double)(isz < 0 ? -isz : isz);
+  double d = __dsub_rn(x, mean);
+  a = __dmul_rn(d, d);
+  double fl = floor(a);
+  fa = (long long)fl;
+  double frac = a - fl;                 // exact
+  kmin = 255u;
+  if (frac >= 0.5) {
+    double om = 1.0 - frac;             // exact for frac >= 0.5
+    long long b = __double_as_longlong(om);
+    int e = (int)((b >> 52) & 0x7ff) - 1023;
+    int ce = e + ((b & 0xFFFFFFFFFFFFFll) != 0 ? 1 : 0);
+    int km = 53 + ce;
+    if (km < 0) km = 0;
+    if (km < SD_K) kmin = (unsigned)km;
+  }
+}
+
+__global__ void __launch_bounds__(SD_THREADS)
+sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean,
+               long long *__restrict__ blkF, uint32_t *__restrict__ blkCum /*[nb][SD_K]*/, uint32_t *__restrict__ blkN, double *__restrict__ blkAmax)
+{
+  __shared__ unsigned hist[SD_K];
+  __shared__ unsigned long long sh64[33];
+  __shared__ unsigned sh32[33];
+  __shared__ double shd[33];
+  if (threadIdx.x < SD_K) hist[threadIdx.x] = 0;
+  __syncthreads();
+  long long base = (long long)blockIdx.x * SD_BLOCK;
+  unsigned long long F = 0;
+  unsigned cnt = 0;
+  double amax = 0.0;
+  for (int g = 0; g < SD_BLOCK / (SD_THREADS * 4); ++g) {
+    long long i = base + (long long)g * (SD_THREADS * 4) + threadIdx.x * 4;
+    unsigned char c[4];
+    int s[4];
+    if (i + 3 < n) {
+      uchar4 c4 = *reinterpret_cast<const uchar4 *>(cls + i);
+      int4 s4 = *reinterpret_cast<const int4 *>(isize + i);
+      c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
+      s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
+    } else {
+      for (int k = 0; k < 4; ++k) { c[k] = (i + k < n) ? cls[i + k] : 0; s[k] = (i + k < n) ? isize[i + k] : 0; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c[k] & CL_INSERT) {
+        double a; long long fa; unsigned km;
+        sd_elem(s[k], mean, a, fa, km);
+        F += (unsigned long long)fa;
+        ++cnt;
+        amax = fmax(amax, a);
+        if (km != 255u) atomicAdd(&hist[km], 1u);
+      }
+  }
+  unsigned long long totF;
+  bk::block_excl_scan<unsigned long long>(F, sh64, totF);
+  unsigned totN;
+  bk::block_excl_scan<unsigned>(cnt, sh32, totN);
+  // block max of amax
+  for (int o = 16; o; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) shd[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < SD_THREADS / 32; ++w) m = fmax(m, shd[w]);
+    blkAmax[blockIdx.x] = m;
+    blkF[blockIdx.x] = (long long)totF;
+    blkN[blockIdx.x] = totN;
+    unsigned run = 0;
+    for (int k = 0; k < SD_K; ++k) { run += hist[k]; blkCum[(size_t)blockIdx.x * SD_K + k] = run; }
+  }
+}
+
+// single CTA, 1024 threads.  out[0] = sd_total, out[1] = out-of-regime flag.
+__global__ void __launch_bounds__(1024)
+sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, int nb,
+           const long long *__restrict__ blkF, const uint32_t *__restrict__ blkCum, const uint32_t *__restrict__ blkN,
+           const double *__restrict__ blkAmax, long long *__restrict__ out)
+{
+  extern __shared__ unsigned char dyn[];
+  double *sa = reinterpret_cast<double *>(dyn);                  // [SD_BLOCK]   a_i, -1 = ineligible
+  unsigned char *skm = dyn + (size_t)SD_BLOCK * 8;               // [SD_BLOCK]   kmin_i
+  __shared__ long long sh_scan[33];
+  __shared__ long long sh_t;
+  __shared__ int sh_j, sh_q, sh_oor, sh_k;
+  if (threadIdx.x == 0) { sh_t = 0; sh_j = 0; sh_oor = 0; }
+  __syncthreads();
+  while (true) {
+    int j0 = sh_j;
+    long long t0 = sh_t;
+    if (j0 >= nb || sh_oor) break;
+    int k0 = binade_of((double)t0);
+    int j = j0 + threadIdx.x;
+    long long delta = 0;
+    if (j < nb) {
+      delta = blkF[j];
+      if (k0 >= 0 && k0 < SD_K) delta += blkCum[(size_t)j * SD_K + k0];
+    }
+    long long tot;
+    long long tstart = t0 + bk::block_excl_scan<long long>(delta, sh_scan, tot);
+    // valid iff every s in this block stays in binade k0
+    bool valid = true;
+    if (j < nb) {
+      double upper = (double)(tstart + delta + (long long)blkN[j] + 2) + blkAmax[j] * 1.000000001 + 2.0;
+      valid = (blkN[j] == 0) || (k0 < SD_K && binade_of((double)tstart) == k0 && binade_of(upper) == k0);
+      if (blkN[j] != 0 && k0 >= SD_K) valid = false;
+    }
+    if (threadIdx.x == 0) sh_q = 1024;
+    __syncthreads();
+    if (j < nb && !valid) atomicMin(&sh_q, (int)threadIdx.x);
+    __syncthreads();
+    int q = sh_q;
+    int nvalid = min(q, nb - j0);          // blocks j0 .. j0+nvalid-1 are final
+    __syncthreads();
+    if (nvalid > 0 && (int)threadIdx.x == nvalid - 1) { sh_t = tstart + delta; sh_j = j0 + nvalid; }
+    __syncthreads();
+    if (q >= 1024 || j0 + q >= nb) continue;
+    // block jq = j0+q is either the first block of a new binade or a real straddler
+    int jq = j0 + q;
+    long long t = sh_t;
+    {
+      double upper = (double)(t + blkF[jq] + (long long)blkN[jq] + 2) + blkAmax[jq] * 1.000000001 + 2.0;
+      int ka = binade_of((double)t), kb = binade_of(upper);
+      if (ka == kb && ka < SD_K && q > 0) continue;   // clean block of the next binade: restart the chunk there
+    }
+    // ---- exact element-level evaluation of block jq ----
+    long long base = (long long)jq * SD_BLOCK;
+    int m = (int)min((long long)SD_BLOCK, n - base);
+    for (int e = threadIdx.x; e < SD_BLOCK; e += 1024) {
+      double a = -1.0; unsigned km = 255u;
+      if (e < m && (cls[base + e] & CL_INSERT)) { long long fa; sd_elem(isize[base + e], mean, a, fa, km); }
+      sa[e] = a; skm[e] = (unsigned char)km;
+    }
+    __syncthreads();
+    constexpr int PER = SD_BLOCK / 1024;
+    int p = 0;
+    while (p < m) {
+      // first eligible element at or after p defines the current binade
+      if (threadIdx.x == 0) sh_q = SD_BLOCK;
+      __syncthreads();
+      {
+        int lo = threadIdx.x * PER, best = SD_BLOCK;
+        for (int e = lo + PER - 1; e >= lo; --e) if (e >= p && e < m && sa[e] >= 0.0) best = e;
+        if (best < SD_BLOCK) atomicMin(&sh_q, best);
+      }
+      __syncthreads();
+      int pe = sh_q;
+      if (pe >= SD_BLOCK) break;                       // no eligible element left
+      __syncthreads();
+      if (threadIdx.x == 0) { sh_k = binade_of((double)t + sa[pe]); sh_q = SD_BLOCK; }
+      __syncthreads();
+      int k = sh_k;
+      if (k >= SD_K) { if (threadIdx.x == 0) sh_oor = 1; __syncthreads(); break; }
+      // per-thread increments over its PER consecutive elements (restricted to e >= pe)
+      int lo = threadIdx.x * PER;
+      long long loc = 0;
+      for (int e = lo; e < lo + PER; ++e)
+        if (e >= pe && e < m && sa[e] >= 0.0) loc += (long long)floor(sa[e]) + ((k >= 0 && skm[e] <= k) ? 1 : 0);
+      long long tt;
+      long long run = t + bk::block_excl_scan<long long>(loc, sh_scan, tt);
+      int cross = SD_BLOCK;
+      for (int e = lo; e < lo + PER; ++e)
+        if (e >= pe && e < m && sa[e] >= 0.0) {
+          if (e > pe && binade_of((double)run + sa[e]) > k && cross == SD_BLOCK) cross = e;
+          run += (long long)floor(sa[e]) + ((k >= 0 && skm[e] <= k) ? 1 : 0);
+        }
+      if (cross < SD_BLOCK) atomicMin(&sh_q, cross);
+      __syncthreads();
+      int qx = sh_q;
+      // add the increments of [pe, qx)
+      long long part = 0;
+      for (int e = lo; e < lo + PER; ++e)
+        if (e >= pe && e < qx && e < m && sa[e] >= 0.0) part += (long long)floor(sa[e]) + ((k >= 0 && skm[e] <= k) ? 1 : 0);
+      long long ptot;
+      bk::block_excl_scan<long long>(part, sh_scan, ptot);
+      t += ptot;
+      p = qx;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { sh_t = t; sh_j = jq + 1; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh_t; out[1] = sh_oor; }
+}
+
+// literal sequential replay (one thread); only used when the total leaves the closed-form regime
+__global__ void sd_sequential(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, long long *out)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  long long t = 0;
+  for (long long i = 0; i < n; ++i)
+    if (cls[i] & CL_INSERT) {
+      int s = isize[i];
+      double x = (double)(s < 0 ? -s : s);
+      double d = __dsub_rn(x, mean);
+      t = (long long)__dadd_rn((double)t, __dmul_rn(d, d));
+    }
+  out[0] = t; out[1] = 0;
+}
+
+// =============================================================================================
+// K2: mate join.  Candidates (ordered by file position) are sorted by the low 64 bits of the name
+// hash with a stable radix sort, so the records sharing a name sit in one run in file order.  The
+// reference's std::map protocol (store first, pair-and-erase on the second, src/BreakID.cc:1424-1494)
+// pairs run positions (0,1), (2,3), ...: the odd one is the "current" record, the even one the
+// stored mate.
+// =============================================================================================
+__global__ void k2_gather_keys(const uint32_t *__restrict__ cand_idx, long long nc, const uint64_t *__restrict__ nh, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nc) { uint32_t i = cand_idx[p]; keys[p] = nh[2 * (size_t)i]; vals[p] = i; }
+}
+
+__global__ void k2_run_heads(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, long long nc, const uint64_t *__restrict__ nh,
+                             uint32_t *__restrict__ head, int *__restrict__ err)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nc) return;
+  unsigned h = 1;
+  if (p > 0 && keys[p] == keys[p - 1]) {
+    h = 0;
+    if (nh[2 * (size_t)vals[p] + 1] != nh[2 * (size_t)vals[p - 1] + 1]) atomicExch(err, 1);   // 64-bit collision of distinct names
+  }
+  head[p] = h;
+}
+
+__global__ void k2_run_starts(const uint32_t *__restrict__ head, const uint32_t *__restrict__ run_id_excl, long long nc, uint32_t *__restrict__ run_start)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nc && head[p]) run_start[run_id_excl[p]] = (uint32_t)p;
+}
+
+struct PairKey { unsigned long long key; };
+
+__device__ __forceinline__ uint32_t genome_pos(const uint32_t *__restrict__ cum, int nt, int tid, int pos)
+{
+  // src/util_bam.cc:57-68: sum of target_len[0..tid) (uint32 wrap) + pos; tid < 0 adds nothing
+  uint32_t p = (tid > 0) ? cum[tid < nt ? tid : nt] : 0u;
+  return p + (uint32_t)pos;
+}
+
+__global__ void k2_emit_pairs(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ head, const uint32_t *__restrict__ run_id_excl,
+                              const uint32_t *__restrict__ run_start, long long nc,
+                              const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ tid,
+                              const int32_t *__restrict__ pos, const int32_t *__restrict__ mtid, const int32_t *__restrict__ mpos,
+                              const uint64_t *__restrict__ nh, const uint32_t *__restrict__ cum, int nt, const int32_t *__restrict__ bucket_rank,
+                              double w, bkid_pair *__restrict__ pairs, unsigned long long *__restrict__ keys, uint32_t *__restrict__ slots,
+                              unsigned long long *__restrict__ counter)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool emit = false;
+  uint32_t i = 0, j = 0;
+  if (p < nc) {
+    uint32_t rid = run_id_excl[p] - (head[p] ? 0u : 1u);     // exclusive scan counts heads before p
+    uint32_t rank = (uint32_t)p - run_start[rid];
+    if (rank & 1u) {
+      i = vals[p]; j = vals[p - 1];
+      int ti = tid[i] < 0 ? -1 : tid[i], tj = tid[j] < 0 ? -1 : tid[j];
+      long long pi = (long long)pos[i] + 1, pj = (long long)pos[j] + 1;
+      long long dp = pi - pj; if (dp < 0) dp = -dp;
+      emit = (ti != tj) || ((double)dp >= w);                 // :1428
+    }
+  }
+  unsigned m = __ballot_sync(0xffffffffu, emit);
+  if (!m) return;
+  unsigned lane = threadIdx.x & 31;
+  unsigned long long basep = 0;
+  if (lane == (unsigned)(__ffs(m) - 1)) basep = atomicAdd(counter, (unsigned long long)__popc(m));
+  basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
+  if (!emit) return;
+  unsigned long long slot = basep + __popc(m & ((1u << lane) - 1u));
+  uint32_t c1 = genome_pos(cum, nt, tid[i], pos[i]);          // :1431 current record's own fields
+  uint32_t c2 = genome_pos(cum, nt, mtid[i], mpos[i]);        // :1432 and its mate FIELDS
+  bkid_pair P;
+  P.name_lo = nh[2 * (size_t)i]; P.name_hi = nh[2 * (size_t)i + 1];
+  int ti = tid[i] < 0 ? -1 : tid[i], tj = tid[j] < 0 ? -1 : tid[j];
+  uint32_t pi = (uint32_t)((long long)pos[i] + 1), pj = (uint32_t)((long long)pos[j] + 1);
+  if (c1 <= c2) {
+    P.p1_flag = flag[i]; P.p1_tid = ti; P.p1_pos = pi; P.p1_mapq = mapq[i];
+    P.p2_flag = flag[j]; P.p2_tid = tj; P.p2_pos = pj; P.p2_mapq = mapq[j];
+    P.p1_chr_pos = c1; P.p2_chr_pos = c2;
+  } else {
+    P.p2_flag = flag[i]; P.p2_tid = ti; P.p2_pos = pi; P.p2_mapq = mapq[i];
+    P.p1_flag = flag[j]; P.p1_tid = tj; P.p1_pos = pj; P.p1_mapq = mapq[j];
+    P.p1_chr_pos = c2; P.p2_chr_pos = c1;
+  }
+  P.p1_strand = (P.p1_flag & F_REVERSE) ? '-' : '+';
+  P.p2_strand = (P.p2_flag & F_REVERSE) ? '-' : '+';
+  int a = P.p1_tid + 1, b = P.p2_tid + 1;
+  int br = bucket_rank[a * (nt + 1) + b];
+  P.bucket = br; P.cluster = -1; P.orig = 0; P._pad = 0;
+  pairs[slot] = P;
+  keys[slot] = ((unsigned long long)(unsigned)br << 32) | (unsigned long long)i;   // bucket order, then order of the second-seen mate
+  slots[slot] = (uint32_t)slot;
+}
+
+__global__ void k2_gather_pairs(const bkid_pair *__restrict__ src, const uint32_t *__restrict__ slots, const unsigned long long *__restrict__ keys,
+                                long long np, bkid_pair *__restrict__ dst, uint32_t *__restrict__ bucket_head)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  bkid_pair P = src[slots[p]];
+  P.orig = (uint32_t)p;
+  dst[p] = P;
+  bucket_head[p] = (p == 0 || (keys[p] >> 32) != (keys[p - 1] >> 32)) ? 1u : 0u;
+}
+
+// dense bucket ids + bucket offsets
+__global__ void k2_bucket_ids(bkid_pair *__restrict__ pairs, const uint32_t *__restrict__ head, const uint32_t *__restrict__ head_excl, long long np,
+                              uint32_t *__restrict__ bucket_off)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  uint32_t b = head_excl[p] - (head[p] ? 0u : 1u);
+  pairs[p].bucket = (int32_t)b;
+  if (head[p]) bucket_off[b] = (uint32_t)p;
+}
+
+// =============================================================================================
+// K3: replay of libstdc++ std::sort (introsort) on (key, value) segments -- see the model and its
+// proof obligations in oracle/oracle.cc (orc_model_sort_perm).  Level-synchronous: one CTA per
+// active segment does median-of-3 + the data-parallel form of __unguarded_partition; segments of
+// <= 16 elements are finished by one thread each (stable insertion sort); depth-exhausted segments
+// run the literal heapsort on one thread.
+// =============================================================================================
+struct Seg { uint32_t f, l; int depth; };
+constexpr int IS_THREADS = 256;
+
+__device__ void seg_insertion_sort(uint32_t *key, uint32_t *val, uint32_t f, uint32_t l)
+{
+  for (uint32_t i = f + 1; i < l; ++i) {
+    uint32_t k = key[i], v = val[i];
+    uint32_t j = i;
+    while (j > f && k < key[j - 1]) { key[j] = key[j - 1]; val[j] = val[j - 1]; --j; }
+    key[j] = k; val[j] = v;
+  }
+}
+
+__device__ void seg_heapsort(uint32_t *key, uint32_t *val, uint32_t f, uint32_t l)
+{
+  // std::__partial_sort(first,last,last): __make_heap + __sort_heap (libstdc++ bits/stl_heap.h)
+  long n = (long)l - (long)f;
+  uint32_t *K = key + f, *V = val + f;
+  auto adjust = [&](long hole, long len, uint32_t vk, uint32_t vv) {
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+      child = 2 * (child + 1);
+      if (K[child] < K[child - 1]) child--;
+      K[hole] = K[child]; V[hole] = V[child];
+      hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+      child = 2 * (child + 1);
+      K[hole] = K[child - 1]; V[hole] = V[child - 1];
+      hole = child - 1;
+    }
+    long parent = (hole - 1) / 2;
+    while (hole > top && K[parent] < vk) {
+      K[hole] = K[parent]; V[hole] = V[parent];
+      hole = parent;
+      parent = (hole - 1) / 2;
+    }
+    K[hole] = vk; V[hole] = vv;
+  };
+  if (n < 2) return;
+  for (long parent = (n - 2) / 2;; --parent) {
+    adjust(parent, n, K[parent], V[parent]);
+    if (parent == 0) break;
+  }
+  for (long last = n - 1; last > 0; --last) {
+    uint32_t vk = K[last], vv = V[last];
+    K[last] = K[0]; V[last] = V[0];
+    adjust(0, last, vk, vv);
+  }
+}
+
+// roots: one segment per bucket
+__global__ void is_init_roots(const uint32_t *__restrict__ seg_off, int nseg, Seg *__restrict__ act, unsigned *__restrict__ n_act,
+                              Seg *__restrict__ term, unsigned *__restrict__ n_term)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  uint32_t f = seg_off[s], l = seg_off[s + 1];
+  uint32_t n = l - f;
+  if (n < 2) return;
+  if (n <= 16) { term[atomicAdd(n_term, 1u)] = Seg{f, l, 0}; return; }
+  int lg = 31 - __clz(n);
+  act[atomicAdd(n_act, 1u)] = Seg{f, l, 2 * lg};
+}
+
+__global__ void __launch_bounds__(IS_THREADS)
+is_level(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__restrict__ act, const unsigned *__restrict__ n_act_p,
+         Seg *__restrict__ nxt, unsigned *__restrict__ n_nxt, Seg *__restrict__ term, unsigned *__restrict__ n_term,
+         uint32_t *__restrict__ scrL, uint32_t *__restrict__ scrR)
+{
+  __shared__ unsigned sh32[33];
+  __shared__ uint32_t sh_p;
+  __shared__ unsigned sh_K;
+  unsigned n_act = *n_act_p;
+  for (unsigned si = blockIdx.x; si < n_act; si += gridDim.x) {
+    Seg s = act[si];
+    uint32_t f = s.f, l = s.l;
+    if (s.depth == 0) {
+      if (threadIdx.x == 0) seg_heapsort(key, val, f, l);
+      __syncthreads();
+      continue;
+    }
+    if (threadIdx.x == 0) {
+      // __move_median_to_first(first, first+1, mid, last-1)
+      uint32_t mid = f + (l - f) / 2, A = f + 1, B = mid, C = l - 1;
+      uint32_t ka = key[A], kb = key[B], kc = key[C], med;
+      if (ka < kb) { if (kb < kc) med = B; else if (ka < kc) med = C; else med = A; }
+      else if (ka < kc) med = A;
+      else if (kb < kc) med = C;
+      else med = B;
+      uint32_t tk = key[f], tv = val[f];
+      key[f] = key[med]; val[f] = val[med];
+      key[med] = tk; val[med] = tv;
+      sh_p = key[f];
+    }
+    __syncthreads();
+    uint32_t pv = sh_p;
+    uint32_t lo = f + 1, cnt = l - lo;
+    // L list: ascending positions with key >= pivot; R list: descending positions with key <= pivot
+    unsigned nL = 0, nR = 0;
+    for (uint32_t b = 0; b < cnt; b += IS_THREADS) {
+      uint32_t e = b + threadIdx.x;
+      unsigned isL = (e < cnt && !(key[lo + e] < pv)) ? 1u : 0u;
+      unsigned totL;
+      unsigned rl = bk::block_excl_scan<unsigned>(isL, sh32, totL);
+      if (isL) scrL[lo + nL + rl] = lo + e;
+      nL += totL;
+      uint32_t er = b + threadIdx.x;                       // e-th from the right
+      unsigned isR = (er < cnt && !(pv < key[l - 1 - er])) ? 1u : 0u;
+      unsigned totR;
+      unsigned rr = bk::block_excl_scan<unsigned>(isR, sh32, totR);
+      if (isR) scrR[lo + nR + rr] = l - 1 - er;
+      nR += totR;
+    }
+    __syncthreads();
+    // K = number of k with L[k] < R[k] (the predicate is true on a prefix)
+    unsigned mn = min(nL, nR), kc = 0;
+    for (unsigned k = threadIdx.x; k < mn; k += IS_THREADS) kc += (scrL[lo + k] < scrR[lo + k]) ? 1u : 0u;
+    unsigned Ktot;
+    bk::block_excl_scan<unsigned>(kc, sh32, Ktot);
+    if (threadIdx.x == 0) sh_K = Ktot;
+    __syncthreads();
+    unsigned K = sh_K;
+    for (unsigned k = threadIdx.x; k < K; k += IS_THREADS) {
+      uint32_t a = scrL[lo + k], b2 = scrR[lo + k];
+      uint32_t tk = key[a], tv = val[a];
+      key[a] = key[b2]; val[a] = val[b2];
+      key[b2] = tk; val[b2] = tv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t rprev = K ? scrR[lo + K - 1] : l;
+      uint32_t cut = (K < nL && scrL[lo + K] < rprev) ? scrL[lo + K] : rprev;
+      Seg c2[2] = {Seg{cut, l, s.depth - 1}, Seg{f, cut, s.depth - 1}};
+      for (int q = 0; q < 2; ++q) {
+        uint32_t sz = c2[q].l - c2[q].f;
+        if (sz > 16) nxt[atomicAdd(n_nxt, 1u)] = c2[q];
+        else if (sz >= 2) term[atomicAdd(n_term, 1u)] = c2[q];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void is_terminal(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__restrict__ term, const unsigned *__restrict__ n_term)
+{
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned n = *n_term;
+  for (; t < n; t += gridDim.x * blockDim.x) seg_insertion_sort(key, val, term[t].f, term[t].l);
+}
+
+// =============================================================================================
+// K4: isolated-pair mask (src/BreakID.cc:1813-1877) over all buckets at once.
+// cur[] holds pair ids in the current (sorted) order, seg_off the bucket boundaries.
+// out_count[p] = how many copies of element p survive (0, 1, or 2 for position 1 of a bucket).
+// =============================================================================================
+__device__ __forceinline__ long long gap32(uint32_t a, uint32_t b)
+{
+  int32_t d = (int32_t)(a - b);
+  return d < 0 ? -(long long)d : (long long)d;
+}
+
+__global__ void k4_mask_count(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ bucket_of, const uint32_t *__restrict__ seg_off,
+                              long long np, const uint32_t *__restrict__ x, const uint32_t *__restrict__ y, long long distance,
+                              uint32_t *__restrict__ out_count)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  uint32_t b = bucket_of[p];
+  uint32_t s = seg_off[b], e = seg_off[b + 1];
+  uint32_t n = e - s, i = (uint32_t)p - s;
+  unsigned c = 0;
+  if (n >= 3 && i >= 1 && i + 1 < n) {
+    uint32_t a = cur[p - 1], m = cur[p], z = cur[p + 1];
+    long long ll = gap32(x[a], x[m]), lr = gap32(x[z], x[m]);
+    long long Lx = ll < lr ? ll : lr;
+    ll = gap32(y[a], y[m]); lr = gap32(y[z], y[m]);
+    long long Ly = ll < lr ? ll : lr;
+    if (!(Lx > distance || Ly > distance)) c = 1;
+    if (i == 1) {                                            // "first read pair" test uses e[1], e[2] (:1830-1835)
+      long long fx = gap32(x[m], x[z]), fy = gap32(y[m], y[z]);
+      if (!(fx > distance || fy > distance)) c += 1;
+    }
+  }
+  out_count[p] = c;
+}
+
+__global__ void k4_mask_write(const uint32_t *__restrict__ cur, const uint32_t *__restrict__ bucket_of, long long np,
+                              const uint32_t *__restrict__ out_count, const uint32_t *__restrict__ out_off,
+                              uint32_t *__restrict__ cur_out, uint32_t *__restrict__ bucket_of_out)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  uint32_t c = out_count[p], o = out_off[p];
+  for (uint32_t k = 0; k < c; ++k) { cur_out[o + k] = cur[p]; bucket_of_out[o + k] = bucket_of[p]; }
+}
+
+// new bucket offsets = scanned offsets sampled at the old bucket starts
+__global__ void k4_new_offsets(const uint32_t *__restrict__ seg_off, int nb, const uint32_t *__restrict__ out_off, long long np, unsigned long long total,
+                               uint32_t *__restrict__ seg_off_out)
+{
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  uint32_t s = seg_off[b];
+  seg_off_out[b] = (s < np) ? out_off[s] : (uint32_t)total;
+}
+
+__global__ void gather_u32(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, long long n, uint32_t *__restrict__ dst)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = src[idx[p]];
+}
+__global__ void iota_u32(uint32_t *dst, long long n)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = (uint32_t)p;
+}
+__global__ void pair_xy(const bkid_pair *__restrict__ pairs, long long np, uint32_t *__restrict__ x, uint32_t *__restrict__ y, uint32_t *__restrict__ bucket_of)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < np) { x[p] = pairs[p].p1_chr_pos; y[p] = pairs[p].p2_chr_pos; bucket_of[p] = (uint32_t)pairs[p].bucket; }
+}
+
+#include "bkid_cluster.cuh"
+#include "bkid_refine.cuh"
+#include "bkid_api.cuh"

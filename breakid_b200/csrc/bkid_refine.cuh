@@ -1,0 +1,543 @@
+// bkid_refine.cuh -- K7 split-read evidence, K8 breakpoint vote, K9 depth/AF, K10 nib 41-mer.
+// Included by bkid_core.cu.
+//
+// The reference answers every per-cluster question with a BAM index query + inflate
+// (src/BreakID.cc:436-474).  Here the records are resident in HBM in coordinate order, so a region
+// query is two binary searches on (tid,pos) plus a window scan with the index iterator's exact
+// overlap rule (htslib hts.c:1776-1777,1963-1965: same tid, pos < end, bam_endpos > max(beg,0)).
+#pragma once
+
+// ---- CIGAR algebra (src/CigarRoller.cc:26-136,187-205,316-346; src/Cigar.cc:80-144) -----------------
+// A "roller" keeps adjacent equal operations merged; op codes follow the reference enum
+// (src/Cigar.h:66-77): 1 match, 3 insert, 4 del, 5 skip, 6 softClip, 7 hardClip, 8 pad.
+struct Roller {
+  // only what the path needs: first two merged ops, op count, totals
+  int nops;
+  int op0, op1;
+  uint32_t c0, c1;
+  int last_op; uint32_t last_cnt;        // last merged op (for end clips)
+  int matches, ref_count;
+  int begin_clips, end_clips;            // accumulated while scanning
+  bool in_begin;
+  bool bad;                              // more structure than we summarise and it matters not: regex fails when nops != 2
+};
+
+__device__ __forceinline__ void roller_init(Roller &r)
+{
+  r.nops = 0; r.op0 = r.op1 = 0; r.c0 = r.c1 = 0; r.last_op = 0; r.last_cnt = 0;
+  r.matches = 0; r.ref_count = 0; r.begin_clips = 0; r.end_clips = 0; r.in_begin = true; r.bad = false;
+}
+__device__ __forceinline__ void roller_add(Roller &r, int op, int count)
+{
+  if ((uint32_t)count == 0) return;                                 // operator+= :33-36
+  if (r.nops == 0 || r.last_op != op) {
+    if (r.nops == 0) { r.op0 = op; r.c0 = (uint32_t)count; }
+    else if (r.nops == 1) { r.op1 = op; r.c1 = (uint32_t)count; }
+    r.nops++;
+    r.last_op = op; r.last_cnt = (uint32_t)count;
+  } else {
+    r.last_cnt += (uint32_t)count;
+    if (r.nops == 1) r.c0 = r.last_cnt; else if (r.nops == 2) r.c1 = r.last_cnt;
+  }
+  if (op == 1) r.matches += count;
+  if (op == 1 || op == 2 || op == 4 || op == 5) r.ref_count += count;
+  bool clip = (op == 6 || op == 7);
+  if (clip && r.in_begin) r.begin_clips += count;
+  if (!clip) r.in_begin = false;
+  if (clip) r.end_clips += count; else r.end_clips = 0;
+}
+__device__ __forceinline__ void roller_add_char(Roller &r, int ch, int count)   // Add(char,int) :67-117
+{
+  switch (ch) {
+    case 0: case 'M': roller_add(r, 1, count); break;
+    case 1: case 'I': roller_add(r, 3, count); break;
+    case 2: case 'D': roller_add(r, 4, count); break;
+    case 3: case 'N': roller_add(r, 5, count); break;
+    case 4: case 'S': roller_add(r, 6, count); break;
+    case 5: case 'H': roller_add(r, 7, count); break;
+    case 6: case 'P': roller_add(r, 8, count); break;
+    case 7: case '=': roller_add(r, 1, count); break;
+    case 8: case 'X': roller_add(r, 1, count); break;
+    default: break;
+  }
+}
+// all-clip cigars: begin clips count every op, end clips too (both loops run over everything)
+__device__ __forceinline__ void roller_set_text(Roller &r, const uint8_t *s, uint32_t len)   // Add(const char*) :120-136
+{
+  roller_init(r);
+  int cnt = 0;
+  uint32_t i = 0;
+  while (i < len) {
+    uint8_t ch = s[i];
+    if (ch >= '0' && ch <= '9') {
+      // (int) strtol: saturate at LONG_MAX then truncate
+      unsigned long long v = 0; bool sat = false;
+      while (i < len && s[i] >= '0' && s[i] <= '9') {
+        if (!sat) { v = v * 10 + (s[i] - '0'); if (v > 0x7fffffffffffffffull) { sat = true; v = 0x7fffffffffffffffull; } }
+        ++i;
+      }
+      cnt = (int)(long long)v;
+    } else { roller_add_char(r, ch, cnt); ++i; }
+  }
+}
+__device__ __forceinline__ void roller_set_bam(Roller &r, const uint32_t *ops, uint32_t n)
+{
+  roller_init(r);
+  for (uint32_t i = 0; i < n; ++i) roller_add_char(r, (int)(ops[i] & 0xF), (int)(ops[i] >> 4));
+}
+__device__ __forceinline__ char roller_op_char(int op)
+{
+  switch (op) { case 1: case 2: return 'M'; case 3: return 'I'; case 4: return 'D'; case 5: return 'N'; case 6: return 'S'; case 7: return 'H'; case 8: return 'P'; }
+  return '?';
+}
+// the merged string matches ([0-9]+[MS]){2}  <=>  exactly two merged ops, each M or S
+__device__ __forceinline__ bool roller_regex_2ms(const Roller &r)
+{
+  return r.nops == 2 && (r.op0 == 1 || r.op0 == 6) && (r.op1 == 1 || r.op1 == 6);
+}
+// full match of ([0-9]+[MS]){2} on raw text
+__device__ __forceinline__ bool text_regex_2ms(const uint8_t *s, uint32_t len)
+{
+  uint32_t i = 0;
+  for (int g = 0; g < 2; ++g) {
+    uint32_t d = i;
+    while (i < len && s[i] >= '0' && s[i] <= '9') ++i;
+    if (i == d || i >= len || (s[i] != 'M' && s[i] != 'S')) return false;
+    ++i;
+  }
+  return i == len;
+}
+__device__ __forceinline__ uint64_t fnv_bytes(uint64_t h, const uint8_t *s, uint32_t len)
+{
+  for (uint32_t i = 0; i < len; ++i) h = (h ^ s[i]) * 0x100000001b3ULL;
+  return h;
+}
+__device__ __forceinline__ uint64_t fnv_uint(uint64_t h, uint32_t v)     // std::to_string(unsigned)
+{
+  char buf[10]; int n = 0;
+  do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) h = (h ^ (uint8_t)buf[--n]) * 0x100000001b3ULL;
+  return h;
+}
+// hash of the roller's string form (valid for the <= 2-op rollers that pass the regex)
+__device__ __forceinline__ uint64_t roller_str_hash(const Roller &r)
+{
+  uint64_t h = 0xcbf29ce484222325ULL;
+  h = fnv_uint(h, r.c0); h = (h ^ (uint8_t)roller_op_char(r.op0)) * 0x100000001b3ULL;
+  h = fnv_uint(h, r.c1); h = (h ^ (uint8_t)roller_op_char(r.op1)) * 0x100000001b3ULL;
+  return h;
+}
+// chromosome-name code: t in 0..23 when the string equals chromID2ChrName(t) (src/util_bam.cc:128-142),
+// ~0 for "", otherwise FNV hash with the top bit set.  The host applies the same rule to header names.
+__device__ __host__ inline uint64_t chr_code(const uint8_t *s, uint32_t len)
+{
+  if (len == 0) return ~0ull;
+  if (len >= 4 && s[0] == 'c' && s[1] == 'h' && s[2] == 'r') {
+    if (len == 4 && s[3] == 'X') return 22;
+    if (len == 4 && s[3] == 'Y') return 23;
+    if (len == 4 && s[3] >= '1' && s[3] <= '9') return (uint64_t)(s[3] - '1');
+    if (len == 5 && s[3] >= '1' && s[3] <= '2' && s[4] >= '0' && s[4] <= '9') {
+      int v = (s[3] - '0') * 10 + (s[4] - '0');
+      if (v >= 10 && v <= 22) return (uint64_t)(v - 1);
+    }
+  }
+  uint64_t h = 0xcbf29ce484222325ULL;
+  for (uint32_t i = 0; i < len; ++i) h = (h ^ s[i]) * 0x100000001b3ULL;
+  return h | (1ull << 63);
+}
+
+struct EvRow {
+  uint64_t pchr, schr, pcig, scig;
+  uint32_t pstart, sstart, pend, send, pbp, sbp;
+  uint8_t ok;        // complementary cigars (counts as evidence)
+  uint8_t fatal;     // the reference would exit(-1) "error cigar" on this record
+  uint8_t secondary;
+  uint8_t _pad[5];
+};
+
+// K7a: one thread per SA-tagged record -- src/BreakID.cc:896-1016
+__global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long n_sa, const uint16_t *__restrict__ flag, const int32_t *__restrict__ tid,
+                                 const int32_t *__restrict__ pos, const uint32_t *__restrict__ cig_off, const uint32_t *__restrict__ cig_ops,
+                                 const uint32_t *__restrict__ sa_off, const uint8_t *__restrict__ sa_txt, const uint32_t *__restrict__ oc_off,
+                                 const uint8_t *__restrict__ oc_txt, int mismatch, EvRow *__restrict__ rows)
+{
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_sa) return;
+  EvRow R;
+  memset(&R, 0, sizeof R);
+  uint32_t i = sa_rec[k];
+  unsigned fl = flag[i];
+  const uint8_t *sa = sa_txt + sa_off[k]; uint32_t sal = sa_off[k + 1] - sa_off[k];
+  const uint8_t *oc = oc_txt + oc_off[k]; uint32_t ocl = oc_off[k + 1] - oc_off[k];
+  // split_string(sa, ",") drops empty fields (src/util_bed.cc:194-222): fields 0,1,3 of the first entry
+  uint32_t fs[4], fe[4]; int nf = 0;
+  {
+    uint32_t p = 0;
+    while (p < sal && nf < 4) {
+      while (p < sal && sa[p] == ',') ++p;
+      if (p >= sal) break;
+      uint32_t q = p;
+      while (q < sal && sa[q] != ',') ++q;
+      fs[nf] = p; fe[nf] = q; ++nf;
+      p = q;
+    }
+  }
+  if (sal == 0 || nf < 4 || (fl & F_DUP) || !(fl & F_PAIRED)) { rows[k] = R; return; }
+  Roller sa_c, rec_c, c1;
+  roller_set_text(sa_c, sa + fs[3], fe[3] - fs[3]);
+  roller_set_bam(rec_c, cig_ops + cig_off[k], cig_off[k + 1] - cig_off[k]);
+  if (ocl) roller_set_text(c1, oc, ocl); else c1 = rec_c;
+  // is_complementary_cigar (src/CigarRoller.cc:323-346)
+  bool ok = roller_regex_2ms(c1) && text_regex_2ms(sa + fs[3], fe[3] - fs[3]);
+  if (ok) {
+    int c1_m = c1.matches, c2_m = sa_c.matches;
+    int c1_s = c1.begin_clips + c1.end_clips, c2_s = sa_c.end_clips + sa_c.begin_clips;
+    ok = (c1_m <= c2_s + mismatch && c1_m >= c2_s - mismatch) && (c1_m + c1_s == c2_m + c2_s);
+  }
+  if (!ok) { rows[k] = R; return; }
+  R.ok = 1;
+  R.secondary = (fl & F_SECONDARY) ? 1 : 0;
+  // stoi(field 1)
+  long long sv = 0; bool neg = false;
+  {
+    uint32_t p = fs[1];
+    while (p < fe[1] && (sa[p] == ' ' || (sa[p] >= 9 && sa[p] <= 13))) ++p;
+    if (p < fe[1] && (sa[p] == '+' || sa[p] == '-')) { neg = sa[p] == '-'; ++p; }
+    while (p < fe[1] && sa[p] >= '0' && sa[p] <= '9') { sv = sv * 10 + (sa[p] - '0'); if (sv > 0x7fffffffll) sv = 0x7fffffffll; ++p; }
+    if (neg) sv = -sv;
+  }
+  uint32_t sa_start = (uint32_t)(int)sv;
+  uint32_t sa_end = sa_start + (uint32_t)sa_c.ref_count - 1u;
+  uint32_t a_start = (uint32_t)((long long)pos[i] + 1);
+  int alen = rec_c.ref_count;
+  uint32_t a_end = (uint32_t)((long long)(alen == 0 ? pos[i] : pos[i] + alen - 1) + 1);
+  int t = tid[i];
+  uint64_t own_chr = (t >= 0 && t < 24) ? (uint64_t)t : ~0ull;
+  uint64_t sa_chr = chr_code(sa + fs[0], fe[0] - fs[0]);
+  uint32_t own_end = ocl ? (a_start + (uint32_t)c1.ref_count - 1u) : a_end;
+  uint64_t own_cig = ocl ? fnv_bytes(0xcbf29ce484222325ULL, oc, ocl) : roller_str_hash(rec_c);
+  uint64_t sa_cig = fnv_bytes(0xcbf29ce484222325ULL, sa + fs[3], fe[3] - fs[3]);
+  uint32_t own_bp = 0, sa_bp = 0;
+  if (c1.begin_clips != 0) own_bp = a_start; else if (c1.end_clips != 0) own_bp = a_end; else R.fatal = 1;
+  if (sa_c.begin_clips != 0) sa_bp = sa_start; else if (sa_c.end_clips != 0) sa_bp = sa_end; else R.fatal = 1;
+  if (!R.secondary) {
+    R.pchr = own_chr; R.pstart = a_start; R.pend = own_end; R.pcig = own_cig; R.pbp = own_bp;
+    R.schr = sa_chr; R.sstart = sa_start; R.send = sa_end; R.scig = sa_cig; R.sbp = sa_bp;
+  } else {
+    R.pchr = sa_chr; R.pstart = sa_start; R.pend = sa_end; R.pcig = sa_cig; R.pbp = sa_bp;
+    R.schr = own_chr; R.sstart = a_start; R.send = own_end; R.scig = own_cig; R.sbp = own_bp;
+  }
+  rows[k] = R;
+}
+
+// ---- record window helpers --------------------------------------------------------------------
+// first record index with (tid,pos) >= (qt,qp); records are coordinate sorted, tid < 0 sorts last
+__device__ __forceinline__ long long rec_lower_bound(const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, long long n, int qt, long long qp)
+{
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    long long m = (lo + hi) >> 1;
+    uint32_t tm = (uint32_t)tid[m];
+    bool less = tm < (uint32_t)qt || (tm == (uint32_t)qt && (long long)pos[m] < qp);
+    if (less) lo = m + 1; else hi = m;
+  }
+  return lo;
+}
+__device__ __forceinline__ long long u32_lower_bound(const uint32_t *__restrict__ a, long long n, long long q)
+{
+  long long lo = 0, hi = n;
+  while (lo < hi) { long long m = (lo + hi) >> 1; if ((long long)a[m] < q) lo = m + 1; else hi = m; }
+  return lo;
+}
+
+struct RegionQ {        // one side of one cluster
+  int tid; int beg, end;            // iterator bounds after clamping (beg >= 0)
+  long long r_lo, r_hi;             // record window [r_lo, r_hi): pos in [beg - maxspan, end)
+  long long s_lo, s_hi;             // SA-slot window
+};
+
+struct RefineView {
+  long long n; const uint16_t *flag; const uint8_t *cls; const int32_t *tid, *pos, *endpos; const uint64_t *nh;
+  long long n_sa; const uint32_t *sa_rec; const EvRow *rows;
+  int maxspan;
+  const uint64_t *canon;            // [nt] chr_code of the header names
+  int nt;
+  const uint8_t *const *nib; const uint64_t *nib_len;   // per tid, may be null
+};
+
+__device__ __forceinline__ void make_region(const RefineView &v, int tid, uint32_t start_u, uint32_t end_u, RegionQ &q)
+{
+  q.tid = tid;
+  int beg = (int)start_u, end = (int)end_u;
+  if (beg < 0) beg = 0;                                       // hts.c:1776
+  q.beg = beg; q.end = end;
+  if (end < beg || tid < 0) { q.r_lo = q.r_hi = 0; q.s_lo = q.s_hi = 0; return; }
+  q.r_lo = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)beg - v.maxspan);
+  q.r_hi = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)end);
+  q.s_lo = u32_lower_bound(v.sa_rec, v.n_sa, q.r_lo);
+  q.s_hi = u32_lower_bound(v.sa_rec, v.n_sa, q.r_hi);
+}
+
+// K7b: per cluster, both regions: coverage, evidence list (SA slots), gate.  One CTA per cluster.
+// ev_list has room for (s_hi-s_lo) of side 1 then side 2 at ev_off[c].
+struct ClusterWork {
+  RegionQ q1, q2;
+  uint32_t n_ev1, n_ev2;     // evidence rows that survive the gate (0 when the side is empty)
+  uint32_t n_entries;
+  uint32_t fatal;
+};
+
+__global__ void k7_regions(RefineView v, const bkid_cluster_rec *__restrict__ cl, uint32_t ncl, int w, ClusterWork *__restrict__ work, uint32_t *__restrict__ ev_cap)
+{
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncl) return;
+  const bkid_cluster_rec &R = cl[c];
+  ClusterWork W;
+  memset(&W, 0, sizeof W);
+  // src/BreakID.cc:430-433: uint64 mean -/+ int w, truncated to uint32, then passed as int
+  make_region(v, R.p1_tid, (uint32_t)(R.p1_mean_pos - (unsigned long long)(long long)w), (uint32_t)(R.p1_mean_pos + (unsigned long long)(long long)w), W.q1);
+  make_region(v, R.p2_tid, (uint32_t)(R.p2_mean_pos - (unsigned long long)(long long)w), (uint32_t)(R.p2_mean_pos + (unsigned long long)(long long)w), W.q2);
+  work[c] = W;
+  ev_cap[c] = (uint32_t)((W.q1.s_hi - W.q1.s_lo) + (W.q2.s_hi - W.q2.s_lo));
+}
+
+constexpr int RF_THREADS = 128;
+
+// counts coverage + collects evidence for one region (CTA-cooperative); returns via shared counters
+__device__ void region_collect(const RefineView &v, const RegionQ &q, uint32_t *__restrict__ list, unsigned *sh_cov, unsigned *sh_ev, unsigned *sh_fatal)
+{
+  if (threadIdx.x == 0) { *sh_cov = 0; *sh_ev = 0; }
+  __syncthreads();
+  unsigned cov = 0;
+  for (long long i = q.r_lo + threadIdx.x; i < q.r_hi; i += blockDim.x)
+    if (v.endpos[i] > q.beg) ++cov;                          // every record counts (src/BreakID.cc:894)
+  cov = bk::warp_sum(cov);
+  if ((threadIdx.x & 31) == 0 && cov) atomicAdd(sh_cov, cov);
+  // evidence rows in record order (ordered compaction so the list order is deterministic)
+  __shared__ unsigned sh32[33];
+  unsigned base = 0;
+  for (long long s0 = q.s_lo; s0 < q.s_hi; s0 += blockDim.x) {
+    long long s = s0 + threadIdx.x;
+    unsigned is = 0;
+    if (s < q.s_hi) {
+      uint32_t i = v.sa_rec[s];
+      if (v.endpos[i] > q.beg && v.rows[s].ok) { is = 1; if (v.rows[s].fatal) atomicExch(sh_fatal, 1u); }
+    }
+    unsigned tot;
+    unsigned r = bk::block_excl_scan<unsigned>(is, sh32, tot);
+    if (is) list[base + r] = (uint32_t)s;
+    base += tot;
+  }
+  if (threadIdx.x == 0) *sh_ev = base;
+  __syncthreads();
+}
+
+__device__ __forceinline__ bool ev_match(const RefineView &v, uint32_t sa, uint32_t sb)
+{
+  const EvRow &a = v.rows[sa], &b = v.rows[sb];
+  uint32_t ia = v.sa_rec[sa], ib = v.sa_rec[sb];
+  return v.nh[2 * (size_t)ia] == v.nh[2 * (size_t)ib] && v.nh[2 * (size_t)ia + 1] == v.nh[2 * (size_t)ib + 1] &&
+         a.secondary != b.secondary && a.pchr == b.pchr && a.schr == b.schr && a.pstart == b.pstart && a.sstart == b.sstart &&
+         a.pend == b.pend && a.send == b.send && a.pcig == b.pcig && a.scig == b.scig && a.pbp == b.pbp && a.sbp == b.sbp;   // new_condition :627-637
+}
+
+// pass 1 (count) / pass 2 (write) of find_sa_reads x2 + the pairing half of find_bp_pair
+template <bool WRITE>
+__global__ void __launch_bounds__(RF_THREADS)
+k7_collect(RefineView v, const bkid_cluster_rec *__restrict__ cl, uint32_t ncl, ClusterWork *__restrict__ work, const uint32_t *__restrict__ ev_off,
+           uint32_t *__restrict__ ev_list, const uint32_t *__restrict__ ent_off, int2 *__restrict__ entries)
+{
+  uint32_t c = blockIdx.x;
+  if (c >= ncl) return;
+  __shared__ unsigned sh_cov, sh_ev, sh_fatal, sh_cnt;
+  ClusterWork &W = work[c];
+  uint32_t *l1 = ev_list + ev_off[c];
+  uint32_t *l2 = l1 + (uint32_t)(W.q1.s_hi - W.q1.s_lo);
+  uint32_t n1, n2;
+  if (!WRITE) {
+    if (threadIdx.x == 0) sh_fatal = 0;
+    __syncthreads();
+    region_collect(v, W.q1, l1, &sh_cov, &sh_ev, &sh_fatal);
+    n1 = (sh_cov < 5 || sh_ev < 2) ? 0 : sh_ev;              // gate :1032-1035
+    __syncthreads();
+    n2 = 0;
+    if (n1 > 0) {                                            // side 2 only if side 1 has reads (:438-439)
+      region_collect(v, W.q2, l2, &sh_cov, &sh_ev, &sh_fatal);
+      n2 = (sh_cov < 5 || sh_ev < 2) ? 0 : sh_ev;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { W.n_ev1 = n1; W.n_ev2 = n2; W.fatal = sh_fatal; }
+  } else { n1 = W.n_ev1; n2 = W.n_ev2; }
+  if (threadIdx.x == 0) sh_cnt = 0;
+  __syncthreads();
+  uint64_t p1code = (cl[c].p1_tid >= 0 && cl[c].p1_tid < v.nt) ? v.canon[cl[c].p1_tid] : chr_code((const uint8_t *)"*", 1);
+  if (n1 > 0 && n2 > 0) {
+    // the reference walks names in map order, then i over side 1, j over side 2; the vote only needs the multiset
+    for (uint32_t a = threadIdx.x; a < n1; a += blockDim.x)
+      for (uint32_t b = 0; b < n2; ++b)
+        if (ev_match(v, l1[a], l2[b])) {
+          unsigned o = atomicAdd(&sh_cnt, 1u);
+          if (WRITE) {
+            const EvRow &A = v.rows[l1[a]];
+            int2 e;
+            if (A.pchr == p1code) { e.x = (int)A.pbp; e.y = (int)A.sbp; }       // :647,671-672
+            else { e.x = (int)A.sbp; e.y = (int)A.pbp; }                         // :717-718
+            entries[ent_off[c] + o] = e;
+          }
+        }
+  }
+  __syncthreads();
+  if (!WRITE && threadIdx.x == 0) W.n_entries = sh_cnt;
+}
+
+__global__ void k7_entry_counts(const ClusterWork *__restrict__ work, uint32_t ncl, uint32_t *__restrict__ cnt, int *__restrict__ fatal)
+{
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncl) return;
+  cnt[c] = work[c].n_entries;
+  if (work[c].fatal) atomicExch(fatal, 1);
+}
+
+// lexicographic order of to_string(x)+","+to_string(y) (std::map<string,int>, src/BreakID.cc:599,806)
+__device__ __forceinline__ int key_str(int x, int y, char *buf)
+{
+  int n = 0;
+  auto put = [&](int v) {
+    char t[12]; int m = 0;
+    long long a = v; bool neg = a < 0; if (neg) a = -a;
+    do { t[m++] = (char)('0' + a % 10); a /= 10; } while (a);
+    if (neg) buf[n++] = '-';
+    while (m) buf[n++] = t[--m];
+  };
+  put(x); buf[n++] = ','; put(y);
+  return n;
+}
+__device__ __forceinline__ bool key_less(int x1, int y1, int x2, int y2)
+{
+  char a[26], b[26];
+  int na = key_str(x1, y1, a), nb = key_str(x2, y2, b);
+  int m = na < nb ? na : nb;
+  for (int i = 0; i < m; ++i) {
+    unsigned char ca = (unsigned char)a[i], cb = (unsigned char)b[i];
+    if (ca != cb) return ca < cb;
+  }
+  return na < nb;
+}
+
+__device__ unsigned depth_at(const RefineView &v, int tid, unsigned long long pos1)
+{
+  // src/util_bed.cc:154-192: iterator over [pos-1, pos); count qual>0 && !DUP && PAIRED (class bit CL_DEPTH)
+  int beg = (int)(pos1 - 1), end = (int)pos1;
+  if (beg < 0) beg = 0;
+  if (end < beg || tid < 0) return 0;
+  long long lo = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)beg - v.maxspan);
+  long long hi = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)end);
+  unsigned d = 0;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x)
+    if (v.endpos[i] > beg && (v.cls[i] & CL_DEPTH)) ++d;
+  return d;
+}
+
+__device__ __forceinline__ char nib_base(const uint8_t *packed, uint64_t nbases, long long pos, char prev)
+{
+  if (pos < 0 || (uint64_t)pos >= nbases) return prev;                  // src/nibtools.cc:45-46 leaves the byte untouched
+  int b = packed[pos >> 1];
+  int x = (pos & 1) ? (b & 0xf) : (b >> 4);                             // high nibble first (:55-61)
+  switch (x) { case 0: case 8: return 'T'; case 1: case 9: return 'C'; case 2: case 10: return 'A'; case 3: case 11: return 'G'; default: return 'N'; }
+}
+
+// K8 + K9 + K10: vote, depth, AF, 41-mers.  One CTA per cluster.
+__global__ void __launch_bounds__(RF_THREADS)
+k8_vote(RefineView v, bkid_cluster_rec *__restrict__ cl, uint32_t ncl, const ClusterWork *__restrict__ work, const uint32_t *__restrict__ ent_off,
+        const int2 *__restrict__ entries, int bp_err, uint32_t *__restrict__ valid)
+{
+  uint32_t c = blockIdx.x;
+  if (c >= ncl) return;
+  __shared__ int sh_best, sh_x, sh_y;
+  __shared__ unsigned sh_d1, sh_d2;
+  __shared__ char sh_seq[2][44];
+  uint32_t m = work[c].n_entries;
+  const int2 *E = entries + ent_off[c];
+  if (threadIdx.x == 0) { sh_best = 0; sh_x = -1; sh_y = -1; sh_d1 = 0; sh_d2 = 0; }
+  __syncthreads();
+  // votes: entries within +-bp_err of each key, mixed int32/uint32 compares (:820-821)
+  int my_best = 0, mx = -1, my = -1;
+  for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+    uint32_t k1 = (uint32_t)E[i].x, k2 = (uint32_t)E[i].y;
+    int cnt = 0;
+    for (uint32_t j = 0; j < m; ++j) {
+      uint32_t a = (uint32_t)E[j].x, b = (uint32_t)E[j].y;
+      if (a <= k1 + (uint32_t)bp_err && a >= k1 - (uint32_t)bp_err && b <= k2 + (uint32_t)bp_err && b >= k2 - (uint32_t)bp_err) ++cnt;
+    }
+    if (cnt > my_best || (cnt == my_best && cnt > 0 && key_less(E[i].x, E[i].y, mx, my))) { my_best = cnt; mx = E[i].x; my = E[i].y; }
+  }
+  // block arg-max: highest count, ties -> lexicographically smallest key string (first strict max in map order, :841-855)
+  for (int o = 16; o; o >>= 1) {
+    int oc = __shfl_xor_sync(0xffffffffu, my_best, o), ox = __shfl_xor_sync(0xffffffffu, mx, o), oy = __shfl_xor_sync(0xffffffffu, my, o);
+    if (oc > my_best || (oc == my_best && oc > 0 && key_less(ox, oy, mx, my))) { my_best = oc; mx = ox; my = oy; }
+  }
+  __shared__ int wb[RF_THREADS / 32], wx[RF_THREADS / 32], wy[RF_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) { wb[threadIdx.x >> 5] = my_best; wx[threadIdx.x >> 5] = mx; wy[threadIdx.x >> 5] = my; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int b = 0, x = -1, y = -1;
+    for (int q = 0; q < RF_THREADS / 32; ++q)
+      if (wb[q] > b || (wb[q] == b && b > 0 && key_less(wx[q], wy[q], x, y))) { b = wb[q]; x = wx[q]; y = wy[q]; }
+    sh_best = b; sh_x = x; sh_y = y;
+  }
+  __syncthreads();
+  int votes = sh_best;
+  bool ok = votes >= 2;                                                   // :446
+  if (threadIdx.x == 0) valid[c] = ok ? 1u : 0u;
+  if (!ok) return;
+  bkid_cluster_rec &R = cl[c];
+  uint32_t p1e = (uint32_t)sh_x; int32_t p2e = sh_y;
+  unsigned d1 = depth_at(v, R.p1_tid, (unsigned long long)p1e);
+  unsigned d2 = depth_at(v, R.p2_tid, (unsigned long long)(long long)p2e);
+  d1 = bk::warp_sum(d1); d2 = bk::warp_sum(d2);
+  if ((threadIdx.x & 31) == 0) { if (d1) atomicAdd(&sh_d1, d1); if (d2) atomicAdd(&sh_d2, d2); }
+  // K10: 41-mer = 1-based [bp-20, bp+20] (src/BreakID.cc:554-557, src/util_bam.cc:78-122); sequential
+  // because an out-of-range base repeats the previous one
+  if (threadIdx.x < 2) {
+    int side = threadIdx.x;
+    int t = side ? R.p2_tid : R.p1_tid;
+    long long bp = side ? (long long)p2e : (long long)(int32_t)p1e;
+    char *out = sh_seq[side];
+    for (int k = 0; k < 44; ++k) out[k] = 0;
+    if (v.nib && t >= 0 && t < v.nt && v.nib[t]) {
+      char prev = 'N';
+      for (int k = 0; k < 41; ++k) { prev = nib_base(v.nib[t], v.nib_len[t], bp - 21 + k, prev); out[k] = prev; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    R.p1_exact_pos = p1e; R.p2_exact_pos = p2e; R.n_split_read = votes;
+    R.p1_bp_depth = (double)sh_d1; R.p2_bp_depth = (double)sh_d2;
+    R.p1_alle_freq = __fdiv_rn((float)(long long)votes, (float)R.p1_bp_depth);   // :475-478
+    R.p2_alle_freq = __fdiv_rn((float)(long long)votes, (float)R.p2_bp_depth);
+    int rpt = 0;
+    for (int side = 0; side < 2; ++side) {
+      const char *s = sh_seq[side];
+      int best = 0;
+      for (int i = 0; s[i];) { int j = i; while (s[j] == s[i]) ++j; if (j - i > best) best = j - i; i = j; }
+      if (best > 10) rpt = 1;                                                     // src/BreakID.cc:560-561
+      for (int k = 0; k < 44; ++k) (side ? R.p2_rpt : R.p1_rpt)[k] = s[k];
+    }
+    R.is_rpt = rpt;
+  }
+}
+
+__global__ void max_span_kernel(const int32_t *__restrict__ pos, const int32_t *__restrict__ endpos, long long n, int *__restrict__ out)
+{
+  int m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = max(m, endpos[i] - pos[i]);
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+__global__ void compact_clusters(const bkid_cluster_rec *__restrict__ src, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ off, uint32_t n,
+                                 bkid_cluster_rec *__restrict__ dst)
+{
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n && keep[c]) dst[off[c]] = src[c];
+}

@@ -1,0 +1,233 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bit-exact: everything on this path is integer / byte / index work, and the FP64 parts
+(insert sd, AHC distances) are required to be bit-identical too."""
+import numpy as np
+import pytest
+
+from conftest import lattice_points
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx1():
+    from breakid_b200 import api
+    c = api.Context([1000000], ["chr1"], device=0)
+    yield c
+    c.close()
+
+
+def test_sort_replay_matches_std_sort(ctx1):
+    import oracle_py as O
+    rng = np.random.RandomState(0)
+    sizes = [0, 1, 2, 3, 15, 16, 17, 18, 31, 32, 33, 50, 100, 257, 1000, 5000, 40000]
+    bad = []
+    for trial in range(120):
+        n = sizes[trial % len(sizes)] if trial % 2 else int(rng.randint(0, 600))
+        kind = trial % 6
+        if kind == 0: key = rng.randint(0, 5, n)
+        elif kind == 1: key = rng.randint(0, max(1, n // 3 + 1), n)
+        elif kind == 2: key = np.sort(rng.randint(0, n + 1, n))
+        elif kind == 3: key = np.sort(rng.randint(0, n + 1, n))[::-1].copy()
+        elif kind == 4: key = rng.randint(0, 2 ** 32, n)
+        else: key = np.repeat(rng.randint(0, 1000, n // 4 + 1), 4)[:n]
+        key = key.astype(np.uint32)
+        a = O.sort_perm(key)
+        b = ctx1.op_sort_perm(key)
+        if not np.array_equal(a, b):
+            bad.append((trial, n, kind))
+    assert not bad, bad
+
+
+def test_sort_replay_depth_limit(ctx1):
+    """median-of-3 killer sequences exhaust the introsort depth budget -> heapsort fallback"""
+    import oracle_py as O
+
+    def killer(n):
+        k = n // 2; a = np.zeros(n, np.uint32)
+        for i in range(1, k + 1):
+            if i % 2: a[i - 1] = i; a[i] = k + i
+            a[k + i - 1] = 2 * i
+        return a
+    for n in (64, 1000, 4096, 20000):
+        key = killer(n)
+        assert np.array_equal(O.sort_perm(key), ctx1.op_sort_perm(key)), n
+
+
+def test_remove_isolated(ctx1):
+    import oracle_py as O
+    rng = np.random.RandomState(1)
+    bad = []
+    for trial in range(150):
+        n = int(rng.randint(0, 400)); kind = trial % 4
+        x, y = lattice_points(rng, n, kind)
+        w = float(rng.choice([120.7, 260.2, 99.0, 1243.15]))
+        a = O.remove_isolated(x, y, w); b = ctx1.op_remove_isolated(x, y, w)
+        if not np.array_equal(a, b):
+            bad.append((trial, n, kind, len(a), len(b)))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cluster_ops(ctx1, mode):
+    import oracle_py as O
+    rng = np.random.RandomState(2 + mode)
+    bad = []
+    for trial in range(200):
+        n = int(rng.randint(2, 120)); kind = trial % 4
+        x, y = lattice_points(rng, n, kind)
+        w = float(rng.choice([120.7, 260.2, 99.0, 1243.15]))
+        keep = O.remove_isolated(x, y, w)
+        xs = np.ascontiguousarray(x[keep]); ys = np.ascontiguousarray(y[keep])
+        if len(xs) < 2:
+            continue
+        ei, ec, er = O.cluster(mode, xs, ys, w)
+        gi, gc, gr = ctx1.op_cluster(mode, xs, ys, w)
+        if mode == 0:
+            same = np.array_equal(ei, gi) and np.array_equal(ec, gc) and er == gr
+        else:   # -fast: the oracle lists members in p1 order, the device groups them by cluster id
+            o1 = np.lexsort((ei, ec)); o2 = np.lexsort((gi, gc))
+            same = np.array_equal(ei[o1], gi[o2]) and np.array_equal(ec[o1], gc[o2]) and er == gr
+        if not same:
+            bad.append((trial, kind, len(xs), len(ei), len(gi), er, gr))
+    assert not bad, bad
+
+
+def test_ahc_unsorted_heavy_ties(ctx1):
+    """util_cluster interface on arbitrary (unsorted) input with exact distance ties and duplicates"""
+    import oracle_py as O
+    rng = np.random.RandomState(9)
+    bad = []
+    for trial in range(150):
+        n = int(rng.randint(2, 70)); kind = trial % 3
+        if kind == 0:
+            x = rng.randint(0, 5, n) * 50; y = rng.randint(0, 5, n) * 50
+        elif kind == 1:
+            k = max(1, n // 6); a = rng.randint(0, k, n); x = a * 1000 + rng.randint(0, 4, n) * 50; y = (a % 2) * 800 + rng.randint(0, 4, n) * 50
+        else:
+            k = max(1, n // 5); a = rng.randint(0, k, n); x = a * 500 + rng.randint(0, 3, n) * 50; y = rng.randint(0, 3, n) * 50 + (a % 3) * 400
+        thr = float(rng.choice([60, 120, 200, 260]))
+        x = x.astype(np.uint32); y = y.astype(np.uint32)
+        ei, ec, er = O.cluster(0, x, y, thr)
+        gi, gc, gr = ctx1.op_cluster(0, x, y, thr)
+        if not (np.array_equal(ei, gi) and np.array_equal(ec, gc) and er == gr):
+            bad.append((trial, kind, n, thr))
+    assert not bad, bad
+
+
+def _ctx_for(hb, **kw):
+    from breakid_b200 import api
+    c = api.Context(hb.target_len, hb.target_names, device=0, **kw)
+    c.push(hb)
+    return c
+
+
+def test_insert_stats_and_classify(small_data):
+    import oracle_py as O
+    d, hb, nibs = small_data
+    c = _ctx_for(hb)
+    m, s = c.insert_stats()
+    om, osd, S, n, T = O.insert_stats(hb)
+    assert (m, s) == (om, osd)
+    cls = c.fetch_class(hb.n)
+    f = hb.cols["flag"].astype(np.int64); q = hb.cols["mapq"].astype(np.int64)
+    ins = ((f & 1) != 0) & ((f & 2) != 0) & ((f & (0x4 | 0x100 | 0x200 | 0x400)) == 0)
+    cand = (q >= 20) & ((f & 0x400) == 0) & ((f & 0x100) == 0) & ((f & 1) != 0) & ((f & 2) == 0)
+    dep = (q > 0) & ((f & 0x400) == 0) & ((f & 1) != 0)
+    assert np.array_equal((cls & 1) != 0, ins)
+    assert np.array_equal((cls & 2) != 0, cand)
+    assert np.array_equal((cls & 4) != 0, dep)
+    c.close()
+
+
+def test_insert_sd_adversarial():
+    """the truncating accumulator: huge insert sizes push the running total through many binades"""
+    import oracle_py as O
+    from breakid_b200 import api
+    rng = np.random.RandomState(3)
+    for case in range(4):
+        n = [5000, 70000, 300000, 20000][case]
+        isz = rng.randint(-2000, 2000, n).astype(np.int32)
+        if case == 1: isz = (rng.randint(0, 2, n) * rng.randint(0, 3000000, n)).astype(np.int32)
+        if case == 3: isz = rng.randint(-2000000000, 2000000000, n).astype(np.int32)     # leaves the closed form (t >= 2^52)
+        flag = np.where(rng.rand(n) < 0.9, 99, rng.choice([97, 1123, 355, 4], n)).astype(np.uint16)
+        z = np.zeros(n, np.int32)
+        hb = api.HostBatch({"flag": flag, "mapq": np.full(n, 60, np.uint8), "tid": z, "pos": np.arange(n, dtype=np.int32), "mtid": z, "mpos": z,
+                            "isize": isz, "endpos": np.arange(n, dtype=np.int32) + 100}, np.arange(2 * n, dtype=np.uint64),
+                           {"sa_rec": np.zeros(0, np.uint32), "cig_off": np.zeros(1, np.uint32), "cig_ops": np.zeros(0, np.uint32),
+                            "sa_off": np.zeros(1, np.uint32), "sa_txt": np.zeros(0, np.uint8)}, [1000000000], ["chr1"])
+        c = _ctx_for(hb)
+        got = c.insert_stats()
+        exp = O.insert_stats(hb)
+        assert got == exp[:2], (case, got, exp)
+        c.close()
+
+
+def test_scan_pairs(small_data):
+    import oracle_py as O
+    d, hb, nibs = small_data
+    c = _ctx_for(hb)
+    m, s = c.insert_stats()
+    w = O.dist(m, s)
+    n = c.scan(w)
+    got = c.fetch_pairs(0)
+    exp = O.scan(hb, 20, w)
+    assert n == len(exp)
+    for k in exp.dtype.names:
+        assert np.array_equal(got[k], exp[k]), k
+    c.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_whole_path(small_data, mode):
+    import oracle_py as O
+    d, hb, nibs = small_data
+    c = _ctx_for(hb, fast=mode)
+    for t, (p, l) in enumerate(nibs):
+        c.set_nib(t, p, l)
+    mean, sd, dist, ncall = c.run()
+    got = c.fetch_clusters()
+    om, osd, od, exp = O.run(hb, nibs, mode=mode)
+    assert (mean, sd, dist) == (om, osd, od)
+    assert len(got) == len(exp), (len(got), len(exp))
+    for k in exp.dtype.names:
+        assert np.array_equal(got[k], exp[k]), (k, got[k], exp[k])
+    assert len(got) >= 5
+    c.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_whole_path_config1(config1_data, mode):
+    import oracle_py as O
+    d, hb, nibs = config1_data
+    c = _ctx_for(hb, fast=mode)
+    for t, (p, l) in enumerate(nibs):
+        c.set_nib(t, p, l)
+    mean, sd, dist, ncall = c.run()
+    got = c.fetch_clusters()
+    om, osd, od, exp = O.run(hb, nibs, mode=mode)
+    assert (mean, sd, dist) == (om, osd, od)
+    assert got.tobytes() == exp.tobytes()
+    assert len(got) == 10          # every planted SV is called
+    c.close()
+
+
+def test_batched_push_equals_single_push(small_data):
+    """records arriving in several batches (streaming decode) give the same result"""
+    from breakid_b200 import api
+    d, hb, nibs = small_data
+    c1 = _ctx_for(hb)
+    r1 = c1.run(); g1 = c1.fetch_clusters()
+    c2 = api.Context(hb.target_len, hb.target_names, device=0)
+    cuts = [0, hb.n // 3, hb.n // 2 + 7, hb.n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sa = hb.side["sa_rec"]; lo = np.searchsorted(sa, a); hi = np.searchsorted(sa, b)
+        co, so, oo = hb.side["cig_off"], hb.side["sa_off"], hb.side["oc_off"]
+        part = api.HostBatch({k: v[a:b] for k, v in hb.cols.items()}, hb.name_hash[2 * a:2 * b],
+                             {"sa_rec": sa[lo:hi] - a, "cig_off": co[lo:hi + 1] - co[lo], "cig_ops": hb.side["cig_ops"][co[lo]:co[hi]],
+                              "sa_off": so[lo:hi + 1] - so[lo], "sa_txt": hb.side["sa_txt"][so[lo]:so[hi]],
+                              "oc_off": oo[lo:hi + 1] - oo[lo], "oc_txt": hb.side["oc_txt"][oo[lo]:oo[hi]]}, hb.target_len, hb.target_names)
+        c2.push(part)
+    r2 = c2.run(); g2 = c2.fetch_clusters()
+    assert r1 == r2 and g1.tobytes() == g2.tobytes()
+    c1.close(); c2.close()
