@@ -190,11 +190,11 @@ def generate(cfg: SynthConfig, device="cpu") -> SynthData:
 
     def emit(flag, mapq, tid, pos, mtid, mpos, isize, endpos, name_id, sa_idx=None):
         n = flag.numel()
-        cols["flag"].append(flag.to(torch.int64))
-        cols["mapq"].append(mapq.to(torch.int64))
-        cols["tid"].append(tid); cols["pos"].append(pos)
-        cols["mtid"].append(mtid); cols["mpos"].append(mpos)
-        cols["isize"].append(isize); cols["endpos"].append(endpos)
+        cols["flag"].append(flag.to(torch.int16))
+        cols["mapq"].append(mapq.to(torch.uint8))
+        cols["tid"].append(tid.to(torch.int32)); cols["pos"].append(pos.to(torch.int32))
+        cols["mtid"].append(mtid.to(torch.int32)); cols["mpos"].append(mpos.to(torch.int32))
+        cols["isize"].append(isize.to(torch.int32)); cols["endpos"].append(endpos.to(torch.int32))
         cols["name_id"].append(name_id)
         sa_mark.append(sa_idx if sa_idx is not None else torch.full((n,), -1, dtype=torch.int64, device=dev))
 
@@ -333,19 +333,19 @@ def generate(cfg: SynthConfig, device="cpu") -> SynthData:
                              o1=torch.cat([torch.where(inv, torch.full_like(k, OP_S), torch.full_like(k, OP_M)), torch.full_like(k, OP_S)])))
 
     # ---------------- merge + coordinate sort ----------------
-    C = {k: torch.cat(v) for k, v in cols.items()}
+    C = {}
+    for k in list(cols.keys()):
+        C[k] = torch.cat(cols.pop(k))
     mark = torch.cat(sa_mark)
-    key = (C["tid"] << 32) | C["pos"]
+    del sa_mark
+    key = (C["tid"].to(torch.int64) << 32) | C["pos"].to(torch.int64)
     order = torch.sort(key, stable=True).indices
-    out = {
-        "flag": C["flag"][order].to(torch.int16),
-        "mapq": C["mapq"][order].to(torch.uint8),
-        "tid": C["tid"][order].to(torch.int32), "pos": C["pos"][order].to(torch.int32),
-        "mtid": C["mtid"][order].to(torch.int32), "mpos": C["mpos"][order].to(torch.int32),
-        "isize": C["isize"][order].to(torch.int32), "endpos": C["endpos"][order].to(torch.int32),
-        "name_id": C["name_id"][order],
-    }
+    del key
+    out = {}
+    for k in list(C.keys()):
+        out[k] = C.pop(k)[order]
     mark = mark[order]
+    del order
     sa_rec = torch.nonzero(mark >= 0).flatten()
     sa_src = mark[sa_rec]                           # index into generation-order SA arrays
     n_sa = sa_rec.numel()
