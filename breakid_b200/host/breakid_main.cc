@@ -1,0 +1,233 @@
+// breakid_main.cc -- drop-in `BreakID` command-line driver on top of the B200 C ABI.
+//
+// Same process contract as the reference main() (reference src/BreakID.cc:6-192): flags
+// -i -o -n -q -t -fast -all -h -? (single-dash long options, src/BreakID.cc:15-26), outputs
+// <o>_fusion.txt, <o>_fusion_all.txt (with -all), <o>_params.txt, <o>_performance.txt, error
+// messages + exit(1) as the reference prints them.  Differences, all additive and default-neutral:
+//   * the option table is terminated, so unknown flags report an error instead of segfaulting, and
+//     -t takes its argument (the reference declares has_arg=0 and then reads optarg);
+//   * -s <k>   sd multiplier of the distance formula (the literal 3 at src/BreakID.cc:103);
+//   * -r <refGene.txt> (default: $BREAKID_INSTALLDIR/ref_files/refGene.txt), -threads, -gpu.
+// Host work: BAM decode (bam_reader.cc), .nib loading, refGene annotation, the final unstable sort
+// by N_DRP and file writing.  Everything between decode and the cluster records runs on the GPU.
+#include <getopt.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/breakid_b200.h"
+#include "annotate.h"
+#include "bam_reader.h"
+#include "nibtools.h"
+
+static const char *kHelp =
+    " Usage: \n \t BreakID -i input.bam -o prefix -n nib_folder <options> \n\n "
+    "     DESCRIPTION\n "
+    "     \t -h -? -help \t help\n "
+    "     \t -i*        \t input bam-file\n "
+    "     \t -o*        \t output file (prefix only)\n "
+    "     \t -n*        \t folder name to nib files\n "
+    "     \t -q         \t encompassing reads quality thresholds  [20]\n"
+    "     \t -t         \t distance relative to (sqrt(2)*(insert size mean +3* insert size sd))  [2]\n "
+    "     \t -fast      \t use the fast cluster strategy [default no] \n "
+    "     \t -all       \t no filter enspan out [default is filter]  \n "
+    "     \t -s         \t sd multiplier of the distance formula [3]\n "
+    "     \t -r         \t refGene.txt [$BREAKID_INSTALLDIR/ref_files/refGene.txt]\n "
+    "     \t -threads   \t BAM decode threads [8]\n "
+    "     \t -gpu       \t CUDA device [0]\n ";
+
+static const char *kFusion[] = {"Unknown", "Translocation", "Inversion", "Duplication", "Deletion"};
+
+struct CallRow {
+  bkid_cluster_rec c;
+  SideAnnotation a1, a2;
+};
+
+static bool exists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static bool cmp_cluster(const CallRow &a, const CallRow &b) { return a.c.n_discordant_pair > b.c.n_discordant_pair; }   // reference src/BreakID.h:185-188
+
+static void write_header(std::ofstream &o)
+{
+  o << "Fusion_Type\tBreakPoint1\tBreakPoint2\tGene1\tBreakPoint_Info_Pair1\tGene2\tBreakPoint_Info_Pair2\tN_DRP\tN_SR\t"
+       "BreakPoint1_Depth\tBreakPoint2_Depth\tBreakPoint1_AF\tBreakPoint2_AF\tBP1_Neighbour_Seq\tBP2_Neighbour_Seq\n";
+}
+
+static void write_row(std::ofstream &o, const CallRow &r, const std::vector<std::string> &names)
+{
+  auto nm = [&](int t) { return t >= 0 && t < (int)names.size() ? names[t] : std::string("*"); };
+  const bkid_cluster_rec &c = r.c;
+  o << kFusion[c.fusion_type] << "\t";
+  o << nm(c.p1_tid) << ":" << c.p1_exact_pos << "\t";
+  o << nm(c.p2_tid) << ":" << c.p2_exact_pos << "\t";
+  o << r.a1.gene << "\t" << r.a1.strand << ":" << r.a1.exon_info << "\t";
+  o << r.a2.gene << "\t" << r.a2.strand << ":" << r.a2.exon_info << "\t";
+  o << (long)c.n_discordant_pair << "\t" << (long)c.n_split_read << "\t";
+  o << c.p1_bp_depth << "\t" << c.p2_bp_depth << "\t";
+  o << c.p1_alle_freq << "\t" << c.p2_alle_freq << "\t";
+  o << c.p1_rpt << "\t" << c.p2_rpt << "\n";
+}
+
+int main(int argc, char *argv[])
+{
+  double t_start = now_s();
+  static struct option longopts[] = {
+      {"help", 0, 0, 'h'}, {"i", 1, 0, 1}, {"o", 1, 0, 2}, {"q", 1, 0, 3}, {"n", 1, 0, 4}, {"fast", 0, 0, 5}, {"t", 1, 0, 6},
+      {"all", 0, 0, 7}, {"s", 1, 0, 8}, {"r", 1, 0, 9}, {"threads", 1, 0, 10}, {"gpu", 1, 0, 11}, {0, 0, 0, 0}};
+  std::string inp, out, nib_dir, refgene;
+  int qual = 20, times = 2, sd_mult = 3, threads = 8, gpu = 0;
+  bool fast = false, filter = true;
+  int opt, li;
+  optind = 0;
+  opterr = 0;
+  while ((opt = getopt_long_only(argc, argv, "h?", longopts, &li)) != -1) {
+    switch (opt) {
+      case 'h': std::cerr << kHelp; exit(1);
+      case 1: inp = optarg; break;
+      case 2: out = optarg; break;
+      case 3: qual = (int)labs(atol(optarg)); break;
+      case 4: nib_dir = optarg; break;
+      case 5: fast = true; break;
+      case 6: times = (int)labs(atol(optarg)); break;
+      case 7: filter = false; break;
+      case 8: sd_mult = (int)labs(atol(optarg)); break;
+      case 9: refgene = optarg; break;
+      case 10: threads = std::max(1, atoi(optarg)); break;
+      case 11: gpu = atoi(optarg); break;
+      case '?':
+        if (optopt == 0 && optind > 0 && (!strcmp(argv[optind - 1], "-?") || !strcmp(argv[optind - 1], "-help"))) { std::cerr << kHelp; exit(1); }
+        std::cerr << kHelp;
+        exit(1);
+      default: std::cerr << "Error: cannot parse arguments.\n"; exit(1);
+    }
+  }
+  if (inp.empty() || out.empty()) { std::cerr << kHelp; std::cerr << "Error: input- and output file is required.\n"; exit(1); }
+  if (nib_dir.empty()) { std::cerr << kHelp; std::cerr << "Error: nib file's root dir is required.\n"; exit(1); }
+  if (refgene.empty()) {
+    const char *inst = getenv("BREAKID_INSTALLDIR");
+    refgene = std::string(inst ? inst : ".") + "/ref_files/refGene.txt";
+  }
+
+  // ---- decode (host) ----
+  std::cout << "start to stats the insert size...\n";
+  char err[256];
+  double t0 = now_s();
+  bkid_host_bam *bam = bkid_host_read_bam(inp.c_str(), threads, err, sizeof err);
+  if (!bam) { std::cerr << "Error: can not open bam-file: " << inp << std::endl; exit(1); }
+  double t_decode = now_s() - t0;
+  const bkid_header *hdr = bkid_host_bam_header(bam);
+  const bkid_batch *batch = bkid_host_bam_batch(bam);
+  {
+    std::ifstream in((nib_dir + "/ref_names.txt").c_str());
+    if (!in.is_open()) { std::cerr << "Error: cannot open reference names file.\n"; exit(1); }     // src/BreakID.cc:1399-1404
+  }
+  std::vector<std::string> names;
+  for (int i = 0; i < hdr->n_targets; ++i) names.emplace_back(hdr->target_name[i]);
+
+  // ---- device ----
+  bkid_params prm;
+  bkid_default_params(&prm);
+  prm.qual = qual; prm.times = times; prm.fast = fast ? 1 : 0; prm.sd_mult = sd_mult;
+  bkid_ctx *ctx = bkid_create(gpu, hdr, &prm);
+  if (!ctx) { std::cerr << "Error: " << bkid_last_error(nullptr) << std::endl; exit(1); }
+  auto die = [&](const char *what) { std::cerr << "Error: " << what << ": " << bkid_last_error(ctx) << std::endl; exit(1); };
+  if (bkid_push_batch(ctx, batch)) die("push_batch");
+  double mean = 0, sd = 0;
+  if (bkid_insert_stats(ctx, &mean, &sd)) die("insert_stats");
+  std::cout << "the insert size mean: " << mean << ", the insert size sd:" << sd << " .\n";
+  double dist = times * sqrt((double)times) * (mean + sd_mult * sd);                                 // src/BreakID.cc:103
+  std::cout << "cluster_dist = span_dist = mask_dist = scan_dist = " << dist << " .\n";
+  double t_scan0 = now_s();
+  int64_t n_pairs = 0, n_clusters = 0, n_called = 0;
+  std::cout << "Scanning discordant read pairs ...\n";
+  if (bkid_scan(ctx, dist, &n_pairs)) die("scan");
+  std::cout << "Scanning discordant read pairs done.\n";
+  double t_scan = now_s() - t_scan0;
+  double t_cl0 = now_s();
+  if (bkid_cluster(ctx, dist, fast ? 1 : 0, &n_clusters)) die("cluster");
+  double t_cluster = now_s() - t_cl0;
+  bkid_timings tm;
+  bkid_get_timings(ctx, &tm);
+  std::vector<Transcript> tx;
+  std::vector<CallRow> rows;
+  double t_bp = 0;
+  if (tm.n_clustered > 0) {
+    // the reference opens the index and refGene as soon as one bucket reaches the break-point stage
+    if (!exists(inp + ".bai") && !exists(inp.substr(0, inp.size() > 4 ? inp.size() - 4 : 0) + ".bai")) {
+      std::cerr << "Error: please index bam-file first:\t" << inp << std::endl;                     // src/BreakID.cc:412-416
+      exit(1);
+    }
+    if (!load_refgene(refgene, tx)) { std::cerr << "Error: cannot open \t" << refgene << std::endl; exit(1); }   // src/RefSeqTranscript.cc:205-209
+    for (int t = 0; t < hdr->n_targets; ++t) {
+      nib nb;
+      if (nb.open(nib_dir + "/hg19_" + names[t] + ".nib") == 0)                                     // src/util_bam.cc:83-86
+        if (bkid_set_nib(ctx, t, nb.payload(), nb.size())) die("set_nib");
+    }
+    double t1 = now_s();
+    if (bkid_refine(ctx, dist, &n_called)) die("refine");
+    t_bp = now_s() - t1;
+    std::vector<bkid_cluster_rec> cl((size_t)std::max<int64_t>(n_called, 1));
+    int64_t n = 0;
+    if (bkid_fetch_clusters(ctx, cl.data(), (int64_t)cl.size(), &n)) die("fetch_clusters");
+    std::cout << "valid cluster count: " << n << std::endl;
+    for (int64_t i = 0; i < n; ++i) {
+      CallRow r;
+      r.c = cl[i];
+      long p1 = (r.c.p1_exact_pos == (uint32_t)-1) ? (long)r.c.p1_mean_pos : (long)r.c.p1_exact_pos;   // src/BreakID.cc:518-534
+      long p2 = (r.c.p2_exact_pos == -1) ? (long)r.c.p2_mean_pos : (long)r.c.p2_exact_pos;
+      auto nm = [&](int t) { return t >= 0 && t < (int)names.size() ? names[t] : std::string("*"); };
+      r.a1 = annotate_side(tx, nm(r.c.p1_tid), p1);
+      r.a2 = annotate_side(tx, nm(r.c.p2_tid), p2);
+      rows.push_back(r);
+    }
+  }
+  // ---- write (src/BreakID.cc:1184-1263): unstable sort by N_DRP, same library sort on the same order ----
+  std::sort(rows.begin(), rows.end(), cmp_cluster);
+  std::ofstream o_all, o_f;
+  if (!filter) { o_all.open((out + "_fusion_all.txt").c_str()); write_header(o_all); }
+  o_f.open((out + "_fusion.txt").c_str());
+  write_header(o_f);
+  for (const CallRow &r : rows) {
+    bool cond_all = r.c.n_split_read > 0 && r.c.p1_exact_pos != (uint32_t)-1 && r.c.p2_exact_pos != -1;
+    bool cond_filter = cond_all && (!(r.a1.gene == "intergenic" && r.a2.gene == "intergenic") && r.a1.gene != r.a2.gene) && !r.c.is_rpt;
+    if (cond_filter) write_row(o_f, r, names);
+    if (!filter && cond_all) write_row(o_all, r, names);
+  }
+  if (!filter) o_all.close();
+  o_f.close();
+  {
+    std::ofstream p((out + "_params.txt").c_str());                                                 // src/BreakID.cc:1170-1182
+    p << "ENSPAN" << std::endl;
+    p << "inp_file\t" << inp << std::endl;
+    p << "out_file\t" << out << std::endl;
+    p << "qual\t" << (long)qual << std::endl;
+    p << "w\t" << dist << std::endl;
+    p << "build\t" << "hg19" << std::endl;
+  }
+  double t_total = now_s() - t_start;
+  std::cout << "the fusion process of file " << inp << "  costs time: " << t_total << " seconds" << std::endl;
+  {
+    bkid_get_timings(ctx, &tm);
+    std::ofstream p((out + "_performance.txt").c_str());                                            // src/BreakID.cc:175-191 (same columns, all filled)
+    p << "scan_dist\tdiscordant pairs\tremove isolated\tafter_cluster\troot cluster\tscanning time\tcluster time\tfind breakpoint time\ttotal time" << std::endl;
+    p << dist << "\t" << n_pairs << "\t" << tm.n_masked << "\t" << tm.n_clustered << "\t" << n_clusters << "\t" << t_scan << "\t" << t_cluster << "\t" << t_bp << "\t" << t_total
+      << std::endl;
+    std::ofstream j((out + "_b200_timings.txt").c_str());
+    j << "decode_s\t" << t_decode << "\nrecords\t" << tm.n_records << "\nh2d_ms\t" << tm.h2d << "\nclassify_ms\t" << tm.classify << "\ninsert_stats_ms\t" << tm.insert_stats
+      << "\njoin_ms\t" << tm.join << "\nbucket_sort_ms\t" << tm.bucket_sort << "\nmask_ms\t" << tm.mask << "\ncluster_ms\t" << tm.cluster << "\nsummarize_ms\t" << tm.summarize
+      << "\nevidence_ms\t" << tm.evidence << "\nrefine_ms\t" << tm.refine << "\n";
+  }
+  bkid_destroy(ctx);
+  bkid_host_bam_free(bam);
+  return 0;
+}

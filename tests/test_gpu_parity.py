@@ -231,3 +231,35 @@ def test_batched_push_equals_single_push(small_data):
     r2 = c2.run(); g2 = c2.fetch_clusters()
     assert r1 == r2 and g1.tobytes() == g2.tobytes()
     c1.close(); c2.close()
+
+
+@pytest.mark.parametrize("mode", ["ahc", "fast"])
+def test_driver_call_files_match_reference_binary(tmp_path, mode):
+    """drop-in check: the BreakID driver (GPU) and the reference CPU binary write byte-identical
+    _fusion.txt / _fusion_all.txt / _params.txt on the same BAM + nib + refGene"""
+    import os
+    import subprocess
+    import oracle_py as O
+    from breakid_b200 import bamio, synth
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    cfg = synth.SynthConfig(chrom_lens=[300000, 200000, 150000], n_tra=3, n_inv=2, n_dup=2, n_del=2, seed=21, sv_jitter=1)
+    d = synth.generate(cfg)
+    paths = bamio.write_dataset(str(tmp_path), d, genes_per_mb=25.0)
+    O.ref_index(paths["bam"])
+    O.ref_install_refgene(paths["refgene"])
+    flags = ["-all"] + (["-fast"] if mode == "fast" else [])
+    r = O.ref_run_binary(paths["bam"], str(tmp_path / "ref"), paths["nib"], fast=(mode == "fast"))
+    assert r.returncode == 0, r.stderr[-500:]
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breakid_b200", "host", "BreakID")
+    g = subprocess.run([drv, "-i", paths["bam"], "-o", str(tmp_path / "gpu"), "-n", paths["nib"], "-r", paths["refgene"]] + flags,
+                       capture_output=True, text=True)
+    assert g.returncode == 0, g.stderr[-500:]
+    for suffix in ("_fusion.txt", "_fusion_all.txt"):
+        a = open(str(tmp_path / "ref") + suffix).read()
+        b = open(str(tmp_path / "gpu") + suffix).read()
+        assert a == b, suffix
+        assert len(a.splitlines()) >= (6 if suffix == "_fusion_all.txt" else 1)
+    pa = open(str(tmp_path / "ref") + "_params.txt").read().replace(str(tmp_path / "ref"), "X")
+    pb = open(str(tmp_path / "gpu") + "_params.txt").read().replace(str(tmp_path / "gpu"), "X")
+    assert pa == pb
