@@ -1,0 +1,84 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/breakid_b200.h
+declares, refuses to run without a GPU (no CPU fallback), the host BAM decoder reproduces the
+generated record batch, and the BreakID driver keeps the reference's argument errors."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from breakid_b200 import api
+    hdr = open(os.path.join(ROOT, "include", "breakid_b200.h")).read()
+    declared = set(re.findall(r"\b(bkid_[a-z_0-9]+)\s*\(", hdr)) - {"bkid_name_hash"}
+    assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
+    lib = ctypes.CDLL(api.LIB_CUDA)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert api.cuda_lib().bkid_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    from breakid_b200 import api
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.BkidError) as e:
+        api.Context([1000], ["chr1"])
+    assert "no usable CUDA device" in str(e.value)
+
+
+def test_pod_layouts_match_header():
+    from breakid_b200 import api
+    assert api.PAIR_DTYPE.itemsize == 64 and api.CLUSTER_DTYPE.itemsize == 192
+    import ctypes
+    assert ctypes.sizeof(api.Batch) == 18 * 8 and ctypes.sizeof(api.Params) == 32
+
+
+def test_host_bam_decoder_roundtrip(tmp_path):
+    from breakid_b200 import api, bamio, synth
+    cfg = synth.SynthConfig(chrom_lens=[80000, 50000], n_tra=1, n_inv=1, n_dup=1, n_del=1, seed=3, min_sv_sep=4000)
+    d = synth.generate(cfg)
+    a = api.HostBatch.from_synth(d)
+    bam = str(tmp_path / "x.bam")
+    bamio.write_bam(bam, d, random_qual=True)
+    for threads in (1, 4):
+        b = api.HostBatch.from_bam(bam, threads)
+        assert a.n == b.n and a.n_sa == b.n_sa
+        for k in a.cols:
+            assert np.array_equal(a.cols[k], b.cols[k]), k
+        assert np.array_equal(a.name_hash, b.name_hash)
+        for k in a.side:
+            assert np.array_equal(a.side[k], b.side[k]), k
+        assert b.target_names == ["chr1", "chr2"] and list(b.target_len) == [80000, 50000]
+
+
+def test_name_hash_vectorised_equals_c():
+    import torch
+    from breakid_b200 import synth
+    ids = torch.tensor([0, 1, 17, 123456789, 9999999999], dtype=torch.int64)
+    got = synth.name_hash_ids(ids).numpy().view(np.uint64)
+    for i, v in enumerate(ids.tolist()):
+        lo, hi = synth.name_hash_py(synth.name_of(v))
+        assert (int(got[i, 0]), int(got[i, 1])) == (lo, hi)
+
+
+def test_driver_argument_errors():
+    drv = os.path.join(ROOT, "breakid_b200", "host", "BreakID")
+    if not os.path.exists(drv):
+        pytest.skip("driver not built")
+    r = subprocess.run([drv], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error: input- and output file is required." in r.stderr
+    r = subprocess.run([drv, "-i", "a.bam", "-o", "x"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error: nib file's root dir is required." in r.stderr
+    r = subprocess.run([drv, "-i", "/nonexistent.bam", "-o", "x", "-n", "."], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error: can not open bam-file" in r.stderr
+    r = subprocess.run([drv, "-h"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage" in r.stderr
+    r = subprocess.run([drv, "-bogus"], capture_output=True, text=True)       # the reference segfaults here
+    assert r.returncode == 1
