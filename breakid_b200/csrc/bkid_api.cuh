@@ -67,7 +67,7 @@ struct bkid_ctx {
   DBuf clusters, clusters_out;
   long long n_clusters = 0, n_called = 0;
   Scratch sc;
-  DBuf tmpA, tmpB, tmpC, tmpD, tmpE, tmpF, tmpG;
+  DBuf tmpA, tmpB, tmpC, tmpD, tmpE, tmpF, tmpG, tmpH;
   bkid_timings tm;
   cudaEvent_t ev[16];
   cudaEvent_t ev_run[2];
@@ -104,27 +104,30 @@ static int exact_sort_segments(bkid_ctx *c, uint32_t *key, uint32_t *val, const 
   TRY(c, c->tmpD.ensure((size_t)n * 4 + 16, 0, st));
   TRY(c, c->tmpE.ensure((size_t)n * 4 + 16, 0, st));
   TRY(c, c->counters.ensure(256, 0, st));
-  unsigned *cnt = c->counters.as<unsigned>() + 16;     // [0]=act A, [1]=act B, [2]=terminal
+  unsigned *cnt = c->counters.as<unsigned>() + 16;     // [0]=act A, [1]=act B, [2]=terminal, [3]=small
   CU(c, cudaMemsetAsync(cnt, 0, 16, st));
   Seg *act[2] = {c->tmpA.as<Seg>(), c->tmpB.as<Seg>()};
   Seg *term = c->tmpC.as<Seg>();
-  BK_LAUNCH(is_init_roots, GRID1(nseg, 256), 256, 0, st, seg_off, nseg, act[0], cnt + 0, term, cnt + 2);
+  TRY(c, c->tmpH.ensure(seg_bytes, 0, st));
+  Seg *small = c->tmpH.as<Seg>();
+  BK_LAUNCH(is_init_roots, GRID1(nseg, 256), 256, 0, st, seg_off, nseg, act[0], cnt + 0, small, cnt + 3, term, cnt + 2);
   int lg = 0;
   for (long long t = n; t > 1; t >>= 1) ++lg;
   int max_levels = 2 * lg + 2;
   int cur = 0;
   for (int level = 0; level < max_levels; ++level) {
-    if (level > 0 && (level % 8) == 0) {               // early exit once no segment is active
+    if (n <= 65536 ? true : (level > 0 && (level % 4) == 0)) {   // early exit once no segment is above the small-segment size               // early exit once no segment is active
       unsigned h = 0;
       CU(c, cudaMemcpyAsync(&h, cnt + cur, 4, cudaMemcpyDeviceToHost, st));
       CU(c, cudaStreamSynchronize(st));
       if (h == 0) break;
     }
     CU(c, cudaMemsetAsync(cnt + (cur ^ 1), 0, 4, st));
-    BK_LAUNCH(is_level, 592, IS_THREADS, 0, st, key, val, act[cur], cnt + cur, act[cur ^ 1], cnt + (cur ^ 1), term, cnt + 2,
+    BK_LAUNCH(is_level, 592, IS_THREADS, 0, st, key, val, act[cur], cnt + cur, act[cur ^ 1], cnt + (cur ^ 1), small, cnt + 3, term, cnt + 2,
               c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>());
     cur ^= 1;
   }
+  BK_LAUNCH(is_small, 2368, ISS_WARPS * 32, 0, st, key, val, small, cnt + 3);
   BK_LAUNCH(is_terminal, 592, 128, 0, st, key, val, term, cnt + 2);
   return 0;
 }
@@ -311,7 +314,10 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   v.thr = (double)thr;
   BK_LAUNCH(ahc_components, GRID1(ncomp, 4), 128, 0, st, v, ncomp);
   BK_LAUNCH(ahc_bucket_flags, GRID1(ncomp, 128), 128, 0, st, comp_flag, comp_bucket, ncomp, bucket_flag);
-  BK_LAUNCH(ahc_replay, GRID1(nseg, 4), 128, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag);
+  // replay: shared-memory form for buckets up to 4096 points (two smem classes), global form above that
+  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 48 * 1024, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, 1024u);
+  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 48 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 1024u, 4096u);
+  BK_LAUNCH(ahc_replay, GRID1(nseg, 4), 128, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
   BK_LAUNCH(ahc_bucket_exact, (unsigned)nseg, 32, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag);
   // final roots -> clusters
   unsigned *cnt = c->counters.as<unsigned>() + 48;
@@ -461,6 +467,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   cudaMemset(c->d_nib_len.p, 0, (size_t)(nt + 1) * 8);
   c->nib.resize(nt); c->nib_len.assign(nt, 0);
   cudaFuncSetAttribute(sd_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_BLOCK * 9);
+  cudaFuncSetAttribute(ahc_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 4096);
   memset(&c->tm, 0, sizeof c->tm);
   if (cudaGetLastError() != cudaSuccess) { g_create_err = "CUDA error during create"; delete c; return nullptr; }
   return c;
@@ -474,7 +481,7 @@ void bkid_destroy(bkid_ctx *c)
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->mtid, &c->mpos, &c->isize, &c->endpos, &c->nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->clusters, &c->clusters_out, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG})
+                  &c->mem_bucket, &c->mem_cluster, &c->clusters, &c->clusters_out, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();

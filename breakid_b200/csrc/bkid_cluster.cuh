@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(128) ahc_components(AhcView v, uint32_t ncomp)
 }
 
 // Kernel B: replay per bucket.  One warp per bucket; lanes own components round-robin.
-__global__ void __launch_bounds__(128) ahc_replay(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag)
+__global__ void __launch_bounds__(128) ahc_replay(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag,
+                                                  uint32_t n_lo)
 {
   uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= nb) return;
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(128) ahc_replay(AhcView v, const uint32_t *__r
   const unsigned lane = threadIdx.x & 31;
   uint32_t c0 = bucket_comp_off[b], c1 = bucket_comp_off[b + 1];
   uint32_t nleaf = v.seg_off[b + 1] - v.seg_off[b];
+  if (nleaf < n_lo) return;                       // small buckets take the shared-memory form
   int32_t g = 0;
   while (true) {
     double bd = 1.7976931348623157e308; int32_t bg = -1; uint32_t bc = 0xffffffffu;
@@ -312,6 +314,80 @@ __global__ void __launch_bounds__(128) ahc_replay(AhcView v, const uint32_t *__r
     ++g;
     __syncwarp();
   }
+}
+
+// Kernel B (shared-memory form): one warp per bucket with every event, cursor and component head of the
+// bucket staged in shared memory, so a replay step is a handful of LDS + shuffles instead of a chain
+// of dependent global loads.  Buckets with n_lo <= points < n_hi are handled; smem = 48 B per point.
+__global__ void __launch_bounds__(32) ahc_replay_smem(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag,
+                                                      uint32_t n_lo, uint32_t n_hi)
+{
+  uint32_t b = blockIdx.x;
+  if (b >= nb || bucket_flag[b]) return;
+  uint32_t nleaf = v.seg_off[b + 1] - v.seg_off[b];
+  if (nleaf < n_lo || nleaf >= n_hi) return;
+  extern __shared__ unsigned char dynsm[];
+  const unsigned lane = threadIdx.x;
+  uint32_t c0 = bucket_comp_off[b], c1 = bucket_comp_off[b + 1], K = c1 - c0;
+  // layout (cap = nleaf): doubles first
+  double *ev_d = reinterpret_cast<double *>(dynsm);                    // [cap]
+  double *hd = ev_d + nleaf;                                             // [cap]
+  int32_t *ev_first = reinterpret_cast<int32_t *>(hd + nleaf);          // [cap]
+  int32_t *ev_g = ev_first + nleaf;                                      // [cap]
+  int32_t *hg = ev_g + nleaf;                                            // [cap]
+  uint32_t *cb = reinterpret_cast<uint32_t *>(hg + nleaf);              // [cap] event base of comp
+  uint32_t *cn = cb + nleaf;                                             // [cap] number of events
+  uint32_t *cc = cn + nleaf;                                             // [cap] leaf count
+  uint32_t *cl = cc + nleaf;                                             // [cap] lbase
+  uint32_t *cur = cl + nleaf;                                            // [cap] cursor
+  // component tables + event bases (warp scan over K)
+  uint32_t run = 0;
+  for (uint32_t q0 = 0; q0 < K; q0 += 32) {
+    uint32_t q = q0 + lane, nev = 0;
+    if (q < K) {
+      uint32_t comp = c0 + q, lbase = v.comp_off[comp], c = v.comp_off[comp + 1] - lbase;
+      nev = v.comp_nnodes[comp] - c;
+      cc[q] = c; cl[q] = lbase; cn[q] = nev; cur[q] = 0;
+    }
+    uint32_t inc = bk::warp_incl_scan(nev);
+    if (q < K) cb[q] = run + inc - nev;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+  for (uint32_t q = lane; q < K; q += 32)
+    for (uint32_t e = 0; e < cn[q]; ++e) { ev_d[cb[q] + e] = v.ev_d[cl[q] + e]; ev_first[cb[q] + e] = v.ev_first[cl[q] + e]; ev_g[cb[q] + e] = -1; }
+  __syncwarp();
+  auto head_of = [&](uint32_t q) {
+    uint32_t k = cur[q];
+    if (k >= cn[q]) { hg[q] = -1; hd[q] = 0.0; return; }
+    int32_t f = ev_first[cb[q] + k];
+    hd[q] = ev_d[cb[q] + k];
+    hg[q] = (uint32_t)f < cc[q] ? (int32_t)(v.comp_leaf[cl[q] + f] - v.seg_off[b]) : (int32_t)nleaf + ev_g[cb[q] + ((uint32_t)f - cc[q])];
+  };
+  for (uint32_t q = lane; q < K; q += 32) head_of(q);
+  __syncwarp();
+  int32_t g = 0;
+  while (true) {
+    double bd = 0.0; int32_t bg = -1; uint32_t bq = 0;
+    for (uint32_t q = lane; q < K; q += 32) {
+      int32_t gi = hg[q];
+      if (gi < 0) continue;
+      double d = hd[q];
+      if (bg < 0 || d < bd || (d == bd && gi > bg)) { bd = d; bg = gi; bq = q; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      int32_t og = __shfl_xor_sync(0xffffffffu, bg, o);
+      uint32_t oq = __shfl_xor_sync(0xffffffffu, bq, o);
+      if (og >= 0 && (bg < 0 || od < bd || (od == bd && og > bg))) { bd = od; bg = og; bq = oq; }
+    }
+    if (bg < 0) break;
+    if (lane == 0) { ev_g[cb[bq] + cur[bq]] = g; cur[bq] += 1; head_of(bq); }
+    ++g;
+    __syncwarp();
+  }
+  for (uint32_t q = lane; q < K; q += 32)
+    for (uint32_t e = 0; e < cn[q]; ++e) v.node_grank[2 * cl[q] + cc[q] + e] = ev_g[cb[q] + e];
 }
 
 // Kernel C: exact online form for buckets with a flagged component (one warp per bucket)

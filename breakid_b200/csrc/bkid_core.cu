@@ -514,6 +514,7 @@ __global__ void k2_bucket_ids(bkid_pair *__restrict__ pairs, const uint32_t *__r
 // =============================================================================================
 struct Seg { uint32_t f, l; int depth; };
 constexpr int IS_THREADS = 256;
+constexpr uint32_t IS_SMALL = 1024;     // segments up to this size are finished by one warp in shared memory
 
 __device__ void seg_insertion_sort(uint32_t *key, uint32_t *val, uint32_t f, uint32_t l)
 {
@@ -564,24 +565,116 @@ __device__ void seg_heapsort(uint32_t *key, uint32_t *val, uint32_t f, uint32_t 
   }
 }
 
+__device__ __forceinline__ void seg_route(const Seg &s, Seg *act, unsigned *n_act, Seg *small, unsigned *n_small, Seg *term, unsigned *n_term)
+{
+  uint32_t sz = s.l - s.f;
+  if (sz > IS_SMALL) act[atomicAdd(n_act, 1u)] = s;
+  else if (sz > 16) small[atomicAdd(n_small, 1u)] = s;
+  else if (sz >= 2) term[atomicAdd(n_term, 1u)] = s;
+}
+
 // roots: one segment per bucket
 __global__ void is_init_roots(const uint32_t *__restrict__ seg_off, int nseg, Seg *__restrict__ act, unsigned *__restrict__ n_act,
-                              Seg *__restrict__ term, unsigned *__restrict__ n_term)
+                              Seg *__restrict__ small, unsigned *__restrict__ n_small, Seg *__restrict__ term, unsigned *__restrict__ n_term)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
   uint32_t f = seg_off[s], l = seg_off[s + 1];
   uint32_t n = l - f;
   if (n < 2) return;
-  if (n <= 16) { term[atomicAdd(n_term, 1u)] = Seg{f, l, 0}; return; }
   int lg = 31 - __clz(n);
-  act[atomicAdd(n_act, 1u)] = Seg{f, l, 2 * lg};
+  seg_route(Seg{f, l, 2 * lg}, act, n_act, small, n_small, term, n_term);
+}
+
+// one warp per small segment, everything in shared memory: the same partition scheme as is_level
+// (L / R lists via ballots), an explicit stack instead of levels, terminal (<= 16) segments finished
+// by one lane each (stable insertion sort), depth-exhausted segments by the literal heapsort.
+constexpr int ISS_WARPS = 2;
+__global__ void __launch_bounds__(ISS_WARPS * 32) is_small(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__restrict__ small, const unsigned *__restrict__ n_small_p)
+{
+  __shared__ uint32_t sk[ISS_WARPS][IS_SMALL], sv[ISS_WARPS][IS_SMALL];
+  __shared__ uint16_t sL[ISS_WARPS][IS_SMALL], sR[ISS_WARPS][IS_SMALL];
+  __shared__ uint16_t tf[ISS_WARPS][IS_SMALL / 2], tl[ISS_WARPS][IS_SMALL / 2];
+  __shared__ int stf[ISS_WARPS][64], stl[ISS_WARPS][64], stdp[ISS_WARPS][64];
+  const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31, ltmask = (1u << lane) - 1u;
+  uint32_t *K = sk[w], *V = sv[w];
+  uint16_t *L = sL[w], *R = sR[w];
+  unsigned n_small = *n_small_p;
+  for (unsigned si = blockIdx.x * ISS_WARPS + w; si < n_small; si += gridDim.x * ISS_WARPS) {
+    Seg s = small[si];
+    int n = (int)(s.l - s.f);
+    for (int i = lane; i < n; i += 32) { K[i] = key[s.f + i]; V[i] = val[s.f + i]; }
+    int sp = 1, nt = 0;
+    if (lane == 0) { stf[w][0] = 0; stl[w][0] = n; stdp[w][0] = s.depth; }
+    __syncwarp();
+    while (sp) {
+      --sp;
+      int first = stf[w][sp], last = stl[w][sp], d = stdp[w][sp];
+      __syncwarp();
+      while (last - first > 16) {
+        if (d == 0) { if (lane == 0) seg_heapsort(K, V, (uint32_t)first, (uint32_t)last); __syncwarp(); first = last; break; }
+        --d;
+        if (lane == 0) {
+          int mid = first + (last - first) / 2, A = first + 1, B = mid, C = last - 1, med;
+          uint32_t ka = K[A], kb = K[B], kc = K[C];
+          if (ka < kb) { if (kb < kc) med = B; else if (ka < kc) med = C; else med = A; }
+          else if (ka < kc) med = A;
+          else if (kb < kc) med = C;
+          else med = B;
+          uint32_t tk = K[first], tv = V[first];
+          K[first] = K[med]; V[first] = V[med]; K[med] = tk; V[med] = tv;
+        }
+        __syncwarp();
+        uint32_t pv = K[first];
+        int lo = first + 1, cnt = last - lo, nL = 0, nR = 0;
+        for (int b = 0; b < cnt; b += 32) {
+          int e = b + (int)lane;
+          bool isL = e < cnt && !(K[lo + e] < pv);
+          unsigned m = __ballot_sync(0xffffffffu, isL);
+          if (isL) L[nL + __popc(m & ltmask)] = (uint16_t)(lo + e);
+          nL += __popc(m);
+          bool isR = e < cnt && !(pv < K[last - 1 - e]);
+          m = __ballot_sync(0xffffffffu, isR);
+          if (isR) R[nR + __popc(m & ltmask)] = (uint16_t)(last - 1 - e);
+          nR += __popc(m);
+        }
+        __syncwarp();
+        int mn = nL < nR ? nL : nR, Kc = 0;
+        for (int b = 0; b < mn; b += 32) {
+          int k = b + (int)lane;
+          unsigned m = __ballot_sync(0xffffffffu, k < mn && L[k] < R[k]);
+          Kc += __popc(m);
+          if (m != 0xffffffffu) break;
+        }
+        for (int k = lane; k < Kc; k += 32) {
+          int a = L[k], b2 = R[k];
+          uint32_t tk = K[a], tv = V[a];
+          K[a] = K[b2]; V[a] = V[b2]; K[b2] = tk; V[b2] = tv;
+        }
+        int rprev = Kc ? (int)R[Kc - 1] : last;
+        int cut = (Kc < nL && (int)L[Kc] < rprev) ? (int)L[Kc] : rprev;
+        __syncwarp();
+        // right part goes on the stack (or to the terminal list), continue with the left part
+        int rs = last - cut;
+        if (rs > 16) { if (lane == 0) { stf[w][sp] = cut; stl[w][sp] = last; stdp[w][sp] = d; } ++sp; }
+        else if (rs >= 2) { if (lane == 0) { tf[w][nt] = (uint16_t)cut; tl[w][nt] = (uint16_t)last; } ++nt; }
+        last = cut;
+        __syncwarp();
+      }
+      if (last - first >= 2) { if (lane == 0) { tf[w][nt] = (uint16_t)first; tl[w][nt] = (uint16_t)last; } ++nt; }
+      __syncwarp();
+    }
+    for (int t = lane; t < nt; t += 32) seg_insertion_sort(K, V, tf[w][t], tl[w][t]);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) { key[s.f + i] = K[i]; val[s.f + i] = V[i]; }
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(IS_THREADS)
 is_level(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__restrict__ act, const unsigned *__restrict__ n_act_p,
-         Seg *__restrict__ nxt, unsigned *__restrict__ n_nxt, Seg *__restrict__ term, unsigned *__restrict__ n_term,
-         uint32_t *__restrict__ scrL, uint32_t *__restrict__ scrR)
+         Seg *__restrict__ nxt, unsigned *__restrict__ n_nxt, Seg *__restrict__ small, unsigned *__restrict__ n_small,
+         Seg *__restrict__ term, unsigned *__restrict__ n_term, uint32_t *__restrict__ scrL, uint32_t *__restrict__ scrR)
 {
   __shared__ unsigned sh32[33];
   __shared__ uint32_t sh_p;
@@ -646,12 +739,8 @@ is_level(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__re
     if (threadIdx.x == 0) {
       uint32_t rprev = K ? scrR[lo + K - 1] : l;
       uint32_t cut = (K < nL && scrL[lo + K] < rprev) ? scrL[lo + K] : rprev;
-      Seg c2[2] = {Seg{cut, l, s.depth - 1}, Seg{f, cut, s.depth - 1}};
-      for (int q = 0; q < 2; ++q) {
-        uint32_t sz = c2[q].l - c2[q].f;
-        if (sz > 16) nxt[atomicAdd(n_nxt, 1u)] = c2[q];
-        else if (sz >= 2) term[atomicAdd(n_term, 1u)] = c2[q];
-      }
+      seg_route(Seg{cut, l, s.depth - 1}, nxt, n_nxt, small, n_small, term, n_term);
+      seg_route(Seg{f, cut, s.depth - 1}, nxt, n_nxt, small, n_small, term, n_term);
     }
     __syncthreads();
   }
