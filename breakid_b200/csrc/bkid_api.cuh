@@ -74,6 +74,19 @@ struct bkid_ctx {
   long long launches0 = 0;
 };
 
+// optional sub-stage timing (env BKID_DEBUG_TIMING=1): CUDA events on the context stream, printed to stderr
+struct SubTimer {
+  cudaStream_t st; bool on; std::vector<std::pair<std::string, cudaEvent_t>> ev;
+  explicit SubTimer(cudaStream_t s) : st(s), on(getenv("BKID_DEBUG_TIMING") != nullptr) { mark("start"); }
+  void mark(const char *name) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back({name, e}); }
+  ~SubTimer() {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    for (size_t i = 1; i < ev.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second); fprintf(stderr, "[bkid-timing] %-28s %8.3f ms\n", ev[i].first.c_str(), ms); }
+    for (auto &e : ev) cudaEventDestroy(e.second);
+  }
+};
+
 static int fail(bkid_ctx *c, int code, const std::string &msg)
 {
   if (c) c->err = msg;
@@ -219,6 +232,7 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   c->roots_per_bucket.assign(nseg, 0);
   if (n == 0) return 0;
   long long thr = (long long)thr_d;                      // long distance_threshold (src/util_cluster.cc:7)
+  SubTimer T_(st);
   TRY(c, c->sc.ensure(n + 8, st));
   // coordinates in leaf order
   DBuf &LX = c->tmpA, &LY = c->tmpB;
@@ -252,6 +266,7 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   BK_LAUNCH(ahc_key_group, GRID1(n, 256), 256, 0, st, head, hex, val, (const uint32_t *)nullptr, n, key);
   bk::radix_sort_pairs(key, val, n, 0, 32 + cbits, c->sc.rt(), st);
   BK_LAUNCH(ahc_comp_heads, GRID1(n, 256), 256, 0, st, key, n, head);
+  T_.mark("ahc: component sorts");
   // component tables
   DBuf &T = c->tmpC;
   size_t nc1 = (size_t)ncomp + 2;
@@ -312,13 +327,30 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   v.comp_nnodes = comp_nnodes; v.comp_pts_used = comp_pts_used; v.comp_row_used = comp_row_used;
   v.comp_head_j = comp_head_j; v.comp_head_d = comp_head_d; v.comp_flag = comp_flag; v.comp_cursor = comp_cursor;
   v.thr = (double)thr;
+  T_.mark("ahc: tables+alloc");
   BK_LAUNCH(ahc_components, GRID1(ncomp, 4), 128, 0, st, v, ncomp);
+  T_.mark("ahc: components kernel");
   BK_LAUNCH(ahc_bucket_flags, GRID1(ncomp, 128), 128, 0, st, comp_flag, comp_bucket, ncomp, bucket_flag);
   // replay: shared-memory form for buckets up to 4096 points (two smem classes), global form above that
-  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 48 * 1024, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, 1024u);
-  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 48 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 1024u, 4096u);
+  T_.mark("ahc: bucket flags");
+  if (T_.on) {
+    std::vector<int32_t> hf(ncomp); std::vector<uint32_t> hoff(ncomp + 1), hnn(ncomp);
+    cudaMemcpyAsync(hf.data(), comp_flag, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hoff.data(), comp_off, (size_t)(ncomp + 1) * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hnn.data(), comp_nnodes, (size_t)ncomp * 4, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    long nf = 0, maxc = 0, merges = 0, fl_pts = 0;
+    for (uint32_t i = 0; i < ncomp; ++i) { uint32_t cs = hoff[i + 1] - hoff[i]; nf += hf[i] != 0; if (hf[i]) fl_pts += cs; maxc = std::max<long>(maxc, cs); merges += hnn[i] - cs; }
+    fprintf(stderr, "[bkid-timing] ncomp %u flagged %ld (points %ld) max comp %ld merges %ld points %lld buckets %d\n", ncomp, nf, fl_pts, maxc, merges, n, nseg);
+  }
+  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 960, st, v, bucket_comp_off, (uint32_t)nseg, 0u, 960u);
+  T_.mark("ahc: replay smem <960");
+  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, 960u, 4096u);
+  T_.mark("ahc: replay smem <4096");
   BK_LAUNCH(ahc_replay, GRID1(nseg, 4), 128, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
-  BK_LAUNCH(ahc_bucket_exact, (unsigned)nseg, 32, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag);
+  T_.mark("ahc: replay global");
+  BK_LAUNCH(ahc_bucket_exact, (unsigned)nseg, 32, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
+  T_.mark("ahc: replay+exact");
   // final roots -> clusters
   unsigned *cnt = c->counters.as<unsigned>() + 48;
   CU(c, cudaMemsetAsync(cnt, 0, 4, st));
@@ -348,6 +380,7 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   // members are positions in the stage-1 order; translate to pair ids
   BK_LAUNCH(gather_u32, GRID1(nm, 256), 256, 0, st, cur, c->tmpE.as<uint32_t>(), (long long)nm, c->mem_pair.as<uint32_t>());
   c->n2 = (long long)nm;
+  T_.mark("ahc: final roots+emit");
   return sync_check(c);
 }
 
@@ -467,7 +500,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   cudaMemset(c->d_nib_len.p, 0, (size_t)(nt + 1) * 8);
   c->nib.resize(nt); c->nib_len.assign(nt, 0);
   cudaFuncSetAttribute(sd_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_BLOCK * 9);
-  cudaFuncSetAttribute(ahc_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 4096);
+  cudaFuncSetAttribute(ahc_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
   memset(&c->tm, 0, sizeof c->tm);
   if (cudaGetLastError() != cudaSuccess) { g_create_err = "CUDA error during create"; delete c; return nullptr; }
   return c;
@@ -673,9 +706,12 @@ int bkid_insert_stats(bkid_ctx *c, double *mean, double *sd)
     long long *out = (long long *)(c->counters.as<unsigned>() + 8);
     cudaEventRecord(c->ev[4], st);
     long long h[2] = {0, 0};
+    SubTimer T_(st);
     if (n > 0 && c->cnt_insert > 0) {
       BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, blkF, blkCum, blkN, blkA);
+      T_.mark("sd: block stats");
       BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, out);
+      T_.mark("sd: resolve");
       CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
       TRY(c, sync_check(c));
       if (h[1]) {                                                              // total left the closed-form regime: literal replay
@@ -718,6 +754,7 @@ int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
   }
   c->n_cand = (long long)nc;
   c->np0 = 0; c->nb = 0;
+  SubTimer T_(st);
   if (nc > 0) {
     TRY(c, c->cand_idx.ensure((size_t)nc * 4 + 64, 0, st));
     BK_LAUNCH(k1_compact, (unsigned)ntiles, K1_THREADS, 0, st, c->cls.as<uint8_t>(), n, tile_off, c->cand_idx.as<uint32_t>());
@@ -725,7 +762,9 @@ int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
     uint64_t *key = c->sc.keys.as<uint64_t>();
     uint32_t *val = c->sc.vals.as<uint32_t>();
     BK_LAUNCH(k2_gather_keys, GRID1(nc, 256), 256, 0, st, c->cand_idx.as<uint32_t>(), (long long)nc, c->p_nh, key, val);
+    T_.mark("join: compact+gather");
     bk::radix_sort_pairs(key, val, (long long)nc, 0, 64, c->sc.rt(), st);
+    T_.mark("join: radix sort 64b");
     uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
     int *errf = (int *)(c->counters.as<unsigned>() + 40);
     CU(c, cudaMemsetAsync(errf, 0, 4, st));
@@ -747,6 +786,7 @@ int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
     CU(c, cudaMemcpyAsync(&np, pcount, 8, cudaMemcpyDeviceToHost, st));
     CU(c, cudaMemcpyAsync(&herr, errf, 4, cudaMemcpyDeviceToHost, st));
     TRY(c, sync_check(c));
+    T_.mark("join: runs+emit");
     if (herr) return fail(c, BKID_ERR_HASH, "two different read names share a 64-bit hash prefix");
     cudaEventRecord(c->ev[7], st);
     c->np0 = (long long)np;

@@ -318,51 +318,79 @@ __global__ void __launch_bounds__(128) ahc_replay(AhcView v, const uint32_t *__r
 
 // Kernel B (shared-memory form): one warp per bucket with every event, cursor and component head of the
 // bucket staged in shared memory, so a replay step is a handful of LDS + shuffles instead of a chain
-// of dependent global loads.  Buckets with n_lo <= points < n_hi are handled; smem = 48 B per point.
-__global__ void __launch_bounds__(32) ahc_replay_smem(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag,
-                                                      uint32_t n_lo, uint32_t n_hi)
+// of dependent global loads.  Components that kernel A flagged (a tie decision depended on global
+// creation ranks -- common, because the isolated-pair mask duplicates one pair per bucket) are not
+// replayed from their speculative events: they are re-run ONLINE inside this loop in exact mode, with
+// the true ranks, while every other component of the bucket keeps its precomputed events.
+// Buckets with n_lo <= points < n_hi are handled; smem = 49 B per point.
+__global__ void __launch_bounds__(32) ahc_replay_smem(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, uint32_t n_lo, uint32_t n_hi)
 {
   uint32_t b = blockIdx.x;
-  if (b >= nb || bucket_flag[b]) return;
+  if (b >= nb) return;
   uint32_t nleaf = v.seg_off[b + 1] - v.seg_off[b];
   if (nleaf < n_lo || nleaf >= n_hi) return;
   extern __shared__ unsigned char dynsm[];
   const unsigned lane = threadIdx.x;
   uint32_t c0 = bucket_comp_off[b], c1 = bucket_comp_off[b + 1], K = c1 - c0;
-  // layout (cap = nleaf): doubles first
-  double *ev_d = reinterpret_cast<double *>(dynsm);                    // [cap]
-  double *hd = ev_d + nleaf;                                             // [cap]
-  int32_t *ev_first = reinterpret_cast<int32_t *>(hd + nleaf);          // [cap]
-  int32_t *ev_g = ev_first + nleaf;                                      // [cap]
-  int32_t *hg = ev_g + nleaf;                                            // [cap]
-  uint32_t *cb = reinterpret_cast<uint32_t *>(hg + nleaf);              // [cap] event base of comp
-  uint32_t *cn = cb + nleaf;                                             // [cap] number of events
-  uint32_t *cc = cn + nleaf;                                             // [cap] leaf count
-  uint32_t *cl = cc + nleaf;                                             // [cap] lbase
-  uint32_t *cur = cl + nleaf;                                            // [cap] cursor
-  // component tables + event bases (warp scan over K)
+  double *ev_d = reinterpret_cast<double *>(dynsm);                    // [cap = nleaf]
+  double *hd = ev_d + nleaf;
+  int32_t *ev_first = reinterpret_cast<int32_t *>(hd + nleaf);
+  int32_t *ev_g = ev_first + nleaf;
+  int32_t *hg = ev_g + nleaf;
+  uint32_t *cb = reinterpret_cast<uint32_t *>(hg + nleaf);              // event base of comp
+  uint32_t *cn = cb + nleaf;                                             // number of precomputed events (0 for flagged comps)
+  uint32_t *cc = cn + nleaf;                                             // leaf count
+  uint32_t *cl = cc + nleaf;                                             // lbase
+  uint32_t *cur = cl + nleaf;                                            // cursor
+  uint8_t *cf = reinterpret_cast<uint8_t *>(cur + nleaf);               // flagged -> online exact mode
+  const uint32_t pbase = v.seg_off[b];
   uint32_t run = 0;
   for (uint32_t q0 = 0; q0 < K; q0 += 32) {
     uint32_t q = q0 + lane, nev = 0;
     if (q < K) {
       uint32_t comp = c0 + q, lbase = v.comp_off[comp], c = v.comp_off[comp + 1] - lbase;
-      nev = v.comp_nnodes[comp] - c;
-      cc[q] = c; cl[q] = lbase; cn[q] = nev; cur[q] = 0;
+      uint8_t fl = v.comp_flag[comp] ? 1 : 0;
+      nev = fl ? 0u : v.comp_nnodes[comp] - c;
+      cc[q] = c; cl[q] = lbase; cn[q] = nev; cur[q] = 0; cf[q] = fl;
     }
     uint32_t inc = bk::warp_incl_scan(nev);
     if (q < K) cb[q] = run + inc - nev;
     run += __shfl_sync(0xffffffffu, inc, 31);
   }
   __syncwarp();
+  // events: `first` is resolved to a global node index here when it is a leaf (>= 0); a merged `first` is
+  // stored as -1 - (its creating event) and resolved through ev_g once that event has its rank
   for (uint32_t q = lane; q < K; q += 32)
-    for (uint32_t e = 0; e < cn[q]; ++e) { ev_d[cb[q] + e] = v.ev_d[cl[q] + e]; ev_first[cb[q] + e] = v.ev_first[cl[q] + e]; ev_g[cb[q] + e] = -1; }
+    for (uint32_t e = 0; e < cn[q]; ++e) {
+      int32_t f = v.ev_first[cl[q] + e];
+      ev_d[cb[q] + e] = v.ev_d[cl[q] + e];
+      ev_first[cb[q] + e] = (uint32_t)f < cc[q] ? (int32_t)(v.comp_leaf[cl[q] + f] - pbase) : -1 - (int32_t)((uint32_t)f - cc[q]);
+      ev_g[cb[q] + e] = -1;
+    }
   __syncwarp();
+  // flagged components start over in exact mode (warp-cooperative, one after the other)
+  for (uint32_t q = 0; q < K; ++q)
+    if (cf[q]) {
+      CompCtx cx = make_cc(v, c0 + q);
+      ahc_comp_init(v, cx);
+      for (uint32_t j = 1; j < cx.c; ++j) ahc_find_best<true>(v, cx, j);
+      ahc_comp_head(v, cx);
+    }
   auto head_of = [&](uint32_t q) {
+    if (cf[q]) {
+      uint32_t comp = c0 + q;
+      int32_t hj = v.comp_head_j[comp];
+      double d = v.comp_head_d[comp];
+      if (hj < 0 || !(d <= v.thr)) { hg[q] = -1; hd[q] = 0.0; return; }
+      hd[q] = d;
+      hg[q] = (uint32_t)hj < cc[q] ? (int32_t)(v.comp_leaf[cl[q] + hj] - pbase) : (int32_t)nleaf + v.node_grank[2 * cl[q] + hj];
+      return;
+    }
     uint32_t k = cur[q];
     if (k >= cn[q]) { hg[q] = -1; hd[q] = 0.0; return; }
     int32_t f = ev_first[cb[q] + k];
     hd[q] = ev_d[cb[q] + k];
-    hg[q] = (uint32_t)f < cc[q] ? (int32_t)(v.comp_leaf[cl[q] + f] - v.seg_off[b]) : (int32_t)nleaf + ev_g[cb[q] + ((uint32_t)f - cc[q])];
+    hg[q] = f >= 0 ? f : (int32_t)nleaf + ev_g[cb[q] + (uint32_t)(-1 - f)];
   };
   for (uint32_t q = lane; q < K; q += 32) head_of(q);
   __syncwarp();
@@ -382,7 +410,11 @@ __global__ void __launch_bounds__(32) ahc_replay_smem(AhcView v, const uint32_t 
       if (og >= 0 && (bg < 0 || od < bd || (od == bd && og > bg))) { bd = od; bg = og; bq = oq; }
     }
     if (bg < 0) break;
-    if (lane == 0) { ev_g[cb[bq] + cur[bq]] = g; cur[bq] += 1; head_of(bq); }
+    if (cf[bq]) {
+      CompCtx cx = make_cc(v, c0 + bq);
+      ahc_merge<true>(v, cx, g);
+      if (lane == 0) head_of(bq);
+    } else if (lane == 0) { ev_g[cb[bq] + cur[bq]] = g; cur[bq] += 1; head_of(bq); }
     ++g;
     __syncwarp();
   }
@@ -391,10 +423,11 @@ __global__ void __launch_bounds__(32) ahc_replay_smem(AhcView v, const uint32_t 
 }
 
 // Kernel C: exact online form for buckets with a flagged component (one warp per bucket)
-__global__ void __launch_bounds__(32) ahc_bucket_exact(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag)
+__global__ void __launch_bounds__(32) ahc_bucket_exact(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag, uint32_t n_lo)
 {
   uint32_t b = blockIdx.x;
   if (b >= nb || !bucket_flag[b]) return;
+  if (v.seg_off[b + 1] - v.seg_off[b] < n_lo) return;     // small buckets: flagged components are re-run inside ahc_replay_smem
   const unsigned lane = threadIdx.x & 31;
   uint32_t c0 = bucket_comp_off[b], c1 = bucket_comp_off[b + 1];
   uint32_t nleaf = v.seg_off[b + 1] - v.seg_off[b];
