@@ -343,10 +343,12 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
     for (uint32_t i = 0; i < ncomp; ++i) { uint32_t cs = hoff[i + 1] - hoff[i]; nf += hf[i] != 0; if (hf[i]) fl_pts += cs; maxc = std::max<long>(maxc, cs); merges += hnn[i] - cs; }
     fprintf(stderr, "[bkid-timing] ncomp %u flagged %ld (points %ld) max comp %ld merges %ld points %lld buckets %d\n", ncomp, nf, fl_pts, maxc, merges, n, nseg);
   }
-  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 960, st, v, bucket_comp_off, (uint32_t)nseg, 0u, 960u);
-  T_.mark("ahc: replay smem <960");
-  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, 960u, 4096u);
-  T_.mark("ahc: replay smem <4096");
+  BK_LAUNCH(ahc_replay_rank, (unsigned)nseg, RK_THREADS, 49 * 900, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, 900u);
+  BK_LAUNCH(ahc_replay_rank, (unsigned)nseg, RK_THREADS, 49 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 900u, 4096u);
+  T_.mark("ahc: replay rank form");
+  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 900, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, 900u);
+  BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 900u, 4096u);
+  T_.mark("ahc: replay smem (flagged)");
   BK_LAUNCH(ahc_replay, GRID1(nseg, 4), 128, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
   T_.mark("ahc: replay global");
   BK_LAUNCH(ahc_bucket_exact, (unsigned)nseg, 32, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
@@ -501,6 +503,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   c->nib.resize(nt); c->nib_len.assign(nt, 0);
   cudaFuncSetAttribute(sd_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_BLOCK * 9);
   cudaFuncSetAttribute(ahc_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
+  cudaFuncSetAttribute(ahc_replay_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
   memset(&c->tm, 0, sizeof c->tm);
   if (cudaGetLastError() != cudaSuccess) { g_create_err = "CUDA error during create"; delete c; return nullptr; }
   return c;

@@ -323,10 +323,11 @@ __global__ void __launch_bounds__(128) ahc_replay(AhcView v, const uint32_t *__r
 // replayed from their speculative events: they are re-run ONLINE inside this loop in exact mode, with
 // the true ranks, while every other component of the bucket keeps its precomputed events.
 // Buckets with n_lo <= points < n_hi are handled; smem = 49 B per point.
-__global__ void __launch_bounds__(32) ahc_replay_smem(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, uint32_t n_lo, uint32_t n_hi)
+__global__ void __launch_bounds__(32) ahc_replay_smem(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag,
+                                                      uint32_t n_lo, uint32_t n_hi)
 {
   uint32_t b = blockIdx.x;
-  if (b >= nb) return;
+  if (b >= nb || !bucket_flag[b]) return;       // buckets without flagged components take the rank form
   uint32_t nleaf = v.seg_off[b + 1] - v.seg_off[b];
   if (nleaf < n_lo || nleaf >= n_hi) return;
   extern __shared__ unsigned char dynsm[];
@@ -420,6 +421,110 @@ __global__ void __launch_bounds__(32) ahc_replay_smem(AhcView v, const uint32_t 
   }
   for (uint32_t q = lane; q < K; q += 32)
     for (uint32_t e = 0; e < cn[q]; ++e) v.node_grank[2 * cl[q] + cc[q] + e] = ev_g[cb[q] + e];
+}
+
+// Kernel B (rank form) for buckets without flagged components: the global pop order of the reference's
+// merge loop is a merge of the per-component event lists, and an event pops before every event of another
+// component whose PREFIX-MAX distance is larger (a component's later, smaller distances pop immediately
+// after the event that set the prefix max).  So the global creation rank of an event is its rank under the
+// key (prefix-max distance, component, index) -- computed by direct counting in shared memory, no
+// sequential replay -- except inside groups of events from different components that share one exact
+// prefix-max value; those (small, rare) groups are resolved by a literal heap walk over the group.
+constexpr int RK_THREADS = 512;
+__global__ void __launch_bounds__(RK_THREADS) ahc_replay_rank(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag,
+                                                              uint32_t n_lo, uint32_t n_hi)
+{
+  uint32_t b = blockIdx.x;
+  if (b >= nb || bucket_flag[b]) return;
+  uint32_t nleaf = v.seg_off[b + 1] - v.seg_off[b];
+  if (nleaf < n_lo || nleaf >= n_hi) return;
+  extern __shared__ unsigned char dynsm[];
+  __shared__ unsigned sh32[33];
+  __shared__ unsigned sh_M;
+  uint32_t c0 = bucket_comp_off[b], c1 = bucket_comp_off[b + 1], K = c1 - c0;
+  double *ev_d = reinterpret_cast<double *>(dynsm);                    // [cap = nleaf]
+  double *ev_pm = ev_d + nleaf;
+  int32_t *ev_first = reinterpret_cast<int32_t *>(ev_pm + nleaf);
+  uint32_t *ev_qi = reinterpret_cast<uint32_t *>(ev_first + nleaf);     // comp (high 16) | index (low 16)
+  uint32_t *rank = ev_qi + nleaf;
+  uint32_t *order = rank + nleaf;
+  uint32_t *cb = order + nleaf, *cn = cb + nleaf, *cc = cn + nleaf, *cl = cc + nleaf;
+  uint8_t *tie = reinterpret_cast<uint8_t *>(cl + nleaf);
+  const uint32_t pbase = v.seg_off[b];
+  unsigned run = 0;
+  for (uint32_t q0 = 0; q0 < K; q0 += RK_THREADS) {
+    uint32_t q = q0 + threadIdx.x;
+    unsigned nev = 0;
+    if (q < K) {
+      uint32_t comp = c0 + q, lbase = v.comp_off[comp], c = v.comp_off[comp + 1] - lbase;
+      nev = v.comp_nnodes[comp] - c;
+      cc[q] = c; cl[q] = lbase; cn[q] = nev;
+    }
+    unsigned tot;
+    unsigned ex = bk::block_excl_scan<unsigned>(nev, sh32, tot);
+    if (q < K) cb[q] = run + ex;
+    run += tot;
+  }
+  if (threadIdx.x == 0) sh_M = run;
+  __syncthreads();
+  const uint32_t M = sh_M;
+  for (uint32_t q = threadIdx.x; q < K; q += RK_THREADS) {
+    double pm = 0.0;
+    for (uint32_t e = 0; e < cn[q]; ++e) {
+      int32_t f = v.ev_first[cl[q] + e];
+      double d = v.ev_d[cl[q] + e];
+      if (d > pm) pm = d;
+      uint32_t o = cb[q] + e;
+      ev_d[o] = d; ev_pm[o] = pm;
+      ev_first[o] = (uint32_t)f < cc[q] ? (int32_t)(v.comp_leaf[cl[q] + f] - pbase) : -1 - (int32_t)((uint32_t)f - cc[q]);
+      ev_qi[o] = (q << 16) | e;
+    }
+  }
+  __syncthreads();
+  // rank by counting; events are stored in (component, index) order, so ev_qi is increasing with the slot
+  for (uint32_t e = threadIdx.x; e < M; e += RK_THREADS) {
+    double pm = ev_pm[e];
+    uint32_t qe = ev_qi[e] >> 16, cnt = 0;
+    bool t = false;
+    for (uint32_t o = 0; o < M; ++o) {
+      double p2 = ev_pm[o];
+      cnt += (p2 < pm || (p2 == pm && o < e)) ? 1u : 0u;
+      t |= (p2 == pm) && ((ev_qi[o] >> 16) != qe);
+    }
+    rank[e] = cnt; order[cnt] = e; tie[e] = t ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t r = 0;
+    while (r < M) {
+      uint32_t e0 = order[r];
+      if (!tie[e0]) { ++r; continue; }
+      uint32_t r2 = r + 1;
+      while (r2 < M && ev_pm[order[r2]] == ev_pm[e0]) ++r2;
+      // literal heap walk over the group [r, r2): heads = first unpopped event of each component's run
+      for (uint32_t s = 0; s < r2 - r; ++s) {
+        int best = -1; double bd = 0.0; int32_t bg = -1;
+        for (uint32_t p = r; p < r2; ++p) {
+          uint32_t e = order[p];
+          if (tie[e] == 2) continue;
+          if (p > r) { uint32_t ep = order[p - 1]; if ((ev_qi[ep] >> 16) == (ev_qi[e] >> 16) && tie[ep] != 2) continue; }
+          int32_t f = ev_first[e];
+          uint32_t q = ev_qi[e] >> 16;
+          int32_t gi = f >= 0 ? f : (int32_t)nleaf + (int32_t)rank[cb[q] + (uint32_t)(-1 - f)];
+          double d = ev_d[e];
+          if (best < 0 || d < bd || (d == bd && gi > bg)) { best = (int)e; bd = d; bg = gi; }
+        }
+        rank[best] = r + s;
+        tie[best] = 2;
+      }
+      r = r2;
+    }
+  }
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < M; e += RK_THREADS) {
+    uint32_t q = ev_qi[e] >> 16, i = ev_qi[e] & 0xffffu;
+    v.node_grank[2 * cl[q] + cc[q] + i] = (int32_t)rank[e];
+  }
 }
 
 // Kernel C: exact online form for buckets with a flagged component (one warp per bucket)

@@ -94,48 +94,62 @@ k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
             uint8_t *__restrict__ cls, uint32_t *__restrict__ tile_cand, unsigned long long *__restrict__ g_sum_abs,
             unsigned long long *__restrict__ g_cnt_insert)
 {
-  __shared__ unsigned long long sh64[33];
-  __shared__ unsigned sh32[33];
+  // The flag predicates are evaluated two records at a time on packed 2x16-bit words and the mapq
+  // predicates four at a time on packed 4x8-bit words (SIMD-in-register video instructions), so the
+  // kernel stays DRAM-bound instead of issue-bound (profiles/r01_ncu_k1_classify.md).
+  __shared__ unsigned long long sh_sum;
+  __shared__ unsigned sh_cnt;                 // n_ins in the low half, n_cand in the high half (<= 4096 each)
+  if (threadIdx.x == 0) { sh_sum = 0; sh_cnt = 0; }
+  __syncthreads();
   long long tile0 = (long long)blockIdx.x * K1_TILE;
   unsigned long long sum_abs = 0;
-  unsigned n_ins = 0, n_cand = 0;
+  unsigned cnt = 0;
+  const unsigned q4 = (unsigned)(qual < 0 ? 0 : (qual > 255 ? 255 : qual)) * 0x01010101u;
+  const bool q_never = qual > 255;           // mapq is 8 bits: nothing can pass
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     long long i = tile0 + g * (K1_THREADS * 4) + threadIdx.x * 4;
     if (i + 3 < n) {
       uint2 f2 = *reinterpret_cast<const uint2 *>(flag + i);
-      uchar4 m4 = *reinterpret_cast<const uchar4 *>(mapq + i);
+      unsigned m4 = *reinterpret_cast<const unsigned *>(mapq + i);
       int4 s4 = *reinterpret_cast<const int4 *>(isize + i);
-      unsigned f[4] = {f2.x & 0xffffu, f2.x >> 16, f2.y & 0xffffu, f2.y >> 16};
-      unsigned m[4] = {m4.x, m4.y, m4.z, m4.w};
-      int s[4] = {s4.x, s4.y, s4.z, s4.w};
-      unsigned c[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        c[k] = classify_one(f[k], m[k], qual);
-        if (c[k] & CL_INSERT) { sum_abs += (unsigned long long)(s[k] < 0 ? -(long long)s[k] : (long long)s[k]); ++n_ins; }
-        n_cand += (c[k] >> 1) & 1u;
-      }
-      *reinterpret_cast<uchar4 *>(cls + i) = make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], (unsigned char)c[3]);
+      // 2x16 masks: 0xFFFF where the predicate holds
+      unsigned ins_lo = __vcmpeq2(f2.x & 0x07070707u, 0x00030003u), ins_hi = __vcmpeq2(f2.y & 0x07070707u, 0x00030003u);     // :1932
+      unsigned bas_lo = __vcmpeq2(f2.x & 0x04010401u, 0x00010001u), bas_hi = __vcmpeq2(f2.y & 0x04010401u, 0x00010001u);     // !DUP && PAIRED
+      unsigned cnd_lo = __vcmpeq2(f2.x & 0x05030503u, 0x00010001u), cnd_hi = __vcmpeq2(f2.y & 0x05030503u, 0x00010001u);     // :1419-1420 flag part
+      // to 4x8 layout (byte k = record k)
+      unsigned ins8 = __byte_perm(ins_lo, ins_hi, 0x6420), bas8 = __byte_perm(bas_lo, bas_hi, 0x6420), cnd8 = __byte_perm(cnd_lo, cnd_hi, 0x6420);
+      unsigned ge8 = q_never ? 0u : __vcmpgeu4(m4, q4), gt8 = __vcmpne4(m4, 0u);
+      cnd8 &= ge8;
+      unsigned c4 = (ins8 & 0x01010101u) | (cnd8 & 0x02020202u) | (bas8 & gt8 & 0x04040404u) | (bas8 & 0x08080808u);
+      *reinterpret_cast<unsigned *>(cls + i) = c4;
+      cnt += __popc(ins8 & 0x01010101u) + (__popc(cnd8 & 0x01010101u) << 16);
+      int a0 = s4.x < 0 ? -s4.x : s4.x, a1 = s4.y < 0 ? -s4.y : s4.y, a2 = s4.z < 0 ? -s4.z : s4.z, a3 = s4.w < 0 ? -s4.w : s4.w;
+      unsigned t = (unsigned)a0 & (unsigned)((int)(ins8 << 24) >> 31);
+      unsigned long long part = t;
+      part += (unsigned)a1 & (unsigned)((int)(ins8 << 16) >> 31);
+      part += (unsigned)a2 & (unsigned)((int)(ins8 << 8) >> 31);
+      part += (unsigned)a3 & (unsigned)((int)ins8 >> 31);
+      sum_abs += part;
     } else {
       for (int k = 0; k < 4; ++k)
         if (i + k < n) {
           unsigned c = classify_one(flag[i + k], mapq[i + k], qual);
           int s = isize[i + k];
-          if (c & CL_INSERT) { sum_abs += (unsigned long long)(s < 0 ? -(long long)s : (long long)s); ++n_ins; }
-          n_cand += (c >> 1) & 1u;
+          if (c & CL_INSERT) { sum_abs += (unsigned long long)(s < 0 ? -(long long)s : (long long)s); cnt += 1u; }
+          cnt += ((c >> 1) & 1u) << 16;
           cls[i + k] = (uint8_t)c;
         }
     }
   }
-  unsigned long long tot64;
-  bk::block_excl_scan<unsigned long long>(sum_abs, sh64, tot64);
-  unsigned tot_ins, tot_cand;
-  bk::block_excl_scan<unsigned>(n_ins, sh32, tot_ins);
-  bk::block_excl_scan<unsigned>(n_cand, sh32, tot_cand);
+  cnt = bk::warp_sum(cnt);
+  sum_abs = bk::warp_sum(sum_abs);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh_cnt, cnt); atomicAdd(&sh_sum, sum_abs); }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    tile_cand[blockIdx.x] = tot_cand;
-    if (tot_ins) { atomicAdd(g_sum_abs, tot64); atomicAdd(g_cnt_insert, (unsigned long long)tot_ins); }
+    unsigned c = sh_cnt;
+    tile_cand[blockIdx.x] = c >> 16;
+    if (c & 0xffffu) { atomicAdd(g_sum_abs, sh_sum); atomicAdd(g_cnt_insert, (unsigned long long)(c & 0xffffu)); }
   }
 }
 
