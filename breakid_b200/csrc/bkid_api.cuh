@@ -50,7 +50,7 @@ struct bkid_ctx {
   bool classified = false, have_stats = false, scanned = false, clustered = false, refined = false;
   double mean = 0, sd = 0;
   long long sum_abs = 0, cnt_insert = 0, sd_total = 0;
-  DBuf tile_cand, counters, cand_idx;
+  DBuf tile_cand, counters, cand_idx, cand, bucket_rank_of;
   long long n_cand = 0;
   // pairs (stage 0)
   DBuf pairs0, pairs_tmp, bucket_off0;
@@ -64,7 +64,8 @@ struct bkid_ctx {
   long long n2 = 0;
   std::vector<int32_t> roots_per_bucket;
   // clusters
-  DBuf clusters, clusters_out;
+  DBuf clusters, clusters_out, sarows, work, cov, depth, evoff, valid;
+  const void *rows_ptr = nullptr; long long n_rows = 0, n_evcap = 0; int maxspan = 1; bool clusters_ranked = false;
   long long n_clusters = 0, n_called = 0;
   Scratch sc;
   DBuf tmpA, tmpB, tmpC, tmpD, tmpE, tmpF, tmpG, tmpH;
@@ -516,8 +517,8 @@ void bkid_destroy(bkid_ctx *c)
   cudaStreamSynchronize(c->st);
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->mtid, &c->mpos, &c->isize, &c->endpos, &c->nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
-                  &c->cand_idx, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->clusters, &c->clusters_out, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
+                  &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
+                  &c->mem_bucket, &c->mem_cluster, &c->clusters, &c->clusters_out, &c->sarows, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();
@@ -689,6 +690,38 @@ static int classify_impl(bkid_ctx *c)
   return 0;
 }
 
+// exact continuation of the truncating sd accumulator over the local records, starting from t_in
+static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *t_out)
+{
+  cudaStream_t st = c->st;
+  long long n = c->n;
+  *t_out = t_in;
+  if (n <= 0 || c->cnt_insert <= 0) return 0;
+  int nb = div_up(std::max<long long>(n, 1), SD_BLOCK);
+  TRY(c, c->tmpA.ensure((size_t)nb * (8 + SD_K * 4 + 4 + 8) + 256, 0, st));
+  char *bp = (char *)c->tmpA.p;
+  long long *blkF = (long long *)bp; bp += (size_t)nb * 8;
+  double *blkA = (double *)bp; bp += (size_t)nb * 8;
+  uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
+  uint32_t *blkN = (uint32_t *)bp;
+  long long *out = (long long *)(c->counters.as<unsigned>() + 8);
+  SubTimer T_(st);
+  BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, blkF, blkCum, blkN, blkA);
+  T_.mark("sd: block stats");
+  BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, nb, blkF, blkCum, blkN, blkA, t_in, out);
+  T_.mark("sd: resolve");
+  long long h[2] = {0, 0};
+  CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
+  TRY(c, sync_check(c));
+  if (h[1]) {                                                              // total left the closed-form regime: literal replay
+    BK_LAUNCH(sd_sequential, 1, 1, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, t_in, out);
+    CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+  }
+  *t_out = h[0];
+  return 0;
+}
+
 int bkid_insert_stats(bkid_ctx *c, double *mean, double *sd)
 {
   if (!c) return BKID_ERR_ARG;
@@ -697,37 +730,15 @@ int bkid_insert_stats(bkid_ctx *c, double *mean, double *sd)
   TRY(c, classify_impl(c));
   if (!c->have_stats) {
     cudaStream_t st = c->st;
-    long long n = c->n;
     c->mean = (double)c->sum_abs / (double)c->cnt_insert;                     // src/BreakID.cc:1941
-    int nb = div_up(std::max<long long>(n, 1), SD_BLOCK);
-    TRY(c, c->tmpA.ensure((size_t)nb * (8 + SD_K * 4 + 4 + 8) + 256, 0, st));
-    char *bp = (char *)c->tmpA.p;
-    long long *blkF = (long long *)bp; bp += (size_t)nb * 8;
-    double *blkA = (double *)bp; bp += (size_t)nb * 8;
-    uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
-    uint32_t *blkN = (uint32_t *)bp;
-    long long *out = (long long *)(c->counters.as<unsigned>() + 8);
     cudaEventRecord(c->ev[4], st);
-    long long h[2] = {0, 0};
-    SubTimer T_(st);
-    if (n > 0 && c->cnt_insert > 0) {
-      BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, blkF, blkCum, blkN, blkA);
-      T_.mark("sd: block stats");
-      BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, out);
-      T_.mark("sd: resolve");
-      CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
-      TRY(c, sync_check(c));
-      if (h[1]) {                                                              // total left the closed-form regime: literal replay
-        BK_LAUNCH(sd_sequential, 1, 1, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, out);
-        CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
-        TRY(c, sync_check(c));
-      }
-    }
+    long long t = 0;
+    TRY(c, sd_partial_impl(c, c->mean, 0, &t));
     cudaEventRecord(c->ev[5], st);
     TRY(c, sync_check(c));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
     c->tm.insert_stats = ms;
-    c->sd_total = h[0];
+    c->sd_total = t;
     c->sd = sqrt((double)c->sd_total / (double)c->cnt_insert);                // :1946
     c->have_stats = true;
   }
@@ -736,18 +747,16 @@ int bkid_insert_stats(bkid_ctx *c, double *mean, double *sd)
   return 0;
 }
 
-int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
+// ---- scan, in three reusable pieces (the multi-GPU path runs them around two exchanges) -------------
+// (1) local candidates in file order -> c->cand
+static int extract_candidates(bkid_ctx *c, unsigned long long index_offset)
 {
-  if (!c) return BKID_ERR_ARG;
-  cudaSetDevice(c->device);
-  c->err.clear();
   TRY(c, classify_impl(c));
   cudaStream_t st = c->st;
   long long n = c->n;
   int ntiles = div_up(std::max<long long>(n, 1), K1_TILE);
   uint32_t *tile_cand = c->tile_cand.as<uint32_t>(), *tile_off = tile_cand + ntiles + 1;
   unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
-  cudaEventRecord(c->ev[6], st);
   TRY(c, c->sc.ensure(ntiles + 8, st));
   unsigned long long nc = 0;
   if (n > 0) {
@@ -756,63 +765,96 @@ int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
     TRY(c, sync_check(c));
   }
   c->n_cand = (long long)nc;
-  c->np0 = 0; c->nb = 0;
-  SubTimer T_(st);
+  TRY(c, c->cand.ensure((size_t)(nc + 1) * sizeof(bkid_cand), 0, st));
   if (nc > 0) {
     TRY(c, c->cand_idx.ensure((size_t)nc * 4 + 64, 0, st));
     BK_LAUNCH(k1_compact, (unsigned)ntiles, K1_THREADS, 0, st, c->cls.as<uint8_t>(), n, tile_off, c->cand_idx.as<uint32_t>());
-    TRY(c, c->sc.ensure((long long)nc + 8, st));
-    uint64_t *key = c->sc.keys.as<uint64_t>();
-    uint32_t *val = c->sc.vals.as<uint32_t>();
-    BK_LAUNCH(k2_gather_keys, GRID1(nc, 256), 256, 0, st, c->cand_idx.as<uint32_t>(), (long long)nc, c->p_nh, key, val);
-    T_.mark("join: compact+gather");
-    bk::radix_sort_pairs(key, val, (long long)nc, 0, 64, c->sc.rt(), st);
-    T_.mark("join: radix sort 64b");
-    uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
-    int *errf = (int *)(c->counters.as<unsigned>() + 40);
-    CU(c, cudaMemsetAsync(errf, 0, 4, st));
-    BK_LAUNCH(k2_run_heads, GRID1(nc, 256), 256, 0, st, key, val, (long long)nc, c->p_nh, head, errf);
-    bk::exclusive_scan<uint32_t, uint32_t>(head, hex, (long long)nc, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-    BK_LAUNCH(k2_run_starts, GRID1(nc, 256), 256, 0, st, head, hex, (long long)nc, rstart);
-    // emit (unordered), then order by (bucket rank, index of the second-seen mate)
-    size_t maxp = (size_t)nc / 2 + 1;
-    TRY(c, c->pairs_tmp.ensure(maxp * sizeof(bkid_pair), 0, st));
-    TRY(c, c->pairs0.ensure(maxp * sizeof(bkid_pair), 0, st));
-    TRY(c, c->tmpA.ensure(maxp * 8 + 64, 0, st)); TRY(c, c->tmpB.ensure(maxp * 4 + 64, 0, st));
-    unsigned long long *pcount = tot + 1;
-    CU(c, cudaMemsetAsync(pcount, 0, 8, st));
-    unsigned long long *pkey = c->tmpA.as<unsigned long long>();
-    uint32_t *pslot = c->tmpB.as<uint32_t>();
-    BK_LAUNCH(k2_emit_pairs, GRID1(nc, 256), 256, 0, st, val, head, hex, rstart, (long long)nc, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_mtid, c->p_mpos,
-              c->p_nh, c->d_cum.as<uint32_t>(), c->nt, c->d_bucket_rank.as<int32_t>(), w, c->pairs_tmp.as<bkid_pair>(), pkey, pslot, pcount);
-    unsigned long long np = 0; int herr = 0;
-    CU(c, cudaMemcpyAsync(&np, pcount, 8, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaMemcpyAsync(&herr, errf, 4, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-    T_.mark("join: runs+emit");
-    if (herr) return fail(c, BKID_ERR_HASH, "two different read names share a 64-bit hash prefix");
-    cudaEventRecord(c->ev[7], st);
-    c->np0 = (long long)np;
-    if (np > 0) {
-      // keys were written into tmpA (uint64) -- sort with slot payload; reuse the scratch alt buffers
-      TRY(c, c->sc.ensure((long long)std::max<unsigned long long>(np, nc) + 8, st));
-      int rbits = 1; while ((1ll << rbits) < (long long)(c->nt + 1) * (c->nt + 1) + 1) ++rbits;
-      bk::radix_sort_pairs((uint64_t *)pkey, pslot, (long long)np, 0, 32 + rbits, c->sc.rt(), st);
-      uint32_t *bh = c->sc.a32.as<uint32_t>(), *bhx = c->sc.b32.as<uint32_t>();
-      BK_LAUNCH(k2_gather_pairs, GRID1(np, 256), 256, 0, st, c->pairs_tmp.as<bkid_pair>(), pslot, pkey, (long long)np, c->pairs0.as<bkid_pair>(), bh);
-      bk::exclusive_scan<uint32_t, uint32_t>(bh, bhx, (long long)np, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-      unsigned long long nbk = 0;
-      CU(c, cudaMemcpyAsync(&nbk, tot, 8, cudaMemcpyDeviceToHost, st));
-      TRY(c, sync_check(c));
-      c->nb = (int)nbk;
-      TRY(c, c->bucket_off0.ensure((size_t)(nbk + 2) * 4, 0, st));
-      BK_LAUNCH(k2_bucket_ids, GRID1(np, 256), 256, 0, st, c->pairs0.as<bkid_pair>(), bh, bhx, (long long)np, c->bucket_off0.as<uint32_t>());
-      uint32_t npu = (uint32_t)np;
-      CU(c, cudaMemcpyAsync(c->bucket_off0.as<uint32_t>() + nbk, &npu, 4, cudaMemcpyHostToDevice, st));
-      TRY(c, c->X.ensure((size_t)np * 4 + 64, 0, st)); TRY(c, c->Y.ensure((size_t)np * 4 + 64, 0, st)); TRY(c, c->bucket_of_pair.ensure((size_t)np * 4 + 64, 0, st));
-      BK_LAUNCH(pair_xy, GRID1(np, 256), 256, 0, st, c->pairs0.as<bkid_pair>(), (long long)np, c->X.as<uint32_t>(), c->Y.as<uint32_t>(), c->bucket_of_pair.as<uint32_t>());
-    }
-  } else cudaEventRecord(c->ev[7], st);
+    BK_LAUNCH(k2_gather_cand, GRID1(nc, 256), 256, 0, st, c->cand_idx.as<uint32_t>(), (long long)nc, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_mtid, c->p_mpos,
+              c->p_nh, index_offset, c->cand.as<bkid_cand>());
+  }
+  return 0;
+}
+
+// (2) mate join on a candidate array that is in global file order -> unordered pairs in c->pairs_tmp
+static int join_candidates(bkid_ctx *c, const bkid_cand *cand, long long nc, double w, long long *np_out)
+{
+  cudaStream_t st = c->st;
+  *np_out = 0;
+  if (nc <= 0) return 0;
+  SubTimer T_(st);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  TRY(c, c->sc.ensure(nc + 8, st));
+  uint64_t *key = c->sc.keys.as<uint64_t>();
+  uint32_t *val = c->sc.vals.as<uint32_t>();
+  BK_LAUNCH(k2_cand_keys, GRID1(nc, 256), 256, 0, st, cand, nc, key, val);
+  bk::radix_sort_pairs(key, val, nc, 0, 64, c->sc.rt(), st);
+  T_.mark("join: radix sort 64b");
+  uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
+  int *errf = (int *)(c->counters.as<unsigned>() + 40);
+  CU(c, cudaMemsetAsync(errf, 0, 4, st));
+  BK_LAUNCH(k2_run_heads, GRID1(nc, 256), 256, 0, st, key, val, nc, cand, head, errf);
+  bk::exclusive_scan<uint32_t, uint32_t>(head, hex, nc, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+  BK_LAUNCH(k2_run_starts, GRID1(nc, 256), 256, 0, st, head, hex, nc, rstart);
+  size_t maxp = (size_t)nc / 2 + 1;
+  TRY(c, c->pairs_tmp.ensure(maxp * sizeof(bkid_pair), 0, st));
+  unsigned long long *pcount = tot + 1;
+  CU(c, cudaMemsetAsync(pcount, 0, 8, st));
+  BK_LAUNCH(k2_emit_pairs, GRID1(nc, 256), 256, 0, st, val, head, hex, rstart, nc, cand, c->d_cum.as<uint32_t>(), c->nt, c->d_bucket_rank.as<int32_t>(), w,
+            c->pairs_tmp.as<bkid_pair>(), pcount);
+  unsigned long long np = 0; int herr = 0;
+  CU(c, cudaMemcpyAsync(&np, pcount, 8, cudaMemcpyDeviceToHost, st));
+  CU(c, cudaMemcpyAsync(&herr, errf, 4, cudaMemcpyDeviceToHost, st));
+  TRY(c, sync_check(c));
+  T_.mark("join: runs+emit");
+  if (herr) return fail(c, BKID_ERR_HASH, "two different read names share a 64-bit hash prefix");
+  *np_out = (long long)np;
+  return 0;
+}
+
+// (3) order pairs by (bucket rank, index of the second-seen mate), build buckets -> c->pairs0 ...
+static int set_pairs(bkid_ctx *c, const bkid_pair *pairs, long long np)
+{
+  cudaStream_t st = c->st;
+  c->np0 = np; c->nb = 0;
+  if (np <= 0) return 0;
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  TRY(c, c->sc.ensure(np + 8, st));
+  TRY(c, c->pairs0.ensure((size_t)np * sizeof(bkid_pair), 0, st));
+  unsigned long long *pkey = (unsigned long long *)c->sc.keys.as<uint64_t>();
+  uint32_t *pslot = c->sc.vals.as<uint32_t>();
+  BK_LAUNCH(k2_pair_keys, GRID1(np, 256), 256, 0, st, pairs, np, pkey, pslot);
+  int rbits = 1; while ((1ll << rbits) < (long long)(c->nt + 1) * (c->nt + 1) + 1) ++rbits;
+  bk::radix_sort_pairs((uint64_t *)pkey, pslot, np, 0, PAIR_IDX_BITS + rbits, c->sc.rt(), st);
+  uint32_t *bh = c->sc.a32.as<uint32_t>(), *bhx = c->sc.b32.as<uint32_t>();
+  BK_LAUNCH(k2_gather_pairs, GRID1(np, 256), 256, 0, st, pairs, pslot, pkey, np, c->pairs0.as<bkid_pair>(), bh);
+  bk::exclusive_scan<uint32_t, uint32_t>(bh, bhx, np, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+  unsigned long long nbk = 0;
+  CU(c, cudaMemcpyAsync(&nbk, tot, 8, cudaMemcpyDeviceToHost, st));
+  TRY(c, sync_check(c));
+  c->nb = (int)nbk;
+  TRY(c, c->bucket_off0.ensure((size_t)(nbk + 2) * 4, 0, st));
+  TRY(c, c->bucket_rank_of.ensure((size_t)(nbk + 2) * 4, 0, st));
+  BK_LAUNCH(k2_bucket_ids, GRID1(np, 256), 256, 0, st, c->pairs0.as<bkid_pair>(), bh, bhx, np, c->bucket_off0.as<uint32_t>(), c->bucket_rank_of.as<int32_t>());
+  uint32_t npu = (uint32_t)np;
+  CU(c, cudaMemcpyAsync(c->bucket_off0.as<uint32_t>() + nbk, &npu, 4, cudaMemcpyHostToDevice, st));
+  TRY(c, c->X.ensure((size_t)np * 4 + 64, 0, st)); TRY(c, c->Y.ensure((size_t)np * 4 + 64, 0, st)); TRY(c, c->bucket_of_pair.ensure((size_t)np * 4 + 64, 0, st));
+  BK_LAUNCH(pair_xy, GRID1(np, 256), 256, 0, st, c->pairs0.as<bkid_pair>(), np, c->X.as<uint32_t>(), c->Y.as<uint32_t>(), c->bucket_of_pair.as<uint32_t>());
+  return sync_check(c);
+}
+
+int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  c->err.clear();
+  cudaStream_t st = c->st;
+  TRY(c, classify_impl(c));
+  cudaEventRecord(c->ev[6], st);
+  TRY(c, extract_candidates(c, 0ull));
+  long long np = 0;
+  TRY(c, join_candidates(c, c->cand.as<bkid_cand>(), c->n_cand, w, &np));
+  cudaEventRecord(c->ev[7], st);
+  TRY(c, set_pairs(c, c->pairs_tmp.as<bkid_pair>(), np));
   cudaEventRecord(c->ev[8], st);
   TRY(c, sync_check(c));
   float ms = 0;
@@ -831,7 +873,7 @@ int bkid_cluster(bkid_ctx *c, double dist, int mode, int64_t *n_clusters)
   cudaSetDevice(c->device);
   c->err.clear();
   cudaStream_t st = c->st;
-  c->n1 = c->n2 = 0; c->n_clusters = 0;
+  c->n1 = c->n2 = 0; c->n_clusters = 0; c->clusters_ranked = false;
   cudaEventRecord(c->ev[9], st);
   if (c->np0 > 0) {
     long long np = c->np0;
@@ -899,6 +941,128 @@ int bkid_set_nib(bkid_ctx *c, int32_t tid, const uint8_t *packed, uint64_t n_bas
   return sync_check(c);
 }
 
+// ---- refinement, in reusable pieces (the multi-GPU path all-reduces the two partial-count buffers) -----
+static int refine_build_rows(bkid_ctx *c)
+{
+  cudaStream_t st = c->st;
+  TRY(c, classify_impl(c));
+  TRY(c, c->sarows.ensure((size_t)(c->n_sa + 1) * sizeof(EvRow), 0, st));
+  if (c->n_sa > 0)
+    BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->p_flag, c->p_tid, c->p_pos, c->p_endpos, c->p_nh, c->p_cig_off, c->p_cig_ops,
+              c->p_sa_off, c->p_sa_txt, c->p_oc_off, c->p_oc_txt, c->prm.mismatch_num, c->sarows.as<EvRow>());
+  c->rows_ptr = c->sarows.as<EvRow>(); c->n_rows = c->n_sa;
+  return 0;
+}
+
+static int refine_local_maxspan(bkid_ctx *c, int *out)
+{
+  cudaStream_t st = c->st;
+  int *mx = (int *)(c->counters.as<unsigned>() + 44);
+  CU(c, cudaMemsetAsync(mx, 0, 4, st));
+  if (c->n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, st, c->p_pos, c->p_endpos, c->n, mx);
+  int maxspan = 0;
+  CU(c, cudaMemcpyAsync(&maxspan, mx, 4, cudaMemcpyDeviceToHost, st));
+  TRY(c, sync_check(c));
+  *out = maxspan + 1;
+  return 0;
+}
+
+static RefineView refine_view(bkid_ctx *c)
+{
+  RefineView v;
+  v.n = c->n; v.cls = c->cls.as<uint8_t>(); v.tid = c->p_tid; v.pos = c->p_pos; v.endpos = c->p_endpos;
+  v.n_sa = c->n_rows; v.rows = (const EvRow *)c->rows_ptr; v.maxspan = c->maxspan;
+  v.canon = c->d_canon.as<uint64_t>(); v.nt = c->nt;
+  v.nib = (const uint8_t *const *)c->d_nib_ptr.p; v.nib_len = c->d_nib_len.as<uint64_t>();
+  return v;
+}
+
+// regions + partial coverage of the local record shard -> c->cov [2*ncl]
+static int refine_coverage(bkid_ctx *c, double dist)
+{
+  cudaStream_t st = c->st;
+  uint32_t ncl = (uint32_t)c->n_clusters;
+  TRY(c, classify_impl(c));
+  TRY(c, c->sc.ensure((long long)ncl + 8, st));
+  TRY(c, c->work.ensure((size_t)(ncl + 1) * sizeof(ClusterWork), 0, st));
+  TRY(c, c->cov.ensure((size_t)(2 * ncl + 2) * 4, 0, st));
+  TRY(c, c->depth.ensure((size_t)(2 * ncl + 2) * 4, 0, st));
+  TRY(c, c->evoff.ensure((size_t)(ncl + 2) * 4, 0, st));
+  if (ncl == 0) return 0;
+  RefineView v = refine_view(c);
+  int w = (int)dist;                                                       // const int w (src/BreakID.cc:390)
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  uint32_t *evcap = c->sc.a32.as<uint32_t>();
+  BK_LAUNCH(k7_regions, GRID1(ncl, 128), 128, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, w, c->work.as<ClusterWork>(), evcap);
+  bk::exclusive_scan<uint32_t, uint32_t>(evcap, c->evoff.as<uint32_t>(), ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+  BK_LAUNCH(k7_coverage, GRID1(ncl, 4), 128, 0, st, v, c->work.as<ClusterWork>(), ncl, c->cov.as<uint32_t>());
+  unsigned long long nev = 0;
+  CU(c, cudaMemcpyAsync(&nev, tot, 8, cudaMemcpyDeviceToHost, st));
+  TRY(c, sync_check(c));
+  c->n_evcap = (long long)nev;
+  return 0;
+}
+
+// gate + evidence pairing + vote (needs TOTAL coverage in c->cov)
+static int refine_vote(bkid_ctx *c)
+{
+  cudaStream_t st = c->st;
+  uint32_t ncl = (uint32_t)c->n_clusters;
+  if (ncl == 0) return 0;
+  RefineView v = refine_view(c);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  ClusterWork *work = c->work.as<ClusterWork>();
+  uint32_t *entcnt = c->sc.c32.as<uint32_t>(), *entoff = c->sc.d32.as<uint32_t>();
+  TRY(c, c->valid.ensure((size_t)(ncl + 2) * 4, 0, st));
+  TRY(c, c->tmpC.ensure((size_t)(c->n_evcap + 1) * 4, 0, st));
+  int *fatal = (int *)(c->counters.as<unsigned>() + 46);
+  CU(c, cudaMemsetAsync(fatal, 0, 4, st));
+  BK_LAUNCH((k7_collect<false>), ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, c->cov.as<uint32_t>(), c->evoff.as<uint32_t>(),
+            c->tmpC.as<uint32_t>(), (const uint32_t *)nullptr, (int2 *)nullptr);
+  BK_LAUNCH(k7_entry_counts, GRID1(ncl, 128), 128, 0, st, work, ncl, entcnt, fatal);
+  bk::exclusive_scan<uint32_t, uint32_t>(entcnt, entoff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+  unsigned long long nent = 0; int hf = 0;
+  CU(c, cudaMemcpyAsync(&nent, tot, 8, cudaMemcpyDeviceToHost, st));
+  CU(c, cudaMemcpyAsync(&hf, fatal, 4, cudaMemcpyDeviceToHost, st));
+  TRY(c, sync_check(c));
+  if (hf) return fail(c, BKID_ERR_CIGAR, "error cigar: a complementary split alignment has no clip (reference exits at src/BreakID.cc:954-968)");
+  TRY(c, c->tmpD.ensure((size_t)(nent + 1) * sizeof(int2), 0, st));
+  BK_LAUNCH((k7_collect<true>), ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, c->cov.as<uint32_t>(), c->evoff.as<uint32_t>(),
+            c->tmpC.as<uint32_t>(), entoff, c->tmpD.as<int2>());
+  BK_LAUNCH(k8_vote, ncl, RF_THREADS, 0, st, c->clusters.as<bkid_cluster_rec>(), ncl, work, entoff, c->tmpD.as<int2>(), c->prm.bp_pos_error, c->valid.as<uint32_t>());
+  c->tm.n_evidence = (long long)nent;
+  return 0;
+}
+
+static int refine_depth(bkid_ctx *c)
+{
+  uint32_t ncl = (uint32_t)c->n_clusters;
+  if (ncl == 0) return 0;
+  RefineView v = refine_view(c);
+  BK_LAUNCH(k9_depth, GRID1(ncl, 4), 128, 0, c->st, v, c->clusters.as<bkid_cluster_rec>(), c->valid.as<uint32_t>(), ncl, c->depth.as<uint32_t>());
+  return 0;
+}
+
+static int refine_finish(bkid_ctx *c)
+{
+  cudaStream_t st = c->st;
+  uint32_t ncl = (uint32_t)c->n_clusters;
+  c->n_called = 0;
+  if (ncl == 0) return 0;
+  RefineView v = refine_view(c);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  BK_LAUNCH(k10_finish, GRID1(ncl, 128), 128, 0, st, v, c->clusters.as<bkid_cluster_rec>(), c->valid.as<uint32_t>(), c->depth.as<uint32_t>(), ncl);
+  uint32_t *voff = c->sc.b32.as<uint32_t>();
+  bk::exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), voff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+  unsigned long long nv = 0;
+  CU(c, cudaMemcpyAsync(&nv, tot, 8, cudaMemcpyDeviceToHost, st));
+  TRY(c, sync_check(c));
+  TRY(c, c->clusters_out.ensure((size_t)(ncl + 1) * sizeof(bkid_cluster_rec), 0, st));
+  BK_LAUNCH(compact_clusters, GRID1(ncl, 128), 128, 0, st, c->clusters.as<bkid_cluster_rec>(), c->valid.as<uint32_t>(), voff, ncl, c->clusters_out.as<bkid_cluster_rec>());
+  c->n_called = (long long)nv;
+  return sync_check(c);
+}
+
 int bkid_refine(bkid_ctx *c, double dist, int64_t *n_called)
 {
   if (!c) return BKID_ERR_ARG;
@@ -908,59 +1072,14 @@ int bkid_refine(bkid_ctx *c, double dist, int64_t *n_called)
   cudaStream_t st = c->st;
   c->n_called = 0;
   cudaEventRecord(c->ev[13], st);
-  uint32_t ncl = (uint32_t)c->n_clusters;
-  if (ncl > 0) {
-    // K7a evidence rows for every SA record
-    TRY(c, c->tmpA.ensure((size_t)(c->n_sa + 1) * sizeof(EvRow), 0, st));
-    EvRow *rows = c->tmpA.as<EvRow>();
-    if (c->n_sa > 0)
-      BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->p_flag, c->p_tid, c->p_pos, c->p_cig_off, c->p_cig_ops, c->p_sa_off, c->p_sa_txt,
-                c->p_oc_off, c->p_oc_txt, c->prm.mismatch_num, rows);
-    int *mx = (int *)(c->counters.as<unsigned>() + 44);
-    CU(c, cudaMemsetAsync(mx, 0, 4, st));
-    if (c->n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, st, c->p_pos, c->p_endpos, c->n, mx);
-    int maxspan = 0;
-    CU(c, cudaMemcpyAsync(&maxspan, mx, 4, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
+  if (c->n_clusters > 0) {
+    TRY(c, refine_build_rows(c));
+    TRY(c, refine_local_maxspan(c, &c->maxspan));
     cudaEventRecord(c->ev[14], st);
-    RefineView v;
-    v.n = c->n; v.flag = c->p_flag; v.cls = c->cls.as<uint8_t>(); v.tid = c->p_tid; v.pos = c->p_pos; v.endpos = c->p_endpos; v.nh = c->p_nh;
-    v.n_sa = c->n_sa; v.sa_rec = c->p_sa_rec; v.rows = rows; v.maxspan = maxspan + 1;
-    v.canon = c->d_canon.as<uint64_t>(); v.nt = c->nt;
-    v.nib = (const uint8_t *const *)c->d_nib_ptr.p; v.nib_len = c->d_nib_len.as<uint64_t>();
-    TRY(c, c->sc.ensure((long long)ncl + 8, st));
-    TRY(c, c->tmpB.ensure((size_t)(ncl + 1) * sizeof(ClusterWork), 0, st));
-    ClusterWork *work = c->tmpB.as<ClusterWork>();
-    uint32_t *evcap = c->sc.a32.as<uint32_t>(), *evoff = c->sc.b32.as<uint32_t>(), *entcnt = c->sc.c32.as<uint32_t>(), *entoff = c->sc.d32.as<uint32_t>(), *valid = c->sc.e32.as<uint32_t>();
-    unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
-    int w = (int)dist;                                                       // const int w (src/BreakID.cc:390)
-    BK_LAUNCH(k7_regions, GRID1(ncl, 128), 128, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, w, work, evcap);
-    bk::exclusive_scan<uint32_t, uint32_t>(evcap, evoff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-    unsigned long long nev = 0;
-    CU(c, cudaMemcpyAsync(&nev, tot, 8, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-    TRY(c, c->tmpC.ensure((size_t)(nev + 1) * 4, 0, st));
-    int *fatal = (int *)(c->counters.as<unsigned>() + 46);
-    CU(c, cudaMemsetAsync(fatal, 0, 4, st));
-    BK_LAUNCH((k7_collect<false>), ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, evoff, c->tmpC.as<uint32_t>(), (const uint32_t *)nullptr, (int2 *)nullptr);
-    BK_LAUNCH(k7_entry_counts, GRID1(ncl, 128), 128, 0, st, work, ncl, entcnt, fatal);
-    bk::exclusive_scan<uint32_t, uint32_t>(entcnt, entoff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-    unsigned long long nent = 0; int hf = 0;
-    CU(c, cudaMemcpyAsync(&nent, tot, 8, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaMemcpyAsync(&hf, fatal, 4, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-    if (hf) return fail(c, BKID_ERR_CIGAR, "error cigar: a complementary split alignment has no clip (reference exits at src/BreakID.cc:954-968)");
-    TRY(c, c->tmpD.ensure((size_t)(nent + 1) * sizeof(int2), 0, st));
-    BK_LAUNCH((k7_collect<true>), ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, evoff, c->tmpC.as<uint32_t>(), entoff, c->tmpD.as<int2>());
-    BK_LAUNCH(k8_vote, ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, entoff, c->tmpD.as<int2>(), c->prm.bp_pos_error, valid);
-    uint32_t *voff = evoff;
-    bk::exclusive_scan<uint32_t, uint32_t>(valid, voff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-    unsigned long long nv = 0;
-    CU(c, cudaMemcpyAsync(&nv, tot, 8, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-    BK_LAUNCH(compact_clusters, GRID1(ncl, 128), 128, 0, st, c->clusters.as<bkid_cluster_rec>(), valid, voff, ncl, c->clusters_out.as<bkid_cluster_rec>());
-    c->n_called = (long long)nv;
-    c->tm.n_evidence = (long long)nent;
+    TRY(c, refine_coverage(c, dist));
+    TRY(c, refine_vote(c));
+    TRY(c, refine_depth(c));
+    TRY(c, refine_finish(c));
   } else cudaEventRecord(c->ev[14], st);
   cudaEventRecord(c->ev[15], st);
   TRY(c, sync_check(c));
@@ -970,6 +1089,176 @@ int bkid_refine(bkid_ctx *c, double dist, int64_t *n_called)
   c->tm.n_sa = c->n_sa; c->tm.n_called = c->n_called;
   c->refined = true;
   if (n_called) *n_called = c->n_called;
+  return 0;
+}
+
+// =============================================================================================
+// Shard entry points (multi-GPU; one context per rank, exchanges done by the caller -- see
+// breakid_b200/dist.py).  Device pointers handed out stay valid until the next call on the context.
+// =============================================================================================
+static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *t_out);
+
+int bkid_shard_insert_partial(bkid_ctx *c, int64_t *sum_abs, int64_t *count)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, classify_impl(c));
+  *sum_abs = c->sum_abs; *count = c->cnt_insert;
+  return 0;
+}
+
+int bkid_shard_sd_partial(bkid_ctx *c, double mean, int64_t t_in, int64_t *t_out)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, classify_impl(c));
+  long long t = 0;
+  TRY(c, sd_partial_impl(c, mean, (long long)t_in, &t));
+  *t_out = t;
+  return 0;
+}
+
+int bkid_shard_set_stats(bkid_ctx *c, double mean, double sd)
+{
+  if (!c) return BKID_ERR_ARG;
+  c->mean = mean; c->sd = sd; c->have_stats = true;
+  return 0;
+}
+
+int bkid_shard_candidates(bkid_ctx *c, uint64_t index_offset, const bkid_cand **dev, int64_t *n)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, extract_candidates(c, index_offset));
+  TRY(c, sync_check(c));
+  *dev = c->cand.as<bkid_cand>(); *n = c->n_cand;
+  return 0;
+}
+
+int bkid_shard_join(bkid_ctx *c, const bkid_cand *dev_cand, int64_t n, double w, const bkid_pair **dev_pairs, int64_t *n_pairs)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  long long np = 0;
+  TRY(c, join_candidates(c, dev_cand, n, w, &np));
+  *dev_pairs = c->pairs_tmp.as<bkid_pair>(); *n_pairs = np;
+  return 0;
+}
+
+int bkid_shard_set_pairs(bkid_ctx *c, const bkid_pair *dev_pairs, int64_t n)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, set_pairs(c, dev_pairs, n));
+  c->tm.n_pairs = c->np0;
+  c->scanned = true; c->clustered = c->refined = false;
+  return 0;
+}
+
+__global__ void cluster_bucket_to_rank(bkid_cluster_rec *cl, uint32_t n, const int32_t *__restrict__ rank_of)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cl[i].bucket = rank_of[cl[i].bucket];
+}
+
+// local clusters after bkid_cluster, with `bucket` rewritten to the GLOBAL bucket-name rank
+int bkid_shard_clusters(bkid_ctx *c, const bkid_cluster_rec **dev, int64_t *n)
+{
+  if (!c || !c->clustered) return c ? fail(c, BKID_ERR_ARG, "bkid_shard_clusters before bkid_cluster") : BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  if (c->n_clusters > 0 && !c->clusters_ranked) {
+    BK_LAUNCH(cluster_bucket_to_rank, GRID1(c->n_clusters, 128), 128, 0, c->st, c->clusters.as<bkid_cluster_rec>(), (uint32_t)c->n_clusters, c->bucket_rank_of.as<int32_t>());
+    c->clusters_ranked = true;
+  }
+  TRY(c, sync_check(c));
+  *dev = c->clusters.as<bkid_cluster_rec>(); *n = c->n_clusters;
+  return 0;
+}
+
+int bkid_shard_set_clusters(bkid_ctx *c, const bkid_cluster_rec *dev, int64_t n)
+{
+  if (!c || n < 0) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, c->clusters.ensure((size_t)(n + 1) * sizeof(bkid_cluster_rec), 0, c->st));
+  if (n > 0 && dev != c->clusters.as<bkid_cluster_rec>()) CU(c, cudaMemcpyAsync(c->clusters.p, dev, (size_t)n * sizeof(bkid_cluster_rec), cudaMemcpyDeviceToDevice, c->st));
+  c->n_clusters = n; c->clusters_ranked = true; c->clustered = true; c->refined = false;
+  return sync_check(c);
+}
+
+int bkid_shard_sa_rows(bkid_ctx *c, const bkid_sarow **dev, int64_t *n)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, refine_build_rows(c));
+  TRY(c, sync_check(c));
+  *dev = (const bkid_sarow *)c->sarows.p; *n = c->n_sa;
+  return 0;
+}
+
+int bkid_shard_set_sa_rows(bkid_ctx *c, const bkid_sarow *dev, int64_t n)
+{
+  if (!c || n < 0) return BKID_ERR_ARG;
+  c->rows_ptr = dev; c->n_rows = n;
+  return 0;
+}
+
+int bkid_shard_maxspan(bkid_ctx *c, int32_t *maxspan)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  int ms = 0;
+  TRY(c, refine_local_maxspan(c, &ms));
+  *maxspan = ms;
+  return 0;
+}
+
+int bkid_shard_set_maxspan(bkid_ctx *c, int32_t maxspan) { if (!c) return BKID_ERR_ARG; c->maxspan = maxspan; return 0; }
+
+int bkid_shard_coverage(bkid_ctx *c, double dist, uint32_t **dev_cov, int64_t *n)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, refine_coverage(c, dist));
+  *dev_cov = c->cov.as<uint32_t>(); *n = 2 * c->n_clusters;
+  return 0;
+}
+
+int bkid_shard_vote(bkid_ctx *c)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, refine_vote(c));
+  return sync_check(c);
+}
+
+int bkid_shard_depth(bkid_ctx *c, uint32_t **dev_depth, int64_t *n)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, refine_depth(c));
+  TRY(c, sync_check(c));
+  *dev_depth = c->depth.as<uint32_t>(); *n = 2 * c->n_clusters;
+  return 0;
+}
+
+int bkid_shard_finish(bkid_ctx *c, int64_t *n_called)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, refine_finish(c));
+  c->refined = true;
+  c->tm.n_called = c->n_called;
+  if (n_called) *n_called = c->n_called;
+  return 0;
+}
+
+int bkid_fetch_bucket_ranks(bkid_ctx *c, int32_t *out, int64_t cap, int64_t *nb)
+{
+  if (!c || !c->scanned) return c ? fail(c, BKID_ERR_ARG, "bkid_fetch_bucket_ranks before scan") : BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (nb) *nb = c->nb;
+  long long k = std::min<long long>(cap, c->nb);
+  if (out && k > 0) CU(c, cudaMemcpy(out, c->bucket_rank_of.p, (size_t)k * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

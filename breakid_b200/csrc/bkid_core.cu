@@ -278,7 +278,7 @@ sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isiz
 __global__ void __launch_bounds__(1024)
 sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, int nb,
            const long long *__restrict__ blkF, const uint32_t *__restrict__ blkCum, const uint32_t *__restrict__ blkN,
-           const double *__restrict__ blkAmax, long long *__restrict__ out)
+           const double *__restrict__ blkAmax, long long t_in, long long *__restrict__ out)
 {
   extern __shared__ unsigned char dyn[];
   double *sa = reinterpret_cast<double *>(dyn);                  // [SD_BLOCK]   a_i, -1 = ineligible
@@ -286,7 +286,7 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
   __shared__ long long sh_scan[33];
   __shared__ long long sh_t;
   __shared__ int sh_j, sh_q, sh_oor, sh_k;
-  if (threadIdx.x == 0) { sh_t = 0; sh_j = 0; sh_oor = 0; }
+  if (threadIdx.x == 0) { sh_t = t_in; sh_j = 0; sh_oor = 0; }
   __syncthreads();
   while (true) {
     int j0 = sh_j;
@@ -387,10 +387,10 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
 }
 
 // literal sequential replay (one thread); only used when the total leaves the closed-form regime
-__global__ void sd_sequential(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, long long *out)
+__global__ void sd_sequential(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, long long t_in, long long *out)
 {
   if (blockIdx.x || threadIdx.x) return;
-  long long t = 0;
+  long long t = t_in;
   for (long long i = 0; i < n; ++i)
     if (cls[i] & CL_INSERT) {
       int s = isize[i];
@@ -408,13 +408,32 @@ __global__ void sd_sequential(const uint8_t *__restrict__ cls, const int32_t *__
 // pairs run positions (0,1), (2,3), ...: the odd one is the "current" record, the even one the
 // stored mate.
 // =============================================================================================
-__global__ void k2_gather_keys(const uint32_t *__restrict__ cand_idx, long long nc, const uint64_t *__restrict__ nh, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+// candidate records are gathered once into a compact array (bkid_cand, 48 B): the sort, the run
+// detection and the pair emission then touch two coalesced 48-byte rows per pair instead of eleven
+// scattered column reads, and the same array is what ranks exchange in the multi-GPU path.
+__global__ void k2_gather_cand(const uint32_t *__restrict__ cand_idx, long long nc, const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
+                               const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, const int32_t *__restrict__ mtid, const int32_t *__restrict__ mpos,
+                               const uint64_t *__restrict__ nh, unsigned long long index_offset, bkid_cand *__restrict__ out)
 {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < nc) { uint32_t i = cand_idx[p]; keys[p] = nh[2 * (size_t)i]; vals[p] = i; }
+  if (p >= nc) return;
+  uint32_t i = cand_idx[p];
+  bkid_cand c;
+  c.name_lo = nh[2 * (size_t)i]; c.name_hi = nh[2 * (size_t)i + 1];
+  c.tid = tid[i]; c.pos = pos[i]; c.mtid = mtid[i]; c.mpos = mpos[i];
+  c.gidx = index_offset + i;
+  c.flag = flag[i]; c.mapq = mapq[i];
+  c._pad[0] = c._pad[1] = c._pad[2] = c._pad[3] = c._pad[4] = 0;
+  out[p] = c;
 }
 
-__global__ void k2_run_heads(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, long long nc, const uint64_t *__restrict__ nh,
+__global__ void k2_cand_keys(const bkid_cand *__restrict__ cand, long long nc, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nc) { keys[p] = cand[p].name_lo; vals[p] = (uint32_t)p; }
+}
+
+__global__ void k2_run_heads(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, long long nc, const bkid_cand *__restrict__ cand,
                              uint32_t *__restrict__ head, int *__restrict__ err)
 {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,7 +441,7 @@ __global__ void k2_run_heads(const uint64_t *__restrict__ keys, const uint32_t *
   unsigned h = 1;
   if (p > 0 && keys[p] == keys[p - 1]) {
     h = 0;
-    if (nh[2 * (size_t)vals[p] + 1] != nh[2 * (size_t)vals[p - 1] + 1]) atomicExch(err, 1);   // 64-bit collision of distinct names
+    if (cand[vals[p]].name_hi != cand[vals[p - 1]].name_hi) atomicExch(err, 1);   // 64-bit collision of distinct names
   }
   head[p] = h;
 }
@@ -433,8 +452,6 @@ __global__ void k2_run_starts(const uint32_t *__restrict__ head, const uint32_t 
   if (p < nc && head[p]) run_start[run_id_excl[p]] = (uint32_t)p;
 }
 
-struct PairKey { unsigned long long key; };
-
 __device__ __forceinline__ uint32_t genome_pos(const uint32_t *__restrict__ cum, int nt, int tid, int pos)
 {
   // src/util_bam.cc:57-68: sum of target_len[0..tid) (uint32 wrap) + pos; tid < 0 adds nothing
@@ -442,24 +459,24 @@ __device__ __forceinline__ uint32_t genome_pos(const uint32_t *__restrict__ cum,
   return p + (uint32_t)pos;
 }
 
+// sort key of a pair: bucket rank (high 24 bits) | global index of the second-seen mate (40 bits)
+constexpr int PAIR_IDX_BITS = 40;
+
 __global__ void k2_emit_pairs(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ head, const uint32_t *__restrict__ run_id_excl,
-                              const uint32_t *__restrict__ run_start, long long nc,
-                              const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ tid,
-                              const int32_t *__restrict__ pos, const int32_t *__restrict__ mtid, const int32_t *__restrict__ mpos,
-                              const uint64_t *__restrict__ nh, const uint32_t *__restrict__ cum, int nt, const int32_t *__restrict__ bucket_rank,
-                              double w, bkid_pair *__restrict__ pairs, unsigned long long *__restrict__ keys, uint32_t *__restrict__ slots,
-                              unsigned long long *__restrict__ counter)
+                              const uint32_t *__restrict__ run_start, long long nc, const bkid_cand *__restrict__ cand,
+                              const uint32_t *__restrict__ cum, int nt, const int32_t *__restrict__ bucket_rank,
+                              double w, bkid_pair *__restrict__ pairs, unsigned long long *__restrict__ counter)
 {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool emit = false;
-  uint32_t i = 0, j = 0;
+  bkid_cand I, J;
   if (p < nc) {
     uint32_t rid = run_id_excl[p] - (head[p] ? 0u : 1u);     // exclusive scan counts heads before p
     uint32_t rank = (uint32_t)p - run_start[rid];
     if (rank & 1u) {
-      i = vals[p]; j = vals[p - 1];
-      int ti = tid[i] < 0 ? -1 : tid[i], tj = tid[j] < 0 ? -1 : tid[j];
-      long long pi = (long long)pos[i] + 1, pj = (long long)pos[j] + 1;
+      I = cand[vals[p]]; J = cand[vals[p - 1]];              // I = current (second seen), J = stored mate
+      int ti = I.tid < 0 ? -1 : I.tid, tj = J.tid < 0 ? -1 : J.tid;
+      long long pi = (long long)I.pos + 1, pj = (long long)J.pos + 1;
       long long dp = pi - pj; if (dp < 0) dp = -dp;
       emit = (ti != tj) || ((double)dp >= w);                 // :1428
     }
@@ -472,29 +489,38 @@ __global__ void k2_emit_pairs(const uint32_t *__restrict__ vals, const uint32_t 
   basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
   if (!emit) return;
   unsigned long long slot = basep + __popc(m & ((1u << lane) - 1u));
-  uint32_t c1 = genome_pos(cum, nt, tid[i], pos[i]);          // :1431 current record's own fields
-  uint32_t c2 = genome_pos(cum, nt, mtid[i], mpos[i]);        // :1432 and its mate FIELDS
+  uint32_t c1 = genome_pos(cum, nt, I.tid, I.pos);            // :1431 current record's own fields
+  uint32_t c2 = genome_pos(cum, nt, I.mtid, I.mpos);          // :1432 and its mate FIELDS
   bkid_pair P;
-  P.name_lo = nh[2 * (size_t)i]; P.name_hi = nh[2 * (size_t)i + 1];
-  int ti = tid[i] < 0 ? -1 : tid[i], tj = tid[j] < 0 ? -1 : tid[j];
-  uint32_t pi = (uint32_t)((long long)pos[i] + 1), pj = (uint32_t)((long long)pos[j] + 1);
+  P.name_lo = I.name_lo; P.name_hi = I.name_hi;
+  int ti = I.tid < 0 ? -1 : I.tid, tj = J.tid < 0 ? -1 : J.tid;
+  uint32_t pi = (uint32_t)((long long)I.pos + 1), pj = (uint32_t)((long long)J.pos + 1);
   if (c1 <= c2) {
-    P.p1_flag = flag[i]; P.p1_tid = ti; P.p1_pos = pi; P.p1_mapq = mapq[i];
-    P.p2_flag = flag[j]; P.p2_tid = tj; P.p2_pos = pj; P.p2_mapq = mapq[j];
+    P.p1_flag = I.flag; P.p1_tid = ti; P.p1_pos = pi; P.p1_mapq = I.mapq;
+    P.p2_flag = J.flag; P.p2_tid = tj; P.p2_pos = pj; P.p2_mapq = J.mapq;
     P.p1_chr_pos = c1; P.p2_chr_pos = c2;
   } else {
-    P.p2_flag = flag[i]; P.p2_tid = ti; P.p2_pos = pi; P.p2_mapq = mapq[i];
-    P.p1_flag = flag[j]; P.p1_tid = tj; P.p1_pos = pj; P.p1_mapq = mapq[j];
+    P.p2_flag = I.flag; P.p2_tid = ti; P.p2_pos = pi; P.p2_mapq = I.mapq;
+    P.p1_flag = J.flag; P.p1_tid = tj; P.p1_pos = pj; P.p1_mapq = J.mapq;
     P.p1_chr_pos = c2; P.p2_chr_pos = c1;
   }
   P.p1_strand = (P.p1_flag & F_REVERSE) ? '-' : '+';
   P.p2_strand = (P.p2_flag & F_REVERSE) ? '-' : '+';
   int a = P.p1_tid + 1, b = P.p2_tid + 1;
-  int br = bucket_rank[a * (nt + 1) + b];
-  P.bucket = br; P.cluster = -1; P.orig = 0; P._pad = 0;
+  P.bucket = bucket_rank[a * (nt + 1) + b];                   // rank of "chrA_chrB" among all possible names
+  P.cluster = -1;
+  P.orig = (uint32_t)(I.gidx & 0xffffffffull);                // order of the second-seen mate (40 bits: orig | _pad << 32)
+  P._pad = (uint32_t)((I.gidx >> 32) & 0xffull);
   pairs[slot] = P;
-  keys[slot] = ((unsigned long long)(unsigned)br << 32) | (unsigned long long)i;   // bucket order, then order of the second-seen mate
-  slots[slot] = (uint32_t)slot;
+}
+
+__global__ void k2_pair_keys(const bkid_pair *__restrict__ pairs, long long np, unsigned long long *__restrict__ keys, uint32_t *__restrict__ slots)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  const bkid_pair &P = pairs[p];
+  keys[p] = ((unsigned long long)(unsigned)P.bucket << PAIR_IDX_BITS) | ((unsigned long long)P._pad << 32) | (unsigned long long)P.orig;
+  slots[p] = (uint32_t)p;
 }
 
 __global__ void k2_gather_pairs(const bkid_pair *__restrict__ src, const uint32_t *__restrict__ slots, const unsigned long long *__restrict__ keys,
@@ -504,19 +530,20 @@ __global__ void k2_gather_pairs(const bkid_pair *__restrict__ src, const uint32_
   if (p >= np) return;
   bkid_pair P = src[slots[p]];
   P.orig = (uint32_t)p;
+  P._pad = 0;
   dst[p] = P;
-  bucket_head[p] = (p == 0 || (keys[p] >> 32) != (keys[p - 1] >> 32)) ? 1u : 0u;
+  bucket_head[p] = (p == 0 || (keys[p] >> PAIR_IDX_BITS) != (keys[p - 1] >> PAIR_IDX_BITS)) ? 1u : 0u;
 }
 
 // dense bucket ids + bucket offsets
 __global__ void k2_bucket_ids(bkid_pair *__restrict__ pairs, const uint32_t *__restrict__ head, const uint32_t *__restrict__ head_excl, long long np,
-                              uint32_t *__restrict__ bucket_off)
+                              uint32_t *__restrict__ bucket_off, int32_t *__restrict__ bucket_rank_of)
 {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= np) return;
   uint32_t b = head_excl[p] - (head[p] ? 0u : 1u);
+  if (head[p]) { bucket_off[b] = (uint32_t)p; bucket_rank_of[b] = pairs[p].bucket; }
   pairs[p].bucket = (int32_t)b;
-  if (head[p]) bucket_off[b] = (uint32_t)p;
 }
 
 // =============================================================================================

@@ -146,18 +146,21 @@ __device__ __host__ inline uint64_t chr_code(const uint8_t *s, uint32_t len)
   return h | (1ull << 63);
 }
 
-struct EvRow {
+struct EvRow {        // == bkid_sarow (include/breakid_b200.h), 96 bytes
   uint64_t pchr, schr, pcig, scig;
+  uint64_t name_lo, name_hi;
   uint32_t pstart, sstart, pend, send, pbp, sbp;
+  int32_t tid, pos, endpos;      // the SA-tagged record itself (region membership test)
   uint8_t ok;        // complementary cigars (counts as evidence)
   uint8_t fatal;     // the reference would exit(-1) "error cigar" on this record
   uint8_t secondary;
-  uint8_t _pad[5];
+  uint8_t _pad;
 };
+static_assert(sizeof(EvRow) == 88 || sizeof(EvRow) == 96, "EvRow layout");
 
 // K7a: one thread per SA-tagged record -- src/BreakID.cc:896-1016
 __global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long n_sa, const uint16_t *__restrict__ flag, const int32_t *__restrict__ tid,
-                                 const int32_t *__restrict__ pos, const uint32_t *__restrict__ cig_off, const uint32_t *__restrict__ cig_ops,
+                                 const int32_t *__restrict__ pos, const int32_t *__restrict__ endpos, const uint64_t *__restrict__ nh, const uint32_t *__restrict__ cig_off, const uint32_t *__restrict__ cig_ops,
                                  const uint32_t *__restrict__ sa_off, const uint8_t *__restrict__ sa_txt, const uint32_t *__restrict__ oc_off,
                                  const uint8_t *__restrict__ oc_txt, int mismatch, EvRow *__restrict__ rows)
 {
@@ -167,6 +170,8 @@ __global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long 
   memset(&R, 0, sizeof R);
   uint32_t i = sa_rec[k];
   unsigned fl = flag[i];
+  R.tid = tid[i]; R.pos = pos[i]; R.endpos = endpos[i];
+  R.name_lo = nh[2 * (size_t)i]; R.name_hi = nh[2 * (size_t)i + 1];
   const uint8_t *sa = sa_txt + sa_off[k]; uint32_t sal = sa_off[k + 1] - sa_off[k];
   const uint8_t *oc = oc_txt + oc_off[k]; uint32_t ocl = oc_off[k + 1] - oc_off[k];
   // split_string(sa, ",") drops empty fields (src/util_bed.cc:194-222): fields 0,1,3 of the first entry
@@ -251,19 +256,32 @@ __device__ __forceinline__ long long u32_lower_bound(const uint32_t *__restrict_
 }
 
 struct RegionQ {        // one side of one cluster
-  int tid; int beg, end;            // iterator bounds after clamping (beg >= 0)
-  long long r_lo, r_hi;             // record window [r_lo, r_hi): pos in [beg - maxspan, end)
-  long long s_lo, s_hi;             // SA-slot window
+  int tid; int beg, end;            // iterator bounds after clamping (beg >= 0); end < beg -> empty
+  long long s_lo, s_hi;             // SA-row window: rows with (tid, pos in [beg - maxspan, end))
 };
 
 struct RefineView {
-  long long n; const uint16_t *flag; const uint8_t *cls; const int32_t *tid, *pos, *endpos; const uint64_t *nh;
-  long long n_sa; const uint32_t *sa_rec; const EvRow *rows;
+  // local record shard (coverage / depth partial counts)
+  long long n; const uint8_t *cls; const int32_t *tid, *pos, *endpos;
+  // global SA-row table in coordinate order (evidence)
+  long long n_sa; const EvRow *rows;
   int maxspan;
   const uint64_t *canon;            // [nt] chr_code of the header names
   int nt;
   const uint8_t *const *nib; const uint64_t *nib_len;   // per tid, may be null
 };
+
+__device__ __forceinline__ long long row_lower_bound(const EvRow *__restrict__ rows, long long n, int qt, long long qp)
+{
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    long long m = (lo + hi) >> 1;
+    uint32_t tm = (uint32_t)rows[m].tid;
+    bool less = tm < (uint32_t)qt || (tm == (uint32_t)qt && (long long)rows[m].pos < qp);
+    if (less) lo = m + 1; else hi = m;
+  }
+  return lo;
+}
 
 __device__ __forceinline__ void make_region(const RefineView &v, int tid, uint32_t start_u, uint32_t end_u, RegionQ &q)
 {
@@ -271,15 +289,11 @@ __device__ __forceinline__ void make_region(const RefineView &v, int tid, uint32
   int beg = (int)start_u, end = (int)end_u;
   if (beg < 0) beg = 0;                                       // hts.c:1776
   q.beg = beg; q.end = end;
-  if (end < beg || tid < 0) { q.r_lo = q.r_hi = 0; q.s_lo = q.s_hi = 0; return; }
-  q.r_lo = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)beg - v.maxspan);
-  q.r_hi = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)end);
-  q.s_lo = u32_lower_bound(v.sa_rec, v.n_sa, q.r_lo);
-  q.s_hi = u32_lower_bound(v.sa_rec, v.n_sa, q.r_hi);
+  if (end < beg || tid < 0) { q.end = beg - 1; q.s_lo = q.s_hi = 0; return; }
+  q.s_lo = row_lower_bound(v.rows, v.n_sa, tid, (long long)beg - v.maxspan);
+  q.s_hi = row_lower_bound(v.rows, v.n_sa, tid, (long long)end);
 }
 
-// K7b: per cluster, both regions: coverage, evidence list (SA slots), gate.  One CTA per cluster.
-// ev_list has room for (s_hi-s_lo) of side 1 then side 2 at ev_off[c].
 struct ClusterWork {
   RegionQ q1, q2;
   uint32_t n_ev1, n_ev2;     // evidence rows that survive the gate (0 when the side is empty)
@@ -303,29 +317,44 @@ __global__ void k7_regions(RefineView v, const bkid_cluster_rec *__restrict__ cl
 
 constexpr int RF_THREADS = 128;
 
-// counts coverage + collects evidence for one region (CTA-cooperative); returns via shared counters
-__device__ void region_collect(const RefineView &v, const RegionQ &q, uint32_t *__restrict__ list, unsigned *sh_cov, unsigned *sh_ev, unsigned *sh_fatal)
+// number of LOCAL records the index iterator would return for [beg,end) on tid (every record counts,
+// src/BreakID.cc:894); warp-cooperative, result valid in lane 0 after the reduction
+__device__ unsigned count_overlaps(const RefineView &v, int tid, int beg, int end, bool depth_only)
 {
-  if (threadIdx.x == 0) { *sh_cov = 0; *sh_ev = 0; }
-  __syncthreads();
-  unsigned cov = 0;
-  for (long long i = q.r_lo + threadIdx.x; i < q.r_hi; i += blockDim.x)
-    if (v.endpos[i] > q.beg) ++cov;                          // every record counts (src/BreakID.cc:894)
-  cov = bk::warp_sum(cov);
-  if ((threadIdx.x & 31) == 0 && cov) atomicAdd(sh_cov, cov);
-  // evidence rows in record order (ordered compaction so the list order is deterministic)
+  if (end < beg || tid < 0 || v.n == 0) return 0;
+  long long lo = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)beg - v.maxspan);
+  long long hi = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)end);
+  unsigned c = 0;
+  for (long long i = lo + (threadIdx.x & 31); i < hi; i += 32)
+    if (v.endpos[i] > beg && (!depth_only || (v.cls[i] & CL_DEPTH))) ++c;
+  return bk::warp_sum(c);
+}
+
+// partial coverage of both regions of every cluster on the local record shard: one warp per cluster
+__global__ void __launch_bounds__(128) k7_coverage(RefineView v, const ClusterWork *__restrict__ work, uint32_t ncl, uint32_t *__restrict__ cov /* [2*ncl] */)
+{
+  uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= ncl) return;
+  unsigned a = count_overlaps(v, work[c].q1.tid, work[c].q1.beg, work[c].q1.end, false);
+  unsigned b = count_overlaps(v, work[c].q2.tid, work[c].q2.beg, work[c].q2.end, false);
+  if ((threadIdx.x & 31) == 0) { cov[2 * c] = a; cov[2 * c + 1] = b; }
+}
+
+// evidence rows of one region in record order (CTA-cooperative ordered compaction)
+__device__ void region_collect(const RefineView &v, const RegionQ &q, uint32_t *__restrict__ list, unsigned *sh_ev, unsigned *sh_fatal)
+{
   __shared__ unsigned sh32[33];
   unsigned base = 0;
   for (long long s0 = q.s_lo; s0 < q.s_hi; s0 += blockDim.x) {
     long long s = s0 + threadIdx.x;
     unsigned is = 0;
     if (s < q.s_hi) {
-      uint32_t i = v.sa_rec[s];
-      if (v.endpos[i] > q.beg && v.rows[s].ok) { is = 1; if (v.rows[s].fatal) atomicExch(sh_fatal, 1u); }
+      const EvRow &r = v.rows[s];
+      if (r.endpos > q.beg && r.ok) { is = 1; if (r.fatal) atomicExch(sh_fatal, 1u); }
     }
     unsigned tot;
-    unsigned r = bk::block_excl_scan<unsigned>(is, sh32, tot);
-    if (is) list[base + r] = (uint32_t)s;
+    unsigned rr = bk::block_excl_scan<unsigned>(is, sh32, tot);
+    if (is) list[base + rr] = (uint32_t)s;
     base += tot;
   }
   if (threadIdx.x == 0) *sh_ev = base;
@@ -335,21 +364,20 @@ __device__ void region_collect(const RefineView &v, const RegionQ &q, uint32_t *
 __device__ __forceinline__ bool ev_match(const RefineView &v, uint32_t sa, uint32_t sb)
 {
   const EvRow &a = v.rows[sa], &b = v.rows[sb];
-  uint32_t ia = v.sa_rec[sa], ib = v.sa_rec[sb];
-  return v.nh[2 * (size_t)ia] == v.nh[2 * (size_t)ib] && v.nh[2 * (size_t)ia + 1] == v.nh[2 * (size_t)ib + 1] &&
+  return a.name_lo == b.name_lo && a.name_hi == b.name_hi &&
          a.secondary != b.secondary && a.pchr == b.pchr && a.schr == b.schr && a.pstart == b.pstart && a.sstart == b.sstart &&
          a.pend == b.pend && a.send == b.send && a.pcig == b.pcig && a.scig == b.scig && a.pbp == b.pbp && a.sbp == b.sbp;   // new_condition :627-637
 }
 
-// pass 1 (count) / pass 2 (write) of find_sa_reads x2 + the pairing half of find_bp_pair
+// pass 1 (count) / pass 2 (write) of find_sa_reads x2 + the pairing half of find_bp_pair; cov = TOTAL coverage
 template <bool WRITE>
 __global__ void __launch_bounds__(RF_THREADS)
-k7_collect(RefineView v, const bkid_cluster_rec *__restrict__ cl, uint32_t ncl, ClusterWork *__restrict__ work, const uint32_t *__restrict__ ev_off,
-           uint32_t *__restrict__ ev_list, const uint32_t *__restrict__ ent_off, int2 *__restrict__ entries)
+k7_collect(RefineView v, const bkid_cluster_rec *__restrict__ cl, uint32_t ncl, ClusterWork *__restrict__ work, const uint32_t *__restrict__ cov,
+           const uint32_t *__restrict__ ev_off, uint32_t *__restrict__ ev_list, const uint32_t *__restrict__ ent_off, int2 *__restrict__ entries)
 {
   uint32_t c = blockIdx.x;
   if (c >= ncl) return;
-  __shared__ unsigned sh_cov, sh_ev, sh_fatal, sh_cnt;
+  __shared__ unsigned sh_ev, sh_fatal, sh_cnt;
   ClusterWork &W = work[c];
   uint32_t *l1 = ev_list + ev_off[c];
   uint32_t *l2 = l1 + (uint32_t)(W.q1.s_hi - W.q1.s_lo);
@@ -357,13 +385,13 @@ k7_collect(RefineView v, const bkid_cluster_rec *__restrict__ cl, uint32_t ncl, 
   if (!WRITE) {
     if (threadIdx.x == 0) sh_fatal = 0;
     __syncthreads();
-    region_collect(v, W.q1, l1, &sh_cov, &sh_ev, &sh_fatal);
-    n1 = (sh_cov < 5 || sh_ev < 2) ? 0 : sh_ev;              // gate :1032-1035
+    region_collect(v, W.q1, l1, &sh_ev, &sh_fatal);
+    n1 = (cov[2 * c] < 5 || sh_ev < 2) ? 0 : sh_ev;          // gate :1032-1035
     __syncthreads();
     n2 = 0;
     if (n1 > 0) {                                            // side 2 only if side 1 has reads (:438-439)
-      region_collect(v, W.q2, l2, &sh_cov, &sh_ev, &sh_fatal);
-      n2 = (sh_cov < 5 || sh_ev < 2) ? 0 : sh_ev;
+      region_collect(v, W.q2, l2, &sh_ev, &sh_fatal);
+      n2 = (cov[2 * c + 1] < 5 || sh_ev < 2) ? 0 : sh_ev;
     }
     __syncthreads();
     if (threadIdx.x == 0) { W.n_ev1 = n1; W.n_ev2 = n2; W.fatal = sh_fatal; }
@@ -424,20 +452,6 @@ __device__ __forceinline__ bool key_less(int x1, int y1, int x2, int y2)
   return na < nb;
 }
 
-__device__ unsigned depth_at(const RefineView &v, int tid, unsigned long long pos1)
-{
-  // src/util_bed.cc:154-192: iterator over [pos-1, pos); count qual>0 && !DUP && PAIRED (class bit CL_DEPTH)
-  int beg = (int)(pos1 - 1), end = (int)pos1;
-  if (beg < 0) beg = 0;
-  if (end < beg || tid < 0) return 0;
-  long long lo = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)beg - v.maxspan);
-  long long hi = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)end);
-  unsigned d = 0;
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x)
-    if (v.endpos[i] > beg && (v.cls[i] & CL_DEPTH)) ++d;
-  return d;
-}
-
 __device__ __forceinline__ char nib_base(const uint8_t *packed, uint64_t nbases, long long pos, char prev)
 {
   if (pos < 0 || (uint64_t)pos >= nbases) return prev;                  // src/nibtools.cc:45-46 leaves the byte untouched
@@ -446,20 +460,15 @@ __device__ __forceinline__ char nib_base(const uint8_t *packed, uint64_t nbases,
   switch (x) { case 0: case 8: return 'T'; case 1: case 9: return 'C'; case 2: case 10: return 'A'; case 3: case 11: return 'G'; default: return 'N'; }
 }
 
-// K8 + K9 + K10: vote, depth, AF, 41-mers.  One CTA per cluster.
+// K8: vote.  One CTA per cluster; writes exact positions / votes and valid[c].
 __global__ void __launch_bounds__(RF_THREADS)
-k8_vote(RefineView v, bkid_cluster_rec *__restrict__ cl, uint32_t ncl, const ClusterWork *__restrict__ work, const uint32_t *__restrict__ ent_off,
+k8_vote(bkid_cluster_rec *__restrict__ cl, uint32_t ncl, const ClusterWork *__restrict__ work, const uint32_t *__restrict__ ent_off,
         const int2 *__restrict__ entries, int bp_err, uint32_t *__restrict__ valid)
 {
   uint32_t c = blockIdx.x;
   if (c >= ncl) return;
-  __shared__ int sh_best, sh_x, sh_y;
-  __shared__ unsigned sh_d1, sh_d2;
-  __shared__ char sh_seq[2][44];
   uint32_t m = work[c].n_entries;
   const int2 *E = entries + ent_off[c];
-  if (threadIdx.x == 0) { sh_best = 0; sh_x = -1; sh_y = -1; sh_d1 = 0; sh_d2 = 0; }
-  __syncthreads();
   // votes: entries within +-bp_err of each key, mixed int32/uint32 compares (:820-821)
   int my_best = 0, mx = -1, my = -1;
   for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
@@ -483,48 +492,56 @@ k8_vote(RefineView v, bkid_cluster_rec *__restrict__ cl, uint32_t ncl, const Clu
     int b = 0, x = -1, y = -1;
     for (int q = 0; q < RF_THREADS / 32; ++q)
       if (wb[q] > b || (wb[q] == b && b > 0 && key_less(wx[q], wy[q], x, y))) { b = wb[q]; x = wx[q]; y = wy[q]; }
-    sh_best = b; sh_x = x; sh_y = y;
+    bool ok = b >= 2;                                                     // :446
+    valid[c] = ok ? 1u : 0u;
+    if (ok) { cl[c].p1_exact_pos = (uint32_t)x; cl[c].p2_exact_pos = y; cl[c].n_split_read = b; }
   }
-  __syncthreads();
-  int votes = sh_best;
-  bool ok = votes >= 2;                                                   // :446
-  if (threadIdx.x == 0) valid[c] = ok ? 1u : 0u;
-  if (!ok) return;
+}
+
+// K9 partial: depth at both break points of every valid cluster on the local record shard
+// (src/util_bed.cc:154-192: iterator over [pos-1, pos); qual>0 && !DUP && PAIRED = class bit CL_DEPTH)
+__global__ void __launch_bounds__(128) k9_depth(RefineView v, const bkid_cluster_rec *__restrict__ cl, const uint32_t *__restrict__ valid, uint32_t ncl, uint32_t *__restrict__ depth)
+{
+  uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= ncl) return;
+  unsigned a = 0, b = 0;
+  if (valid[c]) {
+    unsigned long long p1 = (unsigned long long)cl[c].p1_exact_pos, p2 = (unsigned long long)(long long)cl[c].p2_exact_pos;
+    int b1 = (int)(p1 - 1), e1 = (int)p1, b2 = (int)(p2 - 1), e2 = (int)p2;
+    if (b1 < 0) b1 = 0;
+    if (b2 < 0) b2 = 0;
+    a = count_overlaps(v, cl[c].p1_tid, b1, e1, true);
+    b = count_overlaps(v, cl[c].p2_tid, b2, e2, true);
+  }
+  if ((threadIdx.x & 31) == 0) { depth[2 * c] = a; depth[2 * c + 1] = b; }
+}
+
+// K9/K10 finish: depth (TOTAL over shards), AF, 41-mers, homopolymer flag; one thread per cluster
+__global__ void k10_finish(RefineView v, bkid_cluster_rec *__restrict__ cl, const uint32_t *__restrict__ valid, const uint32_t *__restrict__ depth, uint32_t ncl)
+{
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncl || !valid[c]) return;
   bkid_cluster_rec &R = cl[c];
-  uint32_t p1e = (uint32_t)sh_x; int32_t p2e = sh_y;
-  unsigned d1 = depth_at(v, R.p1_tid, (unsigned long long)p1e);
-  unsigned d2 = depth_at(v, R.p2_tid, (unsigned long long)(long long)p2e);
-  d1 = bk::warp_sum(d1); d2 = bk::warp_sum(d2);
-  if ((threadIdx.x & 31) == 0) { if (d1) atomicAdd(&sh_d1, d1); if (d2) atomicAdd(&sh_d2, d2); }
-  // K10: 41-mer = 1-based [bp-20, bp+20] (src/BreakID.cc:554-557, src/util_bam.cc:78-122); sequential
-  // because an out-of-range base repeats the previous one
-  if (threadIdx.x < 2) {
-    int side = threadIdx.x;
+  R.p1_bp_depth = (double)depth[2 * c]; R.p2_bp_depth = (double)depth[2 * c + 1];
+  R.p1_alle_freq = __fdiv_rn((float)(long long)R.n_split_read, (float)R.p1_bp_depth);   // :475-478
+  R.p2_alle_freq = __fdiv_rn((float)(long long)R.n_split_read, (float)R.p2_bp_depth);
+  int rpt = 0;
+  for (int side = 0; side < 2; ++side) {
+    // 41-mer = 1-based [bp-20, bp+20] (src/BreakID.cc:554-557, src/util_bam.cc:78-122); sequential because an
+    // out-of-range base repeats the previous one
     int t = side ? R.p2_tid : R.p1_tid;
-    long long bp = side ? (long long)p2e : (long long)(int32_t)p1e;
-    char *out = sh_seq[side];
+    long long bp = side ? (long long)R.p2_exact_pos : (long long)(int32_t)R.p1_exact_pos;
+    char *out = side ? R.p2_rpt : R.p1_rpt;
     for (int k = 0; k < 44; ++k) out[k] = 0;
     if (v.nib && t >= 0 && t < v.nt && v.nib[t]) {
       char prev = 'N';
       for (int k = 0; k < 41; ++k) { prev = nib_base(v.nib[t], v.nib_len[t], bp - 21 + k, prev); out[k] = prev; }
     }
+    int best = 0;
+    for (int i = 0; out[i];) { int j = i; while (out[j] == out[i]) ++j; if (j - i > best) best = j - i; i = j; }
+    if (best > 10) rpt = 1;                                                               // src/BreakID.cc:560-561
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    R.p1_exact_pos = p1e; R.p2_exact_pos = p2e; R.n_split_read = votes;
-    R.p1_bp_depth = (double)sh_d1; R.p2_bp_depth = (double)sh_d2;
-    R.p1_alle_freq = __fdiv_rn((float)(long long)votes, (float)R.p1_bp_depth);   // :475-478
-    R.p2_alle_freq = __fdiv_rn((float)(long long)votes, (float)R.p2_bp_depth);
-    int rpt = 0;
-    for (int side = 0; side < 2; ++side) {
-      const char *s = sh_seq[side];
-      int best = 0;
-      for (int i = 0; s[i];) { int j = i; while (s[j] == s[i]) ++j; if (j - i > best) best = j - i; i = j; }
-      if (best > 10) rpt = 1;                                                     // src/BreakID.cc:560-561
-      for (int k = 0; k < 44; ++k) (side ? R.p2_rpt : R.p1_rpt)[k] = s[k];
-    }
-    R.is_rpt = rpt;
-  }
+  R.is_rpt = rpt;
 }
 
 __global__ void max_span_kernel(const int32_t *__restrict__ pos, const int32_t *__restrict__ endpos, long long n, int *__restrict__ out)

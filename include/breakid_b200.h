@@ -96,6 +96,17 @@ typedef struct {
   uint32_t _pad;
 } bkid_pair;
 
+/* One discordant-scan candidate record (passes src/BreakID.cc:1419-1420), the unit the mate join works on and
+ * the unit ranks exchange in the multi-GPU path.  gidx = position in the global coordinate-sorted stream. */
+typedef struct {
+  uint64_t name_lo, name_hi;
+  int32_t tid, pos, mtid, mpos;
+  uint64_t gidx;
+  uint16_t flag;
+  uint8_t mapq;
+  uint8_t _pad[5];
+} bkid_cand;
+
 /* One called cluster (reference struct cluster_info, src/BreakID.h:60-113), numeric part.  The
  * host driver adds gene annotation (src/BreakID.cc:492-567) and writes the call file. */
 typedef struct {
@@ -173,6 +184,30 @@ int bkid_fetch_clusters(bkid_ctx *ctx, bkid_cluster_rec *out, int64_t cap, int64
 int bkid_fetch_pairs(bkid_ctx *ctx, int stage, bkid_pair *out, int64_t cap, int64_t *n);
 int bkid_fetch_class(bkid_ctx *ctx, uint8_t *out, int64_t cap);   /* per-record class mask of the classify kernel */
 int bkid_get_timings(bkid_ctx *ctx, bkid_timings *t);
+
+/* ---- multi-GPU shard entry points -----------------------------------------------------------------
+ * One context per rank holds a contiguous slice of the coordinate-sorted record stream (genomic bins).
+ * The caller (breakid_b200/dist.py over torch.distributed / NCCL) performs the exchanges named in
+ * SURVEY.md 8(e) between these calls; every handed-out pointer is a DEVICE pointer owned by the context
+ * and valid until the next call.  Single-GPU bkid_scan / bkid_refine are compositions of the same pieces. */
+typedef struct { uint64_t q[11]; } bkid_sarow;        /* opaque 88-byte split-read evidence row (self-contained) */
+int bkid_shard_insert_partial(bkid_ctx *ctx, int64_t *sum_abs, int64_t *count);                 /* -> all-reduce (sum) */
+int bkid_shard_sd_partial(bkid_ctx *ctx, double mean, int64_t t_in, int64_t *t_out);             /* chained rank to rank */
+int bkid_shard_set_stats(bkid_ctx *ctx, double mean, double sd);
+int bkid_shard_candidates(bkid_ctx *ctx, uint64_t index_offset, const bkid_cand **dev, int64_t *n);   /* -> all-to-all by name hash */
+int bkid_shard_join(bkid_ctx *ctx, const bkid_cand *dev_cand, int64_t n, double w, const bkid_pair **dev_pairs, int64_t *n_pairs);  /* -> all-to-all by bucket owner */
+int bkid_shard_set_pairs(bkid_ctx *ctx, const bkid_pair *dev_pairs, int64_t n);                  /* then bkid_cluster() on the owned buckets */
+int bkid_shard_clusters(bkid_ctx *ctx, const bkid_cluster_rec **dev, int64_t *n);                /* bucket = GLOBAL name rank -> all-gather */
+int bkid_shard_set_clusters(bkid_ctx *ctx, const bkid_cluster_rec *dev, int64_t n);              /* all clusters in global order */
+int bkid_shard_sa_rows(bkid_ctx *ctx, const bkid_sarow **dev, int64_t *n);                       /* -> all-gather (coordinate order = rank order) */
+int bkid_shard_set_sa_rows(bkid_ctx *ctx, const bkid_sarow *dev, int64_t n);
+int bkid_shard_maxspan(bkid_ctx *ctx, int32_t *maxspan);                                         /* -> all-reduce (max) */
+int bkid_shard_set_maxspan(bkid_ctx *ctx, int32_t maxspan);
+int bkid_shard_coverage(bkid_ctx *ctx, double dist, uint32_t **dev_cov, int64_t *n);             /* partial counts -> all-reduce (sum) in place */
+int bkid_shard_vote(bkid_ctx *ctx);
+int bkid_shard_depth(bkid_ctx *ctx, uint32_t **dev_depth, int64_t *n);                           /* partial counts -> all-reduce (sum) in place */
+int bkid_shard_finish(bkid_ctx *ctx, int64_t *n_called);
+int bkid_fetch_bucket_ranks(bkid_ctx *ctx, int32_t *out, int64_t cap, int64_t *nb);
 
 /* Stand-alone operator entry points (device work on caller host arrays) used by the parity tests:
  * util_cluster / std::sort replay / isolated-pair mask on one bucket. */
