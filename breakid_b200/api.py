@@ -195,7 +195,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_insert_partial", "bkid_shard_sd_partial", "bkid_shard_set_stats", "bkid_shard_candidates", "bkid_shard_join",
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
-           "bkid_shard_finish", "bkid_fetch_bucket_ranks"]
+           "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -252,6 +252,7 @@ def cuda_lib():
         L.bkid_shard_depth.argtypes = [vp, pvp, i64p]
         L.bkid_shard_finish.argtypes = [vp, i64p]
         L.bkid_fetch_bucket_ranks.argtypes = [vp, vp, C.c_int64, i64p]
+        L.bkid_device_copy.argtypes = [vp, vp, vp, C.c_uint64]
         _cuda = L
     return _cuda
 

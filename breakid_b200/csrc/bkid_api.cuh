@@ -1252,6 +1252,14 @@ int bkid_shard_finish(bkid_ctx *c, int64_t *n_called)
   return 0;
 }
 
+int bkid_device_copy(bkid_ctx *c, void *dst, const void *src, uint64_t bytes)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (bytes) CU(c, cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault));
+  return 0;
+}
+
 int bkid_fetch_bucket_ranks(bkid_ctx *c, int32_t *out, int64_t cap, int64_t *nb)
 {
   if (!c || !c->scanned) return c ? fail(c, BKID_ERR_ARG, "bkid_fetch_bucket_ranks before scan") : BKID_ERR_ARG;

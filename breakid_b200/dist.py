@@ -1,0 +1,283 @@
+"""Multi-GPU orchestration of the hot path: one process per GPU, torch.distributed for
+the plumbing (NCCL over NVLink on GPUs; gloo on CPU for the host-logic tests).
+
+Sharding: every rank holds a contiguous slice of the coordinate-sorted record stream (genomic bins).
+
+  stage                         exchange
+  ---------------------------   ----------------------------------------------------------------
+  classify + insert sum/count   all-reduce (sum)                                  [C2]
+  truncating sd accumulator     chained rank to rank (one int64)                   (order dependent)
+  candidate records             all-to-all by name-hash owner                      [C1]  (mates meet)
+  discordant pairs              all-to-all by bucket owner (chr-pair bucket rank)  [C1']
+  mask + clustering + summary   none (buckets are independent, src/BreakID.cc:119-167)
+  cluster summaries             all-gather (small)
+  split-read evidence rows      all-gather (small, stays in coordinate order)      [C3]
+  region coverage / bp depth    partial counts per shard, all-reduce (sum)
+  vote / AF / 41-mers           replicated (tiny)
+
+The per-rank compute is an *engine*: ``GpuEngine`` (the CUDA library through the bkid_shard_* C ABI) or,
+in tests only, an engine built on the CPU oracle.  Everything here is backend agnostic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import api
+
+CAND_B, PAIR_B, CLUSTER_B, SAROW_B = 48, 64, 192, 88
+
+
+class GpuEngine:
+    """per-rank compute on one B200 through the shard entry points of the C ABI"""
+
+    def __init__(self, ctx: api.Context, device: torch.device):
+        self.ctx, self.lib, self.device = ctx, ctx.lib, device
+        self._keep = {}
+
+    def _chk(self, rc):
+        self.ctx._chk(rc)
+
+    def _take(self, ptr, nbytes, row):
+        t = torch.empty((nbytes // row, row) if row else (nbytes,), dtype=torch.uint8, device=self.device)
+        if nbytes:
+            self._chk(self.lib.bkid_device_copy(self.ctx.ctx, t.data_ptr(), ptr, nbytes))
+        return t
+
+    def insert_partial(self):
+        s, n = C.c_int64(), C.c_int64()
+        self._chk(self.lib.bkid_shard_insert_partial(self.ctx.ctx, C.byref(s), C.byref(n)))
+        return s.value, n.value
+
+    def sd_partial(self, mean, t_in):
+        t = C.c_int64()
+        self._chk(self.lib.bkid_shard_sd_partial(self.ctx.ctx, mean, t_in, C.byref(t)))
+        return t.value
+
+    def set_stats(self, mean, sd):
+        self._chk(self.lib.bkid_shard_set_stats(self.ctx.ctx, mean, sd))
+
+    def candidates(self, index_offset):
+        p, n = C.c_void_p(), C.c_int64()
+        self._chk(self.lib.bkid_shard_candidates(self.ctx.ctx, index_offset, C.byref(p), C.byref(n)))
+        return self._take(p, n.value * CAND_B, CAND_B)
+
+    def join(self, cands, w):
+        cands = cands.contiguous()
+        p, n = C.c_void_p(), C.c_int64()
+        self._chk(self.lib.bkid_shard_join(self.ctx.ctx, cands.data_ptr(), cands.shape[0], w, C.byref(p), C.byref(n)))
+        return self._take(p, n.value * PAIR_B, PAIR_B)
+
+    def set_pairs(self, pairs):
+        pairs = pairs.contiguous()
+        self._chk(self.lib.bkid_shard_set_pairs(self.ctx.ctx, pairs.data_ptr(), pairs.shape[0]))
+
+    def cluster(self, d, mode):
+        return self.ctx.cluster(d, mode)
+
+    def clusters(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._chk(self.lib.bkid_shard_clusters(self.ctx.ctx, C.byref(p), C.byref(n)))
+        return self._take(p, n.value * CLUSTER_B, CLUSTER_B)
+
+    def set_clusters(self, t):
+        t = t.contiguous()
+        self._chk(self.lib.bkid_shard_set_clusters(self.ctx.ctx, t.data_ptr(), t.shape[0]))
+
+    def sa_rows(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._chk(self.lib.bkid_shard_sa_rows(self.ctx.ctx, C.byref(p), C.byref(n)))
+        return self._take(p, n.value * SAROW_B, SAROW_B)
+
+    def set_sa_rows(self, t):
+        self._keep["rows"] = t.contiguous()
+        self._chk(self.lib.bkid_shard_set_sa_rows(self.ctx.ctx, self._keep["rows"].data_ptr(), t.shape[0]))
+
+    def maxspan(self):
+        m = C.c_int32()
+        self._chk(self.lib.bkid_shard_maxspan(self.ctx.ctx, C.byref(m)))
+        return m.value
+
+    def set_maxspan(self, m):
+        self._chk(self.lib.bkid_shard_set_maxspan(self.ctx.ctx, m))
+
+    def _counts(self, fn, *a):
+        p, n = C.c_void_p(), C.c_int64()
+        self._chk(fn(self.ctx.ctx, *a, C.byref(p), C.byref(n)))
+        t = torch.empty(n.value, dtype=torch.int32, device=self.device)
+        if n.value:
+            self._chk(self.lib.bkid_device_copy(self.ctx.ctx, t.data_ptr(), p, n.value * 4))
+        return t, p
+
+    def coverage(self, d):
+        t, self._cov_ptr = self._counts(self.lib.bkid_shard_coverage, d)
+        return t
+
+    def commit_coverage(self, t):
+        if t.numel():
+            self._chk(self.lib.bkid_device_copy(self.ctx.ctx, self._cov_ptr, t.data_ptr(), t.numel() * 4))
+
+    def vote(self):
+        self._chk(self.lib.bkid_shard_vote(self.ctx.ctx))
+
+    def depth(self):
+        t, self._dep_ptr = self._counts(self.lib.bkid_shard_depth)
+        return t
+
+    def commit_depth(self, t):
+        if t.numel():
+            self._chk(self.lib.bkid_device_copy(self.ctx.ctx, self._dep_ptr, t.data_ptr(), t.numel() * 4))
+
+    def finish(self):
+        n = C.c_int64()
+        self._chk(self.lib.bkid_shard_finish(self.ctx.ctx, C.byref(n)))
+        return self.ctx.fetch_clusters()
+
+    def bucket_ranks(self):
+        nb = C.c_int64()
+        self._chk(self.lib.bkid_fetch_bucket_ranks(self.ctx.ctx, None, 0, C.byref(nb)))
+        out = np.zeros(max(1, nb.value), np.int32)
+        self._chk(self.lib.bkid_fetch_bucket_ranks(self.ctx.ctx, out.ctypes.data, out.shape[0], C.byref(nb)))
+        return torch.from_numpy(out[:nb.value].copy()).to(self.device)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _world():
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def _rank():
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def _all_gather_rows(t: torch.Tensor) -> torch.Tensor:
+    """concatenate variable-length [n_r, row] byte tensors of all ranks in rank order"""
+    W = _world()
+    if W == 1:
+        return t
+    cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    cnts = [torch.zeros_like(cnt) for _ in range(W)]
+    dist.all_gather(cnts, cnt)
+    cnts = [int(c) for c in cnts]
+    mx = max(cnts + [1])
+    pad = torch.zeros((mx, t.shape[1]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(W)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:c] for o, c in zip(out, cnts)], 0)
+
+
+def _all_to_all_rows(t: torch.Tensor, owner: torch.Tensor) -> torch.Tensor:
+    """route row i of t to rank owner[i]; rows arrive grouped by source rank (rank order) and keep their
+    source order inside a group -- i.e. a stream that was globally ordered stays globally ordered"""
+    W = _world()
+    if W == 1:
+        return t
+    order = torch.sort(owner, stable=True).indices
+    send = t[order].contiguous()
+    scount = torch.bincount(owner, minlength=W).to(torch.int64)
+    rcount = torch.empty_like(scount)
+    dist.all_to_all_single(rcount, scount) if dist.get_backend() != "gloo" else _gloo_a2a_counts(rcount, scount)
+    s_list, r_list = [int(x) for x in scount], [int(x) for x in rcount]
+    recv = torch.empty((sum(r_list), t.shape[1]), dtype=t.dtype, device=t.device)
+    if dist.get_backend() == "gloo":
+        _gloo_a2a_rows(recv, send, s_list, r_list)
+    else:
+        dist.all_to_all_single(recv, send, output_split_sizes=r_list, input_split_sizes=s_list)
+    return recv
+
+
+def _gloo_a2a_counts(rcount, scount):
+    W = _world()
+    allc = [torch.zeros_like(scount) for _ in range(W)]
+    dist.all_gather(allc, scount)
+    r = _rank()
+    for src in range(W):
+        rcount[src] = allc[src][r]
+
+
+def _gloo_a2a_rows(recv, send, s_list, r_list):
+    """all-to-all emulated with all-gather (gloo CPU tests only)"""
+    W, r = _world(), _rank()
+    allsend = _all_gather_rows(send)
+    # counts matrix
+    sc = torch.tensor(s_list, dtype=torch.int64)
+    allc = [torch.zeros_like(sc) for _ in range(W)]
+    dist.all_gather(allc, sc)
+    off = 0
+    o = 0
+    for src in range(W):
+        row0 = off + int(allc[src][:r].sum())
+        k = int(allc[src][r])
+        recv[o:o + k] = allsend[row0:row0 + k]
+        o += k
+        off += int(allc[src].sum())
+
+
+def _reduce(t: torch.Tensor, op):
+    if _world() > 1 and t.numel():
+        dist.all_reduce(t, op=op)
+    return t
+
+
+def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: int = 0):
+    """the whole hot path over all ranks; returns (mean, sd, dist, called cluster records [numpy, bucket =
+    dense id]) -- identical on every rank and identical to the single-GPU / reference result"""
+    W, r = _world(), _rank()
+    dev = engine.device
+    # insert statistics: exact integer sum/count, then the order-dependent sd accumulator chained through the ranks
+    s, n = engine.insert_partial()
+    sn = _reduce(torch.tensor([s, n], dtype=torch.int64, device=dev), dist.ReduceOp.SUM)
+    S, N = int(sn[0]), int(sn[1])
+    mean = float(S) / float(N)
+    t = torch.zeros(1, dtype=torch.int64, device=dev)
+    for src in range(W):
+        if r == src:
+            t[0] = engine.sd_partial(mean, int(t[0]))
+        if W > 1:
+            dist.broadcast(t, src=src)
+    sd = math.sqrt(int(t[0]) / float(N))
+    d = times * math.sqrt(times) * (mean + sd_mult * sd)
+    engine.set_stats(mean, sd)
+    # global index of the first local record
+    ns = torch.zeros(W, dtype=torch.int64, device=dev)
+    ns[r] = n_local
+    _reduce(ns, dist.ReduceOp.SUM)
+    offset = int(ns[:r].sum())
+    # candidates meet their mates on the owner of their name hash
+    cands = engine.candidates(offset)
+    lo = cands.view(torch.int64)[:, 0] if cands.shape[0] else torch.zeros(0, dtype=torch.int64, device=dev)
+    owner = ((lo >> 8) & 0x7fffffff) % W
+    cands = _all_to_all_rows(cands, owner)
+    pairs = engine.join(cands, d)
+    # pairs go to the owner of their chr-pair bucket
+    bucket = pairs.view(torch.int32)[:, 12].to(torch.int64) if pairs.shape[0] else torch.zeros(0, dtype=torch.int64, device=dev)
+    pairs = _all_to_all_rows(pairs, bucket % W)
+    engine.set_pairs(pairs)
+    # dense bucket ids of the reference = rank among ALL buckets that hold at least one pair, over all ranks
+    br = engine.bucket_ranks().to(torch.int32).reshape(-1, 1).contiguous().view(torch.uint8)
+    all_ranks = torch.sort(_all_gather_rows(br).view(torch.int32).reshape(-1)).values
+    engine.cluster(d, mode)
+    # every rank gets every cluster summary, in the reference's order (bucket name rank, cluster id)
+    cl = _all_gather_rows(engine.clusters())
+    if cl.shape[0]:
+        v = cl.view(torch.int32)
+        key = (v[:, 0].to(torch.int64) << 32) | v[:, 1].to(torch.int64)
+        cl = cl[torch.sort(key, stable=True).indices].contiguous()
+    engine.set_clusters(cl)
+    engine.set_sa_rows(_all_gather_rows(engine.sa_rows()))
+    ms = _reduce(torch.tensor([engine.maxspan()], dtype=torch.int32, device=dev), dist.ReduceOp.MAX)
+    engine.set_maxspan(int(ms[0]))
+    engine.commit_coverage(_reduce(engine.coverage(d), dist.ReduceOp.SUM))
+    engine.vote()
+    engine.commit_depth(_reduce(engine.depth(), dist.ReduceOp.SUM))
+    out = engine.finish()
+    if len(out):
+        out = out.copy()
+        out["bucket"] = np.searchsorted(all_ranks.cpu().numpy(), out["bucket"]).astype(np.int32)   # name rank -> dense id
+    return mean, sd, d, out

@@ -208,6 +208,8 @@ int bkid_shard_vote(bkid_ctx *ctx);
 int bkid_shard_depth(bkid_ctx *ctx, uint32_t **dev_depth, int64_t *n);                           /* partial counts -> all-reduce (sum) in place */
 int bkid_shard_finish(bkid_ctx *ctx, int64_t *n_called);
 int bkid_fetch_bucket_ranks(bkid_ctx *ctx, int32_t *out, int64_t cap, int64_t *nb);
+/* plain device/host memcpy on the context's device (lets a caller move shard buffers into its own allocations) */
+int bkid_device_copy(bkid_ctx *ctx, void *dst, const void *src, uint64_t bytes);
 
 /* Stand-alone operator entry points (device work on caller host arrays) used by the parity tests:
  * util_cluster / std::sort replay / isolated-pair mask on one bucket. */

@@ -1102,4 +1102,317 @@ long orc_run(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *t
   return (long)result.size();
 }
 
+
+/* ==========================================================================================
+ * Sharded decomposition of the same path (mirrors the bkid_shard_* entry points of the C ABI): the
+ * records are cut into contiguous slices of the coordinate-sorted stream, candidates are exchanged by
+ * name hash, pairs by bucket owner, coverage / depth are partial counts that get summed, and the
+ * split-read evidence table is global.  tests/test_multi_gloo.py runs these pieces in two processes
+ * over gloo and requires the result to equal orc_run on the unsplit input.
+ * ========================================================================================== */
+typedef struct {
+  uint64_t name_lo, name_hi;
+  int32_t tid, pos, mtid, mpos;
+  uint64_t gidx;
+  uint16_t flag;
+  uint8_t mapq;
+  uint8_t _pad[5];
+} orc_cand;
+
+typedef struct {
+  uint64_t pchr, schr, pcig, scig, name_lo, name_hi;
+  uint32_t pstart, sstart, pend, send, pbp, sbp;
+  int32_t tid, pos, endpos;
+  uint8_t ok, fatal, secondary, _pad;
+} orc_sarow;
+
+static uint64_t chr_code_str(const std::string &x)
+{
+  if (x.empty()) return ~0ull;
+  for (int t = 0; t < 24; ++t) if (chrom_id_name(t) == x) return (uint64_t)t;
+  return orc_str_hash(x.c_str()) | (1ull << 63);
+}
+
+long orc_shard_sd_partial(long n, const uint16_t *flag, const int32_t *isize, double mean, long t_in)
+{
+  const uint32_t filter = F_UNMAP | F_SECONDARY | F_QCFAIL | F_DUP;
+  long t = t_in;
+  for (long i = 0; i < n; ++i)
+    if ((flag[i] & F_PAIRED) && (flag[i] & F_PROPER) && !(flag[i] & filter)) {
+      double x = (double)abs(isize[i]);
+      t += (x - mean) * (x - mean);
+    }
+  return t;
+}
+
+long orc_shard_candidates(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos, const int32_t *mtid,
+                          const int32_t *mpos, const uint64_t *nh, long qual, uint64_t index_offset, orc_cand **out)
+{
+  std::vector<orc_cand> v;
+  for (long i = 0; i < n; ++i)
+    if ((long)mapq[i] >= qual && !(flag[i] & F_DUP) && !(flag[i] & F_SECONDARY) && (flag[i] & F_PAIRED) && !(flag[i] & F_PROPER)) {
+      orc_cand c; memset(&c, 0, sizeof c);
+      c.name_lo = nh[2 * i]; c.name_hi = nh[2 * i + 1]; c.tid = tid[i]; c.pos = pos[i]; c.mtid = mtid[i]; c.mpos = mpos[i];
+      c.gidx = index_offset + (uint64_t)i; c.flag = flag[i]; c.mapq = mapq[i];
+      v.push_back(c);
+    }
+  orc_cand *o = (orc_cand *)calloc(v.size() ? v.size() : 1, sizeof(orc_cand));
+  for (size_t i = 0; i < v.size(); ++i) o[i] = v[i];
+  *out = o;
+  return (long)v.size();
+}
+
+/* join over candidates given in global file order; pairs carry bucket = rank of "chrA_chrB" among ALL possible
+ * names (rank table as in orc_bucket_rank_table) and the second-seen mate's global index in orig | _pad<<32 */
+long orc_shard_join(long n, const orc_cand *cand, int n_targets, const uint32_t *target_len, const int32_t *rank_table, double w, orc_pair **out)
+{
+  std::unordered_map<H128, long, H128Hash> store;
+  std::vector<orc_pair> emitted;
+  for (long i = 0; i < n; ++i) {
+    H128 h{cand[i].name_lo, cand[i].name_hi};
+    auto it = store.find(h);
+    if (it == store.end()) { store[h] = i; continue; }
+    const orc_cand &I = cand[i], &J = cand[it->second];
+    int ti = I.tid < 0 ? -1 : I.tid, tj = J.tid < 0 ? -1 : J.tid;
+    long pi = (long)I.pos + 1, pj = (long)J.pos + 1;
+    if (ti != tj || (double)labs(pi - pj) >= w) {
+      uint32_t c1 = genome_pos(target_len, I.tid, I.pos), c2 = genome_pos(target_len, I.mtid, I.mpos);
+      orc_pair p; memset(&p, 0, sizeof p);
+      p.name_lo = h.lo; p.name_hi = h.hi;
+      if (c1 <= c2) {
+        p.p1_flag = I.flag; p.p1_tid = ti; p.p1_pos = (uint32_t)pi; p.p1_mapq = I.mapq; p.p1_chr_pos = c1; p.p2_chr_pos = c2;
+        p.p2_flag = J.flag; p.p2_tid = tj; p.p2_pos = (uint32_t)pj; p.p2_mapq = J.mapq;
+      } else {
+        p.p2_flag = I.flag; p.p2_tid = ti; p.p2_pos = (uint32_t)pi; p.p2_mapq = I.mapq; p.p1_chr_pos = c2; p.p2_chr_pos = c1;
+        p.p1_flag = J.flag; p.p1_tid = tj; p.p1_pos = (uint32_t)pj; p.p1_mapq = J.mapq;
+      }
+      p.p1_strand = (p.p1_flag & F_REVERSE) ? '-' : '+';
+      p.p2_strand = (p.p2_flag & F_REVERSE) ? '-' : '+';
+      p.bucket = rank_table[(p.p1_tid + 1) * (n_targets + 1) + (p.p2_tid + 1)];
+      p.cluster = -1;
+      p.orig = (uint32_t)(I.gidx & 0xffffffffull); p._pad = (uint32_t)((I.gidx >> 32) & 0xff);
+      emitted.push_back(p);
+    }
+    store.erase(it);
+  }
+  orc_pair *o = (orc_pair *)calloc(emitted.size() ? emitted.size() : 1, sizeof(orc_pair));
+  for (size_t i = 0; i < emitted.size(); ++i) o[i] = emitted[i];
+  *out = o;
+  return (long)emitted.size();
+}
+
+/* mask + cluster + summary of the buckets present in `pairs` (sorted by (bucket rank, second-mate index)); cluster
+ * records keep bucket = global rank and are not refined yet (exact positions -1) */
+long orc_shard_bucket_clusters(long np, const orc_pair *pairs, double dist, int mode, orc_cluster **out)
+{
+  std::vector<orc_cluster> result;
+  long s = 0;
+  while (s < np) {
+    long e = s;
+    while (e < np && pairs[e].bucket == pairs[s].bucket) ++e;
+    long nb = e - s;
+    std::vector<uint32_t> p1(nb), p2(nb), idx(nb + 2);
+    for (long i = 0; i < nb; ++i) { p1[i] = pairs[s + i].p1_chr_pos; p2[i] = pairs[s + i].p2_chr_pos; }
+    long nm = orc_remove_isolated(nb, p1.data(), p2.data(), dist, idx.data());
+    if (nm >= 2) {
+      std::vector<uint32_t> q1(nm), q2(nm), cidx(nm + 2); std::vector<int32_t> cl(nm + 2);
+      for (long i = 0; i < nm; ++i) { q1[i] = p1[idx[i]]; q2[i] = p2[idx[i]]; }
+      int roots = 0;
+      long nc = mode ? orc_cluster_fast(nm, q1.data(), q2.data(), dist, cidx.data(), cl.data(), &roots)
+                     : orc_cluster_ahc(nm, q1.data(), q2.data(), dist, cidx.data(), cl.data(), &roots);
+      std::map<long, std::vector<long>> members;
+      for (long i = 0; i < nc; ++i) members[cl[i]].push_back(s + idx[cidx[i]]);
+      for (auto &kv : members) {
+        orc_cluster c; memset(&c, 0, sizeof c);
+        const orc_pair &f = pairs[kv.second[0]];
+        c.bucket = f.bucket; c.id = (int32_t)kv.first; c.p1_tid = f.p1_tid; c.p2_tid = f.p2_tid;
+        uint64_t s1 = 0, s2 = 0; uint32_t mn1 = UINT32_MAX, mx1 = 0, mn2 = UINT32_MAX, mx2 = 0;
+        bool t_diff = false, t_rev = false, t_same = false, t_def = false;
+        for (long m : kv.second) {
+          const orc_pair &p = pairs[m];
+          s1 += p.p1_pos; s2 += p.p2_pos;
+          mn1 = std::min(mn1, p.p1_pos); mx1 = std::max(mx1, p.p1_pos); mn2 = std::min(mn2, p.p2_pos); mx2 = std::max(mx2, p.p2_pos);
+          if (p.p1_tid != p.p2_tid) t_diff = true;
+          else {
+            if (p.p1_strand == '-' && p.p2_strand == '+') t_rev = true;
+            if (p.p1_strand == p.p2_strand) t_same = true;
+            if (p.p1_strand == '+' && p.p2_strand == '-') t_def = true;
+          }
+        }
+        c.n_discordant_pair = (int64_t)kv.second.size();
+        c.p1_mean_pos = (uint32_t)((double)s1 / (double)c.n_discordant_pair);
+        c.p2_mean_pos = (uint32_t)((double)s2 / (double)c.n_discordant_pair);
+        c.p1_min_pos = mn1; c.p1_max_pos = mx1; c.p2_min_pos = mn2; c.p2_max_pos = mx2;
+        int64_t md = (int64_t)(c.p1_mean_pos - c.p2_mean_pos);
+        if (c.p1_tid == c.p2_tid && md <= 2 * dist && md >= -2 * dist) continue;
+        c.fusion_type = 0;
+        if (t_diff) c.fusion_type = 1;
+        if (t_same) c.fusion_type = 2;
+        if (t_rev) c.fusion_type = 3;
+        if (t_def) c.fusion_type = 4;
+        c.p1_exact_pos = 0xffffffffu; c.p2_exact_pos = -1;
+        result.push_back(c);
+      }
+    }
+    s = e;
+  }
+  orc_cluster *o = (orc_cluster *)calloc(result.size() ? result.size() : 1, sizeof(orc_cluster));
+  for (size_t i = 0; i < result.size(); ++i) o[i] = result[i];
+  *out = o;
+  return (long)result.size();
+}
+
+/* one self-contained evidence row per SA-tagged record of the slice (same layout as the device's EvRow) */
+void orc_shard_sa_rows(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos, const int32_t *endpos,
+                       const uint64_t *nh, long n_sa, const uint32_t *sa_rec, const uint32_t *cig_off, const uint32_t *cig_ops,
+                       const uint32_t *sa_off, const uint8_t *sa_txt, const uint32_t *oc_off, const uint8_t *oc_txt, orc_sarow *rows)
+{
+  for (long k = 0; k < n_sa; ++k) {
+    orc_sarow r; memset(&r, 0, sizeof r);
+    long i = sa_rec[k];
+    r.tid = tid[i]; r.pos = pos[i]; r.endpos = endpos[i]; r.name_lo = nh[2 * i]; r.name_hi = nh[2 * i + 1];
+    rows[k] = r;
+    std::string sa((const char *)sa_txt + sa_off[k], sa_off[k + 1] - sa_off[k]);
+    if (!(!sa.empty() && !(flag[i] & F_DUP) && (flag[i] & F_PAIRED))) continue;
+    std::string oc((const char *)oc_txt + oc_off[k], oc_off[k + 1] - oc_off[k]);
+    std::vector<std::string> f = split_nonempty(sa, ',');
+    if (f.size() < 4) continue;
+    Roller sa_c, c1, rec_c;
+    sa_c.set_text(f[3]);
+    rec_c.set_bam(cig_ops + cig_off[k], (int)(cig_off[k + 1] - cig_off[k]));
+    if (!oc.empty()) c1.set_text(oc); else c1 = rec_c;
+    if (!complementary(c1, f[3], 10)) continue;
+    r.ok = 1; r.secondary = (flag[i] & F_SECONDARY) ? 1 : 0;
+    uint32_t sa_start = (uint32_t)atoi(f[1].c_str()), sa_end = sa_c.aln_end(sa_start);
+    uint32_t a_start = (uint32_t)((long)pos[i] + 1);
+    int alen = rec_c.ref_count();
+    uint32_t a_end = (uint32_t)((long)(alen == 0 ? pos[i] : pos[i] + alen - 1) + 1);
+    uint64_t own_chr = chr_code_str(chrom_id_name(tid[i])), sa_chr = chr_code_str(f[0]);
+    uint32_t own_end = !oc.empty() ? c1.aln_end(a_start) : a_end;
+    uint64_t own_cig = orc_str_hash((!oc.empty() ? oc : rec_c.str()).c_str()), sa_cig = orc_str_hash(f[3].c_str());
+    uint32_t own_bp = 0, sa_bp = 0;
+    if (c1.begin_clips() != 0) own_bp = a_start; else if (c1.end_clips() != 0) own_bp = a_end; else r.fatal = 1;
+    if (sa_c.begin_clips() != 0) sa_bp = sa_start; else if (sa_c.end_clips() != 0) sa_bp = sa_end; else r.fatal = 1;
+    if (!r.secondary) {
+      r.pchr = own_chr; r.pstart = a_start; r.pend = own_end; r.pcig = own_cig; r.pbp = own_bp;
+      r.schr = sa_chr; r.sstart = sa_start; r.send = sa_end; r.scig = sa_cig; r.sbp = sa_bp;
+    } else {
+      r.pchr = sa_chr; r.pstart = sa_start; r.pend = sa_end; r.pcig = sa_cig; r.pbp = sa_bp;
+      r.schr = own_chr; r.sstart = a_start; r.send = own_end; r.scig = own_cig; r.sbp = own_bp;
+    }
+    rows[k] = r;
+  }
+}
+
+static void cluster_regions(const orc_cluster &c, double dist, int *b1, int *e1, int *b2, int *e2)
+{
+  int w = (int)dist;
+  *b1 = (int)(uint32_t)(c.p1_mean_pos - w); *e1 = (int)(uint32_t)(c.p1_mean_pos + w);
+  *b2 = (int)(uint32_t)(c.p2_mean_pos - w); *e2 = (int)(uint32_t)(c.p2_mean_pos + w);
+  if (*b1 < 0) *b1 = 0;
+  if (*b2 < 0) *b2 = 0;
+}
+
+static uint32_t count_overlaps(long n, const int32_t *tid, const int32_t *pos, const int32_t *endpos, const uint16_t *flag, const uint8_t *mapq,
+                               int t, int beg, int end, bool depth_only)
+{
+  if (end < beg || t < 0) return 0;
+  uint32_t c = 0;
+  for (long i = 0; i < n; ++i)
+    if (tid[i] == t && pos[i] < end && endpos[i] > beg && (!depth_only || (mapq[i] > 0 && !(flag[i] & F_DUP) && (flag[i] & F_PAIRED)))) ++c;
+  return c;
+}
+
+/* partial coverage of both regions of every cluster on one slice of records */
+void orc_shard_coverage(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos, const int32_t *endpos,
+                        long ncl, const orc_cluster *cl, double dist, uint32_t *cov)
+{
+  for (long c = 0; c < ncl; ++c) {
+    int b1, e1, b2, e2;
+    cluster_regions(cl[c], dist, &b1, &e1, &b2, &e2);
+    cov[2 * c] = count_overlaps(n, tid, pos, endpos, flag, mapq, cl[c].p1_tid, b1, e1, false);
+    cov[2 * c + 1] = count_overlaps(n, tid, pos, endpos, flag, mapq, cl[c].p2_tid, b2, e2, false);
+  }
+}
+
+/* gate + pairing + vote on the GLOBAL row table with TOTAL coverage; returns -1 on the fatal cigar path */
+long orc_shard_vote(long n_rows, const orc_sarow *rows, long ncl, orc_cluster *cl, const uint32_t *cov, int n_targets, const char *const *names,
+                    double dist, uint32_t *valid)
+{
+  bool fatal = false;
+  for (long c = 0; c < ncl; ++c) {
+    valid[c] = 0;
+    int b1, e1, b2, e2;
+    cluster_regions(cl[c], dist, &b1, &e1, &b2, &e2);
+    auto collect = [&](int t, int beg, int end, uint32_t coverage, std::vector<long> &ev) {
+      ev.clear();
+      if (end < beg || t < 0) return;
+      for (long k = 0; k < n_rows; ++k)
+        if (rows[k].tid == t && rows[k].pos < end && rows[k].endpos > beg && rows[k].ok) { ev.push_back(k); if (rows[k].fatal) fatal = true; }
+      if (coverage < 5 || ev.size() < 2) ev.clear();
+    };
+    std::vector<long> l1, l2;
+    collect(cl[c].p1_tid, b1, e1, cov[2 * c], l1);
+    if (!l1.empty()) collect(cl[c].p2_tid, b2, e2, cov[2 * c + 1], l2);
+    if (l1.empty() || l2.empty()) continue;
+    uint64_t p1code = chr_code_str(cl[c].p1_tid >= 0 && cl[c].p1_tid < n_targets ? names[cl[c].p1_tid] : "*");
+    std::vector<std::pair<int32_t, int32_t>> upd;
+    for (long a : l1) for (long b : l2) {
+      const orc_sarow &A = rows[a], &B = rows[b];
+      if (A.name_lo == B.name_lo && A.name_hi == B.name_hi && A.secondary != B.secondary && A.pchr == B.pchr && A.schr == B.schr &&
+          A.pstart == B.pstart && A.sstart == B.sstart && A.pend == B.pend && A.send == B.send && A.pcig == B.pcig && A.scig == B.scig &&
+          A.pbp == B.pbp && A.sbp == B.sbp) {
+        if (A.pchr == p1code) upd.push_back({(int32_t)A.pbp, (int32_t)A.sbp}); else upd.push_back({(int32_t)A.sbp, (int32_t)A.pbp});
+      }
+    }
+    std::map<std::string, int> cnt;
+    for (auto &u : upd) cnt[std::to_string(u.first) + "," + std::to_string(u.second)] = 0;
+    int best = 0; int32_t bx = -1, by = -1;
+    for (auto &kv : cnt) {
+      size_t q = kv.first.find(',');
+      uint32_t k1 = (uint32_t)strtoull(kv.first.substr(0, q).c_str(), nullptr, 10), k2 = (uint32_t)strtoull(kv.first.substr(q + 1).c_str(), nullptr, 10);
+      for (auto &u : upd)
+        if (((uint32_t)u.first <= k1 + 2 && (uint32_t)u.first >= k1 - 2) && ((uint32_t)u.second <= k2 + 2 && (uint32_t)u.second >= k2 - 2)) kv.second++;
+      if (best < kv.second) { best = kv.second; bx = (int32_t)k1; by = (int32_t)k2; }
+    }
+    if (best >= 2) { valid[c] = 1; cl[c].p1_exact_pos = (uint32_t)bx; cl[c].p2_exact_pos = by; cl[c].n_split_read = best; }
+  }
+  return fatal ? -1 : 0;
+}
+
+void orc_shard_depth(long n, const uint16_t *flag, const uint8_t *mapq, const int32_t *tid, const int32_t *pos, const int32_t *endpos,
+                     long ncl, const orc_cluster *cl, const uint32_t *valid, uint32_t *depth)
+{
+  for (long c = 0; c < ncl; ++c) {
+    depth[2 * c] = depth[2 * c + 1] = 0;
+    if (!valid[c]) continue;
+    uint64_t p1 = (uint64_t)cl[c].p1_exact_pos, p2 = (uint64_t)(int64_t)cl[c].p2_exact_pos;
+    int b1 = (int)(p1 - 1), e1 = (int)p1, b2 = (int)(p2 - 1), e2 = (int)p2;
+    if (b1 < 0) b1 = 0;
+    if (b2 < 0) b2 = 0;
+    depth[2 * c] = count_overlaps(n, tid, pos, endpos, flag, mapq, cl[c].p1_tid, b1, e1, true);
+    depth[2 * c + 1] = count_overlaps(n, tid, pos, endpos, flag, mapq, cl[c].p2_tid, b2, e2, true);
+  }
+}
+
+/* depth (totals), AF, 41-mers; compacts the valid clusters to the front and returns their number */
+long orc_shard_finish(long ncl, orc_cluster *cl, const uint32_t *valid, const uint32_t *depth, const uint8_t *const *nib_packed, const uint64_t *nib_len)
+{
+  long m = 0;
+  for (long c = 0; c < ncl; ++c) {
+    if (!valid[c]) continue;
+    orc_cluster x = cl[c];
+    x.p1_bp_depth = depth[2 * c]; x.p2_bp_depth = depth[2 * c + 1];
+    x.p1_alle_freq = (float)x.n_split_read / (float)x.p1_bp_depth;
+    x.p2_alle_freq = (float)x.n_split_read / (float)x.p2_bp_depth;
+    if (nib_packed) {
+      if (x.p1_tid >= 0 && nib_packed[x.p1_tid]) orc_neighbor_41(nib_packed[x.p1_tid], nib_len[x.p1_tid], (int32_t)x.p1_exact_pos, x.p1_rpt);
+      if (x.p2_tid >= 0 && nib_packed[x.p2_tid]) orc_neighbor_41(nib_packed[x.p2_tid], nib_len[x.p2_tid], x.p2_exact_pos, x.p2_rpt);
+      x.is_rpt = (longest_run(x.p1_rpt) > 10 || longest_run(x.p2_rpt) > 10) ? 1 : 0;
+    }
+    cl[m++] = x;
+  }
+  return m;
+}
+
 }  /* extern "C" */

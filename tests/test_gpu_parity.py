@@ -263,3 +263,37 @@ def test_driver_call_files_match_reference_binary(tmp_path, mode):
     pa = open(str(tmp_path / "ref") + "_params.txt").read().replace(str(tmp_path / "ref"), "X")
     pb = open(str(tmp_path / "gpu") + "_params.txt").read().replace(str(tmp_path / "gpu"), "X")
     assert pa == pb
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_shard_entry_points_single_rank(small_data, mode):
+    """the multi-GPU orchestration (breakid_b200.dist.run_sharded) on one rank, through the bkid_shard_* ABI,
+    equals the monolithic bkid_run and the oracle"""
+    import torch
+    import oracle_py as O
+    from breakid_b200 import api
+    from breakid_b200.dist import GpuEngine, run_sharded
+    d, hb, nibs = small_data
+    c = _ctx_for(hb, fast=mode)
+    for t, (p, l) in enumerate(nibs):
+        c.set_nib(t, p, l)
+    mean, sd, dist_, out = run_sharded(GpuEngine(c, torch.device("cuda", 0)), hb.n, mode=mode)
+    om, osd, od, exp = O.run(hb, nibs, mode=mode)
+    assert (mean, sd, dist_) == (om, osd, od)
+    assert out.tobytes() == exp.tobytes()
+    c.close()
+
+
+def test_sa_rows_match_oracle(small_data):
+    """device split-read evidence rows (CIGAR / SA arithmetic) are byte-identical to the oracle's"""
+    import ctypes as C
+    import torch
+    from breakid_b200.dist import GpuEngine
+    from oracle_engine import OracleEngine
+    d, hb, nibs = small_data
+    c = _ctx_for(hb)
+    got = GpuEngine(c, torch.device("cuda", 0)).sa_rows().cpu().numpy()
+    exp = OracleEngine(hb).sa_rows().numpy()
+    assert got.shape == exp.shape and got.shape[0] > 50
+    assert np.array_equal(got, exp)
+    c.close()
