@@ -662,6 +662,7 @@ int bkid_reset(bkid_ctx *c)
   set_ptrs(c);
   invalidate(c);
   memset(&c->tm, 0, sizeof c->tm);
+  c->launches0 = g_bk_launches;
   return 0;
 }
 
@@ -1353,6 +1354,7 @@ int bkid_get_timings(bkid_ctx *c, bkid_timings *t)
 {
   if (!c || !t) return BKID_ERR_ARG;
   *t = c->tm;
+  t->kernel_launches = g_bk_launches - c->launches0;      // launches since the last bkid_reset / create
   return 0;
 }
 

@@ -43,6 +43,13 @@ class GpuEngine:
     def _chk(self, rc):
         self.ctx._chk(rc)
 
+    def _ready(self, t):
+        """tensors produced by torch / NCCL live on torch's streams; the library works on its own non-blocking
+        stream, so make them visible before handing their pointers over"""
+        t = t.contiguous()
+        torch.cuda.synchronize(self.device)
+        return t
+
     def _take(self, ptr, nbytes, row):
         t = torch.empty((nbytes // row, row) if row else (nbytes,), dtype=torch.uint8, device=self.device)
         if nbytes:
@@ -68,13 +75,13 @@ class GpuEngine:
         return self._take(p, n.value * CAND_B, CAND_B)
 
     def join(self, cands, w):
-        cands = cands.contiguous()
+        cands = self._ready(cands)
         p, n = C.c_void_p(), C.c_int64()
         self._chk(self.lib.bkid_shard_join(self.ctx.ctx, cands.data_ptr(), cands.shape[0], w, C.byref(p), C.byref(n)))
         return self._take(p, n.value * PAIR_B, PAIR_B)
 
     def set_pairs(self, pairs):
-        pairs = pairs.contiguous()
+        pairs = self._ready(pairs)
         self._chk(self.lib.bkid_shard_set_pairs(self.ctx.ctx, pairs.data_ptr(), pairs.shape[0]))
 
     def cluster(self, d, mode):
@@ -86,7 +93,7 @@ class GpuEngine:
         return self._take(p, n.value * CLUSTER_B, CLUSTER_B)
 
     def set_clusters(self, t):
-        t = t.contiguous()
+        t = self._ready(t)
         self._chk(self.lib.bkid_shard_set_clusters(self.ctx.ctx, t.data_ptr(), t.shape[0]))
 
     def sa_rows(self):
@@ -95,7 +102,7 @@ class GpuEngine:
         return self._take(p, n.value * SAROW_B, SAROW_B)
 
     def set_sa_rows(self, t):
-        self._keep["rows"] = t.contiguous()
+        self._keep["rows"] = self._ready(t)
         self._chk(self.lib.bkid_shard_set_sa_rows(self.ctx.ctx, self._keep["rows"].data_ptr(), t.shape[0]))
 
     def maxspan(self):
@@ -119,6 +126,7 @@ class GpuEngine:
         return t
 
     def commit_coverage(self, t):
+        t = self._ready(t)
         if t.numel():
             self._chk(self.lib.bkid_device_copy(self.ctx.ctx, self._cov_ptr, t.data_ptr(), t.numel() * 4))
 
@@ -130,6 +138,7 @@ class GpuEngine:
         return t
 
     def commit_depth(self, t):
+        t = self._ready(t)
         if t.numel():
             self._chk(self.lib.bkid_device_copy(self.ctx.ctx, self._dep_ptr, t.data_ptr(), t.numel() * 4))
 
@@ -270,7 +279,13 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
         key = (v[:, 0].to(torch.int64) << 32) | v[:, 1].to(torch.int64)
         cl = cl[torch.sort(key, stable=True).indices].contiguous()
     engine.set_clusters(cl)
-    engine.set_sa_rows(_all_gather_rows(engine.sa_rows()))
+    rows = _all_gather_rows(engine.sa_rows())
+    if rows.shape[0] and W > 1:
+        # the table is searched by (tid, pos): restore coordinate order when the slices are not genomic bins
+        v = rows.view(torch.int32)
+        key = ((v[:, 18].to(torch.int64) & 0xffffffff) << 32) | (v[:, 19].to(torch.int64) & 0xffffffff)
+        rows = rows[torch.sort(key, stable=True).indices].contiguous()
+    engine.set_sa_rows(rows)
     ms = _reduce(torch.tensor([engine.maxspan()], dtype=torch.int32, device=dev), dist.ReduceOp.MAX)
     engine.set_maxspan(int(ms[0]))
     engine.commit_coverage(_reduce(engine.coverage(d), dist.ReduceOp.SUM))
