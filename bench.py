@@ -165,6 +165,8 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     engine = None
+    shard_timing = {}
+    timing_on = [False]
     if world > 1:
         from breakid_b200.dist import GpuEngine, run_sharded
         engine = GpuEngine(ctx, dev)
@@ -172,7 +174,7 @@ def run_ours(args):
     def run_path():
         if world == 1:
             return ctx.run()
-        mean, sd, dd, out = run_sharded(engine, n, mode=0)
+        mean, sd, dd, out = run_sharded(engine, n, mode=0, timing=shard_timing if (os.environ.get("BKID_DEBUG_TIMING") and timing_on[0]) else None)
         return mean, sd, dd, len(out)
 
     def step_resident():
@@ -191,6 +193,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         ev0.record()
         dev_ms = 0.0
+        timing_on[0] = True
         for _ in range(args.steps):
             res = step_resident()
             tm = ctx.timings()
@@ -198,6 +201,7 @@ def run_ours(args):
             for k in stage:
                 stage[k] += tm[k]
             launches += tm["kernel_launches"]
+        timing_on[0] = False
         barrier()
         ev1.record()
         ev1.synchronize()
@@ -259,6 +263,10 @@ def run_ours(args):
         "clocks": clk.summary(),
         "gen_seconds": gen_s,
     }
+    if rank == 0 and shard_timing:
+        tot = sum(shard_timing.values())
+        for k, v in shard_timing.items():
+            print("[shard-timing] %-28s %8.3f ms/step" % (k, v / args.steps), file=sys.stderr)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_port(args)

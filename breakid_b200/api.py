@@ -192,7 +192,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_scan", "bkid_cluster", "bkid_set_nib", "bkid_refine", "bkid_run", "bkid_fetch_clusters",
            "bkid_fetch_pairs", "bkid_fetch_class", "bkid_get_timings", "bkid_op_sort_perm",
            "bkid_op_remove_isolated", "bkid_op_cluster",
-           "bkid_shard_insert_partial", "bkid_shard_sd_partial", "bkid_shard_set_stats", "bkid_shard_candidates", "bkid_shard_join",
+           "bkid_shard_insert_partial", "bkid_shard_sd_prepare", "bkid_shard_sd_partial", "bkid_shard_set_stats", "bkid_shard_candidates", "bkid_shard_join",
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy"]
@@ -236,6 +236,7 @@ def cuda_lib():
         L.bkid_op_cluster.argtypes = [vp, C.c_int, C.c_int64, vp, vp, C.c_double, vp, vp, i64p, C.POINTER(C.c_int32)]
         pvp = C.POINTER(C.c_void_p)
         L.bkid_shard_insert_partial.argtypes = [vp, i64p, i64p]
+        L.bkid_shard_sd_prepare.argtypes = [vp, C.c_double]
         L.bkid_shard_sd_partial.argtypes = [vp, C.c_double, C.c_int64, i64p]
         L.bkid_shard_set_stats.argtypes = [vp, C.c_double, C.c_double]
         L.bkid_shard_candidates.argtypes = [vp, C.c_uint64, pvp, i64p]

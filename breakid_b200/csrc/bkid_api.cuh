@@ -64,6 +64,7 @@ struct bkid_ctx {
   long long n2 = 0;
   std::vector<int32_t> roots_per_bucket;
   // clusters
+  DBuf sdtab; bool sd_prepared = false; double sd_mean = 0;
   DBuf clusters, clusters_out, sarows, work, cov, depth, evoff, valid;
   const void *rows_ptr = nullptr; long long n_rows = 0, n_evcap = 0; int maxspan = 1; bool clusters_ranked = false;
   long long n_clusters = 0, n_called = 0;
@@ -350,8 +351,35 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 900, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, 900u);
   BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 900u, 4096u);
   T_.mark("ahc: replay smem (flagged)");
-  BK_LAUNCH(ahc_replay, GRID1(nseg, 4), 128, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
-  T_.mark("ahc: replay global");
+  {
+    // buckets >= 4096 points without flagged components: rank form in global memory
+    DBuf &RG = c->tmpF;
+    size_t nn = (size_t)n + 8;
+    TRY(c, RG.ensure(nn * (8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + (size_t)(nseg + 2) * 4 + 256, 0, st));
+    char *q = (char *)RG.p;
+    RankGlobal g;
+    g.pm = (double *)q; q += nn * 8;
+    g.slot_comp = (uint32_t *)q; q += nn * 4;
+    g.first = (int32_t *)q; q += nn * 4;
+    g.rank = (uint32_t *)q; q += nn * 4;
+    g.order = (uint32_t *)q; q += nn * 4;
+    g.is_head = (uint32_t *)q; q += nn * 4;
+    uint32_t *head_excl = (uint32_t *)q; q += nn * 4;
+    uint32_t *bucket_events = (uint32_t *)q; q += (size_t)(nseg + 2) * 4;
+    g.tie = (uint8_t *)q;
+    uint32_t *head_pos = c->sc.e32.as<uint32_t>();
+    CU(c, cudaMemsetAsync(bucket_events, 0, (size_t)(nseg + 2) * 4, st));
+    CU(c, cudaMemsetAsync(g.is_head, 0, nn * 4, st));
+    BK_LAUNCH(ahc_rg_bucket_events, GRID1(ncomp, 128), 128, 0, st, v, ncomp, bucket_events);
+    BK_LAUNCH(ahc_rg_prepare, GRID1(ncomp, 128), 128, 0, st, v, g, ncomp, bucket_flag, 4096u);
+    BK_LAUNCH(ahc_rg_rank, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u);
+    BK_LAUNCH(ahc_rg_heads, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u, bucket_events);
+    bk::exclusive_scan<uint32_t, uint32_t>(g.is_head, head_excl, n, stmp, tot, st);
+    BK_LAUNCH(ahc_rg_head_list, GRID1(n, 256), 256, 0, st, g.is_head, head_excl, n, head_pos);
+    BK_LAUNCH(ahc_rg_ties, GRID1(nseg, 64), 64, 0, st, v, g, (uint32_t)nseg, bucket_flag, 4096u, bucket_events, head_pos, head_excl, n);
+    BK_LAUNCH(ahc_rg_write, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u);
+  }
+  T_.mark("ahc: replay rank form (global)");
   BK_LAUNCH(ahc_bucket_exact, (unsigned)nseg, 32, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
   T_.mark("ahc: replay+exact");
   // final roots -> clusters
@@ -518,7 +546,7 @@ void bkid_destroy(bkid_ctx *c)
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->mtid, &c->mpos, &c->isize, &c->endpos, &c->nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->clusters, &c->clusters_out, &c->sarows, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
+                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->clusters, &c->clusters_out, &c->sarows, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();
@@ -528,7 +556,7 @@ void bkid_destroy(bkid_ctx *c)
   delete c;
 }
 
-static void invalidate(bkid_ctx *c) { c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; }
+static void invalidate(bkid_ctx *c) { c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; }
 
 static int reserve_impl(bkid_ctx *c, long long n, long long n_sa, long long n_cig, long long sa_b, long long oc_b)
 {
@@ -691,24 +719,43 @@ static int classify_impl(bkid_ctx *c)
   return 0;
 }
 
-// exact continuation of the truncating sd accumulator over the local records, starting from t_in
+// exact continuation of the truncating sd accumulator over the local records, starting from t_in:
+// sd_prepare = the streaming pass that builds the per-block tables (independent of t_in),
+// sd_resolve_impl = the single-CTA exact walk from t_in.
+static int sd_prepare_impl(bkid_ctx *c, double mean)
+{
+  cudaStream_t st = c->st;
+  long long n = c->n;
+  c->sd_prepared = false;
+  if (n <= 0 || c->cnt_insert <= 0) return 0;
+  int nb = div_up(std::max<long long>(n, 1), SD_BLOCK);
+  TRY(c, c->sdtab.ensure((size_t)nb * (8 + SD_K * 4 + 4 + 8) + 256, 0, st));
+  char *bp = (char *)c->sdtab.p;
+  long long *blkF = (long long *)bp; bp += (size_t)nb * 8;
+  double *blkA = (double *)bp; bp += (size_t)nb * 8;
+  uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
+  uint32_t *blkN = (uint32_t *)bp;
+  BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, blkF, blkCum, blkN, blkA);
+  c->sd_prepared = true; c->sd_mean = mean;
+  return 0;
+}
+
 static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *t_out)
 {
   cudaStream_t st = c->st;
   long long n = c->n;
   *t_out = t_in;
   if (n <= 0 || c->cnt_insert <= 0) return 0;
+  SubTimer T_(st);
+  if (!c->sd_prepared || c->sd_mean != mean) TRY(c, sd_prepare_impl(c, mean));
+  T_.mark("sd: block stats");
   int nb = div_up(std::max<long long>(n, 1), SD_BLOCK);
-  TRY(c, c->tmpA.ensure((size_t)nb * (8 + SD_K * 4 + 4 + 8) + 256, 0, st));
-  char *bp = (char *)c->tmpA.p;
+  char *bp = (char *)c->sdtab.p;
   long long *blkF = (long long *)bp; bp += (size_t)nb * 8;
   double *blkA = (double *)bp; bp += (size_t)nb * 8;
   uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
   uint32_t *blkN = (uint32_t *)bp;
   long long *out = (long long *)(c->counters.as<unsigned>() + 8);
-  SubTimer T_(st);
-  BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, blkF, blkCum, blkN, blkA);
-  T_.mark("sd: block stats");
   BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, nb, blkF, blkCum, blkN, blkA, t_in, out);
   T_.mark("sd: resolve");
   long long h[2] = {0, 0};
@@ -1106,6 +1153,15 @@ int bkid_shard_insert_partial(bkid_ctx *c, int64_t *sum_abs, int64_t *count)
   TRY(c, classify_impl(c));
   *sum_abs = c->sum_abs; *count = c->cnt_insert;
   return 0;
+}
+
+int bkid_shard_sd_prepare(bkid_ctx *c, double mean)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, classify_impl(c));
+  TRY(c, sd_prepare_impl(c, mean));
+  return sync_check(c);
 }
 
 int bkid_shard_sd_partial(bkid_ctx *c, double mean, int64_t t_in, int64_t *t_out)

@@ -527,6 +527,133 @@ __global__ void __launch_bounds__(RK_THREADS) ahc_replay_rank(AhcView v, const u
   }
 }
 
+// Kernel B (rank form, global memory) for buckets too large for shared memory: same algorithm as
+// ahc_replay_rank, spread over the whole GPU (one thread per event slot for the counting pass).
+struct RankGlobal {
+  double *pm;            // [n] prefix-max distance per event slot, +inf for unused slots
+  uint32_t *slot_comp;   // [n]
+  int32_t *first;        // [n] leaf index (>= 0) or -1 - creating event
+  uint32_t *rank, *order;
+  uint8_t *tie;
+  uint32_t *is_head;
+};
+
+__global__ void ahc_rg_prepare(AhcView v, RankGlobal g, uint32_t ncomp, const int32_t *__restrict__ bucket_flag, uint32_t n_lo)
+{
+  uint32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (comp >= ncomp) return;
+  uint32_t b = v.comp_bucket[comp];
+  if (bucket_flag[b] || v.seg_off[b + 1] - v.seg_off[b] < n_lo) return;
+  uint32_t lbase = v.comp_off[comp], c = v.comp_off[comp + 1] - lbase, nev = v.comp_nnodes[comp] - c;
+  const uint32_t pbase = v.seg_off[b];
+  double pm = 0.0;
+  for (uint32_t e = 0; e < c; ++e) {
+    uint32_t q = lbase + e;
+    g.slot_comp[q] = comp;
+    if (e < nev) {
+      double d = v.ev_d[q];
+      if (d > pm) pm = d;
+      int32_t f = v.ev_first[q];
+      g.pm[q] = pm;
+      g.first[q] = (uint32_t)f < c ? (int32_t)(v.comp_leaf[lbase + f] - pbase) : -1 - (int32_t)((uint32_t)f - c);
+    } else g.pm[q] = __longlong_as_double(0x7ff0000000000000ll);
+    g.tie[q] = 0; g.is_head[q] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) ahc_rg_rank(AhcView v, RankGlobal g, const uint32_t *__restrict__ point_bucket, long long n, const int32_t *__restrict__ bucket_flag, uint32_t n_lo)
+{
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  uint32_t b = point_bucket[e];
+  uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
+  if (bucket_flag[b] || s1 - s0 < n_lo) return;
+  double pm = g.pm[e];
+  if (!(pm < 1.0e300)) return;                         // unused slot
+  uint32_t ce = g.slot_comp[e], cnt = 0;
+  bool t = false;
+  for (uint32_t o = s0; o < s1; ++o) {
+    double p2 = g.pm[o];
+    cnt += (p2 < pm || (p2 == pm && o < (uint32_t)e)) ? 1u : 0u;
+    t |= (p2 == pm) && (g.slot_comp[o] != ce);
+  }
+  g.rank[e] = cnt; g.order[s0 + cnt] = (uint32_t)e; g.tie[e] = t ? 1 : 0;
+}
+
+// group heads in rank order (a group = maximal run of one exact prefix-max value touching >= 2 components)
+__global__ void ahc_rg_heads(AhcView v, RankGlobal g, const uint32_t *__restrict__ point_bucket, long long n, const int32_t *__restrict__ bucket_flag, uint32_t n_lo,
+                             const uint32_t *__restrict__ bucket_events)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t b = point_bucket[p];
+  uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
+  if (bucket_flag[b] || s1 - s0 < n_lo) return;
+  uint32_t r = (uint32_t)p - s0;
+  if (r >= bucket_events[b]) return;
+  uint32_t e = g.order[p];
+  if (!g.tie[e]) return;
+  if (r == 0 || g.pm[g.order[p - 1]] != g.pm[e]) g.is_head[p] = 1;
+}
+
+// per bucket, group after group in ascending prefix-max order: the literal heap walk over the group
+__global__ void ahc_rg_ties(AhcView v, RankGlobal g, uint32_t nb, const int32_t *__restrict__ bucket_flag, uint32_t n_lo, const uint32_t *__restrict__ bucket_events,
+                            const uint32_t *__restrict__ head_pos, const uint32_t *__restrict__ head_excl, long long n)
+{
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
+  if (bucket_flag[b] || s1 - s0 < n_lo || s1 == s0) return;
+  uint32_t nleaf = s1 - s0, M = bucket_events[b];
+  uint32_t h0 = head_excl[s0], h1 = (s1 < (uint32_t)n) ? head_excl[s1] : head_excl[n - 1] + g.is_head[n - 1];
+  for (uint32_t h = h0; h < h1; ++h) {
+    uint32_t p0 = head_pos[h], r = p0 - s0;
+    uint32_t e0 = g.order[p0];
+    uint32_t r2 = r + 1;
+    while (r2 < M && g.pm[g.order[s0 + r2]] == g.pm[e0]) ++r2;
+    for (uint32_t s = 0; s < r2 - r; ++s) {
+      long long best = -1; double bd = 0.0; int32_t bg = -1;
+      for (uint32_t p = r; p < r2; ++p) {
+        uint32_t e = g.order[s0 + p];
+        if (g.tie[e] == 2) continue;
+        if (p > r) { uint32_t ep = g.order[s0 + p - 1]; if (g.slot_comp[ep] == g.slot_comp[e] && g.tie[ep] != 2) continue; }
+        int32_t f = g.first[e];
+        uint32_t comp = g.slot_comp[e];
+        int32_t gi = f >= 0 ? f : (int32_t)nleaf + (int32_t)g.rank[v.comp_off[comp] + (uint32_t)(-1 - f)];
+        double d = v.ev_d[e];
+        if (best < 0 || d < bd || (d == bd && gi > bg)) { best = (long long)e; bd = d; bg = gi; }
+      }
+      g.rank[best] = r + s;
+      g.tie[best] = 2;
+    }
+  }
+}
+
+__global__ void ahc_rg_head_list(const uint32_t *__restrict__ is_head, const uint32_t *__restrict__ head_excl, long long n, uint32_t *__restrict__ head_pos)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n && is_head[p]) head_pos[head_excl[p]] = (uint32_t)p;
+}
+
+__global__ void ahc_rg_bucket_events(AhcView v, uint32_t ncomp, uint32_t *__restrict__ bucket_events)
+{
+  uint32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (comp >= ncomp) return;
+  uint32_t c = v.comp_off[comp + 1] - v.comp_off[comp], nev = v.comp_nnodes[comp] - c;
+  if (nev) atomicAdd(&bucket_events[v.comp_bucket[comp]], nev);
+}
+
+__global__ void ahc_rg_write(AhcView v, RankGlobal g, const uint32_t *__restrict__ point_bucket, long long n, const int32_t *__restrict__ bucket_flag, uint32_t n_lo)
+{
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  uint32_t b = point_bucket[e];
+  if (bucket_flag[b] || v.seg_off[b + 1] - v.seg_off[b] < n_lo) return;
+  if (!(g.pm[e] < 1.0e300)) return;
+  uint32_t comp = g.slot_comp[e], lbase = v.comp_off[comp], c = v.comp_off[comp + 1] - lbase;
+  v.node_grank[2 * lbase + c + ((uint32_t)e - lbase)] = (int32_t)g.rank[e];
+}
+
 // Kernel C: exact online form for buckets with a flagged component (one warp per bucket)
 __global__ void __launch_bounds__(32) ahc_bucket_exact(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag, uint32_t n_lo)
 {

@@ -66,6 +66,9 @@ class GpuEngine:
         self._chk(self.lib.bkid_shard_sd_partial(self.ctx.ctx, mean, t_in, C.byref(t)))
         return t.value
 
+    def sd_prepare(self, mean):
+        self._chk(self.lib.bkid_shard_sd_prepare(self.ctx.ctx, mean))
+
     def set_stats(self, mean, sd):
         self._chk(self.lib.bkid_shard_set_stats(self.ctx.ctx, mean, sd))
 
@@ -188,7 +191,10 @@ def _all_to_all_rows(t: torch.Tensor, owner: torch.Tensor) -> torch.Tensor:
     if W == 1:
         return t
     order = torch.sort(owner, stable=True).indices
-    send = t[order].contiguous()
+    if t.shape[1] % 8 == 0:          # move rows as 8-byte words, not bytes
+        send = t.view(torch.int64)[order].contiguous().view(torch.uint8)
+    else:
+        send = t[order].contiguous()
     scount = torch.bincount(owner, minlength=W).to(torch.int64)
     rcount = torch.empty_like(scount)
     dist.all_to_all_single(rcount, scount) if dist.get_backend() != "gloo" else _gloo_a2a_counts(rcount, scount)
@@ -234,22 +240,35 @@ def _reduce(t: torch.Tensor, op):
     return t
 
 
-def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: int = 0):
+def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: int = 0, timing: Optional[dict] = None):
     """the whole hot path over all ranks; returns (mean, sd, dist, called cluster records [numpy, bucket =
     dense id]) -- identical on every rank and identical to the single-GPU / reference result"""
+    import time as _time
     W, r = _world(), _rank()
     dev = engine.device
+    _t = [_time.perf_counter()]
+
+    def lap(name):
+        if timing is not None:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            now = _time.perf_counter()
+            timing[name] = timing.get(name, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
     # insert statistics: exact integer sum/count, then the order-dependent sd accumulator chained through the ranks
     s, n = engine.insert_partial()
     sn = _reduce(torch.tensor([s, n], dtype=torch.int64, device=dev), dist.ReduceOp.SUM)
     S, N = int(sn[0]), int(sn[1])
     mean = float(S) / float(N)
+    if hasattr(engine, "sd_prepare"):
+        engine.sd_prepare(mean)          # the streaming pass (block tables) runs on all ranks at once; only the cheap resolve is chained
     t = torch.zeros(1, dtype=torch.int64, device=dev)
     for src in range(W):
         if r == src:
             t[0] = engine.sd_partial(mean, int(t[0]))
         if W > 1:
             dist.broadcast(t, src=src)
+    lap('insert stats + sd chain')
     sd = math.sqrt(int(t[0]) / float(N))
     d = times * math.sqrt(times) * (mean + sd_mult * sd)
     engine.set_stats(mean, sd)
@@ -262,36 +281,47 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
     cands = engine.candidates(offset)
     lo = cands.view(torch.int64)[:, 0] if cands.shape[0] else torch.zeros(0, dtype=torch.int64, device=dev)
     owner = ((lo >> 8) & 0x7fffffff) % W
+    lap('candidates')
     cands = _all_to_all_rows(cands, owner)
+    lap('a2a candidates')
     pairs = engine.join(cands, d)
+    lap('join')
     # pairs go to the owner of their chr-pair bucket
     bucket = pairs.view(torch.int32)[:, 12].to(torch.int64) if pairs.shape[0] else torch.zeros(0, dtype=torch.int64, device=dev)
     pairs = _all_to_all_rows(pairs, bucket % W)
+    lap('a2a pairs')
     engine.set_pairs(pairs)
+    lap('set_pairs')
     # dense bucket ids of the reference = rank among ALL buckets that hold at least one pair, over all ranks
     br = engine.bucket_ranks().to(torch.int32).reshape(-1, 1).contiguous().view(torch.uint8)
     all_ranks = torch.sort(_all_gather_rows(br).view(torch.int32).reshape(-1)).values
     engine.cluster(d, mode)
+    lap('mask+cluster')
     # every rank gets every cluster summary, in the reference's order (bucket name rank, cluster id)
     cl = _all_gather_rows(engine.clusters())
     if cl.shape[0]:
         v = cl.view(torch.int32)
         key = (v[:, 0].to(torch.int64) << 32) | v[:, 1].to(torch.int64)
-        cl = cl[torch.sort(key, stable=True).indices].contiguous()
+        cl = cl.view(torch.int64)[torch.sort(key, stable=True).indices].contiguous().view(torch.uint8)
     engine.set_clusters(cl)
+    lap('gather clusters')
     rows = _all_gather_rows(engine.sa_rows())
     if rows.shape[0] and W > 1:
         # the table is searched by (tid, pos): restore coordinate order when the slices are not genomic bins
         v = rows.view(torch.int32)
         key = ((v[:, 18].to(torch.int64) & 0xffffffff) << 32) | (v[:, 19].to(torch.int64) & 0xffffffff)
-        rows = rows[torch.sort(key, stable=True).indices].contiguous()
+        rows = rows.view(torch.int64)[torch.sort(key, stable=True).indices].contiguous().view(torch.uint8)
     engine.set_sa_rows(rows)
+    lap('gather sa rows')
     ms = _reduce(torch.tensor([engine.maxspan()], dtype=torch.int32, device=dev), dist.ReduceOp.MAX)
     engine.set_maxspan(int(ms[0]))
     engine.commit_coverage(_reduce(engine.coverage(d), dist.ReduceOp.SUM))
+    lap('coverage + allreduce')
     engine.vote()
+    lap('vote')
     engine.commit_depth(_reduce(engine.depth(), dist.ReduceOp.SUM))
     out = engine.finish()
+    lap('depth + finish')
     if len(out):
         out = out.copy()
         out["bucket"] = np.searchsorted(all_ranks.cpu().numpy(), out["bucket"]).astype(np.int32)   # name rank -> dense id

@@ -192,6 +192,7 @@ int bkid_get_timings(bkid_ctx *ctx, bkid_timings *t);
  * and valid until the next call.  Single-GPU bkid_scan / bkid_refine are compositions of the same pieces. */
 typedef struct { uint64_t q[11]; } bkid_sarow;        /* opaque 88-byte split-read evidence row (self-contained) */
 int bkid_shard_insert_partial(bkid_ctx *ctx, int64_t *sum_abs, int64_t *count);                 /* -> all-reduce (sum) */
+int bkid_shard_sd_prepare(bkid_ctx *ctx, double mean);                                           /* streaming pass, all ranks at once */
 int bkid_shard_sd_partial(bkid_ctx *ctx, double mean, int64_t t_in, int64_t *t_out);             /* chained rank to rank */
 int bkid_shard_set_stats(bkid_ctx *ctx, double mean, double sd);
 int bkid_shard_candidates(bkid_ctx *ctx, uint64_t index_offset, const bkid_cand **dev, int64_t *n);   /* -> all-to-all by name hash */

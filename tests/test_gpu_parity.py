@@ -297,3 +297,19 @@ def test_sa_rows_match_oracle(small_data):
     assert got.shape == exp.shape and got.shape[0] > 50
     assert np.array_equal(got, exp)
     c.close()
+
+
+def test_ahc_large_bucket_rank_form(ctx1):
+    """one bucket with > 4096 points (global-memory rank-form replay) incl. exact cross-component ties; the
+    oracle side is the component model (proven equal to the literal O(N^3) restatement in the CPU suite)"""
+    import oracle_py as O
+    rng = np.random.RandomState(123)
+    for n, spread in ((5000, 40), (9000, 6)):
+        k = n // 12
+        cx = np.sort(rng.choice(np.arange(0, 40_000_000, 5000), k, replace=False)); cy = rng.randint(0, 40_000_000, k)
+        a = rng.randint(0, k, n)
+        x = (cx[a] + rng.randint(0, spread, n) * 7).astype(np.uint32); y = (cy[a] + rng.randint(0, spread, n) * 7).astype(np.uint32)
+        o = np.argsort(x, kind="stable"); x = np.ascontiguousarray(x[o]); y = np.ascontiguousarray(y[o])
+        ei, ec, er = O.cluster(0, x, y, 1243.15, model=True)
+        gi, gc, gr = ctx1.op_cluster(0, x, y, 1243.15)
+        assert np.array_equal(ei, gi) and np.array_equal(ec, gc) and er == gr, n
