@@ -22,7 +22,7 @@ struct Scratch {          // reusable device scratch for sorts / scans over `cap
 
 struct bkid_ctx {
   int device = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, st2 = nullptr;     // st2: side stream for work that overlaps the join (sd replay, max span)
   bkid_params prm;
   int nt = 0;
   std::vector<uint32_t> target_len;
@@ -64,7 +64,7 @@ struct bkid_ctx {
   long long n2 = 0;
   std::vector<int32_t> roots_per_bucket;
   // clusters
-  DBuf sdtab; bool sd_prepared = false; double sd_mean = 0;
+  DBuf sdtab, sdlut; bool sd_prepared = false; double sd_mean = 0;
   DBuf clusters, clusters_out, sarows, work, cov, depth, evoff, valid;
   const void *rows_ptr = nullptr; long long n_rows = 0, n_evcap = 0; int maxspan = 1; bool clusters_ranked = false;
   long long n_clusters = 0, n_called = 0;
@@ -73,6 +73,8 @@ struct bkid_ctx {
   bkid_timings tm;
   cudaEvent_t ev[16];
   cudaEvent_t ev_run[2];
+  cudaEvent_t ev_side[2];
+  bool maxspan_cached = false;
   long long launches0 = 0;
 };
 
@@ -504,8 +506,10 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   c->device = device;
   if (params) c->prm = *params; else bkid_default_params(&c->prm);
   if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { g_create_err = "cudaStreamCreate failed"; delete c; return nullptr; }
+  cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking);
   for (auto &ev : c->ev) cudaEventCreate(&ev);
   for (auto &ev : c->ev_run) cudaEventCreate(&ev);
+  for (auto &ev : c->ev_side) cudaEventCreate(&ev);
   c->nt = hdr->n_targets;
   for (int i = 0; i < c->nt; ++i) { c->target_len.push_back(hdr->target_len[i]); c->names.emplace_back(hdr->target_name[i]); }
   int nt = c->nt, m = nt + 1;
@@ -546,17 +550,19 @@ void bkid_destroy(bkid_ctx *c)
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->mtid, &c->mpos, &c->isize, &c->endpos, &c->nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->clusters, &c->clusters_out, &c->sarows, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
+                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   for (auto &ev : c->ev_run) cudaEventDestroy(ev);
+  for (auto &ev : c->ev_side) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->st2);
   cudaStreamDestroy(c->st);
   delete c;
 }
 
-static void invalidate(bkid_ctx *c) { c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; }
+static void invalidate(bkid_ctx *c) { c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; c->maxspan_cached = false; }
 
 static int reserve_impl(bkid_ctx *c, long long n, long long n_sa, long long n_cig, long long sa_b, long long oc_b)
 {
@@ -722,24 +728,27 @@ static int classify_impl(bkid_ctx *c)
 // exact continuation of the truncating sd accumulator over the local records, starting from t_in:
 // sd_prepare = the streaming pass that builds the per-block tables (independent of t_in),
 // sd_resolve_impl = the single-CTA exact walk from t_in.
-static int sd_prepare_impl(bkid_ctx *c, double mean)
+static int sd_prepare_impl(bkid_ctx *c, double mean, cudaStream_t st = nullptr)
 {
-  cudaStream_t st = c->st;
+  if (!st) st = c->st;
   long long n = c->n;
   c->sd_prepared = false;
   if (n <= 0 || c->cnt_insert <= 0) return 0;
   int nb = div_up(std::max<long long>(n, 1), SD_BLOCK);
   TRY(c, c->sdtab.ensure((size_t)nb * (8 + SD_K * 4 + 4 + 8) + 256, 0, st));
+  TRY(c, c->sdlut.ensure((size_t)SD_LUT * 8, 0, st));
   char *bp = (char *)c->sdtab.p;
   long long *blkF = (long long *)bp; bp += (size_t)nb * 8;
   double *blkA = (double *)bp; bp += (size_t)nb * 8;
   uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
   uint32_t *blkN = (uint32_t *)bp;
-  BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, blkF, blkCum, blkN, blkA);
+  BK_LAUNCH(sd_build_lut, SD_LUT / 256, 256, 0, st, mean, c->sdlut.as<unsigned long long>());
+  BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, c->sdlut.as<unsigned long long>(), blkF, blkCum, blkN, blkA);
   c->sd_prepared = true; c->sd_mean = mean;
   return 0;
 }
 
+static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *t_out);
 static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *t_out)
 {
   cudaStream_t st = c->st;
@@ -767,6 +776,57 @@ static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *
     TRY(c, sync_check(c));
   }
   *t_out = h[0];
+  return 0;
+}
+
+// side-stream version used by bkid_run: launch the sd replay and the max-span reduction on st2 so that they
+// overlap the distance-independent half of the join, collect later
+static int side_launch(bkid_ctx *c)
+{
+  cudaStream_t s2 = c->st2;
+  long long n = c->n;
+  c->mean = (double)c->sum_abs / (double)c->cnt_insert;                       // src/BreakID.cc:1941
+  cudaEventRecord(c->ev_side[0], s2);
+  if (n > 0 && c->cnt_insert > 0) {
+    TRY(c, sd_prepare_impl(c, c->mean, s2));
+    int nb = div_up(std::max<long long>(n, 1), SD_BLOCK);
+    char *bp = (char *)c->sdtab.p;
+    long long *blkF = (long long *)bp; bp += (size_t)nb * 8;
+    double *blkA = (double *)bp; bp += (size_t)nb * 8;
+    uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
+    uint32_t *blkN = (uint32_t *)bp;
+    long long *out = (long long *)(c->counters.as<unsigned>() + 8);
+    BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, s2, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, 0ll, out);
+  }
+  cudaEventRecord(c->ev_side[1], s2);
+  int *mx = (int *)(c->counters.as<unsigned>() + 44);
+  CU(c, cudaMemsetAsync(mx, 0, 4, s2));
+  if (n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, s2, c->p_pos, c->p_endpos, n, mx);
+  return 0;
+}
+
+static int side_collect(bkid_ctx *c)
+{
+  cudaStream_t s2 = c->st2;
+  long long n = c->n;
+  long long h[2] = {0, 0};
+  int maxspan = 0;
+  if (n > 0 && c->cnt_insert > 0) CU(c, cudaMemcpyAsync(h, c->counters.as<unsigned>() + 8, 16, cudaMemcpyDeviceToHost, s2));
+  CU(c, cudaMemcpyAsync(&maxspan, c->counters.as<unsigned>() + 44, 4, cudaMemcpyDeviceToHost, s2));
+  CU(c, cudaStreamSynchronize(s2));
+  CU(c, cudaGetLastError());
+  if (h[1]) {                                                                 // left the closed-form regime: literal replay
+    long long t = 0;
+    c->sd_prepared = false;
+    TRY(c, sd_partial_impl(c, c->mean, 0, &t));
+    h[0] = t;
+  }
+  float ms = 0; cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1]);
+  c->tm.insert_stats = ms;
+  c->sd_total = h[0];
+  c->sd = sqrt((double)c->sd_total / (double)c->cnt_insert);                  // :1946
+  c->have_stats = true;
+  c->maxspan = maxspan + 1; c->maxspan_cached = true;
   return 0;
 }
 
@@ -823,20 +883,18 @@ static int extract_candidates(bkid_ctx *c, unsigned long long index_offset)
   return 0;
 }
 
-// (2) mate join on a candidate array that is in global file order -> unordered pairs in c->pairs_tmp
-static int join_candidates(bkid_ctx *c, const bkid_cand *cand, long long nc, double w, long long *np_out)
+// (2) mate join on a candidate array that is in global file order -> unordered pairs in c->pairs_tmp.
+// join_presort needs no distance (sort by name hash, run detection); join_emit applies the discordance test.
+static int join_presort(bkid_ctx *c, const bkid_cand *cand, long long nc)
 {
   cudaStream_t st = c->st;
-  *np_out = 0;
   if (nc <= 0) return 0;
-  SubTimer T_(st);
   unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
   TRY(c, c->sc.ensure(nc + 8, st));
   uint64_t *key = c->sc.keys.as<uint64_t>();
   uint32_t *val = c->sc.vals.as<uint32_t>();
   BK_LAUNCH(k2_cand_keys, GRID1(nc, 256), 256, 0, st, cand, nc, key, val);
   bk::radix_sort_pairs(key, val, nc, 0, 64, c->sc.rt(), st);
-  T_.mark("join: radix sort 64b");
   uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
   int *errf = (int *)(c->counters.as<unsigned>() + 40);
   CU(c, cudaMemsetAsync(errf, 0, 4, st));
@@ -845,6 +903,18 @@ static int join_candidates(bkid_ctx *c, const bkid_cand *cand, long long nc, dou
   BK_LAUNCH(k2_run_starts, GRID1(nc, 256), 256, 0, st, head, hex, nc, rstart);
   size_t maxp = (size_t)nc / 2 + 1;
   TRY(c, c->pairs_tmp.ensure(maxp * sizeof(bkid_pair), 0, st));
+  return 0;
+}
+
+static int join_emit(bkid_ctx *c, const bkid_cand *cand, long long nc, double w, long long *np_out)
+{
+  cudaStream_t st = c->st;
+  *np_out = 0;
+  if (nc <= 0) return 0;
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  uint32_t *val = c->sc.vals.as<uint32_t>();
+  uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
+  int *errf = (int *)(c->counters.as<unsigned>() + 40);
   unsigned long long *pcount = tot + 1;
   CU(c, cudaMemsetAsync(pcount, 0, 8, st));
   BK_LAUNCH(k2_emit_pairs, GRID1(nc, 256), 256, 0, st, val, head, hex, rstart, nc, cand, c->d_cum.as<uint32_t>(), c->nt, c->d_bucket_rank.as<int32_t>(), w,
@@ -853,10 +923,15 @@ static int join_candidates(bkid_ctx *c, const bkid_cand *cand, long long nc, dou
   CU(c, cudaMemcpyAsync(&np, pcount, 8, cudaMemcpyDeviceToHost, st));
   CU(c, cudaMemcpyAsync(&herr, errf, 4, cudaMemcpyDeviceToHost, st));
   TRY(c, sync_check(c));
-  T_.mark("join: runs+emit");
   if (herr) return fail(c, BKID_ERR_HASH, "two different read names share a 64-bit hash prefix");
   *np_out = (long long)np;
   return 0;
+}
+
+static int join_candidates(bkid_ctx *c, const bkid_cand *cand, long long nc, double w, long long *np_out)
+{
+  TRY(c, join_presort(c, cand, nc));
+  return join_emit(c, cand, nc, w, np_out);
 }
 
 // (3) order pairs by (bucket rank, index of the second-seen mate), build buckets -> c->pairs0 ...
@@ -1122,7 +1197,7 @@ int bkid_refine(bkid_ctx *c, double dist, int64_t *n_called)
   cudaEventRecord(c->ev[13], st);
   if (c->n_clusters > 0) {
     TRY(c, refine_build_rows(c));
-    TRY(c, refine_local_maxspan(c, &c->maxspan));
+    if (!c->maxspan_cached) TRY(c, refine_local_maxspan(c, &c->maxspan));
     cudaEventRecord(c->ev[14], st);
     TRY(c, refine_coverage(c, dist));
     TRY(c, refine_vote(c));
@@ -1335,11 +1410,36 @@ int bkid_run(bkid_ctx *c, double *mean, double *sd, double *dist, int64_t *n_cal
   int rc;
   cudaSetDevice(c->device);
   cudaEventRecord(c->ev_run[0], c->st);
-  if ((rc = bkid_insert_stats(c, &m, &s)) != 0) return rc;
+  c->err.clear();
+  // classify; then the sd replay + max span run on the side stream while the main stream does the
+  // distance-independent half of the join (compaction, gather, sort by name hash, run detection)
+  if ((rc = classify_impl(c)) != 0) return rc;
+  int64_t np = 0, ncl, ncall;
+  if (c->have_stats) { m = c->mean; s = c->sd; }
+  else {
+    if ((rc = side_launch(c)) != 0) return rc;
+  }
+  cudaEventRecord(c->ev[6], c->st);
+  if ((rc = extract_candidates(c, 0ull)) != 0) return rc;
+  if ((rc = join_presort(c, c->cand.as<bkid_cand>(), c->n_cand)) != 0) return rc;
+  if (!c->have_stats && (rc = side_collect(c)) != 0) return rc;
+  m = c->mean; s = c->sd;
   int times = c->prm.times;
   double d = times * sqrt((double)times) * (m + c->prm.sd_mult * s);          // src/BreakID.cc:103
-  int64_t np, ncl, ncall;
-  if ((rc = bkid_scan(c, d, &np)) != 0) return rc;
+  {
+    long long npl = 0;
+    if ((rc = join_emit(c, c->cand.as<bkid_cand>(), c->n_cand, d, &npl)) != 0) return rc;
+    cudaEventRecord(c->ev[7], c->st);
+    if ((rc = set_pairs(c, c->pairs_tmp.as<bkid_pair>(), npl)) != 0) return rc;
+    cudaEventRecord(c->ev[8], c->st);
+    if ((rc = sync_check(c)) != 0) return rc;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]); c->tm.join = ms;
+    cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); c->tm.bucket_sort = ms;
+    c->tm.n_candidates = c->n_cand; c->tm.n_pairs = c->np0;
+    c->scanned = true; c->clustered = c->refined = false;
+    np = c->np0;
+  }
   if ((rc = bkid_cluster(c, d, c->prm.fast, &ncl)) != 0) return rc;
   if ((rc = bkid_refine(c, d, &ncall)) != 0) return rc;
   if (mean) *mean = m;

@@ -218,8 +218,27 @@ __device__ __forceinline__ void sd_elem(int isz, double mean, double &a, long lo
   }
 }
 
+// |isize| takes few distinct values, and floor(a), kmin depend on it alone once the mean is known: a 64 Ki
+// entry table (kmin in the top byte, floor(a) below; 512 KB, L2/L1 resident) turns the per-record FP64
+// arithmetic of the streaming pass into one lookup, which makes the pass HBM-bound again.
+constexpr int SD_LUT = 65536;
+__device__ __noinline__ unsigned long long sd_entry_slow(int isz, double mean)
+{
+  double a; long long fa; unsigned km;
+  sd_elem(isz, mean, a, fa, km);
+  return ((unsigned long long)km << 56) | ((unsigned long long)fa & 0x00ffffffffffffffull);
+}
+__global__ void sd_build_lut(double mean, unsigned long long *__restrict__ lut)
+{
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= SD_LUT) return;
+  double a; long long fa; unsigned km;
+  sd_elem(x, mean, a, fa, km);
+  lut[x] = ((unsigned long long)km << 56) | ((unsigned long long)fa & 0x00ffffffffffffffull);
+}
+
 __global__ void __launch_bounds__(SD_THREADS)
-sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean,
+sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, const unsigned long long *__restrict__ lut,
                long long *__restrict__ blkF, uint32_t *__restrict__ blkCum /*[nb][SD_K]*/, uint32_t *__restrict__ blkN, double *__restrict__ blkAmax)
 {
   __shared__ unsigned hist[SD_K];
@@ -229,9 +248,9 @@ sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isiz
   if (threadIdx.x < SD_K) hist[threadIdx.x] = 0;
   __syncthreads();
   long long base = (long long)blockIdx.x * SD_BLOCK;
-  unsigned long long F = 0;
+  unsigned long long F = 0, famax = 0;
   unsigned cnt = 0;
-  double amax = 0.0;
+  unsigned hot = 0;        // per-thread counts of the three hot bins 51 / 50 / 49, 10 bits each (<= 32 records per thread)
   for (int g = 0; g < SD_BLOCK / (SD_THREADS * 4); ++g) {
     long long i = base + (long long)g * (SD_THREADS * 4) + threadIdx.x * 4;
     unsigned char c[4];
@@ -245,16 +264,28 @@ sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isiz
       for (int k = 0; k < 4; ++k) { c[k] = (i + k < n) ? cls[i + k] : 0; s[k] = (i + k < n) ? isize[i + k] : 0; }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k) {
       if (c[k] & CL_INSERT) {
-        double a; long long fa; unsigned km;
-        sd_elem(s[k], mean, a, fa, km);
-        F += (unsigned long long)fa;
+        unsigned x = (unsigned)(s[k] < 0 ? -s[k] : s[k]);
+        unsigned long long e = (x < (unsigned)SD_LUT) ? __ldg(lut + x) : sd_entry_slow(s[k], mean);   // the slow path is a real call, not predicated code
+        unsigned long long fa = e & 0x00ffffffffffffffull;
+        unsigned km = (unsigned)(e >> 56);
+        F += fa;
         ++cnt;
-        amax = fmax(amax, a);
-        if (km != 255u) atomicAdd(&hist[km], 1u);
+        famax = fa > famax ? fa : famax;
+        hot += (km == 51u ? 1u : 0u) + (km == 50u ? (1u << 10) : 0u) + (km == 49u ? (1u << 20) : 0u);
+        if (km < 49u) atomicAdd(&hist[km], 1u);
       }
+    }
   }
+  hot = bk::warp_sum(hot);               // <= 1024 per field per warp: no carry between the 10-bit fields
+  if ((threadIdx.x & 31) == 0) {
+    unsigned h51 = hot & 1023u, h50 = (hot >> 10) & 1023u, h49 = hot >> 20;
+    if (h51) atomicAdd(&hist[51], h51);
+    if (h50) atomicAdd(&hist[50], h50);
+    if (h49) atomicAdd(&hist[49], h49);
+  }
+  double amax = (double)(famax + 1);          // upper bound of a: only used to bound the block's binade
   unsigned long long totF;
   bk::block_excl_scan<unsigned long long>(F, sh64, totF);
   unsigned totN;
@@ -269,9 +300,20 @@ sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isiz
     blkAmax[blockIdx.x] = m;
     blkF[blockIdx.x] = (long long)totF;
     blkN[blockIdx.x] = totN;
-    unsigned run = 0;
-    for (int k = 0; k < SD_K; ++k) { run += hist[k]; blkCum[(size_t)blockIdx.x * SD_K + k] = run; }
   }
+  // cumulative histogram by two warps (a serial 52-step loop on one thread used to be the longest part of the block)
+  if (threadIdx.x < 64) {
+    unsigned k = threadIdx.x;
+    unsigned v = k < SD_K ? hist[k] : 0u;
+    unsigned inc = bk::warp_incl_scan(v);
+    if (k == 31) sh32[0] = inc;
+    __syncwarp();
+    // the second warp adds the first warp's total after the barrier below
+    if (k < 32) blkCum[(size_t)blockIdx.x * SD_K + k] = inc;
+    else sh32[1 + (k - 32)] = inc;
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32 && threadIdx.x < SD_K) blkCum[(size_t)blockIdx.x * SD_K + threadIdx.x] = sh32[0] + sh32[1 + (threadIdx.x - 32)];
 }
 
 // single CTA, 1024 threads.  out[0] = sd_total, out[1] = out-of-regime flag.
@@ -554,7 +596,8 @@ __global__ void k2_bucket_ids(bkid_pair *__restrict__ pairs, const uint32_t *__r
 // run the literal heapsort on one thread.
 // =============================================================================================
 struct Seg { uint32_t f, l; int depth; };
-constexpr int IS_THREADS = 256;
+constexpr int IS_THREADS = 512;
+constexpr int IS_ITEMS = 4;
 constexpr uint32_t IS_SMALL = 1024;     // segments up to this size are finished by one warp in shared memory
 
 __device__ void seg_insertion_sort(uint32_t *key, uint32_t *val, uint32_t f, uint32_t l)
@@ -745,21 +788,30 @@ is_level(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__re
     __syncthreads();
     uint32_t pv = sh_p;
     uint32_t lo = f + 1, cnt = l - lo;
-    // L list: ascending positions with key >= pivot; R list: descending positions with key <= pivot
+    // L list: ascending positions with key >= pivot; R list: descending positions with key <= pivot.
+    // Each thread owns IS_ITEMS consecutive elements of a tile (from the left for L, from the right for R), so
+    // one pair of block scans covers IS_THREADS * IS_ITEMS elements.
     unsigned nL = 0, nR = 0;
-    for (uint32_t b = 0; b < cnt; b += IS_THREADS) {
-      uint32_t e = b + threadIdx.x;
-      unsigned isL = (e < cnt && !(key[lo + e] < pv)) ? 1u : 0u;
-      unsigned totL;
-      unsigned rl = bk::block_excl_scan<unsigned>(isL, sh32, totL);
-      if (isL) scrL[lo + nL + rl] = lo + e;
-      nL += totL;
-      uint32_t er = b + threadIdx.x;                       // e-th from the right
-      unsigned isR = (er < cnt && !(pv < key[l - 1 - er])) ? 1u : 0u;
-      unsigned totR;
-      unsigned rr = bk::block_excl_scan<unsigned>(isR, sh32, totR);
-      if (isR) scrR[lo + nR + rr] = l - 1 - er;
-      nR += totR;
+    for (uint32_t b = 0; b < cnt; b += IS_THREADS * IS_ITEMS) {
+      uint32_t e0 = b + threadIdx.x * IS_ITEMS;
+      unsigned mL = 0, mR = 0, cL = 0, cR = 0;
+#pragma unroll
+      for (int k = 0; k < IS_ITEMS; ++k) {
+        uint32_t e = e0 + k;
+        if (e < cnt) {
+          if (!(key[lo + e] < pv)) { mL |= 1u << k; ++cL; }
+          if (!(pv < key[l - 1 - e])) { mR |= 1u << k; ++cR; }
+        }
+      }
+      unsigned tot;
+      unsigned ex = bk::block_excl_scan<unsigned>(cL | (cR << 16), sh32, tot);     // both counts in one scan (tile <= 4096)
+      unsigned oL = nL + (ex & 0xffffu), oR = nR + (ex >> 16);
+#pragma unroll
+      for (int k = 0; k < IS_ITEMS; ++k) {
+        if (mL & (1u << k)) scrL[lo + oL++] = lo + e0 + k;
+        if (mR & (1u << k)) scrR[lo + oR++] = l - 1 - (e0 + k);
+      }
+      nL += tot & 0xffffu; nR += tot >> 16;
     }
     __syncthreads();
     // K = number of k with L[k] < R[k] (the predicate is true on a prefix)
