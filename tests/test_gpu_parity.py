@@ -313,3 +313,106 @@ def test_ahc_large_bucket_rank_form(ctx1):
         ei, ec, er = O.cluster(0, x, y, 1243.15, model=True)
         gi, gc, gr = ctx1.op_cluster(0, x, y, 1243.15)
         assert np.array_equal(ei, gi) and np.array_equal(ec, gc) and er == gr, n
+
+
+def _adversarial_sa_batch(seed, n=4000):
+    """records whose CIGAR / SA / OC fields exercise every branch of the split-read arithmetic: merged and
+    =/X ops, H/I/D/N ops, all-clip cigars, OC tags, multi-entry SA tags, leading zeros, minus strands, odd
+    chromosome names, duplicate / unpaired / secondary flags"""
+    from breakid_b200 import api
+    rng = np.random.RandomState(seed)
+    ops = "MIDNSHP=X"
+
+    def rand_cigar_text(simple):
+        if simple:
+            k = int(rng.randint(1, 149)); j = int(rng.randint(-12, 13))
+            pats = ["%dM%dS" % (k, 150 - k), "%dS%dM" % (150 - k, k), "%dS%dM" % (max(1, k + j), max(1, 150 - k - j)), "%dM%dS" % (max(1, 150 - k - j), max(1, k + j)),
+                    "0%dM%dS" % (k, 150 - k), "%dM%dM%dS" % (k // 2 + 1, k - k // 2, 150 - k), "%d=%dS" % (k, 150 - k), "%dX%dS" % (k, 150 - k), "%dS%dS" % (k, 150 - k)]
+            return pats[rng.randint(0, len(pats))]
+        return "".join("%d%s" % (rng.randint(0, 160), ops[rng.randint(0, len(ops))]) for _ in range(rng.randint(1, 5)))
+
+    def text_to_bam(t):
+        out, num = [], ""
+        for ch in t:
+            if ch.isdigit():
+                num += ch
+            else:
+                out.append((int(num or 0) << 4) | ops.index(ch)); num = ""
+        return out
+    tid = np.sort(rng.randint(0, 3, n)).astype(np.int32)
+    pos = np.zeros(n, np.int32)
+    for t in range(3):
+        m = tid == t
+        pos[m] = np.sort(rng.randint(0, 5000, m.sum()))
+    flag = rng.choice([99, 147, 355, 99 | 0x400, 98, 83, 163, 99 | 0x800, 355 | 0x10], n).astype(np.uint16)
+    names = rng.randint(0, n // 3, n)                         # names repeat: primary / 0x100 partners
+    nh = np.zeros(2 * n, np.uint64)
+    from breakid_b200 import synth
+    for i in range(n):
+        nh[2 * i], nh[2 * i + 1] = synth.name_hash_py(synth.name_of(int(names[i])))
+    sa_rec, cig_off, cig_ops, sa_off, sa_txt, oc_off, oc_txt = [], [0], [], [0], b"", [0], b""
+    endpos = pos + 1
+    chrs = ["chr1", "chr2", "chr3", "chrX", "chr07", "chrUn", "1"]
+    for i in range(n):
+        if rng.rand() < 0.6:
+            own = text_to_bam(rand_cigar_text(rng.rand() < 0.7))[:6] or [(100 << 4)]
+            sa_rec.append(i)
+            cig_ops += own; cig_off.append(len(cig_ops))
+            ref = sum(c >> 4 for c in own if (c & 15) in (0, 2, 3, 7, 8))
+            endpos[i] = pos[i] + ref if not (flag[i] & 4) else pos[i] + 1
+            ent = "%s,%s%d,%s,%s,60,0;" % (chrs[rng.randint(0, len(chrs))], "0" if rng.rand() < 0.05 else "", rng.randint(1, 6000), "+-"[rng.randint(0, 2)], rand_cigar_text(rng.rand() < 0.8))
+            if rng.rand() < 0.15:
+                ent += "chr2,77,+,50M100S,60,0;"
+            if rng.rand() < 0.03:
+                ent = "chr1,5"                                   # fewer than 4 fields: ignored
+            sa_txt += ent.encode(); sa_off.append(len(sa_txt))
+            if rng.rand() < 0.15:
+                oc_txt += rand_cigar_text(rng.rand() < 0.8).encode()
+            oc_off.append(len(oc_txt))
+    z = np.zeros(n, np.int32)
+    hb = api.HostBatch({"flag": flag, "mapq": np.full(n, 60, np.uint8), "tid": tid, "pos": pos, "mtid": tid, "mpos": pos, "isize": z, "endpos": endpos.astype(np.int32)}, nh,
+                       {"sa_rec": np.array(sa_rec, np.uint32), "cig_off": np.array(cig_off, np.uint32), "cig_ops": np.array(cig_ops, np.uint32), "sa_off": np.array(sa_off, np.uint32),
+                        "sa_txt": np.frombuffer(sa_txt, np.uint8), "oc_off": np.array(oc_off, np.uint32), "oc_txt": np.frombuffer(oc_txt or b"", np.uint8)},
+                       [10000, 10000, 10000], ["chr1", "chr2", "chr3"])
+    return hb
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sa_rows_adversarial_cigars(seed):
+    """CIGAR / SA-tag arithmetic on hostile inputs: device evidence rows == oracle rows, byte for byte"""
+    import torch
+    from breakid_b200.dist import GpuEngine
+    from oracle_engine import OracleEngine
+    hb = _adversarial_sa_batch(seed)
+    c = _ctx_for(hb)
+    got = GpuEngine(c, torch.device("cuda", 0)).sa_rows().cpu().numpy()
+    exp = OracleEngine(hb).sa_rows().numpy()
+    assert got.shape == exp.shape and got.shape[0] > 1000
+    bad = np.nonzero((got != exp).any(axis=1))[0]
+    assert len(bad) == 0, (len(bad), bad[:5], got[bad[:2]], exp[bad[:2]])
+    ok = got[:, 84]
+    assert ok.sum() > 50            # some rows are real evidence
+    c.close()
+
+
+def test_degenerate_inputs():
+    """empty batch, no candidates, no SA records: every stage returns cleanly with nothing to call"""
+    from breakid_b200 import api
+    z32 = np.zeros(0, np.int32)
+    empty = api.HostBatch({"flag": np.zeros(0, np.uint16), "mapq": np.zeros(0, np.uint8), "tid": z32, "pos": z32, "mtid": z32, "mpos": z32, "isize": z32, "endpos": z32},
+                          np.zeros(0, np.uint64), {"sa_rec": np.zeros(0, np.uint32), "cig_off": np.zeros(1, np.uint32), "cig_ops": np.zeros(0, np.uint32),
+                                                   "sa_off": np.zeros(1, np.uint32), "sa_txt": np.zeros(0, np.uint8)}, [1000, 2000], ["chr1", "chr2"])
+    c = _ctx_for(empty)
+    assert c.scan(100.0) == 0 and c.cluster(100.0, 0) == 0 and c.refine(100.0) == 0 and len(c.fetch_clusters()) == 0
+    c.close()
+    n = 5000
+    rng = np.random.RandomState(0)
+    pos = np.sort(rng.randint(0, 900, n)).astype(np.int32)
+    z = np.zeros(n, np.int32)
+    proper = api.HostBatch({"flag": np.full(n, 99, np.uint16), "mapq": np.full(n, 60, np.uint8), "tid": z, "pos": pos, "mtid": z, "mpos": pos + 200, "isize": np.full(n, 350, np.int32),
+                            "endpos": pos + 150}, np.arange(2 * n, dtype=np.uint64), {"sa_rec": np.zeros(0, np.uint32), "cig_off": np.zeros(1, np.uint32), "cig_ops": np.zeros(0, np.uint32),
+                                                                                    "sa_off": np.zeros(1, np.uint32), "sa_txt": np.zeros(0, np.uint8)}, [1000, 2000], ["chr1", "chr2"])
+    c = _ctx_for(proper)
+    mean, sd, dist, ncall = c.run()
+    assert (mean, sd) == (350.0, 0.0) and ncall == 0 and len(c.fetch_pairs(0)) == 0
+    c.close()
