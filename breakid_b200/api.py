@@ -28,8 +28,8 @@ class Params(C.Structure):
 
 class Batch(C.Structure):
     _fields_ = [("n", C.c_int64), ("flag", C.c_void_p), ("mapq", C.c_void_p),
-                ("tid", C.c_void_p), ("pos", C.c_void_p), ("mtid", C.c_void_p), ("mpos", C.c_void_p),
-                ("isize", C.c_void_p), ("endpos", C.c_void_p), ("name_hash", C.c_void_p),
+                ("tid", C.c_void_p), ("pos", C.c_void_p), ("isize", C.c_void_p), ("endpos", C.c_void_p),
+                ("n_x", C.c_int64), ("x_rec", C.c_void_p), ("x_mtid", C.c_void_p), ("x_mpos", C.c_void_p), ("x_name_hash", C.c_void_p),
                 ("n_sa", C.c_int64), ("sa_rec", C.c_void_p), ("cig_off", C.c_void_p), ("cig_ops", C.c_void_p),
                 ("sa_off", C.c_void_p), ("sa_txt", C.c_void_p), ("oc_off", C.c_void_p), ("oc_txt", C.c_void_p)]
 
@@ -72,22 +72,42 @@ class Timings(C.Structure):
 
 FUSION_TYPES = ["Unknown", "Translocation", "Inversion", "Duplication", "Deletion"]
 
-_COLS = (("flag", np.uint16), ("mapq", np.uint8), ("tid", np.int32), ("pos", np.int32), ("mtid", np.int32),
-         ("mpos", np.int32), ("isize", np.int32), ("endpos", np.int32))
+_COLS = (("flag", np.uint16), ("mapq", np.uint8), ("tid", np.int32), ("pos", np.int32), ("isize", np.int32), ("endpos", np.int32))
+_XCOLS = (("x_rec", np.uint32), ("x_mtid", np.int32), ("x_mpos", np.int32), ("x_name_hash", np.uint64))
 _SIDE = (("sa_rec", np.uint32), ("cig_off", np.uint32), ("cig_ops", np.uint32), ("sa_off", np.uint32),
          ("sa_txt", np.uint8), ("oc_off", np.uint32), ("oc_txt", np.uint8))
 
 
 class HostBatch:
-    """numpy-backed record batch + header; owns the arrays a ``Batch`` struct points to."""
+    """numpy-backed record batch + header; owns the arrays a ``Batch`` struct points to.
+
+    Built from dense per-record arrays (incl. ``mtid``, ``mpos`` and the [2n] ``name_hash``); the sparse
+    mate/name table of the C ABI (records that are not proper pairs or carry an SA tag) is derived here.
+    ``cols['mtid']``, ``cols['mpos']`` and ``name_hash`` stay available as dense arrays for the CPU oracle,
+    zeroed outside the sparse table (nothing on the path reads them there)."""
 
     def __init__(self, cols: Dict[str, np.ndarray], name_hash: np.ndarray, side: Dict[str, np.ndarray],
                  target_len: Sequence[int], target_names: Sequence[str]):
         self.cols = {k: np.ascontiguousarray(cols[k], dtype=dt) for k, dt in _COLS}
-        self.name_hash = np.ascontiguousarray(name_hash, dtype=np.uint64).reshape(-1)
         self.n = int(self.cols["flag"].shape[0])
-        assert self.name_hash.shape[0] == 2 * self.n
+        name_hash = np.ascontiguousarray(name_hash, dtype=np.uint64).reshape(-1)
+        assert name_hash.shape[0] == 2 * self.n
         n_sa = int(side["sa_rec"].shape[0]) if "sa_rec" in side else 0
+        in_x = (self.cols["flag"] & 2) == 0
+        if n_sa:
+            in_x[np.asarray(side["sa_rec"], dtype=np.int64)] = True
+        xr = np.nonzero(in_x)[0]
+        self.x = {"x_rec": xr.astype(np.uint32), "x_mtid": np.ascontiguousarray(np.asarray(cols["mtid"], np.int32)[xr]),
+                  "x_mpos": np.ascontiguousarray(np.asarray(cols["mpos"], np.int32)[xr]),
+                  "x_name_hash": np.ascontiguousarray(name_hash.reshape(-1, 2)[xr].reshape(-1))}
+        self.n_x = int(xr.shape[0])
+        for k in ("mtid", "mpos"):
+            dense = np.zeros(self.n, np.int32)
+            dense[xr] = self.x["x_" + k]
+            self.cols[k] = dense
+        nh = np.zeros((self.n, 2), np.uint64)
+        nh[xr] = self.x["x_name_hash"].reshape(-1, 2)
+        self.name_hash = nh.reshape(-1)
         side = dict(side)
         if "oc_off" not in side:
             side["oc_off"] = np.zeros(n_sa + 1, np.uint32)
@@ -103,7 +123,9 @@ class HostBatch:
         b.n = self.n
         for k, _ in _COLS:
             setattr(b, k, self.cols[k].ctypes.data)
-        b.name_hash = self.name_hash.ctypes.data
+        b.n_x = self.n_x
+        for k, _ in _XCOLS:
+            setattr(b, k, self.x[k].ctypes.data)
         b.n_sa = self.n_sa
         for k, _ in _SIDE:
             setattr(b, k, self.side[k].ctypes.data)
@@ -118,13 +140,13 @@ class HostBatch:
         return h
 
     def nbytes(self) -> int:
-        return sum(a.nbytes for a in self.cols.values()) + self.name_hash.nbytes + sum(a.nbytes for a in self.side.values())
+        return sum(self.cols[k].nbytes for k, _ in _COLS) + sum(a.nbytes for a in self.x.values()) + sum(a.nbytes for a in self.side.values())
 
     # -- constructors ----------------------------------------------------------------------
     @staticmethod
     def from_synth(d) -> "HostBatch":
         from . import synth
-        cols = {k: d.cols[k].cpu().numpy() for k, _ in _COLS if k != "flag"}
+        cols = {k: d.cols[k].cpu().numpy() for k in ("mapq", "tid", "pos", "mtid", "mpos", "isize", "endpos")}
         cols["flag"] = d.cols["flag"].cpu().numpy().view(np.uint16)
         nh = synth.name_hash_ids(d.cols["name_id"]).cpu().numpy().view(np.uint64).reshape(-1)
         side = {"sa_rec": d.sa_rec.cpu().numpy(), "cig_off": d.cig_off.cpu().numpy(),
@@ -151,7 +173,14 @@ class HostBatch:
                 return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (count * np.dtype(dt).itemsize,)).view(dt).copy()
 
             cols = {k: arr(getattr(b, k), n, dt) for k, dt in _COLS}
-            nh = arr(b.name_hash, 2 * n, np.uint64)
+            n_x = int(b.n_x)
+            xr = arr(b.x_rec, n_x, np.uint32).astype(np.int64)
+            for k in ("mtid", "mpos"):
+                cols[k] = np.zeros(n, np.int32)
+                cols[k][xr] = arr(getattr(b, "x_" + k), n_x, np.int32)
+            nh2 = np.zeros((n, 2), np.uint64)
+            nh2[xr] = arr(b.x_name_hash, 2 * n_x, np.uint64).reshape(-1, 2)
+            nh = nh2.reshape(-1)
             cig_off = arr(b.cig_off, n_sa + 1, np.uint32)
             sa_off = arr(b.sa_off, n_sa + 1, np.uint32)
             oc_off = arr(b.oc_off, n_sa + 1, np.uint32)
@@ -217,7 +246,7 @@ def cuda_lib():
         L.bkid_create.restype = vp
         L.bkid_create.argtypes = [C.c_int, C.POINTER(Header), C.POINTER(Params)]
         L.bkid_destroy.argtypes = [vp]
-        L.bkid_reserve.argtypes = [vp] + [C.c_int64] * 5
+        L.bkid_reserve.argtypes = [vp] + [C.c_int64] * 6
         L.bkid_push_batch.argtypes = [vp, C.POINTER(Batch)]
         L.bkid_push_batch_device.argtypes = [vp, C.POINTER(Batch)]
         L.bkid_reset.argtypes = [vp]
@@ -294,8 +323,8 @@ class Context:
         except Exception:
             pass
 
-    def reserve(self, n, n_sa=0, n_cig=0, sa_bytes=0, oc_bytes=0):
-        self._chk(self.lib.bkid_reserve(self.ctx, n, n_sa, n_cig, sa_bytes, oc_bytes))
+    def reserve(self, n, n_x=0, n_sa=0, n_cig=0, sa_bytes=0, oc_bytes=0):
+        self._chk(self.lib.bkid_reserve(self.ctx, n, n_x, n_sa, n_cig, sa_bytes, oc_bytes))
 
     def push(self, hb: HostBatch):
         b = hb.struct()

@@ -33,10 +33,12 @@ struct bkid_ctx {
   // resident record columns (file order)
   long long n = 0, cap_n = 0;
   bool borrowed = false;
-  DBuf flag, mapq, tid, pos, mtid, mpos, isize, endpos, nh, cls;
+  DBuf flag, mapq, tid, pos, isize, endpos, cls;
+  long long n_x = 0;
+  DBuf x_rec, x_mtid, x_mpos, x_nh;
   const uint16_t *p_flag = nullptr; const uint8_t *p_mapq = nullptr;
-  const int32_t *p_tid = nullptr, *p_pos = nullptr, *p_mtid = nullptr, *p_mpos = nullptr, *p_isize = nullptr, *p_endpos = nullptr;
-  const uint64_t *p_nh = nullptr;
+  const int32_t *p_tid = nullptr, *p_pos = nullptr, *p_isize = nullptr, *p_endpos = nullptr;
+  const uint32_t *p_x_rec = nullptr; const int32_t *p_x_mtid = nullptr, *p_x_mpos = nullptr; const uint64_t *p_x_nh = nullptr;
   // SA side table
   long long n_sa = 0, n_cig = 0, sa_bytes = 0, oc_bytes = 0;
   DBuf sa_rec, cig_off, cig_ops, sa_off, sa_txt, oc_off, oc_txt;
@@ -547,7 +549,7 @@ void bkid_destroy(bkid_ctx *c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
-  for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->mtid, &c->mpos, &c->isize, &c->endpos, &c->nh, &c->cls,
+  for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
                   &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
@@ -564,16 +566,17 @@ void bkid_destroy(bkid_ctx *c)
 
 static void invalidate(bkid_ctx *c) { c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; c->maxspan_cached = false; }
 
-static int reserve_impl(bkid_ctx *c, long long n, long long n_sa, long long n_cig, long long sa_b, long long oc_b)
+static int reserve_impl(bkid_ctx *c, long long n, long long n_x, long long n_sa, long long n_cig, long long sa_b, long long oc_b)
 {
   cudaStream_t st = c->st;
   if (c->borrowed) return fail(c, BKID_ERR_ARG, "context holds borrowed device columns; bkid_reset first");
   size_t k = (size_t)c->n;
   TRY(c, c->flag.ensure((size_t)n * 2 + 64, k * 2, st)); TRY(c, c->mapq.ensure((size_t)n + 64, k, st));
   TRY(c, c->tid.ensure((size_t)n * 4 + 64, k * 4, st)); TRY(c, c->pos.ensure((size_t)n * 4 + 64, k * 4, st));
-  TRY(c, c->mtid.ensure((size_t)n * 4 + 64, k * 4, st)); TRY(c, c->mpos.ensure((size_t)n * 4 + 64, k * 4, st));
   TRY(c, c->isize.ensure((size_t)n * 4 + 64, k * 4, st)); TRY(c, c->endpos.ensure((size_t)n * 4 + 64, k * 4, st));
-  TRY(c, c->nh.ensure((size_t)n * 16 + 64, k * 16, st));
+  size_t kx = (size_t)c->n_x;
+  TRY(c, c->x_rec.ensure((size_t)n_x * 4 + 64, kx * 4, st)); TRY(c, c->x_mtid.ensure((size_t)n_x * 4 + 64, kx * 4, st));
+  TRY(c, c->x_mpos.ensure((size_t)n_x * 4 + 64, kx * 4, st)); TRY(c, c->x_nh.ensure((size_t)n_x * 16 + 64, kx * 16, st));
   size_t s = (size_t)c->n_sa;
   TRY(c, c->sa_rec.ensure((size_t)n_sa * 4 + 64, s * 4, st));
   TRY(c, c->cig_off.ensure((size_t)(n_sa + 1) * 4 + 64, (s + 1) * 4, st));
@@ -585,11 +588,11 @@ static int reserve_impl(bkid_ctx *c, long long n, long long n_sa, long long n_ci
   return 0;
 }
 
-int bkid_reserve(bkid_ctx *c, int64_t n, int64_t n_sa, int64_t n_cig, int64_t sa_b, int64_t oc_b)
+int bkid_reserve(bkid_ctx *c, int64_t n, int64_t n_x, int64_t n_sa, int64_t n_cig, int64_t sa_b, int64_t oc_b)
 {
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device);
-  return reserve_impl(c, std::max<long long>(n, c->n), std::max<long long>(n_sa, c->n_sa), std::max<long long>(n_cig, c->n_cig),
+  return reserve_impl(c, std::max<long long>(n, c->n), std::max<long long>(n_x, c->n_x), std::max<long long>(n_sa, c->n_sa), std::max<long long>(n_cig, c->n_cig),
                       std::max<long long>(sa_b, c->sa_bytes), std::max<long long>(oc_b, c->oc_bytes));
 }
 
@@ -602,21 +605,21 @@ __global__ void add_offset_u32(uint32_t *p, long long n, uint32_t d)
 static void set_ptrs(bkid_ctx *c)
 {
   c->p_flag = c->flag.as<uint16_t>(); c->p_mapq = c->mapq.as<uint8_t>(); c->p_tid = c->tid.as<int32_t>(); c->p_pos = c->pos.as<int32_t>();
-  c->p_mtid = c->mtid.as<int32_t>(); c->p_mpos = c->mpos.as<int32_t>(); c->p_isize = c->isize.as<int32_t>(); c->p_endpos = c->endpos.as<int32_t>();
-  c->p_nh = c->nh.as<uint64_t>();
+  c->p_isize = c->isize.as<int32_t>(); c->p_endpos = c->endpos.as<int32_t>();
+  c->p_x_rec = c->x_rec.as<uint32_t>(); c->p_x_mtid = c->x_mtid.as<int32_t>(); c->p_x_mpos = c->x_mpos.as<int32_t>(); c->p_x_nh = c->x_nh.as<uint64_t>();
   c->p_sa_rec = c->sa_rec.as<uint32_t>(); c->p_cig_off = c->cig_off.as<uint32_t>(); c->p_cig_ops = c->cig_ops.as<uint32_t>();
   c->p_sa_off = c->sa_off.as<uint32_t>(); c->p_sa_txt = c->sa_txt.as<uint8_t>(); c->p_oc_off = c->oc_off.as<uint32_t>(); c->p_oc_txt = c->oc_txt.as<uint8_t>();
 }
 
 static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
 {
-  if (!c || !b || b->n < 0 || b->n_sa < 0) return c ? fail(c, BKID_ERR_ARG, "bad batch") : BKID_ERR_ARG;
+  if (!c || !b || b->n < 0 || b->n_sa < 0 || b->n_x < 0) return c ? fail(c, BKID_ERR_ARG, "bad batch") : BKID_ERR_ARG;
   cudaSetDevice(c->device);
   cudaStream_t st = c->st;
   if ((unsigned long long)(c->n + b->n) >= 0xffffffffull) return fail(c, BKID_ERR_ARG, "more than 2^32-1 records per context");
   invalidate(c);
   cudaEventRecord(c->ev[0], st);
-  long long n0 = c->n, s0 = c->n_sa;
+  long long n0 = c->n, s0 = c->n_sa, x0 = c->n_x;
   // side-table sizes need the last offsets of the incoming batch
   uint32_t ncig = 0, nsa_b = 0, noc_b = 0;
   if (b->n_sa > 0) {
@@ -627,18 +630,23 @@ static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
       CU(c, cudaMemcpy(&noc_b, b->oc_off + b->n_sa, 4, cudaMemcpyDeviceToHost));
     }
   }
-  TRY(c, reserve_impl(c, n0 + b->n, s0 + b->n_sa, c->n_cig + ncig, c->sa_bytes + nsa_b, c->oc_bytes + noc_b));
+  TRY(c, reserve_impl(c, n0 + b->n, x0 + b->n_x, s0 + b->n_sa, c->n_cig + ncig, c->sa_bytes + nsa_b, c->oc_bytes + noc_b));
   size_t n = (size_t)b->n;
   if (n) {
     CU(c, cudaMemcpyAsync(c->flag.as<uint16_t>() + n0, b->flag, n * 2, kind, st));
     CU(c, cudaMemcpyAsync(c->mapq.as<uint8_t>() + n0, b->mapq, n, kind, st));
     CU(c, cudaMemcpyAsync(c->tid.as<int32_t>() + n0, b->tid, n * 4, kind, st));
     CU(c, cudaMemcpyAsync(c->pos.as<int32_t>() + n0, b->pos, n * 4, kind, st));
-    CU(c, cudaMemcpyAsync(c->mtid.as<int32_t>() + n0, b->mtid, n * 4, kind, st));
-    CU(c, cudaMemcpyAsync(c->mpos.as<int32_t>() + n0, b->mpos, n * 4, kind, st));
     CU(c, cudaMemcpyAsync(c->isize.as<int32_t>() + n0, b->isize, n * 4, kind, st));
     CU(c, cudaMemcpyAsync(c->endpos.as<int32_t>() + n0, b->endpos, n * 4, kind, st));
-    CU(c, cudaMemcpyAsync(c->nh.as<uint64_t>() + 2 * n0, b->name_hash, n * 16, kind, st));
+  }
+  size_t nx = (size_t)b->n_x;
+  if (nx) {
+    CU(c, cudaMemcpyAsync(c->x_rec.as<uint32_t>() + x0, b->x_rec, nx * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->x_mtid.as<int32_t>() + x0, b->x_mtid, nx * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->x_mpos.as<int32_t>() + x0, b->x_mpos, nx * 4, kind, st));
+    CU(c, cudaMemcpyAsync(c->x_nh.as<uint64_t>() + 2 * x0, b->x_name_hash, nx * 16, kind, st));
+    if (n0) BK_LAUNCH(add_offset_u32, GRID1(nx, 256), 256, 0, st, c->x_rec.as<uint32_t>() + x0, (long long)nx, (uint32_t)n0);
   }
   size_t ns = (size_t)b->n_sa;
   if (ns) {
@@ -656,7 +664,7 @@ static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
   } else if (s0 == 0) {
     CU(c, cudaMemsetAsync(c->cig_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->sa_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->oc_off.p, 0, 4, st));
   }
-  c->n += b->n; c->n_sa += b->n_sa; c->n_cig += ncig; c->sa_bytes += nsa_b; c->oc_bytes += noc_b;
+  c->n += b->n; c->n_x += b->n_x; c->n_sa += b->n_sa; c->n_cig += ncig; c->sa_bytes += nsa_b; c->oc_bytes += noc_b;
   set_ptrs(c);
   cudaEventRecord(c->ev[1], st);
   TRY(c, sync_check(c));
@@ -676,9 +684,10 @@ int bkid_push_batch_device(bkid_ctx *c, const bkid_batch *b)
     if ((unsigned long long)b->n >= 0xffffffffull) return fail(c, BKID_ERR_ARG, "more than 2^32-1 records per context");
     invalidate(c);
     c->borrowed = true;
-    c->n = b->n; c->n_sa = b->n_sa;
-    c->p_flag = b->flag; c->p_mapq = b->mapq; c->p_tid = b->tid; c->p_pos = b->pos; c->p_mtid = b->mtid; c->p_mpos = b->mpos;
-    c->p_isize = b->isize; c->p_endpos = b->endpos; c->p_nh = b->name_hash;
+    c->n = b->n; c->n_sa = b->n_sa; c->n_x = b->n_x;
+    c->p_flag = b->flag; c->p_mapq = b->mapq; c->p_tid = b->tid; c->p_pos = b->pos;
+    c->p_isize = b->isize; c->p_endpos = b->endpos;
+    c->p_x_rec = b->x_rec; c->p_x_mtid = b->x_mtid; c->p_x_mpos = b->x_mpos; c->p_x_nh = b->x_name_hash;
     c->p_sa_rec = b->sa_rec; c->p_cig_off = b->cig_off; c->p_cig_ops = b->cig_ops; c->p_sa_off = b->sa_off; c->p_sa_txt = b->sa_txt;
     c->p_oc_off = b->oc_off; c->p_oc_txt = b->oc_txt;
     return 0;
@@ -691,7 +700,7 @@ int bkid_reset(bkid_ctx *c)
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
-  c->n = c->n_sa = c->n_cig = c->sa_bytes = c->oc_bytes = 0;
+  c->n = c->n_x = c->n_sa = c->n_cig = c->sa_bytes = c->oc_bytes = 0;
   c->borrowed = false;
   set_ptrs(c);
   invalidate(c);
@@ -877,8 +886,14 @@ static int extract_candidates(bkid_ctx *c, unsigned long long index_offset)
   if (nc > 0) {
     TRY(c, c->cand_idx.ensure((size_t)nc * 4 + 64, 0, st));
     BK_LAUNCH(k1_compact, (unsigned)ntiles, K1_THREADS, 0, st, c->cls.as<uint8_t>(), n, tile_off, c->cand_idx.as<uint32_t>());
-    BK_LAUNCH(k2_gather_cand, GRID1(nc, 256), 256, 0, st, c->cand_idx.as<uint32_t>(), (long long)nc, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_mtid, c->p_mpos,
-              c->p_nh, index_offset, c->cand.as<bkid_cand>());
+    int *miss = (int *)(c->counters.as<unsigned>() + 50);
+    CU(c, cudaMemsetAsync(miss, 0, 4, st));
+    BK_LAUNCH(k2_gather_cand, GRID1(nc, 256), 256, 0, st, c->cand_idx.as<uint32_t>(), (long long)nc, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_x_rec, c->n_x,
+              c->p_x_mtid, c->p_x_mpos, c->p_x_nh, index_offset, c->cand.as<bkid_cand>(), miss);
+    int hm = 0;
+    CU(c, cudaMemcpyAsync(&hm, miss, 4, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    if (hm) return fail(c, BKID_ERR_ARG, "a discordant-scan candidate is missing from the sparse mate/name table (x_rec must list every record that is not a proper pair)");
   }
   return 0;
 }
@@ -1070,9 +1085,18 @@ static int refine_build_rows(bkid_ctx *c)
   cudaStream_t st = c->st;
   TRY(c, classify_impl(c));
   TRY(c, c->sarows.ensure((size_t)(c->n_sa + 1) * sizeof(EvRow), 0, st));
-  if (c->n_sa > 0)
-    BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->p_flag, c->p_tid, c->p_pos, c->p_endpos, c->p_nh, c->p_cig_off, c->p_cig_ops,
-              c->p_sa_off, c->p_sa_txt, c->p_oc_off, c->p_oc_txt, c->prm.mismatch_num, c->sarows.as<EvRow>());
+  {
+    int *miss = (int *)(c->counters.as<unsigned>() + 50);
+    CU(c, cudaMemsetAsync(miss, 0, 4, st));
+    if (c->n_sa > 0) {
+      BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->p_flag, c->p_tid, c->p_pos, c->p_endpos, c->p_x_rec, c->n_x, c->p_x_nh, miss,
+                c->p_cig_off, c->p_cig_ops, c->p_sa_off, c->p_sa_txt, c->p_oc_off, c->p_oc_txt, c->prm.mismatch_num, c->sarows.as<EvRow>());
+      int hm = 0;
+      CU(c, cudaMemcpyAsync(&hm, miss, 4, cudaMemcpyDeviceToHost, st));
+      TRY(c, sync_check(c));
+      if (hm) return fail(c, BKID_ERR_ARG, "an SA-tagged record is missing from the sparse mate/name table");
+    }
+  }
   c->rows_ptr = c->sarows.as<EvRow>(); c->n_rows = c->n_sa;
   return 0;
 }

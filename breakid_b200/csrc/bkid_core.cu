@@ -453,16 +453,27 @@ __global__ void sd_sequential(const uint8_t *__restrict__ cls, const int32_t *__
 // candidate records are gathered once into a compact array (bkid_cand, 48 B): the sort, the run
 // detection and the pair emission then touch two coalesced 48-byte rows per pair instead of eleven
 // scattered column reads, and the same array is what ranks exchange in the multi-GPU path.
+// slot of record i in the sparse table (x_rec ascending), or -1
+__device__ __forceinline__ long long x_slot_of(const uint32_t *__restrict__ x_rec, long long n_x, uint32_t i)
+{
+  long long lo = 0, hi = n_x;
+  while (lo < hi) { long long m = (lo + hi) >> 1; if (x_rec[m] < i) lo = m + 1; else hi = m; }
+  return (lo < n_x && x_rec[lo] == i) ? lo : -1;
+}
+
 __global__ void k2_gather_cand(const uint32_t *__restrict__ cand_idx, long long nc, const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
-                               const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, const int32_t *__restrict__ mtid, const int32_t *__restrict__ mpos,
-                               const uint64_t *__restrict__ nh, unsigned long long index_offset, bkid_cand *__restrict__ out)
+                               const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, const uint32_t *__restrict__ x_rec, long long n_x,
+                               const int32_t *__restrict__ x_mtid, const int32_t *__restrict__ x_mpos, const uint64_t *__restrict__ x_nh,
+                               unsigned long long index_offset, bkid_cand *__restrict__ out, int *__restrict__ missing)
 {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nc) return;
   uint32_t i = cand_idx[p];
   bkid_cand c;
-  c.name_lo = nh[2 * (size_t)i]; c.name_hi = nh[2 * (size_t)i + 1];
-  c.tid = tid[i]; c.pos = pos[i]; c.mtid = mtid[i]; c.mpos = mpos[i];
+  long long x = x_slot_of(x_rec, n_x, i);
+  if (x < 0) { atomicExch(missing, 1); x = 0; if (n_x == 0) { memset(&c, 0, sizeof c); out[p] = c; return; } }
+  c.name_lo = x_nh[2 * (size_t)x]; c.name_hi = x_nh[2 * (size_t)x + 1];
+  c.tid = tid[i]; c.pos = pos[i]; c.mtid = x_mtid[x]; c.mpos = x_mpos[x];
   c.gidx = index_offset + i;
   c.flag = flag[i]; c.mapq = mapq[i];
   c._pad[0] = c._pad[1] = c._pad[2] = c._pad[3] = c._pad[4] = 0;

@@ -160,7 +160,8 @@ static_assert(sizeof(EvRow) == 88 || sizeof(EvRow) == 96, "EvRow layout");
 
 // K7a: one thread per SA-tagged record -- src/BreakID.cc:896-1016
 __global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long n_sa, const uint16_t *__restrict__ flag, const int32_t *__restrict__ tid,
-                                 const int32_t *__restrict__ pos, const int32_t *__restrict__ endpos, const uint64_t *__restrict__ nh, const uint32_t *__restrict__ cig_off, const uint32_t *__restrict__ cig_ops,
+                                 const int32_t *__restrict__ pos, const int32_t *__restrict__ endpos, const uint32_t *__restrict__ x_rec, long long n_x,
+                                 const uint64_t *__restrict__ x_nh, int *__restrict__ missing, const uint32_t *__restrict__ cig_off, const uint32_t *__restrict__ cig_ops,
                                  const uint32_t *__restrict__ sa_off, const uint8_t *__restrict__ sa_txt, const uint32_t *__restrict__ oc_off,
                                  const uint8_t *__restrict__ oc_txt, int mismatch, EvRow *__restrict__ rows)
 {
@@ -171,7 +172,11 @@ __global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long 
   uint32_t i = sa_rec[k];
   unsigned fl = flag[i];
   R.tid = tid[i]; R.pos = pos[i]; R.endpos = endpos[i];
-  R.name_lo = nh[2 * (size_t)i]; R.name_hi = nh[2 * (size_t)i + 1];
+  {
+    long long x = x_slot_of(x_rec, n_x, i);
+    if (x < 0) atomicExch(missing, 1);
+    else { R.name_lo = x_nh[2 * (size_t)x]; R.name_hi = x_nh[2 * (size_t)x + 1]; }
+  }
   const uint8_t *sa = sa_txt + sa_off[k]; uint32_t sal = sa_off[k + 1] - sa_off[k];
   const uint8_t *oc = oc_txt + oc_off[k]; uint32_t ocl = oc_off[k + 1] - oc_off[k];
   // split_string(sa, ",") drops empty fields (src/util_bed.cc:194-222): fields 0,1,3 of the first entry

@@ -69,8 +69,10 @@ struct bkid_host_bam {
   bkid_header hdr;
   std::vector<uint16_t> flag;
   std::vector<uint8_t> mapq;
-  std::vector<int32_t> tid, pos, mtid, mpos, isize, endpos;
-  std::vector<uint64_t> name_hash;
+  std::vector<int32_t> tid, pos, isize, endpos;
+  std::vector<uint32_t> x_rec;
+  std::vector<int32_t> x_mtid, x_mpos;
+  std::vector<uint64_t> x_name_hash;
   std::vector<uint32_t> sa_rec, cig_off, cig_ops, sa_off, oc_off;
   std::vector<uint8_t> sa_txt, oc_txt;
   int32_t first_l_qseq = 0;
@@ -160,10 +162,10 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
   }
   size_t n = rec.size();
   h->flag.resize(n); h->mapq.resize(n);
-  h->tid.resize(n); h->pos.resize(n); h->mtid.resize(n); h->mpos.resize(n); h->isize.resize(n); h->endpos.resize(n);
-  h->name_hash.resize(2 * n);
+  h->tid.resize(n); h->pos.resize(n); h->isize.resize(n); h->endpos.resize(n);
   // 5. columns (parallel) + per-thread SA side tables (merged in order afterwards)
-  struct Side { std::vector<uint32_t> rec, ncig, cig, salen, oclen; std::vector<uint8_t> sa, oc; };
+  struct Side { std::vector<uint32_t> rec, ncig, cig, salen, oclen; std::vector<uint8_t> sa, oc;
+                std::vector<uint32_t> xrec; std::vector<int32_t> xmtid, xmpos; std::vector<uint64_t> xhash; };
   int T = threads;
   std::vector<Side> sides(T);
   size_t chunk = (n + T - 1) / (T ? T : 1);
@@ -179,9 +181,8 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
         uint16_t n_cig = rd16(r + 16), fl = rd16(r + 18);
         int32_t l_seq = (int32_t)rd32(r + 20);
         h->tid[i] = tid; h->pos[i] = pos; h->mapq[i] = mq; h->flag[i] = fl;
-        h->mtid[i] = (int32_t)rd32(r + 24); h->mpos[i] = (int32_t)rd32(r + 28); h->isize[i] = (int32_t)rd32(r + 32);
+        h->isize[i] = (int32_t)rd32(r + 32);
         const char *qn = (const char *)(r + 36);
-        bkid_name_hash(qn, &h->name_hash[2 * i], &h->name_hash[2 * i + 1]);
         const uint8_t *cg = r + 36 + l_name;
         int32_t rlen = 0;
         for (uint32_t k = 0; k < n_cig; ++k) {
@@ -216,7 +217,14 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
           }
           a = v + len;
         }
-        if (sa && sa[0]) {                       // saTag() != "" (src/BreakID.cc:896-898)
+        bool has_sa = sa && sa[0];
+        if (!(fl & 0x2) || has_sa) {             // sparse table: mate fields + name hash only where they can ever be read
+          uint64_t lo, hi;
+          bkid_name_hash(qn, &lo, &hi);
+          S.xrec.push_back((uint32_t)i); S.xmtid.push_back((int32_t)rd32(r + 24)); S.xmpos.push_back((int32_t)rd32(r + 28));
+          S.xhash.push_back(lo); S.xhash.push_back(hi);
+        }
+        if (has_sa) {                            // saTag() != "" (src/BreakID.cc:896-898)
           S.rec.push_back((uint32_t)i);
           S.ncig.push_back(n_cig);
           for (uint32_t k = 0; k < n_cig; ++k) S.cig.push_back(rd32(cg + 4 * k));
@@ -243,6 +251,10 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
     }
     h->sa_txt.insert(h->sa_txt.end(), S.sa.begin(), S.sa.end());
     h->oc_txt.insert(h->oc_txt.end(), S.oc.begin(), S.oc.end());
+    h->x_rec.insert(h->x_rec.end(), S.xrec.begin(), S.xrec.end());
+    h->x_mtid.insert(h->x_mtid.end(), S.xmtid.begin(), S.xmtid.end());
+    h->x_mpos.insert(h->x_mpos.end(), S.xmpos.begin(), S.xmpos.end());
+    h->x_name_hash.insert(h->x_name_hash.end(), S.xhash.begin(), S.xhash.end());
   }
   for (auto &s : h->names) h->name_ptrs.push_back(s.c_str());
   h->hdr.n_targets = (int32_t)h->names.size();
@@ -251,8 +263,10 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
   bkid_batch &B = h->batch;
   B.n = (int64_t)n;
   B.flag = h->flag.data(); B.mapq = h->mapq.data();
-  B.tid = h->tid.data(); B.pos = h->pos.data(); B.mtid = h->mtid.data(); B.mpos = h->mpos.data();
-  B.isize = h->isize.data(); B.endpos = h->endpos.data(); B.name_hash = h->name_hash.data();
+  B.tid = h->tid.data(); B.pos = h->pos.data();
+  B.isize = h->isize.data(); B.endpos = h->endpos.data();
+  B.n_x = (int64_t)h->x_rec.size();
+  B.x_rec = h->x_rec.data(); B.x_mtid = h->x_mtid.data(); B.x_mpos = h->x_mpos.data(); B.x_name_hash = h->x_name_hash.data();
   B.n_sa = (int64_t)h->sa_rec.size();
   B.sa_rec = h->sa_rec.data(); B.cig_off = h->cig_off.data(); B.cig_ops = h->cig_ops.data();
   B.sa_off = h->sa_off.data(); B.sa_txt = h->sa_txt.data();

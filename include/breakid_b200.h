@@ -59,18 +59,26 @@ typedef struct {
 } bkid_params;
 
 /* One struct-of-arrays batch of decoded alignment records, in BAM file order.  All pointers are
- * borrowed for the duration of the call.  Per-record columns are exactly the bam1_core_t fields
- * the reference reads (htslib sam.h:148-157) + bam_endpos (htslib sam.c:344-350) + a 128-bit hash
- * of the read name (bkid_name_hash) which replaces std::string equality in the mate join
- * (src/BreakID.cc:1424) and the split-read name match (src/BreakID.cc:605).
- * Records carrying an SA:Z tag additionally appear in the side table with their raw BAM cigar ops
+ * borrowed for the duration of the call.  Dense per-record columns (19 B/record) are the bam1_core_t
+ * fields every record needs (htslib sam.h:148-157) + bam_endpos (htslib sam.c:344-350).
+ * The mate fields and the 128-bit read-name hash (bkid_name_hash; it replaces std::string equality in
+ * the mate join, src/BreakID.cc:1424, and the split-read name match, src/BreakID.cc:605) are only ever
+ * read for records that can become discordant candidates or split-read evidence, so they travel in a
+ * SPARSE table: the host lists every record that is not a proper pair (flag & 0x2 clear -- a superset of
+ * the candidate predicate src/BreakID.cc:1419-1420) or carries an SA tag, ~1 % of a normal BAM.  The
+ * device re-derives the candidate predicate itself and fails with BKID_ERR_ARG if a candidate is missing
+ * from the table.
+ * Records carrying an SA:Z tag additionally appear in the SA side table with their raw BAM cigar ops
  * and the raw SA / OC tag text; all CIGAR / SA arithmetic happens on the device. */
 typedef struct {
   int64_t n;
   const uint16_t *flag;
   const uint8_t *mapq;
-  const int32_t *tid, *pos, *mtid, *mpos, *isize, *endpos;
-  const uint64_t *name_hash;        /* [2n]: lo, hi */
+  const int32_t *tid, *pos, *isize, *endpos;
+  int64_t n_x;                      /* sparse table of improper / SA-tagged records */
+  const uint32_t *x_rec;            /* [n_x] ascending batch-local record index */
+  const int32_t *x_mtid, *x_mpos;   /* [n_x] */
+  const uint64_t *x_name_hash;      /* [2 n_x]: lo, hi */
   int64_t n_sa;
   const uint32_t *sa_rec;           /* [n_sa] ascending batch-local record index */
   const uint32_t *cig_off;          /* [n_sa+1] into cig_ops */
@@ -154,7 +162,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
 void bkid_destroy(bkid_ctx *ctx);
 
 /* optional capacity hint so pushes never reallocate */
-int bkid_reserve(bkid_ctx *ctx, int64_t n_records, int64_t n_sa, int64_t n_cig_ops, int64_t sa_bytes, int64_t oc_bytes);
+int bkid_reserve(bkid_ctx *ctx, int64_t n_records, int64_t n_x, int64_t n_sa, int64_t n_cig_ops, int64_t sa_bytes, int64_t oc_bytes);
 /* replaces: the samread / sam_read1 loops (src/BreakID.cc:1414,1929) as the producer of records.
  * Host pointers; the host->device copy happens inside (pinned staging, async). */
 int bkid_push_batch(bkid_ctx *ctx, const bkid_batch *batch);

@@ -37,7 +37,7 @@ def test_pod_layouts_match_header():
     from breakid_b200 import api
     assert api.PAIR_DTYPE.itemsize == 64 and api.CLUSTER_DTYPE.itemsize == 192
     import ctypes
-    assert ctypes.sizeof(api.Batch) == 18 * 8 and ctypes.sizeof(api.Params) == 32
+    assert ctypes.sizeof(api.Batch) == 20 * 8 and ctypes.sizeof(api.Params) == 32
 
 
 def test_host_bam_decoder_roundtrip(tmp_path):
@@ -53,6 +53,9 @@ def test_host_bam_decoder_roundtrip(tmp_path):
         for k in a.cols:
             assert np.array_equal(a.cols[k], b.cols[k]), k
         assert np.array_equal(a.name_hash, b.name_hash)
+        assert a.n_x == b.n_x and 0 < a.n_x < a.n // 10
+        for k in a.x:
+            assert np.array_equal(a.x[k], b.x[k]), k
         for k in a.side:
             assert np.array_equal(a.side[k], b.side[k]), k
         assert b.target_names == ["chr1", "chr2"] and list(b.target_len) == [80000, 50000]
