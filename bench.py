@@ -139,6 +139,50 @@ def workload_cfg(scale):
     return synth.config2(scale=scale)
 
 
+def measured_traffic(kernel, n_records):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/*.json written by
+    tools/summarise_profiles.py), scaled per record to this run's launch; None when no capture is committed."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_top_kernels.json"))):
+        try:
+            k = json.load(open(p))["kernels"].get(kernel)
+            if k and k.get("dram_bytes_per_record"):
+                best = (k["dram_bytes_per_record"] * n_records, os.path.basename(p))
+        except Exception:
+            pass
+    return best
+
+
+def split_read_stress(local, dev, steps, scale):
+    """BASELINE.json configs[4] (split-read refinement stress) as a second, short leg: 1000 x scale hotspots with
+    5000 split reads each (1e7 x scale SA-tagged records), clip lengths U(20,130), +-3 bp breakpoint jitter.
+    Reports split reads refined per second = SA-tagged records / (evidence + refine stage time)."""
+    cfg = synth.config5(scale=scale)
+    d = synth.generate(cfg, device=str(dev))
+    names = [synth.chrom_name(t) for t in range(len(cfg.chrom_lens))]
+    b_dev, keep = device_batch(d)
+    n, n_sa = d.n, int(d.sa_rec.numel())
+    del d
+    torch.cuda.empty_cache()
+    ctx = api.Context(cfg.chrom_lens, names, device=local)
+    ev_ms = rf_ms = tot = 0.0
+    for i in range(3 + steps):
+        ctx.reset()
+        ctx.push_device(b_dev)
+        res = ctx.run()
+        tm = ctx.timings()
+        if i >= 3:
+            ev_ms += tm["evidence"]; rf_ms += tm["refine"]; tot += tm["total"]
+    ctx.close()
+    del keep
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE.json configs[4] x scale %g: %d records, %d SA-tagged, %d hotspots called" % (scale, n, n_sa, int(res[3])),
+            "value": n_sa / ((ev_ms + rf_ms) / steps * 1e-3), "unit": "split reads refined/s",
+            "evidence_ms": ev_ms / steps, "refine_ms": rf_ms / steps, "whole_step_ms": tot / steps,
+            "n_evidence": int(tm["n_evidence"]), "steps": steps}
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -255,6 +299,8 @@ def run_ours(args):
     k1_ms = stage["classify"] / args.steps
     k1_bytes = 8.0 * n                                    # flag 2 + mapq 1 + isize 4 read, class 1 written
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    traffic = measured_traffic("k1_classify", n)
+    sr_ms = (stage["evidence"] + stage["refine"]) / args.steps
     line = {
         "metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/i64 integer + f64 (AHC distances)",
@@ -265,10 +311,13 @@ def run_ours(args):
         "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
                 "note": "decode excluded: pinned host SoA batch -> bkid_push_batch -> bkid_run -> bkid_fetch_clusters"},
         "gpu_launches": int(launches),
+        "split_reads": {"value": (n_sa * world / (sr_ms * 1e-3)) if sr_ms > 0 else None, "unit": "split reads refined/s",
+                        "note": "SA-tagged records of this workload / (evidence + refine stage time); the stress workload is in split_read_stress"},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
         "counts": counts,
         "roofline": {"bound": "hbm", "kernel": "k1_classify", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_record": 8},
+                     "traffic": (traffic[0] if traffic else None), "traffic_source": (traffic[1] if traffic else None),
+                     "peak_source": peak_src, "algorithmic_bytes_per_record": 8, "algorithmic_bytes_per_launch": k1_bytes},
         "clocks": clk.summary(),
         "gen_seconds": gen_s,
     }
@@ -276,11 +325,15 @@ def run_ours(args):
         tot = sum(shard_timing.values())
         for k, v in shard_timing.items():
             print("[shard-timing] %-28s %8.3f ms/step" % (k, v / args.steps), file=sys.stderr)
+    ctx.close()
+    del hkeep, b_host
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_stress:
+        line["split_read_stress"] = split_read_stress(local, dev, max(1, min(args.steps, 3)), args.stress_scale)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_port(args)
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -345,6 +398,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nib", action="store_true", help="also upload a random 4-bit genome so 41-mers are produced")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the configs[4] split-read stress leg")
+    ap.add_argument("--stress-scale", type=float, default=1.0, help="fraction of the 1e7-SA-record stress workload")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -22,7 +22,7 @@ struct Scratch {          // reusable device scratch for sorts / scans over `cap
 
 struct bkid_ctx {
   int device = 0;
-  cudaStream_t st = nullptr, st2 = nullptr;     // st2: side stream for work that overlaps the join (sd replay, max span)
+  cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;     // st2: side stream for the sd replay (overlaps the join); st3: max span (needed only by the refinement)
   bkid_params prm;
   int nt = 0;
   std::vector<uint32_t> target_len;
@@ -67,7 +67,7 @@ struct bkid_ctx {
   std::vector<int32_t> roots_per_bucket;
   // clusters
   DBuf sdtab, sdlut; bool sd_prepared = false; double sd_mean = 0;
-  DBuf clusters, clusters_out, sarows, work, cov, depth, evoff, valid;
+  DBuf clusters, clusters_out, sarows, work, cov, depth, evoff, valid, name_key, name_row;
   const void *rows_ptr = nullptr; long long n_rows = 0, n_evcap = 0; int maxspan = 1; bool clusters_ranked = false;
   long long n_clusters = 0, n_called = 0;
   Scratch sc;
@@ -76,7 +76,7 @@ struct bkid_ctx {
   cudaEvent_t ev[16];
   cudaEvent_t ev_run[2];
   cudaEvent_t ev_side[2];
-  bool maxspan_cached = false;
+  bool maxspan_cached = false, maxspan_pending = false;   // pending: max_span_kernel in flight on st3
   long long launches0 = 0;
 };
 
@@ -509,6 +509,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   if (params) c->prm = *params; else bkid_default_params(&c->prm);
   if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { g_create_err = "cudaStreamCreate failed"; delete c; return nullptr; }
   cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking);
   for (auto &ev : c->ev) cudaEventCreate(&ev);
   for (auto &ev : c->ev_run) cudaEventCreate(&ev);
   for (auto &ev : c->ev_side) cudaEventCreate(&ev);
@@ -552,7 +553,7 @@ void bkid_destroy(bkid_ctx *c)
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
+                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();
@@ -560,11 +561,12 @@ void bkid_destroy(bkid_ctx *c)
   for (auto &ev : c->ev_run) cudaEventDestroy(ev);
   for (auto &ev : c->ev_side) cudaEventDestroy(ev);
   cudaStreamDestroy(c->st2);
+  cudaStreamDestroy(c->st3);
   cudaStreamDestroy(c->st);
   delete c;
 }
 
-static void invalidate(bkid_ctx *c) { c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; c->maxspan_cached = false; }
+static void invalidate(bkid_ctx *c) { if (c->maxspan_pending) { cudaStreamSynchronize(c->st3); c->maxspan_pending = false; } c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; c->maxspan_cached = false; }
 
 static int reserve_impl(bkid_ctx *c, long long n, long long n_x, long long n_sa, long long n_cig, long long sa_b, long long oc_b)
 {
@@ -808,9 +810,11 @@ static int side_launch(bkid_ctx *c)
     BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, s2, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, 0ll, out);
   }
   cudaEventRecord(c->ev_side[1], s2);
+  // the max reference span bounds the region-query windows of the refinement only: its own stream, collected there
   int *mx = (int *)(c->counters.as<unsigned>() + 44);
-  CU(c, cudaMemsetAsync(mx, 0, 4, s2));
-  if (n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, s2, c->p_pos, c->p_endpos, n, mx);
+  CU(c, cudaMemsetAsync(mx, 0, 4, c->st3));
+  if (n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, c->st3, c->p_pos, c->p_endpos, n, mx);
+  c->maxspan_pending = true;
   return 0;
 }
 
@@ -819,9 +823,7 @@ static int side_collect(bkid_ctx *c)
   cudaStream_t s2 = c->st2;
   long long n = c->n;
   long long h[2] = {0, 0};
-  int maxspan = 0;
   if (n > 0 && c->cnt_insert > 0) CU(c, cudaMemcpyAsync(h, c->counters.as<unsigned>() + 8, 16, cudaMemcpyDeviceToHost, s2));
-  CU(c, cudaMemcpyAsync(&maxspan, c->counters.as<unsigned>() + 44, 4, cudaMemcpyDeviceToHost, s2));
   CU(c, cudaStreamSynchronize(s2));
   CU(c, cudaGetLastError());
   if (h[1]) {                                                                 // left the closed-form regime: literal replay
@@ -835,7 +837,17 @@ static int side_collect(bkid_ctx *c)
   c->sd_total = h[0];
   c->sd = sqrt((double)c->sd_total / (double)c->cnt_insert);                  // :1946
   c->have_stats = true;
-  c->maxspan = maxspan + 1; c->maxspan_cached = true;
+  return 0;
+}
+
+static int maxspan_collect(bkid_ctx *c)
+{
+  if (!c->maxspan_pending) return 0;
+  int maxspan = 0;
+  CU(c, cudaMemcpyAsync(&maxspan, c->counters.as<unsigned>() + 44, 4, cudaMemcpyDeviceToHost, c->st3));
+  CU(c, cudaStreamSynchronize(c->st3));
+  CU(c, cudaGetLastError());
+  c->maxspan = maxspan + 1; c->maxspan_cached = true; c->maxspan_pending = false;
   return 0;
 }
 
@@ -1104,6 +1116,7 @@ static int refine_build_rows(bkid_ctx *c)
 static int refine_local_maxspan(bkid_ctx *c, int *out)
 {
   cudaStream_t st = c->st;
+  if (c->maxspan_pending) { TRY(c, maxspan_collect(c)); *out = c->maxspan; return 0; }
   int *mx = (int *)(c->counters.as<unsigned>() + 44);
   CU(c, cudaMemsetAsync(mx, 0, 4, st));
   if (c->n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, st, c->p_pos, c->p_endpos, c->n, mx);
@@ -1119,6 +1132,7 @@ static RefineView refine_view(bkid_ctx *c)
   RefineView v;
   v.n = c->n; v.cls = c->cls.as<uint8_t>(); v.tid = c->p_tid; v.pos = c->p_pos; v.endpos = c->p_endpos;
   v.n_sa = c->n_rows; v.rows = (const EvRow *)c->rows_ptr; v.maxspan = c->maxspan;
+  v.name_key = c->name_key.as<uint64_t>(); v.name_row = c->name_row.as<uint32_t>();
   v.canon = c->d_canon.as<uint64_t>(); v.nt = c->nt;
   v.nib = (const uint8_t *const *)c->d_nib_ptr.p; v.nib_len = c->d_nib_len.as<uint64_t>();
   return v;
@@ -1156,6 +1170,14 @@ static int refine_vote(bkid_ctx *c)
   cudaStream_t st = c->st;
   uint32_t ncl = (uint32_t)c->n_clusters;
   if (ncl == 0) return 0;
+  // evidence rows ordered by read-name hash (pairing looks a split read's other half up by name)
+  TRY(c, c->sc.ensure(std::max<long long>(ncl, c->n_rows) + 8, st));
+  TRY(c, c->name_key.ensure((size_t)(c->n_rows + 1) * 8, 0, st));
+  TRY(c, c->name_row.ensure((size_t)(c->n_rows + 1) * 4, 0, st));
+  if (c->n_rows > 0) {
+    BK_LAUNCH(k7_name_keys, GRID1(c->n_rows, 256), 256, 0, st, (const EvRow *)c->rows_ptr, c->n_rows, c->name_key.as<uint64_t>(), c->name_row.as<uint32_t>());
+    bk::radix_sort_pairs(c->name_key.as<uint64_t>(), c->name_row.as<uint32_t>(), c->n_rows, 0, 32, c->sc.rt(), st);
+  }
   RefineView v = refine_view(c);
   unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
   ClusterWork *work = c->work.as<ClusterWork>();
@@ -1177,6 +1199,14 @@ static int refine_vote(bkid_ctx *c)
   BK_LAUNCH((k7_collect<true>), ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, c->cov.as<uint32_t>(), c->evoff.as<uint32_t>(),
             c->tmpC.as<uint32_t>(), entoff, c->tmpD.as<int2>());
   BK_LAUNCH(k8_vote, ncl, RF_THREADS, 0, st, c->clusters.as<bkid_cluster_rec>(), ncl, work, entoff, c->tmpD.as<int2>(), c->prm.bp_pos_error, c->valid.as<uint32_t>());
+  if (nent > K8_SMALL) {                                                   // only then can a cluster be heavy
+    TRY(c, c->tmpE.ensure((size_t)(nent + 1) * 8, 0, st));
+    TRY(c, c->tmpF.ensure((size_t)(nent + 1) * 4, 0, st));
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k8_vote_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K8_BIG_SMEM_KEYS * 8)); attr_set = true; }
+    BK_LAUNCH(k8_vote_big, ncl, K8_BIG_THREADS, K8_BIG_SMEM_KEYS * 8, st, c->clusters.as<bkid_cluster_rec>(), ncl, work, entoff, c->tmpD.as<int2>(), c->tmpE.as<uint64_t>(),
+              c->tmpF.as<uint32_t>(), c->prm.bp_pos_error, c->valid.as<uint32_t>());
+  }
   c->tm.n_evidence = (long long)nent;
   return 0;
 }
@@ -1221,6 +1251,7 @@ int bkid_refine(bkid_ctx *c, double dist, int64_t *n_called)
   cudaEventRecord(c->ev[13], st);
   if (c->n_clusters > 0) {
     TRY(c, refine_build_rows(c));
+    TRY(c, maxspan_collect(c));
     if (!c->maxspan_cached) TRY(c, refine_local_maxspan(c, &c->maxspan));
     cudaEventRecord(c->ev[14], st);
     TRY(c, refine_coverage(c, dist));

@@ -270,6 +270,7 @@ struct RefineView {
   long long n; const uint8_t *cls; const int32_t *tid, *pos, *endpos;
   // global SA-row table in coordinate order (evidence)
   long long n_sa; const EvRow *rows;
+  const uint64_t *name_key; const uint32_t *name_row;   // rows ordered by the low 32 bits of name_lo (evidence pairing)
   int maxspan;
   const uint64_t *canon;            // [nt] chr_code of the header names
   int nt;
@@ -405,19 +406,33 @@ k7_collect(RefineView v, const bkid_cluster_rec *__restrict__ cl, uint32_t ncl, 
   __syncthreads();
   uint64_t p1code = (cl[c].p1_tid >= 0 && cl[c].p1_tid < v.nt) ? v.canon[cl[c].p1_tid] : chr_code((const uint8_t *)"*", 1);
   if (n1 > 0 && n2 > 0) {
-    // the reference walks names in map order, then i over side 1, j over side 2; the vote only needs the multiset
-    for (uint32_t a = threadIdx.x; a < n1; a += blockDim.x)
-      for (uint32_t b = 0; b < n2; ++b)
-        if (ev_match(v, l1[a], l2[b])) {
+    // the reference walks names in map order, then i over side 1, j over side 2 (src/BreakID.cc:603-760); the vote
+    // only needs the multiset of matching (a in side 1, b in side 2) pairs.  A match needs equal read names, so
+    // b is looked up through the name-ordered row index instead of scanning all of side 2: side-2 membership is
+    // the region predicate itself (row window, iterator overlap rule, complementary cigars).
+    const RegionQ &Q2 = W.q2;
+    for (uint32_t a = threadIdx.x; a < n1; a += blockDim.x) {
+      uint32_t ra = l1[a];
+      const EvRow &A = v.rows[ra];
+      uint32_t key = (uint32_t)A.name_lo;
+      long long lo = 0, hi = v.n_sa;
+      while (lo < hi) { long long mid = (lo + hi) >> 1; if ((uint32_t)v.name_key[mid] < key) lo = mid + 1; else hi = mid; }
+      for (long long j = lo; j < v.n_sa && (uint32_t)v.name_key[j] == key; ++j) {
+        uint32_t rb = v.name_row[j];
+        if ((long long)rb < Q2.s_lo || (long long)rb >= Q2.s_hi) continue;
+        const EvRow &B = v.rows[rb];
+        if (!(B.endpos > Q2.beg && B.ok)) continue;
+        if (ev_match(v, ra, rb)) {
           unsigned o = atomicAdd(&sh_cnt, 1u);
           if (WRITE) {
-            const EvRow &A = v.rows[l1[a]];
             int2 e;
             if (A.pchr == p1code) { e.x = (int)A.pbp; e.y = (int)A.sbp; }       // :647,671-672
             else { e.x = (int)A.sbp; e.y = (int)A.pbp; }                         // :717-718
             entries[ent_off[c] + o] = e;
           }
         }
+      }
+    }
   }
   __syncthreads();
   if (!WRITE && threadIdx.x == 0) W.n_entries = sh_cnt;
@@ -465,6 +480,10 @@ __device__ __forceinline__ char nib_base(const uint8_t *packed, uint64_t nbases,
   switch (x) { case 0: case 8: return 'T'; case 1: case 9: return 'C'; case 2: case 10: return 'A'; case 3: case 11: return 'G'; default: return 'N'; }
 }
 
+constexpr uint32_t K8_SMALL = 256;      // clusters with more evidence entries go through k8_vote_big
+constexpr int K8_BIG_THREADS = 256;
+constexpr uint32_t K8_BIG_SMEM_KEYS = 8192;
+
 // K8: vote.  One CTA per cluster; writes exact positions / votes and valid[c].
 __global__ void __launch_bounds__(RF_THREADS)
 k8_vote(bkid_cluster_rec *__restrict__ cl, uint32_t ncl, const ClusterWork *__restrict__ work, const uint32_t *__restrict__ ent_off,
@@ -473,6 +492,7 @@ k8_vote(bkid_cluster_rec *__restrict__ cl, uint32_t ncl, const ClusterWork *__re
   uint32_t c = blockIdx.x;
   if (c >= ncl) return;
   uint32_t m = work[c].n_entries;
+  if (m > K8_SMALL) return;                                               // k8_vote_big
   const int2 *E = entries + ent_off[c];
   // votes: entries within +-bp_err of each key, mixed int32/uint32 compares (:820-821)
   int my_best = 0, mx = -1, my = -1;
@@ -501,6 +521,104 @@ k8_vote(bkid_cluster_rec *__restrict__ cl, uint32_t ncl, const ClusterWork *__re
     valid[c] = ok ? 1u : 0u;
     if (ok) { cl[c].p1_exact_pos = (uint32_t)x; cl[c].p2_exact_pos = y; cl[c].n_split_read = b; }
   }
+}
+
+// K8 for heavy clusters (split-read hotspots): the reference counts identical "x,y" keys in a std::map and
+// then sums, for every key, the counts of all keys within +-bp_err (src/BreakID.cc:806-855).  Same structure
+// here: CTA-wide bitonic sort of the entries (shared memory up to 8192 entries, in place in global memory
+// beyond), unique keys with multiplicities, then the vote over unique keys with an x-window binary search.
+__global__ void __launch_bounds__(K8_BIG_THREADS)
+k8_vote_big(bkid_cluster_rec *__restrict__ cl, uint32_t ncl, const ClusterWork *__restrict__ work, const uint32_t *__restrict__ ent_off,
+            int2 *__restrict__ entries, uint64_t *__restrict__ uniq, uint32_t *__restrict__ ustart, int bp_err, uint32_t *__restrict__ valid)
+{
+  extern __shared__ uint64_t k8_sh[];
+  uint32_t c = blockIdx.x;
+  if (c >= ncl) return;
+  uint32_t m = work[c].n_entries;
+  if (m <= K8_SMALL) return;
+  uint64_t *G = reinterpret_cast<uint64_t *>(entries + ent_off[c]);
+  uint64_t *U = uniq + ent_off[c];
+  uint32_t *S0 = ustart + ent_off[c];
+  const bool in_sh = m <= K8_BIG_SMEM_KEYS;
+  uint64_t *K = in_sh ? k8_sh : G;
+  // key = (uint32 x) << 32 | (uint32 y)
+  for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+    int2 e = reinterpret_cast<const int2 *>(G)[i];
+    K[i] = ((uint64_t)(uint32_t)e.x << 32) | (uint32_t)e.y;
+  }
+  __syncthreads();
+  uint32_t P = 1; while (P < m) P <<= 1;
+  for (uint32_t k = 2; k <= P; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      bool flip = (j == (k >> 1));
+      for (uint32_t t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        uint32_t i = 2 * t - (t & (j - 1));
+        uint32_t p = flip ? (i ^ (2 * j - 1)) : (i + j);
+        if (p < m) {                                   // out-of-range slots are +inf: never swapped down
+          uint64_t a = K[i], b = K[p];
+          if (a > b) { K[i] = b; K[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // unique keys in order + first index of each run
+  __shared__ unsigned sh32[33];
+  __shared__ unsigned sh_nu;
+  unsigned base = 0;
+  for (uint32_t i0 = 0; i0 < m; i0 += blockDim.x) {
+    uint32_t i = i0 + threadIdx.x;
+    unsigned head = (i < m && (i == 0 || K[i] != K[i - 1])) ? 1u : 0u;
+    unsigned tot;
+    unsigned r = bk::block_excl_scan<unsigned>(head, sh32, tot);
+    if (head) { U[base + r] = K[i]; S0[base + r] = i; }
+    base += tot;
+  }
+  if (threadIdx.x == 0) sh_nu = base;
+  __syncthreads();
+  uint32_t nu = sh_nu;
+  uint32_t e = (uint32_t)bp_err;
+  int my_best = 0, mx = -1, my = -1;
+  for (uint32_t i = threadIdx.x; i < nu; i += blockDim.x) {
+    uint32_t k1 = (uint32_t)(U[i] >> 32), k2 = (uint32_t)U[i];
+    uint32_t jlo = 0, jhi = nu;
+    if (k1 >= e && k1 <= 0xffffffffu - e) {             // no uint32 wrap: the x condition is a contiguous key range
+      uint64_t lo_key = (uint64_t)(k1 - e) << 32, hi_key = ((uint64_t)(k1 + e) << 32) | 0xffffffffull;
+      uint32_t lo = 0, hi = nu;
+      while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (U[mid] < lo_key) lo = mid + 1; else hi = mid; }
+      jlo = lo; hi = nu;
+      while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (U[mid] <= hi_key) lo = mid + 1; else hi = mid; }
+      jhi = lo;
+    }
+    int cnt = 0;
+    for (uint32_t j = jlo; j < jhi; ++j) {
+      uint32_t a = (uint32_t)(U[j] >> 32), b = (uint32_t)U[j];
+      if (a <= k1 + e && a >= k1 - e && b <= k2 + e && b >= k2 - e) cnt += (int)(((j + 1 < nu) ? S0[j + 1] : m) - S0[j]);
+    }
+    if (cnt > my_best || (cnt == my_best && cnt > 0 && key_less((int)k1, (int)k2, mx, my))) { my_best = cnt; mx = (int)k1; my = (int)k2; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    int oc = __shfl_xor_sync(0xffffffffu, my_best, o), ox = __shfl_xor_sync(0xffffffffu, mx, o), oy = __shfl_xor_sync(0xffffffffu, my, o);
+    if (oc > my_best || (oc == my_best && oc > 0 && key_less(ox, oy, mx, my))) { my_best = oc; mx = ox; my = oy; }
+  }
+  __shared__ int wb[K8_BIG_THREADS / 32], wx[K8_BIG_THREADS / 32], wy[K8_BIG_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) { wb[threadIdx.x >> 5] = my_best; wx[threadIdx.x >> 5] = mx; wy[threadIdx.x >> 5] = my; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int b = 0, x = -1, y = -1;
+    for (int q = 0; q < K8_BIG_THREADS / 32; ++q)
+      if (wb[q] > b || (wb[q] == b && b > 0 && key_less(wx[q], wy[q], x, y))) { b = wb[q]; x = wx[q]; y = wy[q]; }
+    bool ok = b >= 2;                                                     // :446
+    valid[c] = ok ? 1u : 0u;
+    if (ok) { cl[c].p1_exact_pos = (uint32_t)x; cl[c].p2_exact_pos = y; cl[c].n_split_read = b; }
+  }
+}
+
+// name index: key = name_lo of every evidence row, value = row number (sorted on the low 32 bits afterwards)
+__global__ void k7_name_keys(const EvRow *__restrict__ rows, long long n, uint64_t *__restrict__ key, uint32_t *__restrict__ val)
+{
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { key[i] = rows[i].name_lo; val[i] = (uint32_t)i; }
 }
 
 // K9 partial: depth at both break points of every valid cluster on the local record shard

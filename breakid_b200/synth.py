@@ -65,6 +65,8 @@ class SynthConfig:
     dup_frac: float = 0.05
     lowq_frac: float = 0.05          # fraction of improper records with MAPQ < 20
     sv_jitter: int = 0               # +-jitter on split-read breakpoints (exercises the +-2 vote)
+    split_k_min: Optional[int] = None  # bases on the A side of a split read: U[split_k_min, split_k_max)
+    split_k_max: Optional[int] = None  # (defaults L/2+1 .. L-20; config 5 uses 20 .. 131 = clip lengths U(20,130))
     min_sv_sep: int = 6000
     seed: int = 1
     n_pairs: Optional[int] = None    # override coverage-derived pair count
@@ -294,7 +296,8 @@ def generate(cfg: SynthConfig, device="cpu") -> SynthData:
         s = cfg.split_per_sv
         sv = torch.arange(n_sv, device=dev).repeat_interleave(s)
         ns = sv.numel()
-        k = randint(L // 2 + 1, L - 20, ns)                         # bases on the A side
+        k = randint(cfg.split_k_min if cfg.split_k_min is not None else L // 2 + 1,
+                    cfg.split_k_max if cfg.split_k_max is not None else L - 20, ns)   # bases on the A side
         jit = randint(-cfg.sv_jitter, cfg.sv_jitter + 1, ns) if cfg.sv_jitter else torch.zeros(ns, dtype=torch.int64, device=dev)
         aa = a[sv] + jit
         bb = b[sv] + jit
@@ -495,3 +498,21 @@ def config2(scale: float = 1.0, seed: int = 2) -> SynthConfig:
     lens = [max(200000, int(l * scale)) for l in HG19_LENS]
     nsv = max(8, int(2000 * scale))
     return SynthConfig(chrom_lens=lens, n_tra=nsv // 4, n_inv=nsv // 4, n_dup=nsv // 4, n_del=nsv - 3 * (nsv // 4), seed=seed)
+
+
+def config4(scale: float = 1.0, seed: int = 4) -> SynthConfig:
+    """BASELINE.json configs[3]: tumour-shaped 100x BAM with 500 planted translocations (gene fusions; the
+    annotation path runs on the host over a synthetic refGene, ``write_refgene``)."""
+    lens = [max(200000, int(l * scale)) for l in HG19_LENS]
+    return SynthConfig(chrom_lens=lens, coverage=100.0, n_tra=max(4, int(500 * scale)), n_inv=0, n_dup=0, n_del=0,
+                       span_per_sv=40, split_per_sv=20, seed=seed)
+
+
+def config5(scale: float = 1.0, seed: int = 5, split_per_sv: int = 5000) -> SynthConfig:
+    """BASELINE.json configs[4]: split-read refinement stress.  1000 x scale breakpoint hotspots, each with
+    ``split_per_sv`` split reads (2 SA-tagged records per split read => 1e7 SA-tagged records at scale 1), clip
+    lengths U(20,130) on 150 bp reads, breakpoints jittered +-3 bp (exercises the +-2 vote), thin 2x background."""
+    lens = [max(200000, int(l * scale)) for l in HG19_LENS]
+    nsv = max(4, int(1000 * scale))
+    return SynthConfig(chrom_lens=lens, coverage=2.0, n_tra=nsv // 4, n_inv=nsv // 4, n_dup=nsv // 4, n_del=nsv - 3 * (nsv // 4),
+                       split_per_sv=split_per_sv, sv_jitter=3, split_k_min=20, split_k_max=131, seed=seed)

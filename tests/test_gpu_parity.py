@@ -416,3 +416,42 @@ def test_degenerate_inputs():
     mean, sd, dist, ncall = c.run()
     assert (mean, sd) == (350.0, 0.0) and ncall == 0 and len(c.fetch_pairs(0)) == 0
     c.close()
+
+
+@pytest.mark.parametrize("split_per_sv,scale", [(40, 0.004), (700, 0.004), (4500, 0.002)])
+def test_split_read_hotspots_config5(split_per_sv, scale):
+    """BASELINE.json configs[4] shape (reduced): breakpoint hotspots with hundreds to thousands of split reads each,
+    clip lengths U(20,130), breakpoints jittered +-3 bp.  40 -> per-entry vote, 700 -> shared-memory sort/unique vote,
+    4500 (x2 sides > 8192 entries never happens, but > 256 uniques does not either: the global-memory sort is
+    forced separately in test_vote_big_many_uniques)."""
+    import oracle_py as O
+    from breakid_b200 import api, synth
+    cfg = synth.config5(scale=scale, split_per_sv=split_per_sv)
+    d = synth.generate(cfg)
+    hb = api.HostBatch.from_synth(d)
+    c = _ctx_for(hb)
+    mean, sd, dist, ncall = c.run()
+    got = c.fetch_clusters()
+    om, osd, od, exp = O.run(hb, None, mode=0)
+    assert (mean, sd, dist) == (om, osd, od)
+    assert got.tobytes() == exp.tobytes()
+    assert len(got) >= 4 and int(got["n_split_read"].max()) > split_per_sv // 2
+    c.close()
+
+
+def test_vote_big_many_uniques():
+    """one hotspot whose split reads are spread over +-60 bp: thousands of evidence entries with hundreds of
+    distinct (bp1,bp2) keys -> exercises the windowed vote over unique keys and key-string tie breaking."""
+    import oracle_py as O
+    from breakid_b200 import api, synth
+    cfg = synth.SynthConfig(chrom_lens=[400000, 300000], coverage=2.0, n_tra=1, n_inv=1, n_dup=0, n_del=1,
+                            split_per_sv=9000, sv_jitter=60, split_k_min=20, split_k_max=131, seed=77)
+    d = synth.generate(cfg)
+    hb = api.HostBatch.from_synth(d)
+    c = _ctx_for(hb)
+    mean, sd, dist, ncall = c.run()
+    got = c.fetch_clusters()
+    om, osd, od, exp = O.run(hb, None, mode=0)
+    assert got.tobytes() == exp.tobytes()
+    assert len(got) == 3
+    c.close()
