@@ -212,6 +212,14 @@ def host_lib():
         L.bkid_host_bam_batch.restype = C.c_void_p
         L.bkid_host_bam_batch.argtypes = [C.c_void_p]
         L.bkid_host_bam_free.argtypes = [C.c_void_p]
+        L.bkid_host_bgzf_open.restype = C.c_void_p
+        L.bkid_host_bgzf_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        for f, rt in (("header", C.c_void_p), ("data", C.c_void_p), ("size", C.c_uint64), ("blocks", C.c_void_p), ("n_blocks", C.c_int64),
+                      ("first_record", C.c_uint64), ("usize", C.c_uint64), ("first_l_qseq", C.c_int32)):
+            fn = getattr(L, "bkid_host_bgzf_" + f)
+            fn.restype = rt
+            fn.argtypes = [C.c_void_p]
+        L.bkid_host_bgzf_close.argtypes = [C.c_void_p]
         _host = L
     return _host
 
@@ -224,7 +232,8 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_insert_partial", "bkid_shard_sd_prepare", "bkid_shard_sd_partial", "bkid_shard_set_stats", "bkid_shard_candidates", "bkid_shard_join",
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
-           "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy"]
+           "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
+           "bkid_push_bgzf", "bkid_get_decode_stats", "bkid_fetch_column"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -249,6 +258,9 @@ def cuda_lib():
         L.bkid_reserve.argtypes = [vp] + [C.c_int64] * 6
         L.bkid_push_batch.argtypes = [vp, C.POINTER(Batch)]
         L.bkid_push_batch_device.argtypes = [vp, C.POINTER(Batch)]
+        L.bkid_push_bgzf.argtypes = [vp, vp, vp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
+        L.bkid_get_decode_stats.argtypes = [vp, C.POINTER(DecodeStats)]
+        L.bkid_fetch_column.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.bkid_reset.argtypes = [vp]
         L.bkid_insert_stats.argtypes = [vp, dp, dp]
         L.bkid_scan.argtypes = [vp, C.c_double, i64p]
@@ -291,6 +303,52 @@ class BkidError(RuntimeError):
     pass
 
 
+class BgzfBlock(C.Structure):
+    _fields_ = [("payload_off", C.c_uint64), ("payload_len", C.c_uint32), ("usize", C.c_uint32)]
+
+
+class DecodeStats(C.Structure):
+    _fields_ = [("n_chunks", C.c_int64), ("n_blocks", C.c_int64), ("compressed_bytes", C.c_int64), ("uncompressed_bytes", C.c_int64),
+                ("n_records", C.c_int64), ("total_ms", C.c_float), ("inflate_ms", C.c_float), ("boundaries_ms", C.c_float),
+                ("extract_ms", C.c_float), ("seed_repairs", C.c_int32), ("reserved", C.c_int32)]
+
+
+class BgzfFile:
+    """Host half of the device decode path: mapped BAM file + BGZF block table + parsed BAM header
+    (``bkid_host_bgzf_open``, breakid_b200/host/bam_reader.h)."""
+
+    def __init__(self, path: str):
+        self.lib = host_lib()
+        err = C.create_string_buffer(256)
+        self.h = self.lib.bkid_host_bgzf_open(path.encode(), err, 256)
+        if not self.h:
+            raise IOError("bkid_host_bgzf_open: " + err.value.decode())
+        hd = C.cast(self.lib.bkid_host_bgzf_header(self.h), C.POINTER(Header)).contents
+        self.target_len = [int(hd.target_len[i]) for i in range(hd.n_targets)]
+        self.target_names = [hd.target_name[i].decode() for i in range(hd.n_targets)]
+        self.data = self.lib.bkid_host_bgzf_data(self.h)
+        self.size = int(self.lib.bkid_host_bgzf_size(self.h))
+        self.blocks = self.lib.bkid_host_bgzf_blocks(self.h)
+        self.n_blocks = int(self.lib.bkid_host_bgzf_n_blocks(self.h))
+        self.first_record = int(self.lib.bkid_host_bgzf_first_record(self.h))
+        self.usize = int(self.lib.bkid_host_bgzf_usize(self.h))
+
+    def block_table(self) -> np.ndarray:
+        dt = np.dtype([("payload_off", np.uint64), ("payload_len", np.uint32), ("usize", np.uint32)])
+        return np.ctypeslib.as_array(C.cast(self.blocks, C.POINTER(C.c_uint8)), (self.n_blocks * 16,)).view(dt).copy()
+
+    def close(self):
+        if self.h:
+            self.lib.bkid_host_bgzf_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One device context (``bkid_ctx``)."""
 
@@ -329,6 +387,29 @@ class Context:
     def push(self, hb: HostBatch):
         b = hb.struct()
         self._chk(self.lib.bkid_push_batch(self.ctx, C.byref(b)))
+
+    def push_bgzf(self, f: "BgzfFile", data_ptr=None, blocks=None, n_blocks=None, first_record=None) -> int:
+        """device BGZF inflate + BAM decode of a whole file (``bkid_push_bgzf``); returns the record count.
+        ``data_ptr`` overrides the mapped file with another host copy of the same bytes (e.g. a pinned buffer)."""
+        n = C.c_int64()
+        self._chk(self.lib.bkid_push_bgzf(self.ctx, C.c_void_p(data_ptr if data_ptr is not None else f.data),
+                                          C.c_void_p(blocks if blocks is not None else f.blocks),
+                                          f.n_blocks if n_blocks is None else n_blocks,
+                                          f.first_record if first_record is None else first_record, C.byref(n)))
+        return int(n.value)
+
+    def decode_stats(self) -> dict:
+        s = DecodeStats()
+        self._chk(self.lib.bkid_get_decode_stats(self.ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in DecodeStats._fields_ if k != "reserved"}
+
+    def fetch_column(self, name: str, dtype) -> np.ndarray:
+        nb = C.c_int64()
+        self._chk(self.lib.bkid_fetch_column(self.ctx, name.encode(), None, 0, C.byref(nb)))
+        out = np.zeros(int(nb.value) // np.dtype(dtype).itemsize, dtype)
+        if nb.value:
+            self._chk(self.lib.bkid_fetch_column(self.ctx, name.encode(), out.ctypes.data_as(C.c_void_p), int(nb.value), C.byref(nb)))
+        return out
 
     def push_device(self, b: Batch):
         self._chk(self.lib.bkid_push_batch_device(self.ctx, C.byref(b)))

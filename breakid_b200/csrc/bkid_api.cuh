@@ -20,7 +20,11 @@ struct Scratch {          // reusable device scratch for sorts / scans over `cap
   void release() { for (DBuf *b : {&keys, &keys_alt, &vals, &vals_alt, &hist, &scan_tmp, &a32, &b32, &c32, &d32, &e32}) b->release(); }
 };
 
+struct bkid_decoder;
+static void decoder_free(bkid_ctx *c);
+
 struct bkid_ctx {
+  bkid_decoder *dec = nullptr;              // streaming BGZF/BAM decode state (bkid_bamdec.cuh)
   int device = 0;
   cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;     // st2: side stream for the sd replay (overlaps the join); st3: max span (needed only by the refinement)
   bkid_params prm;
@@ -550,6 +554,7 @@ void bkid_destroy(bkid_ctx *c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
+  decoder_free(c);
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,

@@ -277,3 +277,99 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
 extern "C" const bkid_header *bkid_host_bam_header(const bkid_host_bam *h) { return &h->hdr; }
 extern "C" const bkid_batch *bkid_host_bam_batch(const bkid_host_bam *h) { return &h->batch; }
 extern "C" void bkid_host_bam_free(bkid_host_bam *h) { delete h; }
+
+// ---- host half of the device decode path ----------------------------------------------------------------
+struct bkid_host_bgzf {
+  const uint8_t *file = nullptr; size_t fsz = 0;
+  std::vector<bkid_bgzf_block> blocks;
+  std::vector<uint32_t> target_len;
+  std::vector<std::string> names;
+  std::vector<const char *> name_ptrs;
+  bkid_header hdr;
+  uint64_t first_record = 0, usize = 0;
+  int32_t first_l_qseq = -1;
+};
+
+extern "C" bkid_host_bgzf *bkid_host_bgzf_open(const char *path, char *err, int errlen)
+{
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_err(err, errlen, std::string("cannot open ") + path); return nullptr; }
+  struct stat st;
+  fstat(fd, &st);
+  size_t fsz = (size_t)st.st_size;
+  const uint8_t *file = (const uint8_t *)mmap(nullptr, fsz, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (file == MAP_FAILED) { set_err(err, errlen, "mmap failed"); return nullptr; }
+  bkid_host_bgzf *h = new bkid_host_bgzf();
+  h->file = file; h->fsz = fsz;
+  auto bail = [&](const char *msg) -> bkid_host_bgzf * { set_err(err, errlen, msg); munmap((void *)file, fsz); delete h; return nullptr; };
+  size_t off = 0;
+  while (off + 18 <= fsz) {
+    const uint8_t *p = file + off;
+    if (p[0] != 0x1f || p[1] != 0x8b) return bail("not a BGZF file");
+    uint16_t xlen = rd16(p + 10);
+    uint32_t bsize = 0;
+    for (uint32_t x = 0; x + 4 <= xlen;) {
+      const uint8_t *q = p + 12 + x;
+      uint16_t slen = rd16(q + 2);
+      if (q[0] == 'B' && q[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(q + 4) + 1;
+      x += 4 + slen;
+    }
+    if (!bsize || off + bsize > fsz || bsize < 12u + xlen + 8u) return bail("corrupt BGZF block");
+    bkid_bgzf_block b;
+    b.payload_off = off + 12 + xlen; b.payload_len = bsize - 12 - xlen - 8; b.usize = rd32(p + bsize - 4);
+    h->blocks.push_back(b);
+    h->usize += b.usize;
+    off += bsize;
+  }
+  if (off != fsz) return bail("trailing bytes after the last BGZF block");
+  // BAM header: inflate leading blocks until it is complete
+  std::vector<uint8_t> u;
+  size_t nb = 0;
+  auto need = [&](size_t bytes) -> bool {
+    while (u.size() < bytes && nb < h->blocks.size()) {
+      const bkid_bgzf_block &b = h->blocks[nb++];
+      size_t o = u.size();
+      u.resize(o + b.usize);
+      if (b.usize) {
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) return false;
+        zs.next_in = const_cast<uint8_t *>(file + b.payload_off); zs.avail_in = b.payload_len;
+        zs.next_out = u.data() + o; zs.avail_out = b.usize;
+        int r = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (r != Z_STREAM_END || zs.total_out != b.usize) return false;
+      }
+    }
+    return u.size() >= bytes;
+  };
+  if (!need(12) || memcmp(u.data(), "BAM\1", 4) != 0) return bail("not a BAM file");
+  size_t o = 4;
+  uint32_t l_text = rd32(u.data() + o); o += 4;
+  if (!need(o + l_text + 4)) return bail("truncated BAM header");
+  o += l_text;
+  uint32_t n_ref = rd32(u.data() + o); o += 4;
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    if (!need(o + 4)) return bail("truncated BAM header");
+    uint32_t l_name = rd32(u.data() + o); o += 4;
+    if (!need(o + l_name + 4)) return bail("truncated BAM header");
+    h->names.emplace_back((const char *)(u.data() + o)); o += l_name;
+    h->target_len.push_back(rd32(u.data() + o)); o += 4;
+  }
+  h->first_record = o;
+  if (need(o + 36)) h->first_l_qseq = (int32_t)rd32(u.data() + o + 20);
+  for (auto &s : h->names) h->name_ptrs.push_back(s.c_str());
+  h->hdr.n_targets = (int32_t)h->names.size();
+  h->hdr.target_len = h->target_len.data();
+  h->hdr.target_name = h->name_ptrs.data();
+  return h;
+}
+extern "C" const bkid_header *bkid_host_bgzf_header(const bkid_host_bgzf *h) { return &h->hdr; }
+extern "C" const uint8_t *bkid_host_bgzf_data(const bkid_host_bgzf *h) { return h->file; }
+extern "C" uint64_t bkid_host_bgzf_size(const bkid_host_bgzf *h) { return h->fsz; }
+extern "C" const bkid_bgzf_block *bkid_host_bgzf_blocks(const bkid_host_bgzf *h) { return h->blocks.data(); }
+extern "C" int64_t bkid_host_bgzf_n_blocks(const bkid_host_bgzf *h) { return (int64_t)h->blocks.size(); }
+extern "C" uint64_t bkid_host_bgzf_first_record(const bkid_host_bgzf *h) { return h->first_record; }
+extern "C" uint64_t bkid_host_bgzf_usize(const bkid_host_bgzf *h) { return h->usize; }
+extern "C" int32_t bkid_host_bgzf_first_l_qseq(const bkid_host_bgzf *h) { return h->first_l_qseq; }
+extern "C" void bkid_host_bgzf_close(bkid_host_bgzf *h) { if (!h) return; munmap((void *)h->file, h->fsz); delete h; }

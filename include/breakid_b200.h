@@ -168,6 +168,32 @@ int bkid_reserve(bkid_ctx *ctx, int64_t n_records, int64_t n_x, int64_t n_sa, in
 int bkid_push_batch(bkid_ctx *ctx, const bkid_batch *batch);
 /* same, but every pointer in `batch` is a DEVICE pointer (already-resident input) */
 int bkid_push_batch_device(bkid_ctx *ctx, const bkid_batch *batch);
+/* ---- device BGZF / BAM decode ----------------------------------------------------------
+ * replaces, as the producer of records: bgzf_read_block + inflate_block (htslib-1.3.1/bgzf.c:545-600,388-419) and
+ * bam_read1 (htslib-1.3.1/sam.c:407-441) under the samread / sam_read1 loops of src/BreakID.cc:1414,1929, together
+ * with bam_endpos (sam.c:344-350) and bam_aux_get (sam.c:1267-1290) for the SA:Z / OC:Z tags.
+ * `file` is the whole BAM file in host memory (mmap or a pinned buffer; pinned memory is copied from directly),
+ * `blocks` its BGZF block table in file order (the host only walks the BSIZE / ISIZE fields, see
+ * breakid_b200/host/bam_reader.h: bkid_host_bgzf_open), `first_record_uoffset` the offset of the first alignment
+ * record in the uncompressed stream (= size of the BAM header).  Compressed bytes are streamed to the device in
+ * chunks; inflate, record-boundary search and column extraction run there and append to the context exactly
+ * what bkid_push_batch would have been given by a host decoder.  Deflate stream errors, a wrong ISIZE, corrupt
+ * record sizes and a truncated last record return BKID_ERR_IO.  The gzip CRC32 is not verified. */
+typedef struct {
+  uint64_t payload_off;             /* file offset of the raw deflate payload (block start + 12 + XLEN) */
+  uint32_t payload_len;             /* BSIZE + 1 - 12 - XLEN - 8 */
+  uint32_t usize;                   /* ISIZE (<= 65536) */
+} bkid_bgzf_block;
+typedef struct {
+  int64_t n_chunks, n_blocks, compressed_bytes, uncompressed_bytes, n_records;
+  float total_ms, inflate_ms, boundaries_ms, extract_ms;
+  int32_t seed_repairs, reserved;
+} bkid_decode_stats;
+int bkid_push_bgzf(bkid_ctx *ctx, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks,
+                   uint64_t first_record_uoffset, int64_t *n_records);
+int bkid_get_decode_stats(bkid_ctx *ctx, bkid_decode_stats *stats);
+/* parity-test getter: one input column of the context by name ("flag", "pos", "x_name_hash", "sa_txt", ...) */
+int bkid_fetch_column(bkid_ctx *ctx, const char *name, void *out, int64_t cap_bytes, int64_t *n_bytes);
 /* forget all records (keeps allocations) */
 int bkid_reset(bkid_ctx *ctx);
 

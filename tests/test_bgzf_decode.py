@@ -1,0 +1,187 @@
+"""Device BGZF/BAM decode (bkid_push_bgzf): host half on the CPU, device half against the host decoder on the GPU."""
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from breakid_b200 import api, bamio, synth
+
+
+def _bgzf_write(path, payload: bytes, block=0xff00, level=6, vary=False):
+    rng = np.random.RandomState(9)
+    with open(path, "wb") as f:
+        o = 0
+        while o < len(payload):
+            n = int(rng.randint(1, block)) if vary else block
+            f.write(bamio._bgzf_block(payload[o:o + n], level if not vary else int(rng.choice([0, 1, 6, 9]))))
+            o += n
+        f.write(bamio._BGZF_EOF)
+
+
+def _raw_bam(records, targets):
+    text = "@HD\tVN:1.4\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % t for t in targets)
+    out = b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(targets))
+    for nm, ln in targets:
+        out += struct.pack("<i", len(nm) + 1) + nm.encode() + b"\0" + struct.pack("<i", ln)
+    first = len(out)
+    for r in records:
+        out += struct.pack("<i", len(r)) + r
+    return out, first
+
+
+def _record(tid, pos, name, flag, mapq, cigar, l_seq, mtid, mpos, isize, aux=b""):
+    nm = name.encode() + b"\0"
+    body = struct.pack("<iiBBHHHiiii", tid, pos, len(nm), mapq, 4680, len(cigar), flag, l_seq, mtid, mpos, isize) + nm
+    body += b"".join(struct.pack("<I", (n << 4) | op) for n, op in cigar)
+    body += b"\x11" * ((l_seq + 1) // 2) + b"\x1e" * l_seq + aux
+    return body
+
+
+def _hostile_records(rng, n):
+    """records with every aux type, OC tags, empty SA, long names, unmapped reads, zero-op cigars, big B arrays"""
+    recs = []
+    pos = 100
+    for i in range(n):
+        pos += int(rng.randint(0, 50))
+        k = i % 12
+        name = "read_%d_%s" % (i, "x" * int(rng.randint(0, 60)))
+        flag = int(rng.choice([99, 147, 65, 129, 97, 145, 1089, 4, 77, 141, 1, 2]))
+        cigar = [(int(rng.randint(1, 90)), 0)]
+        aux = b"NMC\x01" + b"MDZ" + b"%d" % int(rng.randint(1, 150)) + b"\0" + b"ASi" + struct.pack("<i", 77)
+        if k == 1: aux += b"SAZchr2,%d,+,40M60S,60,0;\0" % (pos + 7)
+        if k == 2: aux += b"OCZ60M40S\0" + b"SAZchr1,%d,-,60S40M,13,1;chr2,5,+,10M,0,0;\0" % (pos + 999)
+        if k == 3: aux += b"SAZ\0"                                     # empty SA: not an SA record
+        if k == 4: aux += b"XBBs" + struct.pack("<i", 5) + b"\1\0\2\0\3\0\4\0\5\0" + b"SAZchrX,9,+,50M50S,60,0;\0"
+        if k == 5: aux += b"XFf" + struct.pack("<f", 1.5) + b"XHH1A2B\0" + b"XAAq" + b"XSs" + struct.pack("<h", -3)
+        if k == 6: cigar = [(10, 4), (30, 0), (5, 1), (20, 0), (1000, 3), (35, 0), (8, 2), (10, 7), (5, 8), (3, 5)]
+        if k == 7: cigar = []
+        if k == 8: flag |= 4
+        if k == 9: aux = b""
+        if k == 10: aux += b"SAZchr1,1,+,1S1M,0,0;\0" + b"SAZignored,2,+,1M,0,0;\0"   # first occurrence wins
+        if k == 11: aux += b"XBBI" + struct.pack("<i", 300) + bytes(1200)
+        tid = 0 if i < n * 2 // 3 else 1
+        if i == n * 2 // 3: pos = 5
+        l_seq = int(rng.choice([0, 1, 100, 151]))
+        recs.append(_record(tid, pos, name, flag, int(rng.randint(0, 61)), cigar, l_seq, int(rng.choice([-1, 0, 1])), int(rng.randint(-1, 5000)), int(rng.randint(-900, 900)), aux))
+    recs.append(_record(-1, -1, "unmapped_tail", 77, 0, [], 30, -1, -1, 0))
+    return recs
+
+
+def _write_hostile(tmp_path, n=4000, vary=True, seed=3):
+    rng = np.random.RandomState(seed)
+    payload, first = _raw_bam(_hostile_records(rng, n), [("chr1", 500000), ("chr2", 400000)])
+    p = str(tmp_path / "hostile.bam")
+    _bgzf_write(p, payload, vary=vary)
+    return p, payload, first
+
+
+def test_bgzf_open_block_table_and_header(tmp_path):
+    p, payload, first = _write_hostile(tmp_path)
+    f = api.BgzfFile(p)
+    assert f.target_names == ["chr1", "chr2"] and f.target_len == [500000, 400000]
+    assert f.first_record == first and f.usize == len(payload)
+    bt = f.block_table()
+    assert int(bt["usize"].sum()) == len(payload) and f.n_blocks == len(bt)
+    raw = open(p, "rb").read()
+    got = b"".join(zlib.decompress(raw[int(b["payload_off"]):int(b["payload_off"]) + int(b["payload_len"])], -15) for b in bt)
+    assert got == payload
+    f.close()
+    with pytest.raises(IOError):
+        api.BgzfFile(str(tmp_path / "missing.bam"))
+    bad = str(tmp_path / "bad.bam")
+    open(bad, "wb").write(b"not a bam file at all, just text" * 10)
+    with pytest.raises(IOError):
+        api.BgzfFile(bad)
+
+
+_ALL = (("flag", np.uint16), ("mapq", np.uint8), ("tid", np.int32), ("pos", np.int32), ("isize", np.int32), ("endpos", np.int32)) + api._XCOLS + api._SIDE
+
+
+def _assert_same_as_host_decoder(path, chunk_kb=None):
+    hb = api.HostBatch.from_bam(path, threads=4)
+    f = api.BgzfFile(path)
+    if chunk_kb:
+        os.environ["BKID_BGZF_CHUNK_KB"] = str(chunk_kb)
+    try:
+        c = api.Context(f.target_len, f.target_names, device=0)
+        n = c.push_bgzf(f)
+    finally:
+        os.environ.pop("BKID_BGZF_CHUNK_KB", None)
+    assert n == hb.n
+    st = c.decode_stats()
+    assert st["n_records"] == hb.n and st["uncompressed_bytes"] == f.usize
+    for k, dt in _ALL:
+        got = c.fetch_column(k, dt)
+        exp = hb.cols[k] if k in hb.cols else hb.x[k] if k in hb.x else hb.side[k]
+        assert np.array_equal(got, np.asarray(exp, dtype=dt).reshape(-1)), (k, chunk_kb)
+    f.close()
+    return c, hb, st
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk_kb", [None, 64, 300, 1024])
+def test_device_decode_equals_host_decoder_hostile(tmp_path, chunk_kb):
+    p, _, _ = _write_hostile(tmp_path, n=6000)
+    c, hb, st = _assert_same_as_host_decoder(p, chunk_kb)
+    if chunk_kb:
+        assert st["n_chunks"] > 1
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk_kb", [None, 2048])
+def test_device_decode_whole_path(tmp_path, small_data, chunk_kb):
+    """BAM file -> device decode -> whole hot path == oracle on the generator's own batch"""
+    import oracle_py as O
+    d, hb0, nibs = small_data
+    p = str(tmp_path / "reads.bam")
+    bamio.write_bam(p, d)
+    c, hb, st = _assert_same_as_host_decoder(p, chunk_kb)
+    for t, (pl, l) in enumerate(nibs):
+        c.set_nib(t, pl, l)
+    mean, sd, dist, ncall = c.run()
+    got = c.fetch_clusters()
+    om, osd, od, exp = O.run(hb0, nibs, mode=0)
+    assert (mean, sd, dist) == (om, osd, od)
+    assert got.tobytes() == exp.tobytes()
+    # a second file pushed after a reset reuses the decoder state
+    c.reset()
+    f = api.BgzfFile(p)
+    assert c.push_bgzf(f) == hb.n
+    assert c.run()[:3] == (om, osd, od)
+    f.close()
+    c.close()
+
+
+@pytest.mark.gpu
+def test_device_decode_rejects_corrupt_files(tmp_path):
+    p, payload, first = _write_hostile(tmp_path, n=3000, vary=False)
+    raw = bytearray(open(p, "rb").read())
+    f0 = api.BgzfFile(p)
+    bt = f0.block_table()
+    f0.close()
+    # damaged deflate payload (reserved block type in the first byte of block 3)
+    bad = bytearray(raw)
+    bad[int(bt["payload_off"][3])] |= 0x06
+    q = str(tmp_path / "bad_deflate.bam")
+    open(q, "wb").write(bad)
+    f = api.BgzfFile(q)
+    c = api.Context(f.target_len, f.target_names, device=0)
+    with pytest.raises(api.BkidError, match="inflate failed"):
+        c.push_bgzf(f)
+    f.close()
+    # truncated last record: drop the tail of the uncompressed stream
+    q = str(tmp_path / "trunc.bam")
+    _bgzf_write(q, payload[:-10])
+    f = api.BgzfFile(q)
+    with pytest.raises(api.BkidError, match="truncated BAM record"):
+        c.push_bgzf(f)
+    f.close()
+    # the context is still usable afterwards
+    c.reset()
+    f = api.BgzfFile(p)
+    assert c.push_bgzf(f) > 3000
+    f.close()
+    c.close()
