@@ -67,15 +67,22 @@ def write_bam(path: str, d: synth.SynthData, random_qual: bool = True, level: in
     out = open(path, "wb")
     pending = bytearray(hdr)
 
+    from concurrent.futures import ThreadPoolExecutor
+    import os as _os
+    pool = ThreadPoolExecutor(max(1, min(16, _os.cpu_count() or 1)))     # zlib releases the GIL
+
     def flush(final=False):
         nonlocal pending
         mv = memoryview(pending)
         o = 0
+        blks = []
         while len(pending) - o >= 0xff00 or (final and o < len(pending)):
             blk = bytes(mv[o:o + 0xff00])
-            out.write(_bgzf_block(blk, level))
+            blks.append(blk)
             o += len(blk)
         mv.release()
+        for comp in pool.map(lambda b: _bgzf_block(b, level), blks):
+            out.write(comp)
         pending = pending[o:]
 
     flush()
@@ -137,6 +144,7 @@ def write_bam(path: str, d: synth.SynthData, random_qual: bool = True, level: in
         pending += buf.tobytes()
         flush()
     flush(final=True)
+    pool.shutdown()
     out.write(_BGZF_EOF)
     out.close()
 

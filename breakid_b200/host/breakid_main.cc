@@ -118,15 +118,25 @@ int main(int argc, char *argv[])
     refgene = std::string(inst ? inst : ".") + "/ref_files/refGene.txt";
   }
 
-  // ---- decode (host) ----
+  // ---- open: the host walks the BGZF block headers and parses the BAM header; inflate + record decode run on the
+  // device (bkid_push_bgzf).  BKID_HOST_DECODE=1 selects the multi-threaded host decoder instead (A/B checks).
   std::cout << "start to stats the insert size...\n";
   char err[256];
   double t0 = now_s();
-  bkid_host_bam *bam = bkid_host_read_bam(inp.c_str(), threads, err, sizeof err);
-  if (!bam) { std::cerr << "Error: can not open bam-file: " << inp << std::endl; exit(1); }
+  const bool host_decode = getenv("BKID_HOST_DECODE") && atoi(getenv("BKID_HOST_DECODE")) != 0;
+  bkid_host_bam *bam = nullptr;
+  bkid_host_bgzf *bgzf = nullptr;
+  const bkid_header *hdr = nullptr;
+  if (host_decode) {
+    bam = bkid_host_read_bam(inp.c_str(), threads, err, sizeof err);
+    if (!bam) { std::cerr << "Error: can not open bam-file: " << inp << std::endl; exit(1); }
+    hdr = bkid_host_bam_header(bam);
+  } else {
+    bgzf = bkid_host_bgzf_open(inp.c_str(), err, sizeof err);
+    if (!bgzf) { std::cerr << "Error: can not open bam-file: " << inp << std::endl; exit(1); }
+    hdr = bkid_host_bgzf_header(bgzf);
+  }
   double t_decode = now_s() - t0;
-  const bkid_header *hdr = bkid_host_bam_header(bam);
-  const bkid_batch *batch = bkid_host_bam_batch(bam);
   {
     std::ifstream in((nib_dir + "/ref_names.txt").c_str());
     if (!in.is_open()) { std::cerr << "Error: cannot open reference names file.\n"; exit(1); }     // src/BreakID.cc:1399-1404
@@ -141,7 +151,20 @@ int main(int argc, char *argv[])
   bkid_ctx *ctx = bkid_create(gpu, hdr, &prm);
   if (!ctx) { std::cerr << "Error: " << bkid_last_error(nullptr) << std::endl; exit(1); }
   auto die = [&](const char *what) { std::cerr << "Error: " << what << ": " << bkid_last_error(ctx) << std::endl; exit(1); };
-  if (bkid_push_batch(ctx, batch)) die("push_batch");
+  double t_push0 = now_s();
+  bkid_decode_stats dst;
+  memset(&dst, 0, sizeof dst);
+  if (host_decode) {
+    if (bkid_push_batch(ctx, bkid_host_bam_batch(bam))) die("push_batch");
+  } else {
+    int64_t nrec = 0;
+    if (bkid_push_bgzf(ctx, bkid_host_bgzf_data(bgzf), bkid_host_bgzf_blocks(bgzf), bkid_host_bgzf_n_blocks(bgzf), bkid_host_bgzf_first_record(bgzf), &nrec)) {
+      std::cerr << "Error: can not read bam-file: " << inp << " (" << bkid_last_error(ctx) << ")" << std::endl;
+      exit(1);
+    }
+    bkid_get_decode_stats(ctx, &dst);
+  }
+  double t_push = now_s() - t_push0;
   double mean = 0, sd = 0;
   if (bkid_insert_stats(ctx, &mean, &sd)) die("insert_stats");
   std::cout << "the insert size mean: " << mean << ", the insert size sd:" << sd << " .\n";
@@ -223,11 +246,13 @@ int main(int argc, char *argv[])
     p << dist << "\t" << n_pairs << "\t" << tm.n_masked << "\t" << tm.n_clustered << "\t" << n_clusters << "\t" << t_scan << "\t" << t_cluster << "\t" << t_bp << "\t" << t_total
       << std::endl;
     std::ofstream j((out + "_b200_timings.txt").c_str());
-    j << "decode_s\t" << t_decode << "\nrecords\t" << tm.n_records << "\nh2d_ms\t" << tm.h2d << "\nclassify_ms\t" << tm.classify << "\ninsert_stats_ms\t" << tm.insert_stats
+    j << "decoder\t" << (host_decode ? "host" : "device") << "\nopen_s\t" << t_decode << "\npush_s\t" << t_push << "\ninflate_ms\t" << dst.inflate_ms << "\nboundaries_ms\t" << dst.boundaries_ms
+      << "\nextract_ms\t" << dst.extract_ms << "\ncompressed_bytes\t" << dst.compressed_bytes << "\nuncompressed_bytes\t" << dst.uncompressed_bytes << "\nrecords\t" << tm.n_records << "\nh2d_ms\t" << tm.h2d << "\nclassify_ms\t" << tm.classify << "\ninsert_stats_ms\t" << tm.insert_stats
       << "\njoin_ms\t" << tm.join << "\nbucket_sort_ms\t" << tm.bucket_sort << "\nmask_ms\t" << tm.mask << "\ncluster_ms\t" << tm.cluster << "\nsummarize_ms\t" << tm.summarize
       << "\nevidence_ms\t" << tm.evidence << "\nrefine_ms\t" << tm.refine << "\n";
   }
   bkid_destroy(ctx);
-  bkid_host_bam_free(bam);
+  if (bam) bkid_host_bam_free(bam);
+  if (bgzf) bkid_host_bgzf_close(bgzf);
   return 0;
 }
