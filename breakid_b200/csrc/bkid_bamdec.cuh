@@ -30,7 +30,7 @@ constexpr int INF_WARPS = 8;
 
 struct Task { uint64_t src; uint32_t dst; uint32_t clen, ulen; };
 
-__global__ void __launch_bounds__(INF_WARPS * 32) bgzf_inflate(const uint8_t *__restrict__ comp, const Task *__restrict__ tasks, int ntask, uint8_t *__restrict__ unc, int *__restrict__ err)
+__global__ void __launch_bounds__(INF_WARPS * 32, 4) bgzf_inflate(const uint8_t *__restrict__ comp, const Task *__restrict__ tasks, int ntask, uint8_t *__restrict__ unc, int *__restrict__ err)
 {
   __shared__ bki::Tables T[INF_WARPS];
   int w = threadIdx.x >> 5;
@@ -313,7 +313,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   cudaStream_t st = c->st;
   invalidate(c);
   memset(&d->stats, 0, sizeof d->stats);
-  size_t COMP_CAP = (size_t)128 << 20, UNC_CAP = (size_t)512 << 20, CARRY_CAP = (size_t)64 << 20;
+  size_t COMP_CAP = (size_t)512 << 20, UNC_CAP = (size_t)1024 << 20, CARRY_CAP = (size_t)64 << 20;
   if (const char *e = getenv("BKID_BGZF_CHUNK_KB")) {          // tests: small chunks exercise the streaming / carry logic on small files
     long kb = atol(e);
     if (kb >= 64) { UNC_CAP = (size_t)kb << 10; COMP_CAP = UNC_CAP; }
@@ -328,6 +328,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   // chunk boundaries
   std::vector<std::pair<int64_t, int64_t>> chunks;
   uint64_t total_u = 0;
+  size_t max_span = 0, max_unc = 0;
   for (int64_t b0 = 0; b0 < n_blocks;) {
     size_t cb = 0, ub = 0; int64_t b1 = b0;
     uint64_t span0 = blocks[b0].payload_off;
@@ -341,15 +342,19 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     if (cb > COMP_CAP + (1u << 17)) return fail(c, BKID_ERR_IO, "BGZF block larger than 64 KiB");
     chunks.push_back({b0, b1});
     total_u += ub;
+    max_span = std::max(max_span, cb); max_unc = std::max(max_unc, ub);
     b0 = b1;
   }
-  TRY(c, d->unc.ensure(UNC_CAP + CARRY_CAP + 256, 0, st));
-  TRY(c, d->carry.ensure(CARRY_CAP + 256, 0, st));
+  // buffers are sized by what this file needs (small files: small allocations); the carry buffer grows on demand
+  size_t carry_cap = std::min<size_t>(CARRY_CAP, (size_t)4 << 20);
+  TRY(c, d->unc.ensure(max_unc + CARRY_CAP + 256, 0, st));
+  TRY(c, d->carry.ensure(carry_cap + 256, 0, st));
   TRY(c, d->state.ensure(256, 0, st));
-  for (int i = 0; i < 2; ++i) TRY(c, d->comp[i].ensure(COMP_CAP + (1u << 17) + 256, 0, st));
-  if (!pinned && d->h_cap < COMP_CAP + (1u << 17)) {
-    for (int i = 0; i < 2; ++i) { if (d->h_stage[i]) cudaFreeHost(d->h_stage[i]); CU(c, cudaMallocHost((void **)&d->h_stage[i], COMP_CAP + (1u << 17))); }
-    d->h_cap = COMP_CAP + (1u << 17);
+  for (int i = 0; i < (chunks.size() > 1 ? 2 : 1); ++i) TRY(c, d->comp[i].ensure(max_span + 256, 0, st));
+  if (!pinned && d->h_cap < max_span + 256) {
+    for (int i = 0; i < 2; ++i) { if (d->h_stage[i]) cudaFreeHost(d->h_stage[i]); d->h_stage[i] = nullptr; }
+    for (int i = 0; i < (chunks.size() > 1 ? 2 : 1); ++i) CU(c, cudaMallocHost((void **)&d->h_stage[i], max_span + 256));
+    d->h_cap = chunks.size() > 1 ? max_span + 256 : 0;          // a single-slot allocation is not reused for multi-chunk files
   }
   size_t max_tasks = 0;
   for (auto &ch : chunks) max_tasks = std::max<size_t>(max_tasks, (size_t)(ch.second - ch.first));
@@ -406,7 +411,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     CU(c, cudaMemcpyAsync(dt, ht, (size_t)nt * sizeof(Task), cudaMemcpyHostToDevice, st));
     CU(c, cudaStreamWaitEvent(st, d->ev_h2d[slot], 0));
     cudaEventRecord(d->ev_t[1], st);
-    if (nt) BK_LAUNCH(bgzf_inflate, std::min((nt + INF_WARPS - 1) / INF_WARPS, 148 * 7), INF_WARPS * 32, 0, st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 4);
+    if (nt) BK_LAUNCH(bgzf_inflate, std::min((nt + INF_WARPS - 1) / INF_WARPS, 148 * 4), INF_WARPS * 32, 0, st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 4);
     CU(c, cudaEventRecord(d->ev_free[slot], st));
     cudaEventRecord(d->ev_t[2], st);
     d->stats.n_blocks += nt; d->stats.uncompressed_bytes += (int64_t)(total - carry);
@@ -483,7 +488,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     // ---- carry the partial record at the end of the chunk ----
     carry = total - carry_start;
     if (carry > CARRY_CAP) return fail(c, BKID_ERR_IO, "BAM record larger than 64 MiB");
-    if (carry) CU(c, cudaMemcpyAsync(d->carry.p, u + carry_start, carry, cudaMemcpyDeviceToDevice, st));
+    if (carry) { TRY(c, d->carry.ensure((size_t)carry + 256, 0, st)); CU(c, cudaMemcpyAsync(d->carry.p, u + carry_start, carry, cudaMemcpyDeviceToDevice, st)); }
     cudaEventRecord(d->ev_t[4], st);
     TRY(c, sync_check(c));
     {

@@ -55,13 +55,21 @@ struct BitReader {
 BKI_FN void br_init(BitReader &b, const uint8_t *in, uint32_t len) { b.in = in; b.len = len; b.pos = 0; b.buf = 0; b.cnt = 0; b.over = 0; }
 BKI_FN void br_refill(BitReader &b)
 {
-  // keep >= 32 valid bits; past the end zeros are shifted in and counted (reported as ERR_INPUT if consumed)
-  while (b.cnt <= 56) {
-    uint64_t v = 0;
-    if (b.pos < b.len) v = b.in[b.pos]; else b.over++;
-    b.pos++;
-    b.buf |= v << b.cnt;
-    b.cnt += 8;
+  // keep > 32 valid bits.  Aligned 32-bit loads where the payload allows (one load per 4 input bytes); bytes at a
+  // misaligned start and at the tail.  Past the end zeros are shifted in and counted (reported as ERR_INPUT).
+  while (b.cnt <= 32) {
+    const uint8_t *p = b.in + b.pos;
+    if ((((uintptr_t)p) & 3u) == 0 && b.pos + 4 <= b.len) {
+      uint64_t v = *reinterpret_cast<const uint32_t *>(p);
+      b.buf |= v << b.cnt;
+      b.cnt += 32; b.pos += 4;
+    } else {
+      uint64_t v = 0;
+      if (b.pos < b.len) v = *p; else b.over++;
+      b.pos++;
+      b.buf |= v << b.cnt;
+      b.cnt += 8;
+    }
   }
 }
 BKI_FN uint32_t br_peek(const BitReader &b, int n) { return (uint32_t)(b.buf & ((1ull << n) - 1ull)); }
@@ -267,7 +275,7 @@ BKI_FN int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
     }
   } while (!last);
   BKI_SYNC();
-  if (b.over > 8) return ERR_INPUT;                       // consumed bits beyond the payload (refill looks <= 8 bytes ahead)
+  if (b.over > 8) return ERR_INPUT;                       // consumed bits beyond the payload (refill looks <= 5 bytes ahead)
   return op == out_len ? OK : ERR_SIZE;
 }
 
