@@ -330,6 +330,8 @@ def run_ours(args):
     torch.cuda.empty_cache()
     if world == 1 and not args.no_stress:
         line["split_read_stress"] = split_read_stress(local, dev, max(1, min(args.steps, 3)), args.stress_scale)
+    if world == 1 and not args.no_decode:
+        line["e2e_decode_included"] = decode_included(local, max(1, min(args.steps, 3)), min(args.scale, 1.0 / 256))
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_port(args)
@@ -337,6 +339,42 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def decode_included(local, steps, scale):
+    """Decode INCLUDED, on the bounded sample the reference arm runs on (BASELINE.json configs[1] x `scale`, written as
+    a real BGZF BAM with random qualities): compressed file bytes in pinned host memory -> bkid_push_bgzf (device
+    inflate + record decode) -> bkid_run -> bkid_fetch_clusters, all inside the timed region."""
+    from breakid_b200 import bamio
+    cfg = workload_cfg(scale)
+    d = synth.generate(cfg)
+    tmp = tempfile.mkdtemp(prefix="bkid_dec_")
+    bam = os.path.join(tmp, "reads.bam")
+    bamio.write_bam(bam, d, random_qual=True)
+    f = api.BgzfFile(bam)
+    raw = torch.from_numpy(np.fromfile(bam, dtype=np.uint8)).pin_memory()
+    ctx = api.Context(f.target_len, f.target_names, device=local)
+    ts = []
+    for i in range(2 + steps):
+        ctx.reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = ctx.push_bgzf(f, data_ptr=raw.data_ptr())
+        ctx.run()
+        out = ctx.fetch_clusters()
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            ts.append(dt)
+    st = ctx.decode_stats()
+    ctx.close()
+    f.close()
+    os.remove(bam)
+    ms = float(np.mean(ts)) * 1e3
+    return {"value": n / 2.0 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(st["compressed_bytes"]), "d2h_bytes_per_step": int(out.nbytes),
+            "sample": "configs[1] x scale %g: %d records, %d-byte BAM (%d BGZF blocks, %d bytes uncompressed)" % (scale, n, raw.numel(), st["n_blocks"], st["uncompressed_bytes"]),
+            "decode_ms": st["total_ms"], "inflate_ms": st["inflate_ms"], "boundaries_ms": st["boundaries_ms"], "extract_ms": st["extract_ms"],
+            "inflate_GBps_uncompressed": st["uncompressed_bytes"] / (st["inflate_ms"] * 1e-3) / 1e9 if st["inflate_ms"] > 0 else None,
+            "note": "compressed BAM bytes in pinned host memory -> bkid_push_bgzf -> bkid_run -> bkid_fetch_clusters"}
 
 
 def cpu_baseline_port(args):
@@ -364,7 +402,7 @@ def run_reference(args):
     cfg = workload_cfg(scale)
     d = synth.generate(cfg)
     tmp = tempfile.mkdtemp(prefix="bkid_ref_")
-    paths = bamio.write_dataset(tmp, d, random_qual=False)
+    paths = bamio.write_dataset(tmp, d, random_qual=True)          # same bytes as the decode-included leg of our arm
     O.ref_index(paths["bam"])
     O.ref_install_refgene(paths["refgene"])
     times = []
@@ -399,6 +437,7 @@ def main():
     ap.add_argument("--nib", action="store_true", help="also upload a random 4-bit genome so 41-mers are produced")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true", help="skip the configs[4] split-read stress leg")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decode-included leg (BAM file -> device inflate -> hot path)")
     ap.add_argument("--stress-scale", type=float, default=1.0, help="fraction of the 1e7-SA-record stress workload")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -330,36 +330,62 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
   __shared__ int sh_j, sh_q, sh_oor, sh_k;
   if (threadIdx.x == 0) { sh_t = t_in; sh_j = 0; sh_oor = 0; }
   __syncthreads();
+  constexpr int PB = 8;                     // blocks per thread and step: 8192 blocks per step
   while (true) {
     int j0 = sh_j;
     long long t0 = sh_t;
     if (j0 >= nb || sh_oor) break;
     int k0 = binade_of((double)t0);
-    int j = j0 + threadIdx.x;
+    int jb = j0 + (int)threadIdx.x * PB;
+    long long dl[PB];
     long long delta = 0;
-    if (j < nb) {
-      delta = blkF[j];
-      if (k0 >= 0 && k0 < SD_K) delta += blkCum[(size_t)j * SD_K + k0];
+#pragma unroll
+    for (int i = 0; i < PB; ++i) {
+      int j = jb + i;
+      long long v = 0;
+      if (j < nb) {
+        v = blkF[j];
+        if (k0 >= 0 && k0 < SD_K) v += blkCum[(size_t)j * SD_K + k0];
+      }
+      dl[i] = v; delta += v;
     }
     long long tot;
     long long tstart = t0 + bk::block_excl_scan<long long>(delta, sh_scan, tot);
-    // valid iff every s in this block stays in binade k0
-    bool valid = true;
-    if (j < nb) {
-      double upper = (double)(tstart + delta + (long long)blkN[j] + 2) + blkAmax[j] * 1.000000001 + 2.0;
-      valid = (blkN[j] == 0) || (k0 < SD_K && binade_of((double)tstart) == k0 && binade_of(upper) == k0);
-      if (blkN[j] != 0 && k0 >= SD_K) valid = false;
+    // a block is valid iff every s in it stays in binade k0
+    int first_bad = 1024 * PB;
+    long long tend_of[PB];
+    {
+      long long ts = tstart;
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        int j = jb + i;
+        bool valid = true;
+        if (j < nb) {
+          unsigned bn = blkN[j];
+          double upper = (double)(ts + dl[i] + (long long)bn + 2) + blkAmax[j] * 1.000000001 + 2.0;
+          valid = (bn == 0) || (k0 < SD_K && binade_of((double)ts) == k0 && binade_of(upper) == k0);
+          if (bn != 0 && k0 >= SD_K) valid = false;
+          if (!valid && first_bad == 1024 * PB) first_bad = (int)threadIdx.x * PB + i;
+        }
+        ts += dl[i];
+        tend_of[i] = ts;
+      }
     }
-    if (threadIdx.x == 0) sh_q = 1024;
+    if (threadIdx.x == 0) sh_q = 1024 * PB;
     __syncthreads();
-    if (j < nb && !valid) atomicMin(&sh_q, (int)threadIdx.x);
+    if (first_bad < 1024 * PB) atomicMin(&sh_q, first_bad);
     __syncthreads();
     int q = sh_q;
     int nvalid = min(q, nb - j0);          // blocks j0 .. j0+nvalid-1 are final
     __syncthreads();
-    if (nvalid > 0 && (int)threadIdx.x == nvalid - 1) { sh_t = tstart + delta; sh_j = j0 + nvalid; }
+    if (nvalid > 0 && (nvalid - 1) / PB == (int)threadIdx.x) {
+      long long te = tend_of[0];
+#pragma unroll
+      for (int i = 1; i < PB; ++i) if ((nvalid - 1) % PB == i) te = tend_of[i];
+      sh_t = te; sh_j = j0 + nvalid;
+    }
     __syncthreads();
-    if (q >= 1024 || j0 + q >= nb) continue;
+    if (q >= 1024 * PB || j0 + q >= nb) continue;
     // block jq = j0+q is either the first block of a new binade or a real straddler
     int jq = j0 + q;
     long long t = sh_t;

@@ -13,9 +13,9 @@ python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.json
 cat $OUT/bench_$TAG.json
 # launch list (cold-cache, serialised; shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_$TAG.csv \
-  python bench.py --scale $SCALE --steps 1 --no-cpu-baseline --no-stress > $OUT/ncu_list_$TAG.log 2>&1; echo "ncu list rc=$?"
+  python bench.py --scale $SCALE --steps 1 --no-cpu-baseline --no-stress --no-decode > $OUT/ncu_list_$TAG.log 2>&1; echo "ncu list rc=$?"
 # full capture of the streaming kernels + the top latency kernels (first launch of each in the 4th step)
 timeout 1200 ncu --set full --clock-control none --import-source on \
   -k regex:'^(k1_classify|k1_compact|sd_block_stats|sd_resolve|k2_emit_pairs|max_span_kernel|ahc_replay|ahc_components)$' \
-  --launch-count 8 -o $OUT/prof_top_$TAG -f python bench.py --scale $SCALE --steps 1 --no-cpu-baseline --no-stress > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+  --launch-count 8 -o $OUT/prof_top_$TAG -f python bench.py --scale $SCALE --steps 1 --no-cpu-baseline --no-stress --no-decode > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT | tail -8
