@@ -250,7 +250,7 @@ def ref_install_refgene(path):
     shutil.copy(path, os.path.join(REF_INSTALL, "ref_files", "refGene.txt"))
 
 
-def ref_run_binary(bam, prefix, nib_dir, fast=False, all_=True, qual=None, timeout=3600):
+def ref_run_binary(bam, prefix, nib_dir, fast=False, all_=True, qual=None, timeout=3600, extra=()):
     cmd = [REF_BIN, "-i", bam, "-o", prefix, "-n", nib_dir]
     if fast:
         cmd.append("-fast")
@@ -258,6 +258,7 @@ def ref_run_binary(bam, prefix, nib_dir, fast=False, all_=True, qual=None, timeo
         cmd.append("-all")
     if qual is not None:
         cmd += ["-q", str(qual)]
+    cmd += list(extra)
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
 
 

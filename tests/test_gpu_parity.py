@@ -455,3 +455,42 @@ def test_vote_big_many_uniques():
     assert got.tobytes() == exp.tobytes()
     assert len(got) == 3
     c.close()
+
+
+@pytest.mark.parametrize("flags", [[], ["-q", "35"], ["-fast", "-q", "5"]])
+def test_driver_config4_tumour_fusions(tmp_path, flags):
+    """BASELINE.json configs[3] shape (reduced): tumour-like 100x BAM, translocations only, dense synthetic refGene so
+    that most calls are gene fusions (annotation path: gene, strand, exon numbering columns); non-default -q (the
+    reference's -t is declared without an argument, src/BreakID.cc:23, and crashes in atol(NULL): not testable).
+    The driver (device decode + GPU path + host annotation) must write the reference binary's files byte for byte."""
+    import os
+    import subprocess
+    import oracle_py as O
+    from breakid_b200 import bamio, synth
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    cfg = synth.SynthConfig(chrom_lens=[260000, 220000, 180000, 140000], coverage=100.0, n_tra=10, n_inv=0, n_dup=0, n_del=0,
+                            span_per_sv=40, split_per_sv=20, seed=44, sv_jitter=1)
+    d = synth.generate(cfg)
+    paths = bamio.write_dataset(str(tmp_path), d, genes_per_mb=30.0)
+    O.ref_index(paths["bam"])
+    O.ref_install_refgene(paths["refgene"])
+    r = O.ref_run_binary(paths["bam"], str(tmp_path / "ref"), paths["nib"], extra=flags)
+    assert r.returncode == 0, r.stderr[-500:]
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breakid_b200", "host", "BreakID")
+    g = subprocess.run([drv, "-i", paths["bam"], "-o", str(tmp_path / "gpu"), "-n", paths["nib"], "-r", paths["refgene"], "-all"] + flags,
+                       capture_output=True, text=True)
+    assert g.returncode == 0, g.stderr[-500:]
+    for suffix in ("_fusion.txt", "_fusion_all.txt"):
+        a = open(str(tmp_path / "ref") + suffix).read()
+        b = open(str(tmp_path / "gpu") + suffix).read()
+        assert a == b, (suffix, flags)
+    rows = open(str(tmp_path / "gpu") + "_fusion_all.txt").read().splitlines()[1:]
+    assert len(rows) >= 8 and all(x.split("\t")[0] == "Translocation" for x in rows)
+    fused = [x for x in open(str(tmp_path / "gpu") + "_fusion.txt").read().splitlines()[1:]]
+    assert len(fused) >= 1                      # at least one gene-gene fusion survives the filter
+    # host decoder A/B: same files
+    g2 = subprocess.run([drv, "-i", paths["bam"], "-o", str(tmp_path / "gpu_host"), "-n", paths["nib"], "-r", paths["refgene"], "-all"] + flags,
+                        capture_output=True, text=True, env=dict(os.environ, BKID_HOST_DECODE="1"))
+    assert g2.returncode == 0
+    assert open(str(tmp_path / "gpu_host") + "_fusion_all.txt").read() == open(str(tmp_path / "gpu") + "_fusion_all.txt").read()
