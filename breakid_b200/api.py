@@ -233,7 +233,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
-           "bkid_push_bgzf", "bkid_get_decode_stats", "bkid_fetch_column"]
+           "bkid_push_bgzf", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -258,6 +258,7 @@ def cuda_lib():
         L.bkid_reserve.argtypes = [vp] + [C.c_int64] * 6
         L.bkid_push_batch.argtypes = [vp, C.POINTER(Batch)]
         L.bkid_push_batch_device.argtypes = [vp, C.POINTER(Batch)]
+        L.bkid_set_exclude.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.bkid_push_bgzf.argtypes = [vp, vp, vp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
         L.bkid_get_decode_stats.argtypes = [vp, C.POINTER(DecodeStats)]
         L.bkid_fetch_column.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)]
@@ -410,6 +411,11 @@ class Context:
         if nb.value:
             self._chk(self.lib.bkid_fetch_column(self.ctx, name.encode(), out.ctypes.data_as(C.c_void_p), int(nb.value), C.byref(nb)))
         return out
+
+    def set_exclude(self, tid, beg, end):
+        """exclude intervals [beg, end) on target tid (extension, see include/breakid_b200.h: bkid_set_exclude)"""
+        t = np.ascontiguousarray(tid, np.int32); b = np.ascontiguousarray(beg, np.int32); e = np.ascontiguousarray(end, np.int32)
+        self._chk(self.lib.bkid_set_exclude(self.ctx, int(t.shape[0]), t.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p)))
 
     def push_device(self, b: Batch):
         self._chk(self.lib.bkid_push_batch_device(self.ctx, C.byref(b)))

@@ -25,6 +25,9 @@ static void decoder_free(bkid_ctx *c);
 
 struct bkid_ctx {
   bkid_decoder *dec = nullptr;              // streaming BGZF/BAM decode state (bkid_bamdec.cuh)
+  std::vector<int32_t> ex_iv;               // exclude intervals: merged, sorted (tid, beg, end) triples
+  DBuf ex_tab, ex_lo, ex_len, ex_pre;
+  long long n_excluded = 0;
   int device = 0;
   cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;     // st2: side stream for the sd replay (overlaps the join); st3: max span (needed only by the refinement)
   bkid_params prm;
@@ -558,7 +561,7 @@ void bkid_destroy(bkid_ctx *c)
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
+                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();
@@ -716,6 +719,27 @@ int bkid_reset(bkid_ctx *c)
   return 0;
 }
 
+int bkid_set_exclude(bkid_ctx *c, int64_t n_iv, const int32_t *tid, const int32_t *beg, const int32_t *end)
+{
+  if (!c || n_iv < 0 || (n_iv > 0 && (!tid || !beg || !end))) return c ? fail(c, BKID_ERR_ARG, "bad exclude intervals") : BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  std::vector<std::array<int32_t, 3>> v;
+  for (int64_t k = 0; k < n_iv; ++k) {
+    if (tid[k] < 0 || tid[k] >= c->nt) return fail(c, BKID_ERR_ARG, "exclude interval on an unknown target");
+    int32_t b = beg[k] < 0 ? 0 : beg[k];
+    if (end[k] > b) v.push_back({tid[k], b, end[k]});
+  }
+  std::sort(v.begin(), v.end());
+  c->ex_iv.clear();
+  for (auto &x : v) {                                   // merge overlapping / touching intervals
+    size_t m = c->ex_iv.size();
+    if (m && c->ex_iv[m - 3] == x[0] && x[1] <= c->ex_iv[m - 1]) { if (x[2] > c->ex_iv[m - 1]) c->ex_iv[m - 1] = x[2]; }
+    else { c->ex_iv.push_back(x[0]); c->ex_iv.push_back(x[1]); c->ex_iv.push_back(x[2]); }
+  }
+  invalidate(c);
+  return 0;
+}
+
 static int classify_impl(bkid_ctx *c)
 {
   if (c->classified) return 0;
@@ -730,6 +754,20 @@ static int classify_impl(bkid_ctx *c)
   if (n > 0)
     BK_LAUNCH(k1_classify, (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, n, c->prm.qual, c->cls.as<uint8_t>(), c->tile_cand.as<uint32_t>(), g, g + 1);
   cudaEventRecord(c->ev[3], st);
+  int n_iv = (int)(c->ex_iv.size() / 3);
+  c->n_excluded = 0;
+  if (n_iv > 0 && n > 0) {
+    TRY(c, c->ex_tab.ensure((size_t)n_iv * 12 + 64, 0, st)); TRY(c, c->ex_lo.ensure((size_t)n_iv * 4 + 64, 0, st));
+    TRY(c, c->ex_len.ensure((size_t)n_iv * 4 + 64, 0, st)); TRY(c, c->ex_pre.ensure((size_t)(n_iv + 1) * 8 + 64, 0, st));
+    CU(c, cudaMemcpyAsync(c->ex_tab.p, c->ex_iv.data(), (size_t)n_iv * 12, cudaMemcpyHostToDevice, st));
+    BK_LAUNCH(ex_ranges, GRID1(n_iv, 128), 128, 0, st, c->p_tid, c->p_pos, n, c->ex_tab.as<int32_t>(), n_iv, c->ex_lo.as<uint32_t>(), c->ex_len.as<uint32_t>());
+    BK_LAUNCH(ex_prefix, 1, 32, 0, st, c->ex_len.as<uint32_t>(), n_iv, c->ex_pre.as<unsigned long long>());
+    BK_LAUNCH(ex_apply, 148 * 8, 256, 0, st, c->ex_lo.as<uint32_t>(), c->ex_pre.as<unsigned long long>(), n_iv, c->p_isize, c->cls.as<uint8_t>(), c->tile_cand.as<uint32_t>(), g, g + 1);
+    unsigned long long ne = 0;
+    CU(c, cudaMemcpyAsync(&ne, c->ex_pre.as<unsigned long long>() + n_iv, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    c->n_excluded = (long long)ne;
+  }
   unsigned long long h[2] = {0, 0};
   CU(c, cudaMemcpyAsync(h, g, 16, cudaMemcpyDeviceToHost, st));
   TRY(c, sync_check(c));
@@ -1106,7 +1144,7 @@ static int refine_build_rows(bkid_ctx *c)
     int *miss = (int *)(c->counters.as<unsigned>() + 50);
     CU(c, cudaMemsetAsync(miss, 0, 4, st));
     if (c->n_sa > 0) {
-      BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->p_flag, c->p_tid, c->p_pos, c->p_endpos, c->p_x_rec, c->n_x, c->p_x_nh, miss,
+      BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->cls.as<uint8_t>(), c->p_flag, c->p_tid, c->p_pos, c->p_endpos, c->p_x_rec, c->n_x, c->p_x_nh, miss,
                 c->p_cig_off, c->p_cig_ops, c->p_sa_off, c->p_sa_txt, c->p_oc_off, c->p_oc_txt, c->prm.mismatch_num, c->sarows.as<EvRow>());
       int hm = 0;
       CU(c, cudaMemcpyAsync(&hm, miss, 4, cudaMemcpyDeviceToHost, st));

@@ -23,6 +23,7 @@
 #include "prims.cuh"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -43,7 +44,7 @@ void bk_set_cuda_error(cudaError_t e, const char *file, int line)
 using bk::div_up;
 
 enum { F_PAIRED = 0x1, F_PROPER = 0x2, F_UNMAP = 0x4, F_REVERSE = 0x10, F_SECONDARY = 0x100, F_QCFAIL = 0x200, F_DUP = 0x400 };
-enum { CL_INSERT = 1, CL_CAND = 2, CL_DEPTH = 4, CL_SPLITOK = 8 };
+enum { CL_INSERT = 1, CL_CAND = 2, CL_DEPTH = 4, CL_SPLITOK = 8, CL_EXCL = 16 /* record lies in an exclude interval: invisible to every stage */ };
 
 // ---------------------------------------------------------------------------------------------
 // growable device buffer
@@ -151,6 +152,58 @@ k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
     tile_cand[blockIdx.x] = c >> 16;
     if (c & 0xffffu) { atomicAdd(g_sum_abs, sh_sum); atomicAdd(g_cnt_insert, (unsigned long long)(c & 0xffffu)); }
   }
+}
+
+// ---- exclude intervals (extension: north_star's exclude-BED; the reference has no such filter) -----------------
+// Semantics: the reference run on a BAM from which every record whose leftmost coordinate (tid, pos) lies in an
+// interval has been removed.  Records are coordinate sorted, so an interval is one contiguous record-index range:
+// ex_ranges finds it with two binary searches; ex_apply then takes the excluded records back out of what K1
+// produced (class byte, insert sum / count, per-tile candidate counts).  K1 itself is untouched and pays nothing.
+__device__ __forceinline__ long long ex_lower_bound(const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, long long n, int qt, long long qp)
+{
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    long long m = (lo + hi) >> 1;
+    uint32_t tm = (uint32_t)tid[m];
+    bool less = tm < (uint32_t)qt || (tm == (uint32_t)qt && (long long)pos[m] < qp);
+    if (less) lo = m + 1; else hi = m;
+  }
+  return lo;
+}
+// one thread per (merged, sorted) interval; a single trailing thread turns the lengths into a prefix sum
+__global__ void ex_ranges(const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, long long n, const int32_t *__restrict__ iv /* [n_iv][3] */, int n_iv,
+                          uint32_t *__restrict__ lo, uint32_t *__restrict__ len)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_iv) return;
+  long long a = ex_lower_bound(tid, pos, n, iv[3 * k], iv[3 * k + 1]);
+  long long b = ex_lower_bound(tid, pos, n, iv[3 * k], iv[3 * k + 2]);
+  lo[k] = (uint32_t)a; len[k] = (uint32_t)(b > a ? b - a : 0);
+}
+__global__ void ex_prefix(const uint32_t *__restrict__ len, int n_iv, unsigned long long *__restrict__ pre /* [n_iv+1] */)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  unsigned long long s = 0;
+  for (int k = 0; k < n_iv; ++k) { pre[k] = s; s += len[k]; }
+  pre[n_iv] = s;
+}
+__global__ void __launch_bounds__(256)
+ex_apply(const uint32_t *__restrict__ lo, const unsigned long long *__restrict__ pre, int n_iv, const int32_t *__restrict__ isize, uint8_t *__restrict__ cls,
+         uint32_t *__restrict__ tile_cand, unsigned long long *__restrict__ g_sum_abs, unsigned long long *__restrict__ g_cnt_insert)
+{
+  unsigned long long E = pre[n_iv];
+  unsigned long long sum = 0; unsigned cnt = 0;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (unsigned long long)gridDim.x * blockDim.x) {
+    int a = 0, b = n_iv;                       // last k with pre[k] <= e
+    while (b - a > 1) { int m = (a + b) >> 1; if (pre[m] <= e) a = m; else b = m; }
+    long long i = (long long)lo[a] + (long long)(e - pre[a]);
+    unsigned c = cls[i];
+    if (c & CL_INSERT) { int s = isize[i]; sum += (unsigned long long)(s < 0 ? -(long long)s : (long long)s); ++cnt; }
+    if (c & CL_CAND) atomicSub(&tile_cand[i / K1_TILE], 1u);
+    cls[i] = (uint8_t)CL_EXCL;
+  }
+  sum = bk::warp_sum(sum); cnt = bk::warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(g_sum_abs, 0ull - sum); atomicAdd(g_cnt_insert, 0ull - (unsigned long long)cnt); }
 }
 
 // ordered compaction of candidate record indices: each thread owns 16 consecutive class bytes

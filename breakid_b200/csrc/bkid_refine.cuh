@@ -159,7 +159,7 @@ struct EvRow {        // == bkid_sarow (include/breakid_b200.h), 96 bytes
 static_assert(sizeof(EvRow) == 88 || sizeof(EvRow) == 96, "EvRow layout");
 
 // K7a: one thread per SA-tagged record -- src/BreakID.cc:896-1016
-__global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long n_sa, const uint16_t *__restrict__ flag, const int32_t *__restrict__ tid,
+__global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long n_sa, const uint8_t *__restrict__ cls, const uint16_t *__restrict__ flag, const int32_t *__restrict__ tid,
                                  const int32_t *__restrict__ pos, const int32_t *__restrict__ endpos, const uint32_t *__restrict__ x_rec, long long n_x,
                                  const uint64_t *__restrict__ x_nh, int *__restrict__ missing, const uint32_t *__restrict__ cig_off, const uint32_t *__restrict__ cig_ops,
                                  const uint32_t *__restrict__ sa_off, const uint8_t *__restrict__ sa_txt, const uint32_t *__restrict__ oc_off,
@@ -192,7 +192,7 @@ __global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long 
       p = q;
     }
   }
-  if (sal == 0 || nf < 4 || (fl & F_DUP) || !(fl & F_PAIRED)) { rows[k] = R; return; }
+  if (sal == 0 || nf < 4 || (fl & F_DUP) || !(fl & F_PAIRED) || (cls[i] & CL_EXCL)) { rows[k] = R; return; }
   Roller sa_c, rec_c, c1;
   roller_set_text(sa_c, sa + fs[3], fe[3] - fs[3]);
   roller_set_bam(rec_c, cig_ops + cig_off[k], cig_off[k + 1] - cig_off[k]);
@@ -332,7 +332,7 @@ __device__ unsigned count_overlaps(const RefineView &v, int tid, int beg, int en
   long long hi = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)end);
   unsigned c = 0;
   for (long long i = lo + (threadIdx.x & 31); i < hi; i += 32)
-    if (v.endpos[i] > beg && (!depth_only || (v.cls[i] & CL_DEPTH))) ++c;
+    if (v.endpos[i] > beg && (depth_only ? (v.cls[i] & CL_DEPTH) : !(v.cls[i] & CL_EXCL))) ++c;
   return bk::warp_sum(c);
 }
 

@@ -42,6 +42,7 @@ static const char *kHelp =
     "     \t -all       \t no filter enspan out [default is filter]  \n "
     "     \t -s         \t sd multiplier of the distance formula [3]\n "
     "     \t -r         \t refGene.txt [$BREAKID_INSTALLDIR/ref_files/refGene.txt]\n "
+    "     \t -x         \t exclude regions (BED: chrom, start, end): records starting there are ignored [none]\n "
     "     \t -threads   \t BAM decode threads [8]\n "
     "     \t -gpu       \t CUDA device [0]\n ";
 
@@ -83,8 +84,8 @@ int main(int argc, char *argv[])
   double t_start = now_s();
   static struct option longopts[] = {
       {"help", 0, 0, 'h'}, {"i", 1, 0, 1}, {"o", 1, 0, 2}, {"q", 1, 0, 3}, {"n", 1, 0, 4}, {"fast", 0, 0, 5}, {"t", 1, 0, 6},
-      {"all", 0, 0, 7}, {"s", 1, 0, 8}, {"r", 1, 0, 9}, {"threads", 1, 0, 10}, {"gpu", 1, 0, 11}, {0, 0, 0, 0}};
-  std::string inp, out, nib_dir, refgene;
+      {"all", 0, 0, 7}, {"s", 1, 0, 8}, {"r", 1, 0, 9}, {"threads", 1, 0, 10}, {"gpu", 1, 0, 11}, {"x", 1, 0, 12}, {0, 0, 0, 0}};
+  std::string inp, out, nib_dir, refgene, exclude_bed;
   int qual = 20, times = 2, sd_mult = 3, threads = 8, gpu = 0;
   bool fast = false, filter = true;
   int opt, li;
@@ -104,6 +105,7 @@ int main(int argc, char *argv[])
       case 9: refgene = optarg; break;
       case 10: threads = std::max(1, atoi(optarg)); break;
       case 11: gpu = atoi(optarg); break;
+      case 12: exclude_bed = optarg; break;
       case '?':
         if (optopt == 0 && optind > 0 && (!strcmp(argv[optind - 1], "-?") || !strcmp(argv[optind - 1], "-help"))) { std::cerr << kHelp; exit(1); }
         std::cerr << kHelp;
@@ -151,6 +153,20 @@ int main(int argc, char *argv[])
   bkid_ctx *ctx = bkid_create(gpu, hdr, &prm);
   if (!ctx) { std::cerr << "Error: " << bkid_last_error(nullptr) << std::endl; exit(1); }
   auto die = [&](const char *what) { std::cerr << "Error: " << what << ": " << bkid_last_error(ctx) << std::endl; exit(1); };
+  if (!exclude_bed.empty()) {                          // additive: -x regions.bed (chrom, 0-based start, end); not a reference flag
+    std::ifstream bed(exclude_bed.c_str());
+    if (!bed.is_open()) { std::cerr << "Error: cannot open exclude bed-file: " << exclude_bed << std::endl; exit(1); }
+    std::vector<int32_t> xt, xb, xe;
+    std::string line;
+    while (std::getline(bed, line)) {
+      if (line.empty() || line[0] == '#' || !line.compare(0, 5, "track") || !line.compare(0, 7, "browser")) continue;
+      char chrom[256]; long b = 0, e = 0;
+      if (sscanf(line.c_str(), "%255s %ld %ld", chrom, &b, &e) != 3) continue;
+      for (int t = 0; t < hdr->n_targets; ++t)
+        if (names[t] == chrom) { xt.push_back(t); xb.push_back((int32_t)b); xe.push_back((int32_t)e); break; }
+    }
+    if (bkid_set_exclude(ctx, (int64_t)xt.size(), xt.data(), xb.data(), xe.data())) die("set_exclude");
+  }
   double t_push0 = now_s();
   bkid_decode_stats dst;
   memset(&dst, 0, sizeof dst);

@@ -197,6 +197,12 @@ int bkid_fetch_column(bkid_ctx *ctx, const char *name, void *out, int64_t cap_by
 /* forget all records (keeps allocations) */
 int bkid_reset(bkid_ctx *ctx);
 
+/* Extension (BASELINE.json north_star / configs[2]: exclude-BED; the reference has no such filter):
+ * records whose leftmost coordinate (tid, 0-based pos) lies in one of the half-open intervals [beg, end) are
+ * invisible to every stage -- the result is exactly what the reference computes on a BAM from which those records
+ * were removed.  Intervals may overlap and come in any order; n_intervals = 0 clears the filter.  Requires the
+ * coordinate-sorted record order BreakID needs anyway.  Call before bkid_insert_stats / bkid_run. */
+int bkid_set_exclude(bkid_ctx *ctx, int64_t n_intervals, const int32_t *tid, const int32_t *beg, const int32_t *end);
 /* replaces get_mean_insert_size (src/BreakID.cc:1909-1954) */
 int bkid_insert_stats(bkid_ctx *ctx, double *mean, double *sd);
 /* replaces scan_discordant_pairs (src/BreakID.cc:1362-1515): classify, mate join, p1/p2 order, bucket */

@@ -494,3 +494,111 @@ def test_driver_config4_tumour_fusions(tmp_path, flags):
                         capture_output=True, text=True, env=dict(os.environ, BKID_HOST_DECODE="1"))
     assert g2.returncode == 0
     assert open(str(tmp_path / "gpu_host") + "_fusion_all.txt").read() == open(str(tmp_path / "gpu") + "_fusion_all.txt").read()
+
+
+def _prefilter(hb, keep):
+    """HostBatch with only the records keep[i] (what a pre-filtered BAM decodes to)"""
+    from breakid_b200 import api
+    idx = np.nonzero(keep)[0]
+    cols = {k: v[idx] for k, v in hb.cols.items()}
+    nh = hb.name_hash.reshape(-1, 2)[idx].reshape(-1)
+    s = hb.side
+    sa_keep = np.nonzero(keep[s["sa_rec"].astype(np.int64)])[0]
+    new_index = np.cumsum(keep) - 1
+    side = {"sa_rec": new_index[s["sa_rec"].astype(np.int64)[sa_keep]].astype(np.uint32)}
+    for off, dat, dt in (("cig_off", "cig_ops", np.uint32), ("sa_off", "sa_txt", np.uint8), ("oc_off", "oc_txt", np.uint8)):
+        o = s[off].astype(np.int64)
+        parts = [s[dat][o[k]:o[k + 1]] for k in sa_keep]
+        side[dat] = np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt)
+        side[off] = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.uint32)
+    return api.HostBatch(cols, nh, side, hb.target_len, hb.target_names)
+
+
+def _exclude_intervals(d, rng):
+    """intervals that hit planted junctions, noise, chromosome starts/ends; overlapping, touching, empty and duplicate ones"""
+    tr = {k: v.numpy() for k, v in d.truth.items()}
+    iv = []
+    for j in range(0, len(tr["A"]), 3):                       # knock out one side of every third SV
+        iv.append((int(tr["A"][j]), int(tr["a"][j]) - 400, int(tr["a"][j]) + 300))
+    for j in range(1, len(tr["A"]), 4):                       # and thin the other side of some (removes part of the split reads)
+        iv.append((int(tr["B"][j]), int(tr["b"][j]) - 5, int(tr["b"][j]) + 40))
+    L = d.cfg.chrom_lens
+    for t, l in enumerate(L):
+        iv += [(t, 0, 3000), (t, l - 2500, l + 100), (t, l // 2, l // 2 + 5000), (t, l // 2 + 4000, l // 2 + 9000), (t, l // 2 + 9000, l // 2 + 9500)]
+        iv += [(t, int(x), int(x) + int(rng.randint(1, 2000))) for x in rng.randint(0, l, 6)]
+    iv += [(0, 500, 500), (0, 700, 600), (1, -50, 10), (0, 100000, 100001), (0, 100000, 100001)]
+    return np.array(iv, dtype=np.int64)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_exclude_intervals_equal_prefiltered_input(config1_data, mode):
+    """extension (BASELINE.json configs[2]: exclude-BED): device-side exclusion == the oracle on a pre-filtered batch"""
+    import oracle_py as O
+    d, hb, nibs = config1_data
+    iv = _exclude_intervals(d, np.random.RandomState(8))
+    tid, pos = hb.cols["tid"].astype(np.int64), hb.cols["pos"].astype(np.int64)
+    keep = np.ones(hb.n, bool)
+    for t, b, e in iv:
+        keep &= ~((tid == t) & (pos >= max(b, 0)) & (pos < e))
+    assert 0.02 < 1 - keep.mean() < 0.5
+    hbf = _prefilter(hb, keep)
+    om, osd, od, exp = O.run(hbf, nibs, mode=mode)
+    c = _ctx_for(hb, fast=mode)
+    c.set_exclude(iv[:, 0], iv[:, 1], iv[:, 2])
+    for t, (p, l) in enumerate(nibs):
+        c.set_nib(t, p, l)
+    mean, sd, dist, ncall = c.run()
+    got = c.fetch_clusters()
+    assert (mean, sd, dist) == (om, osd, od)
+    assert got.tobytes() == exp.tobytes()
+    assert 3 <= len(got) < 10                                  # some planted SVs were knocked out, some survive
+    # clearing the filter restores the unfiltered result
+    c.set_exclude([], [], [])
+    m2, s2, d2, _ = c.run()
+    o2 = O.run(hb, nibs, mode=mode)
+    assert (m2, s2, d2) == o2[:3] and c.fetch_clusters().tobytes() == o2[3].tobytes()
+    c.close()
+
+
+def test_driver_exclude_bed_matches_reference_on_prefiltered_bam(tmp_path):
+    """driver -x regions.bed on the full BAM == the reference binary on a BAM written without the excluded records"""
+    import os
+    import subprocess
+    import torch
+    import oracle_py as O
+    from breakid_b200 import bamio, synth
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    cfg = synth.SynthConfig(chrom_lens=[300000, 200000, 150000], n_tra=3, n_inv=2, n_dup=2, n_del=2, seed=21, sv_jitter=1)
+    d = synth.generate(cfg)
+    iv = _exclude_intervals(d, np.random.RandomState(4))
+    full = bamio.write_dataset(str(tmp_path / "full"), d, genes_per_mb=25.0)
+    with open(str(tmp_path / "ex.bed"), "w") as f:
+        f.write("# exclude regions\ntrack name=x\n")
+        for t, b, e in iv:
+            f.write("%s\t%d\t%d\n" % (synth.chrom_name(int(t)), max(int(b), 0), int(e)))
+        f.write("chrUn\t5\t10\n")
+    tid, pos = d.cols["tid"].numpy().astype(np.int64), d.cols["pos"].numpy().astype(np.int64)
+    keep = np.ones(d.n, bool)
+    for t, b, e in iv:
+        keep &= ~((tid == t) & (pos >= max(b, 0)) & (pos < e))
+    kt = torch.from_numpy(keep)
+    new_index = torch.cumsum(kt.to(torch.int64), 0) - 1
+    sa_keep = kt[d.sa_rec]
+    parts = lambda off, dat: torch.cat([dat[int(off[k]):int(off[k + 1])] for k in torch.nonzero(sa_keep).flatten().tolist()] or [dat[:0]])
+    lens = lambda off: (off[1:] - off[:-1])[sa_keep]
+    mkoff = lambda l: torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(l, 0)])
+    d2 = synth.SynthData(cfg=cfg, cols={k: v[kt] for k, v in d.cols.items()}, sa_rec=new_index[d.sa_rec[sa_keep]],
+                         cig_off=mkoff(lens(d.cig_off)), cig_ops=parts(d.cig_off, d.cig_ops), sa_off=mkoff(lens(d.sa_off)), sa_txt=parts(d.sa_off, d.sa_txt), truth=d.truth)
+    filt = bamio.write_dataset(str(tmp_path / "filt"), d2, genes_per_mb=25.0)
+    O.ref_index(filt["bam"]); O.ref_index(full["bam"])
+    O.ref_install_refgene(full["refgene"])
+    r = O.ref_run_binary(filt["bam"], str(tmp_path / "ref"), filt["nib"])
+    assert r.returncode == 0, r.stderr[-500:]
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breakid_b200", "host", "BreakID")
+    g = subprocess.run([drv, "-i", full["bam"], "-o", str(tmp_path / "gpu"), "-n", full["nib"], "-r", full["refgene"], "-all", "-x", str(tmp_path / "ex.bed")],
+                       capture_output=True, text=True)
+    assert g.returncode == 0, g.stderr[-500:]
+    for suffix in ("_fusion.txt", "_fusion_all.txt"):
+        assert open(str(tmp_path / "ref") + suffix).read() == open(str(tmp_path / "gpu") + suffix).read(), suffix
+    assert len(open(str(tmp_path / "gpu") + "_fusion_all.txt").read().splitlines()) >= 4
