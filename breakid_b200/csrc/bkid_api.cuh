@@ -313,7 +313,11 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   bk::exclusive_scan<unsigned long long, unsigned long long>(pts_sz, pts_off, ncomp, stmp, tot, st);
   bk::exclusive_scan<unsigned long long, unsigned long long>(row_sz, row_off, ncomp, stmp, tot2, st);
   unsigned long long pool[2] = {0, 0};
+  std::vector<uint32_t> seg_h((size_t)nseg + 1);
+  CU(c, cudaMemcpyAsync(seg_h.data(), seg, (size_t)(nseg + 1) * 4, cudaMemcpyDeviceToHost, st));
   CU(c, cudaMemcpyAsync(pool, tot, 16, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+  bool have_large = false;                               // any bucket beyond the shared-memory replay classes?
+  for (int b = 0; b < nseg; ++b) have_large |= seg_h[b + 1] - seg_h[b] >= 4096u;
   if ((pool[0] * 4 + pool[1] * 12) > (100ull << 30)) return fail(c, BKID_ERR_NOMEM, "AHC component too large for the row pools");
   BK_LAUNCH(ahc_bucket_comp_off, GRID1(nseg + 1, 128), 128, 0, st, comp_bucket, ncomp, (uint32_t)nseg, bucket_comp_off);
   // node arrays + pools + events
@@ -362,7 +366,7 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 900, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, 900u);
   BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 900u, 4096u);
   T_.mark("ahc: replay smem (flagged)");
-  {
+  if (have_large) {
     // buckets >= 4096 points without flagged components: rank form in global memory
     DBuf &RG = c->tmpF;
     size_t nn = (size_t)n + 8;
@@ -383,7 +387,15 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
     CU(c, cudaMemsetAsync(g.is_head, 0, nn * 4, st));
     BK_LAUNCH(ahc_rg_bucket_events, GRID1(ncomp, 128), 128, 0, st, v, ncomp, bucket_events);
     BK_LAUNCH(ahc_rg_prepare, GRID1(ncomp, 128), 128, 0, st, v, g, ncomp, bucket_flag, 4096u);
-    BK_LAUNCH(ahc_rg_rank, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u);
+    {
+      uint64_t *rk = c->sc.keys.as<uint64_t>();
+      uint32_t *rv = c->sc.vals.as<uint32_t>();
+      BK_LAUNCH(ahc_rg_sortkeys, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u, rk, rv);
+      bk::radix_sort_pairs(rk, rv, n, 0, 64, c->sc.rt(), st);
+      BK_LAUNCH(ahc_rg_bucketkeys, GRID1(n, 256), 256, 0, st, curb, rv, n, rk);
+      bk::radix_sort_pairs(rk, rv, n, 0, bbits, c->sc.rt(), st);
+      BK_LAUNCH(ahc_rg_rank_sorted, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u, rv);
+    }
     BK_LAUNCH(ahc_rg_heads, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u, bucket_events);
     bk::exclusive_scan<uint32_t, uint32_t>(g.is_head, head_excl, n, stmp, tot, st);
     BK_LAUNCH(ahc_rg_head_list, GRID1(n, 256), 256, 0, st, g.is_head, head_excl, n, head_pos);
@@ -819,7 +831,7 @@ static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *
   uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
   uint32_t *blkN = (uint32_t *)bp;
   long long *out = (long long *)(c->counters.as<unsigned>() + 8);
-  BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, nb, blkF, blkCum, blkN, blkA, t_in, out);
+  BK_LAUNCH(sd_resolve, 1, SDR_T, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, nb, blkF, blkCum, blkN, blkA, t_in, out);
   T_.mark("sd: resolve");
   long long h[2] = {0, 0};
   CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
@@ -850,7 +862,7 @@ static int side_launch(bkid_ctx *c)
     uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
     uint32_t *blkN = (uint32_t *)bp;
     long long *out = (long long *)(c->counters.as<unsigned>() + 8);
-    BK_LAUNCH(sd_resolve, 1, 1024, SD_BLOCK * 9, s2, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, 0ll, out);
+    BK_LAUNCH(sd_resolve, 1, SDR_T, SD_BLOCK * 9, s2, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, 0ll, out);
   }
   cudaEventRecord(c->ev_side[1], s2);
   // the max reference span bounds the region-query windows of the refinement only: its own stream, collected there

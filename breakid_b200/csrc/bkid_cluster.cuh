@@ -580,6 +580,43 @@ __global__ void __launch_bounds__(256) ahc_rg_rank(AhcView v, RankGlobal g, cons
   g.rank[e] = cnt; g.order[s0 + cnt] = (uint32_t)e; g.tie[e] = t ? 1 : 0;
 }
 
+// The rank of an event under (prefix-max distance, slot) inside its bucket is its position after two stable radix
+// sorts -- by the bit pattern of the (non-negative) prefix max, then by bucket -- instead of O(M^2) counting: buckets
+// of tens of thousands of points (deep coverage, multi-GPU bucket owners) made the counting pass the longest kernel
+// of the whole step.
+__global__ void ahc_rg_sortkeys(AhcView v, RankGlobal g, const uint32_t *__restrict__ point_bucket, long long n, const int32_t *__restrict__ bucket_flag, uint32_t n_lo,
+                                uint64_t *__restrict__ key, uint32_t *__restrict__ val)
+{
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  uint32_t b = point_bucket[e];
+  bool live = !bucket_flag[b] && v.seg_off[b + 1] - v.seg_off[b] >= n_lo;
+  key[e] = live ? (uint64_t)__double_as_longlong(g.pm[e]) : 0x7ff0000000000000ull;
+  val[e] = (uint32_t)e;
+}
+__global__ void ahc_rg_bucketkeys(const uint32_t *__restrict__ point_bucket, const uint32_t *__restrict__ val, long long n, uint64_t *__restrict__ key)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) key[p] = point_bucket[val[p]];
+}
+__global__ void __launch_bounds__(256) ahc_rg_rank_sorted(AhcView v, RankGlobal g, const uint32_t *__restrict__ point_bucket, long long n, const int32_t *__restrict__ bucket_flag,
+                                                          uint32_t n_lo, const uint32_t *__restrict__ sorted)
+{
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t e = sorted[p];
+  uint32_t b = point_bucket[e];
+  uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
+  if (bucket_flag[b] || s1 - s0 < n_lo) return;
+  double pm = g.pm[e];
+  if (!(pm < 1.0e300)) return;                         // unused slot (sorted behind every event of its bucket)
+  uint32_t ce = g.slot_comp[e];
+  bool t = false;
+  for (long long q = p - 1; q >= (long long)s0 && !t; --q) { uint32_t o = sorted[q]; if (g.pm[o] != pm) break; t = g.slot_comp[o] != ce; }
+  for (long long q = p + 1; q < (long long)s1 && !t; ++q) { uint32_t o = sorted[q]; if (g.pm[o] != pm) break; t = g.slot_comp[o] != ce; }
+  g.rank[e] = (uint32_t)(p - s0); g.order[p] = e; g.tie[e] = t ? 1 : 0;
+}
+
 // group heads in rank order (a group = maximal run of one exact prefix-max value touching >= 2 components)
 __global__ void ahc_rg_heads(AhcView v, RankGlobal g, const uint32_t *__restrict__ point_bucket, long long n, const int32_t *__restrict__ bucket_flag, uint32_t n_lo,
                              const uint32_t *__restrict__ bucket_events)

@@ -236,7 +236,7 @@ k1_compact(const uint8_t *__restrict__ cls, long long n, const uint32_t *__restr
 // c = [frac(a) >= 1 - 2^(k-53)], k = floor(log2(t + a)): the correction depends on the running
 // total only through its binade.  So one pass computes, per block of SD_BLOCK records, F = sum of
 // floor(a) and the cumulative histogram cum[k] = #{ i : kmin_i <= k } (kmin_i = 53+ceil(log2(1-frac)));
-// a single-CTA resolver then walks the blocks with exact integer arithmetic, 1024 blocks per step,
+// a single-CTA resolver then walks the blocks with exact integer arithmetic, 4096 blocks per step,
 // and only blocks that really straddle a power of two are re-read element by element.
 // Totals >= 2^52 leave the closed form: the host then runs the literal sequential kernel.
 // =============================================================================================
@@ -369,8 +369,10 @@ sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isiz
   if (threadIdx.x >= 32 && threadIdx.x < SD_K) blkCum[(size_t)blockIdx.x * SD_K + threadIdx.x] = sh32[0] + sh32[1 + (threadIdx.x - 32)];
 }
 
-// single CTA, 1024 threads.  out[0] = sd_total, out[1] = out-of-regime flag.
-__global__ void __launch_bounds__(1024)
+// single CTA of SDR_T threads (few threads: the walk is a chain of block-wide barriers, which are cheaper on a
+// small CTA).  out[0] = sd_total, out[1] = out-of-regime flag.
+constexpr int SDR_T = 256;
+__global__ void __launch_bounds__(SDR_T)
 sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, int nb,
            const long long *__restrict__ blkF, const uint32_t *__restrict__ blkCum, const uint32_t *__restrict__ blkN,
            const double *__restrict__ blkAmax, long long t_in, long long *__restrict__ out)
@@ -383,7 +385,7 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
   __shared__ int sh_j, sh_q, sh_oor, sh_k;
   if (threadIdx.x == 0) { sh_t = t_in; sh_j = 0; sh_oor = 0; }
   __syncthreads();
-  constexpr int PB = 8;                     // blocks per thread and step: 8192 blocks per step
+  constexpr int PB = 16;                    // blocks per thread and step: 4096 blocks per step
   while (true) {
     int j0 = sh_j;
     long long t0 = sh_t;
@@ -405,7 +407,7 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
     long long tot;
     long long tstart = t0 + bk::block_excl_scan<long long>(delta, sh_scan, tot);
     // a block is valid iff every s in it stays in binade k0
-    int first_bad = 1024 * PB;
+    int first_bad = SDR_T * PB;
     long long tend_of[PB];
     {
       long long ts = tstart;
@@ -418,15 +420,15 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
           double upper = (double)(ts + dl[i] + (long long)bn + 2) + blkAmax[j] * 1.000000001 + 2.0;
           valid = (bn == 0) || (k0 < SD_K && binade_of((double)ts) == k0 && binade_of(upper) == k0);
           if (bn != 0 && k0 >= SD_K) valid = false;
-          if (!valid && first_bad == 1024 * PB) first_bad = (int)threadIdx.x * PB + i;
+          if (!valid && first_bad == SDR_T * PB) first_bad = (int)threadIdx.x * PB + i;
         }
         ts += dl[i];
         tend_of[i] = ts;
       }
     }
-    if (threadIdx.x == 0) sh_q = 1024 * PB;
+    if (threadIdx.x == 0) sh_q = SDR_T * PB;
     __syncthreads();
-    if (first_bad < 1024 * PB) atomicMin(&sh_q, first_bad);
+    if (first_bad < SDR_T * PB) atomicMin(&sh_q, first_bad);
     __syncthreads();
     int q = sh_q;
     int nvalid = min(q, nb - j0);          // blocks j0 .. j0+nvalid-1 are final
@@ -438,7 +440,7 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
       sh_t = te; sh_j = j0 + nvalid;
     }
     __syncthreads();
-    if (q >= 1024 * PB || j0 + q >= nb) continue;
+    if (q >= SDR_T * PB || j0 + q >= nb) continue;
     // block jq = j0+q is either the first block of a new binade or a real straddler
     int jq = j0 + q;
     long long t = sh_t;
@@ -450,13 +452,13 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
     // ---- exact element-level evaluation of block jq ----
     long long base = (long long)jq * SD_BLOCK;
     int m = (int)min((long long)SD_BLOCK, n - base);
-    for (int e = threadIdx.x; e < SD_BLOCK; e += 1024) {
+    for (int e = threadIdx.x; e < SD_BLOCK; e += SDR_T) {
       double a = -1.0; unsigned km = 255u;
       if (e < m && (cls[base + e] & CL_INSERT)) { long long fa; sd_elem(isize[base + e], mean, a, fa, km); }
       sa[e] = a; skm[e] = (unsigned char)km;
     }
     __syncthreads();
-    constexpr int PER = SD_BLOCK / 1024;
+    constexpr int PER = SD_BLOCK / SDR_T;
     int p = 0;
     while (p < m) {
       // first eligible element at or after p defines the current binade
