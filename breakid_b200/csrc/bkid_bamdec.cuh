@@ -6,7 +6,8 @@
 // The host only walks the BGZF block headers (BSIZE / ISIZE) and parses the BAM header; compressed bytes go to
 // the GPU as they are in the file.
 //
-//   bgzf_inflate      one warp per BGZF block (bkid_inflate.cuh), 8 warps per CTA, tables in shared memory
+//   bgzf_inflate      groups of 8 lanes, one BGZF block each, four groups per warp in lock step (bkid_inflate.cuh);
+//                     4 warps per CTA, 2.3 KB of Huffman tables per group in shared memory
 //   bam_seed          record boundaries are a serial chain (each record starts where the previous one ends); the
 //                     uncompressed chunk is cut into 256 KiB segments and every segment gets a SEED: the first
 //                     offset that passes a strong record-header predicate three records deep
@@ -17,7 +18,8 @@
 //   bam_extract_cols  one thread per record: dense columns + per-record sizes of its sparse / SA table entries
 //   bam_extract_side  after the scans: sparse mate/name table, SA side table (cigar ops, SA / OC text)
 //
-// Chunks of <= 128 MiB compressed / 512 MiB uncompressed stream through double-buffered staging, so a whole-genome
+// Chunks of <= 1.5 GiB compressed / 3 GiB uncompressed (~48k BGZF blocks: several waves of the inflate grid) stream
+// through double-buffered staging, so a whole-genome
 // BAM (uncompressed 200+ GB) never has to be resident: only the 19 B/record columns stay.
 #pragma once
 #include "bkid_inflate.cuh"
@@ -26,19 +28,40 @@ namespace bamdec {
 
 constexpr uint32_t SEG = 256u << 10;
 constexpr uint32_t NONE = 0xffffffffu;
-constexpr int INF_WARPS = 8;
+constexpr int INF_WARPS = 4;          // warps per CTA
+constexpr int INF_GS = 8;             // lanes per group: four groups per warp, one BGZF block each
+constexpr int INF_NG = 32 / INF_GS;
+constexpr int INF_TOKENS = 8;         // tokens per group and lock-step round
 
 struct Task { uint64_t src; uint32_t dst; uint32_t clen, ulen; };
 
-__global__ void __launch_bounds__(INF_WARPS * 32, 4) bgzf_inflate(const uint8_t *__restrict__ comp, const Task *__restrict__ tasks, int ntask, uint8_t *__restrict__ unc, int *__restrict__ err)
+// All groups of a warp go through the decoder's phases in one instruction stream: a round runs at most one block
+// header (groups that are not at a header wait) and INF_TOKENS tokens per group; __all_sync closes the round and
+// reconverges the warp.  Blocks are dealt to groups round-robin.
+__global__ void __launch_bounds__(INF_WARPS * 32, 6) bgzf_inflate(const uint8_t *__restrict__ comp, const Task *__restrict__ tasks, int ntask, uint8_t *__restrict__ unc, int *__restrict__ err)
 {
-  __shared__ bki::Tables T[INF_WARPS];
-  int w = threadIdx.x >> 5;
-  for (int t = blockIdx.x * INF_WARPS + w; t < ntask; t += gridDim.x * INF_WARPS) {
-    Task k = tasks[t];
-    int rc = bki::inflate_raw(comp + k.src, k.clen, unc + k.dst, k.ulen, T[w]);
-    if (rc && (threadIdx.x & 31) == 0) atomicCAS(err, 0, (t << 4) | rc);
-    __syncwarp();
+  __shared__ bki::Tables T[INF_WARPS][INF_NG];
+  enum { FETCH = 3, IDLE = 4 };
+  const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / INF_GS;
+  bki::Tables &Tg = T[w][grp];
+  const int ngroups = gridDim.x * INF_WARPS * INF_NG;
+  int t = (blockIdx.x * INF_WARPS + w) * INF_NG + grp;
+  bki::Stream s;
+  s.phase = FETCH; s.out = nullptr; s.op = 0; s.out_len = 0; s.last = 0;
+  bki::br_init(s.b, nullptr, 0);
+  for (;;) {
+    if (s.phase == FETCH) {
+      if (t >= ntask) s.phase = IDLE;
+      else { Task k = tasks[t]; bki::stream_init(s, comp + k.src, k.clen, unc + k.dst, k.ulen); }
+    }
+    int rc = 0;
+    bool finished = false;
+    if (s.phase == bki::PH_HEADER) rc = bki::header_step<INF_GS>(s, Tg);
+    if (s.phase == bki::PH_TOKENS && !rc) rc = bki::token_steps<INF_GS>(s, Tg, INF_TOKENS);
+    if (s.phase == bki::PH_DONE && !rc) { rc = bki::stream_finish(s); finished = true; }
+    if (rc) { if ((threadIdx.x & (INF_GS - 1)) == 0) atomicCAS(err, 0, (t << 4) | rc); finished = true; }
+    if (finished) { s.phase = FETCH; t += ngroups; }
+    if (__all_sync(0xffffffffu, s.phase == IDLE)) break;
   }
 }
 
@@ -313,7 +336,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   cudaStream_t st = c->st;
   invalidate(c);
   memset(&d->stats, 0, sizeof d->stats);
-  size_t COMP_CAP = (size_t)512 << 20, UNC_CAP = (size_t)1024 << 20, CARRY_CAP = (size_t)64 << 20;
+  size_t COMP_CAP = (size_t)1536 << 20, UNC_CAP = (size_t)3072 << 20, CARRY_CAP = (size_t)64 << 20;   // unc offsets are 32-bit: UNC_CAP + CARRY_CAP < 4 GiB
   if (const char *e = getenv("BKID_BGZF_CHUNK_KB")) {          // tests: small chunks exercise the streaming / carry logic on small files
     long kb = atol(e);
     if (kb >= 64) { UNC_CAP = (size_t)kb << 10; COMP_CAP = UNC_CAP; }
@@ -411,7 +434,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     CU(c, cudaMemcpyAsync(dt, ht, (size_t)nt * sizeof(Task), cudaMemcpyHostToDevice, st));
     CU(c, cudaStreamWaitEvent(st, d->ev_h2d[slot], 0));
     cudaEventRecord(d->ev_t[1], st);
-    if (nt) BK_LAUNCH(bgzf_inflate, std::min((nt + INF_WARPS - 1) / INF_WARPS, 148 * 4), INF_WARPS * 32, 0, st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 4);
+    if (nt) BK_LAUNCH(bgzf_inflate, std::min((nt + INF_WARPS * INF_NG - 1) / (INF_WARPS * INF_NG), 148 * 6), INF_WARPS * 32, 0, st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 4);
     CU(c, cudaEventRecord(d->ev_free[slot], st));
     cudaEventRecord(d->ev_t[2], st);
     d->stats.n_blocks += nt; d->stats.uncompressed_bytes += (int64_t)(total - carry);

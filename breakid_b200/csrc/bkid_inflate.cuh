@@ -4,11 +4,14 @@
 // htslib-1.3.1/bgzf.c:388-419,545-600), i.e. zlib's inflate() called once per <= 64 KiB BGZF block.  BGZF blocks
 // are independent deflate streams, so a whole BAM decompresses block-parallel: one warp owns one block.
 //
-// Execution model ("warp-uniform decode"): all 32 lanes run the bit reader and the Huffman decode in lock
-// step on the same data (shared-memory tables and uniform global loads broadcast, no divergence, no
-// shuffles), and then split the only data-parallel part, the LZ77 match copy, between them.  An overlapping
-// match (distance < length) is periodic in its first `distance` bytes, so every output byte of a match can
-// be fetched independently: out[op+k] = out[op - dist + k % dist].
+// Execution model ("group-uniform decode"): a GROUP of GS lanes (GS = 8: four groups per warp, each on its own
+// BGZF block) runs the bit reader and the Huffman decode in lock step on the same data (shared-memory tables and
+// uniform global loads broadcast, no shuffles) and splits the only data-parallel part, the LZ77 match copy,
+// between its lanes.  An overlapping match (distance < length) is periodic in its first `distance` bytes, so
+// every output byte of a match can be fetched independently: out[op+k] = out[op - dist + k % dist].
+// The decoder is a resumable state machine (header_step / token_steps): the kernel drives all groups of a warp
+// through the same phase in the same instruction stream, so one issued instruction serves up to four blocks --
+// the first version (one block per warp) was instruction-issue bound at 31 warp-instructions per output byte.
 //
 // The same source compiles as plain C++ (one "lane") so the decoder logic is unit-tested on the CPU against
 // zlib-compressed streams (tests/test_inflate_host.py) before it ever runs on the GPU.
@@ -22,22 +25,23 @@
 #define BKI_FN inline
 #endif
 
+// lane geometry of a group of GS lanes (GS = 1 on the host)
 #if defined(__CUDA_ARCH__)
-#define BKI_LANES 32u
-#define BKI_LANE() (threadIdx.x & 31u)
-#define BKI_SYNC() __syncwarp()
+#define BKI_GSIZE(GS) ((unsigned)(GS))
+#define BKI_GLANE(GS) (threadIdx.x & (unsigned)((GS) - 1))
+#define BKI_GSYNC(GS) __syncwarp((GS) == 32 ? 0xffffffffu : ((((GS) == 32 ? 0u : (1u << ((GS) & 31))) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)((GS) - 1))))
 #else
-#define BKI_LANES 1u
-#define BKI_LANE() 0u
-#define BKI_SYNC() ((void)0)
+#define BKI_GSIZE(GS) 1u
+#define BKI_GLANE(GS) 0u
+#define BKI_GSYNC(GS) ((void)0)
 #endif
 
 namespace bki {
 
-constexpr int FAST_LIT_BITS = 10;
-constexpr int FAST_DIST_BITS = 8;
+constexpr int FAST_LIT_BITS = 9;
+constexpr int FAST_DIST_BITS = 7;
 
-// per-warp decode tables (shared memory on the device): 3.6 KB
+// per-group decode tables (shared memory on the device): 2.3 KB
 struct Tables {
   uint16_t lit_fast[1 << FAST_LIT_BITS];     // (symbol << 4) | code length, 0 = longer than FAST_LIT_BITS
   uint16_t dist_fast[1 << FAST_DIST_BITS];
@@ -132,151 +136,190 @@ BKI_FN int decode_sym(BitReader &b, const uint16_t *fast, int fast_bits, const u
   return -1;
 }
 
-// Inflate one raw deflate stream of `in_len` bytes into exactly `out_len` bytes.  All lanes of the warp call this
-// with identical arguments; returns the same status in every lane.
-BKI_FN int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, Tables &T)
-{
-  const unsigned lane = BKI_LANE();
+enum Phase { PH_HEADER = 0, PH_TOKENS = 1, PH_DONE = 2 };
+
+struct Stream {
   BitReader b;
-  br_init(b, in, in_len);
-  uint32_t op = 0;
-  int last = 0;
-  do {
-    last = (int)br_bits(b, 1);
-    int type = (int)br_bits(b, 2);
-    if (type == 0) {
-      // stored: skip to the byte boundary, LEN / NLEN, raw bytes
-      br_drop(b, b.cnt & 7);
-      uint32_t len = br_bits(b, 16), nlen = br_bits(b, 16);
-      if ((len ^ 0xffffu) != nlen) return ERR_STORED;
-      // bytes still in the bit buffer are at in[pos - cnt/8 ...]
-      uint32_t src = b.pos - (uint32_t)(b.cnt >> 3);
-      if (src + len > in_len) return ERR_INPUT;
-      if (op + len > out_len) return ERR_OUTPUT;
-      for (uint32_t k = lane; k < len; k += BKI_LANES) out[op + k] = in[src + k];
-      op += len;
-      br_init(b, in, in_len); b.pos = src + len;
+  uint8_t *out; uint32_t op, out_len;
+  int last, phase;
+};
+
+BKI_FN void stream_init(Stream &s, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len)
+{
+  br_init(s.b, in, in_len);
+  s.out = out; s.op = 0; s.out_len = out_len; s.last = 0; s.phase = PH_HEADER;
+}
+
+// one deflate block header: a stored block is copied whole; a Huffman block gets its tables built (lane 0 of the
+// group) and the stream moves to PH_TOKENS.  All lanes of the group call this with identical state.
+template <int GS>
+BKI_FN int header_step(Stream &s, Tables &T)
+{
+  const unsigned lane = BKI_GLANE(GS);
+  BitReader &b = s.b;
+  s.last = (int)br_bits(b, 1);
+  int type = (int)br_bits(b, 2);
+  if (type == 0) {
+    // stored: skip to the byte boundary, LEN / NLEN, raw bytes
+    br_drop(b, b.cnt & 7);
+    uint32_t len = br_bits(b, 16), nlen = br_bits(b, 16);
+    if ((len ^ 0xffffu) != nlen) return ERR_STORED;
+    uint32_t src = b.pos - (uint32_t)(b.cnt >> 3);        // bytes still in the bit buffer are at in[pos - cnt/8 ...]
+    if (src + len > b.len) return ERR_INPUT;
+    if (s.op + len > s.out_len) return ERR_OUTPUT;
+    for (uint32_t k = lane; k < len; k += BKI_GSIZE(GS)) s.out[s.op + k] = b.in[src + k];
+    s.op += len;
+    const uint8_t *in = b.in; uint32_t in_len = b.len;
+    br_init(b, in, in_len); b.pos = src + len;
+    s.phase = s.last ? PH_DONE : PH_HEADER;
+    return OK;
+  }
+  if (type == 3) return ERR_BTYPE;
+  int err = 0;
+  BKI_GSYNC(GS);                                          // previous block's table reads are done
+  if (type == 1) {
+    if (lane == 0) {
+      for (int k = 0; k < 144; ++k) T.lens[k] = 8;
+      for (int k = 144; k < 256; ++k) T.lens[k] = 9;
+      for (int k = 256; k < 280; ++k) T.lens[k] = 7;
+      for (int k = 280; k < 288; ++k) T.lens[k] = 8;
+      for (int k = 0; k < 30; ++k) T.lens[288 + k] = 5;
+      build(T.lens, 288, T.lit_count, T.lit_sym, T.lit_fast, FAST_LIT_BITS);
+      build(T.lens + 288, 30, T.dist_count, T.dist_sym, T.dist_fast, FAST_DIST_BITS);
+    }
+  } else {
+    int nlen = (int)br_bits(b, 5) + 257, ndist = (int)br_bits(b, 5) + 1, ncode = (int)br_bits(b, 4) + 4;
+    if (nlen > 286 || ndist > 30) return ERR_CODELEN;
+    // code-length code: 19 symbols of <= 7 bits, decoded bit-serially from per-lane (uniform) registers
+    const char *order = "\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f";
+    uint64_t cl = 0;                                      // 19 x 3 bits
+    for (int i = 0; i < ncode; ++i) cl |= (uint64_t)br_bits(b, 3) << (3 * (int)order[i]);
+    int cl_count[8], cl_offs[8];
+    for (int l = 0; l < 8; ++l) cl_count[l] = 0;
+    for (int k = 0; k < 19; ++k) cl_count[(cl >> (3 * k)) & 7]++;
+    {
+      int left = 1;
+      for (int l = 1; l < 8; ++l) { left <<= 1; left -= cl_count[l]; if (left < 0) return ERR_OVERSUB; }
+    }
+    cl_offs[1] = 0;
+    for (int l = 1; l < 7; ++l) cl_offs[l + 1] = cl_offs[l] + cl_count[l];
+    uint64_t cl_sym_lo = 0, cl_sym_hi = 0;                // sorted symbols, 5 bits each: 12 in lo, 7 in hi
+    for (int k = 0; k < 19; ++k) {
+      int l = (int)((cl >> (3 * k)) & 7);
+      if (!l) continue;
+      int q = cl_offs[l]++;
+      if (q < 12) cl_sym_lo |= (uint64_t)k << (5 * q); else cl_sym_hi |= (uint64_t)k << (5 * (q - 12));
+    }
+    int total = nlen + ndist, i = 0, prev = 0;
+    while (i < total) {
+      if (b.cnt < 16) br_refill(b);
+      int code = 0, first = 0, index = 0, sym = -1;
+      uint64_t bits = b.buf;
+      for (int l = 1; l <= 7; ++l) {
+        code |= (int)(bits & 1u); bits >>= 1;
+        int c = cl_count[l];
+        if (code - c < first) {
+          int q = index + (code - first);
+          sym = (int)((q < 12 ? (cl_sym_lo >> (5 * q)) : (cl_sym_hi >> (5 * (q - 12)))) & 31);
+          br_drop(b, l);
+          break;
+        }
+        index += c; first += c; first <<= 1; code <<= 1;
+      }
+      if (sym < 0) return ERR_CODELEN;
+      if (sym < 16) { if (lane == 0) T.lens[i] = (uint8_t)sym; prev = sym; ++i; }
+      else {
+        int rep, val = 0;
+        if (sym == 16) { if (i == 0) return ERR_CODELEN; val = prev; rep = 3 + (int)br_bits(b, 2); }
+        else if (sym == 17) rep = 3 + (int)br_bits(b, 3);
+        else rep = 11 + (int)br_bits(b, 7);
+        if (i + rep > total) return ERR_CODELEN;
+        if (lane == 0) for (int k = 0; k < rep; ++k) T.lens[i + k] = (uint8_t)val;
+        i += rep; prev = val;
+      }
+    }
+    if (lane == 0) {
+      // the distance lengths follow the literal/length lengths directly: move them to their own slot
+      uint8_t tmp[32];
+      for (int k = 0; k < ndist; ++k) tmp[k] = T.lens[nlen + k];
+      for (int k = nlen; k < 288; ++k) T.lens[k] = 0;
+      for (int k = 0; k < 32; ++k) T.lens[288 + k] = k < ndist ? tmp[k] : 0;
+      int e1 = build(T.lens, 288, T.lit_count, T.lit_sym, T.lit_fast, FAST_LIT_BITS);
+      int e2 = build(T.lens + 288, 32, T.dist_count, T.dist_sym, T.dist_fast, FAST_DIST_BITS);
+      T.lens[0] = (uint8_t)(e1 | e2);                     // status for the other lanes (lens[] is scratch from here on)
+    }
+    BKI_GSYNC(GS);
+    err = T.lens[0] ? ERR_OVERSUB : 0;
+  }
+  BKI_GSYNC(GS);
+  if (err) return err;
+  s.phase = PH_TOKENS;
+  return OK;
+}
+
+// up to `max_tokens` literal / match tokens of the current Huffman block; at the end-of-block symbol the stream moves
+// on to PH_HEADER or PH_DONE
+template <int GS>
+BKI_FN int token_steps(Stream &s, const Tables &T, int max_tokens)
+{
+  const unsigned lane = BKI_GLANE(GS);
+  BitReader &b = s.b;
+  for (int n = 0; n < max_tokens; ++n) {
+    int sym = decode_sym(b, T.lit_fast, FAST_LIT_BITS, T.lit_count, T.lit_sym);
+    if (sym < 0) return ERR_SYMBOL;
+    if (sym < 256) {
+      if (s.op >= s.out_len) return ERR_OUTPUT;
+      if (lane == 0) s.out[s.op] = (uint8_t)sym;
+      ++s.op;
       continue;
     }
-    if (type == 3) return ERR_BTYPE;
-    int err = 0;
-    BKI_SYNC();                                           // previous block's table reads are done
-    if (type == 1) {
-      if (lane == 0) {
-        for (int s = 0; s < 144; ++s) T.lens[s] = 8;
-        for (int s = 144; s < 256; ++s) T.lens[s] = 9;
-        for (int s = 256; s < 280; ++s) T.lens[s] = 7;
-        for (int s = 280; s < 288; ++s) T.lens[s] = 8;
-        for (int s = 0; s < 30; ++s) T.lens[288 + s] = 5;
-        build(T.lens, 288, T.lit_count, T.lit_sym, T.lit_fast, FAST_LIT_BITS);
-        build(T.lens + 288, 30, T.dist_count, T.dist_sym, T.dist_fast, FAST_DIST_BITS);
-      }
-    } else {
-      int nlen = (int)br_bits(b, 5) + 257, ndist = (int)br_bits(b, 5) + 1, ncode = (int)br_bits(b, 4) + 4;
-      if (nlen > 286 || ndist > 30) return ERR_CODELEN;
-      // code-length code: 19 symbols of <= 7 bits, decoded bit-serially from per-lane (uniform) registers
-      const char *order = "\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f";
-      uint64_t cl = 0;                                    // 19 x 3 bits
-      for (int i = 0; i < ncode; ++i) cl |= (uint64_t)br_bits(b, 3) << (3 * (int)order[i]);
-      int cl_count[8], cl_offs[8];
-      for (int l = 0; l < 8; ++l) cl_count[l] = 0;
-      for (int s = 0; s < 19; ++s) cl_count[(cl >> (3 * s)) & 7]++;
-      {
-        int left = 1;
-        for (int l = 1; l < 8; ++l) { left <<= 1; left -= cl_count[l]; if (left < 0) return ERR_OVERSUB; }
-      }
-      cl_offs[1] = 0;
-      for (int l = 1; l < 7; ++l) cl_offs[l + 1] = cl_offs[l] + cl_count[l];
-      uint64_t cl_sym_lo = 0, cl_sym_hi = 0;              // sorted symbols, 5 bits each: 12 in lo, 7 in hi
-      for (int s = 0; s < 19; ++s) {
-        int l = (int)((cl >> (3 * s)) & 7);
-        if (!l) continue;
-        int k = cl_offs[l]++;
-        if (k < 12) cl_sym_lo |= (uint64_t)s << (5 * k); else cl_sym_hi |= (uint64_t)s << (5 * (k - 12));
-      }
-      int total = nlen + ndist, i = 0, prev = 0;
-      while (i < total) {
-        if (b.cnt < 16) br_refill(b);
-        int code = 0, first = 0, index = 0, sym = -1;
-        uint64_t bits = b.buf;
-        for (int l = 1; l <= 7; ++l) {
-          code |= (int)(bits & 1u); bits >>= 1;
-          int c = cl_count[l];
-          if (code - c < first) {
-            int k = index + (code - first);
-            sym = (int)((k < 12 ? (cl_sym_lo >> (5 * k)) : (cl_sym_hi >> (5 * (k - 12)))) & 31);
-            br_drop(b, l);
-            break;
-          }
-          index += c; first += c; first <<= 1; code <<= 1;
-        }
-        if (sym < 0) return ERR_CODELEN;
-        if (sym < 16) { if (lane == 0) T.lens[i] = (uint8_t)sym; prev = sym; ++i; }
-        else {
-          int rep, val = 0;
-          if (sym == 16) { if (i == 0) return ERR_CODELEN; val = prev; rep = 3 + (int)br_bits(b, 2); }
-          else if (sym == 17) rep = 3 + (int)br_bits(b, 3);
-          else rep = 11 + (int)br_bits(b, 7);
-          if (i + rep > total) return ERR_CODELEN;
-          if (lane == 0) for (int k = 0; k < rep; ++k) T.lens[i + k] = (uint8_t)val;
-          i += rep; prev = val;
-        }
-      }
-      if (lane == 0) {
-        // the distance lengths follow the literal/length lengths directly: move them to their own slot
-        uint8_t tmp[32];
-        for (int s = 0; s < ndist; ++s) tmp[s] = T.lens[nlen + s];
-        for (int s = nlen; s < 288; ++s) T.lens[s] = 0;
-        for (int s = 0; s < 32; ++s) T.lens[288 + s] = s < ndist ? tmp[s] : 0;
-        int e1 = build(T.lens, 288, T.lit_count, T.lit_sym, T.lit_fast, FAST_LIT_BITS);
-        int e2 = build(T.lens + 288, 32, T.dist_count, T.dist_sym, T.dist_fast, FAST_DIST_BITS);
-        T.lens[0] = (uint8_t)(e1 | e2);                   // status for the other lanes (lens[] is scratch from here on)
-      }
-      BKI_SYNC();
-      err = T.lens[0] ? ERR_OVERSUB : 0;
+    if (sym == 256) { s.phase = s.last ? PH_DONE : PH_HEADER; return OK; }
+    if (sym > 285) return ERR_SYMBOL;
+    uint32_t len;
+    if (sym < 265) len = (uint32_t)sym - 254u;
+    else if (sym == 285) len = 258u;
+    else {
+      int e = (sym - 261) >> 2;
+      len = ((4u + (uint32_t)((sym - 261) & 3)) << e) + 3u + br_bits(b, e);
     }
-    BKI_SYNC();
-    if (err) return err;
-    // ---- symbols ----
-    for (;;) {
-      int sym = decode_sym(b, T.lit_fast, FAST_LIT_BITS, T.lit_count, T.lit_sym);
-      if (sym < 0) return ERR_SYMBOL;
-      if (sym < 256) {
-        if (op >= out_len) return ERR_OUTPUT;
-        if (lane == 0) out[op] = (uint8_t)sym;
-        ++op;
-        continue;
-      }
-      if (sym == 256) break;
-      if (sym > 285) return ERR_SYMBOL;
-      uint32_t len;
-      if (sym < 265) len = (uint32_t)sym - 254u;
-      else if (sym == 285) len = 258u;
-      else {
-        int e = (sym - 261) >> 2;
-        len = ((4u + (uint32_t)((sym - 261) & 3)) << e) + 3u + br_bits(b, e);
-      }
-      int ds = decode_sym(b, T.dist_fast, FAST_DIST_BITS, T.dist_count, T.dist_sym);
-      if (ds < 0 || ds > 29) return ERR_DIST;
-      uint32_t dist;
-      if (ds < 4) dist = (uint32_t)ds + 1u;
-      else {
-        int e = (ds >> 1) - 1;
-        dist = ((2u + (uint32_t)(ds & 1)) << e) + 1u + br_bits(b, e);
-      }
-      if (dist > op) return ERR_DIST;
-      if (op + len > out_len) return ERR_OUTPUT;
-      BKI_SYNC();                                         // bytes written by other lanes are visible before the copy reads them
-      const uint8_t *src = out + (op - dist);
-      uint8_t *dst = out + op;
-      if (dist >= len) { for (uint32_t k = lane; k < len; k += BKI_LANES) dst[k] = src[k]; }
-      else { for (uint32_t k = lane; k < len; k += BKI_LANES) dst[k] = src[k % dist]; }
-      op += len;
+    int ds = decode_sym(b, T.dist_fast, FAST_DIST_BITS, T.dist_count, T.dist_sym);
+    if (ds < 0 || ds > 29) return ERR_DIST;
+    uint32_t dist;
+    if (ds < 4) dist = (uint32_t)ds + 1u;
+    else {
+      int e = (ds >> 1) - 1;
+      dist = ((2u + (uint32_t)(ds & 1)) << e) + 1u + br_bits(b, e);
     }
-  } while (!last);
-  BKI_SYNC();
-  if (b.over > 8) return ERR_INPUT;                       // consumed bits beyond the payload (refill looks <= 5 bytes ahead)
-  return op == out_len ? OK : ERR_SIZE;
+    if (dist > s.op) return ERR_DIST;
+    if (s.op + len > s.out_len) return ERR_OUTPUT;
+    BKI_GSYNC(GS);                                        // bytes written by other lanes of the group are visible before the copy reads them
+    const uint8_t *src = s.out + (s.op - dist);
+    uint8_t *dst = s.out + s.op;
+    if (dist >= len) { for (uint32_t k = lane; k < len; k += BKI_GSIZE(GS)) dst[k] = src[k]; }
+    else { for (uint32_t k = lane; k < len; k += BKI_GSIZE(GS)) dst[k] = src[k % dist]; }
+    s.op += len;
+  }
+  return OK;
+}
+
+BKI_FN int stream_finish(const Stream &s)
+{
+  if (s.b.over > 8) return ERR_INPUT;                     // consumed bits beyond the payload (refill looks <= 5 bytes ahead)
+  return s.op == s.out_len ? OK : ERR_SIZE;
+}
+
+// Inflate one raw deflate stream of `in_len` bytes into exactly `out_len` bytes (one group, run to completion).
+template <int GS>
+BKI_FN int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, Tables &T)
+{
+  Stream s;
+  stream_init(s, in, in_len, out, out_len);
+  while (s.phase != PH_DONE) {
+    int rc = s.phase == PH_HEADER ? header_step<GS>(s, T) : token_steps<GS>(s, T, 1 << 30);
+    if (rc) return rc;
+  }
+  BKI_GSYNC(GS);
+  return stream_finish(s);
 }
 
 }  // namespace bki

@@ -18,6 +18,8 @@ def lib(tmp_path_factory):
     L = C.CDLL(out)
     L.bki_host_inflate.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32]
     L.bki_host_inflate.restype = C.c_int
+    L.bki_host_inflate_stepped.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int]
+    L.bki_host_inflate_stepped.restype = C.c_int
     return L
 
 
@@ -59,6 +61,10 @@ def test_matches_zlib(lib):
                 rc, out = _inflate(lib, comp, len(data))
                 assert rc == 0, (len(data), level, strategy, mem, rc)
                 assert out == data, (len(data), level, strategy, mem)
+                out2 = np.zeros(max(len(data), 1), np.uint8)            # resumable form, 1 and 7 tokens per step
+                for step in (1, 7):
+                    assert lib.bki_host_inflate_stepped(comp, len(comp), out2.ctypes.data, len(data), step) == 0
+                    assert out2[:len(data)].tobytes() == data, (len(data), level, strategy, mem, step)
                 n += 1
     assert n > 100
 

@@ -40,18 +40,22 @@ def main():
     bt = f.block_table()
     nblk = f.n_blocks
     if a.replicate > 1:
-        # repeat the record-only blocks: find the first block that starts at or after the first record
-        cum = np.concatenate([[0], np.cumsum(bt["usize"].astype(np.int64))])
-        b0 = int(np.searchsorted(cum, f.first_record, side="left"))
-        assert cum[b0] == f.first_record or True
-        body_lo = int(bt["payload_off"][b0]) - 18
-        body_hi = int(bt["payload_off"][-2] + bt["payload_len"][-2] + 8) if bt["usize"][-1] == 0 else len(raw)
-        # only valid when a record starts exactly at block b0; otherwise fall back to no replication
-        body = raw[body_lo:body_hi]
-        parts = [raw[:body_hi]] + [body] * (a.replicate - 1) + [raw[body_hi:]]
-        raw = np.concatenate(parts)
+        # one valid (unsorted) BAM whose record section is repeated: inflate everything, repeat the records, recompress
+        import zlib
+        from concurrent.futures import ThreadPoolExecutor
+        rawb = raw.tobytes()
+        payload = b"".join(zlib.decompress(rawb[int(b["payload_off"]):int(b["payload_off"]) + int(b["payload_len"])], -15) for b in bt if b["usize"])
+        payload = payload[:f.first_record] + payload[f.first_record:] * a.replicate
+        chunks = [payload[o:o + 0xff00] for o in range(0, len(payload), 0xff00)]
+        with ThreadPoolExecutor(os.cpu_count()) as pool:
+            comp = list(pool.map(lambda c: bamio._bgzf_block(c, 1), chunks))
         p2 = os.path.join(tmp, "rep.bam")
-        raw.tofile(p2)
+        with open(p2, "wb") as fo:
+            for c in comp:
+                fo.write(c)
+            fo.write(bamio._BGZF_EOF)
+        del payload, chunks, comp, rawb
+        raw = np.fromfile(p2, dtype=np.uint8)
         f.close()
         f = api.BgzfFile(p2)
         bt = f.block_table(); nblk = f.n_blocks
@@ -63,12 +67,7 @@ def main():
         ctx.reset()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        try:
-            n = ctx.push_bgzf(f, data_ptr=pinned.data_ptr())
-        except api.BkidError as e:
-            if a.replicate > 1:
-                print("replicated file rejected (a record straddles the first record block): " + str(e)); return
-            raise
+        n = ctx.push_bgzf(f, data_ptr=pinned.data_ptr())
         t1 = time.perf_counter()
         if a.replicate == 1:
             r = ctx.run(); cl = ctx.fetch_clusters()
