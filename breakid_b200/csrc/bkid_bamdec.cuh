@@ -355,9 +355,12 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   for (int64_t b0 = 0; b0 < n_blocks;) {
     size_t cb = 0, ub = 0; int64_t b1 = b0;
     uint64_t span0 = blocks[b0].payload_off;
+    // (a small first chunk to fill the copy pipeline sooner was measured slower: one inflate launch costs a full
+    // per-block latency of ~20 ms whatever its size, so fewer, bigger launches win)
+    const size_t ccap = COMP_CAP, ucap = UNC_CAP;
     while (b1 < n_blocks) {
       size_t span = (size_t)(blocks[b1].payload_off + blocks[b1].payload_len + 8 - span0);
-      if (b1 > b0 && (span > COMP_CAP || ub + blocks[b1].usize > UNC_CAP)) break;
+      if (b1 > b0 && (span > ccap || ub + blocks[b1].usize > ucap)) break;
       if (blocks[b1].usize > (1u << 16) || (b1 > b0 && blocks[b1].payload_off < blocks[b1 - 1].payload_off + blocks[b1 - 1].payload_len))
         return fail(c, BKID_ERR_IO, "corrupt BGZF block table");
       cb = span; ub += blocks[b1].usize; ++b1;

@@ -54,26 +54,33 @@ enum Err { OK = 0, ERR_BTYPE = 1, ERR_STORED = 2, ERR_CODELEN = 3, ERR_OVERSUB =
 
 struct BitReader {
   const uint8_t *in; uint32_t len, pos; uint64_t buf; int cnt; int over;
+  uint32_t nextw; int have_next;          // the aligned 32-bit word after `pos`, loaded one refill ahead
 };
 
-BKI_FN void br_init(BitReader &b, const uint8_t *in, uint32_t len) { b.in = in; b.len = len; b.pos = 0; b.buf = 0; b.cnt = 0; b.over = 0; }
+BKI_FN void br_init(BitReader &b, const uint8_t *in, uint32_t len) { b.in = in; b.len = len; b.pos = 0; b.buf = 0; b.cnt = 0; b.over = 0; b.nextw = 0; b.have_next = 0; }
 BKI_FN void br_refill(BitReader &b)
 {
-  // keep > 32 valid bits.  Aligned 32-bit loads where the payload allows (one load per 4 input bytes); bytes at a
-  // misaligned start and at the tail.  Past the end zeros are shifted in and counted (reported as ERR_INPUT).
+  // keep > 32 valid bits.  Aligned 32-bit loads where the payload allows, issued one refill AHEAD of their use so
+  // that the load latency hides behind the tokens decoded in between; bytes at a misaligned start and at the tail.
+  // Past the end zeros are shifted in and counted (reported as ERR_INPUT).
   while (b.cnt <= 32) {
+    if (b.have_next) {
+      b.buf |= (uint64_t)b.nextw << b.cnt;
+      b.cnt += 32; b.pos += 4;
+      b.have_next = 0;
+      if (b.pos + 4 <= b.len) { b.nextw = *reinterpret_cast<const uint32_t *>(b.in + b.pos); b.have_next = 1; }
+      continue;
+    }
     const uint8_t *p = b.in + b.pos;
     if ((((uintptr_t)p) & 3u) == 0 && b.pos + 4 <= b.len) {
-      uint64_t v = *reinterpret_cast<const uint32_t *>(p);
-      b.buf |= v << b.cnt;
-      b.cnt += 32; b.pos += 4;
-    } else {
-      uint64_t v = 0;
-      if (b.pos < b.len) v = *p; else b.over++;
-      b.pos++;
-      b.buf |= v << b.cnt;
-      b.cnt += 8;
+      b.nextw = *reinterpret_cast<const uint32_t *>(p); b.have_next = 1;       // prime the pipeline
+      continue;
     }
+    uint64_t v = 0;
+    if (b.pos < b.len) v = *p; else b.over++;
+    b.pos++;
+    b.buf |= v << b.cnt;
+    b.cnt += 8;
   }
 }
 BKI_FN uint32_t br_peek(const BitReader &b, int n) { return (uint32_t)(b.buf & ((1ull << n) - 1ull)); }
