@@ -31,7 +31,8 @@ class Batch(C.Structure):
                 ("tid", C.c_void_p), ("pos", C.c_void_p), ("isize", C.c_void_p), ("endpos", C.c_void_p),
                 ("n_x", C.c_int64), ("x_rec", C.c_void_p), ("x_mtid", C.c_void_p), ("x_mpos", C.c_void_p), ("x_name_hash", C.c_void_p),
                 ("n_sa", C.c_int64), ("sa_rec", C.c_void_p), ("cig_off", C.c_void_p), ("cig_ops", C.c_void_p),
-                ("sa_off", C.c_void_p), ("sa_txt", C.c_void_p), ("oc_off", C.c_void_p), ("oc_txt", C.c_void_p)]
+                ("sa_off", C.c_void_p), ("sa_txt", C.c_void_p), ("oc_off", C.c_void_p), ("oc_txt", C.c_void_p),
+                ("isize16", C.c_void_p), ("span16", C.c_void_p), ("n_tid_runs", C.c_int64), ("tid_run_start", C.c_void_p), ("tid_run_tid", C.c_void_p)]
 
 
 PAIR_DTYPE = np.dtype([
@@ -118,11 +119,40 @@ class HostBatch:
         self.target_names = [str(x) for x in target_names]
 
     # -- views -----------------------------------------------------------------------------
-    def struct(self) -> Batch:
+    def narrow(self) -> Dict[str, np.ndarray]:
+        """narrow encodings of isize / endpos / tid (include/breakid_b200.h) for the columns that fit; cached"""
+        if getattr(self, "_narrow", None) is None:
+            c, nr = self.cols, {}
+            if self.n:
+                sp = c["endpos"].astype(np.int64) - c["pos"].astype(np.int64)
+                if sp.min() >= 0 and sp.max() <= 65535:
+                    nr["span16"] = sp.astype(np.uint16)
+                fl = c["flag"]
+                read = ((fl & 1) != 0) & ((fl & 2) != 0) & ((fl & (0x4 | 0x100 | 0x200 | 0x400)) == 0)       # src/BreakID.cc:1932
+                iz = c["isize"]
+                if not read.any() or (iz[read].min() >= -32768 and iz[read].max() <= 32767):
+                    nr["isize16"] = np.clip(iz, -32768, 32767).astype(np.int16)
+                start = np.nonzero(np.concatenate([[True], c["tid"][1:] != c["tid"][:-1]]))[0]
+                if start.shape[0] <= 65536:
+                    nr["tid_run_start"] = start.astype(np.uint32)
+                    nr["tid_run_tid"] = np.ascontiguousarray(c["tid"][start])
+            self._narrow = nr
+        return self._narrow
+
+    def struct(self, narrow: bool = True) -> Batch:
         b = Batch()
         b.n = self.n
         for k, _ in _COLS:
             setattr(b, k, self.cols[k].ctypes.data)
+        if narrow:
+            nr = self.narrow()
+            if "span16" in nr:
+                b.span16 = nr["span16"].ctypes.data; b.endpos = None
+            if "isize16" in nr:
+                b.isize16 = nr["isize16"].ctypes.data; b.isize = None
+            if "tid_run_start" in nr:
+                b.n_tid_runs = int(nr["tid_run_start"].shape[0]); b.tid_run_start = nr["tid_run_start"].ctypes.data
+                b.tid_run_tid = nr["tid_run_tid"].ctypes.data; b.tid = None
         b.n_x = self.n_x
         for k, _ in _XCOLS:
             setattr(b, k, self.x[k].ctypes.data)
@@ -385,8 +415,8 @@ class Context:
     def reserve(self, n, n_x=0, n_sa=0, n_cig=0, sa_bytes=0, oc_bytes=0):
         self._chk(self.lib.bkid_reserve(self.ctx, n, n_x, n_sa, n_cig, sa_bytes, oc_bytes))
 
-    def push(self, hb: HostBatch):
-        b = hb.struct()
+    def push(self, hb: HostBatch, narrow: bool = True):
+        b = hb.struct(narrow)
         self._chk(self.lib.bkid_push_batch(self.ctx, C.byref(b)))
 
     def push_bgzf(self, f: "BgzfFile", data_ptr=None, blocks=None, n_blocks=None, first_record=None) -> int:

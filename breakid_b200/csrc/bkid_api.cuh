@@ -624,6 +624,26 @@ __global__ void add_offset_u32(uint32_t *p, long long n, uint32_t d)
   if (i < n) p[i] += d;
 }
 
+// widening of the narrow host encodings (include/breakid_b200.h: isize16 / span16 / tid runs)
+__global__ void widen_isize16(const int16_t *__restrict__ src, long long n, int32_t *__restrict__ dst)
+{
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (int32_t)src[i];
+}
+__global__ void widen_span16(const int32_t *__restrict__ pos, const uint16_t *__restrict__ span, long long n, int32_t *__restrict__ endpos)
+{
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) endpos[i] = pos[i] + (int32_t)span[i];
+}
+__global__ void widen_tid_runs(const uint32_t *__restrict__ start, const int32_t *__restrict__ rtid, int nruns, long long n, int32_t *__restrict__ tid)
+{
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int a = 0, b = nruns;                         // last run with start <= i
+  while (b - a > 1) { int m = (a + b) >> 1; if ((long long)start[m] <= i) a = m; else b = m; }
+  tid[i] = rtid[a];
+}
+
 static void set_ptrs(bkid_ctx *c)
 {
   c->p_flag = c->flag.as<uint16_t>(); c->p_mapq = c->mapq.as<uint8_t>(); c->p_tid = c->tid.as<int32_t>(); c->p_pos = c->pos.as<int32_t>();
@@ -636,6 +656,8 @@ static void set_ptrs(bkid_ctx *c)
 static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
 {
   if (!c || !b || b->n < 0 || b->n_sa < 0 || b->n_x < 0) return c ? fail(c, BKID_ERR_ARG, "bad batch") : BKID_ERR_ARG;
+  if (b->n > 0 && ((!b->isize && !b->isize16) || (!b->endpos && !b->span16) || (!b->tid && (b->n_tid_runs <= 0 || !b->tid_run_start || !b->tid_run_tid))))
+    return fail(c, BKID_ERR_ARG, "bad batch: a dense column is missing in both its wide and its narrow form");
   cudaSetDevice(c->device);
   cudaStream_t st = c->st;
   if ((unsigned long long)(c->n + b->n) >= 0xffffffffull) return fail(c, BKID_ERR_ARG, "more than 2^32-1 records per context");
@@ -657,10 +679,31 @@ static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
   if (n) {
     CU(c, cudaMemcpyAsync(c->flag.as<uint16_t>() + n0, b->flag, n * 2, kind, st));
     CU(c, cudaMemcpyAsync(c->mapq.as<uint8_t>() + n0, b->mapq, n, kind, st));
-    CU(c, cudaMemcpyAsync(c->tid.as<int32_t>() + n0, b->tid, n * 4, kind, st));
     CU(c, cudaMemcpyAsync(c->pos.as<int32_t>() + n0, b->pos, n * 4, kind, st));
-    CU(c, cudaMemcpyAsync(c->isize.as<int32_t>() + n0, b->isize, n * 4, kind, st));
-    CU(c, cudaMemcpyAsync(c->endpos.as<int32_t>() + n0, b->endpos, n * 4, kind, st));
+    // narrow encodings are staged in scratch and widened on the device
+    size_t stage = (b->isize16 ? n * 2 : 0) + (b->span16 ? n * 2 : 0) + (b->tid ? 0 : (size_t)b->n_tid_runs * 8) + 64;
+    TRY(c, c->tmpH.ensure(stage, 0, st));
+    char *sp = (char *)c->tmpH.p;
+    if (b->tid) CU(c, cudaMemcpyAsync(c->tid.as<int32_t>() + n0, b->tid, n * 4, kind, st));
+    else {
+      uint32_t *rs = (uint32_t *)sp; sp += (size_t)b->n_tid_runs * 4;
+      int32_t *rt = (int32_t *)sp; sp += (size_t)b->n_tid_runs * 4;
+      CU(c, cudaMemcpyAsync(rs, b->tid_run_start, (size_t)b->n_tid_runs * 4, kind, st));
+      CU(c, cudaMemcpyAsync(rt, b->tid_run_tid, (size_t)b->n_tid_runs * 4, kind, st));
+      BK_LAUNCH(widen_tid_runs, GRID1(n, 256), 256, 0, st, rs, rt, (int)b->n_tid_runs, (long long)n, c->tid.as<int32_t>() + n0);
+    }
+    if (b->isize) CU(c, cudaMemcpyAsync(c->isize.as<int32_t>() + n0, b->isize, n * 4, kind, st));
+    else {
+      int16_t *s16 = (int16_t *)sp; sp += n * 2;
+      CU(c, cudaMemcpyAsync(s16, b->isize16, n * 2, kind, st));
+      BK_LAUNCH(widen_isize16, GRID1(n, 256), 256, 0, st, s16, (long long)n, c->isize.as<int32_t>() + n0);
+    }
+    if (b->endpos) CU(c, cudaMemcpyAsync(c->endpos.as<int32_t>() + n0, b->endpos, n * 4, kind, st));
+    else {
+      uint16_t *e16 = (uint16_t *)sp; sp += n * 2;
+      CU(c, cudaMemcpyAsync(e16, b->span16, n * 2, kind, st));
+      BK_LAUNCH(widen_span16, GRID1(n, 256), 256, 0, st, c->pos.as<int32_t>() + n0, e16, (long long)n, c->endpos.as<int32_t>() + n0);
+    }
   }
   size_t nx = (size_t)b->n_x;
   if (nx) {
@@ -704,6 +747,7 @@ int bkid_push_batch_device(bkid_ctx *c, const bkid_batch *b)
     // adopt the caller's device columns without copying (already-resident input)
     cudaSetDevice(c->device);
     if ((unsigned long long)b->n >= 0xffffffffull) return fail(c, BKID_ERR_ARG, "more than 2^32-1 records per context");
+    if (b->n > 0 && (!b->tid || !b->isize || !b->endpos)) return fail(c, BKID_ERR_ARG, "bkid_push_batch_device needs the wide tid / isize / endpos columns");
     invalidate(c);
     c->borrowed = true;
     c->n = b->n; c->n_sa = b->n_sa; c->n_x = b->n_x;

@@ -77,6 +77,9 @@ struct bkid_host_bam {
   std::vector<uint8_t> sa_txt, oc_txt;
   int32_t first_l_qseq = 0;
   bkid_batch batch;
+  // narrow encodings (include/breakid_b200.h), filled when the whole batch fits them
+  std::vector<int16_t> isize16; std::vector<uint16_t> span16; std::vector<uint32_t> run_start; std::vector<int32_t> run_tid;
+  bkid_batch batch_narrow;
   double t_inflate = 0, t_parse = 0;
 };
 
@@ -271,11 +274,37 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
   B.sa_rec = h->sa_rec.data(); B.cig_off = h->cig_off.data(); B.cig_ops = h->cig_ops.data();
   B.sa_off = h->sa_off.data(); B.sa_txt = h->sa_txt.data();
   B.oc_off = h->oc_off.data(); B.oc_txt = h->oc_txt.data();
+  B.isize16 = nullptr; B.span16 = nullptr; B.n_tid_runs = 0; B.tid_run_start = nullptr; B.tid_run_tid = nullptr;
+  // narrow forms: 19 -> 11 B/record over PCIe when every value fits
+  h->batch_narrow = B;
+  {
+    bool span_ok = true, isz_ok = true;
+    for (size_t i = 0; i < n && (span_ok || isz_ok); ++i) {
+      int64_t sp = (int64_t)h->endpos[i] - (int64_t)h->pos[i];
+      if (sp < 0 || sp > 65535) span_ok = false;
+      uint16_t fl = h->flag[i];
+      bool read_isize = (fl & 0x1) && (fl & 0x2) && !(fl & (0x4 | 0x100 | 0x200 | 0x400));       // src/BreakID.cc:1932
+      if (read_isize && (h->isize[i] < -32768 || h->isize[i] > 32767)) isz_ok = false;
+    }
+    if (span_ok && n) { h->span16.resize(n); for (size_t i = 0; i < n; ++i) h->span16[i] = (uint16_t)(h->endpos[i] - h->pos[i]); h->batch_narrow.span16 = h->span16.data(); h->batch_narrow.endpos = nullptr; }
+    if (isz_ok && n) {
+      h->isize16.resize(n);
+      for (size_t i = 0; i < n; ++i) { int32_t v = h->isize[i]; h->isize16[i] = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
+      h->batch_narrow.isize16 = h->isize16.data(); h->batch_narrow.isize = nullptr;
+    }
+    for (size_t i = 0; i < n; ++i)
+      if (i == 0 || h->tid[i] != h->tid[i - 1]) { h->run_start.push_back((uint32_t)i); h->run_tid.push_back(h->tid[i]); }
+    if (n && h->run_start.size() <= 65536) {
+      h->batch_narrow.n_tid_runs = (int64_t)h->run_start.size(); h->batch_narrow.tid_run_start = h->run_start.data(); h->batch_narrow.tid_run_tid = h->run_tid.data();
+      h->batch_narrow.tid = nullptr;
+    }
+  }
   return h;
 }
 
 extern "C" const bkid_header *bkid_host_bam_header(const bkid_host_bam *h) { return &h->hdr; }
 extern "C" const bkid_batch *bkid_host_bam_batch(const bkid_host_bam *h) { return &h->batch; }
+extern "C" const bkid_batch *bkid_host_bam_batch_narrow(const bkid_host_bam *h) { return &h->batch_narrow; }
 extern "C" void bkid_host_bam_free(bkid_host_bam *h) { delete h; }
 
 // ---- host half of the device decode path ----------------------------------------------------------------

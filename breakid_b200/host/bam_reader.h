@@ -11,7 +11,8 @@ typedef struct bkid_host_bam bkid_host_bam;
 /* Decode a whole BAM into one record batch.  Returns NULL and fills `err` on failure. */
 bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char *err, int errlen);
 const bkid_header *bkid_host_bam_header(const bkid_host_bam *h);
-const bkid_batch *bkid_host_bam_batch(const bkid_host_bam *h);
+const bkid_batch *bkid_host_bam_batch(const bkid_host_bam *h);            /* wide columns */
+const bkid_batch *bkid_host_bam_batch_narrow(const bkid_host_bam *h);     /* same batch, narrow encodings where the data fits (11 B/record) */
 void bkid_host_bam_free(bkid_host_bam *h);
 
 

@@ -171,7 +171,7 @@ int main(int argc, char *argv[])
   bkid_decode_stats dst;
   memset(&dst, 0, sizeof dst);
   if (host_decode) {
-    if (bkid_push_batch(ctx, bkid_host_bam_batch(bam))) die("push_batch");
+    if (bkid_push_batch(ctx, bkid_host_bam_batch_narrow(bam))) die("push_batch");
   } else {
     int64_t nrec = 0;
     if (bkid_push_bgzf(ctx, bkid_host_bgzf_data(bgzf), bkid_host_bgzf_blocks(bgzf), bkid_host_bgzf_n_blocks(bgzf), bkid_host_bgzf_first_record(bgzf), &nrec)) {

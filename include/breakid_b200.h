@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BKID_ABI_VERSION 1
+#define BKID_ABI_VERSION 2
 
 typedef enum {
   BKID_OK = 0,
@@ -87,6 +87,16 @@ typedef struct {
   const uint8_t *sa_txt;            /* SA:Z value bytes, no terminator */
   const uint32_t *oc_off;           /* [n_sa+1] into oc_txt (all equal when no OC tags) */
   const uint8_t *oc_txt;
+  /* Optional narrow encodings of three dense columns for host batches (bkid_push_batch): a non-NULL narrow column
+   * REPLACES its wide column (pass that one as NULL); the device widens it after the copy.  19 -> 11 B/record
+   * over PCIe.  A decoder uses a narrow form only when the whole batch fits it and sends the wide column otherwise.
+   * Not accepted by bkid_push_batch_device (resident columns are used in place). */
+  const int16_t *isize16;           /* [n] replaces isize: every isize of a record passing the insert-statistics predicate
+                                       (src/BreakID.cc:1932, the only reader of isize) fits int16; other records: any value */
+  const uint16_t *span16;           /* [n] replaces endpos: endpos - pos */
+  int64_t n_tid_runs;               /* run-length form of tid (records are coordinate sorted: one run per target) */
+  const uint32_t *tid_run_start;    /* [n_tid_runs] ascending first record index of each run, [0] = 0 */
+  const int32_t *tid_run_tid;       /* [n_tid_runs] */
 } bkid_batch;
 
 /* A discordant pair (reference struct discordant_pair, src/BreakID.h:39-58) as kept on the device. */

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(api.LIB_CUDA)
     for s in declared:
         assert hasattr(lib, s), s
-    assert api.cuda_lib().bkid_abi_version() == 1
+    assert api.cuda_lib().bkid_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -37,7 +37,7 @@ def test_pod_layouts_match_header():
     from breakid_b200 import api
     assert api.PAIR_DTYPE.itemsize == 64 and api.CLUSTER_DTYPE.itemsize == 192
     import ctypes
-    assert ctypes.sizeof(api.Batch) == 20 * 8 and ctypes.sizeof(api.Params) == 32
+    assert ctypes.sizeof(api.Batch) == 25 * 8 and ctypes.sizeof(api.Params) == 32
 
 
 def test_host_bam_decoder_roundtrip(tmp_path):

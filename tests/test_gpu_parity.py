@@ -602,3 +602,36 @@ def test_driver_exclude_bed_matches_reference_on_prefiltered_bam(tmp_path):
     for suffix in ("_fusion.txt", "_fusion_all.txt"):
         assert open(str(tmp_path / "ref") + suffix).read() == open(str(tmp_path / "gpu") + suffix).read(), suffix
     assert len(open(str(tmp_path / "gpu") + "_fusion_all.txt").read().splitlines()) >= 4
+
+
+def test_narrow_column_encodings(small_data):
+    """isize16 / span16 / tid runs (include/breakid_b200.h) widen on the device to exactly the wide columns; a batch
+    that does not fit falls back to the wide column for that field only"""
+    from breakid_b200 import api
+    d, hb, nibs = small_data
+    assert set(hb.narrow()) == {"span16", "isize16", "tid_run_start", "tid_run_tid"}
+    cn = _ctx_for(hb)                     # narrow (default)
+    cw = api.Context(hb.target_len, hb.target_names, device=0)
+    cw.push(hb, narrow=False)
+    for k, dt in (("tid", np.int32), ("pos", np.int32), ("isize", np.int32), ("endpos", np.int32), ("flag", np.uint16), ("mapq", np.uint8)):
+        a, b = cn.fetch_column(k, dt), cw.fetch_column(k, dt)
+        if k == "isize":                  # only the values the path reads have to survive (they all do here)
+            assert np.array_equal(a, np.clip(b, -32768, 32767))
+        else:
+            assert np.array_equal(a, b), k
+    assert cn.run()[:3] == cw.run()[:3] and cn.fetch_clusters().tobytes() == cw.fetch_clusters().tobytes()
+    cn.close(); cw.close()
+    # a long-span record (RNA-style N skip) and a huge proper-pair insert: those two fields go wide, tid stays narrow
+    cols = {k: v.copy() for k, v in hb.cols.items()}
+    cols["endpos"][7] = cols["pos"][7] + 70000
+    proper = np.nonzero((cols["flag"] & 3) == 3)[0]
+    cols["isize"][proper[5]] = 40000
+    hb2 = api.HostBatch(cols, hb.name_hash, hb.side, hb.target_len, hb.target_names)
+    assert set(hb2.narrow()) == {"tid_run_start", "tid_run_tid"}
+    c2 = _ctx_for(hb2)
+    assert np.array_equal(c2.fetch_column("endpos", np.int32), cols["endpos"]) and np.array_equal(c2.fetch_column("isize", np.int32), cols["isize"])
+    assert np.array_equal(c2.fetch_column("tid", np.int32), cols["tid"])
+    import oracle_py as O
+    om, osd, od, exp = O.run(hb2, None, mode=0)
+    assert c2.run()[:3] == (om, osd, od) and c2.fetch_clusters().tobytes() == exp.tobytes()
+    c2.close()
