@@ -65,6 +65,28 @@ __global__ void __launch_bounds__(INF_WARPS * 32, 6) bgzf_inflate(const uint8_t 
   }
 }
 
+// gzip CRC32 of every inflated block against the value stored after its deflate payload (htslib bgzf.c:338,404-416):
+// one warp per block, 32 contiguous slices, partials advanced over the bytes that follow and XORed together
+__global__ void __launch_bounds__(256) bgzf_crc32(const uint8_t *__restrict__ comp, const Task *__restrict__ tasks, int ntask, const uint8_t *__restrict__ unc, int *__restrict__ err)
+{
+  __shared__ uint32_t tab[256];
+  tab[threadIdx.x] = bki::crc_table_entry(threadIdx.x);
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ntask; t += gridDim.x * 8) {
+    Task k = tasks[t];
+    uint32_t per = (k.ulen + 31u) / 32u;
+    uint32_t lo = min(lane * per, k.ulen), hi = min(lo + per, k.ulen);
+    uint32_t c = bki::crc_run(tab, lane == 0 ? 0xffffffffu : 0u, unc + k.dst + lo, hi - lo);
+    c = bki::crc_shift(c, k.ulen - hi);
+    for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+    c ^= 0xffffffffu;
+    const uint8_t *q = comp + k.src + k.clen;             // CRC32, ISIZE follow the payload
+    uint32_t want = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+    if (lane == 0 && c != want) atomicCAS(err, 0, t + 1);
+  }
+}
+
 __device__ __forceinline__ uint32_t ld32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 __device__ __forceinline__ uint32_t ld16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
@@ -291,6 +313,7 @@ struct bkid_decoder {                 // per-context streaming state, allocated 
   cudaStream_t st_copy = nullptr;
   cudaEvent_t ev_h2d[2], ev_free[2], ev_t[8];
   bool init = false;
+  bool skip_crc = false;                // BKID_BGZF_NO_CRC=1: timing experiments only
   bkid_decode_stats stats;
 };
 
@@ -336,6 +359,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   cudaStream_t st = c->st;
   invalidate(c);
   memset(&d->stats, 0, sizeof d->stats);
+  d->skip_crc = getenv("BKID_BGZF_NO_CRC") != nullptr;
   size_t COMP_CAP = (size_t)1536 << 20, UNC_CAP = (size_t)3072 << 20, CARRY_CAP = (size_t)64 << 20;   // unc offsets are 32-bit: UNC_CAP + CARRY_CAP < 4 GiB
   if (const char *e = getenv("BKID_BGZF_CHUNK_KB")) {          // tests: small chunks exercise the streaming / carry logic on small files
     long kb = atol(e);
@@ -390,7 +414,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     d->h_tasks_cap = 2 * max_tasks + 2;
   }
   TRY(c, d->tasks.ensure((2 * max_tasks + 2) * sizeof(Task), 0, st));
-  int *state = d->state.as<int>();           // [0] changed [1] corrupt [2] carry start [4] inflate err [5] walk err
+  int *state = d->state.as<int>();           // [0] changed [1] corrupt [2] carry start [4] inflate err [5] walk err [6] crc mismatch (block + 1)
   CU(c, cudaMemsetAsync(state, 0, 64, st));
   unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
   if (c->n_sa == 0) { TRY(c, reserve_impl(c, c->n, c->n_x, 1, 1, 1, 1)); CU(c, cudaMemsetAsync(c->cig_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->sa_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->oc_off.p, 0, 4, st)); }
@@ -438,6 +462,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     CU(c, cudaStreamWaitEvent(st, d->ev_h2d[slot], 0));
     cudaEventRecord(d->ev_t[1], st);
     if (nt) BK_LAUNCH(bgzf_inflate, std::min((nt + INF_WARPS * INF_NG - 1) / (INF_WARPS * INF_NG), 148 * 6), INF_WARPS * 32, 0, st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 4);
+    if (nt && !d->skip_crc) BK_LAUNCH(bgzf_crc32, std::min((nt + 7) / 8, 148 * 8), 256, 0, st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 6);
     CU(c, cudaEventRecord(d->ev_free[slot], st));
     cudaEventRecord(d->ev_t[2], st);
     d->stats.n_blocks += nt; d->stats.uncompressed_bytes += (int64_t)(total - carry);
@@ -471,6 +496,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
       CU(c, cudaMemcpyAsync(hstate, state, 32, cudaMemcpyDeviceToHost, st));
       TRY(c, sync_check(c));
       if (hstate[4]) return fail(c, BKID_ERR_IO, "inflate failed: BGZF block " + std::to_string((long long)b0 + (hstate[4] >> 4)) + " (deflate error " + std::to_string(hstate[4] & 15) + ")");
+      if (hstate[6]) return fail(c, BKID_ERR_IO, "CRC32 mismatch in BGZF block " + std::to_string((long long)b0 + hstate[6] - 1));
       if (hstate[1]) return fail(c, BKID_ERR_IO, "corrupt BAM record (block_size < 32)");
       if (!hstate[0]) break;
       d->stats.seed_repairs++;

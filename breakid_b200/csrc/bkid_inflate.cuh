@@ -329,4 +329,49 @@ BKI_FN int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
   return stream_finish(s);
 }
 
+// ---- CRC-32 (gzip / zlib polynomial, reflected) ------------------------------------------------------------------
+// htslib checks every BGZF block against the CRC32 stored after the deflate payload (bgzf.c:338,404-416).  One warp
+// checks one block: every lane runs the byte-table recurrence over its own contiguous slice, advances its partial
+// over the bytes that follow (multiplication by x^(8n) mod P, as zlib's crc32_combine does) and the warp XORs the
+// partials together -- the CRC state is linear in (state, data), so
+//   crc(S0 || S1 || ...) = final_xor ^ XOR_i shift(c_i, bytes after S_i),  c_0 started from ~0, c_i>0 from 0.
+constexpr uint32_t CRC_POLY = 0xedb88320u;
+
+BKI_FN uint32_t crc_table_entry(uint32_t i)
+{
+  uint32_t c = i;
+  for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ CRC_POLY : c >> 1;
+  return c;
+}
+// raw table recurrence over [p, p+n) from state `c` (no pre / post inversion)
+BKI_FN uint32_t crc_run(const uint32_t *tab, uint32_t c, const uint8_t *p, uint32_t n)
+{
+  for (uint32_t i = 0; i < n; ++i) c = tab[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+  return c;
+}
+// a(x) * b(x) mod P in the reflected representation (zlib crc32.c multmodp)
+BKI_FN uint32_t crc_mul(uint32_t a, uint32_t b)
+{
+  uint32_t m = 1u << 31, p = 0;
+  for (;;) {
+    if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+    m >>= 1;
+    b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+  }
+  return p;
+}
+// state after `nbytes` more zero bytes: c * x^(8 nbytes) mod P by square-and-multiply
+BKI_FN uint32_t crc_shift(uint32_t c, uint32_t nbytes)
+{
+  if (nbytes == 0 || c == 0) return c;
+  uint32_t sq = crc_mul(1u << 30, 1u << 30);          // x^2
+  sq = crc_mul(sq, sq); sq = crc_mul(sq, sq);          // x^8
+  uint32_t p = 1u << 31;                                // x^0
+  for (uint32_t n = nbytes; n; n >>= 1) {
+    if (n & 1u) p = crc_mul(sq, p);
+    sq = crc_mul(sq, sq);
+  }
+  return crc_mul(p, c);
+}
+
 }  // namespace bki

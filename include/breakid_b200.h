@@ -187,8 +187,9 @@ int bkid_push_batch_device(bkid_ctx *ctx, const bkid_batch *batch);
  * breakid_b200/host/bam_reader.h: bkid_host_bgzf_open), `first_record_uoffset` the offset of the first alignment
  * record in the uncompressed stream (= size of the BAM header).  Compressed bytes are streamed to the device in
  * chunks; inflate, record-boundary search and column extraction run there and append to the context exactly
- * what bkid_push_batch would have been given by a host decoder.  Deflate stream errors, a wrong ISIZE, corrupt
- * record sizes and a truncated last record return BKID_ERR_IO.  The gzip CRC32 is not verified. */
+ * what bkid_push_batch would have been given by a host decoder.  Deflate stream errors, a wrong ISIZE, a CRC32
+ * mismatch (checked per block like htslib bgzf.c:404-416), corrupt record sizes and a truncated last record
+ * return BKID_ERR_IO. */
 typedef struct {
   uint64_t payload_off;             /* file offset of the raw deflate payload (block start + 12 + XLEN) */
   uint32_t payload_len;             /* BSIZE + 1 - 12 - XLEN - 8 */

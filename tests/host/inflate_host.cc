@@ -20,3 +20,17 @@ extern "C" int bki_host_inflate_stepped(const uint8_t *in, uint32_t in_len, uint
   }
   return bki::stream_finish(s);
 }
+
+// CRC-32 the way the device computes it: `nslices` contiguous slices, partials advanced and XORed together
+extern "C" uint32_t bki_host_crc32_sliced(const uint8_t *p, uint32_t n, int nslices)
+{
+  uint32_t tab[256];
+  for (uint32_t i = 0; i < 256; ++i) tab[i] = bki::crc_table_entry(i);
+  uint32_t per = (n + nslices - 1) / nslices, acc = 0;
+  for (int l = 0; l < nslices; ++l) {
+    uint32_t lo = (uint32_t)l * per < n ? (uint32_t)l * per : n, hi = lo + per < n ? lo + per : n;
+    uint32_t c = bki::crc_run(tab, l == 0 ? 0xffffffffu : 0u, p + lo, hi - lo);
+    acc ^= bki::crc_shift(c, n - hi);
+  }
+  return acc ^ 0xffffffffu;
+}

@@ -172,6 +172,29 @@ def test_device_decode_rejects_corrupt_files(tmp_path):
     with pytest.raises(api.BkidError, match="inflate failed"):
         c.push_bgzf(f)
     f.close()
+    # a flipped bit in the stored CRC32, and a flipped literal that still inflates to the right size: both are CRC errors
+    bad = bytearray(raw)
+    bad[int(bt["payload_off"][5] + bt["payload_len"][5])] ^= 0x10
+    q = str(tmp_path / "bad_crc.bam")
+    open(q, "wb").write(bad)
+    f = api.BgzfFile(q)
+    with pytest.raises(api.BkidError, match="CRC32 mismatch in BGZF block 5"):
+        c.push_bgzf(f)
+    f.close()
+    hits = 0
+    for off in range(40, 400, 7):                      # somewhere in the payload of block 7: most flips change literals only
+        bad = bytearray(raw)
+        bad[int(bt["payload_off"][7]) + off] ^= 0x01
+        open(q, "wb").write(bad)
+        f = api.BgzfFile(q)
+        try:
+            c.reset()
+            c.push_bgzf(f)
+        except api.BkidError as e:
+            hits += 1
+            assert "BGZF block 7" in str(e), str(e)
+        f.close()
+    assert hits == len(range(40, 400, 7))               # no damaged block gets through
     # truncated last record: drop the tail of the uncompressed stream
     q = str(tmp_path / "trunc.bam")
     _bgzf_write(q, payload[:-10])

@@ -20,6 +20,8 @@ def lib(tmp_path_factory):
     L.bki_host_inflate.restype = C.c_int
     L.bki_host_inflate_stepped.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int]
     L.bki_host_inflate_stepped.restype = C.c_int
+    L.bki_host_crc32_sliced.argtypes = [C.c_char_p, C.c_uint32, C.c_int]
+    L.bki_host_crc32_sliced.restype = C.c_uint32
     return L
 
 
@@ -94,3 +96,12 @@ def test_rejects_corrupt_streams(lib):
             except zlib.error:
                 pass                                               # zlib is stricter (e.g. incomplete code sets)
     assert bad >= 1         # most flips only change a literal: catching those is the CRC's job, not the decoder's
+
+
+def test_sliced_crc32_matches_zlib(lib):
+    rng = np.random.RandomState(11)
+    for n in (0, 1, 2, 31, 32, 33, 1000, 65279, 65280, 65536):
+        data = rng.randint(0, 256, n, dtype=np.uint8).tobytes()
+        for k in (1, 2, 8, 32):
+            assert lib.bki_host_crc32_sliced(data, n, k) == (zlib.crc32(data) & 0xffffffff), (n, k)
+    assert lib.bki_host_crc32_sliced(b"\x00" * 5000, 5000, 32) == (zlib.crc32(b"\x00" * 5000) & 0xffffffff)
