@@ -347,6 +347,9 @@ def run_ours(args):
         "gen_seconds": gen_s,
     }
     if rank == 0 and shard_timing:
+        from breakid_b200 import dist as _d
+        for k, v in _d._A2A_T.items():
+            print("[a2a-timing] %-10s %8.3f ms total over all calls" % (k, v), file=sys.stderr)
         tot = sum(shard_timing.values())
         for k, v in shard_timing.items():
             print("[shard-timing] %-28s %8.3f ms/step" % (k, v / args.steps), file=sys.stderr)

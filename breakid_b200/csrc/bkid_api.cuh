@@ -83,6 +83,7 @@ struct bkid_ctx {
   cudaEvent_t ev[16];
   cudaEvent_t ev_run[2];
   cudaEvent_t ev_side[2];
+  bool sd_side_pending = false;           // sd_block_stats in flight on st2 (bkid_shard_sd_prepare)
   bool maxspan_cached = false, maxspan_pending = false;   // pending: max_span_kernel in flight on st3
   long long launches0 = 0;
 };
@@ -586,7 +587,7 @@ void bkid_destroy(bkid_ctx *c)
   delete c;
 }
 
-static void invalidate(bkid_ctx *c) { if (c->maxspan_pending) { cudaStreamSynchronize(c->st3); c->maxspan_pending = false; } c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; c->maxspan_cached = false; }
+static void invalidate(bkid_ctx *c) { if (c->sd_side_pending) { cudaStreamSynchronize(c->st2); c->sd_side_pending = false; } if (c->maxspan_pending) { cudaStreamSynchronize(c->st3); c->maxspan_pending = false; } c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; c->maxspan_cached = false; }
 
 static int reserve_impl(bkid_ctx *c, long long n, long long n_x, long long n_sa, long long n_cig, long long sa_b, long long oc_b)
 {
@@ -1389,8 +1390,12 @@ int bkid_shard_sd_prepare(bkid_ctx *c, double mean)
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device); c->err.clear();
   TRY(c, classify_impl(c));
-  TRY(c, sd_prepare_impl(c, mean));
-  return sync_check(c);
+  // asynchronous on the side stream: the streaming pass overlaps whatever the caller does next on the main stream
+  // (candidate extraction, the candidate all-to-all); bkid_shard_sd_partial joins it
+  TRY(c, sd_prepare_impl(c, mean, c->st2));
+  CU(c, cudaEventRecord(c->ev_side[1], c->st2));
+  c->sd_side_pending = true;
+  return 0;
 }
 
 int bkid_shard_sd_partial(bkid_ctx *c, double mean, int64_t t_in, int64_t *t_out)
@@ -1398,6 +1403,7 @@ int bkid_shard_sd_partial(bkid_ctx *c, double mean, int64_t t_in, int64_t *t_out
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device); c->err.clear();
   TRY(c, classify_impl(c));
+  if (c->sd_side_pending) { CU(c, cudaStreamWaitEvent(c->st, c->ev_side[1], 0)); c->sd_side_pending = false; }
   long long t = 0;
   TRY(c, sd_partial_impl(c, mean, (long long)t_in, &t));
   *t_out = t;

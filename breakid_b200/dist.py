@@ -184,26 +184,43 @@ def _all_gather_rows(t: torch.Tensor) -> torch.Tensor:
     return torch.cat([o[:c] for o, c in zip(out, cnts)], 0)
 
 
+_A2A_T = {}
+
+
 def _all_to_all_rows(t: torch.Tensor, owner: torch.Tensor) -> torch.Tensor:
     """route row i of t to rank owner[i]; rows arrive grouped by source rank (rank order) and keep their
     source order inside a group -- i.e. a stream that was globally ordered stays globally ordered"""
+    import os, time
     W = _world()
     if W == 1:
         return t
+    dbg = os.environ.get("BKID_DEBUG_TIMING") and t.is_cuda
+    t0 = [time.perf_counter()]
+
+    def lap(k):
+        if dbg:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            _A2A_T[k] = _A2A_T.get(k, 0.0) + (now - t0[0]) * 1e3
+            t0[0] = now
     order = torch.sort(owner.to(torch.uint8), stable=True).indices          # W <= 255: one 8-bit radix pass
+    lap("sort")
     if t.shape[1] % 8 == 0:          # move rows as 8-byte words, not bytes
-        send = t.view(torch.int64)[order].contiguous().view(torch.uint8)
+        send = torch.index_select(t.view(torch.int64), 0, order).view(torch.uint8)          # row gather (advanced indexing was 10x slower)
     else:
-        send = t[order].contiguous()
+        send = torch.index_select(t, 0, order)
+    lap("gather")
     scount = torch.bincount(owner.to(torch.int32), minlength=W).to(torch.int64)
     rcount = torch.empty_like(scount)
     dist.all_to_all_single(rcount, scount) if dist.get_backend() != "gloo" else _gloo_a2a_counts(rcount, scount)
     s_list, r_list = [int(x) for x in scount], [int(x) for x in rcount]
+    lap("counts")
     recv = torch.empty((sum(r_list), t.shape[1]), dtype=t.dtype, device=t.device)
     if dist.get_backend() == "gloo":
         _gloo_a2a_rows(recv, send, s_list, r_list)
     else:
         dist.all_to_all_single(recv, send, output_split_sizes=r_list, input_split_sizes=s_list)
+    lap("a2a")
     return recv
 
 
@@ -261,29 +278,31 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
     S, N = int(sn[0]), int(sn[1])
     mean = float(S) / float(N)
     if hasattr(engine, "sd_prepare"):
-        engine.sd_prepare(mean)          # the streaming pass (block tables) runs on all ranks at once; only the cheap resolve is chained
-    t = torch.zeros(1, dtype=torch.int64, device=dev)
-    for src in range(W):
-        if r == src:
-            t[0] = engine.sd_partial(mean, int(t[0]))
-        if W > 1:
-            dist.broadcast(t, src=src)
-    lap('insert stats + sd chain')
-    sd = math.sqrt(int(t[0]) / float(N))
-    d = times * math.sqrt(times) * (mean + sd_mult * sd)
-    engine.set_stats(mean, sd)
+        engine.sd_prepare(mean)          # the streaming pass (block tables) runs on all ranks at once, asynchronously: it overlaps the candidate extraction below
+    lap('insert sum/count')
     # global index of the first local record
     ns = torch.zeros(W, dtype=torch.int64, device=dev)
     ns[r] = n_local
     _reduce(ns, dist.ReduceOp.SUM)
     offset = int(ns[:r].sum())
-    # candidates meet their mates on the owner of their name hash
+    # candidates meet their mates on the owner of their name hash (independent of the distance: before the sd chain)
     cands = engine.candidates(offset)
     lo = cands.view(torch.int64)[:, 0] if cands.shape[0] else torch.zeros(0, dtype=torch.int64, device=dev)
     owner = ((lo >> 8) & 0x7fffffff) % W
     lap('candidates')
     cands = _all_to_all_rows(cands, owner)
     lap('a2a candidates')
+    # only the cheap exact resolve of the order-dependent sd accumulator is chained through the ranks
+    t = torch.zeros(1, dtype=torch.int64, device=dev)
+    for src in range(W):
+        if r == src:
+            t[0] = engine.sd_partial(mean, int(t[0]))
+        if W > 1:
+            dist.broadcast(t, src=src)
+    lap('sd chain')
+    sd = math.sqrt(int(t[0]) / float(N))
+    d = times * math.sqrt(times) * (mean + sd_mult * sd)
+    engine.set_stats(mean, sd)
     pairs = engine.join(cands, d)
     lap('join')
     # pairs go to the owner of their chr-pair bucket
@@ -302,7 +321,7 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
     if cl.shape[0]:
         v = cl.view(torch.int32)
         key = (v[:, 0].to(torch.int64) << 32) | v[:, 1].to(torch.int64)
-        cl = cl.view(torch.int64)[torch.sort(key, stable=True).indices].contiguous().view(torch.uint8)
+        cl = torch.index_select(cl.view(torch.int64), 0, torch.sort(key, stable=True).indices).view(torch.uint8)
     engine.set_clusters(cl)
     lap('gather clusters')
     rows = _all_gather_rows(engine.sa_rows())
@@ -310,7 +329,7 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
         # the table is searched by (tid, pos): restore coordinate order when the slices are not genomic bins
         v = rows.view(torch.int32)
         key = ((v[:, 18].to(torch.int64) & 0xffffffff) << 32) | (v[:, 19].to(torch.int64) & 0xffffffff)
-        rows = rows.view(torch.int64)[torch.sort(key, stable=True).indices].contiguous().view(torch.uint8)
+        rows = torch.index_select(rows.view(torch.int64), 0, torch.sort(key, stable=True).indices).view(torch.uint8)
     engine.set_sa_rows(rows)
     lap('gather sa rows')
     ms = _reduce(torch.tensor([engine.maxspan()], dtype=torch.int32, device=dev), dist.ReduceOp.MAX)
