@@ -263,7 +263,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
-           "bkid_push_bgzf", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude"]
+           "bkid_push_bgzf", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -289,6 +289,7 @@ def cuda_lib():
         L.bkid_push_batch.argtypes = [vp, C.POINTER(Batch)]
         L.bkid_push_batch_device.argtypes = [vp, C.POINTER(Batch)]
         L.bkid_set_exclude.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.bkid_device_gather_rows.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32]
         L.bkid_push_bgzf.argtypes = [vp, vp, vp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
         L.bkid_get_decode_stats.argtypes = [vp, C.POINTER(DecodeStats)]
         L.bkid_fetch_column.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)]

@@ -1552,6 +1552,24 @@ int bkid_device_copy(bkid_ctx *c, void *dst, const void *src, uint64_t bytes)
   return 0;
 }
 
+// row gather for the exchange routing: dst[i] = src[idx[i]], rows of row_bytes (multiple of 16), 16 bytes per thread
+__global__ void gather_rows16(const uint4 *__restrict__ src, const long long *__restrict__ idx, long long n, int chunks, uint4 *__restrict__ dst)
+{
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * chunks) return;
+  long long r = t / chunks; int k = (int)(t - r * chunks);
+  dst[t] = src[idx[r] * chunks + k];
+}
+int bkid_device_gather_rows(bkid_ctx *c, void *dst, const void *src, const int64_t *idx, int64_t n, int32_t row_bytes)
+{
+  if (!c || n < 0 || row_bytes <= 0 || (row_bytes & 15)) return c ? fail(c, BKID_ERR_ARG, "gather rows: row size must be a multiple of 16") : BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (n == 0) return 0;
+  int chunks = row_bytes / 16;
+  BK_LAUNCH(gather_rows16, GRID1(n * chunks, 256), 256, 0, c->st, (const uint4 *)src, (const long long *)idx, (long long)n, chunks, (uint4 *)dst);
+  return sync_check(c);
+}
+
 int bkid_fetch_bucket_ranks(bkid_ctx *c, int32_t *out, int64_t cap, int64_t *nb)
 {
   if (!c || !c->scanned) return c ? fail(c, BKID_ERR_ARG, "bkid_fetch_bucket_ranks before scan") : BKID_ERR_ARG;

@@ -150,6 +150,14 @@ class GpuEngine:
         self._chk(self.lib.bkid_shard_finish(self.ctx.ctx, C.byref(n)))
         return self.ctx.fetch_clusters()
 
+    def gather_rows(self, t, order):
+        """t[order] for [n, row] byte rows (row % 16 == 0) with the library's 16-bytes-per-thread gather"""
+        t = self._ready(t)
+        out = torch.empty((order.shape[0], t.shape[1]), dtype=torch.uint8, device=self.device)
+        order = self._ready(order.to(torch.int64))
+        self._chk(self.lib.bkid_device_gather_rows(self.ctx.ctx, out.data_ptr(), t.data_ptr(), order.data_ptr(), order.shape[0], t.shape[1]))
+        return out
+
     def bucket_ranks(self):
         nb = C.c_int64()
         self._chk(self.lib.bkid_fetch_bucket_ranks(self.ctx.ctx, None, 0, C.byref(nb)))
@@ -187,7 +195,7 @@ def _all_gather_rows(t: torch.Tensor) -> torch.Tensor:
 _A2A_T = {}
 
 
-def _all_to_all_rows(t: torch.Tensor, owner: torch.Tensor) -> torch.Tensor:
+def _all_to_all_rows(t: torch.Tensor, owner: torch.Tensor, engine=None) -> torch.Tensor:
     """route row i of t to rank owner[i]; rows arrive grouped by source rank (rank order) and keep their
     source order inside a group -- i.e. a stream that was globally ordered stays globally ordered"""
     import os, time
@@ -205,7 +213,9 @@ def _all_to_all_rows(t: torch.Tensor, owner: torch.Tensor) -> torch.Tensor:
             t0[0] = now
     order = torch.sort(owner.to(torch.uint8), stable=True).indices          # W <= 255: one 8-bit radix pass
     lap("sort")
-    if t.shape[1] % 8 == 0:          # move rows as 8-byte words, not bytes
+    if engine is not None and hasattr(engine, "gather_rows") and t.shape[1] % 16 == 0:
+        send = engine.gather_rows(t, order)
+    elif t.shape[1] % 8 == 0:          # move rows as 8-byte words, not bytes
         send = torch.index_select(t.view(torch.int64), 0, order).view(torch.uint8)          # row gather (advanced indexing was 10x slower)
     else:
         send = torch.index_select(t, 0, order)
@@ -290,7 +300,7 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
     lo = cands.view(torch.int64)[:, 0] if cands.shape[0] else torch.zeros(0, dtype=torch.int64, device=dev)
     owner = ((lo >> 8) & 0x7fffffff) % W
     lap('candidates')
-    cands = _all_to_all_rows(cands, owner)
+    cands = _all_to_all_rows(cands, owner, engine)
     lap('a2a candidates')
     # only the cheap exact resolve of the order-dependent sd accumulator is chained through the ranks
     t = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -307,7 +317,7 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
     lap('join')
     # pairs go to the owner of their chr-pair bucket
     bucket = pairs.view(torch.int32)[:, 12].to(torch.int64) if pairs.shape[0] else torch.zeros(0, dtype=torch.int64, device=dev)
-    pairs = _all_to_all_rows(pairs, bucket % W)
+    pairs = _all_to_all_rows(pairs, bucket % W, engine)
     lap('a2a pairs')
     engine.set_pairs(pairs)
     lap('set_pairs')

@@ -262,6 +262,8 @@ int bkid_shard_finish(bkid_ctx *ctx, int64_t *n_called);
 int bkid_fetch_bucket_ranks(bkid_ctx *ctx, int32_t *out, int64_t cap, int64_t *nb);
 /* plain device/host memcpy on the context's device (lets a caller move shard buffers into its own allocations) */
 int bkid_device_copy(bkid_ctx *ctx, void *dst, const void *src, uint64_t bytes);
+/* dst[i] = src[idx[i]] for rows of row_bytes (multiple of 16) on the context's device: the send-side permutation of the all-to-all routing */
+int bkid_device_gather_rows(bkid_ctx *ctx, void *dst, const void *src, const int64_t *idx, int64_t n, int32_t row_bytes);
 
 /* Stand-alone operator entry points (device work on caller host arrays) used by the parity tests:
  * util_cluster / std::sort replay / isolated-pair mask on one bucket. */
