@@ -83,6 +83,7 @@ struct bkid_ctx {
   cudaEvent_t ev[16];
   cudaEvent_t ev_run[2];
   cudaEvent_t ev_side[2];
+  bool k8_attr_set = false;
   bool sd_side_pending = false;           // sd_block_stats in flight on st2 (bkid_shard_sd_prepare)
   bool maxspan_cached = false, maxspan_pending = false;   // pending: max_span_kernel in flight on st3
   long long launches0 = 0;
@@ -1302,8 +1303,7 @@ static int refine_vote(bkid_ctx *c)
   if (nent > K8_SMALL) {                                                   // only then can a cluster be heavy
     TRY(c, c->tmpE.ensure((size_t)(nent + 1) * 8, 0, st));
     TRY(c, c->tmpF.ensure((size_t)(nent + 1) * 4, 0, st));
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k8_vote_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K8_BIG_SMEM_KEYS * 8)); attr_set = true; }
+    if (!c->k8_attr_set) { cudaFuncSetAttribute(k8_vote_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K8_BIG_SMEM_KEYS * 8)); c->k8_attr_set = true; }   // per device: kept per context
     BK_LAUNCH(k8_vote_big, ncl, K8_BIG_THREADS, K8_BIG_SMEM_KEYS * 8, st, c->clusters.as<bkid_cluster_rec>(), ncl, work, entoff, c->tmpD.as<int2>(), c->tmpE.as<uint64_t>(),
               c->tmpF.as<uint32_t>(), c->prm.bp_pos_error, c->valid.as<uint32_t>());
   }
