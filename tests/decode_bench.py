@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Decode-included throughput on a bounded sample: BAM file bytes (pinned host memory) -> bkid_push_bgzf (device
 inflate + record decode) -> bkid_run -> bkid_fetch_clusters, next to the host decoder and the two driver binaries.
-   python tools/decode_bench.py [--scale 0.00390625] [--reps 5] [--replicate 1]
+   python tests/decode_bench.py [--scale 0.00390625] [--reps 5] [--replicate 1]
 --replicate N repeats the record blocks N times inside one file (decode-throughput measurement at multi-GB scale;
 such a file is not coordinate sorted, so only the decode is timed on it)."""
 import argparse

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU parity check (run under torchrun on a multi-GPU box):
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
 Every rank takes a contiguous slice of one synthetic dataset; the sharded result must be byte-identical to the
 CPU oracle on the unsplit input (rank 0 checks and prints)."""
 import os
@@ -42,6 +42,23 @@ def main():
             print("mode %d world %d: %d calls, identical to oracle: %s" % (mode, world, len(out), same), flush=True)
             ok = ok and same and len(exp) >= 10
         ctx.close()
+    # exclude intervals on every rank's context (BASELINE.json configs[2] shape: exclude-BED + genomic-bin sharding)
+    from test_gpu_parity import _exclude_intervals, _prefilter
+    iv = _exclude_intervals(d, np.random.RandomState(8))
+    ctx = api.Context(hb.target_len, hb.target_names, device=local)
+    ctx.push(part)
+    ctx.set_exclude(iv[:, 0], iv[:, 1], iv[:, 2])
+    mean, sd, dd, out = run_sharded(GpuEngine(ctx, dev), part.n, mode=0)
+    if rank == 0:
+        tid, pos = hb.cols["tid"].astype(np.int64), hb.cols["pos"].astype(np.int64)
+        keep = np.ones(hb.n, bool)
+        for t, b, e in iv:
+            keep &= ~((tid == t) & (pos >= max(b, 0)) & (pos < e))
+        m, s, d0, exp = O.run(_prefilter(hb, keep), None, mode=0)
+        same = (mean, sd, dd) == (m, s, d0) and out.tobytes() == exp.tobytes()
+        print("exclude world %d: %d calls, identical to oracle on the pre-filtered input: %s" % (world, len(out), same), flush=True)
+        ok = ok and same
+    ctx.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
