@@ -1,5 +1,7 @@
 #include "annotate.h"
 
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <sstream>
@@ -58,23 +60,16 @@ bool load_refgene(const std::string &path, std::vector<Transcript> &out)
   return true;
 }
 
-SideAnnotation annotate_side(const std::vector<Transcript> &tx, const std::string &chrom, long pos)
+static SideAnnotation describe(const std::vector<Transcript> &tx, long which, long pos)
 {
   SideAnnotation a;
-  if (pos == -1) { a.gene = "."; a.exon_info = "."; a.strand = "."; return a; }
-  const Transcript *pick = nullptr;
-  bool any = false;
-  for (const Transcript &t : tx)
-    if (chrom == t.chrom && pos >= (long)t.tx_start && pos <= (long)t.tx_end) {
-      any = true;
-      if (t.cdna_len > 0) pick = &t;                 // every CDS-bearing hit overwrites: the last one wins
-    }
-  if (!any) { a.gene = "intergenic"; a.exon_info = "."; a.strand = "."; return a; }
-  if (!pick) {
+  if (which == -2) { a.gene = "intergenic"; a.exon_info = "."; a.strand = "."; return a; }
+  if (which == -1) {
     // the reference dereferences an empty transcript here (src/BreakID.cc:1757 underflow); out of its domain
     a.gene = ""; a.strand = ""; a.exon_info = ":0-0";
     return a;
   }
+  const Transcript *pick = &tx[(size_t)which];
   int e0 = 0, e1 = 0;
   const std::vector<uint32_t> &p = pick->coding_parts;
   for (size_t i = 0; i + 1 < p.size(); ++i)
@@ -92,4 +87,72 @@ SideAnnotation annotate_side(const std::vector<Transcript> &tx, const std::strin
   a.gene = pick->gene; a.strand = pick->strand;
   a.exon_info = pick->id + ":" + std::to_string(e0) + "-" + std::to_string(e1);
   return a;
+}
+
+SideAnnotation annotate_side(const std::vector<Transcript> &tx, const std::string &chrom, long pos)
+{
+  if (pos == -1) { SideAnnotation a; a.gene = "."; a.exon_info = "."; a.strand = "."; return a; }
+  long pick = -2;
+  for (size_t i = 0; i < tx.size(); ++i) {
+    const Transcript &t = tx[i];
+    if (chrom == t.chrom && pos >= (long)t.tx_start && pos <= (long)t.tx_end) {
+      if (pick == -2) pick = -1;
+      if (t.cdna_len > 0) pick = (long)i;            // every CDS-bearing hit overwrites: the last one wins
+    }
+  }
+  return describe(tx, pick, pos);
+}
+
+void RefGeneIndex::build(const std::vector<Transcript> &tx)
+{
+  chroms.clear(); per_chrom.clear();
+  for (size_t i = 0; i < tx.size(); ++i) {
+    size_t c = 0;
+    while (c < chroms.size() && chroms[c] != tx[i].chrom) ++c;
+    if (c == chroms.size()) { chroms.push_back(tx[i].chrom); per_chrom.emplace_back(); }
+    per_chrom[c].push_back(Entry{tx[i].tx_start, tx[i].tx_end, 0u, (uint32_t)i});
+  }
+  for (auto &v : per_chrom) {
+    std::stable_sort(v.begin(), v.end(), [](const Entry &a, const Entry &b) { return a.start < b.start; });
+    uint32_t m = 0;
+    for (auto &e : v) { m = std::max(m, e.end); e.max_end_so_far = m; }
+  }
+}
+
+long RefGeneIndex::lookup(const std::vector<Transcript> &tx, const std::string &chrom, long pos) const
+{
+  size_t c = 0;
+  while (c < chroms.size() && chroms[c] != chrom) ++c;
+  if (c == chroms.size() || pos < 0) return -2;
+  const std::vector<Entry> &v = per_chrom[c];
+  // entries with start <= pos form a prefix; walk it backwards while anything there can still reach pos
+  size_t hi = (size_t)(std::upper_bound(v.begin(), v.end(), pos, [](long p, const Entry &e) { return p < (long)e.start; }) - v.begin());
+  long pick = -2;
+  for (size_t k = hi; k-- > 0;) {
+    if ((long)v[k].max_end_so_far < pos) break;
+    if ((long)v[k].end >= pos) {
+      if (pick == -2) pick = -1;
+      if (tx[v[k].order].cdna_len > 0 && (long)v[k].order > pick) pick = (long)v[k].order;      // last in file order wins
+    }
+  }
+  return pick;
+}
+
+SideAnnotation annotate_side(const std::vector<Transcript> &tx, const RefGeneIndex &ix, const std::string &chrom, long pos)
+{
+  if (pos == -1) { SideAnnotation a; a.gene = "."; a.exon_info = "."; a.strand = "."; return a; }
+  return describe(tx, ix.lookup(tx, chrom, pos), pos);
+}
+
+// test hook (libbreakid_host.so): both lookups on one query, "gene\tstrand\texon_info" each
+extern "C" int bkid_host_annotate_both(const char *refgene, const char *chrom, long pos, char *linear, char *indexed, int cap)
+{
+  static std::string loaded;
+  static std::vector<Transcript> tx;
+  static RefGeneIndex ix;
+  if (loaded != refgene) { if (!load_refgene(refgene, tx)) return -1; ix.build(tx); loaded = refgene; }
+  SideAnnotation a = annotate_side(tx, chrom, pos), b = annotate_side(tx, ix, chrom, pos);
+  snprintf(linear, cap, "%s\t%s\t%s", a.gene.c_str(), a.strand.c_str(), a.exon_info.c_str());
+  snprintf(indexed, cap, "%s\t%s\t%s", b.gene.c_str(), b.strand.c_str(), b.exon_info.c_str());
+  return 0;
 }

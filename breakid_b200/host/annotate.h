@@ -22,6 +22,20 @@ struct SideAnnotation {
   std::string gene, exon_info, strand;   // "intergenic"/"."/"." when nothing overlaps
 };
 
+// Interval index over the transcripts ("indexed host version"): per chromosome the transcripts sorted
+// by tx_start with a running maximum of tx_end, so a lookup is one binary search plus a walk over the few candidates
+// that can still reach `pos` instead of a scan of the whole file.  File order is kept to reproduce "the last
+// overlapping transcript with a CDS wins".
+struct RefGeneIndex {
+  struct Entry { uint32_t start, end, max_end_so_far; uint32_t order; };      // order = position in the file
+  std::vector<std::string> chroms;
+  std::vector<std::vector<Entry>> per_chrom;
+  void build(const std::vector<Transcript> &tx);
+  // index of the winning transcript, -1 = hits but none with a CDS, -2 = intergenic
+  long lookup(const std::vector<Transcript> &tx, const std::string &chrom, long pos) const;
+};
+
 // returns false when the file cannot be opened
 bool load_refgene(const std::string &path, std::vector<Transcript> &out);
-SideAnnotation annotate_side(const std::vector<Transcript> &tx, const std::string &chrom, long pos);
+SideAnnotation annotate_side(const std::vector<Transcript> &tx, const std::string &chrom, long pos);                              // linear scan (reference order of evaluation)
+SideAnnotation annotate_side(const std::vector<Transcript> &tx, const RefGeneIndex &ix, const std::string &chrom, long pos);     // same result through the index

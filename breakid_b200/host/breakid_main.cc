@@ -198,6 +198,7 @@ int main(int argc, char *argv[])
   bkid_timings tm;
   bkid_get_timings(ctx, &tm);
   std::vector<Transcript> tx;
+  RefGeneIndex tx_index;
   std::vector<CallRow> rows;
   double t_bp = 0;
   if (tm.n_clustered > 0) {
@@ -207,6 +208,7 @@ int main(int argc, char *argv[])
       exit(1);
     }
     if (!load_refgene(refgene, tx)) { std::cerr << "Error: cannot open \t" << refgene << std::endl; exit(1); }   // src/RefSeqTranscript.cc:205-209
+    tx_index.build(tx);
     for (int t = 0; t < hdr->n_targets; ++t) {
       nib nb;
       if (nb.open(nib_dir + "/hg19_" + names[t] + ".nib") == 0)                                     // src/util_bam.cc:83-86
@@ -225,8 +227,8 @@ int main(int argc, char *argv[])
       long p1 = (r.c.p1_exact_pos == (uint32_t)-1) ? (long)r.c.p1_mean_pos : (long)r.c.p1_exact_pos;   // src/BreakID.cc:518-534
       long p2 = (r.c.p2_exact_pos == -1) ? (long)r.c.p2_mean_pos : (long)r.c.p2_exact_pos;
       auto nm = [&](int t) { return t >= 0 && t < (int)names.size() ? names[t] : std::string("*"); };
-      r.a1 = annotate_side(tx, nm(r.c.p1_tid), p1);
-      r.a2 = annotate_side(tx, nm(r.c.p2_tid), p2);
+      r.a1 = annotate_side(tx, tx_index, nm(r.c.p1_tid), p1);
+      r.a2 = annotate_side(tx, tx_index, nm(r.c.p2_tid), p2);
       rows.push_back(r);
     }
   }

@@ -85,3 +85,36 @@ def test_driver_argument_errors():
     assert r.returncode == 1 and "Usage" in r.stderr
     r = subprocess.run([drv, "-bogus"], capture_output=True, text=True)       # the reference segfaults here
     assert r.returncode == 1
+
+
+def test_indexed_refgene_lookup_equals_linear_scan(tmp_path):
+    """the interval index over refGene gives exactly what the reference-order linear scan gives
+    (last overlapping transcript with a CDS wins, NR_ rows skipped, exon numbering), on nested / overlapping genes"""
+    import ctypes as C
+    import numpy as np
+    from breakid_b200 import api, synth
+    p = str(tmp_path / "refGene.txt")
+    synth.write_refgene(p, [400000, 300000, 200000], genes_per_mb=120.0, seed=3)     # dense: many overlapping transcripts
+    rows = open(p).read().splitlines()
+    # add nested transcripts, a CDS-less one covering others, duplicates of a locus in different file positions
+    extra = []
+    for i, r in enumerate(rows[:40]):
+        f = r.split("\t")
+        f[1] = "NM_9%05d" % i; f[12] = "NEST%d" % i
+        extra.append("\t".join(f))
+        g = list(f); g[1] = "NM_8%05d" % i; g[6] = g[7] = g[4]; g[12] = "NOCDS%d" % i       # cdsStart == cdsEnd: no CDS
+        extra.append("\t".join(g))
+    open(p, "w").write("\n".join(rows[:60] + extra + rows[60:]) + "\n")
+    L = api.host_lib()
+    L.bkid_host_annotate_both.argtypes = [C.c_char_p, C.c_char_p, C.c_long, C.c_char_p, C.c_char_p, C.c_int]
+    a, b = C.create_string_buffer(512), C.create_string_buffer(512)
+    rng = np.random.RandomState(5)
+    kinds = set()
+    starts = [int(r.split("\t")[4]) for r in rows] + [int(r.split("\t")[5]) for r in rows]
+    for q in range(6000):
+        chrom = ["chr1", "chr2", "chr3", "chr9"][int(rng.randint(0, 4))]
+        pos = int(rng.choice(starts)) + int(rng.randint(-2, 3)) if q % 3 == 0 else int(rng.randint(0, 420000))
+        assert L.bkid_host_annotate_both(p.encode(), chrom.encode(), pos, a, b, 512) == 0
+        assert a.value == b.value, (chrom, pos, a.value, b.value)
+        kinds.add(a.value.split(b"\t")[0][:4])
+    assert b"inte" in kinds and b"GENE" in kinds and b"NEST" in kinds
