@@ -263,7 +263,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
-           "bkid_push_bgzf", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows"]
+           "bkid_push_bgzf", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -289,6 +289,7 @@ def cuda_lib():
         L.bkid_push_batch.argtypes = [vp, C.POINTER(Batch)]
         L.bkid_push_batch_device.argtypes = [vp, C.POINTER(Batch)]
         L.bkid_set_exclude.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.bkid_op_banded_align.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int32, vp]
         L.bkid_device_gather_rows.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32]
         L.bkid_push_bgzf.argtypes = [vp, vp, vp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
         L.bkid_get_decode_stats.argtypes = [vp, C.POINTER(DecodeStats)]
@@ -419,6 +420,18 @@ class Context:
     def push(self, hb: HostBatch, narrow: bool = True):
         b = hb.struct(narrow)
         self._chk(self.lib.bkid_push_batch(self.ctx, C.byref(b)))
+
+    def op_banded_align(self, queries: Sequence[bytes], refs: Sequence[bytes], w: int) -> np.ndarray:
+        """banded edit distance of queries[i] against refs[i] (extension, bkid_op_banded_align)"""
+        n = len(queries)
+        q = np.frombuffer(b"".join(queries) + b"\0", np.uint8).copy()
+        r = np.frombuffer(b"".join(refs) + b"\0", np.uint8).copy()
+        qo = np.concatenate([[0], np.cumsum([len(x) for x in queries])]).astype(np.uint32)
+        ro = np.concatenate([[0], np.cumsum([len(x) for x in refs])]).astype(np.uint32)
+        out = np.zeros(max(n, 1), np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._chk(self.lib.bkid_op_banded_align(self.ctx, n, p(q), p(qo), p(r), p(ro), int(w), p(out)))
+        return out[:n]
 
     def push_bgzf(self, f: "BgzfFile", data_ptr=None, blocks=None, n_blocks=None, first_record=None) -> int:
         """device BGZF inflate + BAM decode of a whole file (``bkid_push_bgzf``); returns the record count.

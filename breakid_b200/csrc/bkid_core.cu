@@ -1013,3 +1013,5 @@ __global__ void pair_xy(const bkid_pair *__restrict__ pairs, long long np, uint3
 #include "bkid_refine.cuh"
 #include "bkid_api.cuh"
 #include "bkid_bamdec.cuh"
+#include "bkid_align.cuh"
+#include "bkid_align_api.cuh"

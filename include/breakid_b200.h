@@ -273,6 +273,15 @@ int bkid_op_remove_isolated(bkid_ctx *ctx, int64_t n, const uint32_t *p1, const 
 int bkid_op_cluster(bkid_ctx *ctx, int mode, int64_t n, const uint32_t *p1, const uint32_t *p2, double thr,
                     uint32_t *out_idx, int32_t *out_cluster, int64_t *n_out, int32_t *n_roots);
 
+/* Extension (BASELINE.json north_star kernel 4; the reference has no sequence alignment): banded
+ * unit-cost edit distance of n query strings (e.g. the soft-clipped part of a split read) against their own reference
+ * windows, ASCII bases, 'N' never matches.  q / r are the concatenated strings, q_off / r_off their [n+1] offsets,
+ * w (<= 15) the band half-width |j - i| <= w.  out[i] = distance, -1 when the length difference exceeds w, -2 when a
+ * string is longer than 512.  One warp per pair, anti-diagonal wavefront with warp shuffles.  Wiring it into
+ * bkid_refine as a default-off evidence validator needs the read bases in the batch (not part of this ABI yet). */
+int bkid_op_banded_align(bkid_ctx *ctx, int64_t n, const uint8_t *q, const uint32_t *q_off, const uint8_t *r, const uint32_t *r_off,
+                         int32_t w, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

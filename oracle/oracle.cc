@@ -1416,3 +1416,26 @@ long orc_shard_finish(long ncl, orc_cluster *cl, const uint32_t *valid, const ui
 }
 
 }  /* extern "C" */
+
+// ---- extension: banded edit distance (checker of bkid_op_banded_align) ------------------------------------------
+extern "C" int orc_banded_edit(const unsigned char *q, int nq, const unsigned char *r, int nr, int w)
+{
+  if (nr - nq > w || nq - nr > w) return -1;
+  const int INF = 1 << 20;
+  std::vector<int> prev((size_t)nr + 1, INF), cur((size_t)nr + 1, INF);
+  for (int j = 0; j <= nr && j <= w; ++j) prev[j] = j;
+  for (int i = 1; i <= nq; ++i) {
+    std::fill(cur.begin(), cur.end(), INF);
+    int lo = i - w < 0 ? 0 : i - w, hi = i + w > nr ? nr : i + w;
+    for (int j = lo; j <= hi; ++j) {
+      if (j == 0) { cur[j] = i; continue; }
+      int sub = (q[i - 1] == r[j - 1] && q[i - 1] != 'N') ? 0 : 1;
+      int best = prev[j - 1] + sub;                          // (i-1, j-1) is always inside the band
+      if (j - (i - 1) <= w && prev[j] + 1 < best) best = prev[j] + 1;          // (i-1, j) inside the band?
+      if (j - 1 >= lo && cur[j - 1] + 1 < best) best = cur[j - 1] + 1;         // (i, j-1) inside the band?
+      cur[j] = best > INF ? INF : best;
+    }
+    prev.swap(cur);
+  }
+  return prev[nr];
+}

@@ -86,6 +86,10 @@ static inline uint64_t orc_str_hash(const char *s)
   return a;
 }
 
+/* banded unit-cost edit distance (checker of bkid_op_banded_align; an extension, nothing in the reference to follow):
+ * plain row-by-row DP over the band |j - i| <= w; -1 when |nr - nq| > w */
+int orc_banded_edit(const unsigned char *q, int nq, const unsigned char *r, int nr, int w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,6 +185,13 @@ def cluster(mode, p1, p2, thr, model=False):
     return oi[:n], oc[:n], r.value
 
 
+def banded_edit(q: bytes, r: bytes, w: int) -> int:
+    L = olib()
+    L.orc_banded_edit.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int]
+    L.orc_banded_edit.restype = C.c_int
+    return int(L.orc_banded_edit(q, len(q), r, len(r), w))
+
+
 def sort_perm(key, model=False):
     key = np.ascontiguousarray(key, np.uint32)
     perm = np.zeros(key.shape[0], np.uint32)
