@@ -23,7 +23,7 @@ class Header(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("qual", "times", "fast", "min_reads", "bp_pos_error",
-                                         "mismatch_num", "sd_mult", "reserved")]
+                                         "mismatch_num", "sd_mult", "validate_align")]
 
 
 class Batch(C.Structure):
@@ -32,7 +32,8 @@ class Batch(C.Structure):
                 ("n_x", C.c_int64), ("x_rec", C.c_void_p), ("x_mtid", C.c_void_p), ("x_mpos", C.c_void_p), ("x_name_hash", C.c_void_p),
                 ("n_sa", C.c_int64), ("sa_rec", C.c_void_p), ("cig_off", C.c_void_p), ("cig_ops", C.c_void_p),
                 ("sa_off", C.c_void_p), ("sa_txt", C.c_void_p), ("oc_off", C.c_void_p), ("oc_txt", C.c_void_p),
-                ("isize16", C.c_void_p), ("span16", C.c_void_p), ("n_tid_runs", C.c_int64), ("tid_run_start", C.c_void_p), ("tid_run_tid", C.c_void_p)]
+                ("isize16", C.c_void_p), ("span16", C.c_void_p), ("n_tid_runs", C.c_int64), ("tid_run_start", C.c_void_p), ("tid_run_tid", C.c_void_p),
+                ("seq_off", C.c_void_p), ("seq4", C.c_void_p), ("seq_len", C.c_void_p)]
 
 
 PAIR_DTYPE = np.dtype([
@@ -77,6 +78,7 @@ _COLS = (("flag", np.uint16), ("mapq", np.uint8), ("tid", np.int32), ("pos", np.
 _XCOLS = (("x_rec", np.uint32), ("x_mtid", np.int32), ("x_mpos", np.int32), ("x_name_hash", np.uint64))
 _SIDE = (("sa_rec", np.uint32), ("cig_off", np.uint32), ("cig_ops", np.uint32), ("sa_off", np.uint32),
          ("sa_txt", np.uint8), ("oc_off", np.uint32), ("oc_txt", np.uint8))
+_SEQ = (("seq_off", np.uint32), ("seq4", np.uint8), ("seq_len", np.int32))        # optional read bases of the SA records
 
 
 class HostBatch:
@@ -114,9 +116,14 @@ class HostBatch:
             side["oc_off"] = np.zeros(n_sa + 1, np.uint32)
             side["oc_txt"] = np.zeros(0, np.uint8)
         self.side = {k: np.ascontiguousarray(side[k], dtype=dt) for k, dt in _SIDE}
+        self.seq = {k: np.ascontiguousarray(side[k], dtype=dt) for k, dt in _SEQ} if all(k in side for k, _ in _SEQ) else None
         self.n_sa = n_sa
         self.target_len = np.ascontiguousarray(target_len, dtype=np.uint32)
         self.target_names = [str(x) for x in target_names]
+
+    def set_seq(self, seq: Optional[Dict[str, np.ndarray]]):
+        """attach / remove the optional read bases of the SA records (seq_off, seq4, seq_len)"""
+        self.seq = None if seq is None else {k: np.ascontiguousarray(seq[k], dtype=dt) for k, dt in _SEQ}
 
     # -- views -----------------------------------------------------------------------------
     def narrow(self) -> Dict[str, np.ndarray]:
@@ -159,6 +166,9 @@ class HostBatch:
         b.n_sa = self.n_sa
         for k, _ in _SIDE:
             setattr(b, k, self.side[k].ctypes.data)
+        if self.seq is not None:
+            for k, _ in _SEQ:
+                setattr(b, k, self.seq[k].ctypes.data)
         return b
 
     def header(self) -> Header:
@@ -218,6 +228,9 @@ class HostBatch:
                     "cig_ops": arr(b.cig_ops, int(cig_off[-1]), np.uint32), "sa_off": sa_off,
                     "sa_txt": arr(b.sa_txt, int(sa_off[-1]), np.uint8), "oc_off": oc_off,
                     "oc_txt": arr(b.oc_txt, int(oc_off[-1]), np.uint8)}
+            if b.seq_off:
+                seq_off = arr(b.seq_off, n_sa + 1, np.uint32)
+                side.update({"seq_off": seq_off, "seq4": arr(b.seq4, int(seq_off[-1]), np.uint8), "seq_len": arr(b.seq_len, n_sa, np.int32)})
             tl = [int(hd.target_len[i]) for i in range(hd.n_targets)]
             names = [hd.target_name[i].decode() for i in range(hd.n_targets)]
         finally:

@@ -39,7 +39,9 @@ def reg2bin(beg: np.ndarray, end: np.ndarray) -> np.ndarray:
 
 
 def write_bam(path: str, d: synth.SynthData, random_qual: bool = True, level: int = 1,
-              chunk: int = 200_000) -> None:
+              chunk: int = 200_000, sa_seq=None) -> None:
+    """``sa_seq`` = optional seq table (seq_off / seq4 / seq_len, see synth.split_read_sequences): real read bases for
+    the SA-tagged records (all other records carry a constant sequence)."""
     cfg = d.cfg
     L = cfg.read_len
     c = {k: v.cpu().numpy() for k, v in d.cols.items()}
@@ -137,7 +139,9 @@ def write_bam(path: str, d: synth.SynthData, random_qual: bool = True, level: in
         for j in idx_sa:
             k = sa_slot[s + j]
             ops = cig_ops[cig_off[k]:cig_off[k + 1]]
-            blob = ops.astype("<u4").tobytes() + b"\x11" * seq_b + (b"\x1e" * L) \
+            sq = b"\x11" * seq_b if sa_seq is None else bytes(sa_seq["seq4"][int(sa_seq["seq_off"][k]):int(sa_seq["seq_off"][k + 1])])
+            assert len(sq) == seq_b
+            blob = ops.astype("<u4").tobytes() + sq + (b"\x1e" * L) \
                 + b"SAZ" + sa_txt[sa_off[k]:sa_off[k + 1]].tobytes() + b"\x00"
             o = int(off[j]) + hw
             buf[o:o + len(blob)] = np.frombuffer(blob, dtype=np.uint8)

@@ -49,6 +49,8 @@ struct bkid_ctx {
   // SA side table
   long long n_sa = 0, n_cig = 0, sa_bytes = 0, oc_bytes = 0;
   DBuf sa_rec, cig_off, cig_ops, sa_off, sa_txt, oc_off, oc_txt;
+  DBuf seq_off, seq4, seq_len; long long seq_bytes = 0; bool have_seq = false;      // optional read bases of the SA records
+  const uint32_t *p_seq_off = nullptr; const uint8_t *p_seq4 = nullptr; const int32_t *p_seq_len = nullptr;
   const uint32_t *p_sa_rec = nullptr, *p_cig_off = nullptr, *p_cig_ops = nullptr, *p_sa_off = nullptr, *p_oc_off = nullptr;
   const uint8_t *p_sa_txt = nullptr, *p_oc_txt = nullptr;
   // nib
@@ -514,7 +516,7 @@ const char *bkid_last_error(const bkid_ctx *ctx) { return ctx ? ctx->err.c_str()
 
 void bkid_default_params(bkid_params *p)
 {
-  p->qual = 20; p->times = 2; p->fast = 0; p->min_reads = 2; p->bp_pos_error = 2; p->mismatch_num = 10; p->sd_mult = 3; p->reserved = 0;
+  p->qual = 20; p->times = 2; p->fast = 0; p->min_reads = 2; p->bp_pos_error = 2; p->mismatch_num = 10; p->sd_mult = 3; p->validate_align = 0;
 }
 
 bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *params)
@@ -573,7 +575,7 @@ void bkid_destroy(bkid_ctx *c)
   cudaStreamSynchronize(c->st);
   decoder_free(c);
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
-                  &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
+                  &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->seq_off, &c->seq4, &c->seq_len, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
                   &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
     b->release();
@@ -652,6 +654,7 @@ static void set_ptrs(bkid_ctx *c)
   c->p_isize = c->isize.as<int32_t>(); c->p_endpos = c->endpos.as<int32_t>();
   c->p_x_rec = c->x_rec.as<uint32_t>(); c->p_x_mtid = c->x_mtid.as<int32_t>(); c->p_x_mpos = c->x_mpos.as<int32_t>(); c->p_x_nh = c->x_nh.as<uint64_t>();
   c->p_sa_rec = c->sa_rec.as<uint32_t>(); c->p_cig_off = c->cig_off.as<uint32_t>(); c->p_cig_ops = c->cig_ops.as<uint32_t>();
+  c->p_seq_off = c->seq_off.as<uint32_t>(); c->p_seq4 = c->seq4.as<uint8_t>(); c->p_seq_len = c->seq_len.as<int32_t>();
   c->p_sa_off = c->sa_off.as<uint32_t>(); c->p_sa_txt = c->sa_txt.as<uint8_t>(); c->p_oc_off = c->oc_off.as<uint32_t>(); c->p_oc_txt = c->oc_txt.as<uint8_t>();
 }
 
@@ -731,6 +734,21 @@ static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
   } else if (s0 == 0) {
     CU(c, cudaMemsetAsync(c->cig_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->sa_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->oc_off.p, 0, 4, st));
   }
+  if (ns) {                                             // optional read bases of the SA records
+    if (b->seq_off && b->seq4 && b->seq_len && (s0 == 0 || c->have_seq)) {
+      uint32_t nseq_b = 0;
+      if (kind == cudaMemcpyHostToDevice) nseq_b = b->seq_off[ns];
+      else CU(c, cudaMemcpy(&nseq_b, b->seq_off + ns, 4, cudaMemcpyDeviceToHost));
+      TRY(c, c->seq_off.ensure((size_t)(s0 + ns + 1) * 4 + 64, (size_t)(s0 + 1) * 4, st));
+      TRY(c, c->seq_len.ensure((size_t)(s0 + ns) * 4 + 64, (size_t)s0 * 4, st));
+      TRY(c, c->seq4.ensure((size_t)c->seq_bytes + nseq_b + 64, (size_t)c->seq_bytes, st));
+      CU(c, cudaMemcpyAsync(c->seq_off.as<uint32_t>() + s0, b->seq_off, (ns + 1) * 4, kind, st));
+      CU(c, cudaMemcpyAsync(c->seq_len.as<int32_t>() + s0, b->seq_len, ns * 4, kind, st));
+      if (nseq_b) CU(c, cudaMemcpyAsync(c->seq4.as<uint8_t>() + c->seq_bytes, b->seq4, nseq_b, kind, st));
+      if (c->seq_bytes) BK_LAUNCH(add_offset_u32, GRID1(ns + 1, 256), 256, 0, st, c->seq_off.as<uint32_t>() + s0, (long long)ns + 1, (uint32_t)c->seq_bytes);
+      c->seq_bytes += nseq_b; c->have_seq = true;
+    } else c->have_seq = false;
+  }
   c->n += b->n; c->n_x += b->n_x; c->n_sa += b->n_sa; c->n_cig += ncig; c->sa_bytes += nsa_b; c->oc_bytes += noc_b;
   set_ptrs(c);
   cudaEventRecord(c->ev[1], st);
@@ -758,6 +776,7 @@ int bkid_push_batch_device(bkid_ctx *c, const bkid_batch *b)
     c->p_x_rec = b->x_rec; c->p_x_mtid = b->x_mtid; c->p_x_mpos = b->x_mpos; c->p_x_nh = b->x_name_hash;
     c->p_sa_rec = b->sa_rec; c->p_cig_off = b->cig_off; c->p_cig_ops = b->cig_ops; c->p_sa_off = b->sa_off; c->p_sa_txt = b->sa_txt;
     c->p_oc_off = b->oc_off; c->p_oc_txt = b->oc_txt;
+    c->p_seq_off = b->seq_off; c->p_seq4 = b->seq4; c->p_seq_len = b->seq_len; c->have_seq = b->seq_off && b->seq4 && b->seq_len;
     return 0;
   }
   return push_impl(c, b, cudaMemcpyDeviceToDevice);
@@ -769,6 +788,7 @@ int bkid_reset(bkid_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
   c->n = c->n_x = c->n_sa = c->n_cig = c->sa_bytes = c->oc_bytes = 0;
+  c->seq_bytes = 0; c->have_seq = false;
   c->borrowed = false;
   set_ptrs(c);
   invalidate(c);
@@ -1208,6 +1228,12 @@ static int refine_build_rows(bkid_ctx *c)
       CU(c, cudaMemcpyAsync(&hm, miss, 4, cudaMemcpyDeviceToHost, st));
       TRY(c, sync_check(c));
       if (hm) return fail(c, BKID_ERR_ARG, "an SA-tagged record is missing from the sparse mate/name table");
+      if (c->prm.validate_align) {
+        if (!c->have_seq) return fail(c, BKID_ERR_ARG, "validate_align needs the read bases of the SA records (bkid_batch seq_off / seq4 / seq_len)");
+        BK_LAUNCH(k7_validate_rows, GRID1(c->n_sa, AL_WARPS), AL_WARPS * 32, 0, st, c->p_sa_rec, c->n_sa, c->p_flag, c->p_cig_off, c->p_cig_ops, c->p_sa_off, c->p_sa_txt,
+                  c->p_oc_off, c->p_seq_off, c->p_seq4, c->p_seq_len, c->d_canon.as<uint64_t>(), c->nt, (const uint8_t *const *)c->d_nib_ptr.p, c->d_nib_len.as<uint64_t>(),
+                  c->sarows.as<EvRow>());
+      }
     }
   }
   c->rows_ptr = c->sarows.as<EvRow>(); c->n_rows = c->n_sa;

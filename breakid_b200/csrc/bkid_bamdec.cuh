@@ -221,7 +221,7 @@ __device__ void find_sa_oc(const uint8_t *__restrict__ r, uint32_t a, uint32_t e
 
 __global__ void bam_extract_cols(const uint8_t *__restrict__ u, const uint32_t *__restrict__ rec_off, uint32_t nrec, long long n0, Cols C,
                                  uint32_t *__restrict__ xf, uint32_t *__restrict__ sf, uint32_t *__restrict__ ncig, uint32_t *__restrict__ salen, uint32_t *__restrict__ oclen,
-                                 uint32_t *__restrict__ sa_ptr, uint32_t *__restrict__ oc_ptr)
+                                 uint32_t *__restrict__ sa_ptr, uint32_t *__restrict__ oc_ptr, uint32_t *__restrict__ seqb)
 {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrec) return;
@@ -257,18 +257,21 @@ __global__ void bam_extract_cols(const uint8_t *__restrict__ u, const uint32_t *
   salen[i] = sl; oclen[i] = ol;
   sa_ptr[i] = has_sa ? o + sa : 0u;
   oc_ptr[i] = (has_sa && ol) ? o + oc : 0u;
+  seqb[i] = has_sa ? (uint32_t)((l_seq + 1) / 2) : 0u;
 }
 
 struct Side {
   uint32_t *x_rec; int32_t *x_mtid, *x_mpos; uint64_t *x_nh;
   uint32_t *sa_rec, *cig_off, *cig_ops, *sa_off, *oc_off; uint8_t *sa_txt, *oc_txt;
-  long long x0, s0, cig0, sab0, ocb0;          // entries already in the context
+  uint32_t *seq_off; uint8_t *seq4; int32_t *seq_len;
+  long long x0, s0, cig0, sab0, ocb0, seqb0;   // entries already in the context
 };
 
 __global__ void bam_extract_side(const uint8_t *__restrict__ u, const uint32_t *__restrict__ rec_off, uint32_t nrec, long long n0, Side S,
                                  const uint32_t *__restrict__ xf, const uint32_t *__restrict__ xo, const uint32_t *__restrict__ sf, const uint32_t *__restrict__ so,
                                  const uint32_t *__restrict__ ncig, const uint32_t *__restrict__ cigo, const uint32_t *__restrict__ salen, const uint32_t *__restrict__ sao,
-                                 const uint32_t *__restrict__ oclen, const uint32_t *__restrict__ oco, const uint32_t *__restrict__ sa_ptr, const uint32_t *__restrict__ oc_ptr)
+                                 const uint32_t *__restrict__ oclen, const uint32_t *__restrict__ oco, const uint32_t *__restrict__ sa_ptr, const uint32_t *__restrict__ oc_ptr,
+                                 const uint32_t *__restrict__ seqb, const uint32_t *__restrict__ seqo)
 {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrec) return;
@@ -301,13 +304,18 @@ __global__ void bam_extract_side(const uint8_t *__restrict__ u, const uint32_t *
     long long q0 = S.ocb0 + oco[i];
     if (oclen[i]) { const uint8_t *op = u + oc_ptr[i]; for (uint32_t k = 0; k < oclen[i]; ++k) S.oc_txt[q0 + k] = op[k]; }
     S.oc_off[s + 1] = (uint32_t)(q0 + oclen[i]);
+    long long b0 = S.seqb0 + seqo[i];
+    const uint8_t *sq = r + 36 + l_name + 4 * nc;
+    for (uint32_t k = 0; k < seqb[i]; ++k) S.seq4[b0 + k] = sq[k];
+    S.seq_off[s + 1] = (uint32_t)(b0 + seqb[i]);
+    S.seq_len[s] = (int32_t)ld32(r + 20);
   }
 }
 
 }  // namespace bamdec
 
 struct bkid_decoder {                 // per-context streaming state, allocated on first use
-  DBuf comp[2], unc, carry, tasks, seed, cnt, land, base, rec_off, meta[7], metao[5], state;
+  DBuf comp[2], unc, carry, tasks, seed, cnt, land, base, rec_off, meta[8], metao[6], state;
   uint8_t *h_stage[2] = {nullptr, nullptr}; size_t h_cap = 0;
   bamdec::Task *h_tasks = nullptr; size_t h_tasks_cap = 0;
   cudaStream_t st_copy = nullptr;
@@ -522,20 +530,30 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
       TRY(c, c->sc.ensure((long long)nrec + 8, st));
       BK_LAUNCH((bam_walk<true>), GRID1(nsg, 128), 128, 0, st, u, total, nsg, seedv, d->cnt.as<uint32_t>(), d->land.as<uint32_t>(), (uint32_t *)nullptr, d->base.as<uint32_t>(), d->rec_off.as<uint32_t>(), state + 5);
       Cols C{c->flag.as<uint16_t>(), c->mapq.as<uint8_t>(), c->tid.as<int32_t>(), c->pos.as<int32_t>(), c->isize.as<int32_t>(), c->endpos.as<int32_t>()};
-      uint32_t *m[7]; for (int i = 0; i < 7; ++i) m[i] = d->meta[i].as<uint32_t>();
-      uint32_t *mo[5]; for (int i = 0; i < 5; ++i) mo[i] = d->metao[i].as<uint32_t>();
-      BK_LAUNCH(bam_extract_cols, GRID1(nrec, 128), 128, 0, st, u, d->rec_off.as<uint32_t>(), nrec, c->n, C, m[0], m[1], m[2], m[3], m[4], m[5], m[6]);
-      unsigned long long *tots = (unsigned long long *)(c->counters.as<unsigned>() + 52);     // 5 x u64
+      uint32_t *m[8]; for (int i = 0; i < 8; ++i) m[i] = d->meta[i].as<uint32_t>();        // [5],[6] = tag pointers, [7] = seq bytes
+      uint32_t *mo[6]; for (int i = 0; i < 6; ++i) mo[i] = d->metao[i].as<uint32_t>();
+      BK_LAUNCH(bam_extract_cols, GRID1(nrec, 128), 128, 0, st, u, d->rec_off.as<uint32_t>(), nrec, c->n, C, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+      unsigned long long *tots = (unsigned long long *)(c->counters.as<unsigned>() + 52);     // 6 x u64
       for (int i = 0; i < 5; ++i) bk::exclusive_scan<uint32_t, uint32_t>(m[i], mo[i], nrec, c->sc.scan_tmp.as<unsigned long long>(), tots + i, st);
-      unsigned long long ht5[5];
-      CU(c, cudaMemcpyAsync(ht5, tots, 40, cudaMemcpyDeviceToHost, st));
+      bk::exclusive_scan<uint32_t, uint32_t>(m[7], mo[5], nrec, c->sc.scan_tmp.as<unsigned long long>(), tots + 5, st);
+      unsigned long long ht5[6];
+      CU(c, cudaMemcpyAsync(ht5, tots, 48, cudaMemcpyDeviceToHost, st));
       TRY(c, sync_check(c));
       TRY(c, reserve_impl(c, c->n + nrec, c->n_x + (long long)ht5[0], c->n_sa + (long long)ht5[1], c->n_cig + (long long)ht5[2], c->sa_bytes + (long long)ht5[3], c->oc_bytes + (long long)ht5[4]));
+      {
+        size_t s_new = (size_t)(c->n_sa + (long long)ht5[1]);
+        TRY(c, c->seq_off.ensure((s_new + 1) * 4 + 64, (size_t)(c->n_sa + 1) * 4, st));
+        TRY(c, c->seq_len.ensure(s_new * 4 + 64, (size_t)c->n_sa * 4, st));
+        TRY(c, c->seq4.ensure((size_t)c->seq_bytes + (size_t)ht5[5] + 64, (size_t)c->seq_bytes, st));
+        if (c->n_sa == 0) CU(c, cudaMemsetAsync(c->seq_off.p, 0, 4, st));
+      }
       Side S{c->x_rec.as<uint32_t>(), c->x_mtid.as<int32_t>(), c->x_mpos.as<int32_t>(), c->x_nh.as<uint64_t>(),
              c->sa_rec.as<uint32_t>(), c->cig_off.as<uint32_t>(), c->cig_ops.as<uint32_t>(), c->sa_off.as<uint32_t>(), c->oc_off.as<uint32_t>(), c->sa_txt.as<uint8_t>(), c->oc_txt.as<uint8_t>(),
-             c->n_x, c->n_sa, c->n_cig, c->sa_bytes, c->oc_bytes};
-      BK_LAUNCH(bam_extract_side, GRID1(nrec, 128), 128, 0, st, u, d->rec_off.as<uint32_t>(), nrec, c->n, S, m[0], mo[0], m[1], mo[1], m[2], mo[2], m[3], mo[3], m[4], mo[4], m[5], m[6]);
+             c->seq_off.as<uint32_t>(), c->seq4.as<uint8_t>(), c->seq_len.as<int32_t>(),
+             c->n_x, c->n_sa, c->n_cig, c->sa_bytes, c->oc_bytes, c->seq_bytes};
+      BK_LAUNCH(bam_extract_side, GRID1(nrec, 128), 128, 0, st, u, d->rec_off.as<uint32_t>(), nrec, c->n, S, m[0], mo[0], m[1], mo[1], m[2], mo[2], m[3], mo[3], m[4], mo[4], m[5], m[6], m[7], mo[5]);
       c->n += nrec; c->n_x += (long long)ht5[0]; c->n_sa += (long long)ht5[1]; c->n_cig += (long long)ht5[2]; c->sa_bytes += (long long)ht5[3]; c->oc_bytes += (long long)ht5[4];
+      c->seq_bytes += (long long)ht5[5];
     }
     // ---- carry the partial record at the end of the chunk ----
     carry = total - carry_start;
@@ -562,6 +580,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   d->stats.inflate_ms = ms_inf; d->stats.boundaries_ms = ms_bound; d->stats.extract_ms = ms_ext;
   d->stats.n_records = c->n - n_first;
   d->stats.n_chunks = (int64_t)chunks.size();
+  c->have_seq = true;                    // the decoder always extracts the read bases of the SA records
   if (n_records) *n_records = c->n - n_first;
   return 0;
 }
@@ -591,6 +610,9 @@ int bkid_fetch_column(bkid_ctx *c, const char *name, void *out, int64_t cap_byte
   else if (k == "cig_ops") { p = c->p_cig_ops; nb = (size_t)c->n_cig * 4; } else if (k == "sa_off") { p = c->p_sa_off; nb = (ns + 1) * 4; }
   else if (k == "sa_txt") { p = c->p_sa_txt; nb = (size_t)c->sa_bytes; } else if (k == "oc_off") { p = c->p_oc_off; nb = (ns + 1) * 4; }
   else if (k == "oc_txt") { p = c->p_oc_txt; nb = (size_t)c->oc_bytes; }
+  else if (k == "seq_off") { p = c->have_seq ? c->p_seq_off : nullptr; nb = c->have_seq ? (ns + 1) * 4 : 0; }
+  else if (k == "seq4") { p = c->have_seq ? c->p_seq4 : nullptr; nb = c->have_seq ? (size_t)c->seq_bytes : 0; }
+  else if (k == "seq_len") { p = c->have_seq ? c->p_seq_len : nullptr; nb = c->have_seq ? ns * 4 : 0; }
   else return fail(c, BKID_ERR_ARG, "unknown column " + k);
   if (n_bytes) *n_bytes = (int64_t)nb;
   if (out && nb) {

@@ -75,6 +75,7 @@ struct bkid_host_bam {
   std::vector<uint64_t> x_name_hash;
   std::vector<uint32_t> sa_rec, cig_off, cig_ops, sa_off, oc_off;
   std::vector<uint8_t> sa_txt, oc_txt;
+  std::vector<uint32_t> seq_off; std::vector<uint8_t> seq4; std::vector<int32_t> seq_len;      // read bases of the SA records
   int32_t first_l_qseq = 0;
   bkid_batch batch;
   // narrow encodings (include/breakid_b200.h), filled when the whole batch fits them
@@ -167,7 +168,7 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
   h->flag.resize(n); h->mapq.resize(n);
   h->tid.resize(n); h->pos.resize(n); h->isize.resize(n); h->endpos.resize(n);
   // 5. columns (parallel) + per-thread SA side tables (merged in order afterwards)
-  struct Side { std::vector<uint32_t> rec, ncig, cig, salen, oclen; std::vector<uint8_t> sa, oc;
+  struct Side { std::vector<uint32_t> rec, ncig, cig, salen, oclen; std::vector<uint8_t> sa, oc, seq; std::vector<int32_t> lseq;
                 std::vector<uint32_t> xrec; std::vector<int32_t> xmtid, xmpos; std::vector<uint64_t> xhash; };
   int T = threads;
   std::vector<Side> sides(T);
@@ -237,12 +238,15 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
           size_t ol = oc ? strlen((const char *)oc) : 0;
           S.oclen.push_back((uint32_t)ol);
           if (ol) S.oc.insert(S.oc.end(), oc, oc + ol);
+          const uint8_t *sq = cg + 4 * (size_t)n_cig;
+          S.lseq.push_back(l_seq);
+          S.seq.insert(S.seq.end(), sq, sq + (size_t)((l_seq + 1) / 2));
         }
         if (i == 0) h->first_l_qseq = l_seq;
       }
     }
   });
-  h->cig_off.push_back(0); h->sa_off.push_back(0); h->oc_off.push_back(0);
+  h->cig_off.push_back(0); h->sa_off.push_back(0); h->oc_off.push_back(0); h->seq_off.push_back(0);
   for (Side &S : sides) {
     size_t ci = 0;
     for (size_t k = 0; k < S.rec.size(); ++k) {
@@ -251,7 +255,10 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
       h->cig_off.push_back((uint32_t)h->cig_ops.size());
       h->sa_off.push_back(h->sa_off.back() + S.salen[k]);
       h->oc_off.push_back(h->oc_off.back() + S.oclen[k]);
+      h->seq_len.push_back(S.lseq[k]);
+      h->seq_off.push_back(h->seq_off.back() + (uint32_t)((S.lseq[k] + 1) / 2));
     }
+    h->seq4.insert(h->seq4.end(), S.seq.begin(), S.seq.end());
     h->sa_txt.insert(h->sa_txt.end(), S.sa.begin(), S.sa.end());
     h->oc_txt.insert(h->oc_txt.end(), S.oc.begin(), S.oc.end());
     h->x_rec.insert(h->x_rec.end(), S.xrec.begin(), S.xrec.end());
@@ -275,6 +282,7 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
   B.sa_off = h->sa_off.data(); B.sa_txt = h->sa_txt.data();
   B.oc_off = h->oc_off.data(); B.oc_txt = h->oc_txt.data();
   B.isize16 = nullptr; B.span16 = nullptr; B.n_tid_runs = 0; B.tid_run_start = nullptr; B.tid_run_tid = nullptr;
+  B.seq_off = h->seq_off.data(); B.seq4 = h->seq4.data(); B.seq_len = h->seq_len.data();
   // narrow forms: 19 -> 11 B/record over PCIe when every value fits
   h->batch_narrow = B;
   {

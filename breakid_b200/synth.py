@@ -446,6 +446,71 @@ def random_nib_bytes(length: int, seed: int, device="cpu", homopolymer_at=()) ->
     return (codes[0::2] << 4) | codes[1::2]
 
 
+_NIB_ASCII = np.frombuffer(b"TCAGNNNNTCAGNNNN", np.uint8)          # nib code -> base (src/nibtools.cc:55-61; bit 3 = mask flag)
+_BAM_CODE = {ord("A"): 1, ord("C"): 2, ord("G"): 4, ord("T"): 8}
+_COMP = bytes.maketrans(b"ACGTN", b"TGCAN")
+
+
+def nib_ascii(payload, length: int) -> np.ndarray:
+    """packed 4-bit nib payload -> ASCII bases (uint8 array of `length`)"""
+    p = payload.cpu().numpy() if hasattr(payload, "cpu") else np.asarray(payload)
+    codes = np.empty(p.shape[0] * 2, np.uint8)
+    codes[0::2] = p >> 4; codes[1::2] = p & 0xf
+    return _NIB_ASCII[codes[:length]]
+
+
+def pack_bam_seq(ascii_bases: bytes) -> bytes:
+    """ASCII bases -> BAM 4-bit packing ("=ACMGRSVTWYHKDBN", high nibble first)"""
+    c = [_BAM_CODE.get(b, 15) for b in ascii_bases]
+    if len(c) % 2:
+        c.append(0)
+    return bytes((c[i] << 4) | c[i + 1] for i in range(0, len(c), 2))
+
+
+def split_read_sequences(hb, genome: List[np.ndarray], corrupt=(), seed: int = 0):
+    """Read bases for the SA-tagged records of a synthetic batch, consistent with the genome: matched operations copy the
+    reference under the record, the soft clip carries the bases the SA tag points at (reverse-complemented when the two
+    alignments are on different strands).  Records listed in ``corrupt`` (indices into the SA table) get random clip
+    bases instead -- split alignments the validator must reject.  Returns (seq table dict for HostBatch, list of ASCII reads)."""
+    rng = np.random.RandomState(seed)
+    s = hb.side
+    names = {n: t for t, n in enumerate(hb.target_names)}
+    reads, packed, lens = [], [], []
+    for k in range(hb.n_sa):
+        i = int(s["sa_rec"][k])
+        tid, pos, flag = int(hb.cols["tid"][i]), int(hb.cols["pos"][i]), int(hb.cols["flag"][i])
+        ops = s["cig_ops"][int(s["cig_off"][k]):int(s["cig_off"][k + 1])]
+        f = bytes(s["sa_txt"][int(s["sa_off"][k]):int(s["sa_off"][k + 1])]).split(b";")[0].split(b",")
+        sa_tid, sa_pos, sa_minus = names.get(f[0].decode(), -1), int(f[1]), f[2] == b"-"
+        sa_m, num = 0, b""
+        for ch in f[3]:
+            if 48 <= ch <= 57: num += bytes([ch])
+            else:
+                if ch in b"M=X": sa_m += int(num)
+                num = b""
+        window = bytes(genome[sa_tid][sa_pos - 1:sa_pos - 1 + sa_m]) if sa_tid >= 0 else b"N" * sa_m
+        if sa_minus != bool(flag & REVERSE):
+            window = window.translate(_COMP)[::-1]
+        out, cur = b"", pos
+        for op in ops:
+            ln, o = int(op) >> 4, int(op) & 0xf
+            if o in (OP_M, OP_EQ, OP_X):
+                out += bytes(genome[tid][cur:cur + ln]); cur += ln
+            elif o == OP_S:
+                clip = window
+                if k in corrupt:
+                    clip = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), ln))
+                out += (clip + b"N" * ln)[:ln]
+            elif o == OP_I:
+                out += b"N" * ln
+            elif o in (OP_D, OP_N):
+                cur += ln
+        reads.append(out); packed.append(pack_bam_seq(out)); lens.append(len(out))
+    off = np.concatenate([[0], np.cumsum([len(p) for p in packed])]).astype(np.uint32)
+    seq4 = np.frombuffer(b"".join(packed), np.uint8).copy() if packed else np.zeros(0, np.uint8)
+    return {"seq_off": off, "seq4": seq4, "seq_len": np.array(lens, np.int32)}, reads
+
+
 def write_nib(path: str, payload: torch.Tensor, length: int):
     with open(path, "wb") as f:
         f.write(np.array([NIB_MAGIC, length], dtype="<u4").tobytes())

@@ -55,7 +55,9 @@ typedef struct {
   int32_t bp_pos_error;    /* 2          src/BreakID.cc:444-445 */
   int32_t mismatch_num;    /* 10         src/BreakID.cc:891 */
   int32_t sd_mult;         /* 3          the literal in src/BreakID.cc:103 (north_star's -s) */
-  int32_t reserved;
+  int32_t validate_align;  /* 0          extension (north_star kernel 4, not in the reference): 1 = a split alignment only counts as
+                              evidence if the soft-clipped bases of the read align to the reference at the position its SA
+                              tag claims (banded edit distance, band 8, at most len/10 + 2 edits); needs seq4 + nib */
 } bkid_params;
 
 /* One struct-of-arrays batch of decoded alignment records, in BAM file order.  All pointers are
@@ -97,6 +99,12 @@ typedef struct {
   int64_t n_tid_runs;               /* run-length form of tid (records are coordinate sorted: one run per target) */
   const uint32_t *tid_run_start;    /* [n_tid_runs] ascending first record index of each run, [0] = 0 */
   const int32_t *tid_run_tid;       /* [n_tid_runs] */
+  /* Optional: read bases of the SA-tagged records, exactly as the BAM record stores them (4-bit codes "=ACMGRSVTWYHKDBN",
+   * two per byte, high nibble first), for the banded-alignment evidence validator (bkid_params.validate_align).
+   * All three NULL = not provided (the validator then leaves every evidence row as it is). */
+  const uint32_t *seq_off;          /* [n_sa+1] byte offsets into seq4 */
+  const uint8_t *seq4;
+  const int32_t *seq_len;           /* [n_sa] l_seq */
 } bkid_batch;
 
 /* A discordant pair (reference struct discordant_pair, src/BreakID.h:39-58) as kept on the device. */

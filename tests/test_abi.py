@@ -37,7 +37,7 @@ def test_pod_layouts_match_header():
     from breakid_b200 import api
     assert api.PAIR_DTYPE.itemsize == 64 and api.CLUSTER_DTYPE.itemsize == 192
     import ctypes
-    assert ctypes.sizeof(api.Batch) == 25 * 8 and ctypes.sizeof(api.Params) == 32
+    assert ctypes.sizeof(api.Batch) == 28 * 8 and ctypes.sizeof(api.Params) == 32
 
 
 def test_host_bam_decoder_roundtrip(tmp_path):

@@ -67,3 +67,81 @@ def test_banded_align_kernel_equals_oracle():
     with pytest.raises(api.BkidError):
         c.op_banded_align([b"A"], [b"A"], 16)
     c.close()
+
+
+def _validity_by_oracle(hb, genome, reads):
+    """which SA records the validator must keep: python restatement of k7_validate_rows' mapping + the oracle DP"""
+    import oracle_py as O
+    from breakid_b200 import synth
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    s = hb.side
+    names = {n: t for t, n in enumerate(hb.target_names)}
+    keep = np.ones(hb.n_sa, bool)
+    for k in range(hb.n_sa):
+        i = int(s["sa_rec"][k])
+        ops = [(int(o) >> 4, int(o) & 0xf) for o in s["cig_ops"][int(s["cig_off"][k]):int(s["cig_off"][k + 1])]]
+        read = reads[k]
+        if ops[0][1] == synth.OP_S: q = read[:ops[0][0]]
+        elif ops[-1][1] == synth.OP_S: q = read[len(read) - ops[-1][0]:]
+        else: continue
+        f = bytes(s["sa_txt"][int(s["sa_off"][k]):int(s["sa_off"][k + 1])]).split(b";")[0].split(b",")
+        t, sa_pos, sa_minus = names[f[0].decode()], int(f[1]), f[2] == b"-"
+        m, num = 0, b""
+        for ch in f[3]:
+            if 48 <= ch <= 57: num += bytes([ch])
+            else:
+                if ch in b"M": m += int(num)
+                num = b""
+        ref = bytes(genome[t][sa_pos - 1:sa_pos - 1 + m])
+        if sa_minus != bool(int(hb.cols["flag"][i]) & 0x10):
+            q = q.translate(comp)[::-1]
+        dist = O.banded_edit(q, ref, 12)
+        keep[k] = dist >= 0 and dist * 10 <= len(q) + 20
+    return keep
+
+
+@pytest.mark.gpu
+def test_validate_align_drops_split_reads_whose_clip_does_not_align(small_data):
+    """default-off evidence validator (bkid_params.validate_align): with true read bases nothing changes; split reads
+    whose clipped bases are random stop being evidence -- identical to the oracle on the same batch with the SA tags
+    of exactly those records removed"""
+    import oracle_py as O
+    from breakid_b200 import api, synth
+    d, hb0, nibs = small_data
+    genome = [synth.nib_ascii(p, l) for p, l in nibs]
+    rng = np.random.RandomState(3)
+    for frac in (0.0, 0.35):
+        hb = api.HostBatch(hb0.cols, hb0.name_hash, hb0.side, hb0.target_len, hb0.target_names)
+        corrupt = set(np.nonzero(rng.rand(hb.n_sa) < frac)[0].tolist())
+        seq, reads = synth.split_read_sequences(hb, genome, corrupt=corrupt, seed=9)
+        hb.set_seq(seq)
+        keep = _validity_by_oracle(hb, genome, reads)
+        assert (~keep).sum() == len(corrupt)                     # random 60+ base clips never align by chance
+        # expected: SA text of rejected records removed -> they are ordinary records (still counted for coverage)
+        side = dict(hb.side)
+        so = side["sa_off"].astype(np.int64)
+        parts = [side["sa_txt"][so[k]:so[k + 1]] if keep[k] else side["sa_txt"][:0] for k in range(hb.n_sa)]
+        side["sa_txt"] = np.concatenate(parts) if parts else side["sa_txt"]
+        side["sa_off"] = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.uint32)
+        hb_exp = api.HostBatch(hb.cols, hb.name_hash, side, hb.target_len, hb.target_names)
+        om, osd, od, exp = O.run(hb_exp, nibs, mode=0)
+        c = api.Context(hb.target_len, hb.target_names, device=0, validate_align=1)
+        c.push(hb)
+        for t, (p, l) in enumerate(nibs):
+            c.set_nib(t, p, l)
+        mean, sd, dist, ncall = c.run()
+        got = c.fetch_clusters()
+        assert (mean, sd, dist) == (om, osd, od)
+        assert got.tobytes() == exp.tobytes(), frac
+        if frac == 0.0:
+            base = O.run(hb0, nibs, mode=0)[3]
+            assert got.tobytes() == base.tobytes()               # validator on, all evidence true: nothing changes
+        else:
+            assert int(got["n_split_read"].sum()) < int(O.run(hb0, nibs, mode=0)[3]["n_split_read"].sum())
+        c.close()
+    # the flag without read bases is an error, not a silent no-op
+    c = api.Context(hb0.target_len, hb0.target_names, device=0, validate_align=1)
+    c.push(hb0)
+    with pytest.raises(api.BkidError, match="read bases"):
+        c.run()
+    c.close()

@@ -116,6 +116,9 @@ def _assert_same_as_host_decoder(path, chunk_kb=None):
         got = c.fetch_column(k, dt)
         exp = hb.cols[k] if k in hb.cols else hb.x[k] if k in hb.x else hb.side[k]
         assert np.array_equal(got, np.asarray(exp, dtype=dt).reshape(-1)), (k, chunk_kb)
+    if hb.seq is not None:                       # read bases of the SA records
+        for k, dt in api._SEQ:
+            assert np.array_equal(c.fetch_column(k, dt), hb.seq[k]), k
     f.close()
     return c, hb, st
 
@@ -137,8 +140,11 @@ def test_device_decode_whole_path(tmp_path, small_data, chunk_kb):
     import oracle_py as O
     d, hb0, nibs = small_data
     p = str(tmp_path / "reads.bam")
-    bamio.write_bam(p, d)
+    genome = [synth.nib_ascii(pl, l) for pl, l in nibs]
+    seq, reads = synth.split_read_sequences(hb0, genome)
+    bamio.write_bam(p, d, sa_seq=seq)
     c, hb, st = _assert_same_as_host_decoder(p, chunk_kb)
+    assert hb.seq is not None and np.array_equal(hb.seq["seq4"], seq["seq4"]) and np.array_equal(hb.seq["seq_len"], seq["seq_len"])
     for t, (pl, l) in enumerate(nibs):
         c.set_nib(t, pl, l)
     mean, sd, dist, ncall = c.run()
