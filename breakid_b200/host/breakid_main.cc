@@ -43,6 +43,7 @@ static const char *kHelp =
     "     \t -s         \t sd multiplier of the distance formula [3]\n "
     "     \t -r         \t refGene.txt [$BREAKID_INSTALLDIR/ref_files/refGene.txt]\n "
     "     \t -x         \t exclude regions (BED: chrom, start, end): records starting there are ignored [none]\n "
+    "     \t -validate  \t split reads count only if their clipped bases align where the SA tag says (needs nib files) [off]\n "
     "     \t -threads   \t BAM decode threads [8]\n "
     "     \t -gpu       \t CUDA device [0]\n ";
 
@@ -84,10 +85,10 @@ int main(int argc, char *argv[])
   double t_start = now_s();
   static struct option longopts[] = {
       {"help", 0, 0, 'h'}, {"i", 1, 0, 1}, {"o", 1, 0, 2}, {"q", 1, 0, 3}, {"n", 1, 0, 4}, {"fast", 0, 0, 5}, {"t", 1, 0, 6},
-      {"all", 0, 0, 7}, {"s", 1, 0, 8}, {"r", 1, 0, 9}, {"threads", 1, 0, 10}, {"gpu", 1, 0, 11}, {"x", 1, 0, 12}, {0, 0, 0, 0}};
+      {"all", 0, 0, 7}, {"s", 1, 0, 8}, {"r", 1, 0, 9}, {"threads", 1, 0, 10}, {"gpu", 1, 0, 11}, {"x", 1, 0, 12}, {"validate", 0, 0, 13}, {0, 0, 0, 0}};
   std::string inp, out, nib_dir, refgene, exclude_bed;
   int qual = 20, times = 2, sd_mult = 3, threads = 8, gpu = 0;
-  bool fast = false, filter = true;
+  bool fast = false, filter = true, validate = false;
   int opt, li;
   optind = 0;
   opterr = 0;
@@ -106,6 +107,7 @@ int main(int argc, char *argv[])
       case 10: threads = std::max(1, atoi(optarg)); break;
       case 11: gpu = atoi(optarg); break;
       case 12: exclude_bed = optarg; break;
+      case 13: validate = true; break;
       case '?':
         if (optopt == 0 && optind > 0 && (!strcmp(argv[optind - 1], "-?") || !strcmp(argv[optind - 1], "-help"))) { std::cerr << kHelp; exit(1); }
         std::cerr << kHelp;
@@ -149,7 +151,7 @@ int main(int argc, char *argv[])
   // ---- device ----
   bkid_params prm;
   bkid_default_params(&prm);
-  prm.qual = qual; prm.times = times; prm.fast = fast ? 1 : 0; prm.sd_mult = sd_mult;
+  prm.qual = qual; prm.times = times; prm.fast = fast ? 1 : 0; prm.sd_mult = sd_mult; prm.validate_align = validate ? 1 : 0;
   bkid_ctx *ctx = bkid_create(gpu, hdr, &prm);
   if (!ctx) { std::cerr << "Error: " << bkid_last_error(nullptr) << std::endl; exit(1); }
   auto die = [&](const char *what) { std::cerr << "Error: " << what << ": " << bkid_last_error(ctx) << std::endl; exit(1); };
