@@ -37,8 +37,13 @@ def launches(src, dst, title):
     # the bench runs warm-up steps, the timed resident steps, then the e2e steps; the resident steps are identical,
     # take the last one that is followed by another k1_classify (= a complete step)
     assert len(starts) >= 2, "no complete step in the launch list"
-    a, b = starts[-2], starts[-1]
-    step = ours[a:b]
+    # the e2e steps at the end push host batches (widen_* kernels): take the last complete RESIDENT step
+    step = None
+    for a, b in reversed(list(zip(starts[:-1], starts[1:]))):
+        if not any(r[0].startswith("widen_") for r in ours[a:b]):
+            step = ours[a:b]
+            break
+    assert step is not None, "no resident step in the launch list"
     tot = sum(r[3] for r in step)
     agg = OrderedDict()
     for r in step:
