@@ -97,7 +97,7 @@ k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
 {
   // The flag predicates are evaluated two records at a time on packed 2x16-bit words and the mapq
   // predicates four at a time on packed 4x8-bit words (SIMD-in-register video instructions), so the
-  // kernel stays DRAM-bound instead of issue-bound (profiles/r01_ncu_k1_classify.md).
+  // kernel stays DRAM-bound instead of issue-bound (profiles/r01m_ncu_top_kernels.md).
   __shared__ unsigned long long sh_sum;
   __shared__ unsigned sh_cnt;                 // n_ins in the low half, n_cand in the high half (<= 4096 each)
   if (threadIdx.x == 0) { sh_sum = 0; sh_cnt = 0; }
