@@ -85,6 +85,7 @@ struct bkid_ctx {
   cudaEvent_t ev[16];
   cudaEvent_t ev_run[2];
   cudaEvent_t ev_side[2];
+  cudaEvent_t ev_w[4];                   // push_batch: narrow column copied (st) -> widened (st3) -> joined (st)
   bool k8_attr_set = false;
   bool sd_side_pending = false;           // sd_block_stats in flight on st2 (bkid_shard_sd_prepare)
   bool maxspan_cached = false, maxspan_pending = false;   // pending: max_span_kernel in flight on st3
@@ -536,6 +537,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   for (auto &ev : c->ev) cudaEventCreate(&ev);
   for (auto &ev : c->ev_run) cudaEventCreate(&ev);
   for (auto &ev : c->ev_side) cudaEventCreate(&ev);
+  for (auto &ev : c->ev_w) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   c->nt = hdr->n_targets;
   for (int i = 0; i < c->nt; ++i) { c->target_len.push_back(hdr->target_len[i]); c->names.emplace_back(hdr->target_name[i]); }
   int nt = c->nt, m = nt + 1;
@@ -584,6 +586,7 @@ void bkid_destroy(bkid_ctx *c)
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   for (auto &ev : c->ev_run) cudaEventDestroy(ev);
   for (auto &ev : c->ev_side) cudaEventDestroy(ev);
+  for (auto &ev : c->ev_w) cudaEventDestroy(ev);
   cudaStreamDestroy(c->st2);
   cudaStreamDestroy(c->st3);
   cudaStreamDestroy(c->st);
@@ -682,33 +685,43 @@ static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
   TRY(c, reserve_impl(c, n0 + b->n, x0 + b->n_x, s0 + b->n_sa, c->n_cig + ncig, c->sa_bytes + nsa_b, c->oc_bytes + noc_b));
   size_t n = (size_t)b->n;
   if (n) {
-    CU(c, cudaMemcpyAsync(c->flag.as<uint16_t>() + n0, b->flag, n * 2, kind, st));
-    CU(c, cudaMemcpyAsync(c->mapq.as<uint8_t>() + n0, b->mapq, n, kind, st));
-    CU(c, cudaMemcpyAsync(c->pos.as<int32_t>() + n0, b->pos, n * 4, kind, st));
-    // narrow encodings are staged in scratch and widened on the device
+    // Narrow encodings (staged in scratch) go first and are widened on a second stream, so that the widening kernels
+    // overlap the copies of the remaining columns instead of standing between them on the copy stream.
+    cudaStream_t sw = c->st3;
     size_t stage = (b->isize16 ? n * 2 : 0) + (b->span16 ? n * 2 : 0) + (b->tid ? 0 : (size_t)b->n_tid_runs * 8) + 64;
     TRY(c, c->tmpH.ensure(stage, 0, st));
     char *sp = (char *)c->tmpH.p;
+    bool widened = false;
     if (b->tid) CU(c, cudaMemcpyAsync(c->tid.as<int32_t>() + n0, b->tid, n * 4, kind, st));
     else {
       uint32_t *rs = (uint32_t *)sp; sp += (size_t)b->n_tid_runs * 4;
       int32_t *rt = (int32_t *)sp; sp += (size_t)b->n_tid_runs * 4;
       CU(c, cudaMemcpyAsync(rs, b->tid_run_start, (size_t)b->n_tid_runs * 4, kind, st));
       CU(c, cudaMemcpyAsync(rt, b->tid_run_tid, (size_t)b->n_tid_runs * 4, kind, st));
-      BK_LAUNCH(widen_tid_runs, GRID1(n, 256), 256, 0, st, rs, rt, (int)b->n_tid_runs, (long long)n, c->tid.as<int32_t>() + n0);
+      CU(c, cudaEventRecord(c->ev_w[0], st)); CU(c, cudaStreamWaitEvent(sw, c->ev_w[0], 0));
+      BK_LAUNCH(widen_tid_runs, GRID1(n, 256), 256, 0, sw, rs, rt, (int)b->n_tid_runs, (long long)n, c->tid.as<int32_t>() + n0);
+      widened = true;
     }
     if (b->isize) CU(c, cudaMemcpyAsync(c->isize.as<int32_t>() + n0, b->isize, n * 4, kind, st));
     else {
       int16_t *s16 = (int16_t *)sp; sp += n * 2;
       CU(c, cudaMemcpyAsync(s16, b->isize16, n * 2, kind, st));
-      BK_LAUNCH(widen_isize16, GRID1(n, 256), 256, 0, st, s16, (long long)n, c->isize.as<int32_t>() + n0);
+      CU(c, cudaEventRecord(c->ev_w[1], st)); CU(c, cudaStreamWaitEvent(sw, c->ev_w[1], 0));
+      BK_LAUNCH(widen_isize16, GRID1(n, 256), 256, 0, sw, s16, (long long)n, c->isize.as<int32_t>() + n0);
+      widened = true;
     }
+    CU(c, cudaMemcpyAsync(c->pos.as<int32_t>() + n0, b->pos, n * 4, kind, st));
     if (b->endpos) CU(c, cudaMemcpyAsync(c->endpos.as<int32_t>() + n0, b->endpos, n * 4, kind, st));
     else {
       uint16_t *e16 = (uint16_t *)sp; sp += n * 2;
       CU(c, cudaMemcpyAsync(e16, b->span16, n * 2, kind, st));
-      BK_LAUNCH(widen_span16, GRID1(n, 256), 256, 0, st, c->pos.as<int32_t>() + n0, e16, (long long)n, c->endpos.as<int32_t>() + n0);
+      CU(c, cudaEventRecord(c->ev_w[2], st)); CU(c, cudaStreamWaitEvent(sw, c->ev_w[2], 0));
+      BK_LAUNCH(widen_span16, GRID1(n, 256), 256, 0, sw, c->pos.as<int32_t>() + n0, e16, (long long)n, c->endpos.as<int32_t>() + n0);
+      widened = true;
     }
+    CU(c, cudaMemcpyAsync(c->flag.as<uint16_t>() + n0, b->flag, n * 2, kind, st));
+    CU(c, cudaMemcpyAsync(c->mapq.as<uint8_t>() + n0, b->mapq, n, kind, st));
+    if (widened) { CU(c, cudaEventRecord(c->ev_w[3], sw)); CU(c, cudaStreamWaitEvent(st, c->ev_w[3], 0)); }
   }
   size_t nx = (size_t)b->n_x;
   if (nx) {
