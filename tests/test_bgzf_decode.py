@@ -214,3 +214,56 @@ def test_device_decode_rejects_corrupt_files(tmp_path):
     assert c.push_bgzf(f) > 3000
     f.close()
     c.close()
+
+
+@pytest.mark.gpu
+def test_device_decode_edge_files(tmp_path):
+    """no records at all; a BAM header that spans several BGZF blocks (first record deep inside block 3); a single
+    record; every record in its own BGZF block"""
+    rng = np.random.RandomState(4)
+    targets = [("chr1", 500000), ("chr2", 400000)]
+    # 1. header only
+    payload, first = _raw_bam([], targets)
+    p = str(tmp_path / "empty.bam")
+    _bgzf_write(p, payload)
+    f = api.BgzfFile(p)
+    c = api.Context(f.target_len, f.target_names, device=0)
+    assert c.push_bgzf(f) == 0
+    f.close()
+    c.close()
+    # 2. long header: 200 KB of @CO lines in front of the records
+    recs = _hostile_records(rng, 500)
+    text_pad = "".join("@CO\t%s\n" % ("x" * 90) for _ in range(2200))
+    text = "@HD\tVN:1.4\tSO:coordinate\n" + text_pad + "".join("@SQ\tSN:%s\tLN:%d\n" % t for t in targets)
+    out = b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(targets))
+    for nm, ln in targets:
+        out += struct.pack("<i", len(nm) + 1) + nm.encode() + b"\0" + struct.pack("<i", ln)
+    assert len(out) > 3 * 0xff00
+    for r in recs:
+        out += struct.pack("<i", len(r)) + r
+    p = str(tmp_path / "longhdr.bam")
+    _bgzf_write(p, out)
+    cc, hb, st = _assert_same_as_host_decoder(p, None)
+    cc.close()
+    cc, hb, st = _assert_same_as_host_decoder(p, 64)
+    cc.close()
+    # 3. one record; 4. one BGZF block per record (tiny blocks)
+    payload, first = _raw_bam(recs[:1], targets)
+    p = str(tmp_path / "one.bam")
+    _bgzf_write(p, payload)
+    cc, hb, st = _assert_same_as_host_decoder(p, None)
+    assert hb.n == 1
+    cc.close()
+    payload, first = _raw_bam(recs[:300], targets)
+    p = str(tmp_path / "tiny_blocks.bam")
+    with open(p, "wb") as fo:
+        fo.write(bamio._bgzf_block(payload[:first], 6))
+        o = first
+        for r in recs[:300]:
+            n = 4 + len(r)
+            fo.write(bamio._bgzf_block(payload[o:o + n], 6))
+            o += n
+        fo.write(bamio._BGZF_EOF)
+    cc, hb, st = _assert_same_as_host_decoder(p, None)
+    assert hb.n == 300 and st["n_blocks"] == 301
+    cc.close()
