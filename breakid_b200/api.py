@@ -276,7 +276,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
-           "bkid_push_bgzf", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align"]
+           "bkid_push_bgzf", "bkid_push_bgzf_range", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -305,6 +305,7 @@ def cuda_lib():
         L.bkid_op_banded_align.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int32, vp]
         L.bkid_device_gather_rows.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32]
         L.bkid_push_bgzf.argtypes = [vp, vp, vp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
+        L.bkid_push_bgzf_range.argtypes = [vp, vp, vp, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.bkid_get_decode_stats.argtypes = [vp, C.POINTER(DecodeStats)]
         L.bkid_fetch_column.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.bkid_reset.argtypes = [vp]
@@ -455,6 +456,14 @@ class Context:
                                           f.n_blocks if n_blocks is None else n_blocks,
                                           f.first_record if first_record is None else first_record, C.byref(n)))
         return int(n.value)
+
+    def push_bgzf_range(self, f: "BgzfFile", first_block: int, end_block: int, data_ptr=None):
+        """device decode of the records that start inside blocks [first_block, end_block) (``bkid_push_bgzf_range``);
+        returns (n_records, stream offset of the first decoded record, stream offset of the next range's first record)"""
+        n, a, b = C.c_int64(), C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.bkid_push_bgzf_range(self.ctx, C.c_void_p(data_ptr if data_ptr is not None else f.data), C.c_void_p(f.blocks), f.n_blocks,
+                                                f.first_record, first_block, end_block, C.byref(n), C.byref(a), C.byref(b)))
+        return int(n.value), int(a.value), int(b.value)
 
     def decode_stats(self) -> dict:
         s = DecodeStats()

@@ -115,10 +115,11 @@ __device__ bool looks_like_record(const uint8_t *__restrict__ u, uint32_t o, uin
   return true;
 }
 
-// one warp per segment s >= 1: first offset in [s*SEG, (s+1)*SEG) that starts a chain of 3 plausible records
-__global__ void bam_seed(const uint8_t *__restrict__ u, uint32_t total, int n_ref, uint32_t nseg, uint32_t *__restrict__ seed)
+// one warp per segment s >= first_seg (1 when the chain origin is known, 0 when a block range starts mid-stream):
+// first offset in [s*SEG, (s+1)*SEG) that starts a chain of 3 plausible records
+__global__ void bam_seed(const uint8_t *__restrict__ u, uint32_t total, int n_ref, uint32_t nseg, uint32_t *__restrict__ seed, uint32_t first_seg)
 {
-  uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) + 1;
+  uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) + first_seg;
   if (s >= nseg) return;
   uint32_t lane = threadIdx.x & 31;
   uint32_t lo = s * SEG, hi = min(total, lo + SEG);
@@ -141,7 +142,7 @@ __global__ void bam_seed(const uint8_t *__restrict__ u, uint32_t total, int n_re
 // count pass: cnt / land / why (0 = reached the next seed, 1 = end of data or partial record, 2 = block_size < 32)
 template <bool WRITE>
 __global__ void bam_walk(const uint8_t *__restrict__ u, uint32_t total, uint32_t nseg, const uint32_t *__restrict__ seed, uint32_t *__restrict__ cnt, uint32_t *__restrict__ land,
-                         uint32_t *__restrict__ why, const uint32_t *__restrict__ base, uint32_t *__restrict__ rec_off, int *__restrict__ err)
+                         uint32_t *__restrict__ why, const uint32_t *__restrict__ base, uint32_t *__restrict__ rec_off, int *__restrict__ err, uint32_t stop_at)
 {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
@@ -150,7 +151,7 @@ __global__ void bam_walk(const uint8_t *__restrict__ u, uint32_t total, uint32_t
   uint32_t limit = total;
   for (uint32_t j = s + 1; j < nseg; ++j) if (seed[j] != NONE) { limit = seed[j]; break; }
   uint32_t n = 0, w = WRITE ? base[s] : 0, y = 0;
-  while (o < limit) {
+  while (o < limit && o < stop_at) {                       // records starting at or after stop_at belong to the next block range
     if ((uint64_t)o + 4 > total) { y = 1; break; }
     uint32_t bs = ld32(u + o);
     if (bs < 32) { if (WRITE) atomicCAS(err, 0, 1); y = 2; break; }
@@ -164,13 +165,14 @@ __global__ void bam_walk(const uint8_t *__restrict__ u, uint32_t total, uint32_t
 
 // accept seeds by induction from segment 0; drop the first seed the previous walk does not land on
 __global__ void bam_stitch(uint32_t nseg, uint32_t *__restrict__ seed, const uint32_t *__restrict__ land, const uint32_t *__restrict__ why,
-                           int *__restrict__ state /* [0] changed, [1] corrupt, [2] carry start */)
+                           int *__restrict__ state /* [0] changed, [1] corrupt, [2] carry start */, uint32_t stop_at)
 {
   if (blockIdx.x || threadIdx.x) return;
   uint32_t prev = 0;
   state[0] = 0;
   for (uint32_t s = 1; s < nseg; ++s) {
     if (seed[s] == NONE) continue;
+    if (land[prev] >= stop_at) break;                        // the range ends inside segment prev: later seeds are not ours
     if (land[prev] != seed[s]) {                            // seed s is not on the true chain (or lies inside the trailing partial record)
       if (why[prev] == 2) state[1] = 1;                     // the true chain itself hit a corrupt block_size
       seed[s] = NONE; state[0] = 1;
@@ -355,10 +357,15 @@ static void decoder_free(bkid_ctx *c)
   c->dec = nullptr;
 }
 
-int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t *n_records)
+// Decode the records that START in the uncompressed extent of blocks [b_begin, b_end).  b_begin == 0: the chain starts at
+// first_record_uoffset; otherwise the first record is found by seeding (and reported in *first_uoff so that the caller
+// can verify it against where the previous range landed).  b_end < n_blocks: up to `overlap` further blocks are read
+// so that the record straddling the range end completes; *land_uoff = start of the first record of the NEXT range.
+static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t b_begin, int64_t b_end,
+                          int64_t *n_records, uint64_t *first_uoff, uint64_t *land_uoff)
 {
   using namespace bamdec;
-  if (!c || !file || !blocks || n_blocks < 0) return c ? fail(c, BKID_ERR_ARG, "bad bgzf arguments") : BKID_ERR_ARG;
+  if (!c || !file || !blocks || n_blocks < 0 || b_begin < 0 || b_end < b_begin || b_end > n_blocks) return c ? fail(c, BKID_ERR_ARG, "bad bgzf arguments") : BKID_ERR_ARG;
   cudaSetDevice(c->device);
   c->err.clear();
   if (c->borrowed) return fail(c, BKID_ERR_ARG, "context holds borrowed device columns; bkid_reset first");
@@ -384,13 +391,18 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   std::vector<std::pair<int64_t, int64_t>> chunks;
   uint64_t total_u = 0;
   size_t max_span = 0, max_unc = 0;
-  for (int64_t b0 = 0; b0 < n_blocks;) {
+  const int64_t OVERLAP = 64;                               // blocks read past the range end for the straddling record (4 MiB)
+  const int64_t b_last = b_end < n_blocks ? std::min<int64_t>(n_blocks, b_end + OVERLAP) : n_blocks;
+  uint64_t u_begin = 0, u_end = 0;                          // uncompressed offsets of the range in the whole stream
+  for (int64_t b = 0; b < b_end; ++b) { if (b < b_begin) u_begin += blocks[b].usize; u_end += blocks[b].usize; }
+  const bool open_end = b_end >= n_blocks;
+  for (int64_t b0 = b_begin; b0 < b_last;) {
     size_t cb = 0, ub = 0; int64_t b1 = b0;
     uint64_t span0 = blocks[b0].payload_off;
     // (a small first chunk to fill the copy pipeline sooner was measured slower: one inflate launch costs a full
     // per-block latency of ~20 ms whatever its size, so fewer, bigger launches win)
     const size_t ccap = COMP_CAP, ucap = UNC_CAP;
-    while (b1 < n_blocks) {
+    while (b1 < b_last) {
       size_t span = (size_t)(blocks[b1].payload_off + blocks[b1].payload_len + 8 - span0);
       if (b1 > b0 && (span > ccap || ub + blocks[b1].usize > ucap)) break;
       if (blocks[b1].usize > (1u << 16) || (b1 > b0 && blocks[b1].payload_off < blocks[b1 - 1].payload_off + blocks[b1 - 1].payload_len))
@@ -448,10 +460,15 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   cudaEventRecord(d->ev_t[0], st);
   if (!chunks.empty()) TRY(c, stage_chunk(0));
   uint32_t carry = 0;
-  uint64_t skip = first_record_uoffset;            // bytes of the uncompressed stream before the first record (BAM header)
+  uint64_t skip = b_begin == 0 ? first_record_uoffset : 0;      // bytes of the uncompressed stream before the first record (BAM header)
+  bool seek = b_begin > 0;                         // the first record of a mid-stream range is found by seeding
+  bool range_done = false;
+  uint64_t chunk_u0 = u_begin;                     // stream offset of the first NEW byte of the current chunk
+  if (first_uoff) *first_uoff = first_record_uoffset;
+  if (land_uoff) *land_uoff = 0;
   long long n_first = c->n;
   float ms_inf = 0, ms_bound = 0, ms_ext = 0;
-  for (size_t k = 0; k < chunks.size(); ++k) {
+  for (size_t k = 0; k < chunks.size() && !range_done; ++k) {
     int slot = (int)(k & 1);
     if (k + 1 < chunks.size()) TRY(c, stage_chunk(k + 1));
     int64_t b0 = chunks[k].first, b1 = chunks[k].second;
@@ -475,6 +492,9 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     cudaEventRecord(d->ev_t[2], st);
     d->stats.n_blocks += nt; d->stats.uncompressed_bytes += (int64_t)(total - carry);
     // ---- record boundaries ----
+    const uint64_t buf_u0 = chunk_u0 - carry;                 // stream offset of buffer position 0
+    chunk_u0 += total - carry;
+    const uint32_t stop_at = (!open_end && u_end - buf_u0 < (uint64_t)total) ? (uint32_t)(u_end - buf_u0) : 0xffffffffu;
     uint32_t start = 0;
     if (skip) {
       if (skip >= total) { skip -= total; carry = 0; TRY(c, sync_check(c)); continue; }
@@ -491,16 +511,32 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     // the walk kernels treat segment `seg0` as the chain origin: shift the arrays so that it is index 0
     uint32_t nsg = nseg - seg0;
     uint32_t *seedv = seed + seg0;
-    if (nsg > 1) {
-      // seeds for segments seg0+1 .. nseg-1 (kernel indexes segments from the start of the buffer)
-      BK_LAUNCH(bam_seed, GRID1(nseg, 8), 256, 0, st, u, total, c->nt, nseg, seed);
+    if (seek) {
+      // mid-stream range: every segment is seeded, the first seed is the chain origin (verified by the caller against
+      // the landing point of the previous range)
+      BK_LAUNCH(bam_seed, GRID1(nseg + 1, 8), 256, 0, st, u, total, c->nt, nseg, seed, 0u);
+      std::vector<uint32_t> hseed(nseg);
+      CU(c, cudaMemcpyAsync(hseed.data(), seed, (size_t)nseg * 4, cudaMemcpyDeviceToHost, st));
+      TRY(c, sync_check(c));
+      uint32_t s0 = 0;
+      while (s0 < nseg && hseed[s0] == NONE) ++s0;
+      if (s0 == nseg) return fail(c, BKID_ERR_IO, "no BAM record start found at the beginning of the block range");
+      seg0 = s0; nsg = nseg - seg0; seedv = seed + seg0; start = hseed[s0];
+      if (first_uoff) *first_uoff = buf_u0 + start;
+      seek = false;
+    } else {
+      if (nsg > 1) {
+        // seeds for segments seg0+1 .. nseg-1 (kernel indexes segments from the start of the buffer)
+        BK_LAUNCH(bam_seed, GRID1(nseg, 8), 256, 0, st, u, total, c->nt, nseg, seed, 1u);
+      }
+      CU(c, cudaMemcpyAsync(seedv, &start, 4, cudaMemcpyHostToDevice, st));   // pageable 4-byte copy: staged by the driver before return
+      if (seg0) CU(c, cudaMemsetAsync(seed, 0xff, (size_t)seg0 * 4, st));
     }
-    CU(c, cudaMemcpyAsync(seedv, &start, 4, cudaMemcpyHostToDevice, st));   // pageable 4-byte copy: staged by the driver before return
-    if (seg0) CU(c, cudaMemsetAsync(seed, 0xff, (size_t)seg0 * 4, st));
+    const uint32_t stop_rel = stop_at;                        // buffer coordinates (seedv / walkers use absolute buffer offsets)
     int hstate[8];
     for (int iter = 0;; ++iter) {
-      BK_LAUNCH((bam_walk<false>), GRID1(nsg, 128), 128, 0, st, u, total, nsg, seedv, d->cnt.as<uint32_t>(), d->land.as<uint32_t>(), d->base.as<uint32_t>(), (const uint32_t *)nullptr, (uint32_t *)nullptr, state + 5);
-      BK_LAUNCH(bam_stitch, 1, 32, 0, st, nsg, seedv, d->land.as<uint32_t>(), d->base.as<uint32_t>(), state);
+      BK_LAUNCH((bam_walk<false>), GRID1(nsg, 128), 128, 0, st, u, total, nsg, seedv, d->cnt.as<uint32_t>(), d->land.as<uint32_t>(), d->base.as<uint32_t>(), (const uint32_t *)nullptr, (uint32_t *)nullptr, state + 5, stop_rel);
+      BK_LAUNCH(bam_stitch, 1, 32, 0, st, nsg, seedv, d->land.as<uint32_t>(), d->base.as<uint32_t>(), state, stop_rel);
       CU(c, cudaMemcpyAsync(hstate, state, 32, cudaMemcpyDeviceToHost, st));
       TRY(c, sync_check(c));
       if (hstate[4]) return fail(c, BKID_ERR_IO, "inflate failed: BGZF block " + std::to_string((long long)b0 + (hstate[4] >> 4)) + " (deflate error " + std::to_string(hstate[4] & 15) + ")");
@@ -528,7 +564,7 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
       for (auto &m : d->meta) TRY(c, m.ensure((size_t)nrec * 4 + 64, 0, st));
       for (auto &m : d->metao) TRY(c, m.ensure((size_t)nrec * 4 + 64, 0, st));
       TRY(c, c->sc.ensure((long long)nrec + 8, st));
-      BK_LAUNCH((bam_walk<true>), GRID1(nsg, 128), 128, 0, st, u, total, nsg, seedv, d->cnt.as<uint32_t>(), d->land.as<uint32_t>(), (uint32_t *)nullptr, d->base.as<uint32_t>(), d->rec_off.as<uint32_t>(), state + 5);
+      BK_LAUNCH((bam_walk<true>), GRID1(nsg, 128), 128, 0, st, u, total, nsg, seedv, d->cnt.as<uint32_t>(), d->land.as<uint32_t>(), (uint32_t *)nullptr, d->base.as<uint32_t>(), d->rec_off.as<uint32_t>(), state + 5, stop_rel);
       Cols C{c->flag.as<uint16_t>(), c->mapq.as<uint8_t>(), c->tid.as<int32_t>(), c->pos.as<int32_t>(), c->isize.as<int32_t>(), c->endpos.as<int32_t>()};
       uint32_t *m[8]; for (int i = 0; i < 8; ++i) m[i] = d->meta[i].as<uint32_t>();        // [5],[6] = tag pointers, [7] = seq bytes
       uint32_t *mo[6]; for (int i = 0; i < 6; ++i) mo[i] = d->metao[i].as<uint32_t>();
@@ -555,6 +591,13 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
       c->n += nrec; c->n_x += (long long)ht5[0]; c->n_sa += (long long)ht5[1]; c->n_cig += (long long)ht5[2]; c->sa_bytes += (long long)ht5[3]; c->oc_bytes += (long long)ht5[4];
       c->seq_bytes += (long long)ht5[5];
     }
+    if (carry_start >= stop_at) {                             // the walk reached the end of the block range: done
+      if (land_uoff) *land_uoff = buf_u0 + carry_start;
+      range_done = true; carry = 0;
+      cudaEventRecord(d->ev_t[4], st);
+      TRY(c, sync_check(c));
+      continue;
+    }
     // ---- carry the partial record at the end of the chunk ----
     carry = total - carry_start;
     if (carry > CARRY_CAP) return fail(c, BKID_ERR_IO, "BAM record larger than 64 MiB");
@@ -570,7 +613,9 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
     cudaEventElapsedTime(&ms, d->ev_t[2], d->ev_t[3]); ms_bound += ms;
     cudaEventElapsedTime(&ms, d->ev_t[3], d->ev_t[4]); ms_ext += ms;
   }
+  if (!open_end && !range_done) return fail(c, BKID_ERR_IO, "the record straddling the end of the block range does not complete within the overlap");
   if (carry) return fail(c, BKID_ERR_IO, "truncated BAM record at the end of the file");
+  if (open_end && land_uoff) *land_uoff = chunk_u0;
   if (skip) return fail(c, BKID_ERR_IO, "first_record_uoffset beyond the end of the uncompressed stream");
   cudaEventRecord(d->ev_t[5], st);
   TRY(c, sync_check(c));
@@ -583,6 +628,17 @@ int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *bloc
   c->have_seq = true;                    // the decoder always extracts the read bases of the SA records
   if (n_records) *n_records = c->n - n_first;
   return 0;
+}
+
+int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t *n_records)
+{
+  return push_bgzf_impl(c, file, blocks, n_blocks, first_record_uoffset, 0, n_blocks, n_records, nullptr, nullptr);
+}
+
+int bkid_push_bgzf_range(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t first_block, int64_t end_block,
+                         int64_t *n_records, uint64_t *first_record_uoff, uint64_t *next_record_uoff)
+{
+  return push_bgzf_impl(c, file, blocks, n_blocks, first_record_uoffset, first_block, end_block, n_records, first_record_uoff, next_record_uoff);
 }
 
 int bkid_get_decode_stats(bkid_ctx *c, bkid_decode_stats *s)

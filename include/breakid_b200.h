@@ -210,6 +210,15 @@ typedef struct {
 } bkid_decode_stats;
 int bkid_push_bgzf(bkid_ctx *ctx, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks,
                    uint64_t first_record_uoffset, int64_t *n_records);
+/* Same for one rank of a multi-GPU job: decode only the records that START inside the uncompressed extent of BGZF blocks
+ * [first_block, end_block) (genomic-bin sharding of the file itself).  A range that begins mid-stream finds
+ * its first record by seeding and reports its stream offset in *first_record_uoff; *next_record_uoff is the offset of
+ * the first record of the following range (the walk reads up to 64 blocks past end_block to complete the straddling
+ * record).  The caller verifies next_record_uoff[r] == first_record_uoff[r+1] across ranks: with that check the union
+ * of the ranges is exactly the record sequence of the whole file. */
+int bkid_push_bgzf_range(bkid_ctx *ctx, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks,
+                         uint64_t first_record_uoffset, int64_t first_block, int64_t end_block, int64_t *n_records,
+                         uint64_t *first_record_uoff, uint64_t *next_record_uoff);
 int bkid_get_decode_stats(bkid_ctx *ctx, bkid_decode_stats *stats);
 /* parity-test getter: one input column of the context by name ("flag", "pos", "x_name_hash", "sa_txt", ...) */
 int bkid_fetch_column(bkid_ctx *ctx, const char *name, void *out, int64_t cap_bytes, int64_t *n_bytes);

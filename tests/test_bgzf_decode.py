@@ -267,3 +267,42 @@ def test_device_decode_edge_files(tmp_path):
     cc, hb, st = _assert_same_as_host_decoder(p, None)
     assert hb.n == 300 and st["n_blocks"] == 301
     cc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nparts,chunk_kb", [(2, None), (5, None), (3, 256), (16, None)])
+def test_block_range_decode_union_equals_whole_file(tmp_path, nparts, chunk_kb):
+    """multi-GPU ingest: every rank decodes a block range of the file; the ranges stitch exactly (where one range lands
+    is where the next one starts) and their union is the whole-file decode, column by column"""
+    p, payload, first = _write_hostile(tmp_path, n=9000)
+    f = api.BgzfFile(p)
+    whole = api.Context(f.target_len, f.target_names, device=0)
+    n_all = whole.push_bgzf(f)
+    cuts = [f.n_blocks * i // nparts for i in range(nparts + 1)]
+    if chunk_kb:
+        os.environ["BKID_BGZF_CHUNK_KB"] = str(chunk_kb)
+    try:
+        parts, marks = [], []
+        for r in range(nparts):
+            c = api.Context(f.target_len, f.target_names, device=0)
+            n, a, b = c.push_bgzf_range(f, cuts[r], cuts[r + 1])
+            parts.append((c, n)); marks.append((a, b))
+    finally:
+        os.environ.pop("BKID_BGZF_CHUNK_KB", None)
+    assert marks[0][0] == first and marks[-1][1] == f.usize
+    for r in range(nparts - 1):
+        assert marks[r][1] == marks[r + 1][0], (r, marks)             # the cross-rank stitch check
+    assert sum(n for _, n in parts) == n_all
+    base = 0
+    for k, dt in (("flag", np.uint16), ("mapq", np.uint8), ("tid", np.int32), ("pos", np.int32), ("isize", np.int32), ("endpos", np.int32)):
+        assert np.array_equal(np.concatenate([c.fetch_column(k, dt) for c, _ in parts]), whole.fetch_column(k, dt)), k
+    # sparse / SA tables: record indices are range-local, everything else concatenates
+    off = np.cumsum([0] + [n for _, n in parts])
+    assert np.array_equal(np.concatenate([c.fetch_column("x_rec", np.uint32).astype(np.int64) + off[i] for i, (c, _) in enumerate(parts)]),
+                          whole.fetch_column("x_rec", np.uint32).astype(np.int64))
+    for k, dt in (("x_mtid", np.int32), ("x_mpos", np.int32), ("x_name_hash", np.uint64), ("cig_ops", np.uint32), ("sa_txt", np.uint8), ("oc_txt", np.uint8), ("seq4", np.uint8), ("seq_len", np.int32)):
+        assert np.array_equal(np.concatenate([c.fetch_column(k, dt) for c, _ in parts]), whole.fetch_column(k, dt)), k
+    for c, _ in parts:
+        c.close()
+    whole.close()
+    f.close()
