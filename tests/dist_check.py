@@ -59,6 +59,33 @@ def main():
         print("exclude world %d: %d calls, identical to oracle on the pre-filtered input: %s" % (world, len(out), same), flush=True)
         ok = ok and same
     ctx.close()
+    # ingest sharded too: every rank inflates and decodes its own BGZF block range of one BAM file on its GPU
+    import tempfile
+    from breakid_b200 import bamio
+    tmpd = [tempfile.mkdtemp(prefix="bkid_dist_") if rank == 0 else None]
+    dist.broadcast_object_list(tmpd, src=0)
+    bam = os.path.join(tmpd[0], "reads.bam")
+    if rank == 0:
+        bamio.write_bam(bam, d)
+    dist.barrier()
+    f = api.BgzfFile(bam)
+    cuts = [f.n_blocks * i // world for i in range(world + 1)]
+    ctx = api.Context(f.target_len, f.target_names, device=local)
+    n_loc, a, b = ctx.push_bgzf_range(f, cuts[rank], cuts[rank + 1])
+    marks = torch.tensor([a, b, n_loc], dtype=torch.int64, device=dev)
+    allm = [torch.zeros_like(marks) for _ in range(world)]
+    dist.all_gather(allm, marks)
+    stitched = all(int(allm[i][1]) == int(allm[i + 1][0]) for i in range(world - 1)) and sum(int(m[2]) for m in allm) == hb.n
+    for t, (p, l) in enumerate(nibs):
+        ctx.set_nib(t, p, l)
+    mean, sd, dd, out = run_sharded(GpuEngine(ctx, dev), n_loc, mode=0)
+    if rank == 0:
+        m, s, d0, exp = O.run(hb, nibs, mode=0)
+        same = stitched and (mean, sd, dd) == (m, s, d0) and out.tobytes() == exp.tobytes()
+        print("sharded decode world %d: ranges stitch: %s, %d calls, identical to oracle: %s" % (world, stitched, len(out), same), flush=True)
+        ok = ok and same
+    ctx.close()
+    f.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
