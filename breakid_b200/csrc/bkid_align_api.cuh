@@ -12,8 +12,10 @@ int bkid_op_banded_align(bkid_ctx *c, int64_t n, const uint8_t *q, const uint32_
   DBuf dq, dqo, dr, dro, dout;
   int rc = 0;
   if ((rc = dq.ensure(qb + 16, 0, st)) || (rc = dr.ensure(rb + 16, 0, st)) || (rc = dqo.ensure((size_t)(n + 1) * 4, 0, st)) || (rc = dro.ensure((size_t)(n + 1) * 4, 0, st)) ||
-      (rc = dout.ensure((size_t)n * 4, 0, st)))
+      (rc = dout.ensure((size_t)n * 4, 0, st))) {
+    for (DBuf *b : {&dq, &dqo, &dr, &dro, &dout}) b->release();
     return fail(c, rc, g_last_cuda_err);
+  }
   if (qb) cudaMemcpyAsync(dq.p, q, qb, cudaMemcpyHostToDevice, st);
   if (rb) cudaMemcpyAsync(dr.p, r, rb, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(dqo.p, q_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st);

@@ -322,7 +322,11 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   CU(c, cudaMemcpyAsync(seg_h.data(), seg, (size_t)(nseg + 1) * 4, cudaMemcpyDeviceToHost, st));
   CU(c, cudaMemcpyAsync(pool, tot, 16, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
   bool have_large = false;                               // any bucket beyond the shared-memory replay classes?
-  for (int b = 0; b < nseg; ++b) have_large |= seg_h[b + 1] - seg_h[b] >= 4096u;
+  // unflagged buckets from RG_LO points up take the sort-based rank form in global memory.  On the 30x single-GPU workload
+  // this is time-neutral against the O(M^2) counting kernel in shared memory; with deeper coverage (100x, or N ranks' slices
+  // of one genome meeting on a bucket owner) the counting kernel grows quadratically and was the longest kernel of the step.
+  const uint32_t RG_LO = 512u;
+  for (int b = 0; b < nseg; ++b) have_large |= seg_h[b + 1] - seg_h[b] >= RG_LO;
   if ((pool[0] * 4 + pool[1] * 12) > (100ull << 30)) return fail(c, BKID_ERR_NOMEM, "AHC component too large for the row pools");
   BK_LAUNCH(ahc_bucket_comp_off, GRID1(nseg + 1, 128), 128, 0, st, comp_bucket, ncomp, (uint32_t)nseg, bucket_comp_off);
   // node arrays + pools + events
@@ -365,14 +369,13 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
     for (uint32_t i = 0; i < ncomp; ++i) { uint32_t cs = hoff[i + 1] - hoff[i]; nf += hf[i] != 0; if (hf[i]) fl_pts += cs; maxc = std::max<long>(maxc, cs); merges += hnn[i] - cs; }
     fprintf(stderr, "[bkid-timing] ncomp %u flagged %ld (points %ld) max comp %ld merges %ld points %lld buckets %d\n", ncomp, nf, fl_pts, maxc, merges, n, nseg);
   }
-  BK_LAUNCH(ahc_replay_rank, (unsigned)nseg, RK_THREADS, 49 * 900, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, 900u);
-  BK_LAUNCH(ahc_replay_rank, (unsigned)nseg, RK_THREADS, 49 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 900u, 4096u);
+  BK_LAUNCH(ahc_replay_rank, (unsigned)nseg, RK_THREADS, 49 * 512, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, RG_LO);
   T_.mark("ahc: replay rank form");
   BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 900, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 0u, 900u);
   BK_LAUNCH(ahc_replay_smem, (unsigned)nseg, 32, 49 * 4096, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 900u, 4096u);
   T_.mark("ahc: replay smem (flagged)");
   if (have_large) {
-    // buckets >= 4096 points without flagged components: rank form in global memory
+    // buckets >= RG_LO points without flagged components: rank form in global memory
     DBuf &RG = c->tmpF;
     size_t nn = (size_t)n + 8;
     TRY(c, RG.ensure(nn * (8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + (size_t)(nseg + 2) * 4 + 256, 0, st));
@@ -391,21 +394,21 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
     CU(c, cudaMemsetAsync(bucket_events, 0, (size_t)(nseg + 2) * 4, st));
     CU(c, cudaMemsetAsync(g.is_head, 0, nn * 4, st));
     BK_LAUNCH(ahc_rg_bucket_events, GRID1(ncomp, 128), 128, 0, st, v, ncomp, bucket_events);
-    BK_LAUNCH(ahc_rg_prepare, GRID1(ncomp, 128), 128, 0, st, v, g, ncomp, bucket_flag, 4096u);
+    BK_LAUNCH(ahc_rg_prepare, GRID1(ncomp, 128), 128, 0, st, v, g, ncomp, bucket_flag, RG_LO);
     {
       uint64_t *rk = c->sc.keys.as<uint64_t>();
       uint32_t *rv = c->sc.vals.as<uint32_t>();
-      BK_LAUNCH(ahc_rg_sortkeys, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u, rk, rv);
+      BK_LAUNCH(ahc_rg_sortkeys, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO, rk, rv);
       bk::radix_sort_pairs(rk, rv, n, 0, 64, c->sc.rt(), st);
       BK_LAUNCH(ahc_rg_bucketkeys, GRID1(n, 256), 256, 0, st, curb, rv, n, rk);
       bk::radix_sort_pairs(rk, rv, n, 0, bbits, c->sc.rt(), st);
-      BK_LAUNCH(ahc_rg_rank_sorted, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u, rv);
+      BK_LAUNCH(ahc_rg_rank_sorted, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO, rv);
     }
-    BK_LAUNCH(ahc_rg_heads, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u, bucket_events);
+    BK_LAUNCH(ahc_rg_heads, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO, bucket_events);
     bk::exclusive_scan<uint32_t, uint32_t>(g.is_head, head_excl, n, stmp, tot, st);
     BK_LAUNCH(ahc_rg_head_list, GRID1(n, 256), 256, 0, st, g.is_head, head_excl, n, head_pos);
-    BK_LAUNCH(ahc_rg_ties, GRID1(nseg, 64), 64, 0, st, v, g, (uint32_t)nseg, bucket_flag, 4096u, bucket_events, head_pos, head_excl, n);
-    BK_LAUNCH(ahc_rg_write, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, 4096u);
+    BK_LAUNCH(ahc_rg_ties, GRID1(nseg, 64), 64, 0, st, v, g, (uint32_t)nseg, bucket_flag, RG_LO, bucket_events, head_pos, head_excl, n);
+    BK_LAUNCH(ahc_rg_write, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO);
   }
   T_.mark("ahc: replay rank form (global)");
   BK_LAUNCH(ahc_bucket_exact, (unsigned)nseg, 32, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
