@@ -294,8 +294,8 @@ int bkid_op_cluster(bkid_ctx *ctx, int mode, int64_t n, const uint32_t *p1, cons
  * unit-cost edit distance of n query strings (e.g. the soft-clipped part of a split read) against their own reference
  * windows, ASCII bases, 'N' never matches.  q / r are the concatenated strings, q_off / r_off their [n+1] offsets,
  * w (<= 15) the band half-width |j - i| <= w.  out[i] = distance, -1 when the length difference exceeds w, -2 when a
- * string is longer than 512.  One warp per pair, anti-diagonal wavefront with warp shuffles.  Wiring it into
- * bkid_refine as a default-off evidence validator needs the read bases in the batch (not part of this ABI yet). */
+ * string is longer than 512.  One warp per pair, anti-diagonal wavefront with warp shuffles.  bkid_refine uses the same
+ * kernel as a default-off evidence validator (bkid_params.validate_align + the seq_* table of the batch). */
 int bkid_op_banded_align(bkid_ctx *ctx, int64_t n, const uint8_t *q, const uint32_t *q_off, const uint8_t *r, const uint32_t *r_off,
                          int32_t w, int32_t *out);
 
