@@ -255,6 +255,8 @@ def host_lib():
         L.bkid_host_bam_batch.restype = C.c_void_p
         L.bkid_host_bam_batch.argtypes = [C.c_void_p]
         L.bkid_host_bam_free.argtypes = [C.c_void_p]
+        L.bkid_host_bam_batch_narrow.restype = C.c_void_p
+        L.bkid_host_bam_batch_narrow.argtypes = [C.c_void_p]
         L.bkid_host_bgzf_open.restype = C.c_void_p
         L.bkid_host_bgzf_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         for f, rt in (("header", C.c_void_p), ("data", C.c_void_p), ("size", C.c_uint64), ("blocks", C.c_void_p), ("n_blocks", C.c_int64),

@@ -118,3 +118,32 @@ def test_indexed_refgene_lookup_equals_linear_scan(tmp_path):
         assert a.value == b.value, (chrom, pos, a.value, b.value)
         kinds.add(a.value.split(b"\t")[0][:4])
     assert b"inte" in kinds and b"GENE" in kinds and b"NEST" in kinds
+
+
+def test_host_decoder_narrow_batch_matches_python_narrowing(tmp_path):
+    """bkid_host_bam_batch_narrow (C++) picks the same narrow encodings, with the same values, as HostBatch.narrow()"""
+    import ctypes as C
+    from breakid_b200 import api, bamio, synth
+    cfg = synth.SynthConfig(chrom_lens=[80000, 50000], n_tra=1, n_inv=1, n_dup=0, n_del=1, seed=3)
+    d = synth.generate(cfg)
+    p = str(tmp_path / "t.bam")
+    bamio.write_bam(p, d)
+    hb = api.HostBatch.from_bam(p, threads=2)
+    lib = api.host_lib()
+    err = C.create_string_buffer(256)
+    h = lib.bkid_host_read_bam(p.encode(), 2, err, 256)
+    assert h
+    try:
+        b = C.cast(lib.bkid_host_bam_batch_narrow(h), C.POINTER(api.Batch)).contents
+        nr = hb.narrow()
+        assert set(nr) == {"span16", "isize16", "tid_run_start", "tid_run_tid"}
+        assert not b.tid and not b.isize and not b.endpos and b.flag and b.pos          # wide columns replaced, others kept
+        get = lambda ptr, n, dt: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (n * np.dtype(dt).itemsize,)).view(dt).copy()
+        assert np.array_equal(get(b.span16, hb.n, np.uint16), nr["span16"])
+        assert np.array_equal(get(b.isize16, hb.n, np.int16), nr["isize16"])
+        assert int(b.n_tid_runs) == nr["tid_run_start"].shape[0]
+        assert np.array_equal(get(b.tid_run_start, int(b.n_tid_runs), np.uint32), nr["tid_run_start"])
+        assert np.array_equal(get(b.tid_run_tid, int(b.n_tid_runs), np.int32), nr["tid_run_tid"])
+        assert b.seq_off and np.array_equal(get(b.seq_len, hb.n_sa, np.int32), hb.seq["seq_len"])
+    finally:
+        lib.bkid_host_bam_free(h)
