@@ -31,7 +31,7 @@ constexpr uint32_t NONE = 0xffffffffu;
 constexpr int INF_WARPS = 4;          // warps per CTA
 constexpr int INF_GS = 8;             // lanes per group: four groups per warp, one BGZF block each
 constexpr int INF_NG = 32 / INF_GS;
-constexpr int INF_TOKENS = 8;         // tokens per group and lock-step round
+constexpr int INF_TOKENS = 32;        // tokens per group and lock-step round
 
 struct Task { uint64_t src; uint32_t dst; uint32_t clen, ulen; };
 
