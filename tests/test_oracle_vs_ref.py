@@ -158,3 +158,45 @@ def test_whole_path_vs_reference_binary(dataset, mode, tmp_path):
     assert _format_calls(cl, hb.target_names) == exp and len(exp) >= 5
     w_line = [l for l in open(str(tmp_path / "ref") + "_params.txt").read().splitlines() if l.startswith("w\t")][0]
     assert w_line == "w\t%g" % dist
+
+
+def _binary_vs_oracle(cfg, tmp_path, mode=0, qual=None, genes_per_mb=4.0, min_calls=1):
+    """the unmodified reference binary and the oracle on one synthetic dataset: same call records"""
+    from breakid_b200 import api, bamio, synth
+    from test_golden import _format_calls
+    d = synth.generate(cfg)
+    paths = bamio.write_dataset(str(tmp_path), d, random_qual=False, genes_per_mb=genes_per_mb)
+    O.ref_index(paths["bam"])
+    O.ref_install_refgene(paths["refgene"])
+    r = O.ref_run_binary(paths["bam"], str(tmp_path / "ref"), paths["nib"], fast=bool(mode), qual=qual)
+    assert r.returncode == 0, r.stderr[-300:]
+    hb = api.HostBatch.from_synth(d)
+    nibs = [(synth.random_nib_bytes(l, cfg.seed * 1000 + t).numpy(), l) for t, l in enumerate(cfg.chrom_lens)]
+    _, _, dist, cl = O.run(hb, nibs, mode=mode, **({"qual": qual} if qual is not None else {}))
+    exp = set()
+    for ln in open(str(tmp_path / "ref") + "_fusion_all.txt").read().splitlines()[1:]:
+        f = ln.split("\t")
+        exp.add((f[0], f[1], f[2], f[7], f[8], f[9], f[10], f[11], f[12], f[13], f[14]))
+    assert _format_calls(cl, hb.target_names) == exp, (len(exp), len(cl))
+    assert len(exp) >= min_calls
+    return cl
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_hotspots_config5_shape_vs_reference_binary(tmp_path):
+    """BASELINE.json configs[4] shape: hundreds of split reads per breakpoint, clips U(20,130), +-3 bp jitter -- pins the
+    oracle's pairing / vote restatement (find_bp_pair, src/BreakID.cc:577-857) where it is quadratic in the reference"""
+    from breakid_b200 import synth
+    cfg = synth.config5(scale=0.004, split_per_sv=300)
+    cl = _binary_vs_oracle(cfg, tmp_path, min_calls=4)
+    assert int(cl["n_split_read"].max()) > 150
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("mode,qual", [(0, None), (1, 35)])
+def test_tumour_config4_shape_vs_reference_binary(tmp_path, mode, qual):
+    """BASELINE.json configs[3] shape: 100x coverage, translocations only, dense refGene; default and -fast -q 35"""
+    from breakid_b200 import synth
+    cfg = synth.SynthConfig(chrom_lens=[260000, 220000, 180000, 140000], coverage=100.0, n_tra=10, n_inv=0, n_dup=0, n_del=0,
+                            span_per_sv=40, split_per_sv=20, seed=44, sv_jitter=1)
+    _binary_vs_oracle(cfg, tmp_path, mode=mode, qual=qual, genes_per_mb=30.0, min_calls=8)
