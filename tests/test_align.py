@@ -145,3 +145,39 @@ def test_validate_align_drops_split_reads_whose_clip_does_not_align(small_data):
     with pytest.raises(api.BkidError, match="read bases"):
         c.run()
     c.close()
+
+
+@pytest.mark.gpu
+def test_driver_validate_flag(tmp_path):
+    """BreakID -validate (device decode extracts the read bases): with true bases the call file is the reference binary's;
+    with a third of the split reads carrying random clips the supporting split-read counts drop"""
+    import os
+    import subprocess
+    import oracle_py as O
+    from breakid_b200 import api, bamio, synth
+    cfg = synth.SynthConfig(chrom_lens=[300000, 200000, 150000], n_tra=3, n_inv=2, n_dup=2, n_del=2, seed=21, sv_jitter=1)
+    d = synth.generate(cfg)
+    hb = api.HostBatch.from_synth(d)
+    genome = [synth.nib_ascii(synth.random_nib_bytes(l, cfg.seed * 1000 + t), l) for t, l in enumerate(cfg.chrom_lens)]
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breakid_b200", "host", "BreakID")
+    outs = {}
+    for tag, corrupt in (("true", set()), ("bad", set(range(0, hb.n_sa, 3)))):
+        seq, _ = synth.split_read_sequences(hb, genome, corrupt=corrupt, seed=2)
+        wd = tmp_path / tag
+        wd.mkdir()
+        paths = bamio.write_dataset(str(wd), d, genes_per_mb=25.0)
+        bamio.write_bam(paths["bam"], d, sa_seq=seq)
+        open(paths["bam"] + ".bai", "wb").close()                     # the driver only checks that an index file exists
+        for flags in ([], ["-validate"]):
+            g = subprocess.run([drv, "-i", paths["bam"], "-o", str(wd / ("out" + "".join(flags))), "-n", paths["nib"], "-r", paths["refgene"], "-all"] + flags,
+                               capture_output=True, text=True)
+            assert g.returncode == 0, g.stderr[-500:]
+            outs[(tag, bool(flags))] = open(str(wd / ("out" + "".join(flags))) + "_fusion_all.txt").read()
+    nsr = lambda txt: sum(int(l.split("\t")[8]) for l in txt.splitlines()[1:])
+    assert outs[("true", True)] == outs[("true", False)] == outs[("bad", False)]      # the flag is neutral on true bases; off = bases ignored
+    assert nsr(outs[("bad", True)]) < nsr(outs[("true", True)])
+    if O.have_ref():
+        O.ref_index(str(tmp_path / "true" / "reads.bam"))
+        O.ref_install_refgene(str(tmp_path / "true" / "ref_files" / "refGene.txt"))
+        r = O.ref_run_binary(str(tmp_path / "true" / "reads.bam"), str(tmp_path / "ref"), str(tmp_path / "true" / "nib"))
+        assert r.returncode == 0 and open(str(tmp_path / "ref") + "_fusion_all.txt").read() == outs[("true", True)]
