@@ -306,3 +306,39 @@ def test_block_range_decode_union_equals_whole_file(tmp_path, nparts, chunk_kb):
         c.close()
     whole.close()
     f.close()
+
+
+@pytest.mark.gpu
+def test_false_seed_is_repaired_by_the_stitch(tmp_path):
+    """a 600 KB aux array that spans segment boundaries and carries, right behind each boundary, three consecutive
+    perfectly plausible fake records: the seed search must take the bait (they are the first plausible chain of the
+    segment) and the stitch must throw it out again because the true chain does not land there"""
+    rng = np.random.RandomState(12)
+    targets = [("chr1", 500000), ("chr2", 400000)]
+    recs = _hostile_records(rng, 800)
+    payload0, first = _raw_bam(recs[:400], targets)
+    big_off = len(payload0)                                   # stream offset where the big record starts
+    name = "bigrec"
+    head_len = 4 + 32 + len(name) + 1 + 4 + 0 + 0             # block_size + core + name + one cigar op, l_seq = 0
+    aux_hdr = b"XBBc" + struct.pack("<i", 600000)
+    arr0 = big_off + head_len + len(aux_hdr)                  # stream offset of the first array byte
+    arr = bytearray(600000)
+    fake = b"".join(struct.pack("<i", len(r)) + r for r in
+                    [_record(0, 1000 + 7 * k, "fake%d" % k, 99, 60, [(100, 0)], 100, 0, 1200, 300, b"NMC\x01") for k in range(3)])
+    SEG = 256 << 10
+    planted = 0
+    for b in range((arr0 // SEG + 1) * SEG, arr0 + len(arr) - len(fake) - 16, SEG):
+        o = b - arr0 + 3                                      # 3 bytes behind the segment boundary
+        arr[o:o + len(fake)] = fake
+        planted += 1
+    assert planted >= 2
+    big = _record(0, 60000, name, 99, 60, [(50, 0)], 0, 0, 61000, 300, aux_hdr + bytes(arr))
+    payload, _ = _raw_bam(recs[:400] + [big] + recs[400:], targets)
+    # recs[400:] restart at low positions on chr1/chr2: coordinate order does not matter to the decoder
+    p = str(tmp_path / "bait.bam")
+    _bgzf_write(p, payload, vary=True)
+    c, hb, st = _assert_same_as_host_decoder(p, None)
+    assert hb.n == 802 and st["seed_repairs"] >= planted
+    c.close()
+    c, hb, st = _assert_same_as_host_decoder(p, 512)          # several chunks: the bait also sits in carried data
+    c.close()
