@@ -3,6 +3,19 @@
 
 #define GRID1(n, t) (unsigned)div_up((long long)(n), (t))
 
+// slots (in 32-bit words) of the context's small device counter block `counters` (1 KB); 64-bit values are 8-byte aligned
+enum CounterSlot {
+  CS_SD_OUT = 8,        // sd_resolve: [0] total (i64), [1] out-of-regime flag (i64)
+  CS_SORT = 16,         // std::sort replay: active / terminal / small work-list sizes
+  CS_TOTAL = 32,        // grand totals of the exclusive scans (u64 x 2)
+  CS_HASH_ERR = 40,     // mate join: a 64-bit name-hash run with differing high words
+  CS_MAXSPAN = 44,      // max_span_kernel result
+  CS_FATAL = 46,        // the reference's fatal "error cigar" condition was met
+  CS_ROOTS = 48,        // AHC: number of final roots
+  CS_MISSING = 50,      // a candidate / SA record is missing from the sparse mate/name table
+  CS_DECODE = 52        // device decode: totals of the six per-chunk scans (u64 x 6)
+};
+
 struct Scratch {          // reusable device scratch for sorts / scans over `cap` elements
   DBuf keys, keys_alt, vals, vals_alt, hist, scan_tmp, a32, b32, c32, d32, e32;
   int ensure(long long n, cudaStream_t st)
@@ -135,7 +148,7 @@ static int exact_sort_segments(bkid_ctx *c, uint32_t *key, uint32_t *val, const 
   TRY(c, c->tmpD.ensure((size_t)n * 4 + 16, 0, st));
   TRY(c, c->tmpE.ensure((size_t)n * 4 + 16, 0, st));
   TRY(c, c->counters.ensure(256, 0, st));
-  unsigned *cnt = c->counters.as<unsigned>() + 16;     // [0]=act A, [1]=act B, [2]=terminal, [3]=small
+  unsigned *cnt = c->counters.as<unsigned>() + CS_SORT;     // [0]=act A, [1]=act B, [2]=terminal, [3]=small
   CU(c, cudaMemsetAsync(cnt, 0, 16, st));
   Seg *act[2] = {c->tmpA.as<Seg>(), c->tmpB.as<Seg>()};
   Seg *term = c->tmpC.as<Seg>();
@@ -181,7 +194,7 @@ static int mask_pass(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, con
   if (n == 0) { CU(c, cudaMemsetAsync(seg_out, 0, (size_t)(nseg + 1) * 4, st)); *n_out = 0; return 0; }
   TRY(c, c->sc.ensure(n, st));
   uint32_t *cnt = c->sc.a32.as<uint32_t>(), *off = c->sc.b32.as<uint32_t>();
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   BK_LAUNCH(k4_mask_count, GRID1(n, 256), 256, 0, st, cur, curb, seg, n, X, Y, distance, cnt);
   bk::exclusive_scan<uint32_t, uint32_t>(cnt, off, n, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
   unsigned long long h = 0;
@@ -199,7 +212,7 @@ static int compact_pass(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, 
 {
   cudaStream_t st = c->st;
   if (n == 0) { CU(c, cudaMemsetAsync(seg_out, 0, (size_t)(nseg + 1) * 4, st)); *n_out = 0; return 0; }
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   bk::exclusive_scan<uint32_t, uint32_t>(keep, off_keep, n, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
   unsigned long long h = 0;
   CU(c, cudaMemcpyAsync(&h, tot, 8, cudaMemcpyDeviceToHost, st));
@@ -261,7 +274,7 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   uint32_t *val = c->sc.vals.as<uint32_t>();
   uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>();
   unsigned long long *stmp = c->sc.scan_tmp.as<unsigned long long>();
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   int bbits = 1; while ((1ll << bbits) < nseg + 1) ++bbits;
   // pieces: sort by (bucket, x), cut at x gaps
   BK_LAUNCH(ahc_key_bx, GRID1(n, 256), 256, 0, st, curb, LX.as<uint32_t>(), n, key, val);
@@ -414,7 +427,7 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
   BK_LAUNCH(ahc_bucket_exact, (unsigned)nseg, 32, 0, st, v, bucket_comp_off, (uint32_t)nseg, bucket_flag, 4096u);
   T_.mark("ahc: replay+exact");
   // final roots -> clusters
-  unsigned *cnt = c->counters.as<unsigned>() + 48;
+  unsigned *cnt = c->counters.as<unsigned>() + CS_ROOTS;
   CU(c, cudaMemsetAsync(cnt, 0, 4, st));
   uint64_t *rkey = c->sc.keys.as<uint64_t>();
   uint32_t *rnode = c->sc.vals.as<uint32_t>();
@@ -489,9 +502,9 @@ static int cluster_fast(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, 
   // drop ids seen fewer than min_reads times, group the rest by (bucket, cluster)
   uint32_t *curC = curA, *curbC = curbA;     // reuse
   // compact the cluster ids alongside: write cl through the same offsets
-  bk::exclusive_scan<uint32_t, uint32_t>(keep, off, nb2, c->sc.scan_tmp.as<unsigned long long>(), (unsigned long long *)(c->counters.as<unsigned>() + 32), st);
+  bk::exclusive_scan<uint32_t, uint32_t>(keep, off, nb2, c->sc.scan_tmp.as<unsigned long long>(), (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL), st);
   unsigned long long h = 0;
-  CU(c, cudaMemcpyAsync(&h, c->counters.as<unsigned>() + 32, 8, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+  CU(c, cudaMemcpyAsync(&h, c->counters.as<unsigned>() + CS_TOTAL, 8, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
   nc = (long long)h;
   if (nc == 0) return 0;
   BK_LAUNCH(compact_write, GRID1(nb2, 256), 256, 0, st, curB, curbB, keep, off, nb2, curC, curbC);
@@ -912,7 +925,7 @@ static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *
   double *blkA = (double *)bp; bp += (size_t)nb * 8;
   uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
   uint32_t *blkN = (uint32_t *)bp;
-  long long *out = (long long *)(c->counters.as<unsigned>() + 8);
+  long long *out = (long long *)(c->counters.as<unsigned>() + CS_SD_OUT);
   BK_LAUNCH(sd_resolve, 1, SDR_T, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, nb, blkF, blkCum, blkN, blkA, t_in, out);
   T_.mark("sd: resolve");
   long long h[2] = {0, 0};
@@ -943,12 +956,12 @@ static int side_launch(bkid_ctx *c)
     double *blkA = (double *)bp; bp += (size_t)nb * 8;
     uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
     uint32_t *blkN = (uint32_t *)bp;
-    long long *out = (long long *)(c->counters.as<unsigned>() + 8);
+    long long *out = (long long *)(c->counters.as<unsigned>() + CS_SD_OUT);
     BK_LAUNCH(sd_resolve, 1, SDR_T, SD_BLOCK * 9, s2, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, 0ll, out);
   }
   cudaEventRecord(c->ev_side[1], s2);
   // the max reference span bounds the region-query windows of the refinement only: its own stream, collected there
-  int *mx = (int *)(c->counters.as<unsigned>() + 44);
+  int *mx = (int *)(c->counters.as<unsigned>() + CS_MAXSPAN);
   CU(c, cudaMemsetAsync(mx, 0, 4, c->st3));
   if (n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, c->st3, c->p_pos, c->p_endpos, n, mx);
   c->maxspan_pending = true;
@@ -960,7 +973,7 @@ static int side_collect(bkid_ctx *c)
   cudaStream_t s2 = c->st2;
   long long n = c->n;
   long long h[2] = {0, 0};
-  if (n > 0 && c->cnt_insert > 0) CU(c, cudaMemcpyAsync(h, c->counters.as<unsigned>() + 8, 16, cudaMemcpyDeviceToHost, s2));
+  if (n > 0 && c->cnt_insert > 0) CU(c, cudaMemcpyAsync(h, c->counters.as<unsigned>() + CS_SD_OUT, 16, cudaMemcpyDeviceToHost, s2));
   CU(c, cudaStreamSynchronize(s2));
   CU(c, cudaGetLastError());
   if (h[1]) {                                                                 // left the closed-form regime: literal replay
@@ -981,7 +994,7 @@ static int maxspan_collect(bkid_ctx *c)
 {
   if (!c->maxspan_pending) return 0;
   int maxspan = 0;
-  CU(c, cudaMemcpyAsync(&maxspan, c->counters.as<unsigned>() + 44, 4, cudaMemcpyDeviceToHost, c->st3));
+  CU(c, cudaMemcpyAsync(&maxspan, c->counters.as<unsigned>() + CS_MAXSPAN, 4, cudaMemcpyDeviceToHost, c->st3));
   CU(c, cudaStreamSynchronize(c->st3));
   CU(c, cudaGetLastError());
   c->maxspan = maxspan + 1; c->maxspan_cached = true; c->maxspan_pending = false;
@@ -1022,7 +1035,7 @@ static int extract_candidates(bkid_ctx *c, unsigned long long index_offset)
   long long n = c->n;
   int ntiles = div_up(std::max<long long>(n, 1), K1_TILE);
   uint32_t *tile_cand = c->tile_cand.as<uint32_t>(), *tile_off = tile_cand + ntiles + 1;
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   TRY(c, c->sc.ensure(ntiles + 8, st));
   unsigned long long nc = 0;
   if (n > 0) {
@@ -1035,7 +1048,7 @@ static int extract_candidates(bkid_ctx *c, unsigned long long index_offset)
   if (nc > 0) {
     TRY(c, c->cand_idx.ensure((size_t)nc * 4 + 64, 0, st));
     BK_LAUNCH(k1_compact, (unsigned)ntiles, K1_THREADS, 0, st, c->cls.as<uint8_t>(), n, tile_off, c->cand_idx.as<uint32_t>());
-    int *miss = (int *)(c->counters.as<unsigned>() + 50);
+    int *miss = (int *)(c->counters.as<unsigned>() + CS_MISSING);
     CU(c, cudaMemsetAsync(miss, 0, 4, st));
     BK_LAUNCH(k2_gather_cand, GRID1(nc, 256), 256, 0, st, c->cand_idx.as<uint32_t>(), (long long)nc, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_x_rec, c->n_x,
               c->p_x_mtid, c->p_x_mpos, c->p_x_nh, index_offset, c->cand.as<bkid_cand>(), miss);
@@ -1053,14 +1066,14 @@ static int join_presort(bkid_ctx *c, const bkid_cand *cand, long long nc)
 {
   cudaStream_t st = c->st;
   if (nc <= 0) return 0;
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   TRY(c, c->sc.ensure(nc + 8, st));
   uint64_t *key = c->sc.keys.as<uint64_t>();
   uint32_t *val = c->sc.vals.as<uint32_t>();
   BK_LAUNCH(k2_cand_keys, GRID1(nc, 256), 256, 0, st, cand, nc, key, val);
   bk::radix_sort_pairs(key, val, nc, 0, 64, c->sc.rt(), st);
   uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
-  int *errf = (int *)(c->counters.as<unsigned>() + 40);
+  int *errf = (int *)(c->counters.as<unsigned>() + CS_HASH_ERR);
   CU(c, cudaMemsetAsync(errf, 0, 4, st));
   BK_LAUNCH(k2_run_heads, GRID1(nc, 256), 256, 0, st, key, val, nc, cand, head, errf);
   bk::exclusive_scan<uint32_t, uint32_t>(head, hex, nc, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
@@ -1075,10 +1088,10 @@ static int join_emit(bkid_ctx *c, const bkid_cand *cand, long long nc, double w,
   cudaStream_t st = c->st;
   *np_out = 0;
   if (nc <= 0) return 0;
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   uint32_t *val = c->sc.vals.as<uint32_t>();
   uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
-  int *errf = (int *)(c->counters.as<unsigned>() + 40);
+  int *errf = (int *)(c->counters.as<unsigned>() + CS_HASH_ERR);
   unsigned long long *pcount = tot + 1;
   CU(c, cudaMemsetAsync(pcount, 0, 8, st));
   BK_LAUNCH(k2_emit_pairs, GRID1(nc, 256), 256, 0, st, val, head, hex, rstart, nc, cand, c->d_cum.as<uint32_t>(), c->nt, c->d_bucket_rank.as<int32_t>(), w,
@@ -1104,7 +1117,7 @@ static int set_pairs(bkid_ctx *c, const bkid_pair *pairs, long long np)
   cudaStream_t st = c->st;
   c->np0 = np; c->nb = 0;
   if (np <= 0) return 0;
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   TRY(c, c->sc.ensure(np + 8, st));
   TRY(c, c->pairs0.ensure((size_t)np * sizeof(bkid_pair), 0, st));
   unsigned long long *pkey = (unsigned long long *)c->sc.keys.as<uint64_t>();
@@ -1183,7 +1196,7 @@ int bkid_cluster(bkid_ctx *c, double dist, int mode, int64_t *n_clusters)
     long long nm = c->n2;
     TRY(c, c->sc.ensure(nm + 8, st));
     uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *start = c->sc.c32.as<uint32_t>(), *keep = c->sc.d32.as<uint32_t>(), *koff = c->sc.e32.as<uint32_t>();
-    unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+    unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
     BK_LAUNCH(k6_cluster_heads, GRID1(nm, 256), 256, 0, st, c->mem_bucket.as<uint32_t>(), c->mem_cluster.as<int32_t>(), nm, head);
     bk::exclusive_scan<uint32_t, uint32_t>(head, hex, nm, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
     unsigned long long ncl = 0;
@@ -1235,7 +1248,7 @@ static int refine_build_rows(bkid_ctx *c)
   TRY(c, classify_impl(c));
   TRY(c, c->sarows.ensure((size_t)(c->n_sa + 1) * sizeof(EvRow), 0, st));
   {
-    int *miss = (int *)(c->counters.as<unsigned>() + 50);
+    int *miss = (int *)(c->counters.as<unsigned>() + CS_MISSING);
     CU(c, cudaMemsetAsync(miss, 0, 4, st));
     if (c->n_sa > 0) {
       BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->cls.as<uint8_t>(), c->p_flag, c->p_tid, c->p_pos, c->p_endpos, c->p_x_rec, c->n_x, c->p_x_nh, miss,
@@ -1260,7 +1273,7 @@ static int refine_local_maxspan(bkid_ctx *c, int *out)
 {
   cudaStream_t st = c->st;
   if (c->maxspan_pending) { TRY(c, maxspan_collect(c)); *out = c->maxspan; return 0; }
-  int *mx = (int *)(c->counters.as<unsigned>() + 44);
+  int *mx = (int *)(c->counters.as<unsigned>() + CS_MAXSPAN);
   CU(c, cudaMemsetAsync(mx, 0, 4, st));
   if (c->n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, st, c->p_pos, c->p_endpos, c->n, mx);
   int maxspan = 0;
@@ -1295,7 +1308,7 @@ static int refine_coverage(bkid_ctx *c, double dist)
   if (ncl == 0) return 0;
   RefineView v = refine_view(c);
   int w = (int)dist;                                                       // const int w (src/BreakID.cc:390)
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   uint32_t *evcap = c->sc.a32.as<uint32_t>();
   BK_LAUNCH(k7_regions, GRID1(ncl, 128), 128, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, w, c->work.as<ClusterWork>(), evcap);
   bk::exclusive_scan<uint32_t, uint32_t>(evcap, c->evoff.as<uint32_t>(), ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
@@ -1322,12 +1335,12 @@ static int refine_vote(bkid_ctx *c)
     bk::radix_sort_pairs(c->name_key.as<uint64_t>(), c->name_row.as<uint32_t>(), c->n_rows, 0, 32, c->sc.rt(), st);
   }
   RefineView v = refine_view(c);
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   ClusterWork *work = c->work.as<ClusterWork>();
   uint32_t *entcnt = c->sc.c32.as<uint32_t>(), *entoff = c->sc.d32.as<uint32_t>();
   TRY(c, c->valid.ensure((size_t)(ncl + 2) * 4, 0, st));
   TRY(c, c->tmpC.ensure((size_t)(c->n_evcap + 1) * 4, 0, st));
-  int *fatal = (int *)(c->counters.as<unsigned>() + 46);
+  int *fatal = (int *)(c->counters.as<unsigned>() + CS_FATAL);
   CU(c, cudaMemsetAsync(fatal, 0, 4, st));
   BK_LAUNCH((k7_collect<false>), ncl, RF_THREADS, 0, st, v, c->clusters.as<bkid_cluster_rec>(), ncl, work, c->cov.as<uint32_t>(), c->evoff.as<uint32_t>(),
             c->tmpC.as<uint32_t>(), (const uint32_t *)nullptr, (int2 *)nullptr);
@@ -1369,7 +1382,7 @@ static int refine_finish(bkid_ctx *c)
   c->n_called = 0;
   if (ncl == 0) return 0;
   RefineView v = refine_view(c);
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   BK_LAUNCH(k10_finish, GRID1(ncl, 128), 128, 0, st, v, c->clusters.as<bkid_cluster_rec>(), c->valid.as<uint32_t>(), c->depth.as<uint32_t>(), ncl);
   uint32_t *voff = c->sc.b32.as<uint32_t>();
   bk::exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), voff, ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);

@@ -436,7 +436,7 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_bloc
   TRY(c, d->tasks.ensure((2 * max_tasks + 2) * sizeof(Task), 0, st));
   int *state = d->state.as<int>();           // [0] changed [1] corrupt [2] carry start [4] inflate err [5] walk err [6] crc mismatch (block + 1)
   CU(c, cudaMemsetAsync(state, 0, 64, st));
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + 32);
+  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   if (c->n_sa == 0) { TRY(c, reserve_impl(c, c->n, c->n_x, 1, 1, 1, 1)); CU(c, cudaMemsetAsync(c->cig_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->sa_off.p, 0, 4, st)); CU(c, cudaMemsetAsync(c->oc_off.p, 0, 4, st)); }
 
   auto stage_chunk = [&](size_t k) -> int {            // host copy (if needed) + async H2D of chunk k into slot k&1
@@ -569,7 +569,7 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_bloc
       uint32_t *m[8]; for (int i = 0; i < 8; ++i) m[i] = d->meta[i].as<uint32_t>();        // [5],[6] = tag pointers, [7] = seq bytes
       uint32_t *mo[6]; for (int i = 0; i < 6; ++i) mo[i] = d->metao[i].as<uint32_t>();
       BK_LAUNCH(bam_extract_cols, GRID1(nrec, 128), 128, 0, st, u, d->rec_off.as<uint32_t>(), nrec, c->n, C, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
-      unsigned long long *tots = (unsigned long long *)(c->counters.as<unsigned>() + 52);     // 6 x u64
+      unsigned long long *tots = (unsigned long long *)(c->counters.as<unsigned>() + CS_DECODE);     // 6 x u64
       for (int i = 0; i < 5; ++i) bk::exclusive_scan<uint32_t, uint32_t>(m[i], mo[i], nrec, c->sc.scan_tmp.as<unsigned long long>(), tots + i, st);
       bk::exclusive_scan<uint32_t, uint32_t>(m[7], mo[5], nrec, c->sc.scan_tmp.as<unsigned long long>(), tots + 5, st);
       unsigned long long ht5[6];
