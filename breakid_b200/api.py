@@ -306,8 +306,8 @@ def cuda_lib():
         L.bkid_set_exclude.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.bkid_op_banded_align.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int32, vp]
         L.bkid_device_gather_rows.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32]
-        L.bkid_push_bgzf.argtypes = [vp, vp, vp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
-        L.bkid_push_bgzf_range.argtypes = [vp, vp, vp, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.bkid_push_bgzf.argtypes = [vp, vp, C.c_uint64, vp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
+        L.bkid_push_bgzf_range.argtypes = [vp, vp, C.c_uint64, vp, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.bkid_get_decode_stats.argtypes = [vp, C.POINTER(DecodeStats)]
         L.bkid_fetch_column.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.bkid_reset.argtypes = [vp]
@@ -453,7 +453,7 @@ class Context:
         """device BGZF inflate + BAM decode of a whole file (``bkid_push_bgzf``); returns the record count.
         ``data_ptr`` overrides the mapped file with another host copy of the same bytes (e.g. a pinned buffer)."""
         n = C.c_int64()
-        self._chk(self.lib.bkid_push_bgzf(self.ctx, C.c_void_p(data_ptr if data_ptr is not None else f.data),
+        self._chk(self.lib.bkid_push_bgzf(self.ctx, C.c_void_p(data_ptr if data_ptr is not None else f.data), f.size,
                                           C.c_void_p(blocks if blocks is not None else f.blocks),
                                           f.n_blocks if n_blocks is None else n_blocks,
                                           f.first_record if first_record is None else first_record, C.byref(n)))
@@ -463,7 +463,7 @@ class Context:
         """device decode of the records that start inside blocks [first_block, end_block) (``bkid_push_bgzf_range``);
         returns (n_records, stream offset of the first decoded record, stream offset of the next range's first record)"""
         n, a, b = C.c_int64(), C.c_uint64(), C.c_uint64()
-        self._chk(self.lib.bkid_push_bgzf_range(self.ctx, C.c_void_p(data_ptr if data_ptr is not None else f.data), C.c_void_p(f.blocks), f.n_blocks,
+        self._chk(self.lib.bkid_push_bgzf_range(self.ctx, C.c_void_p(data_ptr if data_ptr is not None else f.data), f.size, C.c_void_p(f.blocks), f.n_blocks,
                                                 f.first_record, first_block, end_block, C.byref(n), C.byref(a), C.byref(b)))
         return int(n.value), int(a.value), int(b.value)
 

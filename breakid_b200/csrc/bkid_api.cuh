@@ -1603,7 +1603,9 @@ int bkid_device_copy(bkid_ctx *c, void *dst, const void *src, uint64_t bytes)
 {
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device);
-  if (bytes) CU(c, cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault));
+  // on the context's own stream (a non-blocking stream does not order against the legacy default stream), then
+  // synchronised: the copy is complete, and ordered after everything the library queued, when this returns
+  if (bytes) { CU(c, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, c->st)); CU(c, cudaStreamSynchronize(c->st)); }
   return 0;
 }
 

@@ -163,7 +163,10 @@ __global__ void bam_walk(const uint8_t *__restrict__ u, uint32_t total, uint32_t
   if (!WRITE) { cnt[s] = n; land[s] = o; why[s] = y; }
 }
 
-// accept seeds by induction from segment 0; drop the first seed the previous walk does not land on
+// accept seeds by induction from segment 0; drop the first seed the previous walk does not land on.
+// A seed is tested against the chain BEFORE the range-end test: the record that straddles the end of a block range can
+// jump over a false-positive seed that lies before stop_at, and such a seed must not stay live (its walk would emit
+// records that do not exist).  When the range ends inside segment `prev`, every later seed is killed and the walk repeated.
 __global__ void bam_stitch(uint32_t nseg, uint32_t *__restrict__ seed, const uint32_t *__restrict__ land, const uint32_t *__restrict__ why,
                            int *__restrict__ state /* [0] changed, [1] corrupt, [2] carry start */, uint32_t stop_at)
 {
@@ -172,12 +175,17 @@ __global__ void bam_stitch(uint32_t nseg, uint32_t *__restrict__ seed, const uin
   state[0] = 0;
   for (uint32_t s = 1; s < nseg; ++s) {
     if (seed[s] == NONE) continue;
-    if (land[prev] >= stop_at) break;                        // the range ends inside segment prev: later seeds are not ours
     if (land[prev] != seed[s]) {                            // seed s is not on the true chain (or lies inside the trailing partial record)
+      if (land[prev] >= stop_at) {                          // the range ends inside segment prev: nothing behind it is ours
+        for (uint32_t j = s; j < nseg; ++j) seed[j] = NONE;
+        state[0] = 1;
+        return;
+      }
       if (why[prev] == 2) state[1] = 1;                     // the true chain itself hit a corrupt block_size
       seed[s] = NONE; state[0] = 1;
       return;
     }
+    if (land[prev] >= stop_at) break;                        // on the chain, but at or behind the range end: its walk emits nothing
     prev = s;
   }
   if (why[prev] == 2) state[1] = 1;
@@ -190,7 +198,8 @@ struct Cols {
 struct RecMeta { uint32_t xf, sf, ncig, salen, oclen; };     // arrays of per-record sizes (scanned in place)
 
 // aux walk: offsets (relative to the record start) of the first SA:Z and OC:Z values, 0 = absent (bam_aux_get)
-__device__ void find_sa_oc(const uint8_t *__restrict__ r, uint32_t a, uint32_t end, uint32_t *sa, uint32_t *oc)
+// *bad = 1 when a Z / H value has no NUL inside the record (every later length scan relies on that terminator)
+__device__ void find_sa_oc(const uint8_t *__restrict__ r, uint32_t a, uint32_t end, uint32_t *sa, uint32_t *oc, int *bad)
 {
   *sa = 0; *oc = 0;
   while (a + 3 <= end) {
@@ -202,7 +211,7 @@ __device__ void find_sa_oc(const uint8_t *__restrict__ r, uint32_t a, uint32_t e
       case 's': case 'S': len = 2; break;
       case 'i': case 'I': case 'f': len = 4; break;
       case 'd': len = 8; break;
-      case 'Z': case 'H': { uint32_t k = v; while (k < end && r[k]) ++k; len = (k - v) + 1; break; }
+      case 'Z': case 'H': { uint32_t k = v; while (k < end && r[k]) ++k; if (k >= end) { *bad = 1; return; } len = (k - v) + 1; break; }
       case 'B': {
         if (v + 5 > end) { len = end - v; break; }
         uint8_t st = r[v]; uint32_t cnt = ld32(r + v + 1);
@@ -223,7 +232,7 @@ __device__ void find_sa_oc(const uint8_t *__restrict__ r, uint32_t a, uint32_t e
 
 __global__ void bam_extract_cols(const uint8_t *__restrict__ u, const uint32_t *__restrict__ rec_off, uint32_t nrec, long long n0, Cols C,
                                  uint32_t *__restrict__ xf, uint32_t *__restrict__ sf, uint32_t *__restrict__ ncig, uint32_t *__restrict__ salen, uint32_t *__restrict__ oclen,
-                                 uint32_t *__restrict__ sa_ptr, uint32_t *__restrict__ oc_ptr, uint32_t *__restrict__ seqb)
+                                 uint32_t *__restrict__ sa_ptr, uint32_t *__restrict__ oc_ptr, uint32_t *__restrict__ seqb, int *__restrict__ err)
 {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrec) return;
@@ -235,6 +244,14 @@ __global__ void bam_extract_cols(const uint8_t *__restrict__ u, const uint32_t *
   uint32_t n_cig = ld16(r + 16), fl = ld16(r + 18);
   int32_t l_seq = (int32_t)ld32(r + 20);
   long long g = n0 + i;
+  // bam_read1 (htslib sam.c:427-429) rejects l_qseq < 0, l_qname < 1 and fixed fields that do not fit the record:
+  // everything below indexes the record by these lengths
+  if (l_seq < 0 || l_name < 1 || 32ull + l_name + 4ull * n_cig + (uint64_t)((l_seq + 1) / 2) + (uint64_t)l_seq > (uint64_t)bs) {
+    atomicCAS(err, 0, 3);
+    C.tid[g] = tid; C.pos[g] = pos; C.mapq[g] = 0; C.flag[g] = 0; C.isize[g] = 0; C.endpos[g] = pos + 1;
+    xf[i] = sf[i] = ncig[i] = salen[i] = oclen[i] = sa_ptr[i] = oc_ptr[i] = seqb[i] = 0u;
+    return;
+  }
   C.tid[g] = tid; C.pos[g] = pos; C.mapq[g] = r[13]; C.flag[g] = (uint16_t)fl; C.isize[g] = (int32_t)ld32(r + 32);
   uint32_t cg = 36 + l_name;
   int32_t rlen = 0;
@@ -246,12 +263,14 @@ __global__ void bam_extract_cols(const uint8_t *__restrict__ u, const uint32_t *
   C.endpos[g] = (!(fl & 0x4) && n_cig > 0) ? pos + rlen : pos + 1;                      // bam_endpos, sam.c:344-350
   uint64_t a64 = (uint64_t)cg + 4ull * n_cig + (uint64_t)((l_seq + 1) / 2) + (uint64_t)l_seq;
   uint32_t sa = 0, oc = 0;
-  if (a64 < end) find_sa_oc(r, (uint32_t)a64, end, &sa, &oc);
+  int bad = 0;
+  if (a64 < end) find_sa_oc(r, (uint32_t)a64, end, &sa, &oc, &bad);
+  if (bad) { atomicCAS(err, 0, 3); sa = oc = 0; }
   bool has_sa = sa && r[sa];
   uint32_t sl = 0, ol = 0;
-  if (has_sa) {
-    while (r[sa + sl]) ++sl;
-    if (oc) while (r[oc + ol]) ++ol;
+  if (has_sa) {                                            // both values are NUL-terminated inside the record (find_sa_oc)
+    while (sa + sl < end && r[sa + sl]) ++sl;
+    if (oc) while (oc + ol < end && r[oc + ol]) ++ol;
   }
   xf[i] = (!(fl & 0x2) || has_sa) ? 1u : 0u;
   sf[i] = has_sa ? 1u : 0u;
@@ -361,7 +380,7 @@ static void decoder_free(bkid_ctx *c)
 // first_record_uoffset; otherwise the first record is found by seeding (and reported in *first_uoff so that the caller
 // can verify it against where the previous range landed).  b_end < n_blocks: up to `overlap` further blocks are read
 // so that the record straddling the range end completes; *land_uoff = start of the first record of the NEXT range.
-static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t b_begin, int64_t b_end,
+static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, uint64_t file_size, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t b_begin, int64_t b_end,
                           int64_t *n_records, uint64_t *first_uoff, uint64_t *land_uoff)
 {
   using namespace bamdec;
@@ -405,8 +424,9 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_bloc
     while (b1 < b_last) {
       size_t span = (size_t)(blocks[b1].payload_off + blocks[b1].payload_len + 8 - span0);
       if (b1 > b0 && (span > ccap || ub + blocks[b1].usize > ucap)) break;
-      if (blocks[b1].usize > (1u << 16) || (b1 > b0 && blocks[b1].payload_off < blocks[b1 - 1].payload_off + blocks[b1 - 1].payload_len))
-        return fail(c, BKID_ERR_IO, "corrupt BGZF block table");
+      if (blocks[b1].usize > (1u << 16) || (b1 > b0 && blocks[b1].payload_off < blocks[b1 - 1].payload_off + blocks[b1 - 1].payload_len) ||
+          blocks[b1].payload_off > file_size || (uint64_t)blocks[b1].payload_len + 8 > file_size - blocks[b1].payload_off)
+        return fail(c, BKID_ERR_IO, "corrupt BGZF block table (a block lies outside the file or overlaps its predecessor)");
       cb = span; ub += blocks[b1].usize; ++b1;
     }
     if (cb > COMP_CAP + (1u << 17)) return fail(c, BKID_ERR_IO, "BGZF block larger than 64 KiB");
@@ -475,10 +495,12 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_bloc
     uint64_t span0 = blocks[b0].payload_off;
     Task *ht = d->h_tasks + (size_t)slot * max_tasks;
     int nt = 0; uint32_t uo = carry;
+    std::vector<int64_t> task_block;                          // empty blocks get no task: error messages name the real block
     for (int64_t b = b0; b < b1; ++b) {
-      if (blocks[b].usize) ht[nt++] = Task{blocks[b].payload_off - span0, uo, blocks[b].payload_len, blocks[b].usize};
+      if (blocks[b].usize) { ht[nt++] = Task{blocks[b].payload_off - span0, uo, blocks[b].payload_len, blocks[b].usize}; task_block.push_back(b); }
       uo += blocks[b].usize;
     }
+    auto block_of = [&](long long t) -> long long { return t >= 0 && t < (long long)task_block.size() ? (long long)task_block[(size_t)t] : (long long)b0 + t; };
     uint32_t total = uo;
     uint8_t *u = d->unc.as<uint8_t>();
     Task *dt = d->tasks.as<Task>() + (size_t)slot * max_tasks;
@@ -539,8 +561,8 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_bloc
       BK_LAUNCH(bam_stitch, 1, 32, 0, st, nsg, seedv, d->land.as<uint32_t>(), d->base.as<uint32_t>(), state, stop_rel);
       CU(c, cudaMemcpyAsync(hstate, state, 32, cudaMemcpyDeviceToHost, st));
       TRY(c, sync_check(c));
-      if (hstate[4]) return fail(c, BKID_ERR_IO, "inflate failed: BGZF block " + std::to_string((long long)b0 + (hstate[4] >> 4)) + " (deflate error " + std::to_string(hstate[4] & 15) + ")");
-      if (hstate[6]) return fail(c, BKID_ERR_IO, "CRC32 mismatch in BGZF block " + std::to_string((long long)b0 + hstate[6] - 1));
+      if (hstate[4]) return fail(c, BKID_ERR_IO, "inflate failed: BGZF block " + std::to_string(block_of(hstate[4] >> 4)) + " (deflate error " + std::to_string(hstate[4] & 15) + ")");
+      if (hstate[6]) return fail(c, BKID_ERR_IO, "CRC32 mismatch in BGZF block " + std::to_string(block_of(hstate[6] - 1)));
       if (hstate[1]) return fail(c, BKID_ERR_IO, "corrupt BAM record (block_size < 32)");
       if (!hstate[0]) break;
       d->stats.seed_repairs++;
@@ -568,13 +590,17 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_bloc
       Cols C{c->flag.as<uint16_t>(), c->mapq.as<uint8_t>(), c->tid.as<int32_t>(), c->pos.as<int32_t>(), c->isize.as<int32_t>(), c->endpos.as<int32_t>()};
       uint32_t *m[8]; for (int i = 0; i < 8; ++i) m[i] = d->meta[i].as<uint32_t>();        // [5],[6] = tag pointers, [7] = seq bytes
       uint32_t *mo[6]; for (int i = 0; i < 6; ++i) mo[i] = d->metao[i].as<uint32_t>();
-      BK_LAUNCH(bam_extract_cols, GRID1(nrec, 128), 128, 0, st, u, d->rec_off.as<uint32_t>(), nrec, c->n, C, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+      BK_LAUNCH(bam_extract_cols, GRID1(nrec, 128), 128, 0, st, u, d->rec_off.as<uint32_t>(), nrec, c->n, C, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], state + 5);
       unsigned long long *tots = (unsigned long long *)(c->counters.as<unsigned>() + CS_DECODE);     // 6 x u64
       for (int i = 0; i < 5; ++i) bk::exclusive_scan<uint32_t, uint32_t>(m[i], mo[i], nrec, c->sc.scan_tmp.as<unsigned long long>(), tots + i, st);
       bk::exclusive_scan<uint32_t, uint32_t>(m[7], mo[5], nrec, c->sc.scan_tmp.as<unsigned long long>(), tots + 5, st);
       unsigned long long ht5[6];
+      int hs5 = 0;
       CU(c, cudaMemcpyAsync(ht5, tots, 48, cudaMemcpyDeviceToHost, st));
+      CU(c, cudaMemcpyAsync(&hs5, state + 5, 4, cudaMemcpyDeviceToHost, st));
       TRY(c, sync_check(c));
+      if (hs5 == 3) return fail(c, BKID_ERR_IO, "corrupt BAM record (fixed fields do not fit block_size, or an unterminated tag value)");
+      if (hs5) return fail(c, BKID_ERR_IO, "corrupt BAM record (block_size < 32)");
       TRY(c, reserve_impl(c, c->n + nrec, c->n_x + (long long)ht5[0], c->n_sa + (long long)ht5[1], c->n_cig + (long long)ht5[2], c->sa_bytes + (long long)ht5[3], c->oc_bytes + (long long)ht5[4]));
       {
         size_t s_new = (size_t)(c->n_sa + (long long)ht5[1]);
@@ -630,15 +656,15 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_bloc
   return 0;
 }
 
-int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t *n_records)
+int bkid_push_bgzf(bkid_ctx *c, const uint8_t *file, uint64_t file_size, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t *n_records)
 {
-  return push_bgzf_impl(c, file, blocks, n_blocks, first_record_uoffset, 0, n_blocks, n_records, nullptr, nullptr);
+  return push_bgzf_impl(c, file, file_size, blocks, n_blocks, first_record_uoffset, 0, n_blocks, n_records, nullptr, nullptr);
 }
 
-int bkid_push_bgzf_range(bkid_ctx *c, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t first_block, int64_t end_block,
+int bkid_push_bgzf_range(bkid_ctx *c, const uint8_t *file, uint64_t file_size, const bkid_bgzf_block *blocks, int64_t n_blocks, uint64_t first_record_uoffset, int64_t first_block, int64_t end_block,
                          int64_t *n_records, uint64_t *first_record_uoff, uint64_t *next_record_uoff)
 {
-  return push_bgzf_impl(c, file, blocks, n_blocks, first_record_uoffset, first_block, end_block, n_records, first_record_uoff, next_record_uoff);
+  return push_bgzf_impl(c, file, file_size, blocks, n_blocks, first_record_uoffset, first_block, end_block, n_records, first_record_uoff, next_record_uoff);
 }
 
 int bkid_get_decode_stats(bkid_ctx *c, bkid_decode_stats *s)

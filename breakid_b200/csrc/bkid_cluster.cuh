@@ -275,47 +275,6 @@ __global__ void __launch_bounds__(128) ahc_components(AhcView v, uint32_t ncomp)
   }
 }
 
-// Kernel B: replay per bucket.  One warp per bucket; lanes own components round-robin.
-__global__ void __launch_bounds__(128) ahc_replay(AhcView v, const uint32_t *__restrict__ bucket_comp_off, uint32_t nb, const int32_t *__restrict__ bucket_flag,
-                                                  uint32_t n_lo)
-{
-  uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= nb) return;
-  if (bucket_flag[b]) return;                     // handled by the exact kernel
-  const unsigned lane = threadIdx.x & 31;
-  uint32_t c0 = bucket_comp_off[b], c1 = bucket_comp_off[b + 1];
-  uint32_t nleaf = v.seg_off[b + 1] - v.seg_off[b];
-  if (nleaf < n_lo) return;                       // small buckets take the shared-memory form
-  int32_t g = 0;
-  while (true) {
-    double bd = 1.7976931348623157e308; int32_t bg = -1; uint32_t bc = 0xffffffffu;
-    for (uint32_t comp = c0 + lane; comp < c1; comp += 32) {
-      uint32_t lbase = v.comp_off[comp], c = v.comp_off[comp + 1] - lbase;
-      uint32_t cur = v.comp_cursor[comp], nev = v.comp_nnodes[comp] - c;
-      if (cur >= nev) continue;
-      double d = v.ev_d[lbase + cur];
-      int32_t f = v.ev_first[lbase + cur];
-      int32_t gi = (uint32_t)f < c ? (int32_t)(v.comp_leaf[lbase + f] - v.seg_off[b]) : (int32_t)nleaf + v.node_grank[2 * lbase + f];
-      if (bg < 0 || d < bd || (d == bd && gi > bg)) { bd = d; bg = gi; bc = comp; }
-    }
-    for (int o = 16; o; o >>= 1) {
-      double od = __shfl_xor_sync(0xffffffffu, bd, o);
-      int32_t og = __shfl_xor_sync(0xffffffffu, bg, o);
-      uint32_t oc = __shfl_xor_sync(0xffffffffu, bc, o);
-      if (og >= 0 && (bg < 0 || od < bd || (od == bd && og > bg))) { bd = od; bg = og; bc = oc; }
-    }
-    if (bg < 0) break;
-    if (lane == 0) {
-      uint32_t lbase = v.comp_off[bc], c = v.comp_off[bc + 1] - lbase;
-      uint32_t cur = v.comp_cursor[bc];
-      v.node_grank[2 * lbase + c + cur] = g;
-      v.comp_cursor[bc] = cur + 1;
-    }
-    ++g;
-    __syncwarp();
-  }
-}
-
 // Kernel B (shared-memory form): one warp per bucket with every event, cursor and component head of the
 // bucket staged in shared memory, so a replay step is a handful of LDS + shuffles instead of a chain
 // of dependent global loads.  Components that kernel A flagged (a tie decision depended on global
@@ -559,25 +518,6 @@ __global__ void ahc_rg_prepare(AhcView v, RankGlobal g, uint32_t ncomp, const in
     } else g.pm[q] = __longlong_as_double(0x7ff0000000000000ll);
     g.tie[q] = 0; g.is_head[q] = 0;
   }
-}
-
-__global__ void __launch_bounds__(256) ahc_rg_rank(AhcView v, RankGlobal g, const uint32_t *__restrict__ point_bucket, long long n, const int32_t *__restrict__ bucket_flag, uint32_t n_lo)
-{
-  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  uint32_t b = point_bucket[e];
-  uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
-  if (bucket_flag[b] || s1 - s0 < n_lo) return;
-  double pm = g.pm[e];
-  if (!(pm < 1.0e300)) return;                         // unused slot
-  uint32_t ce = g.slot_comp[e], cnt = 0;
-  bool t = false;
-  for (uint32_t o = s0; o < s1; ++o) {
-    double p2 = g.pm[o];
-    cnt += (p2 < pm || (p2 == pm && o < (uint32_t)e)) ? 1u : 0u;
-    t |= (p2 == pm) && (g.slot_comp[o] != ce);
-  }
-  g.rank[e] = cnt; g.order[s0 + cnt] = (uint32_t)e; g.tie[e] = t ? 1 : 0;
 }
 
 // The rank of an event under (prefix-max distance, slot) inside its bucket is its position after two stable radix

@@ -286,7 +286,7 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
     s, n = engine.insert_partial()
     sn = _reduce(torch.tensor([s, n], dtype=torch.int64, device=dev), dist.ReduceOp.SUM)
     S, N = int(sn[0]), int(sn[1])
-    mean = float(S) / float(N)
+    mean = (float(S) / float(N)) if N else float("nan")      # no proper pair: NaN like the single-GPU path and the reference (0/0 in double)
     if hasattr(engine, "sd_prepare"):
         engine.sd_prepare(mean)          # the streaming pass (block tables) runs on all ranks at once, asynchronously: it overlaps the candidate extraction below
     lap('insert sum/count')
@@ -310,7 +310,7 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
         if W > 1:
             dist.broadcast(t, src=src)
     lap('sd chain')
-    sd = math.sqrt(int(t[0]) / float(N))
+    sd = math.sqrt(int(t[0]) / float(N)) if N else float("nan")
     d = times * math.sqrt(times) * (mean + sd_mult * sd)
     engine.set_stats(mean, sd)
     pairs = engine.join(cands, d)

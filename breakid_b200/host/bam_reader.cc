@@ -95,7 +95,7 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
   int fd = open(path, O_RDONLY);
   if (fd < 0) { set_err(err, errlen, std::string("cannot open ") + path); return nullptr; }
   struct stat st;
-  fstat(fd, &st);
+  if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); set_err(err, errlen, std::string("cannot stat ") + path); return nullptr; }
   size_t fsz = (size_t)st.st_size;
   const uint8_t *file = (const uint8_t *)mmap(nullptr, fsz, PROT_READ, MAP_PRIVATE, fd, 0);
   close(fd);
@@ -109,13 +109,15 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
     if (p[0] != 0x1f || p[1] != 0x8b) { munmap((void *)file, fsz); set_err(err, errlen, "not a BGZF file"); return nullptr; }
     uint16_t xlen = rd16(p + 10);
     uint32_t bsize = 0;
-    for (uint32_t x = 0; x + 4 <= xlen;) {        // find the BC subfield
+    if (off + 12 + xlen > fsz) { munmap((void *)file, fsz); set_err(err, errlen, "corrupt BGZF block"); return nullptr; }
+    for (uint32_t x = 0; x + 4 <= xlen;) {        // find the BC subfield (every subfield must lie inside XLEN)
       const uint8_t *q = p + 12 + x;
       uint16_t slen = rd16(q + 2);
+      if (x + 4 + (uint32_t)slen > xlen) break;
       if (q[0] == 'B' && q[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(q + 4) + 1;
       x += 4 + slen;
     }
-    if (!bsize || off + bsize > fsz) { munmap((void *)file, fsz); set_err(err, errlen, "corrupt BGZF block"); return nullptr; }
+    if (!bsize || off + bsize > fsz || bsize < 12u + xlen + 8u) { munmap((void *)file, fsz); set_err(err, errlen, "corrupt BGZF block"); return nullptr; }
     uint32_t usize = rd32(p + bsize - 4);
     blocks.push_back(Block{off, bsize, usize, utotal});
     utotal += usize;
@@ -172,6 +174,7 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
                 std::vector<uint32_t> xrec; std::vector<int32_t> xmtid, xmpos; std::vector<uint64_t> xhash; };
   int T = threads;
   std::vector<Side> sides(T);
+  std::atomic<bool> bad_record{false};
   size_t chunk = (n + T - 1) / (T ? T : 1);
   parallel_for(T, (size_t)T, [&](size_t tb, size_t te) {
     for (size_t t = tb; t < te; ++t) {
@@ -184,6 +187,8 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
         uint8_t l_name = r[12], mq = r[13];
         uint16_t n_cig = rd16(r + 16), fl = rd16(r + 18);
         int32_t l_seq = (int32_t)rd32(r + 20);
+        // bam_read1 (sam.c:427-429) rejects l_qseq < 0, l_qname < 1 and fixed fields that do not fit the record
+        if (l_seq < 0 || l_name < 1 || 32ull + l_name + 4ull * n_cig + (uint64_t)((l_seq + 1) / 2) + (uint64_t)l_seq > bs) { bad_record = true; continue; }
         h->tid[i] = tid; h->pos[i] = pos; h->mapq[i] = mq; h->flag[i] = fl;
         h->isize[i] = (int32_t)rd32(r + 32);
         const char *qn = (const char *)(r + 36);
@@ -209,6 +214,7 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
             case 'd': len = 8; break;
             case 'Z': case 'H': len = strnlen((const char *)v, end - v) + 1; break;
             case 'B': {
+              if (v + 5 > end) { len = (size_t)(end - v); break; }
               uint8_t st = v[0]; uint32_t cnt = rd32(v + 1);
               size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
               len = 5 + es * cnt; break;
@@ -219,12 +225,19 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
             if (t0 == 'S' && t1 == 'A' && !sa) sa = v;
             if (t0 == 'O' && t1 == 'C' && !oc) oc = v;
           }
+          if (len > (size_t)(end - v)) break;
           a = v + len;
         }
+        // an unterminated Z value (no NUL inside the record) is corrupt
+        if ((sa && strnlen((const char *)sa, end - sa) == (size_t)(end - sa)) || (oc && strnlen((const char *)oc, end - oc) == (size_t)(end - oc))) { bad_record = true; continue; }
         bool has_sa = sa && sa[0];
         if (!(fl & 0x2) || has_sa) {             // sparse table: mate fields + name hash only where they can ever be read
           uint64_t lo, hi;
-          bkid_name_hash(qn, &lo, &hi);
+          {                                    // bkid_name_hash over at most l_name bytes (a name without NUL cannot run past its field)
+            uint64_t a = 0xcbf29ce484222325ULL, b = 0x9E3779B97F4A7C15ULL;
+            for (uint32_t k = 0; k < l_name && qn[k]; ++k) { uint64_t ch = (unsigned char)qn[k]; a = (a ^ ch) * 0x100000001b3ULL; b = (b ^ ch) * 0xff51afd7ed558ccdULL; b ^= b >> 32; }
+            lo = a; hi = b;
+          }
           S.xrec.push_back((uint32_t)i); S.xmtid.push_back((int32_t)rd32(r + 24)); S.xmpos.push_back((int32_t)rd32(r + 28));
           S.xhash.push_back(lo); S.xhash.push_back(hi);
         }
@@ -246,6 +259,7 @@ extern "C" bkid_host_bam *bkid_host_read_bam(const char *path, int threads, char
       }
     }
   });
+  if (bad_record) { delete h; set_err(err, errlen, "corrupt BAM record (fields do not fit block_size or unterminated tag)"); return nullptr; }
   h->cig_off.push_back(0); h->sa_off.push_back(0); h->oc_off.push_back(0); h->seq_off.push_back(0);
   for (Side &S : sides) {
     size_t ci = 0;
@@ -332,7 +346,7 @@ extern "C" bkid_host_bgzf *bkid_host_bgzf_open(const char *path, char *err, int 
   int fd = open(path, O_RDONLY);
   if (fd < 0) { set_err(err, errlen, std::string("cannot open ") + path); return nullptr; }
   struct stat st;
-  fstat(fd, &st);
+  if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); set_err(err, errlen, std::string("cannot stat ") + path); return nullptr; }
   size_t fsz = (size_t)st.st_size;
   const uint8_t *file = (const uint8_t *)mmap(nullptr, fsz, PROT_READ, MAP_PRIVATE, fd, 0);
   close(fd);
@@ -346,9 +360,11 @@ extern "C" bkid_host_bgzf *bkid_host_bgzf_open(const char *path, char *err, int 
     if (p[0] != 0x1f || p[1] != 0x8b) return bail("not a BGZF file");
     uint16_t xlen = rd16(p + 10);
     uint32_t bsize = 0;
-    for (uint32_t x = 0; x + 4 <= xlen;) {
+    if (off + 12 + xlen > fsz) return bail("corrupt BGZF block");
+    for (uint32_t x = 0; x + 4 <= xlen;) {        // every subfield must lie inside XLEN
       const uint8_t *q = p + 12 + x;
       uint16_t slen = rd16(q + 2);
+      if (x + 4 + (uint32_t)slen > xlen) break;
       if (q[0] == 'B' && q[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(q + 4) + 1;
       x += 4 + slen;
     }

@@ -176,7 +176,7 @@ int main(int argc, char *argv[])
     if (bkid_push_batch(ctx, bkid_host_bam_batch_narrow(bam))) die("push_batch");
   } else {
     int64_t nrec = 0;
-    if (bkid_push_bgzf(ctx, bkid_host_bgzf_data(bgzf), bkid_host_bgzf_blocks(bgzf), bkid_host_bgzf_n_blocks(bgzf), bkid_host_bgzf_first_record(bgzf), &nrec)) {
+    if (bkid_push_bgzf(ctx, bkid_host_bgzf_data(bgzf), bkid_host_bgzf_size(bgzf), bkid_host_bgzf_blocks(bgzf), bkid_host_bgzf_n_blocks(bgzf), bkid_host_bgzf_first_record(bgzf), &nrec)) {
       std::cerr << "Error: can not read bam-file: " << inp << " (" << bkid_last_error(ctx) << ")" << std::endl;
       exit(1);
     }

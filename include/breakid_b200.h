@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BKID_ABI_VERSION 2
+#define BKID_ABI_VERSION 3
 
 typedef enum {
   BKID_OK = 0,
@@ -190,7 +190,8 @@ int bkid_push_batch_device(bkid_ctx *ctx, const bkid_batch *batch);
  * replaces, as the producer of records: bgzf_read_block + inflate_block (htslib-1.3.1/bgzf.c:545-600,388-419) and
  * bam_read1 (htslib-1.3.1/sam.c:407-441) under the samread / sam_read1 loops of src/BreakID.cc:1414,1929, together
  * with bam_endpos (sam.c:344-350) and bam_aux_get (sam.c:1267-1290) for the SA:Z / OC:Z tags.
- * `file` is the whole BAM file in host memory (mmap or a pinned buffer; pinned memory is copied from directly),
+ * `file` is the whole BAM file in host memory (mmap or a pinned buffer; pinned memory is copied from directly) and
+ * `file_size` its length: every block of the table must lie inside it (payload + CRC32 + ISIZE), else BKID_ERR_IO;
  * `blocks` its BGZF block table in file order (the host only walks the BSIZE / ISIZE fields, see
  * breakid_b200/host/bam_reader.h: bkid_host_bgzf_open), `first_record_uoffset` the offset of the first alignment
  * record in the uncompressed stream (= size of the BAM header).  Compressed bytes are streamed to the device in
@@ -208,7 +209,7 @@ typedef struct {
   float total_ms, inflate_ms, boundaries_ms, extract_ms;
   int32_t seed_repairs, reserved;
 } bkid_decode_stats;
-int bkid_push_bgzf(bkid_ctx *ctx, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks,
+int bkid_push_bgzf(bkid_ctx *ctx, const uint8_t *file, uint64_t file_size, const bkid_bgzf_block *blocks, int64_t n_blocks,
                    uint64_t first_record_uoffset, int64_t *n_records);
 /* Same for one rank of a multi-GPU job: decode only the records that START inside the uncompressed extent of BGZF blocks
  * [first_block, end_block) (genomic-bin sharding of the file itself).  A range that begins mid-stream finds
@@ -216,7 +217,7 @@ int bkid_push_bgzf(bkid_ctx *ctx, const uint8_t *file, const bkid_bgzf_block *bl
  * the first record of the following range (the walk reads up to 64 blocks past end_block to complete the straddling
  * record).  The caller verifies next_record_uoff[r] == first_record_uoff[r+1] across ranks: with that check the union
  * of the ranges is exactly the record sequence of the whole file. */
-int bkid_push_bgzf_range(bkid_ctx *ctx, const uint8_t *file, const bkid_bgzf_block *blocks, int64_t n_blocks,
+int bkid_push_bgzf_range(bkid_ctx *ctx, const uint8_t *file, uint64_t file_size, const bkid_bgzf_block *blocks, int64_t n_blocks,
                          uint64_t first_record_uoffset, int64_t first_block, int64_t end_block, int64_t *n_records,
                          uint64_t *first_record_uoff, uint64_t *next_record_uoff);
 int bkid_get_decode_stats(bkid_ctx *ctx, bkid_decode_stats *stats);

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(api.LIB_CUDA)
     for s in declared:
         assert hasattr(lib, s), s
-    assert api.cuda_lib().bkid_abi_version() == 2
+    assert api.cuda_lib().bkid_abi_version() == 3
 
 
 def test_no_cpu_fallback():

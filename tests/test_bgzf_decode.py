@@ -342,3 +342,81 @@ def test_false_seed_is_repaired_by_the_stitch(tmp_path):
     c.close()
     c, hb, st = _assert_same_as_host_decoder(p, 512)          # several chunks: the bait also sits in carried data
     c.close()
+
+
+@pytest.mark.gpu
+def test_false_seed_inside_record_straddling_range_end(tmp_path):
+    """block-range ingest: the record that straddles the END of a range carries plausible fake record chains, so the
+    straddling record jumps over false-positive seeds that lie before the range end.  Such a seed must be dropped
+    (it is not on the chain) although the walk that proves it already landed behind the range end."""
+    rng = np.random.RandomState(21)
+    targets = [("chr1", 500000), ("chr2", 400000)]
+    recs = _hostile_records(rng, 800)
+    payload0, first = _raw_bam(recs[:400], targets)
+    big_off = len(payload0)
+    arr = bytearray(900000)
+    fake = b"".join(struct.pack("<i", len(r)) + r for r in
+                    [_record(0, 1000 + 7 * k, "fake%d" % k, 99, 60, [(100, 0)], 100, 0, 1200, 300, b"NMC\x01") for k in range(3)])
+    for o in range(64, len(arr) - len(fake) - 64, 4096):      # bait in every segment, whatever the segment grid of a range is
+        arr[o:o + len(fake)] = fake
+    big = _record(0, 60000, "bigrec", 99, 60, [(50, 0)], 0, 0, 61000, 300, b"XBBc" + struct.pack("<i", len(arr)) + bytes(arr))
+    payload, _ = _raw_bam(recs[:400] + [big] + recs[400:], targets)
+    p = str(tmp_path / "bait_range.bam")
+    _bgzf_write(p, payload, vary=True)
+    f = api.BgzfFile(p)
+    whole = api.Context(f.target_len, f.target_names, device=0)
+    n_all = whole.push_bgzf(f)
+    assert n_all == 802
+    ustart = np.concatenate([[0], np.cumsum(f.block_table()["usize"].astype(np.int64))])
+    for frac in (0.35, 0.6, 0.9):                              # range ends inside the big record, behind 1..3 segments of bait
+        cut = int(np.searchsorted(ustart, big_off + int(frac * len(arr)), side="right") - 1)
+        assert ustart[cut] > big_off + (256 << 10) and ustart[cut] < big_off + len(arr)
+        parts, marks = [], []
+        for a, b in ((0, cut), (cut, f.n_blocks)):
+            c = api.Context(f.target_len, f.target_names, device=0)
+            n, lo, hi = c.push_bgzf_range(f, a, b)
+            parts.append((c, n)); marks.append((lo, hi))
+        assert marks[0][1] == marks[1][0], marks
+        assert sum(n for _, n in parts) == n_all
+        for k, dt in (("flag", np.uint16), ("pos", np.int32), ("isize", np.int32), ("endpos", np.int32)):
+            assert np.array_equal(np.concatenate([c.fetch_column(k, dt) for c, _ in parts]), whole.fetch_column(k, dt)), (frac, k)
+        for c, _ in parts:
+            c.close()
+    whole.close()
+    f.close()
+
+
+@pytest.mark.gpu
+def test_device_decode_rejects_records_whose_fields_do_not_fit(tmp_path):
+    """bam_read1 (htslib sam.c:427-429) rejects l_qseq < 0, l_qname < 1 and fixed fields longer than the record; so does
+    the device decoder (BKID_ERR_IO) instead of indexing past the record.  An SA:Z value without NUL is corrupt too."""
+    targets = [("chr1", 500000)]
+    good = [_record(0, 100 + 10 * i, "r%d" % i, 99, 60, [(50, 0)], 50, 0, 400, 300, b"NMC\x01") for i in range(50)]
+
+    def write(bad, name):
+        payload, _ = _raw_bam(good[:25] + [bad] + good[25:], targets)
+        p = str(tmp_path / name)
+        _bgzf_write(p, payload, vary=False)
+        return p
+
+    r = bytearray(_record(0, 350, "liar", 99, 60, [(50, 0)], 50, 0, 400, 300, b"NMC\x01"))
+    cases = []
+    # body layout (no block_size prefix): refID 0, pos 4, l_read_name 8, mapq 9, bin 10, n_cigar_op 12, flag 14, l_seq 16
+    b1 = bytearray(r); b1[12:14] = struct.pack("<H", 60000)                                            # 60000 cigar ops in a ~120-byte record
+    cases.append(("ncig.bam", bytes(b1)))
+    b2 = bytearray(r); b2[16:20] = struct.pack("<i", 1 << 20)                                          # l_seq = 1 Mi in a ~120-byte record
+    cases.append(("lseq.bam", bytes(b2)))
+    b3 = bytearray(r); b3[16:20] = struct.pack("<i", -5)
+    cases.append(("lseq_neg.bam", bytes(b3)))
+    b0 = bytearray(r); b0[8] = 0                                                                       # l_read_name = 0
+    cases.append(("lname0.bam", bytes(b0)))
+    b4 = _record(0, 350, "unterminated", 99, 60, [(50, 0)], 50, 0, 400, 300, b"NMC\x01SAZchr1,5,+,25M25S,60,0;")   # no NUL
+    cases.append(("sa_nonul.bam", b4))
+    for name, bad in cases:
+        p = write(bad, name)
+        f = api.BgzfFile(p)
+        c = api.Context(f.target_len, f.target_names, device=0)
+        with pytest.raises(api.BkidError) as e:
+            c.push_bgzf(f)
+        assert "corrupt BAM record" in str(e.value), (name, str(e.value))
+        c.close(); f.close()
