@@ -86,16 +86,33 @@ class ClockSampler:
 
 
 def device_batch(d: synth.SynthData):
-    """SynthData (cuda tensors) -> (api.Batch with device pointers, keep-alive list)"""
+    """SynthData (cuda tensors) -> (api.Batch with device pointers, keep-alive dict).  The insert-size and span columns are
+    handed over in their narrow forms (isize16 / span16, include/breakid_b200.h) whenever the whole batch fits them -- what
+    a decoder does -- and stay narrow in HBM; tid stays wide (resident)."""
     keep = {}
     c = d.cols
     keep["flag"] = c["flag"].contiguous()
     keep["mapq"] = c["mapq"].contiguous()
-    for k in ("tid", "pos", "isize", "endpos"):
+    for k in ("tid", "pos"):
         keep[k] = c[k].contiguous()
+    n = d.n
+    flag = c["flag"].to(torch.int32)
+    span = c["endpos"].to(torch.int64) - c["pos"].to(torch.int64)
+    if n and int(span.min()) >= 0 and int(span.max()) <= 65535:
+        keep["span16"] = span.to(torch.int16).contiguous()          # two's-complement wrap: same 16 bits as uint16
+    else:
+        keep["endpos"] = c["endpos"].contiguous()
+    read = ((flag & 1) != 0) & ((flag & 2) != 0) & ((flag & (0x4 | 0x100 | 0x200 | 0x400)) == 0)
+    iz = c["isize"][read]
+    if n and (iz.numel() == 0 or (int(iz.min()) >= -32768 and int(iz.max()) <= 32767)):
+        keep["isize16"] = c["isize"].clamp(-32768, 32767).to(torch.int16).contiguous()
+    else:
+        keep["isize"] = c["isize"].contiguous()
+    del span, read, iz
     # sparse mate/name table: records that are not proper pairs or carry an SA tag (what a host decoder lists)
-    in_x = (c["flag"].to(torch.int32) & 2) == 0
+    in_x = (flag & 2) == 0
     in_x[d.sa_rec] = True
+    del flag
     xr = torch.nonzero(in_x).flatten()
     keep["x_rec"] = xr.to(torch.int32).contiguous()
     keep["x_mtid"] = c["mtid"][xr].contiguous()
@@ -118,32 +135,18 @@ def device_batch(d: synth.SynthData):
 
 
 def host_batch_pinned(keep, n, n_sa, n_x):
-    """pinned host copies of the device columns -> (api.Batch with host pointers, keep-alive, bytes).  The three dense
-    columns that have a narrow encoding in the C ABI (isize16, span16, tid runs) are sent in it, as the host decoder
-    does whenever the batch fits: 11 B/record instead of 19."""
+    """pinned host copies of the device columns -> (api.Batch with host pointers, keep-alive, bytes).  Same column forms as
+    the resident batch, plus tid as one run per target (records are coordinate sorted): 11 B/record instead of 19."""
     hk = {}
     nbytes = 0
-    tid, pos, endpos, isize, flag = keep["tid"], keep["pos"], keep["endpos"], keep["isize"], keep["flag"].to(torch.int32)
-    span = endpos.to(torch.int64) - pos.to(torch.int64)
-    read = ((flag & 1) != 0) & ((flag & 2) != 0) & ((flag & (0x4 | 0x100 | 0x200 | 0x400)) == 0)
-    narrow = {}
-    if n and int(span.min()) >= 0 and int(span.max()) <= 65535:
-        narrow["span16"] = span.to(torch.int16)          # two's-complement wrap: same 16 bits as uint16
-    iz = isize[read]
-    if n and (iz.numel() == 0 or (int(iz.min()) >= -32768 and int(iz.max()) <= 32767)):
-        narrow["isize16"] = isize.clamp(-32768, 32767).to(torch.int16)
+    src = dict(keep)
+    tid = keep["tid"]
     if n:
         start = torch.nonzero(torch.cat([torch.ones(1, dtype=torch.bool, device=tid.device), tid[1:] != tid[:-1]])).flatten()
         if start.numel() <= 65536:
-            narrow["tid_run_start"] = start.to(torch.int32)
-            narrow["tid_run_tid"] = tid[start].contiguous()
-    del span, read, iz
-    skip = set()
-    if narrow.get("span16") is not None: skip.add("endpos")
-    if "isize16" in narrow: skip.add("isize")
-    if "tid_run_start" in narrow: skip.add("tid")
-    src = {k: v for k, v in keep.items() if k not in skip}
-    src.update({k: v for k, v in narrow.items() if v is not None})
+            src["tid_run_start"] = start.to(torch.int32)
+            src["tid_run_tid"] = tid[start].contiguous()
+            del src["tid"]
     for k, v in src.items():
         h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
         h.copy_(v)

@@ -274,7 +274,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_scan", "bkid_cluster", "bkid_set_nib", "bkid_refine", "bkid_run", "bkid_fetch_clusters",
            "bkid_fetch_pairs", "bkid_fetch_class", "bkid_get_timings", "bkid_op_sort_perm",
            "bkid_op_remove_isolated", "bkid_op_cluster",
-           "bkid_shard_insert_partial", "bkid_shard_sd_prepare", "bkid_shard_sd_partial", "bkid_shard_set_stats", "bkid_shard_candidates", "bkid_shard_join",
+           "bkid_shard_insert_partial", "bkid_sd_upper_binade", "bkid_shard_sd_fast", "bkid_shard_sd_fast_collect", "bkid_shard_sd_prepare", "bkid_shard_sd_partial", "bkid_shard_set_stats", "bkid_shard_candidates", "bkid_shard_join",
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
@@ -325,7 +325,12 @@ def cuda_lib():
         L.bkid_op_remove_isolated.argtypes = [vp, C.c_int64, vp, vp, C.c_double, vp, i64p]
         L.bkid_op_cluster.argtypes = [vp, C.c_int, C.c_int64, vp, vp, C.c_double, vp, vp, i64p, C.POINTER(C.c_int32)]
         pvp = C.POINTER(C.c_void_p)
-        L.bkid_shard_insert_partial.argtypes = [vp, i64p, i64p]
+        u64p = C.POINTER(C.c_uint64)
+        L.bkid_shard_insert_partial.argtypes = [vp, i64p, i64p, u64p, u64p]
+        L.bkid_sd_upper_binade.argtypes = [C.c_uint64] * 4
+        L.bkid_sd_upper_binade.restype = C.c_int
+        L.bkid_shard_sd_fast.argtypes = [vp, C.c_double, C.c_int32]
+        L.bkid_shard_sd_fast_collect.argtypes = [vp, u64p, u64p]
         L.bkid_shard_sd_prepare.argtypes = [vp, C.c_double]
         L.bkid_shard_sd_partial.argtypes = [vp, C.c_double, C.c_int64, i64p]
         L.bkid_shard_set_stats.argtypes = [vp, C.c_double, C.c_double]

@@ -5,15 +5,19 @@
 
 // slots (in 32-bit words) of the context's small device counter block `counters` (1 KB); 64-bit values are 8-byte aligned
 enum CounterSlot {
-  CS_SD_OUT = 8,        // sd_resolve: [0] total (i64), [1] out-of-regime flag (i64)
-  CS_SORT = 16,         // std::sort replay: active / terminal / small work-list sizes
+  CS_G = 0,             // K1 results: 6 x u64 (G_SUM .. G_SPAN), 16 words reserved
+  CS_SD_OUT = 16,       // sd_resolve: [0] total (i64), [1] out-of-regime flag (i64)
+  CS_SDF = 20,          // sd_fast: sum floor(a), E, out-of-regime (u64 x 3)
+  CS_SORT = 28,         // std::sort replay: active / terminal / small work-list sizes
   CS_TOTAL = 32,        // grand totals of the exclusive scans (u64 x 2)
-  CS_HASH_ERR = 40,     // mate join: a 64-bit name-hash run with differing high words
+  CS_HASH_ERR = 40,     // mate join: a mixed group beyond the fix-up cap
   CS_MAXSPAN = 44,      // max_span_kernel result
   CS_FATAL = 46,        // the reference's fatal "error cigar" condition was met
   CS_ROOTS = 48,        // AHC: number of final roots
-  CS_MISSING = 50,      // a candidate / SA record is missing from the sparse mate/name table
-  CS_DECODE = 52        // device decode: totals of the six per-chunk scans (u64 x 6)
+  CS_MISSING = 50,      // an SA record is missing from the sparse mate/name table
+  CS_DECODE = 52,       // device decode: totals of the six per-chunk scans (u64 x 6)
+  CS_NC = 64,           // number of candidates found through the sparse table (u32)
+  CS_XBAD = 65          // the sparse table is not strictly ascending / points outside the batch
 };
 
 struct Scratch {          // reusable device scratch for sorts / scans over `cap` elements
@@ -54,6 +58,10 @@ struct bkid_ctx {
   long long n = 0, cap_n = 0;
   bool borrowed = false;
   DBuf flag, mapq, tid, pos, isize, endpos, cls;
+  DBuf isize16, span16;                     // narrow forms of the insert-size / span columns (kept narrow in HBM when the batches have them)
+  int form_isize = 0, form_span = 0;        // 0 = undecided (empty context), 1 = wide (isize / endpos), 2 = narrow (isize16 / span16)
+  long long reserve_hint = 0;               // bkid_reserve on an empty context: applied once the column forms are known
+  const int16_t *p_isize16 = nullptr; const uint16_t *p_span16 = nullptr;
   long long n_x = 0;
   DBuf x_rec, x_mtid, x_mpos, x_nh;
   const uint16_t *p_flag = nullptr; const uint8_t *p_mapq = nullptr;
@@ -74,6 +82,10 @@ struct bkid_ctx {
   bool classified = false, have_stats = false, scanned = false, clustered = false, refined = false;
   double mean = 0, sd = 0;
   long long sum_abs = 0, cnt_insert = 0, sd_total = 0;
+  unsigned long long sum_sq = 0, xmax = 0;  // K1: sum of isize^2 and max |isize| over the insert records
+  long long n_cand_k1 = 0;                  // candidates counted by K1 (the sparse table must list every one of them)
+  int sd_kub = 0;                           // upper bound of the binade of the sd accumulator (sd_fast)
+  bool sd_fast_pending = false;
   DBuf tile_cand, counters, cand_idx, cand, bucket_rank_of;
   long long n_cand = 0;
   // pairs (stage 0)
@@ -592,7 +604,7 @@ void bkid_destroy(bkid_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
   decoder_free(c);
-  for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
+  for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->isize16, &c->span16, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->seq_off, &c->seq4, &c->seq_len, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
                   &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
@@ -609,8 +621,14 @@ void bkid_destroy(bkid_ctx *c)
   delete c;
 }
 
-static void invalidate(bkid_ctx *c) { if (c->sd_side_pending) { cudaStreamSynchronize(c->st2); c->sd_side_pending = false; } if (c->maxspan_pending) { cudaStreamSynchronize(c->st3); c->maxspan_pending = false; } c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; c->maxspan_cached = false; }
+static void invalidate(bkid_ctx *c)
+{
+  if (c->sd_side_pending || c->sd_fast_pending) { cudaStreamSynchronize(c->st2); c->sd_side_pending = false; c->sd_fast_pending = false; }
+  if (c->maxspan_pending) { cudaStreamSynchronize(c->st3); c->maxspan_pending = false; }
+  c->classified = c->have_stats = c->scanned = c->clustered = c->refined = false; c->sd_prepared = false; c->maxspan_cached = false;
+}
 
+// capacity for n records in the column forms the context currently has (an undecided form allocates nothing yet)
 static int reserve_impl(bkid_ctx *c, long long n, long long n_x, long long n_sa, long long n_cig, long long sa_b, long long oc_b)
 {
   cudaStream_t st = c->st;
@@ -618,7 +636,10 @@ static int reserve_impl(bkid_ctx *c, long long n, long long n_x, long long n_sa,
   size_t k = (size_t)c->n;
   TRY(c, c->flag.ensure((size_t)n * 2 + 64, k * 2, st)); TRY(c, c->mapq.ensure((size_t)n + 64, k, st));
   TRY(c, c->tid.ensure((size_t)n * 4 + 64, k * 4, st)); TRY(c, c->pos.ensure((size_t)n * 4 + 64, k * 4, st));
-  TRY(c, c->isize.ensure((size_t)n * 4 + 64, k * 4, st)); TRY(c, c->endpos.ensure((size_t)n * 4 + 64, k * 4, st));
+  if (c->form_isize == 1) TRY(c, c->isize.ensure((size_t)n * 4 + 64, k * 4, st));
+  if (c->form_isize == 2) TRY(c, c->isize16.ensure((size_t)n * 2 + 64, k * 2, st));
+  if (c->form_span == 1) TRY(c, c->endpos.ensure((size_t)n * 4 + 64, k * 4, st));
+  if (c->form_span == 2) TRY(c, c->span16.ensure((size_t)n * 2 + 64, k * 2, st));
   size_t kx = (size_t)c->n_x;
   TRY(c, c->x_rec.ensure((size_t)n_x * 4 + 64, kx * 4, st)); TRY(c, c->x_mtid.ensure((size_t)n_x * 4 + 64, kx * 4, st));
   TRY(c, c->x_mpos.ensure((size_t)n_x * 4 + 64, kx * 4, st)); TRY(c, c->x_nh.ensure((size_t)n_x * 16 + 64, kx * 16, st));
@@ -637,6 +658,7 @@ int bkid_reserve(bkid_ctx *c, int64_t n, int64_t n_x, int64_t n_sa, int64_t n_ci
 {
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device);
+  c->reserve_hint = std::max<long long>(c->reserve_hint, n);
   return reserve_impl(c, std::max<long long>(n, c->n), std::max<long long>(n_x, c->n_x), std::max<long long>(n_sa, c->n_sa), std::max<long long>(n_cig, c->n_cig),
                       std::max<long long>(sa_b, c->sa_bytes), std::max<long long>(oc_b, c->oc_bytes));
 }
@@ -670,11 +692,35 @@ __global__ void widen_tid_runs(const uint32_t *__restrict__ start, const int32_t
 static void set_ptrs(bkid_ctx *c)
 {
   c->p_flag = c->flag.as<uint16_t>(); c->p_mapq = c->mapq.as<uint8_t>(); c->p_tid = c->tid.as<int32_t>(); c->p_pos = c->pos.as<int32_t>();
-  c->p_isize = c->isize.as<int32_t>(); c->p_endpos = c->endpos.as<int32_t>();
+  c->p_isize = c->form_isize == 2 ? nullptr : c->isize.as<int32_t>(); c->p_isize16 = c->form_isize == 2 ? c->isize16.as<int16_t>() : nullptr;
+  c->p_endpos = c->form_span == 2 ? nullptr : c->endpos.as<int32_t>(); c->p_span16 = c->form_span == 2 ? c->span16.as<uint16_t>() : nullptr;
   c->p_x_rec = c->x_rec.as<uint32_t>(); c->p_x_mtid = c->x_mtid.as<int32_t>(); c->p_x_mpos = c->x_mpos.as<int32_t>(); c->p_x_nh = c->x_nh.as<uint64_t>();
   c->p_sa_rec = c->sa_rec.as<uint32_t>(); c->p_cig_off = c->cig_off.as<uint32_t>(); c->p_cig_ops = c->cig_ops.as<uint32_t>();
   c->p_seq_off = c->seq_off.as<uint32_t>(); c->p_seq4 = c->seq4.as<uint8_t>(); c->p_seq_len = c->seq_len.as<int32_t>();
   c->p_sa_off = c->sa_off.as<uint32_t>(); c->p_sa_txt = c->sa_txt.as<uint8_t>(); c->p_oc_off = c->oc_off.as<uint32_t>(); c->p_oc_txt = c->oc_txt.as<uint8_t>();
+}
+
+// The context keeps the insert-size and span columns in ONE form each.  An empty context adopts the form of its first batch;
+// a wide batch arriving at a narrow context widens the records already held (one pass), a narrow batch arriving at a wide
+// context is widened on the way in.  want = 1 wide, 2 narrow.
+static int settle_forms(bkid_ctx *c, int want_isize, int want_span, long long n_new)
+{
+  cudaStream_t st = c->st;
+  long long n0 = c->n;
+  size_t cap = (size_t)std::max<long long>(n0 + n_new, c->reserve_hint);
+  if (c->form_isize == 0) c->form_isize = want_isize;
+  else if (c->form_isize == 2 && want_isize == 1) {
+    TRY(c, c->isize.ensure(cap * 4 + 64, 0, st));
+    if (n0) BK_LAUNCH(widen_isize16, GRID1(n0, 256), 256, 0, st, c->isize16.as<int16_t>(), n0, c->isize.as<int32_t>());
+    c->form_isize = 1;
+  }
+  if (c->form_span == 0) c->form_span = want_span;
+  else if (c->form_span == 2 && want_span == 1) {
+    TRY(c, c->endpos.ensure(cap * 4 + 64, 0, st));
+    if (n0) BK_LAUNCH(widen_span16, GRID1(n0, 256), 256, 0, st, c->pos.as<int32_t>(), c->span16.as<uint16_t>(), n0, c->endpos.as<int32_t>());
+    c->form_span = 1;
+  }
+  return 0;
 }
 
 static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
@@ -698,13 +744,16 @@ static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
       CU(c, cudaMemcpy(&noc_b, b->oc_off + b->n_sa, 4, cudaMemcpyDeviceToHost));
     }
   }
-  TRY(c, reserve_impl(c, n0 + b->n, x0 + b->n_x, s0 + b->n_sa, c->n_cig + ncig, c->sa_bytes + nsa_b, c->oc_bytes + noc_b));
+  if (b->n > 0) TRY(c, settle_forms(c, b->isize ? 1 : 2, b->endpos ? 1 : 2, b->n));
+  TRY(c, reserve_impl(c, std::max<long long>(n0 + b->n, c->reserve_hint), x0 + b->n_x, s0 + b->n_sa, c->n_cig + ncig, c->sa_bytes + nsa_b, c->oc_bytes + noc_b));
   size_t n = (size_t)b->n;
   if (n) {
-    // Narrow encodings (staged in scratch) go first and are widened on a second stream, so that the widening kernels
-    // overlap the copies of the remaining columns instead of standing between them on the copy stream.
+    // Narrow columns that the context keeps narrow are plain copies.  Those it holds wide (and the tid runs, always) are
+    // staged in scratch and widened on a second stream, so that the widening kernels overlap the copies of the
+    // remaining columns instead of standing between them on the copy stream.
     cudaStream_t sw = c->st3;
-    size_t stage = (b->isize16 ? n * 2 : 0) + (b->span16 ? n * 2 : 0) + (b->tid ? 0 : (size_t)b->n_tid_runs * 8) + 64;
+    const bool widen_i = b->isize16 && !b->isize && c->form_isize == 1, widen_s = b->span16 && !b->endpos && c->form_span == 1;
+    size_t stage = (widen_i ? n * 2 : 0) + (widen_s ? n * 2 : 0) + (b->tid ? 0 : (size_t)b->n_tid_runs * 8) + 64;
     TRY(c, c->tmpH.ensure(stage, 0, st));
     char *sp = (char *)c->tmpH.p;
     bool widened = false;
@@ -718,7 +767,8 @@ static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
       BK_LAUNCH(widen_tid_runs, GRID1(n, 256), 256, 0, sw, rs, rt, (int)b->n_tid_runs, (long long)n, c->tid.as<int32_t>() + n0);
       widened = true;
     }
-    if (b->isize) CU(c, cudaMemcpyAsync(c->isize.as<int32_t>() + n0, b->isize, n * 4, kind, st));
+    if (c->form_isize == 2) CU(c, cudaMemcpyAsync(c->isize16.as<int16_t>() + n0, b->isize16, n * 2, kind, st));
+    else if (b->isize) CU(c, cudaMemcpyAsync(c->isize.as<int32_t>() + n0, b->isize, n * 4, kind, st));
     else {
       int16_t *s16 = (int16_t *)sp; sp += n * 2;
       CU(c, cudaMemcpyAsync(s16, b->isize16, n * 2, kind, st));
@@ -727,7 +777,8 @@ static int push_impl(bkid_ctx *c, const bkid_batch *b, cudaMemcpyKind kind)
       widened = true;
     }
     CU(c, cudaMemcpyAsync(c->pos.as<int32_t>() + n0, b->pos, n * 4, kind, st));
-    if (b->endpos) CU(c, cudaMemcpyAsync(c->endpos.as<int32_t>() + n0, b->endpos, n * 4, kind, st));
+    if (c->form_span == 2) CU(c, cudaMemcpyAsync(c->span16.as<uint16_t>() + n0, b->span16, n * 2, kind, st));
+    else if (b->endpos) CU(c, cudaMemcpyAsync(c->endpos.as<int32_t>() + n0, b->endpos, n * 4, kind, st));
     else {
       uint16_t *e16 = (uint16_t *)sp; sp += n * 2;
       CU(c, cudaMemcpyAsync(e16, b->span16, n * 2, kind, st));
@@ -793,15 +844,18 @@ int bkid_push_batch_device(bkid_ctx *c, const bkid_batch *b)
 {
   if (!c || !b) return BKID_ERR_ARG;
   if (c->n == 0 && !c->borrowed && c->flag.p == nullptr) {
-    // adopt the caller's device columns without copying (already-resident input)
+    // adopt the caller's device columns without copying (already-resident input), in whichever form they are
     cudaSetDevice(c->device);
     if ((unsigned long long)b->n >= 0xffffffffull) return fail(c, BKID_ERR_ARG, "more than 2^32-1 records per context");
-    if (b->n > 0 && (!b->tid || !b->isize || !b->endpos)) return fail(c, BKID_ERR_ARG, "bkid_push_batch_device needs the wide tid / isize / endpos columns");
+    if (b->n > 0 && (!b->tid || (!b->isize && !b->isize16) || (!b->endpos && !b->span16)))
+      return fail(c, BKID_ERR_ARG, "bkid_push_batch_device needs tid and the insert-size / span columns (wide or narrow) resident on the device");
     invalidate(c);
     c->borrowed = true;
     c->n = b->n; c->n_sa = b->n_sa; c->n_x = b->n_x;
     c->p_flag = b->flag; c->p_mapq = b->mapq; c->p_tid = b->tid; c->p_pos = b->pos;
-    c->p_isize = b->isize; c->p_endpos = b->endpos;
+    c->p_isize = b->isize; c->p_isize16 = b->isize ? nullptr : b->isize16;
+    c->p_endpos = b->endpos; c->p_span16 = b->endpos ? nullptr : b->span16;
+    c->form_isize = b->isize ? 1 : 2; c->form_span = b->endpos ? 1 : 2;
     c->p_x_rec = b->x_rec; c->p_x_mtid = b->x_mtid; c->p_x_mpos = b->x_mpos; c->p_x_nh = b->x_name_hash;
     c->p_sa_rec = b->sa_rec; c->p_cig_off = b->cig_off; c->p_cig_ops = b->cig_ops; c->p_sa_off = b->sa_off; c->p_sa_txt = b->sa_txt;
     c->p_oc_off = b->oc_off; c->p_oc_txt = b->oc_txt;
@@ -816,11 +870,12 @@ int bkid_reset(bkid_ctx *c)
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
+  invalidate(c);
   c->n = c->n_x = c->n_sa = c->n_cig = c->sa_bytes = c->oc_bytes = 0;
   c->seq_bytes = 0; c->have_seq = false;
   c->borrowed = false;
+  c->form_isize = c->form_span = 0;         // the next first batch decides again (allocations are kept)
   set_ptrs(c);
-  invalidate(c);
   memset(&c->tm, 0, sizeof c->tm);
   c->launches0 = g_bk_launches;
   return 0;
@@ -847,6 +902,8 @@ int bkid_set_exclude(bkid_ctx *c, int64_t n_iv, const int32_t *tid, const int32_
   return 0;
 }
 
+static ISizeCol isize_col(const bkid_ctx *c) { return ISizeCol{c->p_isize, c->p_isize16}; }
+
 static int classify_impl(bkid_ctx *c)
 {
   if (c->classified) return 0;
@@ -854,41 +911,63 @@ static int classify_impl(bkid_ctx *c)
   long long n = c->n;
   int ntiles = div_up(std::max<long long>(n, 1), K1_TILE);
   TRY(c, c->cls.ensure((size_t)n + 64, 0, st));
-  TRY(c, c->tile_cand.ensure((size_t)(ntiles + 1) * 4 * 2 + 64, 0, st));
-  unsigned long long *g = (unsigned long long *)c->counters.as<unsigned>();     // [0] sum |isize|, [1] count
+  unsigned long long *g = (unsigned long long *)(c->counters.as<unsigned>() + CS_G);
   CU(c, cudaMemsetAsync(g, 0, 64, st));
   cudaEventRecord(c->ev[2], st);
-  if (n > 0)
-    BK_LAUNCH(k1_classify, (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, n, c->prm.qual, c->cls.as<uint8_t>(), c->tile_cand.as<uint32_t>(), g, g + 1);
+  const bool i16 = c->p_isize16 != nullptr, s16 = c->p_span16 != nullptr;
+  if (n > 0) {
+    uint8_t *cls = c->cls.as<uint8_t>();
+    if (i16 && s16) BK_LAUNCH((k1_classify<true, true>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, g);
+    else if (i16) BK_LAUNCH((k1_classify<true, false>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, g);
+    else if (s16) BK_LAUNCH((k1_classify<false, true>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, g);
+    else BK_LAUNCH((k1_classify<false, false>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, g);
+  }
   cudaEventRecord(c->ev[3], st);
   int n_iv = (int)(c->ex_iv.size() / 3);
   c->n_excluded = 0;
+  unsigned long long ne = 0;
   if (n_iv > 0 && n > 0) {
     TRY(c, c->ex_tab.ensure((size_t)n_iv * 12 + 64, 0, st)); TRY(c, c->ex_lo.ensure((size_t)n_iv * 4 + 64, 0, st));
     TRY(c, c->ex_len.ensure((size_t)n_iv * 4 + 64, 0, st)); TRY(c, c->ex_pre.ensure((size_t)(n_iv + 1) * 8 + 64, 0, st));
     CU(c, cudaMemcpyAsync(c->ex_tab.p, c->ex_iv.data(), (size_t)n_iv * 12, cudaMemcpyHostToDevice, st));
     BK_LAUNCH(ex_ranges, GRID1(n_iv, 128), 128, 0, st, c->p_tid, c->p_pos, n, c->ex_tab.as<int32_t>(), n_iv, c->ex_lo.as<uint32_t>(), c->ex_len.as<uint32_t>());
     BK_LAUNCH(ex_prefix, 1, 32, 0, st, c->ex_len.as<uint32_t>(), n_iv, c->ex_pre.as<unsigned long long>());
-    BK_LAUNCH(ex_apply, 148 * 8, 256, 0, st, c->ex_lo.as<uint32_t>(), c->ex_pre.as<unsigned long long>(), n_iv, c->p_isize, c->cls.as<uint8_t>(), c->tile_cand.as<uint32_t>(), g, g + 1);
-    unsigned long long ne = 0;
+    BK_LAUNCH(ex_apply, 148 * 8, 256, 0, st, c->ex_lo.as<uint32_t>(), c->ex_pre.as<unsigned long long>(), n_iv, isize_col(c), c->cls.as<uint8_t>(), g);
     CU(c, cudaMemcpyAsync(&ne, c->ex_pre.as<unsigned long long>() + n_iv, 8, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-    c->n_excluded = (long long)ne;
   }
-  unsigned long long h[2] = {0, 0};
-  CU(c, cudaMemcpyAsync(h, g, 16, cudaMemcpyDeviceToHost, st));
+  unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+  CU(c, cudaMemcpyAsync(h, g, 48, cudaMemcpyDeviceToHost, st));
   TRY(c, sync_check(c));
+  c->n_excluded = (long long)ne;
   float ms = 0; cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
   c->tm.classify = ms;
-  c->sum_abs = (long long)h[0]; c->cnt_insert = (long long)h[1];
+  c->sum_abs = (long long)h[G_SUM]; c->cnt_insert = (long long)h[G_CNT]; c->sum_sq = h[G_SQ]; c->n_cand_k1 = (long long)h[G_CAND]; c->xmax = h[G_XMAX];
+  if (s16) { c->maxspan = (int)h[G_SPAN] + 1; c->maxspan_cached = true; }    // the narrow span column was read by K1 anyway
   c->classified = true;
   c->tm.n_records = n;
   return 0;
 }
 
-// exact continuation of the truncating sd accumulator over the local records, starting from t_in:
+// Upper bound K of the binade of the truncating sd accumulator (sd_fast): the final total is at most
+// sum (x - mean)^2 + N (every element adds floor(a) and at most 1), and sum (x - S/N)^2 = (N sum x^2 - S^2) / N exactly.
+// The slack covers the rounding of the mean, of the per-element products and the division.  51 = no useful bound
+// (the sum of squares may have wrapped): every correction candidate then counts and the general path decides.
+static int sd_upper_binade(unsigned long long sum_abs, unsigned long long cnt, unsigned long long sum_sq, unsigned long long xmax)
+{
+  if (cnt == 0) return 0;
+  if (xmax > 65535ull) return 51;
+  unsigned __int128 V = (unsigned __int128)sum_sq * cnt - (unsigned __int128)sum_abs * sum_abs;
+  unsigned __int128 T = V / cnt + 1;
+  T += (T >> 30) + 2 * (unsigned __int128)cnt + 1024;
+  if (T >> 51) return 51;
+  int k = 0;
+  while ((T >> (k + 1)) != 0) ++k;
+  return k;
+}
+
+// exact continuation of the truncating sd accumulator over the local records, starting from t_in (GENERAL path):
 // sd_prepare = the streaming pass that builds the per-block tables (independent of t_in),
-// sd_resolve_impl = the single-CTA exact walk from t_in.
+// sd_partial_impl = the single-CTA exact walk from t_in.
 static int sd_prepare_impl(bkid_ctx *c, double mean, cudaStream_t st = nullptr)
 {
   if (!st) st = c->st;
@@ -904,12 +983,11 @@ static int sd_prepare_impl(bkid_ctx *c, double mean, cudaStream_t st = nullptr)
   uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
   uint32_t *blkN = (uint32_t *)bp;
   BK_LAUNCH(sd_build_lut, SD_LUT / 256, 256, 0, st, mean, c->sdlut.as<unsigned long long>());
-  BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, c->sdlut.as<unsigned long long>(), blkF, blkCum, blkN, blkA);
+  BK_LAUNCH(sd_block_stats, (unsigned)nb, SD_THREADS, 0, st, c->cls.as<uint8_t>(), isize_col(c), n, mean, c->sdlut.as<unsigned long long>(), blkF, blkCum, blkN, blkA);
   c->sd_prepared = true; c->sd_mean = mean;
   return 0;
 }
 
-static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *t_out);
 static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *t_out)
 {
   cudaStream_t st = c->st;
@@ -926,13 +1004,13 @@ static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *
   uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
   uint32_t *blkN = (uint32_t *)bp;
   long long *out = (long long *)(c->counters.as<unsigned>() + CS_SD_OUT);
-  BK_LAUNCH(sd_resolve, 1, SDR_T, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, nb, blkF, blkCum, blkN, blkA, t_in, out);
+  BK_LAUNCH(sd_resolve, 1, SDR_T, SD_BLOCK * 9, st, c->cls.as<uint8_t>(), isize_col(c), n, mean, nb, blkF, blkCum, blkN, blkA, t_in, out);
   T_.mark("sd: resolve");
   long long h[2] = {0, 0};
   CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
   TRY(c, sync_check(c));
   if (h[1]) {                                                              // total left the closed-form regime: literal replay
-    BK_LAUNCH(sd_sequential, 1, 1, 0, st, c->cls.as<uint8_t>(), c->p_isize, n, mean, t_in, out);
+    BK_LAUNCH(sd_sequential, 1, 1, 0, st, c->cls.as<uint8_t>(), isize_col(c), n, mean, t_in, out);
     CU(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, st));
     TRY(c, sync_check(c));
   }
@@ -940,51 +1018,69 @@ static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *
   return 0;
 }
 
-// side-stream version used by bkid_run: launch the sd replay and the max-span reduction on st2 so that they
-// overlap the distance-independent half of the join, collect later
+// the one-pass form: launch on `st`, results in the counter block (collected by sd_fast_collect)
+static int sd_fast_launch(bkid_ctx *c, double mean, int kub, cudaStream_t st)
+{
+  long long n = c->n;
+  unsigned long long *out = (unsigned long long *)(c->counters.as<unsigned>() + CS_SDF);
+  CU(c, cudaMemsetAsync(out, 0, 24, st));
+  c->sd_kub = kub;
+  if (n <= 0 || c->cnt_insert <= 0) return 0;
+  double thr = 1.0 - ldexp(1.0, kub - 53);                                    // corrections need frac(a) >= 1 - 2^(k-53), k <= kub
+  if (c->p_isize16) BK_LAUNCH((sd_fast<true>), 148 * 16, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
+  else BK_LAUNCH((sd_fast<false>), 148 * 16, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
+  return 0;
+}
+// F = sum floor(a), E = elements that could need a correction; exact iff E == 0 (and not out of regime: *E = ~0)
+static int sd_fast_collect(bkid_ctx *c, cudaStream_t st, unsigned long long *F, unsigned long long *E)
+{
+  unsigned long long h[3] = {0, 0, 0};
+  CU(c, cudaMemcpyAsync(h, c->counters.as<unsigned>() + CS_SDF, 24, cudaMemcpyDeviceToHost, st));
+  CU(c, cudaStreamSynchronize(st));
+  CU(c, cudaGetLastError());
+  *F = h[0]; *E = h[2] ? ~0ull : h[1];
+  if (c->sd_kub >= 51 && c->cnt_insert > 0) *E = ~0ull;                        // no useful binade bound: let the general path decide
+  return 0;
+}
+
+// side-stream version used by bkid_run: launch the sd pass (and, for a wide span column, the max-span reduction) so
+// that they overlap candidate extraction and the join's sort; collected before the discordance test needs the distance
 static int side_launch(bkid_ctx *c)
 {
   cudaStream_t s2 = c->st2;
   long long n = c->n;
   c->mean = (double)c->sum_abs / (double)c->cnt_insert;                       // src/BreakID.cc:1941
   cudaEventRecord(c->ev_side[0], s2);
-  if (n > 0 && c->cnt_insert > 0) {
-    TRY(c, sd_prepare_impl(c, c->mean, s2));
-    int nb = div_up(std::max<long long>(n, 1), SD_BLOCK);
-    char *bp = (char *)c->sdtab.p;
-    long long *blkF = (long long *)bp; bp += (size_t)nb * 8;
-    double *blkA = (double *)bp; bp += (size_t)nb * 8;
-    uint32_t *blkCum = (uint32_t *)bp; bp += (size_t)nb * SD_K * 4;
-    uint32_t *blkN = (uint32_t *)bp;
-    long long *out = (long long *)(c->counters.as<unsigned>() + CS_SD_OUT);
-    BK_LAUNCH(sd_resolve, 1, SDR_T, SD_BLOCK * 9, s2, c->cls.as<uint8_t>(), c->p_isize, n, c->mean, nb, blkF, blkCum, blkN, blkA, 0ll, out);
-  }
+  TRY(c, sd_fast_launch(c, c->mean, sd_upper_binade((unsigned long long)c->sum_abs, (unsigned long long)c->cnt_insert, c->sum_sq, c->xmax), s2));
   cudaEventRecord(c->ev_side[1], s2);
-  // the max reference span bounds the region-query windows of the refinement only: its own stream, collected there
-  int *mx = (int *)(c->counters.as<unsigned>() + CS_MAXSPAN);
-  CU(c, cudaMemsetAsync(mx, 0, 4, c->st3));
-  if (n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, c->st3, c->p_pos, c->p_endpos, n, mx);
-  c->maxspan_pending = true;
+  c->sd_fast_pending = true;
+  if (!c->maxspan_cached) {
+    // the max reference span bounds the region-query windows of the refinement only: its own stream, collected there
+    int *mx = (int *)(c->counters.as<unsigned>() + CS_MAXSPAN);
+    CU(c, cudaMemsetAsync(mx, 0, 4, c->st3));
+    if (n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, c->st3, c->p_pos, c->p_endpos, n, mx);
+    c->maxspan_pending = true;
+  }
   return 0;
 }
 
 static int side_collect(bkid_ctx *c)
 {
-  cudaStream_t s2 = c->st2;
-  long long n = c->n;
-  long long h[2] = {0, 0};
-  if (n > 0 && c->cnt_insert > 0) CU(c, cudaMemcpyAsync(h, c->counters.as<unsigned>() + CS_SD_OUT, 16, cudaMemcpyDeviceToHost, s2));
-  CU(c, cudaStreamSynchronize(s2));
-  CU(c, cudaGetLastError());
-  if (h[1]) {                                                                 // left the closed-form regime: literal replay
-    long long t = 0;
-    c->sd_prepared = false;
-    TRY(c, sd_partial_impl(c, c->mean, 0, &t));
-    h[0] = t;
-  }
+  unsigned long long F = 0, E = 0;
+  TRY(c, sd_fast_collect(c, c->st2, &F, &E));
+  c->sd_fast_pending = false;
   float ms = 0; cudaEventElapsedTime(&ms, c->ev_side[0], c->ev_side[1]);
+  long long total = (long long)F;
+  if (E != 0 && c->n > 0 && c->cnt_insert > 0) {                              // some element may need a correction: exact replay (general path)
+    cudaEventRecord(c->ev[4], c->st);
+    TRY(c, sd_partial_impl(c, c->mean, 0, &total));
+    cudaEventRecord(c->ev[5], c->st);
+    TRY(c, sync_check(c));
+    float ms2 = 0; cudaEventElapsedTime(&ms2, c->ev[4], c->ev[5]);
+    ms += ms2;
+  }
   c->tm.insert_stats = ms;
-  c->sd_total = h[0];
+  c->sd_total = total;
   c->sd = sqrt((double)c->sd_total / (double)c->cnt_insert);                  // :1946
   c->have_stats = true;
   return 0;
@@ -1011,8 +1107,14 @@ int bkid_insert_stats(bkid_ctx *c, double *mean, double *sd)
     cudaStream_t st = c->st;
     c->mean = (double)c->sum_abs / (double)c->cnt_insert;                     // src/BreakID.cc:1941
     cudaEventRecord(c->ev[4], st);
-    long long t = 0;
-    TRY(c, sd_partial_impl(c, c->mean, 0, &t));
+    unsigned long long F = 0, E = 0;
+    const bool general_only = getenv("BKID_SD_GENERAL") != nullptr;           // tests: force the block-table / resolver path
+    if (!general_only) {
+      TRY(c, sd_fast_launch(c, c->mean, sd_upper_binade((unsigned long long)c->sum_abs, (unsigned long long)c->cnt_insert, c->sum_sq, c->xmax), st));
+      TRY(c, sd_fast_collect(c, st, &F, &E));
+    }
+    long long t = (long long)F;
+    if ((general_only || E != 0) && c->n > 0 && c->cnt_insert > 0) TRY(c, sd_partial_impl(c, c->mean, 0, &t));
     cudaEventRecord(c->ev[5], st);
     TRY(c, sync_check(c));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
@@ -1027,92 +1129,101 @@ int bkid_insert_stats(bkid_ctx *c, double *mean, double *sd)
 }
 
 // ---- scan, in three reusable pieces (the multi-GPU path runs them around two exchanges) -------------
-// (1) local candidates in file order -> c->cand
-static int extract_candidates(bkid_ctx *c, unsigned long long index_offset)
+// (1) local candidates in file order -> c->cand, straight from the sparse mate/name table (no host round trip: the
+// count stays on the device in CS_NC; K1's count n_cand_k1 sizes everything and is checked against it later).
+// with_keys: also write the join's (name_lo, index) sort pairs.
+static int extract_candidates(bkid_ctx *c, unsigned long long index_offset, bool with_keys)
 {
   TRY(c, classify_impl(c));
   cudaStream_t st = c->st;
-  long long n = c->n;
-  int ntiles = div_up(std::max<long long>(n, 1), K1_TILE);
-  uint32_t *tile_cand = c->tile_cand.as<uint32_t>(), *tile_off = tile_cand + ntiles + 1;
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
-  TRY(c, c->sc.ensure(ntiles + 8, st));
-  unsigned long long nc = 0;
-  if (n > 0) {
-    bk::exclusive_scan<uint32_t, uint32_t>(tile_cand, tile_off, ntiles, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-    CU(c, cudaMemcpyAsync(&nc, tot, 8, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-  }
-  c->n_cand = (long long)nc;
-  TRY(c, c->cand.ensure((size_t)(nc + 1) * sizeof(bkid_cand), 0, st));
-  if (nc > 0) {
-    TRY(c, c->cand_idx.ensure((size_t)nc * 4 + 64, 0, st));
-    BK_LAUNCH(k1_compact, (unsigned)ntiles, K1_THREADS, 0, st, c->cls.as<uint8_t>(), n, tile_off, c->cand_idx.as<uint32_t>());
-    int *miss = (int *)(c->counters.as<unsigned>() + CS_MISSING);
-    CU(c, cudaMemsetAsync(miss, 0, 4, st));
-    BK_LAUNCH(k2_gather_cand, GRID1(nc, 256), 256, 0, st, c->cand_idx.as<uint32_t>(), (long long)nc, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_x_rec, c->n_x,
-              c->p_x_mtid, c->p_x_mpos, c->p_x_nh, index_offset, c->cand.as<bkid_cand>(), miss);
-    int hm = 0;
-    CU(c, cudaMemcpyAsync(&hm, miss, 4, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-    if (hm) return fail(c, BKID_ERR_ARG, "a discordant-scan candidate is missing from the sparse mate/name table (x_rec must list every record that is not a proper pair)");
-  }
+  long long n = c->n, nx = c->n_x;
+  long long cap = std::min<long long>(c->n_cand_k1, nx);      // every candidate is listed: more than n_x cannot be found
+  c->n_cand = cap;
+  unsigned *cs = c->counters.as<unsigned>();
+  CU(c, cudaMemsetAsync(cs + CS_NC, 0, 8, st));
+  TRY(c, c->cand.ensure((size_t)(cap + 1) * sizeof(bkid_cand), 0, st));
+  if (nx <= 0 || n <= 0) return 0;
+  int ntiles = div_up(nx, KX_TILE);
+  TRY(c, c->sc.ensure(std::max<long long>(cap, ntiles) + 8, st));
+  TRY(c, c->tile_cand.ensure((size_t)(ntiles + 1) * 4 * 2 + 64, 0, st));
+  uint32_t *tile_cnt = c->tile_cand.as<uint32_t>(), *tile_off = tile_cnt + ntiles + 1;
+  unsigned long long *tot = (unsigned long long *)(cs + CS_TOTAL);
+  BK_LAUNCH(kx_count, (unsigned)ntiles, KX_THREADS, 0, st, c->p_x_rec, nx, c->cls.as<uint8_t>(), n, tile_cnt, (int *)(cs + CS_XBAD));
+  bk::exclusive_scan<uint32_t, uint32_t>(tile_cnt, tile_off, ntiles, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+  CU(c, cudaMemcpyAsync(cs + CS_NC, tot, 4, cudaMemcpyDeviceToDevice, st));
+  if (cap > 0)     // a table that lists more candidates than K1 counted cannot exist (same predicate, same class bytes)
+    BK_LAUNCH(kx_write, (unsigned)ntiles, KX_THREADS, 0, st, c->p_x_rec, nx, c->cls.as<uint8_t>(), n, tile_off, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_x_mtid, c->p_x_mpos, c->p_x_nh,
+              index_offset, c->cand.as<bkid_cand>(), with_keys ? c->sc.keys.as<uint64_t>() : (uint64_t *)nullptr, c->sc.vals.as<uint32_t>());
+  return 0;
+}
+// the deferred check of (1): called at the next host synchronisation
+static int check_candidates(bkid_ctx *c, const unsigned *h_nc_bad)
+{
+  if (h_nc_bad[1]) return fail(c, BKID_ERR_ARG, "the sparse mate/name table is not strictly ascending or points outside the batch (x_rec)");
+  if ((long long)h_nc_bad[0] != c->n_cand_k1)
+    return fail(c, BKID_ERR_ARG, "a discordant-scan candidate is missing from the sparse mate/name table (x_rec must list every record that is not a proper pair)");
   return 0;
 }
 
-// (2) mate join on a candidate array that is in global file order -> unordered pairs in c->pairs_tmp.
-// join_presort needs no distance (sort by name hash, run detection); join_emit applies the discordance test.
-static int join_presort(bkid_ctx *c, const bkid_cand *cand, long long nc)
+// (2) mate join on a candidate array that is in global file order -> pairs in emission order in c->pairs_tmp.
+// join_presort needs no distance (sort on 32 bits of the name hash); join_emit applies the discordance test.
+// nc_dev: exact candidate count on the device (or nullptr: nc is exact).
+static int join_presort(bkid_ctx *c, const bkid_cand *cand, long long nc, const uint32_t *nc_dev, bool keys_ready)
 {
   cudaStream_t st = c->st;
   if (nc <= 0) return 0;
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
   TRY(c, c->sc.ensure(nc + 8, st));
   uint64_t *key = c->sc.keys.as<uint64_t>();
   uint32_t *val = c->sc.vals.as<uint32_t>();
-  BK_LAUNCH(k2_cand_keys, GRID1(nc, 256), 256, 0, st, cand, nc, key, val);
-  bk::radix_sort_pairs(key, val, nc, 0, 64, c->sc.rt(), st);
-  uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
-  int *errf = (int *)(c->counters.as<unsigned>() + CS_HASH_ERR);
-  CU(c, cudaMemsetAsync(errf, 0, 4, st));
-  BK_LAUNCH(k2_run_heads, GRID1(nc, 256), 256, 0, st, key, val, nc, cand, head, errf);
-  bk::exclusive_scan<uint32_t, uint32_t>(head, hex, nc, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-  BK_LAUNCH(k2_run_starts, GRID1(nc, 256), 256, 0, st, head, hex, nc, rstart);
+  if (!keys_ready) BK_LAUNCH(k2_cand_keys, GRID1(nc, 256), 256, 0, st, cand, nc, key, val);
+  if (bk::radix_sort_pairs(key, val, nc, 0, 32, c->sc.rt(), st, nc_dev) < 0) return fail(c, BKID_ERR_ARG, "more than 2^30 candidates");
   size_t maxp = (size_t)nc / 2 + 1;
   TRY(c, c->pairs_tmp.ensure(maxp * sizeof(bkid_pair), 0, st));
   return 0;
 }
 
-static int join_emit(bkid_ctx *c, const bkid_cand *cand, long long nc, double w, long long *np_out)
+static int join_emit(bkid_ctx *c, const bkid_cand *cand, long long nc, const uint32_t *nc_dev, double w, bool check_table, long long *np_out)
 {
   cudaStream_t st = c->st;
   *np_out = 0;
-  if (nc <= 0) return 0;
-  unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
+  unsigned *cs = c->counters.as<unsigned>();
+  unsigned long long *tot = (unsigned long long *)(cs + CS_TOTAL);
+  uint64_t *key = c->sc.keys.as<uint64_t>();
   uint32_t *val = c->sc.vals.as<uint32_t>();
-  uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *rstart = c->sc.c32.as<uint32_t>();
-  int *errf = (int *)(c->counters.as<unsigned>() + CS_HASH_ERR);
-  unsigned long long *pcount = tot + 1;
-  CU(c, cudaMemsetAsync(pcount, 0, 8, st));
-  BK_LAUNCH(k2_emit_pairs, GRID1(nc, 256), 256, 0, st, val, head, hex, rstart, nc, cand, c->d_cum.as<uint32_t>(), c->nt, c->d_bucket_rank.as<int32_t>(), w,
-            c->pairs_tmp.as<bkid_pair>(), pcount);
-  unsigned long long np = 0; int herr = 0;
-  CU(c, cudaMemcpyAsync(&np, pcount, 8, cudaMemcpyDeviceToHost, st));
-  CU(c, cudaMemcpyAsync(&herr, errf, 4, cudaMemcpyDeviceToHost, st));
-  TRY(c, sync_check(c));
-  if (herr) return fail(c, BKID_ERR_HASH, "two different read names share a 64-bit hash prefix");
+  uint32_t *flag = c->sc.a32.as<uint32_t>(), *off = c->sc.b32.as<uint32_t>(), *mate = c->sc.c32.as<uint32_t>();
+  int *big = (int *)(cs + CS_HASH_ERR);
+  unsigned long long np = 0; int hbig = 0; unsigned hnc[2] = {0, 0};
+  for (int attempt = 0; attempt < 2 && nc > 0; ++attempt) {
+    CU(c, cudaMemsetAsync(big, 0, 4, st));
+    CU(c, cudaMemsetAsync(mate, 0xff, (size_t)nc * 4, st));
+    // attempt 0: groups = equal low 32 bits of the name hash, mixed groups up to 64 records are put in order in place;
+    // attempt 1 (a larger mixed group exists): the remaining 32 bits are sorted too, groups = equal name_lo
+    if (attempt == 1 && bk::radix_sort_pairs(key, val, nc, 32, 64, c->sc.rt(), st, nc_dev) < 0) return fail(c, BKID_ERR_ARG, "more than 2^30 candidates");
+    BK_LAUNCH(k2_join, GRID1(nc, 256), 256, 0, st, key, val, nc_dev, (uint32_t)nc, cand, attempt == 0 ? 32 : 64, attempt == 0 ? 64u : 4096u, w, mate, big);
+    BK_LAUNCH(k2_mate_flags, GRID1(nc, 256), 256, 0, st, mate, nc, flag);
+    bk::exclusive_scan<uint32_t, uint32_t>(flag, off, nc, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    BK_LAUNCH(k2_build_pairs, GRID1(nc, 256), 256, 0, st, mate, off, nc, cand, c->d_cum.as<uint32_t>(), c->nt, c->d_bucket_rank.as<int32_t>(), c->pairs_tmp.as<bkid_pair>());
+    CU(c, cudaMemcpyAsync(&np, tot, 8, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(&hbig, big, 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(hnc, cs + CS_NC, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    if (!hbig) break;
+    if (attempt == 1) return fail(c, BKID_ERR_HASH, "more than 4096 records share a 64-bit read-name hash without sharing the name");
+  }
+  if (check_table) { if (nc <= 0) { CU(c, cudaMemcpyAsync(hnc, cs + CS_NC, 8, cudaMemcpyDeviceToHost, st)); TRY(c, sync_check(c)); } TRY(c, check_candidates(c, hnc)); }
   *np_out = (long long)np;
   return 0;
 }
 
 static int join_candidates(bkid_ctx *c, const bkid_cand *cand, long long nc, double w, long long *np_out)
 {
-  TRY(c, join_presort(c, cand, nc));
-  return join_emit(c, cand, nc, w, np_out);
+  TRY(c, join_presort(c, cand, nc, nullptr, false));
+  return join_emit(c, cand, nc, nullptr, w, false, np_out);
 }
 
-// (3) order pairs by (bucket rank, index of the second-seen mate), build buckets -> c->pairs0 ...
-static int set_pairs(bkid_ctx *c, const bkid_pair *pairs, long long np)
+// (3) group the pairs by bucket, build buckets -> c->pairs0 ...  ordered: the pairs arrive in emission order (one GPU's
+// join) and only need the stable grouping by bucket rank; otherwise they are ordered by (bucket rank, second-mate index)
+static int set_pairs(bkid_ctx *c, const bkid_pair *pairs, long long np, bool ordered)
 {
   cudaStream_t st = c->st;
   c->np0 = np; c->nb = 0;
@@ -1122,9 +1233,9 @@ static int set_pairs(bkid_ctx *c, const bkid_pair *pairs, long long np)
   TRY(c, c->pairs0.ensure((size_t)np * sizeof(bkid_pair), 0, st));
   unsigned long long *pkey = (unsigned long long *)c->sc.keys.as<uint64_t>();
   uint32_t *pslot = c->sc.vals.as<uint32_t>();
-  BK_LAUNCH(k2_pair_keys, GRID1(np, 256), 256, 0, st, pairs, np, pkey, pslot);
+  BK_LAUNCH(k2_pair_keys, GRID1(np, 256), 256, 0, st, pairs, np, ordered ? 1 : 0, pkey, pslot);
   int rbits = 1; while ((1ll << rbits) < (long long)(c->nt + 1) * (c->nt + 1) + 1) ++rbits;
-  bk::radix_sort_pairs((uint64_t *)pkey, pslot, np, 0, PAIR_IDX_BITS + rbits, c->sc.rt(), st);
+  if (bk::radix_sort_pairs((uint64_t *)pkey, pslot, np, ordered ? PAIR_IDX_BITS : 0, PAIR_IDX_BITS + rbits, c->sc.rt(), st) < 0) return fail(c, BKID_ERR_ARG, "more than 2^30 pairs");
   uint32_t *bh = c->sc.a32.as<uint32_t>(), *bhx = c->sc.b32.as<uint32_t>();
   BK_LAUNCH(k2_gather_pairs, GRID1(np, 256), 256, 0, st, pairs, pslot, pkey, np, c->pairs0.as<bkid_pair>(), bh);
   bk::exclusive_scan<uint32_t, uint32_t>(bh, bhx, np, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
@@ -1150,11 +1261,13 @@ int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
   cudaStream_t st = c->st;
   TRY(c, classify_impl(c));
   cudaEventRecord(c->ev[6], st);
-  TRY(c, extract_candidates(c, 0ull));
+  TRY(c, extract_candidates(c, 0ull, true));
   long long np = 0;
-  TRY(c, join_candidates(c, c->cand.as<bkid_cand>(), c->n_cand, w, &np));
+  const uint32_t *nc_dev = c->counters.as<unsigned>() + CS_NC;
+  TRY(c, join_presort(c, c->cand.as<bkid_cand>(), c->n_cand, nc_dev, true));
+  TRY(c, join_emit(c, c->cand.as<bkid_cand>(), c->n_cand, nc_dev, w, true, &np));
   cudaEventRecord(c->ev[7], st);
-  TRY(c, set_pairs(c, c->pairs_tmp.as<bkid_pair>(), np));
+  TRY(c, set_pairs(c, c->pairs_tmp.as<bkid_pair>(), np, true));
   cudaEventRecord(c->ev[8], st);
   TRY(c, sync_check(c));
   float ms = 0;
@@ -1251,7 +1364,7 @@ static int refine_build_rows(bkid_ctx *c)
     int *miss = (int *)(c->counters.as<unsigned>() + CS_MISSING);
     CU(c, cudaMemsetAsync(miss, 0, 4, st));
     if (c->n_sa > 0) {
-      BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->cls.as<uint8_t>(), c->p_flag, c->p_tid, c->p_pos, c->p_endpos, c->p_x_rec, c->n_x, c->p_x_nh, miss,
+      BK_LAUNCH(k7_evidence_rows, GRID1(c->n_sa, 128), 128, 0, st, c->p_sa_rec, c->n_sa, c->cls.as<uint8_t>(), c->p_flag, c->p_tid, c->p_pos, c->p_endpos, c->p_span16, c->p_x_rec, c->n_x, c->p_x_nh, miss,
                 c->p_cig_off, c->p_cig_ops, c->p_sa_off, c->p_sa_txt, c->p_oc_off, c->p_oc_txt, c->prm.mismatch_num, c->sarows.as<EvRow>());
       int hm = 0;
       CU(c, cudaMemcpyAsync(&hm, miss, 4, cudaMemcpyDeviceToHost, st));
@@ -1273,6 +1386,7 @@ static int refine_local_maxspan(bkid_ctx *c, int *out)
 {
   cudaStream_t st = c->st;
   if (c->maxspan_pending) { TRY(c, maxspan_collect(c)); *out = c->maxspan; return 0; }
+  if (c->p_span16) { TRY(c, classify_impl(c)); *out = c->maxspan; return 0; }     // K1 read the narrow span column
   int *mx = (int *)(c->counters.as<unsigned>() + CS_MAXSPAN);
   CU(c, cudaMemsetAsync(mx, 0, 4, st));
   if (c->n > 0) BK_LAUNCH(max_span_kernel, 1184, 256, 0, st, c->p_pos, c->p_endpos, c->n, mx);
@@ -1286,7 +1400,7 @@ static int refine_local_maxspan(bkid_ctx *c, int *out)
 static RefineView refine_view(bkid_ctx *c)
 {
   RefineView v;
-  v.n = c->n; v.cls = c->cls.as<uint8_t>(); v.tid = c->p_tid; v.pos = c->p_pos; v.endpos = c->p_endpos;
+  v.n = c->n; v.cls = c->cls.as<uint8_t>(); v.tid = c->p_tid; v.pos = c->p_pos; v.endpos = c->p_endpos; v.span16 = c->p_span16;
   v.n_sa = c->n_rows; v.rows = (const EvRow *)c->rows_ptr; v.maxspan = c->maxspan;
   v.name_key = c->name_key.as<uint64_t>(); v.name_row = c->name_row.as<uint32_t>();
   v.canon = c->d_canon.as<uint64_t>(); v.nt = c->nt;
@@ -1429,14 +1543,43 @@ int bkid_refine(bkid_ctx *c, double dist, int64_t *n_called)
 // Shard entry points (multi-GPU; one context per rank, exchanges done by the caller -- see
 // breakid_b200/dist.py).  Device pointers handed out stay valid until the next call on the context.
 // =============================================================================================
-static int sd_partial_impl(bkid_ctx *c, double mean, long long t_in, long long *t_out);
 
-int bkid_shard_insert_partial(bkid_ctx *c, int64_t *sum_abs, int64_t *count)
+int bkid_shard_insert_partial(bkid_ctx *c, int64_t *sum_abs, int64_t *count, uint64_t *sum_sq, uint64_t *max_abs)
 {
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device); c->err.clear();
   TRY(c, classify_impl(c));
   *sum_abs = c->sum_abs; *count = c->cnt_insert;
+  if (sum_sq) *sum_sq = c->sum_sq;
+  if (max_abs) *max_abs = c->xmax;
+  return 0;
+}
+
+int bkid_sd_upper_binade(uint64_t sum_abs, uint64_t count, uint64_t sum_sq, uint64_t max_abs)
+{
+  return sd_upper_binade(sum_abs, count, sum_sq, max_abs);
+}
+
+// one-pass form over the local records with the GLOBAL mean and binade bound: asynchronous on the side stream, so it
+// overlaps candidate extraction and the candidate all-to-all; bkid_shard_sd_fast_collect joins it
+int bkid_shard_sd_fast(bkid_ctx *c, double mean, int32_t upper_binade)
+{
+  if (!c) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  TRY(c, classify_impl(c));
+  TRY(c, sd_fast_launch(c, mean, upper_binade, c->st2));
+  c->sd_fast_pending = true;
+  return 0;
+}
+
+int bkid_shard_sd_fast_collect(bkid_ctx *c, uint64_t *sum_floor, uint64_t *n_correctable)
+{
+  if (!c || !sum_floor || !n_correctable) return BKID_ERR_ARG;
+  cudaSetDevice(c->device); c->err.clear();
+  unsigned long long F = 0, E = 0;
+  TRY(c, sd_fast_collect(c, c->st2, &F, &E));
+  c->sd_fast_pending = false;
+  *sum_floor = F; *n_correctable = E == ~0ull ? (uint64_t)1 << 62 : E;      // (summed over ranks by the caller: keep it far from overflow)
   return 0;
 }
 
@@ -1445,8 +1588,7 @@ int bkid_shard_sd_prepare(bkid_ctx *c, double mean)
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device); c->err.clear();
   TRY(c, classify_impl(c));
-  // asynchronous on the side stream: the streaming pass overlaps whatever the caller does next on the main stream
-  // (candidate extraction, the candidate all-to-all); bkid_shard_sd_partial joins it
+  // general path, asynchronous on the side stream; bkid_shard_sd_partial joins it
   TRY(c, sd_prepare_impl(c, mean, c->st2));
   CU(c, cudaEventRecord(c->ev_side[1], c->st2));
   c->sd_side_pending = true;
@@ -1476,8 +1618,11 @@ int bkid_shard_candidates(bkid_ctx *c, uint64_t index_offset, const bkid_cand **
 {
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device); c->err.clear();
-  TRY(c, extract_candidates(c, index_offset));
+  TRY(c, extract_candidates(c, index_offset, false));
+  unsigned hnc[2] = {0, 0};
+  CU(c, cudaMemcpyAsync(hnc, c->counters.as<unsigned>() + CS_NC, 8, cudaMemcpyDeviceToHost, c->st));
   TRY(c, sync_check(c));
+  TRY(c, check_candidates(c, hnc));
   *dev = c->cand.as<bkid_cand>(); *n = c->n_cand;
   return 0;
 }
@@ -1496,7 +1641,7 @@ int bkid_shard_set_pairs(bkid_ctx *c, const bkid_pair *dev_pairs, int64_t n)
 {
   if (!c) return BKID_ERR_ARG;
   cudaSetDevice(c->device); c->err.clear();
-  TRY(c, set_pairs(c, dev_pairs, n));
+  TRY(c, set_pairs(c, dev_pairs, n, false));
   c->tm.n_pairs = c->np0;
   c->scanned = true; c->clustered = c->refined = false;
   return 0;
@@ -1655,17 +1800,18 @@ int bkid_run(bkid_ctx *c, double *mean, double *sd, double *dist, int64_t *n_cal
     if ((rc = side_launch(c)) != 0) return rc;
   }
   cudaEventRecord(c->ev[6], c->st);
-  if ((rc = extract_candidates(c, 0ull)) != 0) return rc;
-  if ((rc = join_presort(c, c->cand.as<bkid_cand>(), c->n_cand)) != 0) return rc;
+  const uint32_t *nc_dev = c->counters.as<unsigned>() + CS_NC;
+  if ((rc = extract_candidates(c, 0ull, true)) != 0) return rc;
+  if ((rc = join_presort(c, c->cand.as<bkid_cand>(), c->n_cand, nc_dev, true)) != 0) return rc;
   if (!c->have_stats && (rc = side_collect(c)) != 0) return rc;
   m = c->mean; s = c->sd;
   int times = c->prm.times;
   double d = times * sqrt((double)times) * (m + c->prm.sd_mult * s);          // src/BreakID.cc:103
   {
     long long npl = 0;
-    if ((rc = join_emit(c, c->cand.as<bkid_cand>(), c->n_cand, d, &npl)) != 0) return rc;
+    if ((rc = join_emit(c, c->cand.as<bkid_cand>(), c->n_cand, nc_dev, d, true, &npl)) != 0) return rc;
     cudaEventRecord(c->ev[7], c->st);
-    if ((rc = set_pairs(c, c->pairs_tmp.as<bkid_pair>(), npl)) != 0) return rc;
+    if ((rc = set_pairs(c, c->pairs_tmp.as<bkid_pair>(), npl, true)) != 0) return rc;
     cudaEventRecord(c->ev[8], c->st);
     if ((rc = sync_check(c)) != 0) return rc;
     float ms = 0;

@@ -28,40 +28,49 @@ namespace bamdec {
 
 constexpr uint32_t SEG = 256u << 10;
 constexpr uint32_t NONE = 0xffffffffu;
-constexpr int INF_WARPS = 4;          // warps per CTA
-constexpr int INF_GS = 8;             // lanes per group: four groups per warp, one BGZF block each
-constexpr int INF_NG = 32 / INF_GS;
-constexpr int INF_TOKENS = 32;        // tokens per group and lock-step round
+constexpr int INF_LITMAX = 4;         // literals per lane and step
+constexpr int INF_STEPS = 8;          // lane steps between two rounds of block fetch / header scheduling
+constexpr int INF_HBATCH = 6;         // a block header is parsed once this many lanes of the warp wait for one ...
+constexpr int INF_HWAIT = 24;         // ... or a lane has waited this many rounds (the parse is a long divergent section)
+constexpr int INF_CTAS_PER_SM = 5;    // 44 KB of tables per warp
 
 struct Task { uint64_t src; uint32_t dst; uint32_t clen, ulen; };
 
-// All groups of a warp go through the decoder's phases in one instruction stream: a round runs at most one block
-// header (groups that are not at a header wait) and INF_TOKENS tokens per group; __all_sync closes the round and
-// reconverges the warp.  Blocks are dealt to groups round-robin.
-__global__ void __launch_bounds__(INF_WARPS * 32, 6) bgzf_inflate(const uint8_t *__restrict__ comp, const Task *__restrict__ tasks, int ntask, uint8_t *__restrict__ unc, int *__restrict__ err)
+// One warp per CTA, one BGZF block per LANE (bkid_inflate.cuh): every lane fetches its blocks from a global queue and
+// runs its own decoder; the warp executes the union of the lanes' paths.  Header parses (thousands of instructions,
+// once per deflate block) are batched: a lane that reaches a header waits until a few others have too.
+__global__ void __launch_bounds__(32, INF_CTAS_PER_SM) bgzf_inflate(const uint8_t *__restrict__ comp, const Task *__restrict__ tasks, int ntask, uint8_t *__restrict__ unc,
+                                                                    int *__restrict__ err, unsigned *__restrict__ next_task)
 {
-  __shared__ bki::Tables T[INF_WARPS][INF_NG];
-  enum { FETCH = 3, IDLE = 4 };
-  const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / INF_GS;
-  bki::Tables &Tg = T[w][grp];
-  const int ngroups = gridDim.x * INF_WARPS * INF_NG;
-  int t = (blockIdx.x * INF_WARPS + w) * INF_NG + grp;
-  bki::Stream s;
-  s.phase = FETCH; s.out = nullptr; s.op = 0; s.out_len = 0; s.last = 0;
-  bki::br_init(s.b, nullptr, 0);
+  extern __shared__ __align__(16) unsigned char inf_smem[];
+  bki::Tab &T = reinterpret_cast<bki::Tab *>(inf_smem)[threadIdx.x];
+  enum { FETCH = 8, IDLE = 9 };
+  bki::Lane L;
+  L.phase = FETCH;
+  int t = -1, waited = 0;
   for (;;) {
-    if (s.phase == FETCH) {
-      if (t >= ntask) s.phase = IDLE;
-      else { Task k = tasks[t]; bki::stream_init(s, comp + k.src, k.clen, unc + k.dst, k.ulen); }
+    if (L.phase == FETCH) {
+      t = (int)atomicAdd(next_task, 1u);
+      if (t >= ntask) L.phase = IDLE;
+      else { Task k = tasks[t]; bki::lane_init(L, comp + k.src, k.clen, unc + k.dst, k.ulen); waited = 0; }
     }
     int rc = 0;
+    const bool want_h = L.phase == bki::PH_HEADER;
+    const unsigned hm = __ballot_sync(0xffffffffu, want_h);
+    if (hm) {
+      const unsigned busy = __ballot_sync(0xffffffffu, L.phase == bki::PH_TOKENS || L.phase == bki::PH_STORED);
+      if (want_h) ++waited;
+      const bool go = __popc(hm) >= INF_HBATCH || busy == 0u || __any_sync(0xffffffffu, want_h && waited > INF_HWAIT);
+      if (go && want_h) { rc = bki::lane_header(L, T); waited = 0; }
+    }
+#pragma unroll 1
+    for (int r = 0; r < INF_STEPS; ++r)
+      if (!rc && (L.phase == bki::PH_TOKENS || L.phase == bki::PH_STORED)) rc = bki::lane_step<INF_LITMAX>(L, T);
     bool finished = false;
-    if (s.phase == bki::PH_HEADER) rc = bki::header_step<INF_GS>(s, Tg);
-    if (s.phase == bki::PH_TOKENS && !rc) rc = bki::token_steps<INF_GS>(s, Tg, INF_TOKENS);
-    if (s.phase == bki::PH_DONE && !rc) { rc = bki::stream_finish(s); finished = true; }
-    if (rc) { if ((threadIdx.x & (INF_GS - 1)) == 0) atomicCAS(err, 0, (t << 4) | rc); finished = true; }
-    if (finished) { s.phase = FETCH; t += ngroups; }
-    if (__all_sync(0xffffffffu, s.phase == IDLE)) break;
+    if (!rc && L.phase == bki::PH_DONE) { rc = bki::lane_finish(L); finished = true; }
+    if (rc) { atomicCAS(err, 0, (t << 4) | rc); finished = true; }
+    if (finished) L.phase = FETCH;
+    if (__all_sync(0xffffffffu, L.phase == IDLE)) break;
   }
 }
 
@@ -354,6 +363,7 @@ static int decoder_init(bkid_ctx *c)
   CU(c, cudaStreamCreateWithFlags(&d->st_copy, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) { CU(c, cudaEventCreateWithFlags(&d->ev_h2d[i], cudaEventDisableTiming)); CU(c, cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming)); }
   for (int i = 0; i < 8; ++i) CU(c, cudaEventCreate(&d->ev_t[i]));
+  CU(c, cudaFuncSetAttribute(bamdec::bgzf_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * sizeof(bki::Tab))));
   d->init = true;
   return 0;
 }
@@ -392,6 +402,7 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, uint64_t file_size, 
   bkid_decoder *d = c->dec;
   cudaStream_t st = c->st;
   invalidate(c);
+  TRY(c, settle_forms(c, 1, 1, 0));                           // the decoder writes the wide insert-size / end columns
   memset(&d->stats, 0, sizeof d->stats);
   d->skip_crc = getenv("BKID_BGZF_NO_CRC") != nullptr;
   size_t COMP_CAP = (size_t)1536 << 20, UNC_CAP = (size_t)3072 << 20, CARRY_CAP = (size_t)64 << 20;   // unc offsets are 32-bit: UNC_CAP + CARRY_CAP < 4 GiB
@@ -508,7 +519,10 @@ static int push_bgzf_impl(bkid_ctx *c, const uint8_t *file, uint64_t file_size, 
     CU(c, cudaMemcpyAsync(dt, ht, (size_t)nt * sizeof(Task), cudaMemcpyHostToDevice, st));
     CU(c, cudaStreamWaitEvent(st, d->ev_h2d[slot], 0));
     cudaEventRecord(d->ev_t[1], st);
-    if (nt) BK_LAUNCH(bgzf_inflate, std::min((nt + INF_WARPS * INF_NG - 1) / (INF_WARPS * INF_NG), 148 * 6), INF_WARPS * 32, 0, st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 4);
+    if (nt) {
+      CU(c, cudaMemsetAsync(state + 7, 0, 4, st));            // block queue head
+      BK_LAUNCH(bgzf_inflate, std::min((nt + 31) / 32, 148 * INF_CTAS_PER_SM), 32, 32 * sizeof(bki::Tab), st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 4, (unsigned *)(state + 7));
+    }
     if (nt && !d->skip_crc) BK_LAUNCH(bgzf_crc32, std::min((nt + 7) / 8, 148 * 8), 256, 0, st, d->comp[slot].as<uint8_t>(), dt, nt, u, state + 6);
     CU(c, cudaEventRecord(d->ev_free[slot], st));
     cudaEventRecord(d->ev_t[2], st);
@@ -685,7 +699,16 @@ int bkid_fetch_column(bkid_ctx *c, const char *name, void *out, int64_t cap_byte
   size_t n = (size_t)c->n, nx = (size_t)c->n_x, ns = (size_t)c->n_sa;
   if (k == "flag") { p = c->p_flag; nb = n * 2; } else if (k == "mapq") { p = c->p_mapq; nb = n; }
   else if (k == "tid") { p = c->p_tid; nb = n * 4; } else if (k == "pos") { p = c->p_pos; nb = n * 4; }
-  else if (k == "isize") { p = c->p_isize; nb = n * 4; } else if (k == "endpos") { p = c->p_endpos; nb = n * 4; }
+  else if (k == "isize" || k == "endpos") {
+    nb = n * 4;
+    p = k == "isize" ? (const void *)c->p_isize : (const void *)c->p_endpos;
+    if (!p && n) {                                         // kept narrow in HBM: the getter hands out the wide form
+      TRY(c, c->tmpH.ensure(nb + 64, 0, c->st));
+      if (k == "isize") BK_LAUNCH(widen_isize16, GRID1(n, 256), 256, 0, c->st, c->p_isize16, (long long)n, c->tmpH.as<int32_t>());
+      else BK_LAUNCH(widen_span16, GRID1(n, 256), 256, 0, c->st, c->p_pos, c->p_span16, (long long)n, c->tmpH.as<int32_t>());
+      p = c->tmpH.p;
+    }
+  }
   else if (k == "x_rec") { p = c->p_x_rec; nb = nx * 4; } else if (k == "x_mtid") { p = c->p_x_mtid; nb = nx * 4; }
   else if (k == "x_mpos") { p = c->p_x_mpos; nb = nx * 4; } else if (k == "x_name_hash") { p = c->p_x_nh; nb = nx * 16; }
   else if (k == "sa_rec") { p = c->p_sa_rec; nb = ns * 4; } else if (k == "cig_off") { p = c->p_cig_off; nb = (ns + 1) * 4; }

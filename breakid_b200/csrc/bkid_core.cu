@@ -73,12 +73,18 @@ struct DBuf {
 #define BK_TRY(x) do { int rc__ = (x); if (rc__ != 0) return rc__; } while (0)
 
 // =============================================================================================
-// K1: classify + insert statistics.  One block per tile of 4096 records; each thread handles 4
-// groups of 4 consecutive records with 64/32/128-bit loads of flag/mapq/isize and one 32-bit store of
-// the class mask.  Algorithmic traffic: 2 + 1 + 4 B read, 1 B written per record.
+// K1: classify + insert statistics (+ maximal reference span).  One block per tile of 4096 records; a
+// thread handles 2 groups of 8 consecutive records with 128/64-bit loads and one 64-bit store of the
+// class bytes.  The insert-size and span columns come in their narrow forms when the batch has them
+// (include/breakid_b200.h: isize16 / span16 -- they stay narrow in HBM):
+//   narrow: flag 2 + mapq 1 + isize16 2 + span16 2 read, class 1 written = 8 B/record, max span included
+//   wide  : flag 2 + mapq 1 + isize 4 read, class 1 written = 8 B/record (max span: separate pass over pos/endpos)
+// Global results g[]: [0] sum |isize|, [1] count, [2] sum isize^2 (all over records passing :1932),
+// [3] number of discordant-scan candidates, [4] max |isize| of an insert record, [5] max span.
 // =============================================================================================
 constexpr int K1_THREADS = 256;
 constexpr int K1_TILE = 4096;
+enum { G_SUM = 0, G_CNT = 1, G_SQ = 2, G_CAND = 3, G_XMAX = 4, G_SPAN = 5 };
 
 __device__ __forceinline__ unsigned classify_one(unsigned flag, unsigned mapq, int qual)
 {
@@ -90,67 +96,103 @@ __device__ __forceinline__ unsigned classify_one(unsigned flag, unsigned mapq, i
   return c;
 }
 
-__global__ void __launch_bounds__(K1_THREADS)
-k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ isize, long long n, int qual,
-            uint8_t *__restrict__ cls, uint32_t *__restrict__ tile_cand, unsigned long long *__restrict__ g_sum_abs,
-            unsigned long long *__restrict__ g_cnt_insert)
+// the insert-size column in either form (only records passing :1932 ever read it)
+struct ISizeCol {
+  const int32_t *w; const int16_t *h;
+  __device__ __forceinline__ int at(long long i) const { return h ? (int)h[i] : w[i]; }
+};
+
+// four records: packed flag predicates (2 x 16 bit per word), packed mapq predicates (4 x 8 bit)
+__device__ __forceinline__ unsigned classify4(unsigned f01, unsigned f23, unsigned m4, unsigned q4, bool q_never, unsigned &ins8)
 {
-  // The flag predicates are evaluated two records at a time on packed 2x16-bit words and the mapq
-  // predicates four at a time on packed 4x8-bit words (SIMD-in-register video instructions), so the
-  // kernel stays DRAM-bound instead of issue-bound (profiles/r01m_ncu_top_kernels.md).
-  __shared__ unsigned long long sh_sum;
-  __shared__ unsigned sh_cnt;                 // n_ins in the low half, n_cand in the high half (<= 4096 each)
-  if (threadIdx.x == 0) { sh_sum = 0; sh_cnt = 0; }
+  unsigned ins_lo = __vcmpeq2(f01 & 0x07070707u, 0x00030003u), ins_hi = __vcmpeq2(f23 & 0x07070707u, 0x00030003u);     // :1932
+  unsigned bas_lo = __vcmpeq2(f01 & 0x04010401u, 0x00010001u), bas_hi = __vcmpeq2(f23 & 0x04010401u, 0x00010001u);     // !DUP && PAIRED
+  unsigned cnd_lo = __vcmpeq2(f01 & 0x05030503u, 0x00010001u), cnd_hi = __vcmpeq2(f23 & 0x05030503u, 0x00010001u);     // :1419-1420 flag part
+  ins8 = __byte_perm(ins_lo, ins_hi, 0x6420);
+  unsigned bas8 = __byte_perm(bas_lo, bas_hi, 0x6420), cnd8 = __byte_perm(cnd_lo, cnd_hi, 0x6420);
+  unsigned ge8 = q_never ? 0u : __vcmpgeu4(m4, q4), gt8 = __vcmpne4(m4, 0u);
+  cnd8 &= ge8;
+  return (ins8 & 0x01010101u) | (cnd8 & 0x02020202u) | (bas8 & gt8 & 0x04040404u) | (bas8 & 0x08080808u);
+}
+
+template <bool I16, bool S16>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ isize, const int16_t *__restrict__ isize16,
+            const uint16_t *__restrict__ span16, long long n, int qual, uint8_t *__restrict__ cls, unsigned long long *__restrict__ g)
+{
+  __shared__ unsigned long long sh_sum, sh_sq;
+  __shared__ unsigned sh_cnt, sh_xmax, sh_span;      // sh_cnt: n_ins in the low half, n_cand in the high half (<= 4096 each)
+  if (threadIdx.x == 0) { sh_sum = 0; sh_sq = 0; sh_cnt = 0; sh_xmax = 0; sh_span = 0; }
   __syncthreads();
-  long long tile0 = (long long)blockIdx.x * K1_TILE;
-  unsigned long long sum_abs = 0;
-  unsigned cnt = 0;
+  const long long tile0 = (long long)blockIdx.x * K1_TILE;
+  unsigned long long sum_abs = 0, sum_sq = 0;
+  unsigned cnt = 0, xmax = 0, smax2 = 0;
   const unsigned q4 = (unsigned)(qual < 0 ? 0 : (qual > 255 ? 255 : qual)) * 0x01010101u;
   const bool q_never = qual > 255;           // mapq is 8 bits: nothing can pass
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    long long i = tile0 + g * (K1_THREADS * 4) + threadIdx.x * 4;
-    if (i + 3 < n) {
-      uint2 f2 = *reinterpret_cast<const uint2 *>(flag + i);
-      unsigned m4 = *reinterpret_cast<const unsigned *>(mapq + i);
-      int4 s4 = *reinterpret_cast<const int4 *>(isize + i);
-      // 2x16 masks: 0xFFFF where the predicate holds
-      unsigned ins_lo = __vcmpeq2(f2.x & 0x07070707u, 0x00030003u), ins_hi = __vcmpeq2(f2.y & 0x07070707u, 0x00030003u);     // :1932
-      unsigned bas_lo = __vcmpeq2(f2.x & 0x04010401u, 0x00010001u), bas_hi = __vcmpeq2(f2.y & 0x04010401u, 0x00010001u);     // !DUP && PAIRED
-      unsigned cnd_lo = __vcmpeq2(f2.x & 0x05030503u, 0x00010001u), cnd_hi = __vcmpeq2(f2.y & 0x05030503u, 0x00010001u);     // :1419-1420 flag part
-      // to 4x8 layout (byte k = record k)
-      unsigned ins8 = __byte_perm(ins_lo, ins_hi, 0x6420), bas8 = __byte_perm(bas_lo, bas_hi, 0x6420), cnd8 = __byte_perm(cnd_lo, cnd_hi, 0x6420);
-      unsigned ge8 = q_never ? 0u : __vcmpgeu4(m4, q4), gt8 = __vcmpne4(m4, 0u);
-      cnd8 &= ge8;
-      unsigned c4 = (ins8 & 0x01010101u) | (cnd8 & 0x02020202u) | (bas8 & gt8 & 0x04040404u) | (bas8 & 0x08080808u);
-      *reinterpret_cast<unsigned *>(cls + i) = c4;
-      cnt += __popc(ins8 & 0x01010101u) + (__popc(cnd8 & 0x01010101u) << 16);
-      int a0 = s4.x < 0 ? -s4.x : s4.x, a1 = s4.y < 0 ? -s4.y : s4.y, a2 = s4.z < 0 ? -s4.z : s4.z, a3 = s4.w < 0 ? -s4.w : s4.w;
-      unsigned t = (unsigned)a0 & (unsigned)((int)(ins8 << 24) >> 31);
-      unsigned long long part = t;
-      part += (unsigned)a1 & (unsigned)((int)(ins8 << 16) >> 31);
-      part += (unsigned)a2 & (unsigned)((int)(ins8 << 8) >> 31);
-      part += (unsigned)a3 & (unsigned)((int)ins8 >> 31);
-      sum_abs += part;
+  for (int gq = 0; gq < 2; ++gq) {
+    long long i = tile0 + gq * (K1_THREADS * 8) + threadIdx.x * 8;
+    if (i + 7 < n) {
+      uint4 f8 = *reinterpret_cast<const uint4 *>(flag + i);
+      uint2 m8 = *reinterpret_cast<const uint2 *>(mapq + i);
+      unsigned insA, insB;
+      unsigned cA = classify4(f8.x, f8.y, m8.x, q4, q_never, insA), cB = classify4(f8.z, f8.w, m8.y, q4, q_never, insB);
+      *reinterpret_cast<uint2 *>(cls + i) = make_uint2(cA, cB);
+      cnt += __popc(cA & 0x01010101u) + __popc(cB & 0x01010101u) + ((__popc(cA & 0x02020202u) + __popc(cB & 0x02020202u)) << 16);
+      if (S16) {
+        uint4 p8 = *reinterpret_cast<const uint4 *>(span16 + i);
+        smax2 = __vmaxu2(__vmaxu2(smax2, p8.x), __vmaxu2(__vmaxu2(p8.y, p8.z), p8.w));
+      }
+      if (I16) {
+        uint4 s8 = *reinterpret_cast<const uint4 *>(isize16 + i);
+        // insert masks back to 2 x 16 bit: byte k of ins8 = record k
+        unsigned w[4] = {s8.x, s8.y, s8.z, s8.w};
+        unsigned mk[4] = {__byte_perm(insA, 0, 0x1100), __byte_perm(insA, 0, 0x3322), __byte_perm(insB, 0, 0x1100), __byte_perm(insB, 0, 0x3322)};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          unsigned a2 = __vabs2(w[q]) & mk[q];                  // |x| per halfword (|-32768| = 32768 as unsigned), 0 where not an insert record
+          unsigned lo = a2 & 0xffffu, hi = a2 >> 16;
+          sum_abs += lo + hi;
+          sum_sq += (unsigned long long)lo * lo + (unsigned long long)hi * hi;
+          xmax = max(xmax, max(lo, hi));
+        }
+      } else {
+        int4 sA = *reinterpret_cast<const int4 *>(isize + i), sB = *reinterpret_cast<const int4 *>(isize + i + 4);
+        int sv[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          unsigned mk = (unsigned)((int)(((q < 4 ? insA : insB) << (24 - 8 * (q & 3)))) >> 31);
+          unsigned a = (unsigned)(sv[q] < 0 ? -sv[q] : sv[q]) & mk;
+          sum_abs += a; sum_sq += (unsigned long long)a * a; xmax = max(xmax, a);
+        }
+      }
     } else {
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 8; ++k)
         if (i + k < n) {
           unsigned c = classify_one(flag[i + k], mapq[i + k], qual);
-          int s = isize[i + k];
-          if (c & CL_INSERT) { sum_abs += (unsigned long long)(s < 0 ? -(long long)s : (long long)s); cnt += 1u; }
+          if (c & CL_INSERT) {
+            int sv = I16 ? (int)isize16[i + k] : isize[i + k];
+            unsigned a = (unsigned)(sv < 0 ? -sv : sv);
+            sum_abs += a; sum_sq += (unsigned long long)a * a; xmax = max(xmax, a); cnt += 1u;
+          }
+          if (S16) smax2 = __vmaxu2(smax2, (unsigned)span16[i + k]);
           cnt += ((c >> 1) & 1u) << 16;
           cls[i + k] = (uint8_t)c;
         }
     }
   }
+  unsigned smax = max(smax2 & 0xffffu, smax2 >> 16);
   cnt = bk::warp_sum(cnt);
   sum_abs = bk::warp_sum(sum_abs);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh_cnt, cnt); atomicAdd(&sh_sum, sum_abs); }
+  sum_sq = bk::warp_sum(sum_sq);
+  for (int o = 16; o; o >>= 1) { xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o)); smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh_cnt, cnt); atomicAdd(&sh_sum, sum_abs); atomicAdd(&sh_sq, sum_sq); atomicMax(&sh_xmax, xmax); atomicMax(&sh_span, smax); }
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned c = sh_cnt;
-    tile_cand[blockIdx.x] = c >> 16;
-    if (c & 0xffffu) { atomicAdd(g_sum_abs, sh_sum); atomicAdd(g_cnt_insert, (unsigned long long)(c & 0xffffu)); }
+    if (c & 0xffffu) { atomicAdd(g + G_SUM, sh_sum); atomicAdd(g + G_CNT, (unsigned long long)(c & 0xffffu)); atomicAdd(g + G_SQ, sh_sq); atomicMax(g + G_XMAX, (unsigned long long)sh_xmax); }
+    if (c >> 16) atomicAdd(g + G_CAND, (unsigned long long)(c >> 16));
+    if (S16 && sh_span) atomicMax(g + G_SPAN, (unsigned long long)sh_span);
   }
 }
 
@@ -188,45 +230,24 @@ __global__ void ex_prefix(const uint32_t *__restrict__ len, int n_iv, unsigned l
   pre[n_iv] = s;
 }
 __global__ void __launch_bounds__(256)
-ex_apply(const uint32_t *__restrict__ lo, const unsigned long long *__restrict__ pre, int n_iv, const int32_t *__restrict__ isize, uint8_t *__restrict__ cls,
-         uint32_t *__restrict__ tile_cand, unsigned long long *__restrict__ g_sum_abs, unsigned long long *__restrict__ g_cnt_insert)
+ex_apply(const uint32_t *__restrict__ lo, const unsigned long long *__restrict__ pre, int n_iv, ISizeCol isz, uint8_t *__restrict__ cls, unsigned long long *__restrict__ g)
 {
   unsigned long long E = pre[n_iv];
-  unsigned long long sum = 0; unsigned cnt = 0;
+  unsigned long long sum = 0, sq = 0; unsigned cnt = 0, ncand = 0;
   for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (unsigned long long)gridDim.x * blockDim.x) {
     int a = 0, b = n_iv;                       // last k with pre[k] <= e
     while (b - a > 1) { int m = (a + b) >> 1; if (pre[m] <= e) a = m; else b = m; }
     long long i = (long long)lo[a] + (long long)(e - pre[a]);
     unsigned c = cls[i];
-    if (c & CL_INSERT) { int s = isize[i]; sum += (unsigned long long)(s < 0 ? -(long long)s : (long long)s); ++cnt; }
-    if (c & CL_CAND) atomicSub(&tile_cand[i / K1_TILE], 1u);
+    if (c & CL_INSERT) { int s = isz.at(i); unsigned long long x = (unsigned long long)(s < 0 ? -(long long)s : (long long)s); sum += x; sq += x * x; ++cnt; }
+    if (c & CL_CAND) ++ncand;
     cls[i] = (uint8_t)CL_EXCL;
   }
-  sum = bk::warp_sum(sum); cnt = bk::warp_sum(cnt);
-  if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(g_sum_abs, 0ull - sum); atomicAdd(g_cnt_insert, 0ull - (unsigned long long)cnt); }
-}
-
-// ordered compaction of candidate record indices: each thread owns 16 consecutive class bytes
-__global__ void __launch_bounds__(K1_THREADS)
-k1_compact(const uint8_t *__restrict__ cls, long long n, const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ cand_idx)
-{
-  __shared__ unsigned sh32[33];
-  long long i0 = (long long)blockIdx.x * K1_TILE + threadIdx.x * 16;
-  unsigned char c[16];
-  if (i0 + 15 < n) {
-    uint4 v = *reinterpret_cast<const uint4 *>(cls + i0);
-    memcpy(c, &v, 16);
-  } else {
-    for (int k = 0; k < 16; ++k) c[k] = (i0 + k < n) ? cls[i0 + k] : 0;
+  sum = bk::warp_sum(sum); sq = bk::warp_sum(sq); cnt = bk::warp_sum(cnt); ncand = bk::warp_sum(ncand);
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt) { atomicAdd(g + G_SUM, 0ull - sum); atomicAdd(g + G_CNT, 0ull - (unsigned long long)cnt); atomicAdd(g + G_SQ, 0ull - sq); }
+    if (ncand) atomicAdd(g + G_CAND, 0ull - (unsigned long long)ncand);
   }
-  unsigned cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) cnt += (c[k] >> 1) & 1u;
-  unsigned tot;
-  unsigned off = bk::block_excl_scan<unsigned>(cnt, sh32, tot) + tile_off[blockIdx.x];
-#pragma unroll
-  for (int k = 0; k < 16; ++k)
-    if (c[k] & CL_CAND) cand_idx[off++] = (uint32_t)(i0 + k);
 }
 
 // =============================================================================================
@@ -291,7 +312,7 @@ __global__ void sd_build_lut(double mean, unsigned long long *__restrict__ lut)
 }
 
 __global__ void __launch_bounds__(SD_THREADS)
-sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, const unsigned long long *__restrict__ lut,
+sd_block_stats(const uint8_t *__restrict__ cls, ISizeCol isz, long long n, double mean, const unsigned long long *__restrict__ lut,
                long long *__restrict__ blkF, uint32_t *__restrict__ blkCum /*[nb][SD_K]*/, uint32_t *__restrict__ blkN, double *__restrict__ blkAmax)
 {
   __shared__ unsigned hist[SD_K];
@@ -310,11 +331,11 @@ sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isiz
     int s[4];
     if (i + 3 < n) {
       uchar4 c4 = *reinterpret_cast<const uchar4 *>(cls + i);
-      int4 s4 = *reinterpret_cast<const int4 *>(isize + i);
       c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
-      s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
+      if (isz.h) { short4 h4 = *reinterpret_cast<const short4 *>(isz.h + i); s[0] = h4.x; s[1] = h4.y; s[2] = h4.z; s[3] = h4.w; }
+      else { int4 s4 = *reinterpret_cast<const int4 *>(isz.w + i); s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w; }
     } else {
-      for (int k = 0; k < 4; ++k) { c[k] = (i + k < n) ? cls[i + k] : 0; s[k] = (i + k < n) ? isize[i + k] : 0; }
+      for (int k = 0; k < 4; ++k) { c[k] = (i + k < n) ? cls[i + k] : 0; s[k] = (i + k < n) ? isz.at(i + k) : 0; }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -372,7 +393,7 @@ sd_block_stats(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isiz
 // single CTA of SDR_T threads (256 threads x 16 blocks per step measured slower than 1024 x 8).  out[0] = sd_total, out[1] = out-of-regime flag.
 constexpr int SDR_T = 1024;
 __global__ void __launch_bounds__(SDR_T)
-sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, int nb,
+sd_resolve(const uint8_t *__restrict__ cls, ISizeCol isz, long long n, double mean, int nb,
            const long long *__restrict__ blkF, const uint32_t *__restrict__ blkCum, const uint32_t *__restrict__ blkN,
            const double *__restrict__ blkAmax, long long t_in, long long *__restrict__ out)
 {
@@ -453,7 +474,7 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
     int m = (int)min((long long)SD_BLOCK, n - base);
     for (int e = threadIdx.x; e < SD_BLOCK; e += SDR_T) {
       double a = -1.0; unsigned km = 255u;
-      if (e < m && (cls[base + e] & CL_INSERT)) { long long fa; sd_elem(isize[base + e], mean, a, fa, km); }
+      if (e < m && (cls[base + e] & CL_INSERT)) { long long fa; sd_elem(isz.at(base + e), mean, a, fa, km); }
       sa[e] = a; skm[e] = (unsigned char)km;
     }
     __syncthreads();
@@ -509,18 +530,76 @@ sd_resolve(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, l
 }
 
 // literal sequential replay (one thread); only used when the total leaves the closed-form regime
-__global__ void sd_sequential(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, long long n, double mean, long long t_in, long long *out)
+__global__ void sd_sequential(const uint8_t *__restrict__ cls, ISizeCol isz, long long n, double mean, long long t_in, long long *out)
 {
   if (blockIdx.x || threadIdx.x) return;
   long long t = t_in;
   for (long long i = 0; i < n; ++i)
     if (cls[i] & CL_INSERT) {
-      int s = isize[i];
+      int s = isz.at(i);
       double x = (double)(s < 0 ? -s : s);
       double d = __dsub_rn(x, mean);
       t = (long long)__dadd_rn((double)t, __dmul_rn(d, d));
     }
   out[0] = t; out[1] = 0;
+}
+
+// ---- the common case in ONE streaming pass -----------------------------------------------------------------
+// With S, N and the sum of squares from K1 the final total is bounded before the pass: T <= T_ub, so every running
+// total lies in a binade k <= K = floor(log2(T_ub)).  An element then needs a correction only if
+// frac(a) >= 1 - 2^(K-53) =: thr.  sd_fast adds up floor(a) and COUNTS such elements (E).  E = 0 (no insert size
+// whose squared deviation has a fraction that close to 1 -- |isize| takes a few hundred values, K is ~39 for a 30x
+// genome, so this is the normal case) means total = sum floor(a) exactly, independent of the order: no block tables,
+// no resolver, and in the multi-GPU path no rank-to-rank chain.  E > 0 falls back to the general path above.
+// Arithmetic per record: 6 FP64 instructions, no conversions -- x -> double by the 2^52 bit pattern, floor(a) by a
+// round-down add of 2^52 (exact for 0 <= a < 2^51; larger values raise the out-of-regime flag).
+// out[0] += sum floor(a), out[1] += E, out[2] |= out of regime.
+template <bool NARROW>
+__global__ void __launch_bounds__(256)
+sd_fast(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, const int16_t *__restrict__ isize16, long long n, double mean, double thr,
+        unsigned long long *__restrict__ out)
+{
+  const double M52 = 4503599627370496.0;
+  unsigned long long F = 0; unsigned E = 0, oor = 0;
+  const long long ngroups = (n + 7) / 8;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += (long long)gridDim.x * blockDim.x) {
+    long long i = gi * 8;
+    unsigned char c[8]; int sv[8];
+    if (i + 7 < n) {
+      uint2 c8 = *reinterpret_cast<const uint2 *>(cls + i);
+      memcpy(c, &c8, 8);
+      if (NARROW) {
+        uint4 h8 = *reinterpret_cast<const uint4 *>(isize16 + i);
+        short hs[8]; memcpy(hs, &h8, 16);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sv[k] = hs[k];
+      } else {
+        int4 a4 = *reinterpret_cast<const int4 *>(isize + i), b4 = *reinterpret_cast<const int4 *>(isize + i + 4);
+        sv[0] = a4.x; sv[1] = a4.y; sv[2] = a4.z; sv[3] = a4.w; sv[4] = b4.x; sv[5] = b4.y; sv[6] = b4.z; sv[7] = b4.w;
+      }
+    } else {
+      for (int k = 0; k < 8; ++k) { c[k] = (i + k < n) ? cls[i + k] : 0; sv[k] = (i + k < n) ? (NARROW ? (int)isize16[i + k] : isize[i + k]) : 0; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      unsigned x = (unsigned)(sv[k] < 0 ? -sv[k] : sv[k]);
+      double xd = __dsub_rn(__hiloint2double(0x43300000, (int)x), M52);      // exact for x < 2^32
+      double d = __dsub_rn(xd, mean);
+      double a = __dmul_rn(d, d);
+      double sft = __dadd_rd(a, M52);                                         // 2^52 + floor(a)
+      double fr = __dsub_rn(a, __dsub_rn(sft, M52));                          // frac(a), exact
+      bool on = (c[k] & CL_INSERT) != 0;
+      F += on ? ((unsigned long long)__double_as_longlong(sft) & 0xFFFFFFFFFFFFFull) : 0ull;
+      E += (on && fr >= thr) ? 1u : 0u;
+      oor |= (on && !(a < 2251799813685248.0)) ? 1u : 0u;
+    }
+  }
+  F = bk::warp_sum(F); E = bk::warp_sum(E); oor = bk::warp_sum(oor);
+  if ((threadIdx.x & 31) == 0) {
+    if (F) atomicAdd(out, F);
+    if (E) atomicAdd(out + 1, (unsigned long long)E);
+    if (oor) atomicOr(out + 2, 1ull);
+  }
 }
 
 // =============================================================================================
@@ -541,48 +620,73 @@ __device__ __forceinline__ long long x_slot_of(const uint32_t *__restrict__ x_re
   return (lo < n_x && x_rec[lo] == i) ? lo : -1;
 }
 
-__global__ void k2_gather_cand(const uint32_t *__restrict__ cand_idx, long long nc, const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
-                               const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, const uint32_t *__restrict__ x_rec, long long n_x,
-                               const int32_t *__restrict__ x_mtid, const int32_t *__restrict__ x_mpos, const uint64_t *__restrict__ x_nh,
-                               unsigned long long index_offset, bkid_cand *__restrict__ out, int *__restrict__ missing)
+// ---- candidates straight from the sparse mate/name table -------------------------------------------------------
+// Every candidate (:1419-1420) is by construction listed in the sparse table (it is not a proper pair), and the table is
+// in file order: one pass over its ~1 % entries yields the compact candidate array in file order -- no sweep over the
+// class bytes of all records, no search.  kx_count: candidates per 1024-entry tile (and the table's sanity: strictly
+// ascending record indices inside the batch); kx_write: ordered compaction into bkid_cand rows + the join's sort keys.
+constexpr int KX_THREADS = 256;
+constexpr int KX_ITEMS = 4;
+constexpr int KX_TILE = KX_THREADS * KX_ITEMS;
+
+__global__ void __launch_bounds__(KX_THREADS) kx_count(const uint32_t *__restrict__ x_rec, long long n_x, const uint8_t *__restrict__ cls, long long n,
+                                                       uint32_t *__restrict__ tile_cnt, int *__restrict__ bad)
 {
-  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nc) return;
-  uint32_t i = cand_idx[p];
-  bkid_cand c;
-  long long x = x_slot_of(x_rec, n_x, i);
-  if (x < 0) { atomicExch(missing, 1); x = 0; if (n_x == 0) { memset(&c, 0, sizeof c); out[p] = c; return; } }
-  c.name_lo = x_nh[2 * (size_t)x]; c.name_hi = x_nh[2 * (size_t)x + 1];
-  c.tid = tid[i]; c.pos = pos[i]; c.mtid = x_mtid[x]; c.mpos = x_mpos[x];
-  c.gidx = index_offset + i;
-  c.flag = flag[i]; c.mapq = mapq[i];
-  c._pad[0] = c._pad[1] = c._pad[2] = c._pad[3] = c._pad[4] = 0;
-  out[p] = c;
+  __shared__ unsigned sh32[33];
+  long long j0 = (long long)blockIdx.x * KX_TILE + threadIdx.x * KX_ITEMS;
+  unsigned cnt = 0;
+#pragma unroll
+  for (int k = 0; k < KX_ITEMS; ++k) {
+    long long j = j0 + k;
+    if (j < n_x) {
+      uint32_t r = x_rec[j];
+      if ((long long)r >= n || (j > 0 && x_rec[j - 1] >= r)) atomicExch(bad, 1);
+      else cnt += (cls[r] >> 1) & 1u;
+    }
+  }
+  unsigned tot;
+  bk::block_excl_scan<unsigned>(cnt, sh32, tot);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(KX_THREADS) kx_write(const uint32_t *__restrict__ x_rec, long long n_x, const uint8_t *__restrict__ cls, long long n, const uint32_t *__restrict__ tile_off,
+                                                       const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ tid, const int32_t *__restrict__ pos,
+                                                       const int32_t *__restrict__ x_mtid, const int32_t *__restrict__ x_mpos, const uint64_t *__restrict__ x_nh,
+                                                       unsigned long long index_offset, bkid_cand *__restrict__ out, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+  __shared__ unsigned sh32[33];
+  long long j0 = (long long)blockIdx.x * KX_TILE + threadIdx.x * KX_ITEMS;
+  unsigned is[KX_ITEMS], cnt = 0;
+  uint32_t rr[KX_ITEMS];
+#pragma unroll
+  for (int k = 0; k < KX_ITEMS; ++k) {
+    long long j = j0 + k;
+    is[k] = 0; rr[k] = 0;
+    if (j < n_x) { uint32_t r = x_rec[j]; rr[k] = r; if ((long long)r < n) is[k] = (cls[r] >> 1) & 1u; }
+    cnt += is[k];
+  }
+  unsigned tot;
+  unsigned off = bk::block_excl_scan<unsigned>(cnt, sh32, tot) + tile_off[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < KX_ITEMS; ++k)
+    if (is[k]) {
+      long long j = j0 + k; uint32_t i = rr[k];
+      bkid_cand c;
+      c.name_lo = x_nh[2 * (size_t)j]; c.name_hi = x_nh[2 * (size_t)j + 1];
+      c.tid = tid[i]; c.pos = pos[i]; c.mtid = x_mtid[j]; c.mpos = x_mpos[j];
+      c.gidx = index_offset + i;
+      c.flag = flag[i]; c.mapq = mapq[i];
+      c._pad[0] = c._pad[1] = c._pad[2] = c._pad[3] = c._pad[4] = 0;
+      out[off] = c;
+      if (keys) { keys[off] = c.name_lo; vals[off] = off; }
+      ++off;
+    }
 }
 
 __global__ void k2_cand_keys(const bkid_cand *__restrict__ cand, long long nc, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p < nc) { keys[p] = cand[p].name_lo; vals[p] = (uint32_t)p; }
-}
-
-__global__ void k2_run_heads(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, long long nc, const bkid_cand *__restrict__ cand,
-                             uint32_t *__restrict__ head, int *__restrict__ err)
-{
-  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nc) return;
-  unsigned h = 1;
-  if (p > 0 && keys[p] == keys[p - 1]) {
-    h = 0;
-    if (cand[vals[p]].name_hi != cand[vals[p - 1]].name_hi) atomicExch(err, 1);   // 64-bit collision of distinct names
-  }
-  head[p] = h;
-}
-
-__global__ void k2_run_starts(const uint32_t *__restrict__ head, const uint32_t *__restrict__ run_id_excl, long long nc, uint32_t *__restrict__ run_start)
-{
-  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < nc && head[p]) run_start[run_id_excl[p]] = (uint32_t)p;
 }
 
 __device__ __forceinline__ uint32_t genome_pos(const uint32_t *__restrict__ cum, int nt, int tid, int pos)
@@ -594,34 +698,18 @@ __device__ __forceinline__ uint32_t genome_pos(const uint32_t *__restrict__ cum,
 
 // sort key of a pair: bucket rank (high 24 bits) | global index of the second-seen mate (40 bits)
 constexpr int PAIR_IDX_BITS = 40;
+constexpr uint32_t NO_MATE = 0xffffffffu;
 
-__global__ void k2_emit_pairs(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ head, const uint32_t *__restrict__ run_id_excl,
-                              const uint32_t *__restrict__ run_start, long long nc, const bkid_cand *__restrict__ cand,
-                              const uint32_t *__restrict__ cum, int nt, const int32_t *__restrict__ bucket_rank,
-                              double w, bkid_pair *__restrict__ pairs, unsigned long long *__restrict__ counter)
+// one discordant pair from its two records: I = current (second seen), J = the stored mate (src/BreakID.cc:1428-1480)
+__device__ __forceinline__ bool pair_is_discordant(const bkid_cand &I, const bkid_cand &J, double w)
 {
-  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool emit = false;
-  bkid_cand I, J;
-  if (p < nc) {
-    uint32_t rid = run_id_excl[p] - (head[p] ? 0u : 1u);     // exclusive scan counts heads before p
-    uint32_t rank = (uint32_t)p - run_start[rid];
-    if (rank & 1u) {
-      I = cand[vals[p]]; J = cand[vals[p - 1]];              // I = current (second seen), J = stored mate
-      int ti = I.tid < 0 ? -1 : I.tid, tj = J.tid < 0 ? -1 : J.tid;
-      long long pi = (long long)I.pos + 1, pj = (long long)J.pos + 1;
-      long long dp = pi - pj; if (dp < 0) dp = -dp;
-      emit = (ti != tj) || ((double)dp >= w);                 // :1428
-    }
-  }
-  unsigned m = __ballot_sync(0xffffffffu, emit);
-  if (!m) return;
-  unsigned lane = threadIdx.x & 31;
-  unsigned long long basep = 0;
-  if (lane == (unsigned)(__ffs(m) - 1)) basep = atomicAdd(counter, (unsigned long long)__popc(m));
-  basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
-  if (!emit) return;
-  unsigned long long slot = basep + __popc(m & ((1u << lane) - 1u));
+  int ti = I.tid < 0 ? -1 : I.tid, tj = J.tid < 0 ? -1 : J.tid;
+  long long pi = (long long)I.pos + 1, pj = (long long)J.pos + 1;
+  long long dp = pi - pj; if (dp < 0) dp = -dp;
+  return (ti != tj) || ((double)dp >= w);                     // :1428
+}
+__device__ __forceinline__ bkid_pair make_pair(const bkid_cand &I, const bkid_cand &J, const uint32_t *__restrict__ cum, int nt, const int32_t *__restrict__ bucket_rank)
+{
   uint32_t c1 = genome_pos(cum, nt, I.tid, I.pos);            // :1431 current record's own fields
   uint32_t c2 = genome_pos(cum, nt, I.mtid, I.mpos);          // :1432 and its mate FIELDS
   bkid_pair P;
@@ -644,15 +732,87 @@ __global__ void k2_emit_pairs(const uint32_t *__restrict__ vals, const uint32_t 
   P.cluster = -1;
   P.orig = (uint32_t)(I.gidx & 0xffffffffull);                // order of the second-seen mate (40 bits: orig | _pad << 32)
   P._pad = (uint32_t)((I.gidx >> 32) & 0xffull);
-  pairs[slot] = P;
+  return P;
 }
 
-__global__ void k2_pair_keys(const bkid_pair *__restrict__ pairs, long long np, unsigned long long *__restrict__ keys, uint32_t *__restrict__ slots)
+// The join proper.  (keys, vals) = (name_lo, candidate index) stably sorted on the low `group_bits` bits of name_lo, so
+// all records of a read name sit in one GROUP in file order -- possibly interleaved with the few other names that share
+// those bits (3.4e6 names on 32 bits: ~1e3 groups).  The thread at the head of a group walks it: a group that is not
+// one name is first sorted, stably, on the full 128-bit name (insertion sort, <= cap members; this is also what
+// resolves two names that share all 64 bits of name_lo); then the records of every name are taken in file order and
+// paired (0,1), (2,3), ... -- the reference's std::map store / pair-and-erase protocol (src/BreakID.cc:1424-1494) --
+// and mate[second seen] = stored mate for the pairs that pass the discordance test.  A larger mixed group raises
+// *too_big: the caller then sorts on all 64 bits and runs the walk again.
+__global__ void __launch_bounds__(256) k2_join(uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, const uint32_t *__restrict__ nc_dev, uint32_t nc_host,
+                                               const bkid_cand *__restrict__ cand, int group_bits, uint32_t cap, double w, uint32_t *__restrict__ mate, int *__restrict__ too_big)
+{
+  const uint32_t nc = nc_dev ? *nc_dev : nc_host;
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nc) return;
+  const uint64_t gmask = group_bits >= 64 ? ~0ull : ((1ull << group_bits) - 1ull);
+  const uint64_t k0 = keys[p], gk = k0 & gmask;
+  if (p > 0 && (keys[p - 1] & gmask) == gk) return;             // not the head of its group
+  uint32_t e = p + 1;
+  while (e < nc && (keys[e] & gmask) == gk) ++e;
+  if (e - p < 2) return;                                        // a lone record has no mate
+  uint64_t hi_prev = cand[vals[p]].name_hi;
+  bool mixed = false;
+  for (uint32_t q = p + 1; q < e && !mixed; ++q) mixed = keys[q] != k0 || cand[vals[q]].name_hi != hi_prev;
+  if (mixed) {
+    if (e - p > cap) { atomicExch(too_big, 1); return; }
+    for (uint32_t i = p + 1; i < e; ++i) {                      // stable insertion sort on (name_lo, name_hi)
+      uint64_t kl = keys[i]; uint32_t v = vals[i]; uint64_t kh = cand[v].name_hi;
+      uint32_t j = i;
+      while (j > p) {
+        uint64_t pl = keys[j - 1], ph = cand[vals[j - 1]].name_hi;
+        if (pl < kl || (pl == kl && ph <= kh)) break;
+        keys[j] = pl; vals[j] = vals[j - 1]; --j;
+      }
+      keys[j] = kl; vals[j] = v;
+    }
+    hi_prev = cand[vals[p]].name_hi;
+  }
+  uint32_t run_start = p;
+  uint64_t lo_prev = keys[p];
+  for (uint32_t q = p + 1; q < e; ++q) {
+    uint32_t vq = vals[q];
+    uint64_t lo = keys[q], hi = cand[vq].name_hi;
+    if (lo != lo_prev || hi != hi_prev) { run_start = q; lo_prev = lo; hi_prev = hi; continue; }
+    if ((q - run_start) & 1u) {
+      uint32_t vj = vals[q - 1];
+      bkid_cand I = cand[vq], J = cand[vj];
+      if (pair_is_discordant(I, J, w)) mate[vq] = vj;
+    }
+  }
+}
+
+__global__ void k2_mate_flags(const uint32_t *__restrict__ mate, long long nc, uint32_t *__restrict__ flag)
+{
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nc) flag[q] = mate[q] != NO_MATE ? 1u : 0u;
+}
+
+// pairs in the order of their second-seen mate (= the order in which the reference's scan emits them)
+__global__ void k2_build_pairs(const uint32_t *__restrict__ mate, const uint32_t *__restrict__ off, long long nc, const bkid_cand *__restrict__ cand,
+                               const uint32_t *__restrict__ cum, int nt, const int32_t *__restrict__ bucket_rank, bkid_pair *__restrict__ pairs)
+{
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nc) return;
+  uint32_t m = mate[q];
+  if (m == NO_MATE) return;
+  bkid_cand I = cand[q], J = cand[m];
+  pairs[off[q]] = make_pair(I, J, cum, nt, bucket_rank);
+}
+
+// ordered: the pairs already arrive in emission order (single GPU) -> key = bucket rank alone (a stable sort keeps the
+// order inside a bucket); otherwise (pairs gathered from several ranks) key = bucket rank | index of the second-seen mate
+__global__ void k2_pair_keys(const bkid_pair *__restrict__ pairs, long long np, int ordered, unsigned long long *__restrict__ keys, uint32_t *__restrict__ slots)
 {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= np) return;
   const bkid_pair &P = pairs[p];
-  keys[p] = ((unsigned long long)(unsigned)P.bucket << PAIR_IDX_BITS) | ((unsigned long long)P._pad << 32) | (unsigned long long)P.orig;
+  keys[p] = ordered ? ((unsigned long long)(unsigned)P.bucket << PAIR_IDX_BITS)
+                    : (((unsigned long long)(unsigned)P.bucket << PAIR_IDX_BITS) | ((unsigned long long)P._pad << 32) | (unsigned long long)P.orig);
   slots[p] = (uint32_t)p;
 }
 

@@ -1,23 +1,26 @@
-// bkid_inflate.cuh -- DEFLATE (RFC 1951) decoder for BGZF blocks, written for one warp per block.
+// bkid_inflate.cuh -- DEFLATE (RFC 1951) decoder for BGZF blocks: ONE LANE PER BLOCK.
 //
 // Role in the reference: htslib's inflate_block / bgzf_read_block (thirdparty/samtools/samtools-1.3.1/
 // htslib-1.3.1/bgzf.c:388-419,545-600), i.e. zlib's inflate() called once per <= 64 KiB BGZF block.  BGZF blocks
-// are independent deflate streams, so a whole BAM decompresses block-parallel: one warp owns one block.
+// are independent deflate streams, so a whole BAM decompresses block-parallel.
 //
-// Execution model ("group-uniform decode"): a GROUP of GS lanes (GS = 8: four groups per warp, each on its own
-// BGZF block) runs the bit reader and the Huffman decode in lock step on the same data (shared-memory tables and
-// uniform global loads broadcast, no shuffles) and splits the only data-parallel part, the LZ77 match copy,
-// between its lanes.  An overlapping match (distance < length) is periodic in its first `distance` bytes, so
-// every output byte of a match can be fetched independently: out[op+k] = out[op - dist + k % dist].
-// The decoder is a resumable state machine (header_step / token_steps): the kernel drives all groups of a warp
-// through the same phase in the same instruction stream, so one issued instruction serves up to four blocks --
-// the first version (one block per warp) was instruction-issue bound at 31 warp-instructions per output byte.
+// Execution model.  Every lane of a warp owns its own BGZF block and runs an independent scalar decoder: private
+// Huffman tables in shared memory (2 KB per lane), a 64-bit bit buffer fed by aligned 32-bit loads issued one word
+// ahead, and an 8-byte PENDING WORD through which all output goes, so that the decoder issues one aligned 64-bit
+// store per 8 output bytes instead of byte stores (with 32 lanes on 32 different blocks every memory instruction
+// touches 32 different lines: the instruction count per byte, not coalescing, is what has to be small).  One
+// lane_step() decodes up to LITMAX literals, or one match token, and moves up to 8 match bytes: the source of a
+// match is read with two aligned 64-bit loads (or taken from the pending word when it has not been stored yet), an
+// overlapping match (distance < 8) is extended in registers (the output is periodic in `distance`).
+// A warp therefore advances 32 blocks per issued instruction.  The round-1 kernel ("group-uniform": 8 lanes per
+// block, all lanes decoding the same bits) needed 15.5 warp-instructions per output byte and 20 ms per 64 KiB block.
 //
-// The same source compiles as plain C++ (one "lane") so the decoder logic is unit-tested on the CPU against
-// zlib-compressed streams (tests/test_inflate_host.py) before it ever runs on the GPU.
+// The same source compiles as plain C++ so the decoder logic is unit-tested on the CPU against zlib-compressed
+// streams (tests/test_inflate_host.py) before it ever runs on the GPU.
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define BKI_FN __host__ __device__ __forceinline__
@@ -25,74 +28,63 @@
 #define BKI_FN inline
 #endif
 
-// lane geometry of a group of GS lanes (GS = 1 on the host)
-#if defined(__CUDA_ARCH__)
-#define BKI_GSIZE(GS) ((unsigned)(GS))
-#define BKI_GLANE(GS) (threadIdx.x & (unsigned)((GS) - 1))
-#define BKI_GSYNC(GS) __syncwarp((GS) == 32 ? 0xffffffffu : ((((GS) == 32 ? 0u : (1u << ((GS) & 31))) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)((GS) - 1))))
-#else
-#define BKI_GSIZE(GS) 1u
-#define BKI_GLANE(GS) 0u
-#define BKI_GSYNC(GS) ((void)0)
-#endif
-
 namespace bki {
 
-constexpr int FAST_LIT_BITS = 9;
-constexpr int FAST_DIST_BITS = 7;
+constexpr int LIT_BITS = 8;
+constexpr int DIST_BITS = 6;
 
-// per-group decode tables (shared memory on the device): 2.3 KB
-struct Tables {
-  uint16_t lit_fast[1 << FAST_LIT_BITS];     // (symbol << 4) | code length, 0 = longer than FAST_LIT_BITS
-  uint16_t dist_fast[1 << FAST_DIST_BITS];
-  uint16_t lit_count[16], dist_count[16];    // canonical code: number of codes of each length
-  uint16_t lit_sym[288], dist_sym[32];       // symbols ordered by (length, symbol)
-  uint8_t lens[320];                         // code lengths: literal/length then distance
+// per-lane decode tables (shared memory on the device): 1392 bytes, 43.5 KB per warp -> 5 warps per SM.  The number of
+// blocks in flight per SM is what this decoder's throughput scales with (it is latency-bound), hence the small root
+// tables: 96.4 % of the literal/length codes of a BAM stream are <= 8 bits (measured on the bench sample).
+struct Tab {
+  uint16_t lit_fast[1 << LIT_BITS];     // (symbol << 4) | code length; 0 = code longer than LIT_BITS (or unused).
+                                        // Doubles as the code-length scratch while a block header is read (320 of 512 bytes)
+  uint16_t lit_sym[288];                // symbols ordered by (length, symbol)
+  uint16_t lit_lim[16], lit_off[16];    // canonical code, left-justified to 15 bits: lim[l] = end of the codes of length l
+  uint16_t dist_fast[1 << DIST_BITS];
+  uint16_t dist_lim[16], dist_off[16];
+  uint8_t dist_sym[32];
+  uint8_t pad[16];
 };
+static_assert(sizeof(Tab) == 1392 && sizeof(Tab) % 16 == 0, "one lane's tables");
 
 enum Err { OK = 0, ERR_BTYPE = 1, ERR_STORED = 2, ERR_CODELEN = 3, ERR_OVERSUB = 4, ERR_SYMBOL = 5, ERR_DIST = 6, ERR_OUTPUT = 7, ERR_INPUT = 8, ERR_SIZE = 9 };
+enum Phase { PH_HEADER = 0, PH_TOKENS = 1, PH_STORED = 2, PH_DONE = 3 };
 
-struct BitReader {
-  const uint8_t *in; uint32_t len, pos; uint64_t buf; int cnt; int over;
-  uint32_t nextw; int have_next;          // the aligned 32-bit word after `pos`, loaded one refill ahead
-};
-
-BKI_FN void br_init(BitReader &b, const uint8_t *in, uint32_t len) { b.in = in; b.len = len; b.pos = 0; b.buf = 0; b.cnt = 0; b.over = 0; b.nextw = 0; b.have_next = 0; }
-BKI_FN void br_refill(BitReader &b)
+BKI_FN uint32_t ld32a(const uint8_t *p)
 {
-  // keep > 32 valid bits.  Aligned 32-bit loads where the payload allows, issued one refill AHEAD of their use so
-  // that the load latency hides behind the tokens decoded in between; bytes at a misaligned start and at the tail.
-  // Past the end zeros are shifted in and counted (reported as ERR_INPUT).
-  while (b.cnt <= 32) {
-    if (b.have_next) {
-      b.buf |= (uint64_t)b.nextw << b.cnt;
-      b.cnt += 32; b.pos += 4;
-      b.have_next = 0;
-      if (b.pos + 4 <= b.len) { b.nextw = *reinterpret_cast<const uint32_t *>(b.in + b.pos); b.have_next = 1; }
-      continue;
-    }
-    const uint8_t *p = b.in + b.pos;
-    if ((((uintptr_t)p) & 3u) == 0 && b.pos + 4 <= b.len) {
-      b.nextw = *reinterpret_cast<const uint32_t *>(p); b.have_next = 1;       // prime the pipeline
-      continue;
-    }
-    uint64_t v = 0;
-    if (b.pos < b.len) v = *p; else b.over++;
-    b.pos++;
-    b.buf |= v << b.cnt;
-    b.cnt += 8;
-  }
+#ifdef __CUDA_ARCH__
+  return *reinterpret_cast<const uint32_t *>(p);
+#else
+  uint32_t v; memcpy(&v, p, 4); return v;
+#endif
 }
-BKI_FN uint32_t br_peek(const BitReader &b, int n) { return (uint32_t)(b.buf & ((1ull << n) - 1ull)); }
-BKI_FN void br_drop(BitReader &b, int n) { b.buf >>= n; b.cnt -= n; }
-BKI_FN uint32_t br_bits(BitReader &b, int n)
+BKI_FN uint64_t ld64a(const uint8_t *p)
 {
-  if (b.cnt < n) br_refill(b);
-  uint32_t v = br_peek(b, n);
-  br_drop(b, n);
-  return v;
+#ifdef __CUDA_ARCH__
+  return *reinterpret_cast<const uint64_t *>(p);
+#else
+  uint64_t v; memcpy(&v, p, 8); return v;
+#endif
 }
-
+BKI_FN void st64a(uint8_t *p, uint64_t v)
+{
+#ifdef __CUDA_ARCH__
+  *reinterpret_cast<uint64_t *>(p) = v;
+#else
+  memcpy(p, &v, 8);
+#endif
+}
+BKI_FN uint32_t rev15(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+  return __brev(v) >> 17;
+#else
+  uint32_t r = 0;
+  for (int i = 0; i < 15; ++i) { r = (r << 1) | (v & 1u); v >>= 1; }
+  return r;
+#endif
+}
 BKI_FN uint32_t rev_bits(uint32_t v, int n)
 {
   uint32_t r = 0;
@@ -100,107 +92,133 @@ BKI_FN uint32_t rev_bits(uint32_t v, int n)
   return r;
 }
 
-// canonical Huffman tables from code lengths (lane 0 only; callers synchronise).  Returns 0, or ERR_OVERSUB for
-// an over-subscribed set.  Incomplete sets are accepted like zlib does for a single distance code.
-BKI_FN int build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sym, uint16_t *fast, int fast_bits)
+// One lane's stream state.  Output positions are offsets from `ob`, the 8-byte aligned address at or below the
+// block's first output byte: R0 = first byte, R = next byte, Rend = one past the last.
+struct Lane {
+  const uint8_t *in; uint32_t in_len, ipos;      // ipos: offset of the next (4-byte aligned) input word
+  uint64_t bits; uint32_t nbits, nextw;           // bit buffer, its fill, the word loaded one refill ahead
+  uint8_t *ob; uint32_t R, R0, Rend;
+  uint64_t pend; uint32_t head_lo;                // pending output word; first valid byte of the block's FIRST word (foreign bytes below)
+  uint32_t copy_rem, copy_dist, stored_rem;
+  int phase, last;
+};
+
+// The input may be read up to 16 bytes past `in_len` and 3 bytes before `in` (aligned word loads); the caller's
+// buffer provides that slack (BGZF: the next block's header / the staging buffer's padding).
+BKI_FN void lane_init(Lane &L, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len)
 {
+  uint32_t a = (uint32_t)((uintptr_t)in & 3u);
+  L.in = in; L.in_len = in_len;
+  L.bits = (uint64_t)(ld32a(in - a) >> (8u * a)); L.nbits = 32u - 8u * a; L.ipos = 4u - a;
+  L.nextw = ld32a(in + L.ipos);
+  uint32_t a0 = (uint32_t)((uintptr_t)out & 7u);
+  L.ob = out - a0; L.R0 = a0; L.R = a0; L.Rend = a0 + out_len;
+  L.pend = 0; L.head_lo = a0;
+  L.copy_rem = 0; L.copy_dist = 0; L.stored_rem = 0;
+  L.phase = PH_HEADER; L.last = 0;
+}
+
+// > 32 valid bits afterwards
+BKI_FN void refill(Lane &L)
+{
+  if (L.nbits <= 32u) {
+    L.bits |= (uint64_t)L.nextw << L.nbits;
+    L.nbits += 32u; L.ipos += 4u;
+    L.nextw = ld32a(L.in + L.ipos);
+  }
+}
+BKI_FN void drop(Lane &L, uint32_t n) { L.bits >>= n; L.nbits -= n; }
+BKI_FN uint32_t take(Lane &L, uint32_t n) { uint32_t v = (uint32_t)L.bits & ((1u << n) - 1u); drop(L, n); return v; }
+
+// canonical Huffman tables from code lengths.  Returns 0, or ERR_OVERSUB for an over-subscribed set; incomplete
+// sets are accepted (zlib accepts them for a single distance code; the unused code space decodes to an error).
+template <typename SYM>
+BKI_FN int build_table(const uint8_t *lens, int n, uint16_t *fast, int fast_bits, uint16_t *lim, uint16_t *off, SYM *sym)
+{
+  uint16_t count[16], offs[16];
   for (int l = 0; l < 16; ++l) count[l] = 0;
   for (int s = 0; s < n; ++s) count[lens[s]]++;
+  count[0] = 0;
   int left = 1;
   for (int l = 1; l < 16; ++l) { left <<= 1; left -= count[l]; if (left < 0) return ERR_OVERSUB; }
-  uint16_t offs[16];
-  offs[1] = 0;
+  offs[0] = 0; offs[1] = 0;
   for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
-  for (int s = 0; s < n; ++s) if (lens[s]) sym[offs[lens[s]]++] = (uint16_t)s;
+  uint32_t code = 0;
+  lim[0] = 0; off[0] = 0;
+  for (int l = 1; l < 16; ++l) {
+    code = (code + count[l - 1]) << 1;                       // first code of length l
+    lim[l] = (uint16_t)((code + count[l]) << (15 - l));      // <= 32768
+    off[l] = offs[l];
+  }
+  for (int s = 0; s < n; ++s) if (lens[s]) sym[offs[lens[s]]++] = (SYM)s;
   for (int i = 0; i < (1 << fast_bits); ++i) fast[i] = 0;
   // fast table: codes no longer than fast_bits, indexed by the next bits of the stream (LSB first)
-  uint32_t code = 0; int idx = 0;
+  code = 0;
   for (int l = 1; l <= fast_bits; ++l) {
-    for (int k = 0; k < count[l]; ++k, ++idx, ++code) {
-      uint32_t r = rev_bits(code, l);
-      uint16_t e = (uint16_t)((sym[idx] << 4) | l);
+    code = (code + count[l - 1]) << 1;
+    for (int k = 0; k < count[l]; ++k) {
+      uint32_t r = rev_bits(code + (uint32_t)k, l);
+      uint16_t e = (uint16_t)(((uint32_t)sym[off[l] + k] << 4) | (uint32_t)l);
       for (uint32_t j = r; j < (1u << fast_bits); j += (1u << l)) fast[j] = e;
     }
-    code <<= 1;
   }
   return 0;
 }
 
-// one symbol: fast table, else bit-serial canonical decode (codes longer than the fast table are rare)
-BKI_FN int decode_sym(BitReader &b, const uint16_t *fast, int fast_bits, const uint16_t *count, const uint16_t *sym)
+// codes longer than the fast table: compare the next 15 bits (in code order) against the per-length limits.  The
+// limits of all candidate lengths are loaded first (independent loads), then one compare chain finds the length.
+template <typename SYM, int FROM>
+BKI_FN int slow_sym(uint64_t bits, const uint16_t *lim, const uint16_t *off, const SYM *sym, uint32_t &len)
 {
-  if (b.cnt < 16) br_refill(b);
-  uint32_t e = fast[br_peek(b, fast_bits)];
-  if (e) { br_drop(b, (int)(e & 15u)); return (int)(e >> 4); }
-  int code = 0, first = 0, index = 0;
-  uint64_t bits = b.buf;
-  for (int l = 1; l <= 15; ++l) {
-    code |= (int)(bits & 1u); bits >>= 1;
-    int c = count[l];
-    if (code - c < first) { br_drop(b, l); return sym[index + (code - first)]; }
-    index += c; first += c; first <<= 1; code <<= 1;
-  }
-  return -1;
+  uint32_t v = rev15((uint32_t)bits & 0x7fffu);
+  uint32_t lm[17 - FROM];                                   // lim[FROM-1 .. 15]
+#pragma unroll
+  for (int k = 0; k < 17 - FROM; ++k) lm[k] = lim[FROM - 1 + k];
+  int l = 16; uint32_t lo = 0;
+#pragma unroll
+  for (int k = 16 - FROM; k >= 1; --k) if (v < lm[k]) { l = FROM - 1 + k; lo = lm[k - 1]; }
+  if (l > 15) return -1;
+  len = (uint32_t)l;
+  return (int)sym[off[l] + ((v - lo) >> (15 - l))];
 }
 
-enum Phase { PH_HEADER = 0, PH_TOKENS = 1, PH_DONE = 2 };
-
-struct Stream {
-  BitReader b;
-  uint8_t *out; uint32_t op, out_len;
-  int last, phase;
-};
-
-BKI_FN void stream_init(Stream &s, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len)
+// One deflate block header.  A stored block switches the lane to PH_STORED (the raw bytes then flow through the
+// bit buffer); a Huffman block gets its tables built and the lane moves to PH_TOKENS.
+BKI_FN int lane_header(Lane &L, Tab &T)
 {
-  br_init(s.b, in, in_len);
-  s.out = out; s.op = 0; s.out_len = out_len; s.last = 0; s.phase = PH_HEADER;
-}
-
-// one deflate block header: a stored block is copied whole; a Huffman block gets its tables built (lane 0 of the
-// group) and the stream moves to PH_TOKENS.  All lanes of the group call this with identical state.
-template <int GS>
-BKI_FN int header_step(Stream &s, Tables &T)
-{
-  const unsigned lane = BKI_GLANE(GS);
-  BitReader &b = s.b;
-  s.last = (int)br_bits(b, 1);
-  int type = (int)br_bits(b, 2);
+  refill(L);
+  L.last = (int)take(L, 1);
+  uint32_t type = take(L, 2);
   if (type == 0) {
-    // stored: skip to the byte boundary, LEN / NLEN, raw bytes
-    br_drop(b, b.cnt & 7);
-    uint32_t len = br_bits(b, 16), nlen = br_bits(b, 16);
+    drop(L, L.nbits & 7u);                                  // to the byte boundary (ipos * 8 is a multiple of 8)
+    refill(L);
+    uint32_t len = take(L, 16), nlen = take(L, 16);
     if ((len ^ 0xffffu) != nlen) return ERR_STORED;
-    uint32_t src = b.pos - (uint32_t)(b.cnt >> 3);        // bytes still in the bit buffer are at in[pos - cnt/8 ...]
-    if (src + len > b.len) return ERR_INPUT;
-    if (s.op + len > s.out_len) return ERR_OUTPUT;
-    for (uint32_t k = lane; k < len; k += BKI_GSIZE(GS)) s.out[s.op + k] = b.in[src + k];
-    s.op += len;
-    const uint8_t *in = b.in; uint32_t in_len = b.len;
-    br_init(b, in, in_len); b.pos = src + len;
-    s.phase = s.last ? PH_DONE : PH_HEADER;
+    uint32_t at = L.ipos - (L.nbits >> 3);                  // byte offset of the first raw byte
+    if (at + len > L.in_len) return ERR_INPUT;
+    if (L.R + len > L.Rend) return ERR_OUTPUT;
+    L.stored_rem = len;
+    L.phase = len ? PH_STORED : (L.last ? PH_DONE : PH_HEADER);
     return OK;
   }
   if (type == 3) return ERR_BTYPE;
-  int err = 0;
-  BKI_GSYNC(GS);                                          // previous block's table reads are done
+  uint8_t *lens = reinterpret_cast<uint8_t *>(T.lit_fast);    // 320 bytes of scratch: build_table reads the lengths before it fills `fast`
+  int nlen, ndist;
   if (type == 1) {
-    if (lane == 0) {
-      for (int k = 0; k < 144; ++k) T.lens[k] = 8;
-      for (int k = 144; k < 256; ++k) T.lens[k] = 9;
-      for (int k = 256; k < 280; ++k) T.lens[k] = 7;
-      for (int k = 280; k < 288; ++k) T.lens[k] = 8;
-      for (int k = 0; k < 30; ++k) T.lens[288 + k] = 5;
-      build(T.lens, 288, T.lit_count, T.lit_sym, T.lit_fast, FAST_LIT_BITS);
-      build(T.lens + 288, 30, T.dist_count, T.dist_sym, T.dist_fast, FAST_DIST_BITS);
-    }
+    nlen = 288; ndist = 30;
+    for (int k = 0; k < 144; ++k) lens[k] = 8;
+    for (int k = 144; k < 256; ++k) lens[k] = 9;
+    for (int k = 256; k < 280; ++k) lens[k] = 7;
+    for (int k = 280; k < 288; ++k) lens[k] = 8;
+    for (int k = 0; k < 30; ++k) lens[288 + k] = 5;
   } else {
-    int nlen = (int)br_bits(b, 5) + 257, ndist = (int)br_bits(b, 5) + 1, ncode = (int)br_bits(b, 4) + 4;
+    nlen = (int)take(L, 5) + 257; ndist = (int)take(L, 5) + 1;
+    int ncode = (int)take(L, 4) + 4;
     if (nlen > 286 || ndist > 30) return ERR_CODELEN;
-    // code-length code: 19 symbols of <= 7 bits, decoded bit-serially from per-lane (uniform) registers
+    // code-length code: 19 symbols of <= 7 bits, kept in registers and decoded bit-serially
     const char *order = "\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f";
     uint64_t cl = 0;                                      // 19 x 3 bits
-    for (int i = 0; i < ncode; ++i) cl |= (uint64_t)br_bits(b, 3) << (3 * (int)order[i]);
+    for (int i = 0; i < ncode; ++i) { refill(L); cl |= (uint64_t)take(L, 3) << (3 * (int)order[i]); }
     int cl_count[8], cl_offs[8];
     for (int l = 0; l < 8; ++l) cl_count[l] = 0;
     for (int k = 0; k < 19; ++k) cl_count[(cl >> (3 * k)) & 7]++;
@@ -219,114 +237,174 @@ BKI_FN int header_step(Stream &s, Tables &T)
     }
     int total = nlen + ndist, i = 0, prev = 0;
     while (i < total) {
-      if (b.cnt < 16) br_refill(b);
+      refill(L);
+      if (L.ipos > L.in_len + 16u) return ERR_INPUT;
       int code = 0, first = 0, index = 0, sym = -1;
-      uint64_t bits = b.buf;
+      uint64_t b = L.bits;
       for (int l = 1; l <= 7; ++l) {
-        code |= (int)(bits & 1u); bits >>= 1;
+        code |= (int)(b & 1u); b >>= 1;
         int c = cl_count[l];
         if (code - c < first) {
           int q = index + (code - first);
           sym = (int)((q < 12 ? (cl_sym_lo >> (5 * q)) : (cl_sym_hi >> (5 * (q - 12)))) & 31);
-          br_drop(b, l);
+          drop(L, (uint32_t)l);
           break;
         }
         index += c; first += c; first <<= 1; code <<= 1;
       }
       if (sym < 0) return ERR_CODELEN;
-      if (sym < 16) { if (lane == 0) T.lens[i] = (uint8_t)sym; prev = sym; ++i; }
+      if (sym < 16) { lens[i] = (uint8_t)sym; prev = sym; ++i; }
       else {
         int rep, val = 0;
-        if (sym == 16) { if (i == 0) return ERR_CODELEN; val = prev; rep = 3 + (int)br_bits(b, 2); }
-        else if (sym == 17) rep = 3 + (int)br_bits(b, 3);
-        else rep = 11 + (int)br_bits(b, 7);
+        if (sym == 16) { if (i == 0) return ERR_CODELEN; val = prev; rep = 3 + (int)take(L, 2); }
+        else if (sym == 17) rep = 3 + (int)take(L, 3);
+        else rep = 11 + (int)take(L, 7);
         if (i + rep > total) return ERR_CODELEN;
-        if (lane == 0) for (int k = 0; k < rep; ++k) T.lens[i + k] = (uint8_t)val;
+        for (int k = 0; k < rep; ++k) lens[i + k] = (uint8_t)val;
         i += rep; prev = val;
       }
     }
-    if (lane == 0) {
-      // the distance lengths follow the literal/length lengths directly: move them to their own slot
-      uint8_t tmp[32];
-      for (int k = 0; k < ndist; ++k) tmp[k] = T.lens[nlen + k];
-      for (int k = nlen; k < 288; ++k) T.lens[k] = 0;
-      for (int k = 0; k < 32; ++k) T.lens[288 + k] = k < ndist ? tmp[k] : 0;
-      int e1 = build(T.lens, 288, T.lit_count, T.lit_sym, T.lit_fast, FAST_LIT_BITS);
-      int e2 = build(T.lens + 288, 32, T.dist_count, T.dist_sym, T.dist_fast, FAST_DIST_BITS);
-      T.lens[0] = (uint8_t)(e1 | e2);                     // status for the other lanes (lens[] is scratch from here on)
-    }
-    BKI_GSYNC(GS);
-    err = T.lens[0] ? ERR_OVERSUB : 0;
   }
-  BKI_GSYNC(GS);
-  if (err) return err;
-  s.phase = PH_TOKENS;
+  // distances first: the literal/length build ends by overwriting the scratch with its fast table
+  int e2 = build_table<uint8_t>(lens + nlen, ndist, T.dist_fast, DIST_BITS, T.dist_lim, T.dist_off, T.dist_sym);
+  int e1 = build_table<uint16_t>(lens, nlen, T.lit_fast, LIT_BITS, T.lit_lim, T.lit_off, T.lit_sym);
+  if (e1 | e2) return ERR_OVERSUB;
+  L.phase = PH_TOKENS;
   return OK;
 }
 
-// up to `max_tokens` literal / match tokens of the current Huffman block; at the end-of-block symbol the stream moves
-// on to PH_HEADER or PH_DONE
-template <int GS>
-BKI_FN int token_steps(Stream &s, const Tables &T, int max_tokens)
+BKI_FN void flush_word(Lane &L, uint32_t W)
 {
-  const unsigned lane = BKI_GLANE(GS);
-  BitReader &b = s.b;
-  for (int n = 0; n < max_tokens; ++n) {
-    int sym = decode_sym(b, T.lit_fast, FAST_LIT_BITS, T.lit_count, T.lit_sym);
-    if (sym < 0) return ERR_SYMBOL;
-    if (sym < 256) {
-      if (s.op >= s.out_len) return ERR_OUTPUT;
-      if (lane == 0) s.out[s.op] = (uint8_t)sym;
-      ++s.op;
-      continue;
-    }
-    if (sym == 256) { s.phase = s.last ? PH_DONE : PH_HEADER; return OK; }
-    if (sym > 285) return ERR_SYMBOL;
-    uint32_t len;
-    if (sym < 265) len = (uint32_t)sym - 254u;
-    else if (sym == 285) len = 258u;
-    else {
-      int e = (sym - 261) >> 2;
-      len = ((4u + (uint32_t)((sym - 261) & 3)) << e) + 3u + br_bits(b, e);
-    }
-    int ds = decode_sym(b, T.dist_fast, FAST_DIST_BITS, T.dist_count, T.dist_sym);
-    if (ds < 0 || ds > 29) return ERR_DIST;
-    uint32_t dist;
-    if (ds < 4) dist = (uint32_t)ds + 1u;
-    else {
-      int e = (ds >> 1) - 1;
-      dist = ((2u + (uint32_t)(ds & 1)) << e) + 1u + br_bits(b, e);
-    }
-    if (dist > s.op) return ERR_DIST;
-    if (s.op + len > s.out_len) return ERR_OUTPUT;
-    BKI_GSYNC(GS);                                        // bytes written by other lanes of the group are visible before the copy reads them
-    const uint8_t *src = s.out + (s.op - dist);
-    uint8_t *dst = s.out + s.op;
-    if (dist >= len) { for (uint32_t k = lane; k < len; k += BKI_GSIZE(GS)) dst[k] = src[k]; }
-    else { for (uint32_t k = lane; k < len; k += BKI_GSIZE(GS)) dst[k] = src[k % dist]; }
-    s.op += len;
+  if (L.head_lo) {                                           // the block's first word: the bytes below head_lo belong to the previous block
+    for (uint32_t b = L.head_lo; b < 8u; ++b) L.ob[W + b] = (uint8_t)(L.pend >> (8u * b));
+    L.head_lo = 0;
+  } else st64a(L.ob + W, L.pend);
+}
+
+// append the n (1..8) low bytes of v (higher bytes zero)
+BKI_FN void emit(Lane &L, uint64_t v, uint32_t n)
+{
+  uint32_t k = L.R & 7u;
+  L.pend |= v << (8u * k);
+  if (k + n >= 8u) {
+    flush_word(L, L.R & ~7u);
+    L.pend = k ? v >> (64u - 8u * k) : 0ull;
   }
+  L.R += n;
+}
+
+// One step of a lane in PH_TOKENS / PH_STORED: up to LITMAX literals, or one match token, plus up to 8 match bytes.
+template <int LITMAX>
+BKI_FN int lane_step(Lane &L, const Tab &T)
+{
+  uint64_t v = 0; uint32_t n = 0;
+  if (L.phase == PH_STORED) {
+    refill(L);
+    n = L.stored_rem < 4u ? L.stored_rem : 4u;
+    v = L.bits & ((1ull << (8u * n)) - 1ull);
+    drop(L, 8u * n);
+    L.stored_rem -= n;
+    if (L.stored_rem == 0) L.phase = L.last ? PH_DONE : PH_HEADER;
+  } else {
+    if (L.copy_rem == 0) {
+      refill(L);
+      if (L.ipos > L.in_len + 16u) return ERR_INPUT;         // a corrupt stream cannot run away from its payload
+      uint32_t e = T.lit_fast[(uint32_t)L.bits & ((1u << LIT_BITS) - 1u)], len;
+      int sym;
+      if (e) { len = e & 15u; sym = (int)(e >> 4); }
+      else { sym = slow_sym<uint16_t, LIT_BITS + 1>(L.bits, T.lit_lim, T.lit_off, T.lit_sym, len); if (sym < 0) return ERR_SYMBOL; }
+      drop(L, len);
+      if (sym < 256) {
+        v = (uint64_t)sym; n = 1;
+#pragma unroll
+        for (int j = 1; j < LITMAX; ++j) {
+          refill(L);
+          uint32_t e2 = T.lit_fast[(uint32_t)L.bits & ((1u << LIT_BITS) - 1u)];
+          if (e2 == 0 || e2 >= (256u << 4)) break;
+          drop(L, e2 & 15u);
+          v |= (uint64_t)(e2 >> 4) << (8u * n);
+          ++n;
+        }
+        if (L.R + n > L.Rend) return ERR_OUTPUT;
+      } else if (sym == 256) {
+        L.phase = L.last ? PH_DONE : PH_HEADER;
+        return OK;
+      } else {
+        if (sym > 285) return ERR_SYMBOL;
+        uint32_t mlen;
+        if (sym < 265) mlen = (uint32_t)sym - 254u;
+        else if (sym == 285) mlen = 258u;
+        else {
+          uint32_t eb = (uint32_t)(sym - 261) >> 2;
+          mlen = ((4u + ((uint32_t)(sym - 261) & 3u)) << eb) + 3u + take(L, eb);
+        }
+        refill(L);
+        uint32_t ed = T.dist_fast[(uint32_t)L.bits & ((1u << DIST_BITS) - 1u)], dl;
+        int ds;
+        if (ed) { dl = ed & 15u; ds = (int)(ed >> 4); }
+        else { ds = slow_sym<uint8_t, DIST_BITS + 1>(L.bits, T.dist_lim, T.dist_off, T.dist_sym, dl); if (ds < 0) return ERR_DIST; }
+        drop(L, dl);
+        if (ds > 29) return ERR_DIST;
+        uint32_t dist;
+        if (ds < 4) dist = (uint32_t)ds + 1u;
+        else {
+          uint32_t eb = ((uint32_t)ds >> 1) - 1u;
+          dist = ((2u + ((uint32_t)ds & 1u)) << eb) + 1u + take(L, eb);
+        }
+        if (dist > L.R - L.R0) return ERR_DIST;
+        if (L.R + mlen > L.Rend) return ERR_OUTPUT;
+        L.copy_rem = mlen; L.copy_dist = dist;
+      }
+    }
+    if (L.copy_rem) {
+      // up to 8 bytes of the match.  Source position S < R; words below the pending word are in memory already.
+      uint32_t S = L.R - L.copy_dist, Ws = S & ~7u, s = S & 7u, Wb = L.R & ~7u;
+      uint64_t m0 = (Ws == Wb) ? L.pend : ld64a(L.ob + Ws);
+      v = m0;
+      if (s) {
+        uint32_t W1 = Ws + 8u;
+        uint64_t m1 = (W1 == Wb) ? L.pend : (W1 < Wb ? ld64a(L.ob + W1) : 0ull);
+        v = (m0 >> (8u * s)) | (m1 << (64u - 8u * s));
+      }
+      if (L.copy_dist < 8u) {                                // overlapping match: the output is periodic in `dist`
+        uint32_t sh = 8u * L.copy_dist;
+        v &= (1ull << sh) - 1ull;
+        v |= v << sh;
+        if (2u * sh < 64u) v |= v << (2u * sh);
+        if (4u * sh < 64u) v |= v << (4u * sh);
+      }
+      n = L.copy_rem < 8u ? L.copy_rem : 8u;
+      if (n < 8u) v &= (1ull << (8u * n)) - 1ull;
+      L.copy_rem -= n;
+    }
+  }
+  if (n) emit(L, v, n);
   return OK;
 }
 
-BKI_FN int stream_finish(const Stream &s)
+// end of the stream: store the bytes still pending, check the sizes
+BKI_FN int lane_finish(Lane &L)
 {
-  if (s.b.over > 8) return ERR_INPUT;                     // consumed bits beyond the payload (refill looks <= 5 bytes ahead)
-  return s.op == s.out_len ? OK : ERR_SIZE;
+  uint32_t k = L.R & 7u;
+  if (k) {
+    uint32_t W = L.R & ~7u;
+    for (uint32_t b = L.head_lo; b < k; ++b) L.ob[W + b] = (uint8_t)(L.pend >> (8u * b));
+  }
+  if ((uint64_t)L.ipos * 8u - L.nbits > (uint64_t)L.in_len * 8u) return ERR_INPUT;   // consumed bits beyond the payload
+  return L.R == L.Rend ? OK : ERR_SIZE;
 }
 
-// Inflate one raw deflate stream of `in_len` bytes into exactly `out_len` bytes (one group, run to completion).
-template <int GS>
-BKI_FN int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, Tables &T)
+// Inflate one raw deflate stream of `in_len` bytes into exactly `out_len` bytes (one lane, run to completion).
+template <int LITMAX>
+BKI_FN int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, Tab &T)
 {
-  Stream s;
-  stream_init(s, in, in_len, out, out_len);
-  while (s.phase != PH_DONE) {
-    int rc = s.phase == PH_HEADER ? header_step<GS>(s, T) : token_steps<GS>(s, T, 1 << 30);
+  Lane L;
+  lane_init(L, in, in_len, out, out_len);
+  while (L.phase != PH_DONE) {
+    int rc = L.phase == PH_HEADER ? lane_header(L, T) : lane_step<LITMAX>(L, T);
     if (rc) return rc;
   }
-  BKI_GSYNC(GS);
-  return stream_finish(s);
+  return lane_finish(L);
 }
 
 // ---- CRC-32 (gzip / zlib polynomial, reflected) ------------------------------------------------------------------

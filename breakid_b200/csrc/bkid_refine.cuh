@@ -160,7 +160,7 @@ static_assert(sizeof(EvRow) == 88 || sizeof(EvRow) == 96, "EvRow layout");
 
 // K7a: one thread per SA-tagged record -- src/BreakID.cc:896-1016
 __global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long n_sa, const uint8_t *__restrict__ cls, const uint16_t *__restrict__ flag, const int32_t *__restrict__ tid,
-                                 const int32_t *__restrict__ pos, const int32_t *__restrict__ endpos, const uint32_t *__restrict__ x_rec, long long n_x,
+                                 const int32_t *__restrict__ pos, const int32_t *__restrict__ endpos, const uint16_t *__restrict__ span16, const uint32_t *__restrict__ x_rec, long long n_x,
                                  const uint64_t *__restrict__ x_nh, int *__restrict__ missing, const uint32_t *__restrict__ cig_off, const uint32_t *__restrict__ cig_ops,
                                  const uint32_t *__restrict__ sa_off, const uint8_t *__restrict__ sa_txt, const uint32_t *__restrict__ oc_off,
                                  const uint8_t *__restrict__ oc_txt, int mismatch, EvRow *__restrict__ rows)
@@ -171,7 +171,7 @@ __global__ void k7_evidence_rows(const uint32_t *__restrict__ sa_rec, long long 
   memset(&R, 0, sizeof R);
   uint32_t i = sa_rec[k];
   unsigned fl = flag[i];
-  R.tid = tid[i]; R.pos = pos[i]; R.endpos = endpos[i];
+  R.tid = tid[i]; R.pos = pos[i]; R.endpos = endpos ? endpos[i] : pos[i] + (int32_t)span16[i];
   {
     long long x = x_slot_of(x_rec, n_x, i);
     if (x < 0) atomicExch(missing, 1);
@@ -267,7 +267,8 @@ struct RegionQ {        // one side of one cluster
 
 struct RefineView {
   // local record shard (coverage / depth partial counts)
-  long long n; const uint8_t *cls; const int32_t *tid, *pos, *endpos;
+  long long n; const uint8_t *cls; const int32_t *tid, *pos, *endpos; const uint16_t *span16;   // bam_endpos: endpos[i], or pos[i] + span16[i] (narrow column)
+  __device__ __forceinline__ int32_t end_of(long long i) const { return endpos ? endpos[i] : pos[i] + (int32_t)span16[i]; }
   // global SA-row table in coordinate order (evidence)
   long long n_sa; const EvRow *rows;
   const uint64_t *name_key; const uint32_t *name_row;   // rows ordered by the low 32 bits of name_lo (evidence pairing)
@@ -332,7 +333,7 @@ __device__ unsigned count_overlaps(const RefineView &v, int tid, int beg, int en
   long long hi = rec_lower_bound(v.tid, v.pos, v.n, tid, (long long)end);
   unsigned c = 0;
   for (long long i = lo + (threadIdx.x & 31); i < hi; i += 32)
-    if (v.endpos[i] > beg && (depth_only ? (v.cls[i] & CL_DEPTH) : !(v.cls[i] & CL_EXCL))) ++c;
+    if (v.end_of(i) > beg && (depth_only ? (v.cls[i] & CL_DEPTH) : !(v.cls[i] & CL_EXCL))) ++c;
   return bk::warp_sum(c);
 }
 

@@ -136,105 +136,182 @@ static inline void exclusive_scan(const InT *in, OutT *out, long long n, unsigne
 static inline size_t scan_tmp_elems(long long n) { return (size_t)div_up(n > 0 ? n : 1, SCAN_TILE) + 1; }
 
 // ---------------------------------------------------------------------------------------------
-// stable LSD radix sort, 8-bit digits, (uint64 key, uint32 value).
-// Per pass: histogram per chunk (RS_CHUNK elements per block), column scan, ranked scatter.
-// Ranking inside a block: elements are taken in rounds of blockDim; within a round warp w lane l
-// holds element w*32+l; __match_any_sync groups equal digits inside a warp; per-(round,warp) digit
-// counts are prefix-summed per digit by one thread per digit.  This is the classic stable
-// multi-split; it keeps the pass at one read of keys for the histogram and one read+write of
-// keys+values for the scatter.
+// stable LSD radix sort on (uint64 key, uint32 value), 8-bit digits, ONESWEEP form:
+//   os_hist       one pass over the keys builds the digit histograms of ALL passes (shared-memory atomics, one
+//                 global atomicAdd per bin and CTA); os_hist_scan turns them into exclusive digit offsets
+//   os_pass       one kernel per digit: a CTA takes the next tile from an atomic ticket, ranks its 4096 keys
+//                 (match-any inside a warp, per-warp digit counters, no atomics), publishes its digit counts and
+//                 resolves "keys with this digit in earlier tiles" by decoupled look-back over the tile status
+//                 words (flag + count in ONE 32-bit word, so no fence protocol), reorders the tile in shared
+//                 memory and writes every digit run as one contiguous, coalesced range.
+// A 64-bit sort is 2 + 8 launches and reads the keys once for the histograms plus once per pass, instead of the
+// 40 launches (histogram + 3-kernel scan + uncoalesced scatter per pass) of the round-1 LSD sort.
+// The element count may live on the device (n_dev): grids are sized from a host upper bound, late tiles exit.
+// Elements per sort < 2^30 (tile status words carry 30-bit counts); everything sorted here is candidate-sized.
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
-constexpr int RS_ROUNDS = 8;                       // elements per thread per block
-constexpr int RS_CHUNK = RS_THREADS * RS_ROUNDS;   // 2048 elements per block
-constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int OS_THREADS = 256;
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_ITEMS = 16;
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;          // 4096 keys per tile
+constexpr int OS_MAX_PASSES = 8;
+constexpr unsigned OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VAL_MASK = (1u << 30) - 1u;
+constexpr size_t OS_SMEM = (size_t)OS_TILE * 12 + (size_t)OS_WARPS * 256 * 4 + 2 * 256 * 4 + 40 * 4;
 
-__global__ void __launch_bounds__(RS_THREADS) rs_histogram(const uint64_t *__restrict__ keys, long long n, int shift, uint32_t *__restrict__ hist /*[256][nblocks]*/, int nblocks)
+__global__ void __launch_bounds__(256) os_hist(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ n_dev, uint32_t n_host, int lo_bit, int npass,
+                                               uint32_t *__restrict__ ghist /* [npass][256] */)
 {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
+  __shared__ uint32_t h[OS_MAX_PASSES][256];
+  for (int p = 0; p < npass; ++p) h[p][threadIdx.x] = 0;
   __syncthreads();
-  long long base = (long long)blockIdx.x * RS_CHUNK;
-#pragma unroll
-  for (int r = 0; r < RS_ROUNDS; ++r) {
-    long long i = base + r * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  const uint32_t n = n_dev ? *n_dev : n_host;
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+    uint64_t k = keys[i] >> lo_bit;
+    for (int p = 0; p < npass; ++p) { atomicAdd(&h[p][(uint32_t)k & 255u], 1u); k >>= 8; }
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  for (int p = 0; p < npass; ++p) { uint32_t v = h[p][threadIdx.x]; if (v) atomicAdd(&ghist[p * 256 + threadIdx.x], v); }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, long long n, int shift,
-                                                         const uint32_t *__restrict__ hist_scanned, int nblocks,
-                                                         uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+__global__ void __launch_bounds__(256) os_hist_scan(uint32_t *__restrict__ ghist, int npass)
 {
-  __shared__ uint16_t cnt[RS_ROUNDS * RS_WARPS][256];   // 32 KB
-  __shared__ uint32_t goff[256];
-  for (int i = threadIdx.x; i < RS_ROUNDS * RS_WARPS * 256 / 2; i += RS_THREADS) ((uint32_t *)cnt)[i] = 0;
-  goff[threadIdx.x] = hist_scanned[(size_t)threadIdx.x * nblocks + blockIdx.x];
+  __shared__ uint32_t sh[33];
+  for (int p = 0; p < npass; ++p) {
+    uint32_t v = ghist[p * 256 + threadIdx.x], tot;
+    uint32_t ex = block_excl_scan<uint32_t>(v, sh, tot);
+    ghist[p * 256 + threadIdx.x] = ex;
+  }
+}
+
+__global__ void __launch_bounds__(OS_THREADS) os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
+                                                      const uint32_t *__restrict__ n_dev, uint32_t n_host, int shift, const uint32_t *__restrict__ ghist_excl,
+                                                      uint32_t *__restrict__ status /* [ntiles][256], zeroed */, uint32_t *__restrict__ ticket)
+{
+  extern __shared__ __align__(16) unsigned char os_smem[];
+  uint64_t *skey = reinterpret_cast<uint64_t *>(os_smem);
+  uint32_t *sval = reinterpret_cast<uint32_t *>(os_smem + (size_t)OS_TILE * 8);
+  uint32_t *whist = sval + OS_TILE;                 // [OS_WARPS][256]
+  uint32_t *toff = whist + OS_WARPS * 256;          // [256] first slot of digit d inside the reordered tile
+  uint32_t *gbase = toff + 256;                     // [256] global slot of the first key of digit d of this tile
+  uint32_t *misc = gbase + 256;                     // [0] tile id, [1..33] scan scratch
+  if (threadIdx.x == 0) misc[0] = atomicAdd(ticket, 1u);
+  for (int i = threadIdx.x; i < OS_WARPS * 256; i += OS_THREADS) whist[i] = 0;
   __syncthreads();
-  long long base = (long long)blockIdx.x * RS_CHUNK;
-  unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  uint64_t k[RS_ROUNDS];
-  uint32_t v[RS_ROUNDS];
-  uint16_t rank_in_warp[RS_ROUNDS];
+  const uint32_t tile = misc[0];
+  const uint32_t n = n_dev ? *n_dev : n_host;
+  const uint32_t base = tile * (uint32_t)OS_TILE;
+  if (base >= n) return;                             // tickets are handed out in order: no earlier tile waits on this one
+  const uint32_t cnt = min((uint32_t)OS_TILE, n - base);
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31, ltmask = (1u << l) - 1u;
+  uint64_t k[OS_ITEMS];
+  uint32_t v[OS_ITEMS];
+  uint16_t rk[OS_ITEMS];
+  // warp w owns the contiguous slice [w * 32 * ITEMS, ...): element order inside the tile = (warp, round, lane)
 #pragma unroll
-  for (int r = 0; r < RS_ROUNDS; ++r) {
-    long long i = base + r * RS_THREADS + threadIdx.x;
-    bool ok = i < n;
-    k[r] = ok ? keys[i] : ~0ull;
-    v[r] = ok ? vals[i] : 0u;
-    unsigned d = ok ? (unsigned)((k[r] >> shift) & 255u) : 256u;
+  for (int r = 0; r < OS_ITEMS; ++r) {
+    uint32_t i = w * (32u * OS_ITEMS) + (uint32_t)r * 32u + l;
+    bool ok = i < cnt;
+    k[r] = ok ? kin[base + i] : ~0ull;
+    v[r] = ok ? vin[base + i] : 0u;
+  }
+  uint32_t *wh = whist + w * 256;
+#pragma unroll
+  for (int r = 0; r < OS_ITEMS; ++r) {
+    uint32_t i = w * (32u * OS_ITEMS) + (uint32_t)r * 32u + l;
+    bool ok = i < cnt;
+    unsigned d = ok ? (unsigned)(k[r] >> shift) & 255u : 256u;
     unsigned m = __match_any_sync(0xffffffffu, d);
-    rank_in_warp[r] = (uint16_t)__popc(m & ((1u << l) - 1u));
-    if (ok && rank_in_warp[r] == 0) cnt[r * RS_WARPS + w][d] = (uint16_t)__popc(m);
+    int leader = __ffs(m) - 1;
+    uint32_t old = 0;
+    if ((int)l == leader && ok) { old = wh[d]; wh[d] = old + __popc(m); }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rk[r] = (uint16_t)(old + __popc(m & ltmask));
+    __syncwarp();
   }
   __syncthreads();
-  {  // exclusive prefix over the (round, warp) slots for digit = threadIdx.x
-    unsigned d = threadIdx.x, run = 0;
-#pragma unroll 4
-    for (int s = 0; s < RS_ROUNDS * RS_WARPS; ++s) { unsigned c = cnt[s][d]; cnt[s][d] = (uint16_t)run; run += c; }
+  // digit d = threadIdx.x: exclusive prefix over the warps, tile total
+  uint32_t c = 0;
+  {
+    const unsigned d = threadIdx.x;
+#pragma unroll
+    for (int ww = 0; ww < OS_WARPS; ++ww) { uint32_t t = whist[ww * 256 + d]; whist[ww * 256 + d] = c; c += t; }
+    volatile uint32_t *st = status + (size_t)tile * 256 + d;
+    if (tile == 0) *st = OS_FLAG_PREFIX | c;
+    else {
+      *st = OS_FLAG_AGG | c;
+      uint32_t excl = 0;
+      for (int t = (int)tile - 1; t >= 0; --t) {
+        volatile uint32_t *q = status + (size_t)t * 256 + d;
+        uint32_t sv;
+        do { sv = *q; } while ((sv >> 30) == 0u);
+        excl += sv & OS_VAL_MASK;
+        if ((sv >> 30) == 2u) break;
+      }
+      *st = OS_FLAG_PREFIX | (excl + c);
+      gbase[d] = ghist_excl[d] + excl;
+    }
+    if (tile == 0) gbase[d] = ghist_excl[d];
+    uint32_t tot;
+    toff[d] = block_excl_scan<uint32_t>(c, misc + 1, tot);
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < RS_ROUNDS; ++r) {
-    long long i = base + r * RS_THREADS + threadIdx.x;
-    if (i < n) {
-      unsigned d = (unsigned)((k[r] >> shift) & 255u);
-      uint32_t dst = goff[d] + cnt[r * RS_WARPS + w][d] + rank_in_warp[r];
-      keys_out[dst] = k[r];
-      vals_out[dst] = v[r];
+  for (int r = 0; r < OS_ITEMS; ++r) {
+    uint32_t i = w * (32u * OS_ITEMS) + (uint32_t)r * 32u + l;
+    if (i < cnt) {
+      unsigned d = (unsigned)(k[r] >> shift) & 255u;
+      uint32_t pos = toff[d] + wh[d] + rk[r];
+      skey[pos] = k[r]; sval[pos] = v[r];
     }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < cnt; i += OS_THREADS) {
+    uint64_t kk = skey[i];
+    unsigned d = (unsigned)(kk >> shift) & 255u;
+    uint32_t dst = gbase[d] + (i - toff[d]);
+    kout[dst] = kk; vout[dst] = sval[i];
   }
 }
 
 struct RadixTmp {
   uint64_t *keys_alt; uint32_t *vals_alt; uint32_t *hist; unsigned long long *scan_tmp;
 };
-static inline size_t radix_hist_elems(long long n) { return (size_t)256 * (size_t)div_up(n > 0 ? n : 1, RS_CHUNK); }
-
-// sorts by bits [lo_bit, hi_bit) of the key; result is left in (keys, vals) (copies back if the
-// number of passes is odd).  Stable.
-static inline int radix_sort_pairs(uint64_t *keys, uint32_t *vals, long long n, int lo_bit, int hi_bit, const RadixTmp &t, cudaStream_t st)
+// work space of one sort in 32-bit words: digit histograms of all passes, the tickets, the tile status words of all passes
+static inline size_t radix_hist_elems(long long n)
 {
-  if (n <= 1) return 0;
-  int nblocks = div_up(n, RS_CHUNK);
+  size_t tiles = (size_t)div_up(n > 0 ? n : 1, OS_TILE);
+  return (size_t)OS_MAX_PASSES * 256 + 64 + (size_t)OS_MAX_PASSES * tiles * 256;
+}
+
+// sorts by bits [lo_bit, hi_bit) of the key; result is left in (keys, vals) (copies back if the number of passes is
+// odd).  Stable.  n = host upper bound of the element count; n_dev (optional) = exact count on the device.
+static inline int radix_sort_pairs(uint64_t *keys, uint32_t *vals, long long n, int lo_bit, int hi_bit, const RadixTmp &t, cudaStream_t st, const uint32_t *n_dev = nullptr)
+{
+  if (n <= 1 || hi_bit <= lo_bit) return 0;
+  if (n >= (1ll << 30)) return -1;
+  static bool attr_set = false;                       // per process; the attribute is per device function (set again per device below)
+  static int attr_dev = -1;
+  int dev = 0; cudaGetDevice(&dev);
+  if (!attr_set || attr_dev != dev) { cudaFuncSetAttribute(os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OS_SMEM); attr_set = true; attr_dev = dev; }
+  int npass = (hi_bit - lo_bit + 7) / 8;
+  if (npass > OS_MAX_PASSES) npass = OS_MAX_PASSES;
+  int ntiles = div_up(n, OS_TILE);
+  uint32_t *ghist = t.hist, *tickets = t.hist + OS_MAX_PASSES * 256, *status = t.hist + OS_MAX_PASSES * 256 + 64;
+  cudaMemsetAsync(t.hist, 0, ((size_t)OS_MAX_PASSES * 256 + 64 + (size_t)npass * ntiles * 256) * 4, st);
+  int hgrid = ntiles < 148 * 8 ? ntiles : 148 * 8;
+  BK_LAUNCH(os_hist, hgrid, 256, 0, st, keys, n_dev, (uint32_t)n, lo_bit, npass, ghist);
+  BK_LAUNCH(os_hist_scan, 1, 256, 0, st, ghist, npass);
   uint64_t *ki = keys, *ko = t.keys_alt;
   uint32_t *vi = vals, *vo = t.vals_alt;
-  int passes = 0;
-  for (int shift = lo_bit; shift < hi_bit; shift += 8) {
-    BK_LAUNCH(rs_histogram, nblocks, RS_THREADS, 0, st, ki, n, shift, t.hist, nblocks);
-    exclusive_scan<uint32_t, uint32_t>(t.hist, t.hist, (long long)256 * nblocks, t.scan_tmp, nullptr, st);
-    BK_LAUNCH(rs_scatter, nblocks, RS_THREADS, 0, st, ki, vi, n, shift, t.hist, nblocks, ko, vo);
+  for (int p = 0; p < npass; ++p) {
+    BK_LAUNCH(os_pass, ntiles, OS_THREADS, OS_SMEM, st, ki, vi, ko, vo, n_dev, (uint32_t)n, lo_bit + 8 * p, ghist + p * 256, status + (size_t)p * ntiles * 256, tickets + p);
     uint64_t *tk = ki; ki = ko; ko = tk;
     uint32_t *tv = vi; vi = vo; vo = tv;
-    ++passes;
   }
-  if (passes & 1) {
+  if (npass & 1) {
     cudaMemcpyAsync(keys, ki, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(vals, vi, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
   }
-  return passes;
+  return npass;
 }
 
 }  // namespace bk

@@ -5,8 +5,10 @@ Sharding: every rank holds a contiguous slice of the coordinate-sorted record st
 
   stage                         exchange
   ---------------------------   ----------------------------------------------------------------
-  classify + insert sum/count   all-reduce (sum)                                  [C2]
-  truncating sd accumulator     chained rank to rank (one int64)                   (order dependent)
+  classify + insert statistics  all-reduce (sum |isize|, count, sum isize^2; max |isize|)   [C2]
+  truncating sd accumulator     one pass on all ranks at once + all-reduce (sum floor, #correctable): exact and order
+                                independent whenever no record can need a rounding correction below the accumulator's
+                                final binade (the normal case); otherwise the exact replay chained rank to rank
   candidate records             all-to-all by name-hash owner                      [C1]  (mates meet)
   discordant pairs              all-to-all by bucket owner (chr-pair bucket rank)  [C1']
   mask + clustering + summary   none (buckets are independent, src/BreakID.cc:119-167)
@@ -57,9 +59,17 @@ class GpuEngine:
         return t
 
     def insert_partial(self):
-        s, n = C.c_int64(), C.c_int64()
-        self._chk(self.lib.bkid_shard_insert_partial(self.ctx.ctx, C.byref(s), C.byref(n)))
-        return s.value, n.value
+        s, n, q, m = C.c_int64(), C.c_int64(), C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.bkid_shard_insert_partial(self.ctx.ctx, C.byref(s), C.byref(n), C.byref(q), C.byref(m)))
+        return s.value, n.value, q.value, m.value
+
+    def sd_fast(self, mean, kub):
+        self._chk(self.lib.bkid_shard_sd_fast(self.ctx.ctx, mean, kub))
+
+    def sd_fast_collect(self):
+        f, e = C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.bkid_shard_sd_fast_collect(self.ctx.ctx, C.byref(f), C.byref(e)))
+        return f.value, e.value
 
     def sd_partial(self, mean, t_in):
         t = C.c_int64()
@@ -267,6 +277,20 @@ def _reduce(t: torch.Tensor, op):
     return t
 
 
+def sd_upper_binade(S: int, N: int, SQ: int, XM: int) -> int:
+    """upper bound of the binade of the truncating sd accumulator from the global sums -- the same integer arithmetic as
+    bkid_sd_upper_binade (breakid_b200/csrc/bkid_api.cuh: sd_upper_binade)"""
+    if N == 0:
+        return 0
+    if XM > 65535:
+        return 51
+    T = (SQ * N - S * S) // N + 1
+    T += (T >> 30) + 2 * N + 1024
+    if T >> 51:
+        return 51
+    return T.bit_length() - 1
+
+
 def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: int = 0, timing: Optional[dict] = None):
     """the whole hot path over all ranks; returns (mean, sd, dist, called cluster records [numpy, bucket =
     dense id]) -- identical on every rank and identical to the single-GPU / reference result"""
@@ -283,12 +307,13 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
             timing[name] = timing.get(name, 0.0) + (now - _t[0]) * 1e3
             _t[0] = now
     # insert statistics: exact integer sum/count, then the order-dependent sd accumulator chained through the ranks
-    s, n = engine.insert_partial()
-    sn = _reduce(torch.tensor([s, n], dtype=torch.int64, device=dev), dist.ReduceOp.SUM)
-    S, N = int(sn[0]), int(sn[1])
+    s, n, sq, xm = engine.insert_partial()
+    sn = _reduce(torch.tensor([s, n, sq & 0xffffffff, sq >> 32], dtype=torch.int64, device=dev), dist.ReduceOp.SUM)
+    S, N, SQ = int(sn[0]), int(sn[1]), int(sn[2]) + (int(sn[3]) << 32)
+    XM = int(_reduce(torch.tensor([xm], dtype=torch.int64, device=dev), dist.ReduceOp.MAX)[0])
     mean = (float(S) / float(N)) if N else float("nan")      # no proper pair: NaN like the single-GPU path and the reference (0/0 in double)
-    if hasattr(engine, "sd_prepare"):
-        engine.sd_prepare(mean)          # the streaming pass (block tables) runs on all ranks at once, asynchronously: it overlaps the candidate extraction below
+    kub = sd_upper_binade(S, N, SQ, XM)
+    engine.sd_fast(mean, kub)            # one streaming pass on all ranks at once, asynchronously: it overlaps the candidate extraction below
     lap('insert sum/count')
     # global index of the first local record
     ns = torch.zeros(W, dtype=torch.int64, device=dev)
@@ -302,14 +327,22 @@ def run_sharded(engine, n_local: int, times: int = 2, sd_mult: int = 3, mode: in
     lap('candidates')
     cands = _all_to_all_rows(cands, owner, engine)
     lap('a2a candidates')
-    # only the cheap exact resolve of the order-dependent sd accumulator is chained through the ranks
+    # sd accumulator: sum floor(a) over all ranks is the exact total when no record can need a correction (E == 0);
+    # only otherwise the order-dependent replay is chained through the ranks
+    f, e = engine.sd_fast_collect()
+    fe = _reduce(torch.tensor([f, min(e, 1 << 40)], dtype=torch.int64, device=dev), dist.ReduceOp.SUM)
     t = torch.zeros(1, dtype=torch.int64, device=dev)
-    for src in range(W):
-        if r == src:
-            t[0] = engine.sd_partial(mean, int(t[0]))
-        if W > 1:
-            dist.broadcast(t, src=src)
-    lap('sd chain')
+    if int(fe[1]) == 0:
+        t[0] = int(fe[0])
+    elif N:
+        if hasattr(engine, "sd_prepare"):
+            engine.sd_prepare(mean)      # block tables on all ranks at once
+        for src in range(W):
+            if r == src:
+                t[0] = engine.sd_partial(mean, int(t[0]))
+            if W > 1:
+                dist.broadcast(t, src=src)
+    lap('sd')
     sd = math.sqrt(int(t[0]) / float(N)) if N else float("nan")
     d = times * math.sqrt(times) * (mean + sd_mult * sd)
     engine.set_stats(mean, sd)

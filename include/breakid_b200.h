@@ -32,7 +32,8 @@ typedef enum {
   BKID_ERR_ARG = -2,        /* bad argument or call order */
   BKID_ERR_NOMEM = -3,      /* device memory exhausted (e.g. AHC component too large) */
   BKID_ERR_CIGAR = -4,      /* the reference's fatal "error cigar" path, src/BreakID.cc:954-968 */
-  BKID_ERR_HASH = -5,       /* 64-bit name-hash run with differing 128-bit hashes could not be resolved */
+  BKID_ERR_HASH = -5,       /* > 4096 records share the 64-bit name hash of different read names (names with equal 64-bit hashes
+                               are otherwise told apart by the other 64 bits of the 128-bit hash) */
   BKID_ERR_IO = -6
 } bkid_status;
 
@@ -92,7 +93,9 @@ typedef struct {
   /* Optional narrow encodings of three dense columns for host batches (bkid_push_batch): a non-NULL narrow column
    * REPLACES its wide column (pass that one as NULL); the device widens it after the copy.  19 -> 11 B/record
    * over PCIe.  A decoder uses a narrow form only when the whole batch fits it and sends the wide column otherwise.
-   * Not accepted by bkid_push_batch_device (resident columns are used in place). */
+   * A context whose batches all carry a column in its narrow form KEEPS it narrow in HBM (the classify kernel then reads
+   * 8 B/record including the span maximum the region queries need); bkid_push_batch_device adopts resident isize16 /
+   * span16 columns in place (tid must be resident in its wide form). */
   const int16_t *isize16;           /* [n] replaces isize: every isize of a record passing the insert-statistics predicate
                                        (src/BreakID.cc:1932, the only reader of isize) fits int16; other records: any value */
   const uint16_t *span16;           /* [n] replaces endpos: endpos - pos */
@@ -260,9 +263,19 @@ int bkid_get_timings(bkid_ctx *ctx, bkid_timings *t);
  * SURVEY.md 8(e) between these calls; every handed-out pointer is a DEVICE pointer owned by the context
  * and valid until the next call.  Single-GPU bkid_scan / bkid_refine are compositions of the same pieces. */
 typedef struct { uint64_t q[11]; } bkid_sarow;        /* opaque 88-byte split-read evidence row (self-contained) */
-int bkid_shard_insert_partial(bkid_ctx *ctx, int64_t *sum_abs, int64_t *count);                 /* -> all-reduce (sum) */
-int bkid_shard_sd_prepare(bkid_ctx *ctx, double mean);                                           /* streaming pass, all ranks at once */
-int bkid_shard_sd_partial(bkid_ctx *ctx, double mean, int64_t t_in, int64_t *t_out);             /* chained rank to rank */
+/* insert statistics of the local records (src/BreakID.cc:1932-1941): sum |isize|, count, sum isize^2 -> all-reduce (sum);
+ * max |isize| -> all-reduce (max) */
+int bkid_shard_insert_partial(bkid_ctx *ctx, int64_t *sum_abs, int64_t *count, uint64_t *sum_sq, uint64_t *max_abs);
+/* upper bound of the binade the truncating sd accumulator (src/BreakID.cc:1913,1944) can reach, from the GLOBAL sums */
+int bkid_sd_upper_binade(uint64_t sum_abs, uint64_t count, uint64_t sum_sq, uint64_t max_abs);
+/* one streaming pass per rank, all ranks at once, asynchronous: sum floor((|isize| - mean)^2) and the number of records whose
+ * rounding could ever add 1 below that binade.  All-reduce (sum) both: when the second sum is 0 -- the normal case -- the
+ * accumulator equals the first sum EXACTLY, independent of the record order, and there is no rank-to-rank chain. */
+int bkid_shard_sd_fast(bkid_ctx *ctx, double mean, int32_t upper_binade);
+int bkid_shard_sd_fast_collect(bkid_ctx *ctx, uint64_t *sum_floor, uint64_t *n_correctable);
+/* otherwise: the exact order-dependent replay, block tables on all ranks at once, then chained rank to rank */
+int bkid_shard_sd_prepare(bkid_ctx *ctx, double mean);
+int bkid_shard_sd_partial(bkid_ctx *ctx, double mean, int64_t t_in, int64_t *t_out);
 int bkid_shard_set_stats(bkid_ctx *ctx, double mean, double sd);
 int bkid_shard_candidates(bkid_ctx *ctx, uint64_t index_offset, const bkid_cand **dev, int64_t *n);   /* -> all-to-all by name hash */
 int bkid_shard_join(bkid_ctx *ctx, const bkid_cand *dev_cand, int64_t n, double w, const bkid_pair **dev_pairs, int64_t *n_pairs);  /* -> all-to-all by bucket owner */

@@ -55,10 +55,27 @@ class OracleEngine:
         self.rank_table = np.zeros((len(hb.target_names) + 1) ** 2, np.int32)
         self.o.orc_bucket_rank_table(len(hb.target_names), O._names(hb), self.rank_table)
 
-    def insert_partial(self):
+    def _insert_x(self):
         f = self.hb.cols["flag"].astype(np.int64); s = self.hb.cols["isize"].astype(np.int64)
         ok = ((f & 1) != 0) & ((f & 2) != 0) & ((f & (0x4 | 0x100 | 0x200 | 0x400)) == 0)
-        return int(np.abs(s[ok]).sum()), int(ok.sum())
+        return np.abs(s[ok])
+
+    def insert_partial(self):
+        x = self._insert_x()
+        xu = x.astype(np.uint64)
+        return int(x.sum()), int(x.shape[0]), int((xu * xu).sum(dtype=np.uint64)), int(x.max(initial=0))       # uint64 wrap-around like the device
+
+    def sd_fast(self, mean, kub):
+        """CPU restatement of the one-pass sd form: sum floor(a) and the number of elements whose fraction could round
+        the accumulator up below binade kub (a = (|isize| - mean)^2 in IEEE double, like src/BreakID.cc:1944)"""
+        x = self._insert_x().astype(np.float64)
+        d = x - mean
+        a = d * d
+        fl = np.floor(a)
+        self._sdf = (int(fl.astype(object).sum()) if x.shape[0] else 0, int(((a - fl) >= 1.0 - 2.0 ** (kub - 53)).sum()) if kub < 51 else 1 << 40)
+
+    def sd_fast_collect(self):
+        return self._sdf
 
     def sd_partial(self, mean, t_in):
         return self.o.orc_shard_sd_partial(self.hb.n, self.hb.cols["flag"], self.hb.cols["isize"], mean, t_in)

@@ -635,3 +635,138 @@ def test_narrow_column_encodings(small_data):
     om, osd, od, exp = O.run(hb2, None, mode=0)
     assert c2.run()[:3] == (om, osd, od) and c2.fetch_clusters().tobytes() == exp.tobytes()
     c2.close()
+
+
+def _split_batches(api, hb, cuts):
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sa = hb.side["sa_rec"]; lo = np.searchsorted(sa, a); hi = np.searchsorted(sa, b)
+        co, so, oo = hb.side["cig_off"], hb.side["sa_off"], hb.side["oc_off"]
+        parts.append(api.HostBatch({k: v[a:b] for k, v in hb.cols.items()}, hb.name_hash[2 * a:2 * b],
+                                   {"sa_rec": sa[lo:hi] - a, "cig_off": co[lo:hi + 1] - co[lo], "cig_ops": hb.side["cig_ops"][co[lo]:co[hi]],
+                                    "sa_off": so[lo:hi + 1] - so[lo], "sa_txt": hb.side["sa_txt"][so[lo]:so[hi]],
+                                    "oc_off": oo[lo:hi + 1] - oo[lo], "oc_txt": hb.side["oc_txt"][oo[lo]:oo[hi]]}, hb.target_len, hb.target_names))
+    return parts
+
+
+@pytest.mark.parametrize("order", [(True, False, True), (False, True, True), (True, True, False)])
+def test_mixed_narrow_and_wide_batches(small_data, order):
+    """the context keeps isize / span narrow in HBM while every batch has them narrow; a wide batch arriving later
+    widens what is already held, a narrow batch arriving at a wide context is widened on the way in"""
+    from breakid_b200 import api
+    d, hb, nibs = small_data
+    c1 = _ctx_for(hb)
+    r1 = c1.run(); g1 = c1.fetch_clusters()
+    c2 = api.Context(hb.target_len, hb.target_names, device=0)
+    for part, narrow in zip(_split_batches(api, hb, [0, hb.n // 3, hb.n // 2 + 7, hb.n]), order):
+        c2.push(part, narrow=narrow)
+    for k, dt in (("isize", np.int32), ("endpos", np.int32), ("tid", np.int32)):
+        a, b = c2.fetch_column(k, dt), hb.cols[k]
+        assert np.array_equal(np.clip(a, -32768, 32767), np.clip(b, -32768, 32767)) if k == "isize" else np.array_equal(a, b), k
+    r2 = c2.run(); g2 = c2.fetch_clusters()
+    assert r1 == r2 and g1.tobytes() == g2.tobytes()
+    c1.close(); c2.close()
+
+
+@pytest.mark.parametrize("variant", ["low32_small_groups", "low32_big_groups", "lo64_collisions"])
+def test_join_name_hash_collisions(small_data, variant):
+    """the join sorts on 32 bits of the 128-bit read-name hash and puts groups that hold several names in order in
+    place; bigger mixed groups make it sort the other 32 bits too; names that share all 64 bits of the low word are told
+    apart by the high word.  Forced here by degrading the hash: results must not change (the oracle compares 128 bits)."""
+    import oracle_py as O
+    from breakid_b200 import api
+    d, hb, nibs = small_data
+    nh = hb.name_hash.reshape(-1, 2).copy()
+    lo, hi = nh[:, 0].copy(), nh[:, 1].copy()
+    if variant == "low32_small_groups":
+        lo = (lo & np.uint64(0xffffffff00000000)) | (lo & np.uint64(0x3ff))          # 1024 values of the sorted bits
+    elif variant == "low32_big_groups":
+        lo = (lo & np.uint64(0xffffffff00000000)) | (lo & np.uint64(0x3))            # 4 values: groups far beyond the in-place cap
+    else:
+        hi = hi ^ (lo * np.uint64(0x9E3779B97F4A7C15))                                # keep 128 bits distinct ...
+        lo = lo & np.uint64(0x1f)                                                     # ... while only 32 values of name_lo remain
+    nh2 = np.stack([lo, hi], 1).reshape(-1)
+    # same names <=> same 128-bit value, before and after
+    assert len(np.unique(nh.view([("a", "<u8"), ("b", "<u8")]))) == len(np.unique(np.stack([lo, hi], 1).copy().view([("a", "<u8"), ("b", "<u8")])))
+    hb2 = api.HostBatch(hb.cols, nh2, hb.side, hb.target_len, hb.target_names)
+    c = _ctx_for(hb2)
+    m, s = c.insert_stats()
+    w = O.dist(m, s)
+    n = c.scan(w)
+    got = c.fetch_pairs(0)
+    exp = O.scan(hb2, 20, w)
+    assert n == len(exp) and n > 50
+    for k in exp.dtype.names:
+        assert np.array_equal(got[k], exp[k]), k
+    ref = O.scan(hb, 20, w)
+    for k in ("p1_pos", "p2_pos", "p1_chr_pos", "p2_chr_pos", "bucket"):             # and the pairs are those of the undegraded hash
+        assert np.array_equal(got[k], ref[k]), k
+    c.close()
+
+
+def test_sparse_table_is_validated(small_data):
+    """a candidate missing from the sparse mate/name table, or a table that is not strictly ascending, is an argument
+    error -- never a silently different result"""
+    import ctypes as C
+    from breakid_b200 import api
+    d, hb, nibs = small_data
+    cand = np.nonzero(((hb.cols["flag"] & 0x703) == 0x1) & (hb.cols["mapq"] >= 20))[0]
+    for what in ("missing", "unsorted"):
+        c = api.Context(hb.target_len, hb.target_names, device=0)
+        b = hb.struct()
+        x = {k: v.copy() for k, v in hb.x.items()}
+        j = int(np.searchsorted(x["x_rec"], cand[len(cand) // 2]))
+        if what == "missing":
+            x = {"x_rec": np.delete(x["x_rec"], j), "x_mtid": np.delete(x["x_mtid"], j), "x_mpos": np.delete(x["x_mpos"], j),
+                 "x_name_hash": np.delete(x["x_name_hash"].reshape(-1, 2), j, 0).reshape(-1).copy()}
+        else:
+            x["x_rec"][j], x["x_rec"][j + 1] = x["x_rec"][j + 1], x["x_rec"][j]
+        b.n_x = int(x["x_rec"].shape[0])
+        for k in x:
+            setattr(b, k, x[k].ctypes.data)
+        c._chk(c.lib.bkid_push_batch(c.ctx, C.byref(b)))
+        with pytest.raises(api.BkidError) as e:
+            c.run()
+        assert "sparse mate/name table" in str(e.value), (what, str(e.value))
+        c.close()
+
+
+def test_sd_one_pass_form_equals_block_table_form(small_data, monkeypatch):
+    """bkid_insert_stats takes the one-pass form (sum floor(a), exact when no record can need a rounding correction below
+    the accumulator's final binade) and only otherwise the block tables + resolver: both must give the oracle's sd"""
+    import oracle_py as O
+    d, hb, nibs = small_data
+    exp = O.insert_stats(hb)[:2]
+    c = _ctx_for(hb)
+    assert c.insert_stats() == exp
+    c.close()
+    monkeypatch.setenv("BKID_SD_GENERAL", "1")
+    c = _ctx_for(hb)
+    assert c.insert_stats() == exp
+    c.close()
+
+
+def test_sd_one_pass_form_detects_correctable_records():
+    """insert sizes spread over [0, 30000]: the accumulator reaches binade 45, so every record whose squared deviation has a
+    fraction >= 1 - 2^-8 may need a rounding correction: the one-pass form must notice them (E > 0, computed here the same
+    way on the CPU) and the exact replay must then agree with the oracle's literal loop"""
+    import oracle_py as O
+    from breakid_b200 import api, dist as D
+    rng = np.random.RandomState(8)
+    n = 200000
+    isz = (rng.randint(0, 30001, n) * rng.choice([-1, 1], n)).astype(np.int32)
+    flag = np.full(n, 99, np.uint16)
+    z = np.zeros(n, np.int32)
+    x = np.abs(isz).astype(np.int64)
+    S, N, SQ = int(x.sum()), n, int((x * x).sum())
+    kub = D.sd_upper_binade(S, N, SQ, int(x.max()))
+    a = (x.astype(np.float64) - float(S) / float(N)) ** 2
+    assert 40 <= kub < 51 and int(((a - np.floor(a)) >= 1.0 - 2.0 ** (kub - 53)).sum()) > 100
+    hb = api.HostBatch({"flag": flag, "mapq": np.full(n, 60, np.uint8), "tid": z, "pos": np.arange(n, dtype=np.int32), "mtid": z, "mpos": z,
+                        "isize": isz, "endpos": np.arange(n, dtype=np.int32) + 100}, np.arange(2 * n, dtype=np.uint64),
+                       {"sa_rec": np.zeros(0, np.uint32), "cig_off": np.zeros(1, np.uint32), "cig_ops": np.zeros(0, np.uint32),
+                        "sa_off": np.zeros(1, np.uint32), "sa_txt": np.zeros(0, np.uint8)}, [1000000000], ["chr1"])
+    assert "isize16" in hb.narrow()
+    c = _ctx_for(hb)
+    assert c.insert_stats() == O.insert_stats(hb)[:2]
+    c.close()

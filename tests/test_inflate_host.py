@@ -1,5 +1,6 @@
 """The DEFLATE decoder of the device BGZF path (breakid_b200/csrc/bkid_inflate.cuh) compiled as plain C++ and
-checked against zlib on the CPU: stored / fixed / dynamic blocks, long codes, overlapping matches, corrupt input."""
+checked against zlib on the CPU: stored / fixed / dynamic blocks, long codes, overlapping matches of every short
+distance, every alignment of the input and output windows, tiny outputs, corrupt input."""
 import ctypes as C
 import os
 import subprocess
@@ -18,8 +19,8 @@ def lib(tmp_path_factory):
     L = C.CDLL(out)
     L.bki_host_inflate.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32]
     L.bki_host_inflate.restype = C.c_int
-    L.bki_host_inflate_stepped.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int]
-    L.bki_host_inflate_stepped.restype = C.c_int
+    L.bki_host_inflate_var.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    L.bki_host_inflate_var.restype = C.c_int
     L.bki_host_crc32_sliced.argtypes = [C.c_char_p, C.c_uint32, C.c_int]
     L.bki_host_crc32_sliced.restype = C.c_uint32
     return L
@@ -63,10 +64,10 @@ def test_matches_zlib(lib):
                 rc, out = _inflate(lib, comp, len(data))
                 assert rc == 0, (len(data), level, strategy, mem, rc)
                 assert out == data, (len(data), level, strategy, mem)
-                out2 = np.zeros(max(len(data), 1), np.uint8)            # resumable form, 1 and 7 tokens per step
-                for step in (1, 7):
-                    assert lib.bki_host_inflate_stepped(comp, len(comp), out2.ctypes.data, len(data), step) == 0
-                    assert out2[:len(data)].tobytes() == data, (len(data), level, strategy, mem, step)
+                out2 = np.zeros(max(len(data), 1), np.uint8)            # one literal per step; misaligned input / output windows
+                for litmax, im, om in ((1, 0, 0), (4, 1, 3), (4, 3, 7), (1, 2, 5)):
+                    assert lib.bki_host_inflate_var(comp, len(comp), out2.ctypes.data, len(data), litmax, im, om) == 0
+                    assert out2[:len(data)].tobytes() == data, (len(data), level, strategy, mem, litmax, im, om)
                 n += 1
     assert n > 100
 
@@ -105,3 +106,27 @@ def test_sliced_crc32_matches_zlib(lib):
         for k in (1, 2, 8, 32):
             assert lib.bki_host_crc32_sliced(data, n, k) == (zlib.crc32(data) & 0xffffffff), (n, k)
     assert lib.bki_host_crc32_sliced(b"\x00" * 5000, 5000, 32) == (zlib.crc32(b"\x00" * 5000) & 0xffffffff)
+
+
+def test_every_short_distance_length_and_alignment(lib):
+    """the 8-byte pending word: matches of distance 1..40 and lengths 3..30 at all eight output alignments, and
+    outputs of 0..20 bytes (first word == last word) -- bytes outside the output window must stay untouched"""
+    rng = np.random.RandomState(17)
+    for dist in list(range(1, 20)) + [23, 24, 25, 31, 32, 33, 40]:
+        seedb = rng.randint(0, 256, dist, dtype=np.uint8).tobytes()
+        data = b""
+        for ln in range(3, 31):
+            data += rng.randint(0, 256, 3, dtype=np.uint8).tobytes() + seedb + (seedb * 40)[:ln]
+        comp = _raw(data, 9)
+        out = np.zeros(len(data), np.uint8)
+        for om in range(8):
+            assert lib.bki_host_inflate_var(comp, len(comp), out.ctypes.data, len(data), 4, om & 3, om) == 0
+            assert out.tobytes() == data, (dist, om)
+    for n in range(0, 21):
+        data = rng.randint(0, 4, n, dtype=np.uint8).tobytes()
+        for level in (0, 6):
+            comp = _raw(data, level)
+            out = np.zeros(max(n, 1), np.uint8)
+            for om in range(8):
+                assert lib.bki_host_inflate_var(comp, len(comp), out.ctypes.data, n, 4, 0, om) == 0, (n, level, om)
+                assert out[:n].tobytes() == data
