@@ -278,7 +278,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
-           "bkid_push_bgzf", "bkid_push_bgzf_range", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align"]
+           "bkid_push_bgzf", "bkid_push_bgzf_range", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align", "bkid_profile_kernels", "bkid_profile_report"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -349,12 +349,32 @@ def cuda_lib():
         L.bkid_shard_finish.argtypes = [vp, i64p]
         L.bkid_fetch_bucket_ranks.argtypes = [vp, vp, C.c_int64, i64p]
         L.bkid_device_copy.argtypes = [vp, vp, vp, C.c_uint64]
+        L.bkid_profile_kernels.argtypes = [C.c_int]
+        L.bkid_profile_report.argtypes = [C.c_char_p, C.c_int64]
+        L.bkid_profile_report.restype = C.c_int64
         _cuda = L
     return _cuda
 
 
 class BkidError(RuntimeError):
     pass
+
+
+def profile_kernels(on: bool):
+    """switch the per-kernel CUDA-event timing of the library on / off (bkid_profile_kernels)"""
+    cuda_lib().bkid_profile_kernels(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """{kernel name: (launches, milliseconds)} of everything launched since profiling was switched on (and reset)"""
+    L = cuda_lib()
+    buf = C.create_string_buffer(1 << 16)
+    L.bkid_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        nm, n, ms = line.split("\t")
+        out[nm] = (int(n), float(ms))
+    return out
 
 
 class BgzfBlock(C.Structure):

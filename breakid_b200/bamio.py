@@ -71,7 +71,8 @@ def write_bam(path: str, d: synth.SynthData, random_qual: bool = True, level: in
 
     from concurrent.futures import ThreadPoolExecutor
     import os as _os
-    pool = ThreadPoolExecutor(max(1, min(16, _os.cpu_count() or 1)))     # zlib releases the GIL
+    pool = ThreadPoolExecutor(max(1, min(32, _os.cpu_count() or 1)))     # zlib releases the GIL
+    futures = []
 
     def flush(final=False):
         nonlocal pending
@@ -83,33 +84,28 @@ def write_bam(path: str, d: synth.SynthData, random_qual: bool = True, level: in
             blks.append(blk)
             o += len(blk)
         mv.release()
-        for comp in pool.map(lambda b: _bgzf_block(b, level), blks):
-            out.write(comp)
+        futures.extend(pool.submit(_bgzf_block, b, level) for b in blks)      # compression overlaps the record assembly
+        while len(futures) > 4096:                                             # bound the backlog: write the oldest blocks
+            out.write(futures.pop(0).result())
         pending = pending[o:]
 
     flush()
     digits = np.array([10 ** (9 - i) for i in range(10)], dtype=np.int64)
+    head_dt = np.dtype([
+        ("block_size", "<i4"), ("tid", "<i4"), ("pos", "<i4"), ("l_name", "u1"), ("mapq", "u1"),
+        ("bin", "<u2"), ("n_cigar", "<u2"), ("flag", "<u2"), ("l_seq", "<i4"),
+        ("mtid", "<i4"), ("mpos", "<i4"), ("isize", "<i4"), ("name", "u1", NAME)])
+    hw = head_dt.itemsize                               # 36 + NAME
+    row_w = hw + 4 + seq_b + L                          # a record without aux, one cigar op: every non-SA record
+    cig1 = np.frombuffer(struct.pack("<I", (L << 4) | 0), dtype=np.uint8)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         m = e - s
         sa_m = is_sa[s:e]
-        # per-record sizes
-        size = np.full(m, fixed, dtype=np.int64)
         idx_sa = np.nonzero(sa_m)[0]
-        extra = np.zeros(m, dtype=np.int64)
-        for j in idx_sa:
-            k = sa_slot[s + j]
-            nc = cig_off[k + 1] - cig_off[k]
-            extra[j] = 4 * (nc - 1) + 3 + (sa_off[k + 1] - sa_off[k]) + 1
-        size += extra
-        off = np.zeros(m + 1, dtype=np.int64); off[1:] = np.cumsum(size + 4)
-        buf = np.zeros(int(off[-1]), dtype=np.uint8)
-        # fixed part as a structured block
-        rec = np.zeros(m, dtype=np.dtype([
-            ("block_size", "<i4"), ("tid", "<i4"), ("pos", "<i4"), ("l_name", "u1"), ("mapq", "u1"),
-            ("bin", "<u2"), ("n_cigar", "<u2"), ("flag", "<u2"), ("l_seq", "<i4"),
-            ("mtid", "<i4"), ("mpos", "<i4"), ("isize", "<i4"), ("name", "u1", NAME)]))
-        rec["block_size"] = size
+        # fixed part of every record as a structured block
+        rec = np.zeros(m, dtype=head_dt)
+        rec["block_size"] = fixed
         rec["tid"] = c["tid"][s:e]; rec["pos"] = c["pos"][s:e]
         rec["l_name"] = NAME; rec["mapq"] = c["mapq"][s:e]
         rec["bin"] = reg2bin(c["pos"][s:e].astype(np.int64), c["endpos"][s:e].astype(np.int64))
@@ -120,34 +116,36 @@ def write_bam(path: str, d: synth.SynthData, random_qual: bool = True, level: in
         nm[:, 0] = ord("r")
         nm[:, 1:11] = ((nid[:, None] // digits[None, :]) % 10 + 48).astype(np.uint8)
         rec["name"] = nm
-        for j in idx_sa:
-            k = sa_slot[s + j]
-            rec["n_cigar"][j] = cig_off[k + 1] - cig_off[k]
-        head = rec.view(np.uint8).reshape(m, -1)          # [m, 36+NAME]
-        hw = head.shape[1]
-        rows = off[:-1, None] + np.arange(hw)[None, :]
-        buf[rows] = head
-        # cigar + seq + qual for the fixed-layout records
-        plain = np.nonzero(~sa_m)[0]
-        if plain.size:
-            tail = np.zeros((plain.size, 4 + seq_b + L), dtype=np.uint8)
-            tail[:, 0:4] = np.frombuffer(struct.pack("<I", (L << 4) | 0), dtype=np.uint8)
-            tail[:, 4:4 + seq_b] = 0x11
-            tail[:, 4 + seq_b:] = rng.randint(2, 41, (plain.size, L)).astype(np.uint8) if random_qual else 30
-            rows = (off[plain] + hw)[:, None] + np.arange(tail.shape[1])[None, :]
-            buf[rows] = tail
-        for j in idx_sa:
-            k = sa_slot[s + j]
-            ops = cig_ops[cig_off[k]:cig_off[k + 1]]
-            sq = b"\x11" * seq_b if sa_seq is None else bytes(sa_seq["seq4"][int(sa_seq["seq_off"][k]):int(sa_seq["seq_off"][k + 1])])
-            assert len(sq) == seq_b
-            blob = ops.astype("<u4").tobytes() + sq + (b"\x1e" * L) \
-                + b"SAZ" + sa_txt[sa_off[k]:sa_off[k + 1]].tobytes() + b"\x00"
-            o = int(off[j]) + hw
-            buf[o:o + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
-        pending += buf.tobytes()
+        # all records laid out as fixed-width rows (column slices, no index arrays); the few SA-tagged records are
+        # re-serialised with their own cigar / tag bytes and spliced in between the runs of plain rows
+        rows = np.empty((m, row_w), dtype=np.uint8)
+        rows[:, :hw] = rec.view(np.uint8).reshape(m, hw)
+        rows[:, hw:hw + 4] = cig1
+        rows[:, hw + 4:hw + 4 + seq_b] = 0x11
+        rows[:, hw + 4 + seq_b:] = rng.randint(2, 41, (m, L)).astype(np.uint8) if random_qual else 30
+        if idx_sa.size == 0:
+            pending += rows.tobytes()
+        else:
+            prev = 0
+            for j in idx_sa:
+                if j > prev:
+                    pending += rows[prev:j].tobytes()
+                k = sa_slot[s + j]
+                ops = cig_ops[cig_off[k]:cig_off[k + 1]]
+                sq = b"\x11" * seq_b if sa_seq is None else bytes(sa_seq["seq4"][int(sa_seq["seq_off"][k]):int(sa_seq["seq_off"][k + 1])])
+                assert len(sq) == seq_b
+                blob = ops.astype("<u4").tobytes() + sq + (b"\x1e" * L) + b"SAZ" + sa_txt[sa_off[k]:sa_off[k + 1]].tobytes() + b"\x00"
+                r1 = rec[j:j + 1].copy()
+                r1["n_cigar"] = ops.shape[0]
+                r1["block_size"] = hw - 4 + len(blob)
+                pending += r1.tobytes() + blob
+                prev = j + 1
+            if prev < m:
+                pending += rows[prev:].tobytes()
         flush()
     flush(final=True)
+    for fu in futures:
+        out.write(fu.result())
     pool.shutdown()
     out.write(_BGZF_EOF)
     out.close()

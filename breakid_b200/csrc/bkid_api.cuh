@@ -172,7 +172,7 @@ static int exact_sort_segments(bkid_ctx *c, uint32_t *key, uint32_t *val, const 
   int max_levels = 2 * lg + 2;
   int cur = 0;
   for (int level = 0; level < max_levels; ++level) {
-    if (n <= 65536 ? true : (level > 0 && (level % 4) == 0)) {   // early exit once no segment is above the small-segment size               // early exit once no segment is active
+    if (level > 0 && (level % 4) == 0) {                          // early exit once no segment is above the small-segment size (polled every 4th level: a poll is a host round trip)
       unsigned h = 0;
       CU(c, cudaMemcpyAsync(&h, cnt + cur, 4, cudaMemcpyDeviceToHost, st));
       CU(c, cudaStreamSynchronize(st));
@@ -432,7 +432,7 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
     BK_LAUNCH(ahc_rg_heads, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO, bucket_events);
     bk::exclusive_scan<uint32_t, uint32_t>(g.is_head, head_excl, n, stmp, tot, st);
     BK_LAUNCH(ahc_rg_head_list, GRID1(n, 256), 256, 0, st, g.is_head, head_excl, n, head_pos);
-    BK_LAUNCH(ahc_rg_ties, GRID1(nseg, 64), 64, 0, st, v, g, (uint32_t)nseg, bucket_flag, RG_LO, bucket_events, head_pos, head_excl, n);
+    BK_LAUNCH(ahc_rg_ties, GRID1(nseg, 4), 128, 0, st, v, g, (uint32_t)nseg, bucket_flag, RG_LO, bucket_events, head_pos, head_excl, n);
     BK_LAUNCH(ahc_rg_write, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO);
   }
   T_.mark("ahc: replay rank form (global)");
@@ -909,7 +909,7 @@ static int classify_impl(bkid_ctx *c)
   if (c->classified) return 0;
   cudaStream_t st = c->st;
   long long n = c->n;
-  int ntiles = div_up(std::max<long long>(n, 1), K1_TILE);
+  int ntiles = std::min(div_up(std::max<long long>(n, 1), K1_TILE), 148 * 8);    // persistent: 8 CTAs of 256 threads per SM
   TRY(c, c->cls.ensure((size_t)n + 64, 0, st));
   unsigned long long *g = (unsigned long long *)(c->counters.as<unsigned>() + CS_G);
   CU(c, cudaMemsetAsync(g, 0, 64, st));
@@ -1027,8 +1027,8 @@ static int sd_fast_launch(bkid_ctx *c, double mean, int kub, cudaStream_t st)
   c->sd_kub = kub;
   if (n <= 0 || c->cnt_insert <= 0) return 0;
   double thr = 1.0 - ldexp(1.0, kub - 53);                                    // corrections need frac(a) >= 1 - 2^(k-53), k <= kub
-  if (c->p_isize16) BK_LAUNCH((sd_fast<true>), 148 * 16, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
-  else BK_LAUNCH((sd_fast<false>), 148 * 16, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
+  if (c->p_isize16) BK_LAUNCH((sd_fast<true>), 148 * 8, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
+  else BK_LAUNCH((sd_fast<false>), 148 * 8, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
   return 0;
 }
 // F = sum floor(a), E = elements that could need a correction; exact iff E == 0 (and not out of regime: *E = ~0)
@@ -1145,14 +1145,15 @@ static int extract_candidates(bkid_ctx *c, unsigned long long index_offset, bool
   if (nx <= 0 || n <= 0) return 0;
   int ntiles = div_up(nx, KX_TILE);
   TRY(c, c->sc.ensure(std::max<long long>(cap, ntiles) + 8, st));
-  TRY(c, c->tile_cand.ensure((size_t)(ntiles + 1) * 4 * 2 + 64, 0, st));
+  TRY(c, c->tile_cand.ensure((size_t)(ntiles + 1) * 4 * 2 + (size_t)ntiles * KX_THREADS + 64, 0, st));
   uint32_t *tile_cnt = c->tile_cand.as<uint32_t>(), *tile_off = tile_cnt + ntiles + 1;
+  uint8_t *is_cand = (uint8_t *)(tile_off + ntiles + 1);                 // 4 candidate bits per kx thread
   unsigned long long *tot = (unsigned long long *)(cs + CS_TOTAL);
-  BK_LAUNCH(kx_count, (unsigned)ntiles, KX_THREADS, 0, st, c->p_x_rec, nx, c->cls.as<uint8_t>(), n, tile_cnt, (int *)(cs + CS_XBAD));
+  BK_LAUNCH(kx_count, (unsigned)ntiles, KX_THREADS, 0, st, c->p_x_rec, nx, c->cls.as<uint8_t>(), n, tile_cnt, is_cand, (int *)(cs + CS_XBAD));
   bk::exclusive_scan<uint32_t, uint32_t>(tile_cnt, tile_off, ntiles, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
   CU(c, cudaMemcpyAsync(cs + CS_NC, tot, 4, cudaMemcpyDeviceToDevice, st));
   if (cap > 0)     // a table that lists more candidates than K1 counted cannot exist (same predicate, same class bytes)
-    BK_LAUNCH(kx_write, (unsigned)ntiles, KX_THREADS, 0, st, c->p_x_rec, nx, c->cls.as<uint8_t>(), n, tile_off, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_x_mtid, c->p_x_mpos, c->p_x_nh,
+    BK_LAUNCH(kx_write, (unsigned)ntiles, KX_THREADS, 0, st, c->p_x_rec, nx, is_cand, n, tile_off, c->p_flag, c->p_mapq, c->p_tid, c->p_pos, c->p_x_mtid, c->p_x_mpos, c->p_x_nh,
               index_offset, c->cand.as<bkid_cand>(), with_keys ? c->sc.keys.as<uint64_t>() : (uint64_t *)nullptr, c->sc.vals.as<uint32_t>());
   return 0;
 }
@@ -1885,6 +1886,36 @@ int bkid_fetch_class(bkid_ctx *c, uint8_t *out, int64_t cap)
   long long k = std::min<long long>(cap, c->n);
   if (k > 0) CU(c, cudaMemcpy(out, c->cls.p, (size_t)k, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// per-kernel device times: switch on, run, then read "name<TAB>launches<TAB>milliseconds" lines (all kernels launched
+// since it was switched on, summed by name; the report resets the collection)
+int bkid_profile_kernels(int on)
+{
+  g_bk_prof_on = on != 0;
+  return 0;
+}
+int64_t bkid_profile_report(char *buf, int64_t cap)
+{
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<long long, double>> agg;
+  std::vector<std::string> order;
+  for (auto &r : g_prof_recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+    std::string nm = r.name;
+    while (!nm.empty() && (nm.front() == '(' || nm.front() == ' ')) nm.erase(nm.begin());
+    while (!nm.empty() && (nm.back() == ')' || nm.back() == ' ')) nm.pop_back();
+    auto it = agg.find(nm);
+    if (it == agg.end()) { order.push_back(nm); agg[nm] = {1, (double)ms}; } else { it->second.first++; it->second.second += ms; }
+    g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  std::string out;
+  char line[256];
+  for (auto &nm : order) { snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", nm.c_str(), agg[nm].first, agg[nm].second); out += line; }
+  if (buf && cap > 0) { size_t k = std::min<size_t>((size_t)cap - 1, out.size()); memcpy(buf, out.data(), k); buf[k] = 0; }
+  return (int64_t)out.size() + 1;
 }
 
 int bkid_get_timings(bkid_ctx *c, bkid_timings *t)

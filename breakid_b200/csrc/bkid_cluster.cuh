@@ -573,35 +573,58 @@ __global__ void ahc_rg_heads(AhcView v, RankGlobal g, const uint32_t *__restrict
   if (r == 0 || g.pm[g.order[p - 1]] != g.pm[e]) g.is_head[p] = 1;
 }
 
-// per bucket, group after group in ascending prefix-max order: the literal heap walk over the group
-__global__ void ahc_rg_ties(AhcView v, RankGlobal g, uint32_t nb, const int32_t *__restrict__ bucket_flag, uint32_t n_lo, const uint32_t *__restrict__ bucket_events,
-                            const uint32_t *__restrict__ head_pos, const uint32_t *__restrict__ head_excl, long long n)
+// per bucket, group after group in ascending prefix-max order: the literal heap walk over the group.  One WARP per bucket:
+// the groups of a bucket depend on each other (a candidate's global index can be the rank an earlier group assigned), so
+// they run in order; inside a group every step picks the minimum over the group's live candidates, which the lanes search
+// in parallel (lexicographic warp reduction on (distance, -global index)).  One thread per bucket spent 0.5 ms here on the
+// 30x workload: sqrt(dx^2+dy^2) of integer offsets takes few distinct values, so tie groups are large.
+__global__ void __launch_bounds__(128) ahc_rg_ties(AhcView v, RankGlobal g, uint32_t nb, const int32_t *__restrict__ bucket_flag, uint32_t n_lo, const uint32_t *__restrict__ bucket_events,
+                                                   const uint32_t *__restrict__ head_pos, const uint32_t *__restrict__ head_excl, long long n)
 {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= nb) return;
+  const unsigned lane = threadIdx.x & 31;
   uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
   if (bucket_flag[b] || s1 - s0 < n_lo || s1 == s0) return;
   uint32_t nleaf = s1 - s0, M = bucket_events[b];
   uint32_t h0 = head_excl[s0], h1 = (s1 < (uint32_t)n) ? head_excl[s1] : head_excl[n - 1] + g.is_head[n - 1];
+  volatile uint8_t *tie = g.tie;
+  volatile uint32_t *rank = g.rank;
   for (uint32_t h = h0; h < h1; ++h) {
     uint32_t p0 = head_pos[h], r = p0 - s0;
     uint32_t e0 = g.order[p0];
+    const double pm0 = g.pm[e0];
+    // group end: first position whose prefix max differs (lanes probe 32 positions at a time)
     uint32_t r2 = r + 1;
-    while (r2 < M && g.pm[g.order[s0 + r2]] == g.pm[e0]) ++r2;
+    for (;;) {
+      uint32_t q = r2 + lane;
+      bool same = q < M && g.pm[g.order[s0 + q]] == pm0;
+      unsigned m = __ballot_sync(0xffffffffu, same);
+      if (m == 0xffffffffu) { r2 += 32; continue; }
+      r2 += (uint32_t)__ffs(~m) - 1u;
+      break;
+    }
     for (uint32_t s = 0; s < r2 - r; ++s) {
       long long best = -1; double bd = 0.0; int32_t bg = -1;
-      for (uint32_t p = r; p < r2; ++p) {
+      for (uint32_t p = r + lane; p < r2; p += 32) {
         uint32_t e = g.order[s0 + p];
-        if (g.tie[e] == 2) continue;
-        if (p > r) { uint32_t ep = g.order[s0 + p - 1]; if (g.slot_comp[ep] == g.slot_comp[e] && g.tie[ep] != 2) continue; }
+        if (tie[e] == 2) continue;
+        if (p > r) { uint32_t ep = g.order[s0 + p - 1]; if (g.slot_comp[ep] == g.slot_comp[e] && tie[ep] != 2) continue; }
         int32_t f = g.first[e];
         uint32_t comp = g.slot_comp[e];
-        int32_t gi = f >= 0 ? f : (int32_t)nleaf + (int32_t)g.rank[v.comp_off[comp] + (uint32_t)(-1 - f)];
+        int32_t gi = f >= 0 ? f : (int32_t)nleaf + (int32_t)rank[v.comp_off[comp] + (uint32_t)(-1 - f)];
         double d = v.ev_d[e];
         if (best < 0 || d < bd || (d == bd && gi > bg)) { best = (long long)e; bd = d; bg = gi; }
       }
-      g.rank[best] = r + s;
-      g.tie[best] = 2;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+        double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        int32_t og = __shfl_xor_sync(0xffffffffu, bg, o);
+        if (ob >= 0 && (best < 0 || od < bd || (od == bd && og > bg))) { best = ob; bd = od; bg = og; }
+      }
+      if (lane == 0) { rank[best] = r + s; tie[best] = 2; }
+      __syncwarp();
     }
   }
 }

@@ -27,12 +27,33 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
 thread_local long long g_bk_launches = 0;
 static thread_local std::string g_last_cuda_err;
 static std::string g_create_err;
+
+// ---- per-kernel timing (bkid_profile_kernels / bkid_profile_report) ----------------------------------------------
+bool g_bk_prof_on = false;
+namespace {
+struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event()
+{
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void bk_prof_begin(const char *name, cudaStream_t st)
+{
+  ProfRec r{name, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+void bk_prof_end(cudaStream_t st) { if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, st); }
 
 void bk_set_cuda_error(cudaError_t e, const char *file, int line)
 {
@@ -120,15 +141,21 @@ __global__ void __launch_bounds__(K1_THREADS)
 k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ isize, const int16_t *__restrict__ isize16,
             const uint16_t *__restrict__ span16, long long n, int qual, uint8_t *__restrict__ cls, unsigned long long *__restrict__ g)
 {
-  __shared__ unsigned long long sh_sum, sh_sq;
-  __shared__ unsigned sh_cnt, sh_xmax, sh_span;      // sh_cnt: n_ins in the low half, n_cand in the high half (<= 4096 each)
-  if (threadIdx.x == 0) { sh_sum = 0; sh_sq = 0; sh_cnt = 0; sh_xmax = 0; sh_span = 0; }
+  __shared__ unsigned long long sh_sum, sh_sq, sh_cnt, sh_cand;
+  __shared__ unsigned sh_xmax, sh_span;
+  if (threadIdx.x == 0) { sh_sum = 0; sh_sq = 0; sh_cnt = 0; sh_cand = 0; sh_xmax = 0; sh_span = 0; }
   __syncthreads();
-  const long long tile0 = (long long)blockIdx.x * K1_TILE;
+  // persistent grid (a few CTAs per SM walk the tiles): the six global results cost one atomic per CTA, not per tile --
+  // 150 k tiles x 6 same-sector atomics serialised in L2 and made the kernel 2.4x slower than its memory time
   unsigned long long sum_abs = 0, sum_sq = 0;
-  unsigned cnt = 0, xmax = 0, smax2 = 0;
+  unsigned long long cnt_ins = 0, cnt_cand = 0;
+  unsigned xmax = 0, smax2 = 0;
   const unsigned q4 = (unsigned)(qual < 0 ? 0 : (qual > 255 ? 255 : qual)) * 0x01010101u;
   const bool q_never = qual > 255;           // mapq is 8 bits: nothing can pass
+  const long long ntiles = (n + K1_TILE - 1) / K1_TILE;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const long long tile0 = tile * K1_TILE;
+  unsigned cnt = 0;
 #pragma unroll
   for (int gq = 0; gq < 2; ++gq) {
     long long i = tile0 + gq * (K1_THREADS * 8) + threadIdx.x * 8;
@@ -181,17 +208,18 @@ k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
         }
     }
   }
+  cnt_ins += cnt & 0xffffu; cnt_cand += cnt >> 16;      // per tile and thread <= 16 each: the packed counter cannot carry
+  }
   unsigned smax = max(smax2 & 0xffffu, smax2 >> 16);
-  cnt = bk::warp_sum(cnt);
+  cnt_ins = bk::warp_sum(cnt_ins); cnt_cand = bk::warp_sum(cnt_cand);
   sum_abs = bk::warp_sum(sum_abs);
   sum_sq = bk::warp_sum(sum_sq);
   for (int o = 16; o; o >>= 1) { xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o)); smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o)); }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh_cnt, cnt); atomicAdd(&sh_sum, sum_abs); atomicAdd(&sh_sq, sum_sq); atomicMax(&sh_xmax, xmax); atomicMax(&sh_span, smax); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh_cnt, cnt_ins); atomicAdd(&sh_cand, cnt_cand); atomicAdd(&sh_sum, sum_abs); atomicAdd(&sh_sq, sum_sq); atomicMax(&sh_xmax, xmax); atomicMax(&sh_span, smax); }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned c = sh_cnt;
-    if (c & 0xffffu) { atomicAdd(g + G_SUM, sh_sum); atomicAdd(g + G_CNT, (unsigned long long)(c & 0xffffu)); atomicAdd(g + G_SQ, sh_sq); atomicMax(g + G_XMAX, (unsigned long long)sh_xmax); }
-    if (c >> 16) atomicAdd(g + G_CAND, (unsigned long long)(c >> 16));
+    if (sh_cnt) { atomicAdd(g + G_SUM, sh_sum); atomicAdd(g + G_CNT, sh_cnt); atomicAdd(g + G_SQ, sh_sq); atomicMax(g + G_XMAX, (unsigned long long)sh_xmax); }
+    if (sh_cand) atomicAdd(g + G_CAND, sh_cand);
     if (S16 && sh_span) atomicMax(g + G_SPAN, (unsigned long long)sh_span);
   }
 }
@@ -554,13 +582,39 @@ __global__ void sd_sequential(const uint8_t *__restrict__ cls, ISizeCol isz, lon
 // Arithmetic per record: 6 FP64 instructions, no conversions -- x -> double by the 2^52 bit pattern, floor(a) by a
 // round-down add of 2^52 (exact for 0 <= a < 2^51; larger values raise the out-of-regime flag).
 // out[0] += sum floor(a), out[1] += E, out[2] |= out of regime.
+// floor(a) and the correction test of one |isize| (FP64 path): returns floor(a), sets rare / oor
+__device__ __forceinline__ unsigned long long sd_fast_eval(unsigned x, double mean, double thr, bool &rare, bool &oor)
+{
+  const double M52 = 4503599627370496.0;
+  double xd = __dsub_rn(__hiloint2double(0x43300000, (int)x), M52);      // exact for x < 2^32
+  double d = __dsub_rn(xd, mean);
+  double a = __dmul_rn(d, d);
+  double sft = __dadd_rd(a, M52);                                         // 2^52 + floor(a)
+  double fr = __dsub_rn(a, __dsub_rn(sft, M52));                          // frac(a), exact
+  rare = fr >= thr;
+  oor = !(a < 2251799813685248.0);
+  return (unsigned long long)__double_as_longlong(sft) & 0xFFFFFFFFFFFFFull;
+}
+// |isize| takes few values, all near the mean: every CTA first tabulates floor(a) for the SDF_WIN values around the mean in
+// shared memory (32-bit entries -- random lanes hit 32 banks; 0xffffffff = does not fit / needs the full evaluation), so
+// the streaming loop costs one shared load and a handful of integer instructions per record instead of six FP64 ones
+// (the all-FP64 version ran at 0.47 of the HBM peak: FP64-pipe bound).
+constexpr int SDF_WIN = 4096;
 template <bool NARROW>
 __global__ void __launch_bounds__(256)
 sd_fast(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, const int16_t *__restrict__ isize16, long long n, double mean, double thr,
         unsigned long long *__restrict__ out)
 {
-  const double M52 = 4503599627370496.0;
-  unsigned long long F = 0; unsigned E = 0, oor = 0;
+  __shared__ uint32_t tab[SDF_WIN];
+  const double mc = mean < 0.0 ? 0.0 : (mean > 2.0e9 ? 2.0e9 : mean);      // NaN -> 0 as well
+  const unsigned xlo = (unsigned)mc > (unsigned)(SDF_WIN / 2) ? (unsigned)mc - (unsigned)(SDF_WIN / 2) : 0u;
+  for (int k = threadIdx.x; k < SDF_WIN; k += blockDim.x) {
+    bool rare, oor;
+    unsigned long long fa = sd_fast_eval(xlo + (unsigned)k, mean, thr, rare, oor);
+    tab[k] = (rare || oor || fa >= 0xffffffffull) ? 0xffffffffu : (uint32_t)fa;
+  }
+  __syncthreads();
+  unsigned long long F = 0; unsigned E = 0, oorf = 0;
   const long long ngroups = (n + 7) / 8;
   for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += (long long)gridDim.x * blockDim.x) {
     long long i = gi * 8;
@@ -582,23 +636,23 @@ sd_fast(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, cons
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+      if (!(c[k] & CL_INSERT)) continue;
       unsigned x = (unsigned)(sv[k] < 0 ? -sv[k] : sv[k]);
-      double xd = __dsub_rn(__hiloint2double(0x43300000, (int)x), M52);      // exact for x < 2^32
-      double d = __dsub_rn(xd, mean);
-      double a = __dmul_rn(d, d);
-      double sft = __dadd_rd(a, M52);                                         // 2^52 + floor(a)
-      double fr = __dsub_rn(a, __dsub_rn(sft, M52));                          // frac(a), exact
-      bool on = (c[k] & CL_INSERT) != 0;
-      F += on ? ((unsigned long long)__double_as_longlong(sft) & 0xFFFFFFFFFFFFFull) : 0ull;
-      E += (on && fr >= thr) ? 1u : 0u;
-      oor |= (on && !(a < 2251799813685248.0)) ? 1u : 0u;
+      unsigned w = x - xlo;
+      uint32_t t = w < (unsigned)SDF_WIN ? tab[w] : 0xffffffffu;
+      if (t != 0xffffffffu) F += t;
+      else {
+        bool rare, oor;
+        F += sd_fast_eval(x, mean, thr, rare, oor);
+        E += rare ? 1u : 0u; oorf |= oor ? 1u : 0u;
+      }
     }
   }
-  F = bk::warp_sum(F); E = bk::warp_sum(E); oor = bk::warp_sum(oor);
+  F = bk::warp_sum(F); E = bk::warp_sum(E); oorf = bk::warp_sum(oorf);
   if ((threadIdx.x & 31) == 0) {
     if (F) atomicAdd(out, F);
     if (E) atomicAdd(out + 1, (unsigned long long)E);
-    if (oor) atomicOr(out + 2, 1ull);
+    if (oorf) atomicOr(out + 2, 1ull);
   }
 }
 
@@ -630,52 +684,59 @@ constexpr int KX_ITEMS = 4;
 constexpr int KX_TILE = KX_THREADS * KX_ITEMS;
 
 __global__ void __launch_bounds__(KX_THREADS) kx_count(const uint32_t *__restrict__ x_rec, long long n_x, const uint8_t *__restrict__ cls, long long n,
-                                                       uint32_t *__restrict__ tile_cnt, int *__restrict__ bad)
+                                                       uint32_t *__restrict__ tile_cnt, uint8_t *__restrict__ is_cand /* [n_x / KX_ITEMS]: 4 flag bits per thread */, int *__restrict__ bad)
 {
   __shared__ unsigned sh32[33];
   long long j0 = (long long)blockIdx.x * KX_TILE + threadIdx.x * KX_ITEMS;
-  unsigned cnt = 0;
+  unsigned cnt = 0, bits = 0;
+  uint32_t r[KX_ITEMS]; unsigned char c[KX_ITEMS];
+  uint32_t rprev = j0 > 0 && j0 < n_x ? x_rec[j0 - 1] : 0u;
+#pragma unroll
+  for (int k = 0; k < KX_ITEMS; ++k) r[k] = j0 + k < n_x ? x_rec[j0 + k] : 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < KX_ITEMS; ++k) c[k] = (j0 + k < n_x && (long long)r[k] < n) ? cls[r[k]] : 0;      // independent loads: issued together
 #pragma unroll
   for (int k = 0; k < KX_ITEMS; ++k) {
     long long j = j0 + k;
     if (j < n_x) {
-      uint32_t r = x_rec[j];
-      if ((long long)r >= n || (j > 0 && x_rec[j - 1] >= r)) atomicExch(bad, 1);
-      else cnt += (cls[r] >> 1) & 1u;
+      if ((long long)r[k] >= n || (j > 0 && rprev >= r[k])) atomicExch(bad, 1);
+      else if (c[k] & CL_CAND) { ++cnt; bits |= 1u << k; }
+      rprev = r[k];
     }
   }
+  if (j0 < n_x) is_cand[j0 / KX_ITEMS] = (uint8_t)bits;
   unsigned tot;
   bk::block_excl_scan<unsigned>(cnt, sh32, tot);
   if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(KX_THREADS) kx_write(const uint32_t *__restrict__ x_rec, long long n_x, const uint8_t *__restrict__ cls, long long n, const uint32_t *__restrict__ tile_off,
+__global__ void __launch_bounds__(KX_THREADS) kx_write(const uint32_t *__restrict__ x_rec, long long n_x, const uint8_t *__restrict__ is_cand, long long n, const uint32_t *__restrict__ tile_off,
                                                        const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ tid, const int32_t *__restrict__ pos,
                                                        const int32_t *__restrict__ x_mtid, const int32_t *__restrict__ x_mpos, const uint64_t *__restrict__ x_nh,
                                                        unsigned long long index_offset, bkid_cand *__restrict__ out, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
   __shared__ unsigned sh32[33];
   long long j0 = (long long)blockIdx.x * KX_TILE + threadIdx.x * KX_ITEMS;
-  unsigned is[KX_ITEMS], cnt = 0;
-  uint32_t rr[KX_ITEMS];
-#pragma unroll
-  for (int k = 0; k < KX_ITEMS; ++k) {
-    long long j = j0 + k;
-    is[k] = 0; rr[k] = 0;
-    if (j < n_x) { uint32_t r = x_rec[j]; rr[k] = r; if ((long long)r < n) is[k] = (cls[r] >> 1) & 1u; }
-    cnt += is[k];
-  }
+  const unsigned bits = j0 < n_x ? (unsigned)is_cand[j0 / KX_ITEMS] : 0u;       // kx_count's verdict: the class bytes are not read again
   unsigned tot;
-  unsigned off = bk::block_excl_scan<unsigned>(cnt, sh32, tot) + tile_off[blockIdx.x];
+  unsigned off = bk::block_excl_scan<unsigned>(__popc(bits), sh32, tot) + tile_off[blockIdx.x];
+  if (!bits) return;
+  // gather the four dense fields of all candidates of this thread first (independent loads), then write the rows
+  uint32_t i4[KX_ITEMS]; int32_t t4[KX_ITEMS], p4[KX_ITEMS]; uint16_t f4[KX_ITEMS]; uint8_t m4[KX_ITEMS];
+#pragma unroll
+  for (int k = 0; k < KX_ITEMS; ++k) i4[k] = (bits >> k) & 1u ? x_rec[j0 + k] : 0u;
 #pragma unroll
   for (int k = 0; k < KX_ITEMS; ++k)
-    if (is[k]) {
-      long long j = j0 + k; uint32_t i = rr[k];
+    if ((bits >> k) & 1u) { t4[k] = tid[i4[k]]; p4[k] = pos[i4[k]]; f4[k] = flag[i4[k]]; m4[k] = mapq[i4[k]]; }
+#pragma unroll
+  for (int k = 0; k < KX_ITEMS; ++k)
+    if ((bits >> k) & 1u) {
+      long long j = j0 + k;
       bkid_cand c;
       c.name_lo = x_nh[2 * (size_t)j]; c.name_hi = x_nh[2 * (size_t)j + 1];
-      c.tid = tid[i]; c.pos = pos[i]; c.mtid = x_mtid[j]; c.mpos = x_mpos[j];
-      c.gidx = index_offset + i;
-      c.flag = flag[i]; c.mapq = mapq[i];
+      c.tid = t4[k]; c.pos = p4[k]; c.mtid = x_mtid[j]; c.mpos = x_mpos[j];
+      c.gidx = index_offset + i4[k];
+      c.flag = f4[k]; c.mapq = m4[k];
       c._pad[0] = c._pad[1] = c._pad[2] = c._pad[3] = c._pad[4] = 0;
       out[off] = c;
       if (keys) { keys[off] = c.name_lo; vals[off] = off; }

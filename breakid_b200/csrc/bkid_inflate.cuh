@@ -96,21 +96,23 @@ BKI_FN uint32_t rev_bits(uint32_t v, int n)
 // block's first output byte: R0 = first byte, R = next byte, Rend = one past the last.
 struct Lane {
   const uint8_t *in; uint32_t in_len, ipos;      // ipos: offset of the next (4-byte aligned) input word
-  uint64_t bits; uint32_t nbits, nextw;           // bit buffer, its fill, the word loaded one refill ahead
+  uint64_t bits; uint32_t nbits, nextw, nextw2;   // bit buffer, its fill, the two words loaded ahead (each load is consumed two refills later)
+  uint64_t m0, m1;                                // match source words of the next chunk, loaded one step ahead (see lane_step)
   uint8_t *ob; uint32_t R, R0, Rend;
   uint64_t pend; uint32_t head_lo;                // pending output word; first valid byte of the block's FIRST word (foreign bytes below)
   uint32_t copy_rem, copy_dist, stored_rem;
   int phase, last;
 };
 
-// The input may be read up to 16 bytes past `in_len` and 3 bytes before `in` (aligned word loads); the caller's
+// The input may be read up to 24 bytes past `in_len` and 3 bytes before `in` (aligned word loads); the caller's
 // buffer provides that slack (BGZF: the next block's header / the staging buffer's padding).
 BKI_FN void lane_init(Lane &L, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len)
 {
   uint32_t a = (uint32_t)((uintptr_t)in & 3u);
   L.in = in; L.in_len = in_len;
   L.bits = (uint64_t)(ld32a(in - a) >> (8u * a)); L.nbits = 32u - 8u * a; L.ipos = 4u - a;
-  L.nextw = ld32a(in + L.ipos);
+  L.nextw = ld32a(in + L.ipos); L.nextw2 = ld32a(in + L.ipos + 4);
+  L.m0 = 0; L.m1 = 0;
   uint32_t a0 = (uint32_t)((uintptr_t)out & 7u);
   L.ob = out - a0; L.R0 = a0; L.R = a0; L.Rend = a0 + out_len;
   L.pend = 0; L.head_lo = a0;
@@ -124,7 +126,8 @@ BKI_FN void refill(Lane &L)
   if (L.nbits <= 32u) {
     L.bits |= (uint64_t)L.nextw << L.nbits;
     L.nbits += 32u; L.ipos += 4u;
-    L.nextw = ld32a(L.in + L.ipos);
+    L.nextw = L.nextw2;
+    L.nextw2 = ld32a(L.in + L.ipos + 4u);
   }
 }
 BKI_FN void drop(Lane &L, uint32_t n) { L.bits >>= n; L.nbits -= n; }
@@ -293,92 +296,107 @@ BKI_FN void emit(Lane &L, uint64_t v, uint32_t n)
   L.R += n;
 }
 
-// One step of a lane in PH_TOKENS / PH_STORED: up to LITMAX literals, or one match token, plus up to 8 match bytes.
+// match source of the next chunk (up to 8 bytes at S = R - dist, S < R): the two aligned words around S that are already in
+// memory are LOADED here and used one step later, so that their latency (these are bytes written moments ago: an L2
+// round trip) overlaps the decode work the warp does for its other lanes in between.  Words at or above the pending word
+// are not in memory yet: lane_copy_chunk takes them from `pend`, which the lane does not touch between the two calls.
+BKI_FN void lane_copy_issue(Lane &L)
+{
+  uint32_t S = L.R - L.copy_dist, Ws = S & ~7u, Wb = L.R & ~7u;
+  if (Ws < Wb) L.m0 = ld64a(L.ob + Ws);
+  if ((S & 7u) && Ws + 8u < Wb) L.m1 = ld64a(L.ob + Ws + 8u);
+}
+BKI_FN void lane_copy_chunk(Lane &L)
+{
+  uint32_t S = L.R - L.copy_dist, Ws = S & ~7u, s = S & 7u, Wb = L.R & ~7u;
+  uint64_t m0 = (Ws == Wb) ? L.pend : L.m0;
+  uint64_t v = m0;
+  if (s) {
+    uint32_t W1 = Ws + 8u;
+    uint64_t m1 = (W1 == Wb) ? L.pend : (W1 < Wb ? L.m1 : 0ull);
+    v = (m0 >> (8u * s)) | (m1 << (64u - 8u * s));
+  }
+  if (L.copy_dist < 8u) {                                // overlapping match: the output is periodic in `dist`
+    uint32_t sh = 8u * L.copy_dist;
+    v &= (1ull << sh) - 1ull;
+    v |= v << sh;
+    if (2u * sh < 64u) v |= v << (2u * sh);
+    if (4u * sh < 64u) v |= v << (4u * sh);
+  }
+  uint32_t n = L.copy_rem < 8u ? L.copy_rem : 8u;
+  if (n < 8u) v &= (1ull << (8u * n)) - 1ull;
+  L.copy_rem -= n;
+  emit(L, v, n);
+  if (L.copy_rem) lane_copy_issue(L);
+}
+
+// One step of a lane in PH_TOKENS / PH_STORED: first up to 8 bytes of a match in progress (its source words were loaded a
+// step ago), then -- unless the match goes on -- one token: up to LITMAX literals, or a match whose first source words
+// are requested right away.  The match branch comes BEFORE the literal branch so that, in a warp, the literal work of
+// the other lanes runs while those loads are in flight.
 template <int LITMAX>
 BKI_FN int lane_step(Lane &L, const Tab &T)
 {
-  uint64_t v = 0; uint32_t n = 0;
   if (L.phase == PH_STORED) {
     refill(L);
-    n = L.stored_rem < 4u ? L.stored_rem : 4u;
-    v = L.bits & ((1ull << (8u * n)) - 1ull);
+    uint32_t n = L.stored_rem < 4u ? L.stored_rem : 4u;
+    uint64_t v = L.bits & ((1ull << (8u * n)) - 1ull);
     drop(L, 8u * n);
     L.stored_rem -= n;
     if (L.stored_rem == 0) L.phase = L.last ? PH_DONE : PH_HEADER;
-  } else {
-    if (L.copy_rem == 0) {
-      refill(L);
-      if (L.ipos > L.in_len + 16u) return ERR_INPUT;         // a corrupt stream cannot run away from its payload
-      uint32_t e = T.lit_fast[(uint32_t)L.bits & ((1u << LIT_BITS) - 1u)], len;
-      int sym;
-      if (e) { len = e & 15u; sym = (int)(e >> 4); }
-      else { sym = slow_sym<uint16_t, LIT_BITS + 1>(L.bits, T.lit_lim, T.lit_off, T.lit_sym, len); if (sym < 0) return ERR_SYMBOL; }
-      drop(L, len);
-      if (sym < 256) {
-        v = (uint64_t)sym; n = 1;
-#pragma unroll
-        for (int j = 1; j < LITMAX; ++j) {
-          refill(L);
-          uint32_t e2 = T.lit_fast[(uint32_t)L.bits & ((1u << LIT_BITS) - 1u)];
-          if (e2 == 0 || e2 >= (256u << 4)) break;
-          drop(L, e2 & 15u);
-          v |= (uint64_t)(e2 >> 4) << (8u * n);
-          ++n;
-        }
-        if (L.R + n > L.Rend) return ERR_OUTPUT;
-      } else if (sym == 256) {
-        L.phase = L.last ? PH_DONE : PH_HEADER;
-        return OK;
-      } else {
-        if (sym > 285) return ERR_SYMBOL;
-        uint32_t mlen;
-        if (sym < 265) mlen = (uint32_t)sym - 254u;
-        else if (sym == 285) mlen = 258u;
-        else {
-          uint32_t eb = (uint32_t)(sym - 261) >> 2;
-          mlen = ((4u + ((uint32_t)(sym - 261) & 3u)) << eb) + 3u + take(L, eb);
-        }
-        refill(L);
-        uint32_t ed = T.dist_fast[(uint32_t)L.bits & ((1u << DIST_BITS) - 1u)], dl;
-        int ds;
-        if (ed) { dl = ed & 15u; ds = (int)(ed >> 4); }
-        else { ds = slow_sym<uint8_t, DIST_BITS + 1>(L.bits, T.dist_lim, T.dist_off, T.dist_sym, dl); if (ds < 0) return ERR_DIST; }
-        drop(L, dl);
-        if (ds > 29) return ERR_DIST;
-        uint32_t dist;
-        if (ds < 4) dist = (uint32_t)ds + 1u;
-        else {
-          uint32_t eb = ((uint32_t)ds >> 1) - 1u;
-          dist = ((2u + ((uint32_t)ds & 1u)) << eb) + 1u + take(L, eb);
-        }
-        if (dist > L.R - L.R0) return ERR_DIST;
-        if (L.R + mlen > L.Rend) return ERR_OUTPUT;
-        L.copy_rem = mlen; L.copy_dist = dist;
-      }
-    }
-    if (L.copy_rem) {
-      // up to 8 bytes of the match.  Source position S < R; words below the pending word are in memory already.
-      uint32_t S = L.R - L.copy_dist, Ws = S & ~7u, s = S & 7u, Wb = L.R & ~7u;
-      uint64_t m0 = (Ws == Wb) ? L.pend : ld64a(L.ob + Ws);
-      v = m0;
-      if (s) {
-        uint32_t W1 = Ws + 8u;
-        uint64_t m1 = (W1 == Wb) ? L.pend : (W1 < Wb ? ld64a(L.ob + W1) : 0ull);
-        v = (m0 >> (8u * s)) | (m1 << (64u - 8u * s));
-      }
-      if (L.copy_dist < 8u) {                                // overlapping match: the output is periodic in `dist`
-        uint32_t sh = 8u * L.copy_dist;
-        v &= (1ull << sh) - 1ull;
-        v |= v << sh;
-        if (2u * sh < 64u) v |= v << (2u * sh);
-        if (4u * sh < 64u) v |= v << (4u * sh);
-      }
-      n = L.copy_rem < 8u ? L.copy_rem : 8u;
-      if (n < 8u) v &= (1ull << (8u * n)) - 1ull;
-      L.copy_rem -= n;
-    }
+    emit(L, v, n);
+    return OK;
   }
-  if (n) emit(L, v, n);
+  if (L.copy_rem) lane_copy_chunk(L);
+  if (L.copy_rem) return OK;
+  refill(L);
+  if (L.ipos > L.in_len + 16u) return ERR_INPUT;           // a corrupt stream cannot run away from its payload
+  uint32_t e = T.lit_fast[(uint32_t)L.bits & ((1u << LIT_BITS) - 1u)], len;
+  int sym;
+  if (e) { len = e & 15u; sym = (int)(e >> 4); }
+  else { sym = slow_sym<uint16_t, LIT_BITS + 1>(L.bits, T.lit_lim, T.lit_off, T.lit_sym, len); if (sym < 0) return ERR_SYMBOL; }
+  drop(L, len);
+  if (sym > 256) {
+    if (sym > 285) return ERR_SYMBOL;
+    uint32_t mlen;
+    if (sym < 265) mlen = (uint32_t)sym - 254u;
+    else if (sym == 285) mlen = 258u;
+    else {
+      uint32_t eb = (uint32_t)(sym - 261) >> 2;
+      mlen = ((4u + ((uint32_t)(sym - 261) & 3u)) << eb) + 3u + take(L, eb);
+    }
+    refill(L);
+    uint32_t ed = T.dist_fast[(uint32_t)L.bits & ((1u << DIST_BITS) - 1u)], dl;
+    int ds;
+    if (ed) { dl = ed & 15u; ds = (int)(ed >> 4); }
+    else { ds = slow_sym<uint8_t, DIST_BITS + 1>(L.bits, T.dist_lim, T.dist_off, T.dist_sym, dl); if (ds < 0) return ERR_DIST; }
+    drop(L, dl);
+    if (ds > 29) return ERR_DIST;
+    uint32_t dist;
+    if (ds < 4) dist = (uint32_t)ds + 1u;
+    else {
+      uint32_t eb = ((uint32_t)ds >> 1) - 1u;
+      dist = ((2u + ((uint32_t)ds & 1u)) << eb) + 1u + take(L, eb);
+    }
+    if (dist > L.R - L.R0) return ERR_DIST;
+    if (L.R + mlen > L.Rend) return ERR_OUTPUT;
+    L.copy_rem = mlen; L.copy_dist = dist;
+    lane_copy_issue(L);
+    return OK;
+  }
+  if (sym == 256) { L.phase = L.last ? PH_DONE : PH_HEADER; return OK; }
+  uint64_t v = (uint64_t)sym; uint32_t n = 1;
+#pragma unroll
+  for (int j = 1; j < LITMAX; ++j) {
+    refill(L);
+    uint32_t e2 = T.lit_fast[(uint32_t)L.bits & ((1u << LIT_BITS) - 1u)];
+    if (e2 == 0 || e2 >= (256u << 4)) break;
+    drop(L, e2 & 15u);
+    v |= (uint64_t)(e2 >> 4) << (8u * n);
+    ++n;
+  }
+  if (L.R + n > L.Rend) return ERR_OUTPUT;
+  emit(L, v, n);
   return OK;
 }
 

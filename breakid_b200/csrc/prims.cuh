@@ -16,8 +16,18 @@
 
 void bk_set_cuda_error(cudaError_t e, const char *file, int line);
 extern thread_local long long g_bk_launches;
+// per-kernel device times (bkid_profile_kernels): when switched on, every launch is bracketed by two CUDA events on
+// the stream it is launched on; off (the default) costs one predictable branch
+extern bool g_bk_prof_on;
+void bk_prof_begin(const char *name, cudaStream_t st);
+void bk_prof_end(cudaStream_t st);
 #define BK_LAUNCH(kernel, grid, block, smem, stream, ...)                   \
-  do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); ++g_bk_launches; } while (0)
+  do {                                                                      \
+    if (g_bk_prof_on) bk_prof_begin(#kernel, (stream));                     \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
+    if (g_bk_prof_on) bk_prof_end((stream));                                \
+    ++g_bk_launches;                                                        \
+  } while (0)
 
 namespace bk {
 

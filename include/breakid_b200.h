@@ -256,6 +256,11 @@ int bkid_fetch_clusters(bkid_ctx *ctx, bkid_cluster_rec *out, int64_t cap, int64
 int bkid_fetch_pairs(bkid_ctx *ctx, int stage, bkid_pair *out, int64_t cap, int64_t *n);
 int bkid_fetch_class(bkid_ctx *ctx, uint8_t *out, int64_t cap);   /* per-record class mask of the classify kernel */
 int bkid_get_timings(bkid_ctx *ctx, bkid_timings *t);
+/* Measurement aid: with profiling on, every kernel the library launches is bracketed by two CUDA events on its own stream.
+ * bkid_profile_report writes one "kernel<TAB>launches<TAB>milliseconds" line per kernel name (summed since switched on; the
+ * report resets the collection) into buf and returns the size needed.  Process-wide; off by default. */
+int bkid_profile_kernels(int on);
+int64_t bkid_profile_report(char *buf, int64_t cap);
 
 /* ---- multi-GPU shard entry points -----------------------------------------------------------------
  * One context per rank holds a contiguous slice of the coordinate-sorted record stream (genomic bins).

@@ -89,7 +89,11 @@ void orc_insert_stats(long n, const uint16_t *flag, const int32_t *isize, double
 }
 
 /* src/BreakID.cc:103 -- one distance used by scan, mask, span and cluster stages */
-double orc_dist(double mean, double sd, int times) { return times * sqrt(times) * (mean + 3 * sd); }
+/* src/BreakID.cc:103.  The literal 3 is the only thing the extension flag -s replaces (include/breakid_b200.h: bkid_params.sd_mult);
+ * its reference counterpart is the same binary with that one literal read from the environment (oracle/Makefile: ref_s). */
+static int g_sd_mult = 3;
+void orc_set_sd_mult(int m) { g_sd_mult = m; }
+double orc_dist(double mean, double sd, int times) { return times * sqrt(times) * (mean + g_sd_mult * sd); }
 
 /* ------------------------------------------------------------------------------------------
  * a2/a3. discordant-pair scan -- src/BreakID.cc:1362-1515, src/util_bam.cc:7-47,57-68.

@@ -157,8 +157,12 @@ def insert_stats(hb):
     return m.value, s.value, a.value, b.value, c.value
 
 
-def dist(mean, sd, times=2):
-    return olib().orc_dist(mean, sd, times)
+def dist(mean, sd, times=2, sd_mult=3):
+    olib().orc_set_sd_mult(int(sd_mult))
+    try:
+        return olib().orc_dist(mean, sd, times)
+    finally:
+        olib().orc_set_sd_mult(3)
 
 
 def scan(hb, qual, w):
@@ -222,8 +226,17 @@ def neighbor_41(packed, nbases, bp):
     return buf.value
 
 
-def run(hb, nibs=None, qual=20, times=2, mode=0):
-    """whole hot path; nibs = list of (packed uint8 array, n_bases) per tid or None"""
+def run(hb, nibs=None, qual=20, times=2, mode=0, sd_mult=3):
+    """whole hot path; nibs = list of (packed uint8 array, n_bases) per tid or None.  sd_mult replaces the literal 3 of
+    src/BreakID.cc:103 (the -s extension)"""
+    olib().orc_set_sd_mult(int(sd_mult))
+    try:
+        return _run(hb, nibs, qual, times, mode)
+    finally:
+        olib().orc_set_sd_mult(3)
+
+
+def _run(hb, nibs, qual, times, mode):
     c, s = hb.cols, hb.side
     nt = len(hb.target_names)
     if nibs is not None:
@@ -257,8 +270,15 @@ def ref_install_refgene(path):
     shutil.copy(path, os.path.join(REF_INSTALL, "ref_files", "refGene.txt"))
 
 
-def ref_run_binary(bam, prefix, nib_dir, fast=False, all_=True, qual=None, timeout=3600, extra=()):
-    cmd = [REF_BIN, "-i", bam, "-o", prefix, "-n", nib_dir]
+def ref_run_binary(bam, prefix, nib_dir, fast=False, all_=True, qual=None, timeout=3600, extra=(), sd_mult=None):
+    """the reference binary.  sd_mult: the binary built by `make -C oracle ref_s`, in which the literal 3 of
+    src/BreakID.cc:103 is read from BREAKID_SD_MULT (the reference has no -s flag: an unknown flag makes it crash)"""
+    env = None
+    exe = REF_BIN
+    if sd_mult is not None:
+        exe = REF_BIN + "_s"
+        env = dict(os.environ, BREAKID_SD_MULT=str(int(sd_mult)))
+    cmd = [exe, "-i", bam, "-o", prefix, "-n", nib_dir]
     if fast:
         cmd.append("-fast")
     if all_:
@@ -266,7 +286,7 @@ def ref_run_binary(bam, prefix, nib_dir, fast=False, all_=True, qual=None, timeo
     if qual is not None:
         cmd += ["-q", str(qual)]
     cmd += list(extra)
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
 
 
 def ref_scan(bam, qual, w, nib_dir):

@@ -20,8 +20,9 @@ OURS_SKIP = ("native::", "at::", "vectorized_elementwise", "elementwise_kernel",
 
 
 def short(name):
-    n = name.split("(")[0]
-    return n.replace("void ", "").strip()
+    import re
+    m = re.match(r"^(?:void )?([\w:]+)", name.strip())          # templated kernels: k1_classify<(bool)1, (bool)1>(...) -> k1_classify
+    return m.group(1) if m else name.split("(")[0].replace("void ", "").strip()
 
 
 def launches(src, dst, title):
@@ -33,7 +34,7 @@ def launches(src, dst, title):
             continue
         rows.append((short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"])))
     ours = [r for r in rows if not any(s in r[0] for s in OURS_SKIP)]
-    starts = [i for i, r in enumerate(ours) if r[0] == "k1_classify"]
+    starts = [i for i, r in enumerate(ours) if r[0].startswith("k1_classify")]
     # the bench runs warm-up steps, the timed resident steps, then the e2e steps; the resident steps are identical,
     # take the last one that is followed by another k1_classify (= a complete step)
     assert len(starts) >= 2, "no complete step in the launch list"
