@@ -469,15 +469,25 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     engine = None
+    libdist = None
     shard_timing = {}
     timing_on = [False]
     if world > 1:
-        from breakid_b200.dist import GpuEngine, run_sharded
-        engine = GpuEngine(ctx, dev)
+        from breakid_b200.dist import GpuEngine, LibraryDist, DIST_STAGES, run_sharded
+        if args.py_dist:
+            engine = GpuEngine(ctx, dev)              # the Python-orchestrated exchanges (torch.distributed), kept for A/B
+        else:
+            libdist = LibraryDist(ctx, dev)           # the exchanges inside the library: NCCL calls from C++
 
     def run_path():
         if world == 1:
             return ctx.run()
+        if libdist is not None:
+            mean, sd, dd, nc, tms = libdist.run(0)
+            if timing_on[0]:
+                for k, v in zip(DIST_STAGES, tms):
+                    shard_timing[k] = shard_timing.get(k, 0.0) + v
+            return mean, sd, dd, nc
         mean, sd, dd, out = run_sharded(engine, n, mode=0, timing=shard_timing if timing_on[0] else None)
         return mean, sd, dd, len(out)
 
@@ -542,7 +552,7 @@ def run_ours(args):
         ctx.reset()
         ctx.lib.bkid_push_batch(ctx.ctx, C.byref(b_host))
         r = run_path()
-        out = ctx.fetch_clusters() if world == 1 else None
+        out = ctx.fetch_clusters() if (world == 1 or libdist is not None) else None
         return r, out
     input_bytes = sum(v.numel() * v.element_size() for v in keep.values())
     del keep
@@ -618,8 +628,11 @@ def run_ours(args):
     }
     if world > 1:
         from breakid_b200 import dist as _d
-        line["collective_ms_per_step"] = {k: v / 2.0 / max(1, 1) for k, v in _d._A2A_T.items()}
+        line["exchanges"] = ("inside the library: NCCL all-reduce / grouped send-recv issued from C++ (bkid_dist_run)" if libdist is not None
+                             else "Python-orchestrated (torch.distributed), --py-dist")
         line["sharded_parity"] = pre
+        if libdist is not None:
+            libdist.close()
     ctx.close()
     del hkeep, b_host
     torch.cuda.empty_cache()
@@ -707,10 +720,14 @@ def sharded_parity(rank, world, local, dev):
     cuts = [hb.n * i // world for i in range(world + 1)]
     part = _slice(hb, cuts[rank], cuts[rank + 1])
     res = {}
+    from breakid_b200.dist import LibraryDist
     for label, mode, kw, sdm in (("ahc", 0, {}, 3), ("fast", 1, {"fast": 1}, 3), ("q20_s15", 0, {"qual": 20, "sd_mult": 15}, 15)):
         ctx = api.Context(hb.target_len, hb.target_names, device=local, **kw)
         ctx.push(part)
-        mean, sd, dd, out = run_sharded(GpuEngine(ctx, dev), part.n, mode=mode, sd_mult=sdm)
+        ld = LibraryDist(ctx, dev)
+        mean, sd, dd, ncall, _ = ld.run(mode)
+        out = ctx.fetch_clusters()
+        ld.close()
         ok = True
         if rank == 0:
             m, s, d0, exp = O.run(hb, None, mode=mode, sd_mult=sdm)
@@ -791,6 +808,7 @@ def main():
     ap.add_argument("--no-decode", action="store_true", help="skip the decode-included e2e (BAM file -> device inflate -> hot path)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison on configs[1] x 1/16")
     ap.add_argument("--stress-scale", type=float, default=1.0, help="fraction of the 1e7-SA-record stress workload")
+    ap.add_argument("--py-dist", action="store_true", help="N > 1: use the Python-orchestrated exchanges instead of the library's NCCL path")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -278,7 +278,8 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_set_pairs", "bkid_shard_clusters", "bkid_shard_set_clusters", "bkid_shard_sa_rows", "bkid_shard_set_sa_rows",
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
-           "bkid_push_bgzf", "bkid_push_bgzf_range", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align", "bkid_profile_kernels", "bkid_profile_report"]
+           "bkid_push_bgzf", "bkid_push_bgzf_range", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align", "bkid_profile_kernels", "bkid_profile_report",
+           "bkid_comm_nccl_unique_id", "bkid_comm_nccl_init", "bkid_comm_nccl_init_all", "bkid_comm_local_create", "bkid_comm_destroy", "bkid_dist_run", "bkid_dist_run_threads"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -349,6 +350,14 @@ def cuda_lib():
         L.bkid_shard_finish.argtypes = [vp, i64p]
         L.bkid_fetch_bucket_ranks.argtypes = [vp, vp, C.c_int64, i64p]
         L.bkid_device_copy.argtypes = [vp, vp, vp, C.c_uint64]
+        L.bkid_comm_nccl_unique_id.argtypes = [vp]
+        L.bkid_comm_nccl_init.restype = vp
+        L.bkid_comm_nccl_init.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.bkid_comm_nccl_init_all.argtypes = [vp, C.c_int, vp]
+        L.bkid_comm_local_create.argtypes = [C.c_int, vp]
+        L.bkid_comm_destroy.argtypes = [vp]
+        L.bkid_dist_run.argtypes = [vp, vp, C.c_int, dp, dp, dp, i64p, C.POINTER(C.c_float)]
+        L.bkid_dist_run_threads.argtypes = [vp, vp, C.c_int, C.c_int, dp, dp, dp, i64p]
         L.bkid_profile_kernels.argtypes = [C.c_int]
         L.bkid_profile_report.argtypes = [C.c_char_p, C.c_int64]
         L.bkid_profile_report.restype = C.c_int64
@@ -358,6 +367,30 @@ def cuda_lib():
 
 class BkidError(RuntimeError):
     pass
+
+
+def dist_run_local(ctxs: Sequence["Context"], mode: int = 0):
+    """the sharded hot path with the exchanges inside the library, every rank a host thread of this process
+    (``bkid_comm_local_create`` + ``bkid_dist_run_threads``): contexts may share one device.  ctxs[r] holds the r-th slice
+    of the coordinate-sorted stream.  Returns [(mean, sd, dist, n_called)] per rank; fetch the calls from any context."""
+    L = cuda_lib()
+    W = len(ctxs)
+    comms = (C.c_void_p * W)()
+    rc = L.bkid_comm_local_create(W, comms)
+    if rc:
+        raise BkidError("bkid_comm_local_create failed: %d" % rc)
+    try:
+        cp = (C.c_void_p * W)(*[c.ctx for c in ctxs])
+        m, s, d = (C.c_double * W)(), (C.c_double * W)(), (C.c_double * W)()
+        n = (C.c_int64 * W)()
+        rc = L.bkid_dist_run_threads(cp, comms, W, mode, m, s, d, n)
+        if rc:
+            msgs = [(L.bkid_last_error(c.ctx) or b"").decode() for c in ctxs]
+            raise BkidError("bkid_dist_run_threads: error %d: %s" % (rc, "; ".join(x for x in msgs if x)))
+        return [(m[r], s[r], d[r], n[r]) for r in range(W)]
+    finally:
+        for r in range(W):
+            L.bkid_comm_destroy(comms[r])
 
 
 def profile_kernels(on: bool):

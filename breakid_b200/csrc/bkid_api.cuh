@@ -45,7 +45,7 @@ struct bkid_ctx {
   std::vector<int32_t> ex_iv;               // exclude intervals: merged, sorted (tid, beg, end) triples
   DBuf ex_tab, ex_lo, ex_len, ex_pre;
   long long n_excluded = 0;
-  int device = 0;
+  int device = 0, n_sm = 148;
   cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;     // st2: side stream for the sd replay (overlaps the join); st3: max span (needed only by the refinement)
   bkid_params prm;
   int nt = 0;
@@ -57,7 +57,7 @@ struct bkid_ctx {
   // resident record columns (file order)
   long long n = 0, cap_n = 0;
   bool borrowed = false;
-  DBuf flag, mapq, tid, pos, isize, endpos, cls;
+  DBuf flag, mapq, tid, pos, isize, endpos, cls, cand_bits;
   DBuf isize16, span16;                     // narrow forms of the insert-size / span columns (kept narrow in HBM when the batches have them)
   int form_isize = 0, form_span = 0;        // 0 = undecided (empty context), 1 = wide (isize / endpos), 2 = narrow (isize16 / span16)
   long long reserve_hint = 0;               // bkid_reserve on an empty context: applied once the column forms are known
@@ -106,6 +106,7 @@ struct bkid_ctx {
   long long n_clusters = 0, n_called = 0;
   Scratch sc;
   DBuf tmpA, tmpB, tmpC, tmpD, tmpE, tmpF, tmpG, tmpH;
+  DBuf dist_send, dist_recv, dist_rows;     // multi-GPU exchanges (bkid_dist.cuh)
   bkid_timings tm;
   cudaEvent_t ev[16];
   cudaEvent_t ev_run[2];
@@ -432,7 +433,9 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
     BK_LAUNCH(ahc_rg_heads, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO, bucket_events);
     bk::exclusive_scan<uint32_t, uint32_t>(g.is_head, head_excl, n, stmp, tot, st);
     BK_LAUNCH(ahc_rg_head_list, GRID1(n, 256), 256, 0, st, g.is_head, head_excl, n, head_pos);
-    BK_LAUNCH(ahc_rg_ties, GRID1(nseg, 4), 128, 0, st, v, g, (uint32_t)nseg, bucket_flag, RG_LO, bucket_events, head_pos, head_excl, n);
+    const uint32_t RG_SMEM = 200u << 10;                   // buckets whose event tables fit are walked out of shared memory
+    BK_LAUNCH(ahc_rg_ties_smem, (unsigned)nseg, 128, RG_SMEM, st, v, g, (uint32_t)nseg, bucket_flag, RG_LO, bucket_events, head_pos, head_excl, n, RG_SMEM);
+    BK_LAUNCH(ahc_rg_ties, GRID1(nseg, 4), 128, 0, st, v, g, (uint32_t)nseg, bucket_flag, RG_LO, bucket_events, head_pos, head_excl, n, RG_SMEM);
     BK_LAUNCH(ahc_rg_write, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO);
   }
   T_.mark("ahc: replay rank form (global)");
@@ -558,6 +561,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   if (cudaSetDevice(device) != cudaSuccess) { g_create_err = "cudaSetDevice failed"; return nullptr; }
   bkid_ctx *c = new bkid_ctx();
   c->device = device;
+  cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
   if (params) c->prm = *params; else bkid_default_params(&c->prm);
   if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { g_create_err = "cudaStreamCreate failed"; delete c; return nullptr; }
   cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking);
@@ -593,6 +597,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   cudaFuncSetAttribute(sd_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_BLOCK * 9);
   cudaFuncSetAttribute(ahc_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
   cudaFuncSetAttribute(ahc_replay_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
+  cudaFuncSetAttribute(ahc_rg_ties_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
   memset(&c->tm, 0, sizeof c->tm);
   if (cudaGetLastError() != cudaSuccess) { g_create_err = "CUDA error during create"; delete c; return nullptr; }
   return c;
@@ -604,10 +609,10 @@ void bkid_destroy(bkid_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
   decoder_free(c);
-  for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->isize16, &c->span16, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
+  for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->isize16, &c->span16, &c->cand_bits, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->seq_off, &c->seq4, &c->seq_len, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH})
+                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH, &c->dist_send, &c->dist_recv, &c->dist_rows})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();
@@ -909,18 +914,26 @@ static int classify_impl(bkid_ctx *c)
   if (c->classified) return 0;
   cudaStream_t st = c->st;
   long long n = c->n;
-  int ntiles = std::min(div_up(std::max<long long>(n, 1), K1_TILE), 148 * 8);    // persistent: 8 CTAs of 256 threads per SM
+  int ntiles = div_up(std::max<long long>(n, 1), K1_TILE);
   TRY(c, c->cls.ensure((size_t)n + 64, 0, st));
+  TRY(c, c->cand_bits.ensure((size_t)n / 8 + 64, 0, st));
   unsigned long long *g = (unsigned long long *)(c->counters.as<unsigned>() + CS_G);
   CU(c, cudaMemsetAsync(g, 0, 64, st));
   cudaEventRecord(c->ev[2], st);
   const bool i16 = c->p_isize16 != nullptr, s16 = c->p_span16 != nullptr;
   if (n > 0) {
     uint8_t *cls = c->cls.as<uint8_t>();
-    if (i16 && s16) BK_LAUNCH((k1_classify<true, true>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, g);
-    else if (i16) BK_LAUNCH((k1_classify<true, false>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, g);
-    else if (s16) BK_LAUNCH((k1_classify<false, true>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, g);
-    else BK_LAUNCH((k1_classify<false, false>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, g);
+    // persistent grid = exactly what is resident at once (a partial second wave of persistent CTAs would idle most SMs)
+    int occ = 0;
+    if (i16 && s16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_classify<true, true>, K1_THREADS, 0);
+    else if (i16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_classify<true, false>, K1_THREADS, 0);
+    else if (s16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_classify<false, true>, K1_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_classify<false, false>, K1_THREADS, 0);
+    ntiles = std::min(ntiles, c->n_sm * std::max(occ, 1));
+    if (i16 && s16) BK_LAUNCH((k1_classify<true, true>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, c->cand_bits.as<uint8_t>(), g);
+    else if (i16) BK_LAUNCH((k1_classify<true, false>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, c->cand_bits.as<uint8_t>(), g);
+    else if (s16) BK_LAUNCH((k1_classify<false, true>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, c->cand_bits.as<uint8_t>(), g);
+    else BK_LAUNCH((k1_classify<false, false>), (unsigned)ntiles, K1_THREADS, 0, st, c->p_flag, c->p_mapq, c->p_isize, c->p_isize16, c->p_span16, n, c->prm.qual, cls, c->cand_bits.as<uint8_t>(), g);
   }
   cudaEventRecord(c->ev[3], st);
   int n_iv = (int)(c->ex_iv.size() / 3);
@@ -932,7 +945,7 @@ static int classify_impl(bkid_ctx *c)
     CU(c, cudaMemcpyAsync(c->ex_tab.p, c->ex_iv.data(), (size_t)n_iv * 12, cudaMemcpyHostToDevice, st));
     BK_LAUNCH(ex_ranges, GRID1(n_iv, 128), 128, 0, st, c->p_tid, c->p_pos, n, c->ex_tab.as<int32_t>(), n_iv, c->ex_lo.as<uint32_t>(), c->ex_len.as<uint32_t>());
     BK_LAUNCH(ex_prefix, 1, 32, 0, st, c->ex_len.as<uint32_t>(), n_iv, c->ex_pre.as<unsigned long long>());
-    BK_LAUNCH(ex_apply, 148 * 8, 256, 0, st, c->ex_lo.as<uint32_t>(), c->ex_pre.as<unsigned long long>(), n_iv, isize_col(c), c->cls.as<uint8_t>(), g);
+    BK_LAUNCH(ex_apply, 148 * 8, 256, 0, st, c->ex_lo.as<uint32_t>(), c->ex_pre.as<unsigned long long>(), n_iv, isize_col(c), c->cls.as<uint8_t>(), c->cand_bits.as<uint8_t>(), g);
     CU(c, cudaMemcpyAsync(&ne, c->ex_pre.as<unsigned long long>() + n_iv, 8, cudaMemcpyDeviceToHost, st));
   }
   unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
@@ -1027,8 +1040,12 @@ static int sd_fast_launch(bkid_ctx *c, double mean, int kub, cudaStream_t st)
   c->sd_kub = kub;
   if (n <= 0 || c->cnt_insert <= 0) return 0;
   double thr = 1.0 - ldexp(1.0, kub - 53);                                    // corrections need frac(a) >= 1 - 2^(k-53), k <= kub
-  if (c->p_isize16) BK_LAUNCH((sd_fast<true>), 148 * 8, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
-  else BK_LAUNCH((sd_fast<false>), 148 * 8, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
+  int occ = 0;
+  if (c->p_isize16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sd_fast<true>, 256, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sd_fast<false>, 256, 0);
+  const int grid = c->n_sm * std::max(occ, 1);
+  if (c->p_isize16) BK_LAUNCH((sd_fast<true>), grid, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
+  else BK_LAUNCH((sd_fast<false>), grid, 256, 0, st, c->cls.as<uint8_t>(), c->p_isize, c->p_isize16, n, mean, thr, out);
   return 0;
 }
 // F = sum floor(a), E = elements that could need a correction; exact iff E == 0 (and not out of regime: *E = ~0)
@@ -1145,11 +1162,11 @@ static int extract_candidates(bkid_ctx *c, unsigned long long index_offset, bool
   if (nx <= 0 || n <= 0) return 0;
   int ntiles = div_up(nx, KX_TILE);
   TRY(c, c->sc.ensure(std::max<long long>(cap, ntiles) + 8, st));
-  TRY(c, c->tile_cand.ensure((size_t)(ntiles + 1) * 4 * 2 + (size_t)ntiles * KX_THREADS + 64, 0, st));
+  TRY(c, c->tile_cand.ensure((size_t)(ntiles + 1) * 4 * 2 + (size_t)ntiles * KX_THREADS + 64, 0, st));       // one flag byte per kx thread
   uint32_t *tile_cnt = c->tile_cand.as<uint32_t>(), *tile_off = tile_cnt + ntiles + 1;
   uint8_t *is_cand = (uint8_t *)(tile_off + ntiles + 1);                 // 4 candidate bits per kx thread
   unsigned long long *tot = (unsigned long long *)(cs + CS_TOTAL);
-  BK_LAUNCH(kx_count, (unsigned)ntiles, KX_THREADS, 0, st, c->p_x_rec, nx, c->cls.as<uint8_t>(), n, tile_cnt, is_cand, (int *)(cs + CS_XBAD));
+  BK_LAUNCH(kx_count, (unsigned)ntiles, KX_THREADS, 0, st, c->p_x_rec, nx, c->cand_bits.as<uint8_t>(), n, tile_cnt, is_cand, (int *)(cs + CS_XBAD));
   bk::exclusive_scan<uint32_t, uint32_t>(tile_cnt, tile_off, ntiles, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
   CU(c, cudaMemcpyAsync(cs + CS_NC, tot, 4, cudaMemcpyDeviceToDevice, st));
   if (cap > 0)     // a table that lists more candidates than K1 counted cannot exist (same predicate, same class bytes)

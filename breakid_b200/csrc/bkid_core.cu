@@ -26,7 +26,9 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
+#include <memory>
 #include <map>
 #include <string>
 #include <vector>
@@ -139,7 +141,8 @@ __device__ __forceinline__ unsigned classify4(unsigned f01, unsigned f23, unsign
 template <bool I16, bool S16>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, const int32_t *__restrict__ isize, const int16_t *__restrict__ isize16,
-            const uint16_t *__restrict__ span16, long long n, int qual, uint8_t *__restrict__ cls, unsigned long long *__restrict__ g)
+            const uint16_t *__restrict__ span16, long long n, int qual, uint8_t *__restrict__ cls, uint8_t *__restrict__ cand_bits /* [n/8]: bit k of byte i = record 8i+k is a candidate */,
+            unsigned long long *__restrict__ g)
 {
   __shared__ unsigned long long sh_sum, sh_sq, sh_cnt, sh_cand;
   __shared__ unsigned sh_xmax, sh_span;
@@ -165,6 +168,11 @@ k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
       unsigned insA, insB;
       unsigned cA = classify4(f8.x, f8.y, m8.x, q4, q_never, insA), cB = classify4(f8.z, f8.w, m8.y, q4, q_never, insB);
       *reinterpret_cast<uint2 *>(cls + i) = make_uint2(cA, cB);
+      {  // candidate bit of byte k (0x02) -> bit k of one byte: the sparse-table pass reads 1 bit per entry instead of 1 byte
+        unsigned a = (cA >> 1) & 0x01010101u, b = (cB >> 1) & 0x01010101u;
+        a = (a | (a >> 7) | (a >> 14) | (a >> 21)) & 0xfu; b = (b | (b >> 7) | (b >> 14) | (b >> 21)) & 0xfu;
+        cand_bits[i >> 3] = (uint8_t)(a | (b << 4));
+      }
       cnt += __popc(cA & 0x01010101u) + __popc(cB & 0x01010101u) + ((__popc(cA & 0x02020202u) + __popc(cB & 0x02020202u)) << 16);
       if (S16) {
         uint4 p8 = *reinterpret_cast<const uint4 *>(span16 + i);
@@ -194,6 +202,7 @@ k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
         }
       }
     } else {
+      unsigned tail_bits = 0;
       for (int k = 0; k < 8; ++k)
         if (i + k < n) {
           unsigned c = classify_one(flag[i + k], mapq[i + k], qual);
@@ -205,7 +214,9 @@ k1_classify(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq,
           if (S16) smax2 = __vmaxu2(smax2, (unsigned)span16[i + k]);
           cnt += ((c >> 1) & 1u) << 16;
           cls[i + k] = (uint8_t)c;
+          tail_bits |= ((c >> 1) & 1u) << k;
         }
+      if (i < n) cand_bits[i >> 3] = (uint8_t)tail_bits;
     }
   }
   cnt_ins += cnt & 0xffffu; cnt_cand += cnt >> 16;      // per tile and thread <= 16 each: the packed counter cannot carry
@@ -258,7 +269,8 @@ __global__ void ex_prefix(const uint32_t *__restrict__ len, int n_iv, unsigned l
   pre[n_iv] = s;
 }
 __global__ void __launch_bounds__(256)
-ex_apply(const uint32_t *__restrict__ lo, const unsigned long long *__restrict__ pre, int n_iv, ISizeCol isz, uint8_t *__restrict__ cls, unsigned long long *__restrict__ g)
+ex_apply(const uint32_t *__restrict__ lo, const unsigned long long *__restrict__ pre, int n_iv, ISizeCol isz, uint8_t *__restrict__ cls, uint8_t *__restrict__ cand_bits,
+         unsigned long long *__restrict__ g)
 {
   unsigned long long E = pre[n_iv];
   unsigned long long sum = 0, sq = 0; unsigned cnt = 0, ncand = 0;
@@ -268,7 +280,7 @@ ex_apply(const uint32_t *__restrict__ lo, const unsigned long long *__restrict__
     long long i = (long long)lo[a] + (long long)(e - pre[a]);
     unsigned c = cls[i];
     if (c & CL_INSERT) { int s = isz.at(i); unsigned long long x = (unsigned long long)(s < 0 ? -(long long)s : (long long)s); sum += x; sq += x * x; ++cnt; }
-    if (c & CL_CAND) ++ncand;
+    if (c & CL_CAND) { ++ncand; atomicAnd(reinterpret_cast<unsigned *>(cand_bits + ((i >> 3) & ~3ll)), ~(1u << (unsigned)(((i >> 3) & 3ll) * 8 + (i & 7)))); }
     cls[i] = (uint8_t)CL_EXCL;
   }
   sum = bk::warp_sum(sum); sq = bk::warp_sum(sq); cnt = bk::warp_sum(cnt); ncand = bk::warp_sum(ncand);
@@ -605,48 +617,59 @@ __global__ void __launch_bounds__(256)
 sd_fast(const uint8_t *__restrict__ cls, const int32_t *__restrict__ isize, const int16_t *__restrict__ isize16, long long n, double mean, double thr,
         unsigned long long *__restrict__ out)
 {
-  __shared__ uint32_t tab[SDF_WIN];
+  // tab[0 .. WIN) = floor(a) of |isize| = xlo + k; tab[WIN] = "outside the window / needs the full evaluation" (also used for
+  // entries that do not fit: rare, out of regime, or >= 2^28 so that eight entries add up in 32 bits); tab[WIN + 1] = 0 is
+  // where records that do not pass the insert predicate are sent -- no branch per record
+  __shared__ uint32_t tab[SDF_WIN + 2];
   const double mc = mean < 0.0 ? 0.0 : (mean > 2.0e9 ? 2.0e9 : mean);      // NaN -> 0 as well
   const unsigned xlo = (unsigned)mc > (unsigned)(SDF_WIN / 2) ? (unsigned)mc - (unsigned)(SDF_WIN / 2) : 0u;
   for (int k = threadIdx.x; k < SDF_WIN; k += blockDim.x) {
     bool rare, oor;
     unsigned long long fa = sd_fast_eval(xlo + (unsigned)k, mean, thr, rare, oor);
-    tab[k] = (rare || oor || fa >= 0xffffffffull) ? 0xffffffffu : (uint32_t)fa;
+    tab[k] = (rare || oor || fa >= (1ull << 28)) ? 0xffffffffu : (uint32_t)fa;
   }
+  if (threadIdx.x == 0) { tab[SDF_WIN] = 0xffffffffu; tab[SDF_WIN + 1] = 0u; }
   __syncthreads();
   unsigned long long F = 0; unsigned E = 0, oorf = 0;
   const long long ngroups = (n + 7) / 8;
   for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += (long long)gridDim.x * blockDim.x) {
     long long i = gi * 8;
-    unsigned char c[8]; int sv[8];
+    unsigned cm;                                         // bit 8k = record k passes the insert predicate
+    int sv[8];
     if (i + 7 < n) {
       uint2 c8 = *reinterpret_cast<const uint2 *>(cls + i);
-      memcpy(c, &c8, 8);
+      cm = (c8.x & 0x01010101u) | ((c8.y & 0x01010101u) << 1);     // records 0-3 at bits 0,8,16,24; records 4-7 at bits 1,9,17,25
       if (NARROW) {
         uint4 h8 = *reinterpret_cast<const uint4 *>(isize16 + i);
-        short hs[8]; memcpy(hs, &h8, 16);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sv[k] = hs[k];
+        sv[0] = (int)(short)(h8.x & 0xffffu); sv[1] = (int)h8.x >> 16; sv[2] = (int)(short)(h8.y & 0xffffu); sv[3] = (int)h8.y >> 16;
+        sv[4] = (int)(short)(h8.z & 0xffffu); sv[5] = (int)h8.z >> 16; sv[6] = (int)(short)(h8.w & 0xffffu); sv[7] = (int)h8.w >> 16;
       } else {
         int4 a4 = *reinterpret_cast<const int4 *>(isize + i), b4 = *reinterpret_cast<const int4 *>(isize + i + 4);
         sv[0] = a4.x; sv[1] = a4.y; sv[2] = a4.z; sv[3] = a4.w; sv[4] = b4.x; sv[5] = b4.y; sv[6] = b4.z; sv[7] = b4.w;
       }
     } else {
-      for (int k = 0; k < 8; ++k) { c[k] = (i + k < n) ? cls[i + k] : 0; sv[k] = (i + k < n) ? (NARROW ? (int)isize16[i + k] : isize[i + k]) : 0; }
+      cm = 0;
+      for (int k = 0; k < 8; ++k) {
+        bool on = i + k < n && (cls[i + k] & CL_INSERT);
+        sv[k] = (i + k < n) ? (NARROW ? (int)isize16[i + k] : isize[i + k]) : 0;
+        if (on) cm |= k < 4 ? (1u << (8 * k)) : (2u << (8 * (k - 4)));
+      }
     }
+    unsigned part = 0;                                   // eight table entries < 2^28 each
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (!(c[k] & CL_INSERT)) continue;
+      const unsigned bit = k < 4 ? (1u << (8 * k)) : (2u << (8 * (k - 4)));
       unsigned x = (unsigned)(sv[k] < 0 ? -sv[k] : sv[k]);
-      unsigned w = x - xlo;
-      uint32_t t = w < (unsigned)SDF_WIN ? tab[w] : 0xffffffffu;
-      if (t != 0xffffffffu) F += t;
+      unsigned w = min(x - xlo, (unsigned)SDF_WIN);     // x < xlo wraps to a huge value: the window-miss entry
+      uint32_t t = tab[(cm & bit) ? w : (unsigned)(SDF_WIN + 1)];
+      if (t != 0xffffffffu) part += t;
       else {
         bool rare, oor;
         F += sd_fast_eval(x, mean, thr, rare, oor);
         E += rare ? 1u : 0u; oorf |= oor ? 1u : 0u;
       }
     }
+    F += part;
   }
   F = bk::warp_sum(F); E = bk::warp_sum(E); oorf = bk::warp_sum(oorf);
   if ((threadIdx.x & 31) == 0) {
@@ -680,11 +703,11 @@ __device__ __forceinline__ long long x_slot_of(const uint32_t *__restrict__ x_re
 // class bytes of all records, no search.  kx_count: candidates per 1024-entry tile (and the table's sanity: strictly
 // ascending record indices inside the batch); kx_write: ordered compaction into bkid_cand rows + the join's sort keys.
 constexpr int KX_THREADS = 256;
-constexpr int KX_ITEMS = 4;
+constexpr int KX_ITEMS = 2;
 constexpr int KX_TILE = KX_THREADS * KX_ITEMS;
 
-__global__ void __launch_bounds__(KX_THREADS) kx_count(const uint32_t *__restrict__ x_rec, long long n_x, const uint8_t *__restrict__ cls, long long n,
-                                                       uint32_t *__restrict__ tile_cnt, uint8_t *__restrict__ is_cand /* [n_x / KX_ITEMS]: 4 flag bits per thread */, int *__restrict__ bad)
+__global__ void __launch_bounds__(KX_THREADS) kx_count(const uint32_t *__restrict__ x_rec, long long n_x, const uint8_t *__restrict__ cand_bits, long long n,
+                                                       uint32_t *__restrict__ tile_cnt, uint8_t *__restrict__ is_cand /* [n_x / KX_ITEMS]: KX_ITEMS flag bits per thread */, int *__restrict__ bad)
 {
   __shared__ unsigned sh32[33];
   long long j0 = (long long)blockIdx.x * KX_TILE + threadIdx.x * KX_ITEMS;
@@ -694,7 +717,8 @@ __global__ void __launch_bounds__(KX_THREADS) kx_count(const uint32_t *__restric
 #pragma unroll
   for (int k = 0; k < KX_ITEMS; ++k) r[k] = j0 + k < n_x ? x_rec[j0 + k] : 0xffffffffu;
 #pragma unroll
-  for (int k = 0; k < KX_ITEMS; ++k) c[k] = (j0 + k < n_x && (long long)r[k] < n) ? cls[r[k]] : 0;      // independent loads: issued together
+  for (int k = 0; k < KX_ITEMS; ++k)      // independent loads, issued together; neighbouring entries share bitmap sectors (1 bit per record)
+    c[k] = (j0 + k < n_x && (long long)r[k] < n) ? (unsigned char)(((cand_bits[r[k] >> 3] >> (r[k] & 7u)) & 1u) ? CL_CAND : 0) : 0;
 #pragma unroll
   for (int k = 0; k < KX_ITEMS; ++k) {
     long long j = j0 + k;
@@ -717,11 +741,12 @@ __global__ void __launch_bounds__(KX_THREADS) kx_write(const uint32_t *__restric
 {
   __shared__ unsigned sh32[33];
   long long j0 = (long long)blockIdx.x * KX_TILE + threadIdx.x * KX_ITEMS;
+  __shared__ __align__(16) bkid_cand srow[KX_TILE];             // the tile's rows are assembled here and leave as one contiguous, coalesced range
   const unsigned bits = j0 < n_x ? (unsigned)is_cand[j0 / KX_ITEMS] : 0u;       // kx_count's verdict: the class bytes are not read again
   unsigned tot;
-  unsigned off = bk::block_excl_scan<unsigned>(__popc(bits), sh32, tot) + tile_off[blockIdx.x];
-  if (!bits) return;
-  // gather the four dense fields of all candidates of this thread first (independent loads), then write the rows
+  unsigned loc = bk::block_excl_scan<unsigned>(__popc(bits), sh32, tot);
+  const unsigned tile0 = tile_off[blockIdx.x];
+  // gather the four dense fields of this thread's candidates first (independent loads), then assemble the rows
   uint32_t i4[KX_ITEMS]; int32_t t4[KX_ITEMS], p4[KX_ITEMS]; uint16_t f4[KX_ITEMS]; uint8_t m4[KX_ITEMS];
 #pragma unroll
   for (int k = 0; k < KX_ITEMS; ++k) i4[k] = (bits >> k) & 1u ? x_rec[j0 + k] : 0u;
@@ -738,10 +763,14 @@ __global__ void __launch_bounds__(KX_THREADS) kx_write(const uint32_t *__restric
       c.gidx = index_offset + i4[k];
       c.flag = f4[k]; c.mapq = m4[k];
       c._pad[0] = c._pad[1] = c._pad[2] = c._pad[3] = c._pad[4] = 0;
-      out[off] = c;
-      if (keys) { keys[off] = c.name_lo; vals[off] = off; }
-      ++off;
+      srow[loc++] = c;
     }
+  __syncthreads();
+  const uint4 *sv = reinterpret_cast<const uint4 *>(srow);
+  uint4 *ov = reinterpret_cast<uint4 *>(out + tile0);
+  for (unsigned i = threadIdx.x; i < tot * 3u; i += KX_THREADS) ov[i] = sv[i];
+  if (keys)
+    for (unsigned i = threadIdx.x; i < tot; i += KX_THREADS) { keys[tile0 + i] = srow[i].name_lo; vals[tile0 + i] = tile0 + i; }
 }
 
 __global__ void k2_cand_keys(const bkid_cand *__restrict__ cand, long long nc, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
@@ -1234,5 +1263,6 @@ __global__ void pair_xy(const bkid_pair *__restrict__ pairs, long long np, uint3
 #include "bkid_refine.cuh"
 #include "bkid_align.cuh"
 #include "bkid_api.cuh"
+#include "bkid_dist.cuh"
 #include "bkid_bamdec.cuh"
 #include "bkid_align_api.cuh"

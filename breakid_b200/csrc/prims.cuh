@@ -5,6 +5,7 @@
 // Everything is HBM-bound integer work: 128-bit loads where alignment allows, grids sized from the
 // SM count, no tensor cores.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -158,6 +159,9 @@ static inline size_t scan_tmp_elems(long long n) { return (size_t)div_up(n > 0 ?
 // 40 launches (histogram + 3-kernel scan + uncoalesced scatter per pass) of the round-1 LSD sort.
 // The element count may live on the device (n_dev): grids are sized from a host upper bound, late tiles exit.
 // Elements per sort < 2^30 (tile status words carry 30-bit counts); everything sorted here is candidate-sized.
+// Measured and not kept (round 2, B200, 44 passes of the resident step = 0.88 ms with the look-back below): a
+// warp-cooperative 32-tile window per digit (2.1 ms: 32 serial digits per warp cost every small sort eight round trips)
+// and an 8-tile window per thread (2.3 ms: the spinning first wave re-reads eight status words per thread and starves L2).
 // ---------------------------------------------------------------------------------------------
 constexpr int OS_THREADS = 256;
 constexpr int OS_WARPS = OS_THREADS / 32;
@@ -298,10 +302,12 @@ static inline int radix_sort_pairs(uint64_t *keys, uint32_t *vals, long long n, 
 {
   if (n <= 1 || hi_bit <= lo_bit) return 0;
   if (n >= (1ll << 30)) return -1;
-  static bool attr_set = false;                       // per process; the attribute is per device function (set again per device below)
-  static int attr_dev = -1;
+  static std::atomic<unsigned long long> attr_done{0};   // one bit per device: the attribute belongs to the device's copy of the function
   int dev = 0; cudaGetDevice(&dev);
-  if (!attr_set || attr_dev != dev) { cudaFuncSetAttribute(os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OS_SMEM); attr_set = true; attr_dev = dev; }
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1)) {   // ranks-as-threads call this concurrently, one device each
+    cudaFuncSetAttribute(os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OS_SMEM);
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
   int npass = (hi_bit - lo_bit + 7) / 8;
   if (npass > OS_MAX_PASSES) npass = OS_MAX_PASSES;
   int ntiles = div_up(n, OS_TILE);

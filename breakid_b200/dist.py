@@ -176,6 +176,45 @@ class GpuEngine:
         return torch.from_numpy(out[:nb.value].copy()).to(self.device)
 
 
+class LibraryDist:
+    """The sharded path with the exchanges INSIDE the library (``bkid_dist_run``, breakid_b200/csrc/bkid_dist.cuh): NCCL calls
+    issued by the C++ code on the context's stream.  torch.distributed is used exactly once, to hand rank 0's NCCL unique id
+    to the other ranks."""
+
+    def __init__(self, ctx: api.Context, device: torch.device):
+        self.ctx, self.lib = ctx, ctx.lib
+        W, r = _world(), _rank()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if r == 0:
+            buf = (C.c_uint8 * 128)()
+            if self.lib.bkid_comm_nccl_unique_id(buf):
+                raise api.BkidError("bkid_comm_nccl_unique_id: " + (self.lib.bkid_last_error(None) or b"").decode())
+            ident = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        if W > 1:
+            t = ident.to(device)
+            dist.broadcast(t, src=0)
+            ident = t.cpu()
+        raw = (C.c_uint8 * 128)(*ident.tolist())
+        self.comm = self.lib.bkid_comm_nccl_init(raw, r, W, device.index if device.index is not None else 0)
+        if not self.comm:
+            raise api.BkidError("bkid_comm_nccl_init: " + (self.lib.bkid_last_error(None) or b"").decode())
+
+    def run(self, mode: int = 0):
+        """collective; returns (mean, sd, dist, n_called, stage_ms[9])"""
+        m, s, d, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        tm = (C.c_float * 9)()
+        self.ctx._chk(self.lib.bkid_dist_run(self.ctx.ctx, self.comm, mode, C.byref(m), C.byref(s), C.byref(d), C.byref(n), tm))
+        return m.value, s.value, d.value, n.value, list(tm)
+
+    def close(self):
+        if self.comm:
+            self.lib.bkid_comm_destroy(self.comm)
+            self.comm = None
+
+
+DIST_STAGES = ("insert statistics", "candidates", "a2a candidates", "join", "a2a pairs", "mask + cluster", "gathers", "refine", "total")
+
+
 # ---------------------------------------------------------------------------------------------------
 def _world():
     return dist.get_world_size() if dist.is_initialized() else 1

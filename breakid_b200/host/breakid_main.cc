@@ -7,7 +7,11 @@
 //   * the option table is terminated, so unknown flags report an error instead of segfaulting, and
 //     -t takes its argument (the reference declares has_arg=0 and then reads optarg);
 //   * -s <k>   sd multiplier of the distance formula (the literal 3 at src/BreakID.cc:103);
-//   * -r <refGene.txt> (default: $BREAKID_INSTALLDIR/ref_files/refGene.txt), -threads, -gpu.
+//   * -r <refGene.txt> (default: $BREAKID_INSTALLDIR/ref_files/refGene.txt), -threads, -gpu;
+//   * -gpu 0,1,2,...  several GPUs of one box: one host thread and one context per device, every rank inflates and
+//     decodes its own BGZF block range of the BAM (genomic-bin sharding of the file itself), the exchanges between the
+//     ranks are NCCL calls inside the library (bkid_dist_run).  A device may be named more than once (-gpu 0,0,0): the
+//     ranks then share it and exchange through device copies -- that is how the path is tested on a one-GPU box.
 // Host work: BAM decode (bam_reader.cc), .nib loading, refGene annotation, the final unstable sort
 // by N_DRP and file writing.  Everything between decode and the cluster records runs on the GPU.
 #include <getopt.h>
@@ -21,7 +25,9 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/breakid_b200.h"
@@ -45,7 +51,7 @@ static const char *kHelp =
     "     \t -x         \t exclude regions (BED: chrom, start, end): records starting there are ignored [none]\n "
     "     \t -validate  \t split reads count only if their clipped bases align where the SA tag says (needs nib files) [off]\n "
     "     \t -threads   \t BAM decode threads [8]\n "
-    "     \t -gpu       \t CUDA device [0]\n ";
+    "     \t -gpu       \t CUDA device, or a comma separated list (one rank per entry, NCCL between them) [0]\n ";
 
 static const char *kFusion[] = {"Unknown", "Translocation", "Inversion", "Duplication", "Deletion"};
 
@@ -80,6 +86,71 @@ static void write_row(std::ofstream &o, const CallRow &r, const std::vector<std:
   o << c.p1_rpt << "\t" << c.p2_rpt << "\n";
 }
 
+// annotation, the final unstable sort by N_DRP and the four output files (reference src/BreakID.cc:492-567,1170-1263,175-191):
+// shared by the single-GPU and the multi-GPU path.  `extra` writes the <o>_b200_timings.txt body.
+template <typename Extra>
+static void finish_and_write(const std::string &inp, const std::string &out, const std::string &refgene, const std::vector<std::string> &names,
+                             const std::vector<bkid_cluster_rec> &cl, bool filter, int qual, double dist, bool reached_breakpoint_stage, double t_start,
+                             int64_t n_pairs, int64_t n_masked, int64_t n_clustered, int64_t n_clusters, double t_scan, double t_cluster, double t_bp, Extra extra)
+{
+  std::vector<Transcript> tx;
+  RefGeneIndex tx_index;
+  std::vector<CallRow> rows;
+  if (reached_breakpoint_stage) {
+    // the reference opens the index and refGene as soon as one bucket reaches the break-point stage
+    if (!exists(inp + ".bai") && !exists(inp.substr(0, inp.size() > 4 ? inp.size() - 4 : 0) + ".bai")) {
+      std::cerr << "Error: please index bam-file first:\t" << inp << std::endl;                     // src/BreakID.cc:412-416
+      exit(1);
+    }
+    if (!load_refgene(refgene, tx)) { std::cerr << "Error: cannot open \t" << refgene << std::endl; exit(1); }   // src/RefSeqTranscript.cc:205-209
+    tx_index.build(tx);
+    std::cout << "valid cluster count: " << cl.size() << std::endl;
+    for (const bkid_cluster_rec &c : cl) {
+      CallRow r;
+      r.c = c;
+      long p1 = (r.c.p1_exact_pos == (uint32_t)-1) ? (long)r.c.p1_mean_pos : (long)r.c.p1_exact_pos;   // src/BreakID.cc:518-534
+      long p2 = (r.c.p2_exact_pos == -1) ? (long)r.c.p2_mean_pos : (long)r.c.p2_exact_pos;
+      auto nm = [&](int t) { return t >= 0 && t < (int)names.size() ? names[t] : std::string("*"); };
+      r.a1 = annotate_side(tx, tx_index, nm(r.c.p1_tid), p1);
+      r.a2 = annotate_side(tx, tx_index, nm(r.c.p2_tid), p2);
+      rows.push_back(r);
+    }
+  }
+  // ---- write (src/BreakID.cc:1184-1263): unstable sort by N_DRP, same library sort on the same order ----
+  std::sort(rows.begin(), rows.end(), cmp_cluster);
+  std::ofstream o_all, o_f;
+  if (!filter) { o_all.open((out + "_fusion_all.txt").c_str()); write_header(o_all); }
+  o_f.open((out + "_fusion.txt").c_str());
+  write_header(o_f);
+  for (const CallRow &r : rows) {
+    bool cond_all = r.c.n_split_read > 0 && r.c.p1_exact_pos != (uint32_t)-1 && r.c.p2_exact_pos != -1;
+    bool cond_filter = cond_all && (!(r.a1.gene == "intergenic" && r.a2.gene == "intergenic") && r.a1.gene != r.a2.gene) && !r.c.is_rpt;
+    if (cond_filter) write_row(o_f, r, names);
+    if (!filter && cond_all) write_row(o_all, r, names);
+  }
+  if (!filter) o_all.close();
+  o_f.close();
+  {
+    std::ofstream p((out + "_params.txt").c_str());                                                 // src/BreakID.cc:1170-1182
+    p << "ENSPAN" << std::endl;
+    p << "inp_file\t" << inp << std::endl;
+    p << "out_file\t" << out << std::endl;
+    p << "qual\t" << (long)qual << std::endl;
+    p << "w\t" << dist << std::endl;
+    p << "build\t" << "hg19" << std::endl;
+  }
+  double t_total = now_s() - t_start;
+  std::cout << "the fusion process of file " << inp << "  costs time: " << t_total << " seconds" << std::endl;
+  {
+    std::ofstream p((out + "_performance.txt").c_str());                                            // src/BreakID.cc:175-191 (same columns, all filled)
+    p << "scan_dist\tdiscordant pairs\tremove isolated\tafter_cluster\troot cluster\tscanning time\tcluster time\tfind breakpoint time\ttotal time" << std::endl;
+    p << dist << "\t" << n_pairs << "\t" << n_masked << "\t" << n_clustered << "\t" << n_clusters << "\t" << t_scan << "\t" << t_cluster << "\t" << t_bp << "\t" << t_total
+      << std::endl;
+    std::ofstream j((out + "_b200_timings.txt").c_str());
+    extra(j);
+  }
+}
+
 int main(int argc, char *argv[])
 {
   double t_start = now_s();
@@ -88,6 +159,7 @@ int main(int argc, char *argv[])
       {"all", 0, 0, 7}, {"s", 1, 0, 8}, {"r", 1, 0, 9}, {"threads", 1, 0, 10}, {"gpu", 1, 0, 11}, {"x", 1, 0, 12}, {"validate", 0, 0, 13}, {0, 0, 0, 0}};
   std::string inp, out, nib_dir, refgene, exclude_bed;
   int qual = 20, times = 2, sd_mult = 3, threads = 8, gpu = 0;
+  std::vector<int> gpus;
   bool fast = false, filter = true, validate = false;
   int opt, li;
   optind = 0;
@@ -105,7 +177,12 @@ int main(int argc, char *argv[])
       case 8: sd_mult = (int)labs(atol(optarg)); break;
       case 9: refgene = optarg; break;
       case 10: threads = std::max(1, atoi(optarg)); break;
-      case 11: gpu = atoi(optarg); break;
+      case 11: {
+        gpus.clear();
+        for (const char *q = optarg; *q;) { gpus.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+        gpu = gpus.empty() ? 0 : gpus[0];
+        break;
+      }
       case 12: exclude_bed = optarg; break;
       case 13: validate = true; break;
       case '?':
@@ -152,13 +229,10 @@ int main(int argc, char *argv[])
   bkid_params prm;
   bkid_default_params(&prm);
   prm.qual = qual; prm.times = times; prm.fast = fast ? 1 : 0; prm.sd_mult = sd_mult; prm.validate_align = validate ? 1 : 0;
-  bkid_ctx *ctx = bkid_create(gpu, hdr, &prm);
-  if (!ctx) { std::cerr << "Error: " << bkid_last_error(nullptr) << std::endl; exit(1); }
-  auto die = [&](const char *what) { std::cerr << "Error: " << what << ": " << bkid_last_error(ctx) << std::endl; exit(1); };
+  std::vector<int32_t> xt, xb, xe;
   if (!exclude_bed.empty()) {                          // additive: -x regions.bed (chrom, 0-based start, end); not a reference flag
     std::ifstream bed(exclude_bed.c_str());
     if (!bed.is_open()) { std::cerr << "Error: cannot open exclude bed-file: " << exclude_bed << std::endl; exit(1); }
-    std::vector<int32_t> xt, xb, xe;
     std::string line;
     while (std::getline(bed, line)) {
       if (line.empty() || line[0] == '#' || !line.compare(0, 5, "track") || !line.compare(0, 7, "browser")) continue;
@@ -167,8 +241,77 @@ int main(int argc, char *argv[])
       for (int t = 0; t < hdr->n_targets; ++t)
         if (names[t] == chrom) { xt.push_back(t); xb.push_back((int32_t)b); xe.push_back((int32_t)e); break; }
     }
-    if (bkid_set_exclude(ctx, (int64_t)xt.size(), xt.data(), xb.data(), xe.data())) die("set_exclude");
   }
+  const int W = (int)std::max<size_t>(gpus.size(), 1);
+  if (W > 1) {
+    // ================= several GPUs: one rank per -gpu entry, sharded ingest, exchanges inside the library =================
+    if (host_decode) { std::cerr << "Error: -gpu with several devices needs the device decoder (unset BKID_HOST_DECODE)\n"; exit(1); }
+    std::vector<bkid_ctx *> ctxs(W, nullptr);
+    for (int r = 0; r < W; ++r) {
+      ctxs[r] = bkid_create(gpus[r], hdr, &prm);
+      if (!ctxs[r]) { std::cerr << "Error: " << bkid_last_error(nullptr) << std::endl; exit(1); }
+      if (!xt.empty() && bkid_set_exclude(ctxs[r], (int64_t)xt.size(), xt.data(), xb.data(), xe.data())) { std::cerr << "Error: set_exclude: " << bkid_last_error(ctxs[r]) << std::endl; exit(1); }
+    }
+    double t_push0 = now_s();
+    const int64_t nblk = bkid_host_bgzf_n_blocks(bgzf);
+    std::vector<int64_t> nrec(W, 0);
+    std::vector<uint64_t> first(W, 0), next(W, 0);
+    std::vector<int> rcs(W, 0);
+    {
+      std::vector<std::thread> th;
+      for (int r = 0; r < W; ++r)
+        th.emplace_back([&, r] {
+          rcs[r] = bkid_push_bgzf_range(ctxs[r], bkid_host_bgzf_data(bgzf), bkid_host_bgzf_size(bgzf), bkid_host_bgzf_blocks(bgzf), nblk, bkid_host_bgzf_first_record(bgzf),
+                                        nblk * r / W, nblk * (r + 1) / W, &nrec[r], &first[r], &next[r]);
+        });
+      for (auto &t : th) t.join();
+    }
+    for (int r = 0; r < W; ++r)
+      if (rcs[r]) { std::cerr << "Error: can not read bam-file: " << inp << " (" << bkid_last_error(ctxs[r]) << ")" << std::endl; exit(1); }
+    for (int r = 0; r + 1 < W; ++r)        // where one range landed is where the next one started: the union is exactly the file's record sequence
+      if (next[r] != first[r + 1]) { std::cerr << "Error: can not read bam-file: " << inp << " (the block ranges of ranks " << r << " and " << r + 1 << " do not stitch)" << std::endl; exit(1); }
+    double t_push = now_s() - t_push0;
+    // nib files are needed by the refinement of every rank (41-mers are replicated work)
+    for (int t = 0; t < hdr->n_targets; ++t) {
+      nib nb;
+      if (nb.open(nib_dir + "/hg19_" + names[t] + ".nib") == 0)
+        for (int r = 0; r < W; ++r)
+          if (bkid_set_nib(ctxs[r], t, nb.payload(), nb.size())) { std::cerr << "Error: set_nib: " << bkid_last_error(ctxs[r]) << std::endl; exit(1); }
+    }
+    std::vector<bkid_comm *> comms(W, nullptr);
+    const bool distinct = std::set<int>(gpus.begin(), gpus.end()).size() == (size_t)W;
+    if ((distinct ? bkid_comm_nccl_init_all(gpus.data(), W, comms.data()) : bkid_comm_local_create(W, comms.data())) != 0) {
+      std::cerr << "Error: cannot create the communicators: " << bkid_last_error(nullptr) << std::endl; exit(1);
+    }
+    std::vector<double> mean(W), sd(W), dist(W);
+    std::vector<int64_t> ncall(W);
+    double t_run0 = now_s();
+    std::cout << "Scanning discordant read pairs ...\n";
+    if (bkid_dist_run_threads(ctxs.data(), comms.data(), W, fast ? 1 : 0, mean.data(), sd.data(), dist.data(), ncall.data())) {
+      for (int r = 0; r < W; ++r) if (*bkid_last_error(ctxs[r])) std::cerr << "Error: rank " << r << ": " << bkid_last_error(ctxs[r]) << std::endl;
+      exit(1);
+    }
+    std::cout << "Scanning discordant read pairs done.\n";
+    double t_run = now_s() - t_run0;
+    std::cout << "the insert size mean: " << mean[0] << ", the insert size sd:" << sd[0] << " .\n";
+    std::cout << "cluster_dist = span_dist = mask_dist = scan_dist = " << dist[0] << " .\n";
+    std::vector<bkid_cluster_rec> cl((size_t)std::max<int64_t>(ncall[0], 1));
+    int64_t n = 0;
+    if (bkid_fetch_clusters(ctxs[0], cl.data(), (int64_t)cl.size(), &n)) { std::cerr << "Error: fetch_clusters: " << bkid_last_error(ctxs[0]) << std::endl; exit(1); }
+    cl.resize((size_t)n);
+    int64_t pairs = 0, masked = 0, clustered = 0, nclusters = 0, records = 0;
+    for (int r = 0; r < W; ++r) { bkid_timings t; bkid_get_timings(ctxs[r], &t); pairs += t.n_pairs; masked += t.n_masked; clustered += t.n_clustered; nclusters += t.n_clusters; records += nrec[r]; }
+    finish_and_write(inp, out, refgene, names, cl, filter, qual, dist[0], clustered > 0, t_start, pairs, masked, clustered, nclusters, t_run, 0.0, 0.0,
+                     [&](std::ofstream &j) { j << "decoder\tdevice\nranks\t" << W << "\ncommunicator\t" << (distinct ? "nccl" : "local") << "\nopen_s\t" << t_decode << "\npush_s\t" << t_push
+                                                << "\nrun_s\t" << t_run << "\nrecords\t" << records << "\n"; });
+    for (int r = 0; r < W; ++r) { bkid_comm_destroy(comms[r]); bkid_destroy(ctxs[r]); }
+    bkid_host_bgzf_close(bgzf);
+    return 0;
+  }
+  bkid_ctx *ctx = bkid_create(gpu, hdr, &prm);
+  if (!ctx) { std::cerr << "Error: " << bkid_last_error(nullptr) << std::endl; exit(1); }
+  auto die = [&](const char *what) { std::cerr << "Error: " << what << ": " << bkid_last_error(ctx) << std::endl; exit(1); };
+  if (!xt.empty() && bkid_set_exclude(ctx, (int64_t)xt.size(), xt.data(), xb.data(), xe.data())) die("set_exclude");
   double t_push0 = now_s();
   bkid_decode_stats dst;
   memset(&dst, 0, sizeof dst);
@@ -199,18 +342,13 @@ int main(int argc, char *argv[])
   double t_cluster = now_s() - t_cl0;
   bkid_timings tm;
   bkid_get_timings(ctx, &tm);
-  std::vector<Transcript> tx;
-  RefGeneIndex tx_index;
-  std::vector<CallRow> rows;
+  std::vector<bkid_cluster_rec> cl;
   double t_bp = 0;
   if (tm.n_clustered > 0) {
-    // the reference opens the index and refGene as soon as one bucket reaches the break-point stage
     if (!exists(inp + ".bai") && !exists(inp.substr(0, inp.size() > 4 ? inp.size() - 4 : 0) + ".bai")) {
       std::cerr << "Error: please index bam-file first:\t" << inp << std::endl;                     // src/BreakID.cc:412-416
       exit(1);
     }
-    if (!load_refgene(refgene, tx)) { std::cerr << "Error: cannot open \t" << refgene << std::endl; exit(1); }   // src/RefSeqTranscript.cc:205-209
-    tx_index.build(tx);
     for (int t = 0; t < hdr->n_targets; ++t) {
       nib nb;
       if (nb.open(nib_dir + "/hg19_" + names[t] + ".nib") == 0)                                     // src/util_bam.cc:83-86
@@ -219,58 +357,19 @@ int main(int argc, char *argv[])
     double t1 = now_s();
     if (bkid_refine(ctx, dist, &n_called)) die("refine");
     t_bp = now_s() - t1;
-    std::vector<bkid_cluster_rec> cl((size_t)std::max<int64_t>(n_called, 1));
+    cl.resize((size_t)std::max<int64_t>(n_called, 1));
     int64_t n = 0;
     if (bkid_fetch_clusters(ctx, cl.data(), (int64_t)cl.size(), &n)) die("fetch_clusters");
-    std::cout << "valid cluster count: " << n << std::endl;
-    for (int64_t i = 0; i < n; ++i) {
-      CallRow r;
-      r.c = cl[i];
-      long p1 = (r.c.p1_exact_pos == (uint32_t)-1) ? (long)r.c.p1_mean_pos : (long)r.c.p1_exact_pos;   // src/BreakID.cc:518-534
-      long p2 = (r.c.p2_exact_pos == -1) ? (long)r.c.p2_mean_pos : (long)r.c.p2_exact_pos;
-      auto nm = [&](int t) { return t >= 0 && t < (int)names.size() ? names[t] : std::string("*"); };
-      r.a1 = annotate_side(tx, tx_index, nm(r.c.p1_tid), p1);
-      r.a2 = annotate_side(tx, tx_index, nm(r.c.p2_tid), p2);
-      rows.push_back(r);
-    }
+    cl.resize((size_t)n);
   }
-  // ---- write (src/BreakID.cc:1184-1263): unstable sort by N_DRP, same library sort on the same order ----
-  std::sort(rows.begin(), rows.end(), cmp_cluster);
-  std::ofstream o_all, o_f;
-  if (!filter) { o_all.open((out + "_fusion_all.txt").c_str()); write_header(o_all); }
-  o_f.open((out + "_fusion.txt").c_str());
-  write_header(o_f);
-  for (const CallRow &r : rows) {
-    bool cond_all = r.c.n_split_read > 0 && r.c.p1_exact_pos != (uint32_t)-1 && r.c.p2_exact_pos != -1;
-    bool cond_filter = cond_all && (!(r.a1.gene == "intergenic" && r.a2.gene == "intergenic") && r.a1.gene != r.a2.gene) && !r.c.is_rpt;
-    if (cond_filter) write_row(o_f, r, names);
-    if (!filter && cond_all) write_row(o_all, r, names);
-  }
-  if (!filter) o_all.close();
-  o_f.close();
-  {
-    std::ofstream p((out + "_params.txt").c_str());                                                 // src/BreakID.cc:1170-1182
-    p << "ENSPAN" << std::endl;
-    p << "inp_file\t" << inp << std::endl;
-    p << "out_file\t" << out << std::endl;
-    p << "qual\t" << (long)qual << std::endl;
-    p << "w\t" << dist << std::endl;
-    p << "build\t" << "hg19" << std::endl;
-  }
-  double t_total = now_s() - t_start;
-  std::cout << "the fusion process of file " << inp << "  costs time: " << t_total << " seconds" << std::endl;
-  {
-    bkid_get_timings(ctx, &tm);
-    std::ofstream p((out + "_performance.txt").c_str());                                            // src/BreakID.cc:175-191 (same columns, all filled)
-    p << "scan_dist\tdiscordant pairs\tremove isolated\tafter_cluster\troot cluster\tscanning time\tcluster time\tfind breakpoint time\ttotal time" << std::endl;
-    p << dist << "\t" << n_pairs << "\t" << tm.n_masked << "\t" << tm.n_clustered << "\t" << n_clusters << "\t" << t_scan << "\t" << t_cluster << "\t" << t_bp << "\t" << t_total
-      << std::endl;
-    std::ofstream j((out + "_b200_timings.txt").c_str());
-    j << "decoder\t" << (host_decode ? "host" : "device") << "\nopen_s\t" << t_decode << "\npush_s\t" << t_push << "\ninflate_ms\t" << dst.inflate_ms << "\nboundaries_ms\t" << dst.boundaries_ms
-      << "\nextract_ms\t" << dst.extract_ms << "\ncompressed_bytes\t" << dst.compressed_bytes << "\nuncompressed_bytes\t" << dst.uncompressed_bytes << "\nrecords\t" << tm.n_records << "\nh2d_ms\t" << tm.h2d << "\nclassify_ms\t" << tm.classify << "\ninsert_stats_ms\t" << tm.insert_stats
-      << "\njoin_ms\t" << tm.join << "\nbucket_sort_ms\t" << tm.bucket_sort << "\nmask_ms\t" << tm.mask << "\ncluster_ms\t" << tm.cluster << "\nsummarize_ms\t" << tm.summarize
-      << "\nevidence_ms\t" << tm.evidence << "\nrefine_ms\t" << tm.refine << "\n";
-  }
+  bkid_get_timings(ctx, &tm);
+  finish_and_write(inp, out, refgene, names, cl, filter, qual, dist, tm.n_clustered > 0, t_start, n_pairs, tm.n_masked, tm.n_clustered, n_clusters, t_scan, t_cluster, t_bp,
+                   [&](std::ofstream &j) {
+                     j << "decoder\t" << (host_decode ? "host" : "device") << "\nopen_s\t" << t_decode << "\npush_s\t" << t_push << "\ninflate_ms\t" << dst.inflate_ms << "\nboundaries_ms\t" << dst.boundaries_ms
+                       << "\nextract_ms\t" << dst.extract_ms << "\ncompressed_bytes\t" << dst.compressed_bytes << "\nuncompressed_bytes\t" << dst.uncompressed_bytes << "\nrecords\t" << tm.n_records << "\nh2d_ms\t" << tm.h2d << "\nclassify_ms\t" << tm.classify << "\ninsert_stats_ms\t" << tm.insert_stats
+                       << "\njoin_ms\t" << tm.join << "\nbucket_sort_ms\t" << tm.bucket_sort << "\nmask_ms\t" << tm.mask << "\ncluster_ms\t" << tm.cluster << "\nsummarize_ms\t" << tm.summarize
+                       << "\nevidence_ms\t" << tm.evidence << "\nrefine_ms\t" << tm.refine << "\n";
+                   });
   bkid_destroy(ctx);
   if (bam) bkid_host_bam_free(bam);
   if (bgzf) bkid_host_bgzf_close(bgzf);

@@ -301,6 +301,30 @@ int bkid_device_copy(bkid_ctx *ctx, void *dst, const void *src, uint64_t bytes);
 /* dst[i] = src[idx[i]] for rows of row_bytes (multiple of 16) on the context's device: the send-side permutation of the all-to-all routing */
 int bkid_device_gather_rows(bkid_ctx *ctx, void *dst, const void *src, const int64_t *idx, int64_t n, int32_t row_bytes);
 
+/* ---- the sharded path with the exchanges inside the library ------------------------------------------------------------
+ * One rank per GPU; rank r holds the r-th genomic bin of the coordinate-sorted record stream (pushed with bkid_push_batch /
+ * bkid_push_bgzf_range as usual).  bkid_dist_run is COLLECTIVE: every rank calls it with its own context and communicator
+ * and gets the same calls (bkid_fetch_clusters), identical to a single-context run over the whole stream.  The exchanges
+ * (all-reduce of the insert sums, all-to-all of candidate records by name-hash owner and of pairs by bucket owner,
+ * all-gather of cluster summaries / evidence rows, all-reduce of coverage / depth counts) are NCCL calls on the context's
+ * stream: ncclAllReduce and grouped ncclSend / ncclRecv.  libnccl.so.2 is loaded on first use.
+ *   one rank per process:  rank 0 calls bkid_comm_nccl_unique_id and hands the 128 bytes to the others (any channel:
+ *                          MPI, torch.distributed, a file), then every rank calls bkid_comm_nccl_init;
+ *   one process, one host thread per GPU:  bkid_comm_nccl_init_all(devices, world, comms), then bkid_dist_run from the
+ *                          rank's own thread, or bkid_dist_run_threads which starts the threads itself;
+ *   bkid_comm_local_create: ranks as threads of one process whose contexts may share ONE device -- exchanges are device
+ *                          copies behind a barrier.  For tests on a one-GPU box; same code path otherwise. */
+typedef struct bkid_comm bkid_comm;
+int bkid_comm_nccl_unique_id(uint8_t *id128);
+bkid_comm *bkid_comm_nccl_init(const uint8_t *id128, int rank, int world, int device);
+int bkid_comm_nccl_init_all(const int *devices, int world, bkid_comm **out);
+int bkid_comm_local_create(int world, bkid_comm **out);
+void bkid_comm_destroy(bkid_comm *comm);
+/* stage_ms (optional, 9 floats): insert statistics, candidates, candidate all-to-all, join, pair all-to-all, mask + cluster,
+ * gathers, refinement, total -- host wall clock of this rank */
+int bkid_dist_run(bkid_ctx *ctx, bkid_comm *comm, int mode, double *mean, double *sd, double *dist, int64_t *n_called, float *stage_ms);
+int bkid_dist_run_threads(bkid_ctx **ctxs, bkid_comm **comms, int world, int mode, double *mean, double *sd, double *dist, int64_t *n_called);
+
 /* Stand-alone operator entry points (device work on caller host arrays) used by the parity tests:
  * util_cluster / std::sort replay / isolated-pair mask on one bucket. */
 int bkid_op_sort_perm(bkid_ctx *ctx, int64_t n, const uint32_t *key, uint32_t *perm);

@@ -20,7 +20,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     from breakid_b200 import api, synth
-    from breakid_b200.dist import GpuEngine, run_sharded
+    from breakid_b200.dist import GpuEngine, LibraryDist, run_sharded
     from test_multi_gloo import _slice
     import oracle_py as O
     ok = True
@@ -36,11 +36,22 @@ def main():
         for t, (p, l) in enumerate(nibs):
             ctx.set_nib(t, p, l)
         mean, sd, dd, out = run_sharded(GpuEngine(ctx, dev), part.n, mode=mode)
+        # the same through the library's own exchanges (NCCL calls from C++, bkid_dist_run): every rank checks its own copy
+        ctx2 = api.Context(hb.target_len, hb.target_names, device=local, fast=mode)
+        ctx2.push(part)
+        for t, (p, l) in enumerate(nibs):
+            ctx2.set_nib(t, p, l)
+        ld = LibraryDist(ctx2, dev)
+        lm, ls, ldd, ln, _ = ld.run(mode)
+        lout = ctx2.fetch_clusters()
+        m, s, d0, exp = O.run(hb, nibs, mode=mode)
+        lib_same = torch.tensor([1 if ((lm, ls, ldd) == (m, s, d0) and lout.tobytes() == exp.tobytes()) else 0], device=dev)
+        dist.all_reduce(lib_same, op=dist.ReduceOp.MIN)
+        ld.close(); ctx2.close()
         if rank == 0:
-            m, s, d0, exp = O.run(hb, nibs, mode=mode)
             same = (mean, sd, dd) == (m, s, d0) and out.tobytes() == exp.tobytes()
-            print("mode %d world %d: %d calls, identical to oracle: %s" % (mode, world, len(out), same), flush=True)
-            ok = ok and same and len(exp) >= 10
+            print("mode %d world %d: %d calls, identical to oracle: %s; library exchanges (NCCL in C++) identical on every rank: %s" % (mode, world, len(out), same, bool(int(lib_same[0]))), flush=True)
+            ok = ok and same and bool(int(lib_same[0])) and len(exp) >= 10
         ctx.close()
     # exclude intervals on every rank's context (BASELINE.json configs[2] shape: exclude-BED + genomic-bin sharding)
     from test_gpu_parity import _exclude_intervals, _prefilter
@@ -59,6 +70,19 @@ def main():
         print("exclude world %d: %d calls, identical to oracle on the pre-filtered input: %s" % (world, len(out), same), flush=True)
         ok = ok and same
     ctx.close()
+    # the full configs[2] shape through the library's exchanges: exclude intervals + -q 20 -s 15
+    ctx = api.Context(hb.target_len, hb.target_names, device=local, qual=20, sd_mult=15)
+    ctx.push(part)
+    ctx.set_exclude(iv[:, 0], iv[:, 1], iv[:, 2])
+    ld = LibraryDist(ctx, dev)
+    lm, ls, ldd, ln, _ = ld.run(0)
+    lout = ctx.fetch_clusters()
+    ld.close(); ctx.close()
+    if rank == 0:
+        m, s, d0, exp = O.run(_prefilter(hb, keep), None, qual=20, mode=0, sd_mult=15)
+        same = (lm, ls, ldd) == (m, s, d0) and lout.tobytes() == exp.tobytes()
+        print("exclude + -q 20 -s 15 world %d (library exchanges): %d calls, identical to oracle on the pre-filtered input: %s" % (world, len(lout), same), flush=True)
+        ok = ok and same
     # ingest sharded too: every rank inflates and decodes its own BGZF block range of one BAM file on its GPU
     import tempfile
     from breakid_b200 import bamio

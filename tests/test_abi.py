@@ -75,15 +75,15 @@ def test_driver_argument_errors():
     drv = os.path.join(ROOT, "breakid_b200", "host", "BreakID")
     if not os.path.exists(drv):
         pytest.skip("driver not built")
-    r = subprocess.run([drv], capture_output=True, text=True)
+    r = subprocess.run([drv], timeout=600, capture_output=True, text=True)
     assert r.returncode == 1 and "Error: input- and output file is required." in r.stderr
-    r = subprocess.run([drv, "-i", "a.bam", "-o", "x"], capture_output=True, text=True)
+    r = subprocess.run([drv, "-i", "a.bam", "-o", "x"], timeout=600, capture_output=True, text=True)
     assert r.returncode == 1 and "Error: nib file's root dir is required." in r.stderr
-    r = subprocess.run([drv, "-i", "/nonexistent.bam", "-o", "x", "-n", "."], capture_output=True, text=True)
+    r = subprocess.run([drv, "-i", "/nonexistent.bam", "-o", "x", "-n", "."], timeout=600, capture_output=True, text=True)
     assert r.returncode == 1 and "Error: can not open bam-file" in r.stderr
-    r = subprocess.run([drv, "-h"], capture_output=True, text=True)
+    r = subprocess.run([drv, "-h"], timeout=600, capture_output=True, text=True)
     assert r.returncode == 1 and "Usage" in r.stderr
-    r = subprocess.run([drv, "-bogus"], capture_output=True, text=True)       # the reference segfaults here
+    r = subprocess.run([drv, "-bogus"], timeout=600, capture_output=True, text=True)       # the reference segfaults here
     assert r.returncode == 1
 
 

@@ -170,7 +170,7 @@ def test_driver_validate_flag(tmp_path):
         open(paths["bam"] + ".bai", "wb").close()                     # the driver only checks that an index file exists
         for flags in ([], ["-validate"]):
             g = subprocess.run([drv, "-i", paths["bam"], "-o", str(wd / ("out" + "".join(flags))), "-n", paths["nib"], "-r", paths["refgene"], "-all"] + flags,
-                               capture_output=True, text=True)
+                               timeout=600, capture_output=True, text=True)
             assert g.returncode == 0, g.stderr[-500:]
             outs[(tag, bool(flags))] = open(str(wd / ("out" + "".join(flags))) + "_fusion_all.txt").read()
     nsr = lambda txt: sum(int(l.split("\t")[8]) for l in txt.splitlines()[1:])

@@ -253,7 +253,7 @@ def test_driver_call_files_match_reference_binary(tmp_path, mode):
     assert r.returncode == 0, r.stderr[-500:]
     drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breakid_b200", "host", "BreakID")
     g = subprocess.run([drv, "-i", paths["bam"], "-o", str(tmp_path / "gpu"), "-n", paths["nib"], "-r", paths["refgene"]] + flags,
-                       capture_output=True, text=True)
+                       timeout=600, capture_output=True, text=True)
     assert g.returncode == 0, g.stderr[-500:]
     for suffix in ("_fusion.txt", "_fusion_all.txt"):
         a = open(str(tmp_path / "ref") + suffix).read()
@@ -479,7 +479,7 @@ def test_driver_config4_tumour_fusions(tmp_path, flags):
     assert r.returncode == 0, r.stderr[-500:]
     drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breakid_b200", "host", "BreakID")
     g = subprocess.run([drv, "-i", paths["bam"], "-o", str(tmp_path / "gpu"), "-n", paths["nib"], "-r", paths["refgene"], "-all"] + flags,
-                       capture_output=True, text=True)
+                       timeout=600, capture_output=True, text=True)
     assert g.returncode == 0, g.stderr[-500:]
     for suffix in ("_fusion.txt", "_fusion_all.txt"):
         a = open(str(tmp_path / "ref") + suffix).read()
@@ -491,7 +491,7 @@ def test_driver_config4_tumour_fusions(tmp_path, flags):
     assert len(fused) >= 1                      # at least one gene-gene fusion survives the filter
     # host decoder A/B: same files
     g2 = subprocess.run([drv, "-i", paths["bam"], "-o", str(tmp_path / "gpu_host"), "-n", paths["nib"], "-r", paths["refgene"], "-all"] + flags,
-                        capture_output=True, text=True, env=dict(os.environ, BKID_HOST_DECODE="1"))
+                        timeout=600, capture_output=True, text=True, env=dict(os.environ, BKID_HOST_DECODE="1"))
     assert g2.returncode == 0
     assert open(str(tmp_path / "gpu_host") + "_fusion_all.txt").read() == open(str(tmp_path / "gpu") + "_fusion_all.txt").read()
 
@@ -597,7 +597,7 @@ def test_driver_exclude_bed_matches_reference_on_prefiltered_bam(tmp_path):
     assert r.returncode == 0, r.stderr[-500:]
     drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breakid_b200", "host", "BreakID")
     g = subprocess.run([drv, "-i", full["bam"], "-o", str(tmp_path / "gpu"), "-n", full["nib"], "-r", full["refgene"], "-all", "-x", str(tmp_path / "ex.bed")],
-                       capture_output=True, text=True)
+                       timeout=600, capture_output=True, text=True)
     assert g.returncode == 0, g.stderr[-500:]
     for suffix in ("_fusion.txt", "_fusion_all.txt"):
         assert open(str(tmp_path / "ref") + suffix).read() == open(str(tmp_path / "gpu") + suffix).read(), suffix
@@ -769,4 +769,48 @@ def test_sd_one_pass_form_detects_correctable_records():
     assert "isize16" in hb.narrow()
     c = _ctx_for(hb)
     assert c.insert_stats() == O.insert_stats(hb)[:2]
+    c.close()
+
+
+@pytest.mark.parametrize("flags,sd_mult", [(["-s", "15"], 15), (["-q", "20", "-s", "15"], 15), (["-s", "1", "-fast"], 1)])
+def test_driver_sd_multiplier_matches_patched_reference(tmp_path, flags, sd_mult):
+    """-s (extension: the literal 3 of `times * sqrt(times) * (mean + 3 * sd)`, src/BreakID.cc:103; BASELINE.json configs[2] is quoted
+    with `-q 20 -s 15`).  Oracle: the reference binary built with that ONE literal read from the environment (oracle/Makefile
+    ref_s) -- the reference itself crashes on an unknown flag."""
+    import os
+    import subprocess
+    import oracle_py as O
+    from breakid_b200 import bamio, synth
+    if not O.have_ref() or not os.path.exists(O.REF_BIN + "_s"):
+        pytest.skip("oracle/_ref/BreakID_ref_s not built (needs /root/reference at build time)")
+    cfg = synth.SynthConfig(chrom_lens=[300000, 200000, 150000], n_tra=3, n_inv=2, n_dup=2, n_del=2, seed=29, sv_jitter=1)
+    d = synth.generate(cfg)
+    paths = bamio.write_dataset(str(tmp_path), d, genes_per_mb=25.0)
+    O.ref_index(paths["bam"])
+    O.ref_install_refgene(paths["refgene"])
+    r = O.ref_run_binary(paths["bam"], str(tmp_path / "ref"), paths["nib"], fast="-fast" in flags, qual=20 if "-q" in flags else None, sd_mult=sd_mult)
+    assert r.returncode == 0, r.stderr[-500:]
+    r3 = O.ref_run_binary(paths["bam"], str(tmp_path / "ref3"), paths["nib"], fast="-fast" in flags, qual=20 if "-q" in flags else None)
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breakid_b200", "host", "BreakID")
+    g = subprocess.run([drv, "-i", paths["bam"], "-o", str(tmp_path / "gpu"), "-n", paths["nib"], "-r", paths["refgene"], "-all"] + flags, timeout=600, capture_output=True, text=True)
+    assert g.returncode == 0, g.stderr[-500:]
+    for suffix in ("_fusion.txt", "_fusion_all.txt"):
+        assert open(str(tmp_path / "ref") + suffix).read() == open(str(tmp_path / "gpu") + suffix).read(), suffix
+    pa = open(str(tmp_path / "ref") + "_params.txt").read().replace(str(tmp_path / "ref"), "X")
+    pb = open(str(tmp_path / "gpu") + "_params.txt").read().replace(str(tmp_path / "gpu"), "X")
+    assert pa == pb
+    assert pa != open(str(tmp_path / "ref3") + "_params.txt").read().replace(str(tmp_path / "ref3"), "X")     # the flag really changes w
+
+
+@pytest.mark.parametrize("sd_mult", [15, 1])
+def test_params_sd_mult_equals_oracle(small_data, sd_mult):
+    """bkid_params.sd_mult through the C ABI against the oracle with the same multiplier"""
+    import oracle_py as O
+    d, hb, nibs = small_data
+    c = _ctx_for(hb, sd_mult=sd_mult)
+    mean, sd, dist, ncall = c.run()
+    got = c.fetch_clusters()
+    om, osd, od, exp = O.run(hb, None, mode=0, sd_mult=sd_mult)
+    assert (mean, sd, dist) == (om, osd, od) and dist == O.dist(om, osd, sd_mult=sd_mult)
+    assert got.tobytes() == exp.tobytes()
     c.close()

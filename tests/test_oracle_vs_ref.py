@@ -200,3 +200,29 @@ def test_tumour_config4_shape_vs_reference_binary(tmp_path, mode, qual):
     cfg = synth.SynthConfig(chrom_lens=[260000, 220000, 180000, 140000], coverage=100.0, n_tra=10, n_inv=0, n_dup=0, n_del=0,
                             span_per_sv=40, split_per_sv=20, seed=44, sv_jitter=1)
     _binary_vs_oracle(cfg, tmp_path, mode=mode, qual=qual, genes_per_mb=30.0, min_calls=8)
+
+
+@pytest.mark.skipif(not O.have_ref() or not os.path.exists(O.REF_BIN + "_s"), reason="oracle/_ref/BreakID_ref_s not built")
+@pytest.mark.parametrize("sd_mult,mode,qual", [(15, 0, 20), (15, 1, None), (1, 0, None), (3, 0, None)])
+def test_sd_multiplier_oracle_vs_patched_reference(dataset, tmp_path, sd_mult, mode, qual):
+    """the oracle's sd multiplier (the -s extension) against the reference binary whose literal 3 (src/BreakID.cc:103) is read
+    from the environment -- with 3 that binary must reproduce the unmodified one"""
+    from breakid_b200 import synth
+    from test_golden import _format_calls
+    d, hb, paths = dataset
+    r = O.ref_run_binary(paths["bam"], str(tmp_path / "ref"), paths["nib"], fast=bool(mode), qual=qual, sd_mult=sd_mult)
+    assert r.returncode == 0, r.stderr[-300:]
+    nibs = [(synth.random_nib_bytes(l, d.cfg.seed * 1000 + t).numpy(), l) for t, l in enumerate(d.cfg.chrom_lens)]
+    _, _, dist, cl = O.run(hb, nibs, mode=mode, sd_mult=sd_mult, **({"qual": qual} if qual is not None else {}))
+    exp = set()
+    for ln in open(str(tmp_path / "ref") + "_fusion_all.txt").read().splitlines()[1:]:
+        f = ln.split("\t")
+        exp.add((f[0], f[1], f[2], f[7], f[8], f[9], f[10], f[11], f[12], f[13], f[14]))
+    assert _format_calls(cl, hb.target_names) == exp
+    w_line = [l for l in open(str(tmp_path / "ref") + "_params.txt").read().splitlines() if l.startswith("w\t")][0]
+    assert w_line == "w\t%g" % dist
+    if sd_mult == 3:
+        r0 = O.ref_run_binary(paths["bam"], str(tmp_path / "ref0"), paths["nib"], fast=bool(mode), qual=qual)
+        assert r0.returncode == 0
+        for suffix in ("_fusion.txt", "_fusion_all.txt"):
+            assert open(str(tmp_path / "ref") + suffix).read() == open(str(tmp_path / "ref0") + suffix).read()
