@@ -394,8 +394,8 @@ static int dist_run_impl(bkid_ctx *c, bkid_comm *cm, int mode, double *mean_o, d
   if (W > RT_MAXW) return fail(c, BKID_ERR_ARG, "more than 32 ranks");
   // ---- insert statistics ----
   TRY(c, classify_impl(c));
-  TRY(c, c->tmpG.ensure(4096, 0, st));
-  unsigned long long *dv = c->tmpG.as<unsigned long long>();
+  TRY(c, c->dist_scalars.ensure(4096, 0, st));
+  unsigned long long *dv = c->dist_scalars.as<unsigned long long>();
   unsigned long long hv[4] = {(unsigned long long)c->sum_abs, (unsigned long long)c->cnt_insert, c->sum_sq, (unsigned long long)c->n};
   CU(c, cudaMemcpyAsync(dv, hv, 32, cudaMemcpyHostToDevice, st));
   if (cm->allreduce(dv, 3, BK_U64, BK_SUM, st)) return fail(c, BKID_ERR_CUDA, "all-reduce failed: " + cm->err);

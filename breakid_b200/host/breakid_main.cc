@@ -51,7 +51,7 @@ static const char *kHelp =
     "     \t -x         \t exclude regions (BED: chrom, start, end): records starting there are ignored [none]\n "
     "     \t -validate  \t split reads count only if their clipped bases align where the SA tag says (needs nib files) [off]\n "
     "     \t -threads   \t BAM decode threads [8]\n "
-    "     \t -gpu       \t CUDA device, or a comma separated list (one rank per entry, NCCL between them) [0]\n ";
+    "     \t -gpu       \t CUDA device, or a list / range such as 0,1 or 0-7 (one rank per entry, NCCL between them) [0]\n ";
 
 static const char *kFusion[] = {"Unknown", "Translocation", "Inversion", "Duplication", "Deletion"};
 
@@ -179,7 +179,14 @@ int main(int argc, char *argv[])
       case 10: threads = std::max(1, atoi(optarg)); break;
       case 11: {
         gpus.clear();
-        for (const char *q = optarg; *q;) { gpus.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+        for (const char *q = optarg; *q;) {                 // "3", "0,1,2" or "0-7" (ranges and lists mix: "0-3,6")
+          int a = atoi(q), b = a;
+          while (*q && *q != ',' && *q != '-') ++q;
+          if (*q == '-') { b = atoi(++q); while (*q && *q != ',') ++q; }
+          if (b < a || b - a > 63) { std::cerr << "Error: bad -gpu range\n"; exit(1); }
+          for (int g = a; g <= b; ++g) gpus.push_back(g);
+          if (*q == ',') ++q;
+        }
         gpu = gpus.empty() ? 0 : gpus[0];
         break;
       }
