@@ -1298,6 +1298,37 @@ int bkid_scan(bkid_ctx *c, double w, int64_t *n_pairs)
   return 0;
 }
 
+// K6: one summary record per cluster of the member list (c->mem_pair / mem_bucket / mem_cluster index c->pairs0, grouped by
+// (bucket, cluster id)); clusters whose mean positions are closer than 2*dist on one chromosome are dropped (src/BreakID.cc:300-350)
+static int summarize_impl(bkid_ctx *c, double dist)
+{
+  cudaStream_t st = c->st;
+  if (c->n2 > 0) {
+    long long nm = c->n2;
+    TRY(c, c->sc.ensure(nm + 8, st));
+    uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *start = c->sc.c32.as<uint32_t>(), *keep = c->sc.d32.as<uint32_t>(), *koff = c->sc.e32.as<uint32_t>();
+    unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
+    BK_LAUNCH(k6_cluster_heads, GRID1(nm, 256), 256, 0, st, c->mem_bucket.as<uint32_t>(), c->mem_cluster.as<int32_t>(), nm, head);
+    bk::exclusive_scan<uint32_t, uint32_t>(head, hex, nm, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    unsigned long long ncl = 0;
+    CU(c, cudaMemcpyAsync(&ncl, tot, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    BK_LAUNCH(k6_cluster_starts, GRID1(nm, 256), 256, 0, st, head, hex, nm, start);
+    TRY(c, c->clusters.ensure((size_t)(ncl + 1) * sizeof(bkid_cluster_rec), 0, st));
+    TRY(c, c->clusters_out.ensure((size_t)(ncl + 1) * sizeof(bkid_cluster_rec), 0, st));
+    BK_LAUNCH(k6_summarize, GRID1(ncl, 128), 128, 0, st, c->pairs0.as<bkid_pair>(), c->mem_pair.as<uint32_t>(), c->mem_cluster.as<int32_t>(), start, (uint32_t)ncl, nm, dist,
+              c->clusters_out.as<bkid_cluster_rec>(), keep);
+    bk::exclusive_scan<uint32_t, uint32_t>(keep, koff, (long long)ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
+    unsigned long long nk = 0;
+    CU(c, cudaMemcpyAsync(&nk, tot, 8, cudaMemcpyDeviceToHost, st));
+    TRY(c, sync_check(c));
+    BK_LAUNCH(compact_clusters, GRID1(ncl, 128), 128, 0, st, c->clusters_out.as<bkid_cluster_rec>(), keep, koff, (uint32_t)ncl, c->clusters.as<bkid_cluster_rec>());
+    c->n_clusters = (long long)nk;
+    c->tm.n_clustered = nm;
+  }
+  return 0;
+}
+
 int bkid_cluster(bkid_ctx *c, double dist, int mode, int64_t *n_clusters)
 {
   if (!c) return BKID_ERR_ARG;
@@ -1323,30 +1354,7 @@ int bkid_cluster(bkid_ctx *c, double dist, int mode, int64_t *n_clusters)
     else TRY(c, cluster_ahc(c, c->cur1.as<uint32_t>(), c->curb1.as<uint32_t>(), c->seg1.as<uint32_t>(), c->n1, c->nb, c->X.as<uint32_t>(), c->Y.as<uint32_t>(), dist));
   }
   cudaEventRecord(c->ev[11], st);
-  // K6 summary
-  if (c->n2 > 0) {
-    long long nm = c->n2;
-    TRY(c, c->sc.ensure(nm + 8, st));
-    uint32_t *head = c->sc.a32.as<uint32_t>(), *hex = c->sc.b32.as<uint32_t>(), *start = c->sc.c32.as<uint32_t>(), *keep = c->sc.d32.as<uint32_t>(), *koff = c->sc.e32.as<uint32_t>();
-    unsigned long long *tot = (unsigned long long *)(c->counters.as<unsigned>() + CS_TOTAL);
-    BK_LAUNCH(k6_cluster_heads, GRID1(nm, 256), 256, 0, st, c->mem_bucket.as<uint32_t>(), c->mem_cluster.as<int32_t>(), nm, head);
-    bk::exclusive_scan<uint32_t, uint32_t>(head, hex, nm, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-    unsigned long long ncl = 0;
-    CU(c, cudaMemcpyAsync(&ncl, tot, 8, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-    BK_LAUNCH(k6_cluster_starts, GRID1(nm, 256), 256, 0, st, head, hex, nm, start);
-    TRY(c, c->clusters.ensure((size_t)(ncl + 1) * sizeof(bkid_cluster_rec), 0, st));
-    TRY(c, c->clusters_out.ensure((size_t)(ncl + 1) * sizeof(bkid_cluster_rec), 0, st));
-    BK_LAUNCH(k6_summarize, GRID1(ncl, 128), 128, 0, st, c->pairs0.as<bkid_pair>(), c->mem_pair.as<uint32_t>(), c->mem_cluster.as<int32_t>(), start, (uint32_t)ncl, nm, dist,
-              c->clusters_out.as<bkid_cluster_rec>(), keep);
-    bk::exclusive_scan<uint32_t, uint32_t>(keep, koff, (long long)ncl, c->sc.scan_tmp.as<unsigned long long>(), tot, st);
-    unsigned long long nk = 0;
-    CU(c, cudaMemcpyAsync(&nk, tot, 8, cudaMemcpyDeviceToHost, st));
-    TRY(c, sync_check(c));
-    BK_LAUNCH(compact_clusters, GRID1(ncl, 128), 128, 0, st, c->clusters_out.as<bkid_cluster_rec>(), keep, koff, (uint32_t)ncl, c->clusters.as<bkid_cluster_rec>());
-    c->n_clusters = (long long)nk;
-    c->tm.n_clustered = nm;
-  }
+  TRY(c, summarize_impl(c, dist));
   cudaEventRecord(c->ev[12], st);
   TRY(c, sync_check(c));
   float ms = 0;
@@ -2021,6 +2029,54 @@ int bkid_op_cluster(bkid_ctx *c, int mode, int64_t n, const uint32_t *p1, const 
   }
   for (DBuf *b : {&x, &y, &cur, &curb, &seg}) b->release();
   return rc;
+}
+
+
+// K6 on a caller-built member list: pairs of ONE chr-pair bucket with their cluster ids (grouped by cluster id, as after the
+// reference's sort by cmp_enspan_id, src/BreakID.cc:141).  Leaves the summaries in the context as bkid_cluster does, so
+// bkid_refine / bkid_fetch_clusters follow.  The records' `bucket` is the pairs' own.
+int bkid_op_summarize(bkid_ctx *c, int64_t n, const bkid_pair *pairs, double dist, int64_t *n_clusters)
+{
+  if (!c || n < 0 || (n > 0 && !pairs)) return BKID_ERR_ARG;
+  cudaSetDevice(c->device);
+  c->err.clear();
+  cudaStream_t st = c->st;
+  size_t m = (size_t)std::max<int64_t>(n, 1);
+  TRY(c, c->pairs0.ensure(m * sizeof(bkid_pair), 0, st));
+  TRY(c, c->mem_pair.ensure(m * 4 + 16, 0, st)); TRY(c, c->mem_bucket.ensure(m * 4 + 16, 0, st)); TRY(c, c->mem_cluster.ensure(m * 4 + 16, 0, st));
+  TRY(c, c->counters.ensure(1024, 0, st));
+  std::vector<int32_t> cl((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    cl[(size_t)i] = pairs[i].cluster;
+    if (i > 0 && pairs[i].cluster < pairs[i - 1].cluster) return fail(c, BKID_ERR_ARG, "bkid_op_summarize: pairs are not grouped by ascending cluster id");
+  }
+  c->n2 = n; c->n_clusters = 0;
+  if (n > 0) {
+    CU(c, cudaMemcpyAsync(c->pairs0.p, pairs, (size_t)n * sizeof(bkid_pair), cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(c->mem_cluster.p, cl.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemsetAsync(c->mem_bucket.p, 0, (size_t)n * 4, st));
+    BK_LAUNCH(iota_u32, GRID1(n, 256), 256, 0, st, c->mem_pair.as<uint32_t>(), (long long)n);
+    TRY(c, sync_check(c));                                   // `cl` and the caller's pairs are pageable: copies done before return
+  }
+  TRY(c, summarize_impl(c, dist));
+  TRY(c, sync_check(c));
+  c->clustered = true; c->clusters_ranked = true; c->refined = false;
+  c->tm.n_clusters = c->n_clusters;
+  if (n_clusters) *n_clusters = c->n_clusters;
+  return 0;
+}
+
+// thresholds of the NEXT stage calls (qual, times, min_reads, bp_pos_error, mismatch_num, sd_mult, validate_align, fast);
+// pairs and clusters derived from the old ones are dropped (and the classification, if qual changed); the records stay
+int bkid_set_params(bkid_ctx *c, const bkid_params *p)
+{
+  if (!c || !p) return BKID_ERR_ARG;
+  if (p->times < 1 || p->min_reads < 1 || p->qual < 0) return fail(c, BKID_ERR_ARG, "bad parameters");
+  cudaSetDevice(c->device);
+  if (p->qual != c->prm.qual) invalidate(c);               // the class bytes depend on the MAPQ threshold
+  else c->scanned = c->clustered = c->refined = false;
+  c->prm = *p;
+  return 0;
 }
 
 }  // extern "C"

@@ -333,6 +333,16 @@ int bkid_op_remove_isolated(bkid_ctx *ctx, int64_t n, const uint32_t *p1, const 
 int bkid_op_cluster(bkid_ctx *ctx, int mode, int64_t n, const uint32_t *p1, const uint32_t *p2, double thr,
                     uint32_t *out_idx, int32_t *out_cluster, int64_t *n_out, int32_t *n_roots);
 
+/* K6 + the per-bucket call of src/BreakID.cc:146 (findClusterBreakPointInfoSaTag) for a caller that drives the stages
+ * bucket by bucket like the reference's main(): `pairs` = the pairs of ONE chr-pair bucket with their cluster ids, grouped
+ * by ascending cluster id (src/BreakID.cc:141 sorts by cmp_enspan_id).  Leaves the cluster summaries in the context exactly
+ * as bkid_cluster does; bkid_refine + bkid_fetch_clusters then return the bucket's cluster_info records.  Used by
+ * include/compat/BreakID_stages.h. */
+int bkid_op_summarize(bkid_ctx *ctx, int64_t n, const bkid_pair *pairs, double dist, int64_t *n_clusters);
+/* Replace the thresholds used by the next stage calls (the context keeps its records).  src/BreakID.cc passes qual / w /
+ * min_reads to every stage function separately; the stage-wise compat layer forwards them through this call. */
+int bkid_set_params(bkid_ctx *ctx, const bkid_params *params);
+
 /* Extension (BASELINE.json north_star kernel 4; the reference has no sequence alignment): banded
  * unit-cost edit distance of n query strings (e.g. the soft-clipped part of a split read) against their own reference
  * windows, ASCII bases, 'N' never matches.  q / r are the concatenated strings, q_off / r_off their [n+1] offsets,
