@@ -107,6 +107,7 @@ struct bkid_ctx {
   Scratch sc;
   DBuf tmpA, tmpB, tmpC, tmpD, tmpE, tmpF, tmpG, tmpH;
   DBuf dist_send, dist_recv, dist_rows;     // multi-GPU exchanges (bkid_dist.cuh)
+  DBuf sortbig;                             // big-segment lists / tile status of the std::sort replay (exact_sort_segments)
   DBuf dist_scalars;                        // all-reduce operands of one bkid_dist_run: never shared with a stage's scratch (those are re-sized under it)
   bkid_timings tm;
   cudaEvent_t ev[16];
@@ -168,19 +169,44 @@ static int exact_sort_segments(bkid_ctx *c, uint32_t *key, uint32_t *val, const 
   Seg *term = c->tmpC.as<Seg>();
   TRY(c, c->tmpH.ensure(seg_bytes, 0, st));
   Seg *small = c->tmpH.as<Seg>();
-  BK_LAUNCH(is_init_roots, GRID1(nseg, 256), 256, 0, st, seg_off, nseg, act[0], cnt + 0, small, cnt + 3, term, cnt + 2);
+  // big segments (> IS_BIG elements, several CTAs each): two lists, their packed sizes (count << 32 | tiles), two tickets, tile status words
+  const bool big_possible = n > (long long)IS_BIG;
+  const size_t maxbig = (size_t)(n / IS_BIG) + 2, maxtiles = (size_t)(n / IS_BTILE) + maxbig + 2;
+  BigSeg *big[2] = {nullptr, nullptr};
+  unsigned long long *bigcnt = nullptr, *status = nullptr;
+  unsigned *tickets = nullptr;
+  if (big_possible) {
+    TRY(c, c->sortbig.ensure(64 + 2 * maxbig * sizeof(BigSeg) + maxtiles * 8, 0, st));
+    char *base = (char *)c->sortbig.p;
+    bigcnt = (unsigned long long *)base; tickets = (unsigned *)(base + 16);
+    big[0] = (BigSeg *)(base + 64); big[1] = big[0] + maxbig;
+    status = (unsigned long long *)(big[1] + maxbig);
+    CU(c, cudaMemsetAsync(base, 0, 64, st));
+    CU(c, cudaMemsetAsync(status, 0, maxtiles * 8, st));
+  }
+  BK_LAUNCH(is_init_roots, GRID1(nseg, 256), 256, 0, st, seg_off, nseg, act[0], cnt + 0, small, cnt + 3, term, cnt + 2, big[0], bigcnt);
   int lg = 0;
   for (long long t = n; t > 1; t >>= 1) ++lg;
   int max_levels = 2 * lg + 2;
   int cur = 0;
+  bool any_big = big_possible;                              // until a poll shows the big lists have drained (children are never larger than their parent)
   for (int level = 0; level < max_levels; ++level) {
     if (level > 0 && (level % 4) == 0) {                          // early exit once no segment is above the small-segment size (polled every 4th level: a poll is a host round trip)
       unsigned h = 0;
+      unsigned long long hb = 0;
       CU(c, cudaMemcpyAsync(&h, cnt + cur, 4, cudaMemcpyDeviceToHost, st));
+      if (any_big) CU(c, cudaMemcpyAsync(&hb, bigcnt + cur, 8, cudaMemcpyDeviceToHost, st));
       CU(c, cudaStreamSynchronize(st));
-      if (h == 0) break;
+      if (hb == 0) any_big = false;
+      if (h == 0 && !any_big) break;
     }
     CU(c, cudaMemsetAsync(cnt + (cur ^ 1), 0, 4, st));
+    if (any_big) {                                             // the two kernels reset each other's counters: no memsets between levels
+      BK_LAUNCH(is_big_part, 592, IS_THREADS, 0, st, key, val, big[cur], bigcnt + cur, tickets, status, c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>(),
+                bigcnt + (cur ^ 1), tickets + 1);
+      BK_LAUNCH(is_big_swap, 592, IS_THREADS, 0, st, key, val, big[cur], bigcnt + cur, tickets + 1, c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>(),
+                act[cur ^ 1], cnt + (cur ^ 1), small, cnt + 3, term, cnt + 2, big[cur ^ 1], bigcnt + (cur ^ 1), tickets, status);
+    }
     BK_LAUNCH(is_level, 592, IS_THREADS, 0, st, key, val, act[cur], cnt + cur, act[cur ^ 1], cnt + (cur ^ 1), small, cnt + 3, term, cnt + 2,
               c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>());
     cur ^= 1;
@@ -613,7 +639,7 @@ void bkid_destroy(bkid_ctx *c)
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->isize16, &c->span16, &c->cand_bits, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->seq_off, &c->seq4, &c->seq_len, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH, &c->dist_send, &c->dist_recv, &c->dist_rows, &c->dist_scalars})
+                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH, &c->dist_send, &c->dist_recv, &c->dist_rows, &c->dist_scalars, &c->sortbig})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();

@@ -990,17 +990,32 @@ __device__ void seg_heapsort(uint32_t *key, uint32_t *val, uint32_t f, uint32_t 
   }
 }
 
-__device__ __forceinline__ void seg_route(const Seg &s, Seg *act, unsigned *n_act, Seg *small, unsigned *n_small, Seg *term, unsigned *n_term)
+// A segment above IS_BIG elements is partitioned by several CTAs (is_big_part / is_big_swap below): one CTA streams a
+// 200 K element bucket at ~0.4 ms per level, and the skewed partitions the replay must reproduce keep such a segment
+// alive for 20+ levels (measured: 16 ms of is_level on one rank of the 8-GPU workload).
+struct BigSeg { uint32_t f, l; int depth; uint32_t tile_base, ntiles, pv, ready, nL, nR, _pad; };
+constexpr uint32_t IS_BIG = 49152;       // above the largest chr-pair bucket of a 30x genome (~35 K pairs): the single-GPU step never pays for the extra launches
+constexpr uint32_t IS_BTILE = 2048;     // elements per tile of a big segment (= IS_THREADS * IS_ITEMS)
+__device__ __forceinline__ void big_route(const Seg &s, BigSeg *big, unsigned long long *n_big /* count << 32 | tiles */)
+{
+  uint32_t nt = (s.l - s.f - 1 + IS_BTILE - 1) / IS_BTILE;
+  unsigned long long old = atomicAdd(n_big, (1ull << 32) | (unsigned long long)nt);      // list slot and tile range in ONE atomic: slots are ordered by tile_base
+  big[old >> 32] = BigSeg{s.f, s.l, s.depth, (uint32_t)old, nt, 0u, 0u, 0u, 0u, 0u};
+}
+__device__ __forceinline__ void seg_route(const Seg &s, Seg *act, unsigned *n_act, Seg *small, unsigned *n_small, Seg *term, unsigned *n_term,
+                                          BigSeg *big = nullptr, unsigned long long *n_big = nullptr)
 {
   uint32_t sz = s.l - s.f;
-  if (sz > IS_SMALL) act[atomicAdd(n_act, 1u)] = s;
+  if (big && sz > IS_BIG) big_route(s, big, n_big);
+  else if (sz > IS_SMALL) act[atomicAdd(n_act, 1u)] = s;
   else if (sz > 16) small[atomicAdd(n_small, 1u)] = s;
   else if (sz >= 2) term[atomicAdd(n_term, 1u)] = s;
 }
 
 // roots: one segment per bucket
 __global__ void is_init_roots(const uint32_t *__restrict__ seg_off, int nseg, Seg *__restrict__ act, unsigned *__restrict__ n_act,
-                              Seg *__restrict__ small, unsigned *__restrict__ n_small, Seg *__restrict__ term, unsigned *__restrict__ n_term)
+                              Seg *__restrict__ small, unsigned *__restrict__ n_small, Seg *__restrict__ term, unsigned *__restrict__ n_term,
+                              BigSeg *__restrict__ big, unsigned long long *__restrict__ n_big)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
@@ -1008,7 +1023,7 @@ __global__ void is_init_roots(const uint32_t *__restrict__ seg_off, int nseg, Se
   uint32_t n = l - f;
   if (n < 2) return;
   int lg = 31 - __clz(n);
-  seg_route(Seg{f, l, 2 * lg}, act, n_act, small, n_small, term, n_term);
+  seg_route(Seg{f, l, 2 * lg}, act, n_act, small, n_small, term, n_term, big, n_big);
 }
 
 // one warp per small segment, everything in shared memory: the same partition scheme as is_level
@@ -1145,7 +1160,7 @@ is_level(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__re
         }
       }
       unsigned tot;
-      unsigned ex = bk::block_excl_scan<unsigned>(cL | (cR << 16), sh32, tot);     // both counts in one scan (tile <= 4096)
+      unsigned ex = bk::block_excl_scan<unsigned>(cL | (cR << 16), sh32, tot);     // both counts in one scan (tile <= 4096; 16 elements per thread was measured slower: 0.46 vs 0.34 ms, the strided loads stop coalescing)
       unsigned oL = nL + (ex & 0xffffu), oR = nR + (ex >> 16);
 #pragma unroll
       for (int k = 0; k < IS_ITEMS; ++k) {
@@ -1177,6 +1192,153 @@ is_level(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__re
       seg_route(Seg{f, cut, s.depth - 1}, nxt, n_nxt, small, n_small, term, n_term);
     }
     __syncthreads();
+  }
+}
+
+// ---- big segments: the same partition step, one tile per CTA ---------------------------------------------------
+// is_big_part   tickets hand out (segment, tile) in list order.  Tile 0 moves the median to the front and publishes the
+//               pivot; every tile flags its slice from the left (L: key >= pivot) and from the right (R: key <= pivot),
+//               gets "L / R entries in earlier tiles" by decoupled look-back over 64-bit status words (flag + both running
+//               sums in one word) and writes its entries of the L / R position lists in place.  Earlier tiles of a segment
+//               hold earlier tickets, so whatever a tile waits for is already running.
+// is_big_swap   every tile finds K (the predicate L[k] < R[k] holds on a prefix: binary search), swaps its slice of the
+//               K pairs; tile 0 routes the two children.
+constexpr unsigned long long BS_AGG = 1ull << 62, BS_PREFIX = 2ull << 62, BS_SUM_MASK = (1ull << 31) - 1ull;
+
+__device__ __forceinline__ const BigSeg *big_find(const BigSeg *big, unsigned nb, uint32_t ticket, unsigned &idx)
+{
+  unsigned a = 0, b = nb;                                    // last slot with tile_base <= ticket
+  while (b - a > 1) { unsigned m = (a + b) >> 1; if (big[m].tile_base <= ticket) a = m; else b = m; }
+  idx = a;
+  return big + a;
+}
+
+__global__ void __launch_bounds__(IS_THREADS)
+is_big_part(uint32_t *__restrict__ key, uint32_t *__restrict__ val, BigSeg *__restrict__ big, const unsigned long long *__restrict__ n_big_p,
+            unsigned *__restrict__ ticket_p, unsigned long long *__restrict__ status, uint32_t *__restrict__ scrL, uint32_t *__restrict__ scrR,
+            unsigned long long *__restrict__ n_big_nxt, unsigned *__restrict__ ticket_swap)
+{
+  __shared__ unsigned sh32[33];
+  __shared__ unsigned sh_ticket, sh_exL, sh_exR;
+  const unsigned long long nbp = *n_big_p;
+  const unsigned nb = (unsigned)(nbp >> 32), ntickets = (unsigned)nbp;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *n_big_nxt = 0ull; *ticket_swap = 0u; }      // what is_big_swap (the next launch) counts with
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh_ticket = atomicAdd(ticket_p, 1u);
+    __syncthreads();
+    const unsigned ticket = sh_ticket;
+    if (ticket >= ntickets) return;
+    unsigned si;
+    const BigSeg *sp = big_find(big, nb, ticket, si);
+    const uint32_t f = sp->f, l = sp->l, tile = ticket - sp->tile_base, ntiles = sp->ntiles;
+    volatile BigSeg *vs = big + si;
+    if (sp->depth == 0) {                                    // depth exhausted: the literal heapsort, one thread (never seen on real data)
+      if (tile == 0 && threadIdx.x == 0) seg_heapsort(key, val, f, l);
+      continue;
+    }
+    if (tile == 0) {
+      if (threadIdx.x == 0) {
+        uint32_t mid = f + (l - f) / 2, A = f + 1, B = mid, C = l - 1;
+        uint32_t ka = __ldcg(key + A), kb = __ldcg(key + B), kc = __ldcg(key + C), med;
+        if (ka < kb) { if (kb < kc) med = B; else if (ka < kc) med = C; else med = A; }
+        else if (ka < kc) med = A;
+        else if (kb < kc) med = C;
+        else med = B;
+        uint32_t tk = __ldcg(key + f), tv = __ldcg(val + f), mk = __ldcg(key + med), mv = __ldcg(val + med);
+        key[f] = mk; val[f] = mv; key[med] = tk; val[med] = tv;
+        vs->pv = mk;
+        __threadfence();
+        vs->ready = 1u;
+      }
+    } else if (threadIdx.x == 0) {
+      while (vs->ready == 0u) { }
+      __threadfence();
+    }
+    __syncthreads();
+    const uint32_t pv = vs->pv;
+    const uint32_t lo = f + 1, cnt = l - lo;
+    const uint32_t e0 = tile * IS_BTILE + threadIdx.x * IS_ITEMS;
+    unsigned mL = 0, mR = 0, cL = 0, cR = 0;
+#pragma unroll
+    for (int k = 0; k < IS_ITEMS; ++k) {
+      uint32_t e = e0 + k;
+      if (e < cnt) {
+        if (!(__ldcg(key + lo + e) < pv)) { mL |= 1u << k; ++cL; }
+        if (!(pv < __ldcg(key + l - 1 - e))) { mR |= 1u << k; ++cR; }
+      }
+    }
+    unsigned tot;
+    unsigned ex = bk::block_excl_scan<unsigned>(cL | (cR << 16), sh32, tot);
+    if (threadIdx.x == 0) {
+      unsigned long long mine = ((unsigned long long)(tot & 0xffffu) << 31) | (unsigned long long)(tot >> 16);      // L sum << 31 | R sum
+      volatile unsigned long long *st = status + ticket;
+      unsigned long long exl = 0;
+      if (tile == 0) *st = BS_PREFIX | mine;
+      else {
+        *st = BS_AGG | mine;
+        for (int t = (int)ticket - 1;; --t) {
+          unsigned long long sv;
+          do { sv = *(volatile unsigned long long *)(status + t); } while ((sv >> 62) == 0ull);
+          exl += sv & ((1ull << 62) - 1ull);
+          if ((sv >> 62) == 2ull) break;
+        }
+        *st = BS_PREFIX | (exl + mine);
+      }
+      sh_exL = (unsigned)((exl >> 31) & BS_SUM_MASK); sh_exR = (unsigned)(exl & BS_SUM_MASK);
+      if (tile == ntiles - 1) { vs->nL = sh_exL + (tot & 0xffffu); vs->nR = sh_exR + (tot >> 16); }
+    }
+    __syncthreads();
+    unsigned oL = sh_exL + (ex & 0xffffu), oR = sh_exR + (ex >> 16);
+#pragma unroll
+    for (int k = 0; k < IS_ITEMS; ++k) {
+      if (mL & (1u << k)) scrL[lo + oL++] = lo + e0 + k;
+      if (mR & (1u << k)) scrR[lo + oR++] = l - 1 - (e0 + k);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(IS_THREADS)
+is_big_swap(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const BigSeg *__restrict__ big, const unsigned long long *__restrict__ n_big_p,
+            unsigned *__restrict__ ticket_p, const uint32_t *__restrict__ scrL, const uint32_t *__restrict__ scrR,
+            Seg *__restrict__ nxt, unsigned *__restrict__ n_nxt, Seg *__restrict__ small, unsigned *__restrict__ n_small, Seg *__restrict__ term, unsigned *__restrict__ n_term,
+            BigSeg *__restrict__ big_nxt, unsigned long long *__restrict__ n_big_nxt, unsigned *__restrict__ ticket_part, unsigned long long *__restrict__ status)
+{
+  __shared__ unsigned sh_ticket, sh_K;
+  const unsigned long long nbp = *n_big_p;
+  const unsigned nb = (unsigned)(nbp >> 32), ntickets = (unsigned)nbp;
+  // reset what the next level's is_big_part uses: its ticket and the status words this level touched
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket_part = 0u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ntickets; i += gridDim.x * blockDim.x) status[i] = 0ull;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh_ticket = atomicAdd(ticket_p, 1u);
+    __syncthreads();
+    const unsigned ticket = sh_ticket;
+    if (ticket >= ntickets) return;
+    unsigned si;
+    const BigSeg *sp = big_find(big, nb, ticket, si);
+    if (sp->depth == 0) continue;
+    const uint32_t f = sp->f, l = sp->l, lo = f + 1, tile = ticket - sp->tile_base, nL = sp->nL, nR = sp->nR;
+    const uint32_t mn = min(nL, nR);
+    if (threadIdx.x == 0) {
+      uint32_t a = 0, b = mn;                                // first k with !(L[k] < R[k])
+      while (a < b) { uint32_t m = (a + b) >> 1; if (scrL[lo + m] < scrR[lo + m]) a = m + 1; else b = m; }
+      sh_K = a;
+    }
+    __syncthreads();
+    const uint32_t K = sh_K;
+    for (uint32_t k = tile * IS_BTILE + threadIdx.x; k < K && k < (tile + 1) * IS_BTILE; k += IS_THREADS) {
+      uint32_t a = scrL[lo + k], b2 = scrR[lo + k];
+      uint32_t ka = __ldcg(key + a), va = __ldcg(val + a), kb = __ldcg(key + b2), vb = __ldcg(val + b2);
+      key[a] = kb; val[a] = vb; key[b2] = ka; val[b2] = va;
+    }
+    if (tile == 0 && threadIdx.x == 0) {
+      uint32_t rprev = K ? scrR[lo + K - 1] : l;
+      uint32_t cut = (K < nL && scrL[lo + K] < rprev) ? scrL[lo + K] : rprev;
+      seg_route(Seg{cut, l, sp->depth - 1}, nxt, n_nxt, small, n_small, term, n_term, big_nxt, n_big_nxt);
+      seg_route(Seg{f, cut, sp->depth - 1}, nxt, n_nxt, small, n_small, term, n_term, big_nxt, n_big_nxt);
+    }
   }
 }
 

@@ -74,7 +74,7 @@ int main(int, char **argv) {
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("flags", [["-all"], ["-all", "-fast"], ["-q", "30", "-t", "3"]])
+@pytest.mark.parametrize("flags", [["-all"], ["-all", "-fast"], ["-q", "30"]])
 def test_reference_main_built_against_compat_headers_writes_reference_call_files(tmp_path, flags):
     import oracle_py as O
     from breakid_b200 import bamio, synth

@@ -54,6 +54,46 @@ def test_sort_replay_depth_limit(ctx1):
         assert np.array_equal(O.sort_perm(key), ctx1.op_sort_perm(key)), n
 
 
+def test_sort_replay_big_segments(ctx1):
+    """segments above 48 K elements are partitioned by several CTAs (is_big_part / is_big_swap): tile boundaries, heavy ties,
+    sorted / reversed / merged-runs inputs, the depth-exhausted heapsort, against std::sort"""
+    import oracle_py as O
+    rng = np.random.RandomState(12)
+
+    def killer(n):
+        k = n // 2; a = np.zeros(n, np.uint32)
+        for i in range(1, k + 1):
+            if i % 2: a[i - 1] = i; a[i] = k + i
+            a[k + i - 1] = 2 * i
+        return a
+    cases = []
+    for n in (16385, 49152, 49153, 49154, 51201, 53249, 65536, 70001, 300000, 1 << 20):
+        cases += [("ties5", rng.randint(0, 5, n)), ("ties", rng.randint(0, n // 3 + 1, n)), ("sorted", np.sort(rng.randint(0, n + 1, n))),
+                  ("reversed", np.sort(rng.randint(0, n + 1, n))[::-1].copy()), ("random", rng.randint(0, 2 ** 32, n)),
+                  ("runs", np.concatenate([np.sort(rng.randint(0, 2 ** 31, n - n // 2)), np.sort(rng.randint(0, 2 ** 31, n // 2))])),
+                  ("const", np.full(n, 7))]
+    cases += [("killer", killer(n)) for n in (30000, 60000, 100000)]
+    bad = []
+    for name, key in cases:
+        key = key.astype(np.uint32)
+        if not np.array_equal(O.sort_perm(key), ctx1.op_sort_perm(key)):
+            bad.append((name, len(key)))
+    assert not bad, bad
+
+
+def test_remove_isolated_big_buckets(ctx1):
+    """the mask over buckets of 50 K .. 400 K pairs (three sort replays through the multi-CTA partition) against the oracle"""
+    import oracle_py as O
+    rng = np.random.RandomState(13)
+    for n, span in ((50000, 3_000_000), (120000, 40_000_000), (400000, 100_000_000)):
+        x = rng.randint(0, span, n).astype(np.uint32); y = rng.randint(0, span, n).astype(np.uint32)
+        k = n // 10                                       # planted dense groups + exact duplicates
+        x[:k] = (rng.randint(0, 50, k) * 1000 + rng.randint(0, 3, k) * 50).astype(np.uint32); y[:k] = (rng.randint(0, 50, k) * 1000 + rng.randint(0, 3, k) * 50).astype(np.uint32)
+        p = rng.permutation(n); x = x[p]; y = y[p]
+        a = O.remove_isolated(x, y, 1243.15); b = ctx1.op_remove_isolated(x, y, 1243.15)
+        assert np.array_equal(a, b), (n, len(a), len(b))
+
+
 def test_remove_isolated(ctx1):
     import oracle_py as O
     rng = np.random.RandomState(1)
