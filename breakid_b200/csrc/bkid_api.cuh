@@ -17,7 +17,8 @@ enum CounterSlot {
   CS_MISSING = 50,      // an SA record is missing from the sparse mate/name table
   CS_DECODE = 52,       // device decode: totals of the six per-chunk scans (u64 x 6)
   CS_NC = 64,           // number of candidates found through the sparse table (u32)
-  CS_XBAD = 65          // the sparse table is not strictly ascending / points outside the batch
+  CS_XBAD = 65,         // the sparse table is not strictly ascending / points outside the batch
+  CS_RG_TICKET = 66     // AHC tie groups: the next group to hand out
 };
 
 struct Scratch {          // reusable device scratch for sorts / scans over `cap` elements
@@ -460,9 +461,9 @@ static int cluster_ahc(bkid_ctx *c, const uint32_t *cur, const uint32_t *curb, c
     BK_LAUNCH(ahc_rg_heads, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO, bucket_events);
     bk::exclusive_scan<uint32_t, uint32_t>(g.is_head, head_excl, n, stmp, tot, st);
     BK_LAUNCH(ahc_rg_head_list, GRID1(n, 256), 256, 0, st, g.is_head, head_excl, n, head_pos);
-    const uint32_t RG_SMEM = 200u << 10;                   // buckets whose event tables fit are walked out of shared memory
-    BK_LAUNCH(ahc_rg_ties_smem, (unsigned)nseg, 128, RG_SMEM, st, v, g, (uint32_t)nseg, bucket_flag, RG_LO, bucket_events, head_pos, head_excl, n, RG_SMEM);
-    BK_LAUNCH(ahc_rg_ties, GRID1(nseg, 4), 128, 0, st, v, g, (uint32_t)nseg, bucket_flag, RG_LO, bucket_events, head_pos, head_excl, n, RG_SMEM);
+    unsigned *rg_ticket = c->counters.as<unsigned>() + CS_RG_TICKET;
+    CU(c, cudaMemsetAsync(rg_ticket, 0, 4, st));
+    BK_LAUNCH(ahc_rg_ties, 148 * 4, 128, 0, st, v, g, curb, bucket_flag, RG_LO, bucket_events, head_pos, tot, rg_ticket);      // one warp per tie group, ticket order
     BK_LAUNCH(ahc_rg_write, GRID1(n, 256), 256, 0, st, v, g, curb, n, bucket_flag, RG_LO);
   }
   T_.mark("ahc: replay rank form (global)");
@@ -624,7 +625,6 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   cudaFuncSetAttribute(sd_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_BLOCK * 9);
   cudaFuncSetAttribute(ahc_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
   cudaFuncSetAttribute(ahc_replay_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
-  cudaFuncSetAttribute(ahc_rg_ties_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
   memset(&c->tm, 0, sizeof c->tm);
   if (cudaGetLastError() != cudaSuccess) { g_create_err = "CUDA error during create"; delete c; return nullptr; }
   return c;

@@ -573,44 +573,34 @@ __global__ void ahc_rg_heads(AhcView v, RankGlobal g, const uint32_t *__restrict
   if (r == 0 || g.pm[g.order[p - 1]] != g.pm[e]) g.is_head[p] = 1;
 }
 
-// shared-memory footprint of one bucket's event tables (ahc_rg_ties_smem below)
-struct RgSmemLayout { uint32_t off_pm, off_d, off_ord, off_first, off_comp, off_rank, off_done, total; };
-__host__ __device__ inline RgSmemLayout rg_smem_layout(uint32_t M, uint32_t nleaf)
+// Tie groups (one exact prefix-max value touching >= 2 components): the literal heap walk over the group decides the
+// order of its events.  ONE WARP PER GROUP, groups handed out by an atomic ticket in rank order.  A group only depends on
+// earlier groups through the rank of the event that created a candidate's first node (same component, smaller or equal
+// prefix max): the warp waits for exactly those events (tie == 2) before it walks, everything else runs concurrently.
+// Earlier groups hold earlier tickets, so whatever a warp waits for is already running.  Inside a group every step picks
+// the minimum over the live candidates, which the lanes search in parallel (lexicographic warp reduction on (distance,
+// -global index)); sqrt(dx^2+dy^2) of integer offsets takes few distinct values, so a bucket has hundreds of such groups.
+// Measured on B200 before this form: one warp per BUCKET walking its groups in order took 0.65 ms (30x genome, global
+// memory) / 0.30 ms (events staged in shared memory), and 3.6 - 6.7 ms per rank on the 8-GPU workload whose buckets no
+// longer fit shared memory.
+__global__ void __launch_bounds__(128) ahc_rg_ties(AhcView v, RankGlobal g, const uint32_t *__restrict__ point_bucket, const int32_t *__restrict__ bucket_flag, uint32_t n_lo,
+                                                   const uint32_t *__restrict__ bucket_events, const uint32_t *__restrict__ head_pos, const unsigned long long *__restrict__ n_heads_p,
+                                                   unsigned *__restrict__ ticket)
 {
-  RgSmemLayout L;
-  uint32_t o = 0;
-  L.off_pm = o; o += M * 8;
-  L.off_d = o; o += M * 8;
-  L.off_ord = o; o += M * 4;
-  L.off_first = o; o += M * 4;
-  L.off_comp = o; o += M * 4;
-  L.off_rank = o; o += nleaf * 4;
-  L.off_done = o; o += (nleaf + 15u) & ~15u;
-  L.total = o;
-  return L;
-}
-// per bucket, group after group in ascending prefix-max order: the literal heap walk over the group.  One WARP per bucket:
-// the groups of a bucket depend on each other (a candidate's global index can be the rank an earlier group assigned), so
-// they run in order; inside a group every step picks the minimum over the group's live candidates, which the lanes search
-// in parallel (lexicographic warp reduction on (distance, -global index)).  One thread per bucket spent 0.5 ms here on the
-// 30x workload: sqrt(dx^2+dy^2) of integer offsets takes few distinct values, so tie groups are large.
-__global__ void __launch_bounds__(128) ahc_rg_ties(AhcView v, RankGlobal g, uint32_t nb, const int32_t *__restrict__ bucket_flag, uint32_t n_lo, const uint32_t *__restrict__ bucket_events,
-                                                   const uint32_t *__restrict__ head_pos, const uint32_t *__restrict__ head_excl, long long n, uint32_t smem_cap)
-{
-  uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= nb) return;
   const unsigned lane = threadIdx.x & 31;
-  uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
-  if (bucket_flag[b] || s1 - s0 < n_lo || s1 == s0) return;
-  uint32_t nleaf = s1 - s0, M = bucket_events[b];
-  if (rg_smem_layout(M, nleaf).total <= smem_cap) return;   // staged in shared memory by ahc_rg_ties_smem
-  uint32_t h0 = head_excl[s0], h1 = (s1 < (uint32_t)n) ? head_excl[s1] : head_excl[n - 1] + g.is_head[n - 1];
+  const unsigned n_heads = (unsigned)*n_heads_p;
   volatile uint8_t *tie = g.tie;
   volatile uint32_t *rank = g.rank;
-  for (uint32_t h = h0; h < h1; ++h) {
-    uint32_t p0 = head_pos[h], r = p0 - s0;
-    uint32_t e0 = g.order[p0];
-    const double pm0 = g.pm[e0];
+  for (;;) {
+    unsigned h = 0;
+    if (lane == 0) h = atomicAdd(ticket, 1u);
+    h = __shfl_sync(0xffffffffu, h, 0);
+    if (h >= n_heads) return;
+    const uint32_t p0 = head_pos[h], b = point_bucket[p0];
+    const uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
+    if (bucket_flag[b] || s1 - s0 < n_lo) continue;
+    const uint32_t nleaf = s1 - s0, M = bucket_events[b], r = p0 - s0;
+    const double pm0 = g.pm[g.order[p0]];
     // group end: first position whose prefix max differs (lanes probe 32 positions at a time)
     uint32_t r2 = r + 1;
     for (;;) {
@@ -621,6 +611,18 @@ __global__ void __launch_bounds__(128) ahc_rg_ties(AhcView v, RankGlobal g, uint
       r2 += (uint32_t)__ffs(~m) - 1u;
       break;
     }
+    // wait for the creators that sit in EARLIER groups (a creator inside this group is ranked by this walk before its
+    // dependant becomes eligible: events of one component are taken in order)
+    for (uint32_t p = r + lane; p < r2; p += 32) {
+      uint32_t e = g.order[s0 + p];
+      int32_t f = g.first[e];
+      if (f >= 0) continue;
+      uint32_t ce = v.comp_off[g.slot_comp[e]] + (uint32_t)(-1 - f);
+      if (g.pm[ce] == pm0) continue;
+      while (tie[ce] == 1) { }
+    }
+    __threadfence();
+    __syncwarp();
     for (uint32_t s = 0; s < r2 - r; ++s) {
       long long best = -1; double bd = 0.0; int32_t bg = -1;
       for (uint32_t p = r + lane; p < r2; p += 32) {
@@ -640,83 +642,10 @@ __global__ void __launch_bounds__(128) ahc_rg_ties(AhcView v, RankGlobal g, uint
         int32_t og = __shfl_xor_sync(0xffffffffu, bg, o);
         if (ob >= 0 && (best < 0 || od < bd || (od == bd && og > bg))) { best = ob; bd = od; bg = og; }
       }
-      if (lane == 0) { rank[best] = r + s; tie[best] = 2; }
+      if (lane == 0) { rank[best] = r + s; __threadfence(); tie[best] = 2; }
       __syncwarp();
     }
   }
-}
-
-// The same walk with the bucket's events staged in shared memory: the walk is a chain of dependent reads (group after
-// group, step after step), so what it costs is load latency -- 30 cycles from shared memory instead of an L2 round trip.
-// One CTA per bucket; all threads stage, warp 0 walks.  Buckets that do not fit (smem_cap bytes) are left to ahc_rg_ties.
-__global__ void __launch_bounds__(128) ahc_rg_ties_smem(AhcView v, RankGlobal g, uint32_t nb, const int32_t *__restrict__ bucket_flag, uint32_t n_lo, const uint32_t *__restrict__ bucket_events,
-                                                        const uint32_t *__restrict__ head_pos, const uint32_t *__restrict__ head_excl, long long n, uint32_t smem_cap)
-{
-  extern __shared__ __align__(16) unsigned char rg_smem[];
-  uint32_t b = blockIdx.x;
-  if (b >= nb) return;
-  uint32_t s0 = v.seg_off[b], s1 = v.seg_off[b + 1];
-  if (bucket_flag[b] || s1 - s0 < n_lo || s1 == s0) return;
-  uint32_t nleaf = s1 - s0, M = bucket_events[b];
-  uint32_t h0 = head_excl[s0], h1 = (s1 < (uint32_t)n) ? head_excl[s1] : head_excl[n - 1] + g.is_head[n - 1];
-  if (h1 == h0) return;                                     // no tie group in this bucket
-  RgSmemLayout L = rg_smem_layout(M, nleaf);
-  if (L.total > smem_cap) return;                           // ahc_rg_ties (global memory) takes it
-  double *pm = reinterpret_cast<double *>(rg_smem + L.off_pm), *dd = reinterpret_cast<double *>(rg_smem + L.off_d);
-  uint32_t *ord = reinterpret_cast<uint32_t *>(rg_smem + L.off_ord), *comp = reinterpret_cast<uint32_t *>(rg_smem + L.off_comp);
-  int32_t *first = reinterpret_cast<int32_t *>(rg_smem + L.off_first);
-  volatile uint32_t *rank = reinterpret_cast<uint32_t *>(rg_smem + L.off_rank);      // by event slot (e - s0)
-  volatile uint8_t *done = rg_smem + L.off_done;                                     // by event slot: tie[e] == 2
-  for (uint32_t p = threadIdx.x; p < M; p += blockDim.x) {
-    uint32_t e = g.order[s0 + p];
-    uint32_t cp = g.slot_comp[e];
-    int32_t f = g.first[e];
-    // first node of the event: a leaf index (>= 0), or -1 - (slot of the event that created the merged node)
-    ord[p] = e - s0; pm[p] = g.pm[e]; dd[p] = v.ev_d[e]; comp[p] = cp;
-    first[p] = f >= 0 ? f : -1 - (int32_t)(v.comp_off[cp] - s0 + (uint32_t)(-1 - f));
-  }
-  for (uint32_t q = threadIdx.x; q < nleaf; q += blockDim.x) { rank[q] = g.rank[s0 + q]; done[q] = g.tie[s0 + q] == 2 ? 1 : 0; }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const unsigned lane = threadIdx.x;
-    for (uint32_t h = h0; h < h1; ++h) {
-      uint32_t r = head_pos[h] - s0;
-      const double pm0 = pm[r];
-      uint32_t r2 = r + 1;
-      for (;;) {
-        uint32_t q = r2 + lane;
-        bool same = q < M && pm[q] == pm0;
-        unsigned m = __ballot_sync(0xffffffffu, same);
-        if (m == 0xffffffffu) { r2 += 32; continue; }
-        r2 += (uint32_t)__ffs(~m) - 1u;
-        break;
-      }
-      for (uint32_t s = 0; s < r2 - r; ++s) {
-        int best = -1; double bd = 0.0; int32_t bg = -1;
-        for (uint32_t p = r + lane; p < r2; p += 32) {
-          uint32_t e = ord[p];
-          if (done[e]) continue;
-          if (p > r) { uint32_t ep = ord[p - 1]; if (comp[p - 1] == comp[p] && !done[ep]) continue; }
-          int32_t f = first[p];
-          int32_t gi = f >= 0 ? f : (int32_t)nleaf + (int32_t)rank[(uint32_t)(-1 - f)];
-          double d = dd[p];
-          if (best < 0 || d < bd || (d == bd && gi > bg)) { best = (int)e; bd = d; bg = gi; }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          int ob = __shfl_xor_sync(0xffffffffu, best, o);
-          double od = __shfl_xor_sync(0xffffffffu, bd, o);
-          int32_t og = __shfl_xor_sync(0xffffffffu, bg, o);
-          if (ob >= 0 && (best < 0 || od < bd || (od == bd && og > bg))) { best = ob; bd = od; bg = og; }
-        }
-        if (lane == 0) { rank[best] = r + s; done[best] = 1; }
-        __syncwarp();
-      }
-    }
-  }
-  __syncthreads();
-  for (uint32_t q = threadIdx.x; q < nleaf; q += blockDim.x)
-    if (done[q]) { g.rank[s0 + q] = rank[q]; g.tie[s0 + q] = 2; }
 }
 
 __global__ void ahc_rg_head_list(const uint32_t *__restrict__ is_head, const uint32_t *__restrict__ head_excl, long long n, uint32_t *__restrict__ head_pos)
