@@ -18,7 +18,8 @@ enum CounterSlot {
   CS_DECODE = 52,       // device decode: totals of the six per-chunk scans (u64 x 6)
   CS_NC = 64,           // number of candidates found through the sparse table (u32)
   CS_XBAD = 65,         // the sparse table is not strictly ascending / points outside the batch
-  CS_RG_TICKET = 66     // AHC tie groups: the next group to hand out
+  CS_RG_TICKET = 66,    // AHC tie groups: the next group to hand out
+  CS_SORT_HEAP = 67     // std::sort replay: depth-exhausted segments waiting for is_heap
 };
 
 struct Scratch {          // reusable device scratch for sorts / scans over `cap` elements
@@ -108,6 +109,7 @@ struct bkid_ctx {
   Scratch sc;
   DBuf tmpA, tmpB, tmpC, tmpD, tmpE, tmpF, tmpG, tmpH;
   DBuf dist_send, dist_recv, dist_rows;     // multi-GPU exchanges (bkid_dist.cuh)
+  DBuf sortheap;                            // depth-exhausted segments of the std::sort replay
   DBuf sortbig;                             // big-segment lists / tile status of the std::sort replay (exact_sort_segments)
   DBuf dist_scalars;                        // all-reduce operands of one bkid_dist_run: never shared with a stage's scratch (those are re-sized under it)
   bkid_timings tm;
@@ -170,6 +172,11 @@ static int exact_sort_segments(bkid_ctx *c, uint32_t *key, uint32_t *val, const 
   Seg *term = c->tmpC.as<Seg>();
   TRY(c, c->tmpH.ensure(seg_bytes, 0, st));
   Seg *small = c->tmpH.as<Seg>();
+  // depth-exhausted segments above the small size (each > 1024 elements, disjoint): finished by is_heap after the last level
+  TRY(c, c->sortheap.ensure(((size_t)n / IS_SMALL + 16) * sizeof(Seg), 0, st));
+  Seg *heapl = c->sortheap.as<Seg>();
+  unsigned *n_heap = c->counters.as<unsigned>() + CS_SORT_HEAP;
+  CU(c, cudaMemsetAsync(n_heap, 0, 4, st));
   // big segments (> IS_BIG elements, several CTAs each): two lists, their packed sizes (count << 32 | tiles), two tickets, tile status words
   const bool big_possible = n > (long long)IS_BIG;
   const size_t maxbig = (size_t)(n / IS_BIG) + 2, maxtiles = (size_t)(n / IS_BTILE) + maxbig + 2;
@@ -204,14 +211,15 @@ static int exact_sort_segments(bkid_ctx *c, uint32_t *key, uint32_t *val, const 
     CU(c, cudaMemsetAsync(cnt + (cur ^ 1), 0, 4, st));
     if (any_big) {                                             // the two kernels reset each other's counters: no memsets between levels
       BK_LAUNCH(is_big_part, 592, IS_THREADS, 0, st, key, val, big[cur], bigcnt + cur, tickets, status, c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>(),
-                bigcnt + (cur ^ 1), tickets + 1);
+                bigcnt + (cur ^ 1), tickets + 1, heapl, n_heap);
       BK_LAUNCH(is_big_swap, 592, IS_THREADS, 0, st, key, val, big[cur], bigcnt + cur, tickets + 1, c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>(),
                 act[cur ^ 1], cnt + (cur ^ 1), small, cnt + 3, term, cnt + 2, big[cur ^ 1], bigcnt + (cur ^ 1), tickets, status);
     }
     BK_LAUNCH(is_level, 592, IS_THREADS, 0, st, key, val, act[cur], cnt + cur, act[cur ^ 1], cnt + (cur ^ 1), small, cnt + 3, term, cnt + 2,
-              c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>());
+              c->tmpD.as<uint32_t>(), c->tmpE.as<uint32_t>(), heapl, n_heap);
     cur ^= 1;
   }
+  BK_LAUNCH(is_heap, 148, 256, IS_HEAP_SMEM_ELEMS * 8 + 16, st, key, val, heapl, n_heap);
   BK_LAUNCH(is_small, 2368, ISS_WARPS * 32, 0, st, key, val, small, cnt + 3);
   BK_LAUNCH(is_terminal, 592, 128, 0, st, key, val, term, cnt + 2);
   return 0;
@@ -623,6 +631,7 @@ bkid_ctx *bkid_create(int device, const bkid_header *hdr, const bkid_params *par
   cudaMemset(c->d_nib_len.p, 0, (size_t)(nt + 1) * 8);
   c->nib.resize(nt); c->nib_len.assign(nt, 0);
   cudaFuncSetAttribute(sd_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_BLOCK * 9);
+  cudaFuncSetAttribute(is_heap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IS_HEAP_SMEM_ELEMS * 8 + 16));
   cudaFuncSetAttribute(ahc_replay_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
   cudaFuncSetAttribute(ahc_replay_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 4096);
   memset(&c->tm, 0, sizeof c->tm);
@@ -639,7 +648,7 @@ void bkid_destroy(bkid_ctx *c)
   for (DBuf *b : {&c->d_cum, &c->d_bucket_rank, &c->d_canon, &c->flag, &c->mapq, &c->tid, &c->pos, &c->isize, &c->endpos, &c->isize16, &c->span16, &c->cand_bits, &c->x_rec, &c->x_mtid, &c->x_mpos, &c->x_nh, &c->cls,
                   &c->sa_rec, &c->cig_off, &c->cig_ops, &c->sa_off, &c->sa_txt, &c->oc_off, &c->oc_txt, &c->seq_off, &c->seq4, &c->seq_len, &c->d_nib_ptr, &c->d_nib_len, &c->tile_cand, &c->counters,
                   &c->cand_idx, &c->cand, &c->bucket_rank_of, &c->pairs0, &c->pairs_tmp, &c->bucket_off0, &c->X, &c->Y, &c->bucket_of_pair, &c->cur1, &c->curb1, &c->seg1, &c->mem_pair,
-                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH, &c->dist_send, &c->dist_recv, &c->dist_rows, &c->dist_scalars, &c->sortbig})
+                  &c->mem_bucket, &c->mem_cluster, &c->sdtab, &c->sdlut, &c->clusters, &c->clusters_out, &c->sarows, &c->name_key, &c->name_row, &c->ex_tab, &c->ex_lo, &c->ex_len, &c->ex_pre, &c->work, &c->cov, &c->depth, &c->evoff, &c->valid, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->tmpE, &c->tmpF, &c->tmpG, &c->tmpH, &c->dist_send, &c->dist_recv, &c->dist_rows, &c->dist_scalars, &c->sortbig, &c->sortheap})
     b->release();
   for (auto &b : c->nib) b.release();
   c->sc.release();

@@ -1114,7 +1114,8 @@ __global__ void __launch_bounds__(ISS_WARPS * 32) is_small(uint32_t *__restrict_
 __global__ void __launch_bounds__(IS_THREADS)
 is_level(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__restrict__ act, const unsigned *__restrict__ n_act_p,
          Seg *__restrict__ nxt, unsigned *__restrict__ n_nxt, Seg *__restrict__ small, unsigned *__restrict__ n_small,
-         Seg *__restrict__ term, unsigned *__restrict__ n_term, uint32_t *__restrict__ scrL, uint32_t *__restrict__ scrR)
+         Seg *__restrict__ term, unsigned *__restrict__ n_term, uint32_t *__restrict__ scrL, uint32_t *__restrict__ scrR,
+         Seg *__restrict__ heap, unsigned *__restrict__ n_heap)
 {
   __shared__ unsigned sh32[33];
   __shared__ uint32_t sh_p;
@@ -1123,9 +1124,8 @@ is_level(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__re
   for (unsigned si = blockIdx.x; si < n_act; si += gridDim.x) {
     Seg s = act[si];
     uint32_t f = s.f, l = s.l;
-    if (s.depth == 0) {
-      if (threadIdx.x == 0) seg_heapsort(key, val, f, l);
-      __syncthreads();
+    if (s.depth == 0) {                                        // depth budget spent: the literal heapsort, done by is_heap at the end of the sort
+      if (threadIdx.x == 0) heap[atomicAdd(n_heap, 1u)] = s;
       continue;
     }
     if (threadIdx.x == 0) {
@@ -1216,7 +1216,7 @@ __device__ __forceinline__ const BigSeg *big_find(const BigSeg *big, unsigned nb
 __global__ void __launch_bounds__(IS_THREADS)
 is_big_part(uint32_t *__restrict__ key, uint32_t *__restrict__ val, BigSeg *__restrict__ big, const unsigned long long *__restrict__ n_big_p,
             unsigned *__restrict__ ticket_p, unsigned long long *__restrict__ status, uint32_t *__restrict__ scrL, uint32_t *__restrict__ scrR,
-            unsigned long long *__restrict__ n_big_nxt, unsigned *__restrict__ ticket_swap)
+            unsigned long long *__restrict__ n_big_nxt, unsigned *__restrict__ ticket_swap, Seg *__restrict__ heap, unsigned *__restrict__ n_heap)
 {
   __shared__ unsigned sh32[33];
   __shared__ unsigned sh_ticket, sh_exL, sh_exR;
@@ -1233,8 +1233,8 @@ is_big_part(uint32_t *__restrict__ key, uint32_t *__restrict__ val, BigSeg *__re
     const BigSeg *sp = big_find(big, nb, ticket, si);
     const uint32_t f = sp->f, l = sp->l, tile = ticket - sp->tile_base, ntiles = sp->ntiles;
     volatile BigSeg *vs = big + si;
-    if (sp->depth == 0) {                                    // depth exhausted: the literal heapsort, one thread (never seen on real data)
-      if (tile == 0 && threadIdx.x == 0) seg_heapsort(key, val, f, l);
+    if (sp->depth == 0) {                                    // depth budget spent: is_heap finishes the segment
+      if (tile == 0 && threadIdx.x == 0) heap[atomicAdd(n_heap, 1u)] = Seg{f, l, 0};
       continue;
     }
     if (tile == 0) {
@@ -1339,6 +1339,74 @@ is_big_swap(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const BigSeg
       seg_route(Seg{cut, l, sp->depth - 1}, nxt, n_nxt, small, n_small, term, n_term, big_nxt, n_big_nxt);
       seg_route(Seg{f, cut, sp->depth - 1}, nxt, n_nxt, small, n_small, term, n_term, big_nxt, n_big_nxt);
     }
+  }
+}
+
+// Depth-exhausted segments above the small-segment size: the literal std::__partial_sort heapsort, one thread, on a copy of
+// the segment in shared memory (a dependent walk down the heap per element: 30-cycle shared-memory loads instead of L2 round
+// trips).  Near-sorted input -- the p2 order of a same-chromosome bucket right after its p1 sort -- drives median-of-3 into
+// its worst case, so deep-coverage buckets DO end here: a 4 459 element segment took ~10 ms from global memory.
+constexpr uint32_t IS_HEAP_SMEM_ELEMS = 25600;          // 200 KB of (key, value)
+
+// the same heapsort as seg_heapsort on (key, value) pairs held as one 8-byte word each, 32-bit indices; H[1] is 16-byte
+// aligned, so the two children of a hole (indices 2h+1, 2h+2) come with ONE 16-byte load
+__device__ __forceinline__ void heap_adjust_pairs(uint2 *H, int hole, int len, uint2 v)
+{
+  const int top = hole;
+  int child = hole;
+  const int lim = (len - 1) / 2;
+  while (child < lim) {
+    child = 2 * (child + 1);
+    uint4 c2 = *reinterpret_cast<const uint4 *>(H + child - 1);          // (key, val) of child-1 and of child
+    uint2 pick = make_uint2(c2.z, c2.w);
+    if (c2.z < c2.x) { --child; pick = make_uint2(c2.x, c2.y); }
+    H[hole] = pick;
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    H[hole] = H[child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > top && H[parent].x < v.x) {
+    H[hole] = H[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  H[hole] = v;
+}
+__device__ __forceinline__ void heapsort_pairs(uint2 *H, int n)
+{
+  if (n < 2) return;
+  for (int parent = (n - 2) / 2;; --parent) {
+    heap_adjust_pairs(H, parent, n, H[parent]);
+    if (parent == 0) break;
+  }
+  for (int last = n - 1; last > 0; --last) {
+    uint2 v = H[last];
+    H[last] = H[0];
+    heap_adjust_pairs(H, 0, last, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) is_heap(uint32_t *__restrict__ key, uint32_t *__restrict__ val, const Seg *__restrict__ heap, const unsigned *__restrict__ n_heap_p)
+{
+  extern __shared__ __align__(16) unsigned char hs_raw[];
+  uint2 *H = reinterpret_cast<uint2 *>(hs_raw + 8);        // &H[1] is 16-byte aligned
+  const unsigned n_heap = *n_heap_p;
+  for (unsigned si = blockIdx.x; si < n_heap; si += gridDim.x) {
+    const uint32_t f = heap[si].f, l = heap[si].l, n = l - f;
+    if (n > IS_HEAP_SMEM_ELEMS) {
+      if (threadIdx.x == 0) seg_heapsort(key, val, f, l);
+      continue;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) H[i] = make_uint2(key[f + i], val[f + i]);
+    __syncthreads();
+    if (threadIdx.x == 0) heapsort_pairs(H, (int)n);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { uint2 e = H[i]; key[f + i] = e.x; val[f + i] = e.y; }
   }
 }
 

@@ -110,3 +110,13 @@ def test_complementary_cigars():
     bad = [c for c in cig if O.olib().orc_is_complementary(c[0].encode(), c[1].encode(), 10) != c[2]]
     assert not bad, bad[:5]
     assert sum(c[2] for c in cig) > 100
+
+
+def test_depth_exhausted_keys_model_equals_std_sort():
+    """the level-synchronous model of std::sort (what the GPU kernels implement) on keys that exhaust the introsort depth
+    budget on ~4 000 element segments (real bucket, tests/golden/make_depth_exhausted_keys.py)"""
+    import oracle_py as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "depth_exhausted_sort_keys.npz"))
+    for name in ("sort2", "sort3"):
+        key = g[name]
+        assert np.array_equal(O.sort_perm(key), O.sort_perm(key, model=True)), name

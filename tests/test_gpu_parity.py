@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
 inputs.  Bit-exact: everything on this path is integer / byte / index work, and the FP64 parts
 (insert sd, AHC distances) are required to be bit-identical too."""
+import os
+
 import numpy as np
 import pytest
 
@@ -79,6 +81,18 @@ def test_sort_replay_big_segments(ctx1):
         if not np.array_equal(O.sort_perm(key), ctx1.op_sort_perm(key)):
             bad.append((name, len(key)))
     assert not bad, bad
+
+
+def test_sort_replay_depth_exhausted_segments(ctx1):
+    """keys of a real near-sorted bucket (tests/golden/make_depth_exhausted_keys.py): introsort runs out of depth on segments
+    of ~4 000 elements, which is_heap finishes with the literal heapsort out of shared memory"""
+    import oracle_py as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "depth_exhausted_sort_keys.npz"))
+    for name in ("sort2", "sort3"):
+        key = g[name]
+        assert np.array_equal(O.sort_perm(key), ctx1.op_sort_perm(key)), name
+        rep = np.concatenate([key, key[::-1], key])          # the same with every key three times: ties inside the heapsort
+        assert np.array_equal(O.sort_perm(rep), ctx1.op_sort_perm(rep)), name
 
 
 def test_remove_isolated_big_buckets(ctx1):

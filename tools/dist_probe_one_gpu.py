@@ -72,6 +72,26 @@ def main():
         print(json.dumps({"replay_rank": r, "pairs": int(p.shape[0]), "buckets": int((sizes > 0).sum()), "largest_buckets": sorted(sizes.tolist())[-3:],
                           "mask_ms": round(tm["mask"], 3), "cluster_ms": round(tm["cluster"], 3),
                           "kernels": {nm: [v[0], round(v[1], 3)] for nm, v in sorted(rep.items(), key=lambda kv: -kv[1][1]) if v[1] > 0.04 * tot}}), flush=True)
+        if tm["mask"] > 6.0 and os.environ.get("BKID_PROBE_DUMP"):
+            # which bucket is it?  time the mask of every large bucket on its own and keep the slowest one's coordinates
+            import time
+            worst = (0.0, None)
+            for bk_ in np.nonzero(sizes > 20000)[0]:
+                q = p[p["bucket"] == bk_]
+                q = q[np.argsort(q["orig"], kind="stable")]
+                x = q["p1_chr_pos"].copy(); y = q["p2_chr_pos"].copy()
+                c2.op_remove_isolated(x, y, dist_thr)
+                api.profile_kernels(True); api.profile_report()
+                out = c2.op_remove_isolated(x, y, dist_thr)
+                rep2 = api.profile_report(); api.profile_kernels(False)
+                dt = sum(v[1] for v in rep2.values())
+                lv = rep2.get("is_level", (0, 0.0))
+                print(json.dumps({"rank": r, "bucket": int(bk_), "pairs": int(len(q)), "kept": int(len(out)), "kernel_ms": round(dt, 3), "is_level": [lv[0], round(lv[1], 3)],
+                                  "tids": [int(q["p1_tid"][0]), int(q["p2_tid"][0])]}), flush=True)
+                if dt > worst[0]:
+                    worst = (dt, (x, y, int(bk_)))
+            if worst[1] is not None:
+                np.savez_compressed(os.path.join(ROOT, "gpurun_out", "slow_bucket_rank%d.npz" % r), x=worst[1][0], y=worst[1][1], bucket=worst[1][2], w=dist_thr)
         c2.close()
 
 
