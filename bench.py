@@ -688,6 +688,15 @@ def run_ours(args):
     }
     if world > 1:
         from breakid_b200 import dist as _d
+        import torch.distributed as dist
+        # every rank's own stage walls (a stage that ends in a collective includes the wait for the slowest rank) and its
+        # device-side mask / cluster times: where the step's critical path is
+        mine = torch.tensor([shard_timing.get(k, 0.0) / 2.0 for k in DIST_STAGES] + [tm["mask"], tm["cluster"], float(tm["n_pairs"]), float(tm["n_masked"])],
+                            device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        line["stage_ms_per_rank"] = {"columns": list(DIST_STAGES) + ["mask (device)", "cluster (device)", "pairs owned", "pairs after mask"],
+                                     "rows": [[round(float(x), 3) for x in r.tolist()] for r in allr]}
         line["exchanges"] = ("inside the library: NCCL all-reduce / grouped send-recv issued from C++ (bkid_dist_run)" if libdist is not None
                              else "Python-orchestrated (torch.distributed), --py-dist")
         line["sharded_parity"] = pre
