@@ -279,7 +279,8 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_maxspan", "bkid_shard_set_maxspan", "bkid_shard_coverage", "bkid_shard_vote", "bkid_shard_depth",
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
            "bkid_push_bgzf", "bkid_push_bgzf_range", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align", "bkid_profile_kernels", "bkid_profile_report",
-           "bkid_comm_nccl_unique_id", "bkid_comm_nccl_init", "bkid_comm_nccl_init_all", "bkid_comm_local_create", "bkid_comm_destroy", "bkid_dist_run", "bkid_dist_run_threads"]
+           "bkid_comm_nccl_unique_id", "bkid_comm_nccl_init", "bkid_comm_nccl_init_all", "bkid_comm_local_create", "bkid_comm_destroy", "bkid_dist_run", "bkid_dist_run_threads",
+           "bkid_op_summarize", "bkid_set_params"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -325,6 +326,8 @@ def cuda_lib():
         L.bkid_op_sort_perm.argtypes = [vp, C.c_int64, vp, vp]
         L.bkid_op_remove_isolated.argtypes = [vp, C.c_int64, vp, vp, C.c_double, vp, i64p]
         L.bkid_op_cluster.argtypes = [vp, C.c_int, C.c_int64, vp, vp, C.c_double, vp, vp, i64p, C.POINTER(C.c_int32)]
+        L.bkid_op_summarize.argtypes = [vp, C.c_int64, vp, C.c_double, i64p]
+        L.bkid_set_params.argtypes = [vp, vp]
         pvp = C.POINTER(C.c_void_p)
         u64p = C.POINTER(C.c_uint64)
         L.bkid_shard_insert_partial.argtypes = [vp, i64p, i64p, u64p, u64p]
@@ -615,6 +618,26 @@ class Context:
         n = C.c_int64()
         self._chk(self.lib.bkid_op_remove_isolated(self.ctx, p1.shape[0], p1.ctypes.data, p2.ctypes.data, w, out.ctypes.data, C.byref(n)))
         return out[:n.value]
+
+    def set_params(self, **kw):
+        """replace thresholds for the next stage calls (``bkid_set_params``); unknown names raise"""
+        p = Params()
+        for k, _ in Params._fields_:
+            setattr(p, k, getattr(self.params, k))
+        for k, v in kw.items():
+            if k not in dict(Params._fields_):
+                raise KeyError(k)
+            setattr(p, k, int(v))
+        self._chk(self.lib.bkid_set_params(self.ctx, C.byref(p)))
+        self.params = p
+
+    def op_summarize(self, pairs: np.ndarray, dist: float) -> int:
+        """K6 on the pairs of one bucket (PAIR_DTYPE rows grouped by ascending ``cluster``): leaves the summaries in the context,
+        ``refine`` + ``fetch_clusters`` then give the bucket's calls (``bkid_op_summarize``)"""
+        pairs = np.ascontiguousarray(pairs, PAIR_DTYPE)
+        n = C.c_int64()
+        self._chk(self.lib.bkid_op_summarize(self.ctx, pairs.shape[0], pairs.ctypes.data, dist, C.byref(n)))
+        return n.value
 
     def op_cluster(self, mode, p1, p2, thr):
         p1 = np.ascontiguousarray(p1, np.uint32); p2 = np.ascontiguousarray(p2, np.uint32)
