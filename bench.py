@@ -821,17 +821,36 @@ def sharded_parity(rank, world, local, dev):
 
 
 def cpu_baseline_port(args):
-    """oracle port (single thread) on a bounded sample of the same workload, decode excluded"""
+    """CPU baseline on the host cores of this box, on the bounded sample the e2e leg ran on: ONE run of the reference CPU
+    binary (oracle/_ref/BreakID_ref, single-threaded, BAM decode included -- 10-30 s of CPU work at the default sample) when it
+    is built, with the oracle port (decode excluded) on the same records beside it; the port alone otherwise."""
     import oracle_py as O
-    scale = min(args.scale, 1.0 / 64)
-    cfg = workload_cfg(scale)
+    scale = min(sample_scale(args.steps, args.warmup), args.scale)
+    cores = os.cpu_count()
+    if os.path.exists(O.REF_BIN):
+        paths, n = sample_dataset(scale)
+        O.ref_install_refgene(paths["refgene"])
+        tmp = tempfile.mkdtemp(prefix="bkid_cpu_")
+        t0 = time.perf_counter()
+        r = O.ref_run_binary(paths["bam"], os.path.join(tmp, "ref"), paths["nib"])
+        dt = time.perf_counter() - t0
+        if r.returncode == 0:
+            hb = api.HostBatch.from_bam(paths["bam"], threads=cores or 8)
+            t0 = time.perf_counter()
+            O.run(hb, None, mode=0)
+            dp = time.perf_counter() - t0
+            return {"value": n / 2.0 / dt, "unit": UNIT, "cores": 1, "kind": "reference", "seconds": dt,
+                    "sample": "configs[1] x 1/%d: %d records, %d-byte BAM, decode included, one run of oracle/_ref/BreakID_ref (single-threaded program, host has %d cores)"
+                              % (round(1 / scale), n, os.path.getsize(paths["bam"]), cores),
+                    "port": {"value": hb.n / 2.0 / dp, "unit": UNIT, "cores": 1, "seconds": dp, "what": "oracle/liboracle.so orc_run on the same records, decode excluded"}}
+    cfg = workload_cfg(min(args.scale, 1.0 / 4))
     d = synth.generate(cfg)
     hb = api.HostBatch.from_synth(d)
     t0 = time.perf_counter()
     O.run(hb, None, mode=0)
     dt = time.perf_counter() - t0
     return {"value": hb.n / 2.0 / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
-            "sample": "configs[1] x scale %g: %d records, oracle/liboracle.so orc_run (AHC mode, decode excluded), host has %d cores" % (scale, hb.n, os.cpu_count())}
+            "sample": "configs[1] x 1/4: %d records, oracle/liboracle.so orc_run (AHC mode, decode excluded), host has %d cores" % (hb.n, cores)}
 
 
 def run_reference(args):
