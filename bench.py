@@ -471,6 +471,22 @@ def align_leg(local, n_pairs=1 << 20):
 
 
 # algorithmic bytes per unit of the kernels that matter; unit counts are taken from the run
+NCU_TRAFFIC = os.path.join(ROOT, "profiles", "r02h_ncu_front_kernels.json")
+
+
+def ncu_traffic(kernel, n):
+    """DRAM bytes per launch of `kernel` for n records: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    capture (profiles/r02h_ncu_front_kernels.{md,json}, same kernel body, 619 243 482 records), scaled per record; None when the
+    kernel is not in that capture"""
+    try:
+        prof = json.load(open(NCU_TRAFFIC))
+    except OSError:
+        return None
+    base = kernel.split("<")[0]
+    k = prof["kernels"].get(base)
+    return k["dram_bytes_per_record"] * n if k else None
+
+
 def kernel_bytes(name, cnt, n):
     nc, npair = cnt["n_candidates"], cnt["n_pairs"]
     if name.startswith("k1_classify"):
@@ -660,8 +676,8 @@ def run_ours(args):
         dom["frac"] = dom["achieved_GBps"] / peak if dom["achieved_GBps"] else None
     whole_bytes = 11.0 * n                                # K1 8 + sd pass 3 B/record: what the step must read once
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
-                "note": "dominant kernel by measured time (CUDA events around every launch on its own stream, two extra untimed steps); DRAM traffic per launch: profiles/ (ncu --set full)",
+                "traffic": ncu_traffic(dom["kernel"], n), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
+                "note": "dominant kernel by measured time (CUDA events around every launch on its own stream, two extra untimed steps); traffic = DRAM bytes per launch from one ncu --set full capture (profiles/r02h_ncu_front_kernels.md), scaled per record",
                 "kernels": klist,
                 "whole_step": {"algorithmic_bytes": whole_bytes, "bytes_are": "11 B/record must be read once (K1 8 + insert-sd pass 3); everything after K1 works on the 1 % candidates",
                                "ms_per_step": ms_step, "achieved_GBps": whole_bytes * (1 if world == 1 else 1) / (ms_step * 1e-3) / 1e9,
