@@ -913,3 +913,25 @@ def test_stage_by_stage_equals_whole_run(small_data, mode):
     a["bucket"] = 0; b["bucket"] = 0
     assert a.tobytes() == b.tobytes()
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_genome_longer_than_2_32_bases(mode):
+    """targets of 2.1 + 2.1 + 0.4 Gb: genome-wide pair coordinates wrap in uint32 like combine_genome_chr_pos
+    (src/util_bam.cc:57-68; the oracle's wrap is pinned to the reference in test_scan_wraps_genome_coordinates_like_the_reference);
+    scan pairs and the whole path must equal the oracle"""
+    import oracle_py as O
+    from breakid_b200 import api, synth
+    cfg = synth.SynthConfig(chrom_lens=[2_100_000_000, 2_100_000_000, 400_000_000], n_pairs=40000, n_tra=6, n_inv=3, n_dup=3, n_del=3, seed=7, sv_jitter=1)
+    d = synth.generate(cfg)
+    hb = api.HostBatch.from_synth(d)
+    ctx = api.Context(hb.target_len, hb.target_names, device=0, fast=mode)
+    ctx.push(hb)
+    mean, sd, dist, n = ctx.run()
+    om, osd, od, exp = O.run(hb, None, mode=mode)
+    assert (mean, sd, dist) == (om, osd, od)
+    got_pairs = ctx.fetch_pairs(0)
+    ref_pairs = O.scan(hb, 20, od)
+    assert np.array_equal(np.sort(got_pairs["p2_chr_pos"]), np.sort(ref_pairs["p2_chr_pos"])) and int((ref_pairs["p2_chr_pos"] < 400_000_000).sum()) >= 3
+    assert ctx.fetch_clusters().tobytes() == exp.tobytes() and len(exp) >= 8
+    ctx.close()

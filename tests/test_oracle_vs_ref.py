@@ -226,3 +226,23 @@ def test_sd_multiplier_oracle_vs_patched_reference(dataset, tmp_path, sd_mult, m
         assert r0.returncode == 0
         for suffix in ("_fusion.txt", "_fusion_all.txt"):
             assert open(str(tmp_path / "ref") + suffix).read() == open(str(tmp_path / "ref0") + suffix).read()
+
+
+def test_scan_wraps_genome_coordinates_like_the_reference(tmp_path):
+    """a genome longer than 2^32 bases: combine_genome_chr_pos (src/util_bam.cc:57-68) adds target lengths in uint32, so the
+    genome-wide coordinate of a pair far enough into the third target wraps; the oracle must wrap exactly like the reference
+    (scan output compared byte for byte on a BAM whose targets are 2.1 + 2.1 + 0.4 Gb)"""
+    from breakid_b200 import api, bamio, synth
+    cfg = synth.SynthConfig(chrom_lens=[2_100_000_000, 2_100_000_000, 400_000_000], n_pairs=40000, n_tra=6, n_inv=3, n_dup=3, n_del=3, seed=7, sv_jitter=1)
+    d = synth.generate(cfg)
+    hb = api.HostBatch.from_synth(d)
+    bam = str(tmp_path / "w.bam")
+    bamio.write_bam(bam, d)
+    synth.write_ref_names(str(tmp_path / "ref_names.txt"), 3)
+    om, osd, _, _, _ = O.insert_stats(hb)
+    w = O.dist(om, osd)
+    pairs = O.scan(hb, 20, w)
+    wrapped = pairs[(pairs["p2_tid"] == 2) & (pairs["p2_pos"] > 95_000_000)]
+    assert len(wrapped) >= 3 and np.all(wrapped["p2_chr_pos"] == ((4_200_000_000 + wrapped["p2_pos"].astype(np.int64) - 1) % 2 ** 32))
+    assert np.all(wrapped["p2_chr_pos"] < 400_000_000)                       # i.e. it really wrapped
+    assert pairs.tobytes() == O.ref_scan(bam, 20, w, str(tmp_path)).tobytes()
