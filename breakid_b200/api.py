@@ -280,7 +280,7 @@ EXPORTS = ["bkid_abi_version", "bkid_last_error", "bkid_default_params", "bkid_c
            "bkid_shard_finish", "bkid_fetch_bucket_ranks", "bkid_device_copy",
            "bkid_push_bgzf", "bkid_push_bgzf_range", "bkid_get_decode_stats", "bkid_fetch_column", "bkid_set_exclude", "bkid_device_gather_rows", "bkid_op_banded_align", "bkid_profile_kernels", "bkid_profile_report",
            "bkid_comm_nccl_unique_id", "bkid_comm_nccl_init", "bkid_comm_nccl_init_all", "bkid_comm_local_create", "bkid_comm_destroy", "bkid_dist_run", "bkid_dist_run_threads",
-           "bkid_op_summarize", "bkid_set_params"]
+           "bkid_op_summarize", "bkid_set_params", "bkid_lpt_owner_table"]
 
 CAND_BYTES = 48
 SAROW_BYTES = 88
@@ -328,6 +328,7 @@ def cuda_lib():
         L.bkid_op_cluster.argtypes = [vp, C.c_int, C.c_int64, vp, vp, C.c_double, vp, vp, i64p, C.POINTER(C.c_int32)]
         L.bkid_op_summarize.argtypes = [vp, C.c_int64, vp, C.c_double, i64p]
         L.bkid_set_params.argtypes = [vp, vp]
+        L.bkid_lpt_owner_table.argtypes = [vp, C.c_int, C.c_int, vp]
         pvp = C.POINTER(C.c_void_p)
         u64p = C.POINTER(C.c_uint64)
         L.bkid_shard_insert_partial.argtypes = [vp, i64p, i64p, u64p, u64p]

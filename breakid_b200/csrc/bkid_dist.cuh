@@ -618,6 +618,18 @@ int bkid_comm_local_create(int world, bkid_comm **out)
 
 void bkid_comm_destroy(bkid_comm *cm) { delete cm; }
 
+// the bucket -> rank table bkid_dist_run derives from the global pairs-per-bucket histogram (pure host code; exported so
+// that the CPU test-suite can check it: every rank must compute the same table from the same histogram)
+int bkid_lpt_owner_table(const uint64_t *hist, int n_buckets, int world, uint8_t *owner)
+{
+  if (!hist || !owner || n_buckets < 0 || world < 1 || world > RT_MAXW) return BKID_ERR_ARG;
+  std::vector<unsigned long long> h(hist, hist + n_buckets);
+  std::vector<uint8_t> o;
+  lpt_owner_table(h, world, o);
+  if (n_buckets) memcpy(owner, o.data(), (size_t)n_buckets);
+  return 0;
+}
+
 int bkid_dist_run(bkid_ctx *c, bkid_comm *cm, int mode, double *mean, double *sd, double *dist, int64_t *n_called, float *stage_ms /* [9] or NULL */)
 {
   if (!c || !cm) return BKID_ERR_ARG;

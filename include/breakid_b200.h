@@ -323,6 +323,9 @@ void bkid_comm_destroy(bkid_comm *comm);
 /* stage_ms (optional, 9 floats): insert statistics, candidates, candidate all-to-all, join, pair all-to-all, mask + cluster,
  * gathers, refinement, total -- host wall clock of this rank */
 int bkid_dist_run(bkid_ctx *ctx, bkid_comm *comm, int mode, double *mean, double *sd, double *dist, int64_t *n_called, float *stage_ms);
+/* The bucket -> rank table of the pair exchange: longest-processing-time-first on the GLOBAL pairs-per-bucket histogram
+ * (index = bucket name rank), cost model m * (1 + log2(m + 1) / 16).  Pure host code, identical on every rank. */
+int bkid_lpt_owner_table(const uint64_t *hist, int n_buckets, int world, uint8_t *owner);
 int bkid_dist_run_threads(bkid_ctx **ctxs, bkid_comm **comms, int world, int mode, double *mean, double *sd, double *dist, int64_t *n_called);
 
 /* Stand-alone operator entry points (device work on caller host arrays) used by the parity tests:

@@ -147,3 +147,27 @@ def test_host_decoder_narrow_batch_matches_python_narrowing(tmp_path):
         assert b.seq_off and np.array_equal(get(b.seq_len, hb.n_sa, np.int32), hb.seq["seq_len"])
     finally:
         lib.bkid_host_bam_free(h)
+
+
+def test_bucket_owner_table_is_balanced_and_deterministic():
+    """bkid_lpt_owner_table (host part of the multi-GPU pair exchange): every non-empty bucket gets an owner < world, the
+    estimated loads differ by at most the largest bucket, the same histogram gives the same table, world 1 owns everything"""
+    import ctypes as C
+    import numpy as np
+    from breakid_b200 import api
+    L = api.cuda_lib()
+    rng = np.random.RandomState(4)
+    for world in (1, 2, 3, 8, 32):
+        for trial in range(20):
+            nb = int(rng.choice([1, 7, 300, 625]))
+            hist = (rng.pareto(1.2, nb) * 1000).astype(np.uint64) * (rng.rand(nb) < 0.8)
+            hist = np.ascontiguousarray(hist, np.uint64)
+            own = np.full(nb, 255, np.uint8); own2 = own.copy()
+            assert L.bkid_lpt_owner_table(hist.ctypes.data, nb, world, own.ctypes.data) == 0
+            assert L.bkid_lpt_owner_table(hist.ctypes.data, nb, world, own2.ctypes.data) == 0
+            assert np.array_equal(own, own2) and int(own.max()) < world
+            m = hist.astype(np.float64)
+            cost = m * (1.0 + np.log2(m + 1.0) / 16.0)
+            load = np.array([cost[own == r].sum() for r in range(world)])
+            assert load.max() - load.min() <= cost.max() + 1e-6
+    assert L.bkid_lpt_owner_table(None, 3, 2, None) != 0 and L.bkid_lpt_owner_table(hist.ctypes.data, nb, 33, own.ctypes.data) != 0
