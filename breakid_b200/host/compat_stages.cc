@@ -16,6 +16,7 @@
 
 #include "../../include/breakid_b200.h"
 #include "../../include/compat/BreakID_stages.h"
+#include "../../include/compat/util_bed.h"
 #include "annotate.h"
 #include "bam_reader.h"
 #include "nibtools.h"
@@ -502,4 +503,33 @@ std::string chromID2ChrName(int refID)
   if (refID == 22) return "chrX";
   if (refID >= 0 && refID < 22) return "chr" + std::to_string(refID + 1);
   return "";
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// src/util_bed.h:22-31 (string helpers)
+// ---------------------------------------------------------------------------------------------------------------
+int find_longest_repeat_substring(const std::string &s)
+{
+  size_t best = 0;
+  for (size_t i = 0; i < s.size();) {
+    size_t j = i + 1;
+    while (j < s.size() && s[j] == s[i]) ++j;
+    if (j - i > best) best = j - i;
+    i = j;
+  }
+  return (int)best;
+}
+
+std::vector<std::string> split_string(const std::string &s, const std::string &delim)
+{
+  std::vector<std::string> out;
+  if (delim.empty()) { out.push_back(s); return out; }
+  for (size_t a = 0;;) {
+    size_t b = s.find(delim, a);
+    std::string piece = s.substr(a, b == std::string::npos ? std::string::npos : b - a);
+    if (!piece.empty()) out.push_back(piece);
+    if (b == std::string::npos) break;
+    a = b + delim.size();
+  }
+  return out;
 }

@@ -13,6 +13,7 @@
 #include <sstream>
 
 #include "BreakID_stages.h"
+#include "util_bed.h"
 
 using namespace std;
 

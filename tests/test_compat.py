@@ -12,7 +12,8 @@ COMPAT_LIB = os.path.join(ROOT, "breakid_b200", "host", "libbreakid_compat.so")
 STAGE_FUNCTIONS = ["get_mean_insert_size", "scan_discordant_pairs", "add_enspan_point_id", "remove_isolated_pairs", "find_cluster_pairs_enspan_ahc",
                    "find_cluster_pairs_enspan_fast", "findClusterBreakPointInfoSaTag", "write_enspan_out", "write_enspan_params", "annotate_cluster_for_sa_tag",
                    "determine_fusion_type_from_drp", "build_pair_array", "add_cluster_id_for_enspan_vec", "init_cluster", "print_root_nodes",
-                   "combine_genome_chr_pos", "get_right_neighbor_sequence_nib", "get_left_neighbor_sequence_nib", "chromID2ChrName"]
+                   "combine_genome_chr_pos", "get_right_neighbor_sequence_nib", "get_left_neighbor_sequence_nib", "chromID2ChrName",
+                   "find_longest_repeat_substring", "split_string"]
 
 
 def test_compat_headers_compile_on_their_own(tmp_path):
@@ -71,6 +72,41 @@ int main(int, char **argv) {
     assert out[2] == seq[4:14]
     assert out[3] == "%d %d" % ((4000000000 + 10) % 2**32, (4000000000 + 500000000 + 3) % 2**32)
     assert out[4] == "chr1 chrX chrY []"
+
+
+def test_string_helpers_of_util_bed(tmp_path):
+    """find_longest_repeat_substring against the reference's own function (oracle/_ref/libbreakid_ref.so) and the oracle's
+    restatement on random base strings; split_string against its definition"""
+    if not os.path.exists(COMPAT_LIB):
+        pytest.skip("libbreakid_compat.so not built")
+    import numpy as np
+    import oracle_py as O
+    rng = np.random.RandomState(3)
+    cases = ["A", "AC", "AAAAAAAAAAAAC", "ACGT", "TTTTTTTTTTTGGGGGGGGGGGGG"] + ["".join(rng.choice(list("ACGTN"), p=[.4, .2, .2, .15, .05], size=int(rng.randint(1, 60)))) for _ in range(200)]
+    src = tmp_path / "t.cc"
+    src.write_text('''#include "util_bed.h"
+#include <cstdio>
+#include <iostream>
+int main() {
+  std::string s;
+  while (std::getline(std::cin, s)) printf("%d\\n", find_longest_repeat_substring(s));
+  for (auto &p : split_string("a,,b,c,", ",")) printf("[%s]", p.c_str());
+  for (auto &p : split_string("x--y", "--")) printf("[%s]", p.c_str());
+  for (auto &p : split_string("whole", "")) printf("[%s]", p.c_str());
+  printf("\\n");
+  return 0; }
+''')
+    exe = tmp_path / "t"
+    host = os.path.dirname(COMPAT_LIB)
+    csrc = os.path.join(ROOT, "breakid_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include", "compat"), str(src), "-o", str(exe), "-L" + host, "-lbreakid_compat",
+                           "-Wl,-rpath," + host, "-Wl,-rpath," + csrc, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    out = subprocess.run([str(exe)], input="\n".join(cases) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    got = [int(x) for x in out[:len(cases)]]
+    assert got == [O.olib().orc_longest_repeat(c.encode()) for c in cases]
+    if O.have_ref():
+        assert got == [O.rlib().ref_longest_repeat(c.encode()) for c in cases]
+    assert out[len(cases)] == "[a][b][c][x][y][whole]"
 
 
 @pytest.mark.gpu
